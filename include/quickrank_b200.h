@@ -1,0 +1,183 @@
+/* quickrank_b200 — C ABI of the B200-native LambdaMART / GBRT hot path.
+ *
+ * This is the drop-in boundary: everything the reference (hpclab/quickrank @ c569a59) does
+ * inside its per-iteration loop and its ensemble-scoring loop is reachable through these entry
+ * points, with plain pointers and sizes only.  The reference has no FFI of its own; its extension
+ * seam is the set of protected virtual hooks of `quickrank::learning::forests::Mart`
+ * (include/learning/forests/mart.h:118-147) plus `LTR_Algorithm::score_dataset`
+ * (include/learning/ltr_algorithm.h:73) and the link symbol `double ranker(float*)`
+ * (src/quickscore.cc:62).  Each function below names the reference interface it replaces
+ * (paths relative to the reference root).  INTEGRATION.md shows the subclass a QuickRank
+ * maintainer would add on top of this header.
+ *
+ * Conventions (same as the reference's hooks): single caller thread per
+ * context, not re-entrant; all pointers are HOST pointers unless the name says `_device`; every
+ * function returns 0 on success and a QR_E* code otherwise, qr_last_error() then holds a message
+ * (the reference prints to std::cerr and exits — the C++ host in host/ does exactly that with the
+ * message).  There is no CPU fallback: without a CUDA device every compute entry fails with
+ * QR_ENODEVICE.
+ */
+#ifndef QUICKRANK_B200_H
+#define QUICKRANK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QR_OK 0
+#define QR_EINVAL 1     /* bad argument */
+#define QR_ENODEVICE 2  /* no CUDA device / CUDA runtime failure at start-up */
+#define QR_ECUDA 3      /* CUDA error during execution */
+#define QR_ELIMIT 4     /* input exceeds a documented limit of this build */
+#define QR_ENOMEM 5
+#define QR_ECOMM 6      /* NCCL / multi-GPU failure */
+
+/* --algo names of the reference (src/learning/ltr_algorithm_factory.cc:67-219) */
+enum qr_algo {
+  QR_ALGO_MART = 0,           /* forests::Mart */
+  QR_ALGO_LAMBDAMART = 1,     /* forests::LambdaMart */
+  QR_ALGO_OBVMART = 2,        /* forests::ObliviousMart */
+  QR_ALGO_OBVLAMBDAMART = 3   /* forests::ObliviousLambdaMart */
+};
+
+/* How per-bin gradient sums are accumulated.
+ *  FAST       64-bit fixed-point integer accumulation in shared memory: order-independent, so the
+ *             histogram (and every split) is deterministic, identical for duplicated columns and
+ *             identical for any number of GPUs.
+ *  REFERENCE  every per-bin sum, prefix sum, squares sum and leaf sum is accumulated in FP64 in the
+ *             reference's own order (ascending document id per bin, then ascending bin:
+ *             src/learning/tree/rtnode_histogram.cc:51-63), which makes split indices bit-exact
+ *             with the reference even where its own rounding breaks a tie.  Parity mode. */
+enum qr_hist_mode { QR_HIST_FAST = 0, QR_HIST_REFERENCE = 1 };
+
+typedef struct {
+  uint32_t algo;             /* enum qr_algo */
+  uint32_t nleaves;          /* --num-leaves (leaf-wise algos) */
+  uint32_t treedepth;        /* --tree-depth (oblivious algos; leaves = 1 << depth) */
+  uint32_t minleafsupport;   /* --min-leaf-support */
+  uint64_t nthresholds;      /* --num-thresholds, 0 = one per distinct value (mart.cc:144-158) */
+  uint64_t ndcg_cutoff;      /* NDCG@k; 0 = no cutoff (metric.h:65-67) */
+  double shrinkage;          /* --shrinkage */
+  uint32_t hist_mode;        /* enum qr_hist_mode */
+  int32_t device;            /* CUDA device ordinal, -1 = current device */
+} qr_params;
+
+/* Flat pre-order (left child first) regression tree; leaves have feature == -1.  Replaces the
+ * RTNode pointer graph (include/learning/tree/rtnode.h:38-168).  Arrays are caller-owned with
+ * room for `capacity` nodes (2*leaves-1 suffices). */
+typedef struct {
+  uint32_t capacity;
+  uint32_t nnodes;
+  uint32_t nleaves;
+  int32_t *feature;         /* RTNode::featureidx (0-based); XML featureid = feature+1 (rt.cc:350-352) */
+  uint32_t *threshold_idx;  /* index into the feature's threshold list (rt.cc:289) */
+  float *threshold;         /* RTNode::threshold (rt.cc:317-318) */
+  int32_t *left;            /* node index of the `<=` child */
+  int32_t *right;
+  double *value;            /* RTNode::avglabel: leaf output for leaves, node mean otherwise */
+  double *deviance;         /* RTNode::deviance (rtnode.h:106) */
+  uint64_t *count;          /* RTNode::nsampleids */
+} qr_flat_tree;
+
+typedef struct qr_ctx qr_ctx;        /* one training run on one GPU (Mart::init .. Mart::clear) */
+typedef struct qr_scorer qr_scorer;  /* one ensemble resident on one GPU */
+
+const char *qr_last_error(void);
+/* Number of visible CUDA devices (0 if none); never fails. */
+int qr_device_count(void);
+
+/* ---- training ------------------------------------------------------------------------------ */
+
+/* Replaces Mart::init / LambdaMart::init (mart.cc:117-176, lambdamart.cc:35-39) together with
+ * RTRootHistogram::RTRootHistogram (rtnode_histogram.cc:227-253): per-feature argsort, threshold
+ * lists, bin map; uploads labels/query offsets; zeroes scores.  `feat_colmajor` is
+ * VerticalDataset::data_ (include/data/vertical_dataset.h:66): feat[f*N + doc]. */
+int qr_ctx_create(const float *feat_colmajor, size_t N, size_t F, const float *labels,
+                  const uint64_t *qoffsets, size_t Q, const qr_params *params, qr_ctx **out);
+/* Same, from the row-major layout of data::Dataset (include/data/dataset.h:65-66); the transpose
+ * done by VerticalDataset's constructor (vertical_dataset.cc:29-70) happens on the device. */
+int qr_ctx_create_rowmajor(const float *feat_rowmajor, size_t N, size_t F, const float *labels,
+                           const uint64_t *qoffsets, size_t Q, const qr_params *params,
+                           qr_ctx **out);
+/* Replaces Mart::clear (mart.cc:178-206). */
+int qr_ctx_destroy(qr_ctx *ctx);
+
+/* thresholds_[f] / thresholds_size_[f] (mart.h:150-151); pointer valid until qr_ctx_destroy. */
+int qr_get_thresholds(qr_ctx *ctx, size_t f, const float **thresholds, size_t *n);
+
+/* Replaces LambdaMart::compute_pseudoresponses (lambdamart.cc:62-152) or, for the MART algos,
+ * Mart::compute_pseudoresponses (mart.cc:418-431).  Result stays on the device. */
+int qr_compute_pseudoresponses(qr_ctx *ctx);
+
+/* Replaces hist_->update (mart.cc:335, rtnode_histogram.cc:172-204) + fit_regressor_on_gradient
+ * (mart.cc:433-445 / lambdamart.cc:47-60 / obliviousmart.cc, obliviouslambdamart.cc:55-66):
+ * RegressionTree::fit or ObliviousRT::fit followed by update_output.  `out` may be NULL. */
+int qr_fit_tree(qr_ctx *ctx, qr_flat_tree *out);
+
+/* Replaces Mart::update_modelscores(VerticalDataset...) (mart.cc:459-468) for the tree just
+ * fitted: scores[i] += weight * leaf(doc_i). */
+int qr_update_modelscores(qr_ctx *ctx, double weight);
+
+/* scores[i] += weight * tree(doc_i) for an arbitrary tree of this context's binning (DART's
+ * add/subtract passes, dart.cc:634-687; weight carries the sign). */
+int qr_apply_tree(qr_ctx *ctx, const qr_flat_tree *tree, double weight);
+
+/* Replaces Metric::evaluate_dataset(VerticalDataset, scores) for Ndcg (metric.h:93-106,
+ * ndcg.cc:49-58) on the training scores held by the context. */
+int qr_evaluate(qr_ctx *ctx, double *metric);
+
+/* One whole iteration of Mart::learn's loop body (mart.cc:331-347) without returning to the
+ * host in between; tree and metric may be NULL. */
+int qr_boost_iteration(qr_ctx *ctx, qr_flat_tree *tree, double *metric);
+
+/* parity taps (device <-> host copies of the state arrays named in mart.h:153-160) */
+int qr_get_scores(qr_ctx *ctx, double *scores);
+int qr_set_scores(qr_ctx *ctx, const double *scores);
+int qr_get_pseudoresponses(qr_ctx *ctx, double *lambdas, double *weights /* may be NULL */);
+int qr_set_pseudoresponses(qr_ctx *ctx, const double *lambdas, const double *weights);
+int qr_get_leaf_assignment(qr_ctx *ctx, uint32_t *leaf_of_doc); /* DFS leaf index per doc */
+int qr_get_bins(qr_ctx *ctx, size_t f, uint32_t *bins);         /* stmap[f][doc] */
+int qr_get_ranking(qr_ctx *ctx, uint32_t *position_of_rank);    /* per query, as RankedResults::pos_of_rank */
+/* measured per-tree quantities for the roofline formula:
+ * rho = sum over splits of n_left / N, sigma = sum over splits of n_node / N */
+int qr_last_tree_stats(qr_ctx *ctx, double *rho, double *sigma, uint32_t *nsplits);
+/* number of kernel launches issued by this context so far */
+uint64_t qr_launch_count(qr_ctx *ctx);
+/* device time (ms, CUDA events on the context's stream) spent per phase since the last reset:
+ * [0] pseudo-responses, [1] histogram kernels, [2] split scan, [3] partition, [4] leaf fit +
+ * score update, [5] ranking/NDCG; also returns per-phase launch counts (either may be NULL). */
+int qr_phase_times(qr_ctx *ctx, double ms[6], uint64_t launches[6], int reset);
+int qr_set_profiling(qr_ctx *ctx, int enabled);
+
+/* ---- multi-GPU (one process per GPU; documents sharded by query) ------ */
+#define QR_COMM_ID_BYTES 128
+/* rank 0 creates the id, the host broadcasts it by any means (torch.distributed, MPI, a file). */
+int qr_comm_unique_id(unsigned char id[QR_COMM_ID_BYTES]);
+/* Joins the context to a world of `world` contexts; afterwards histograms, leaf sums and the
+ * metric are all-reduced over NCCL so that every rank grows the identical tree. */
+int qr_ctx_comm_init(qr_ctx *ctx, const unsigned char id[QR_COMM_ID_BYTES], int rank, int world);
+
+/* ---- scoring ------------------------------------------------------------------------------- */
+
+/* Uploads an ensemble (replaces building Ensemble from XML, ensemble.cc / mart.cc:37-89). */
+int qr_scorer_create(const qr_flat_tree *trees, const double *weights, size_t ntrees, size_t F,
+                     int device, qr_scorer **out);
+int qr_scorer_destroy(qr_scorer *s);
+/* Replaces LTR_Algorithm::score_dataset (ltr_algorithm.cc:44-52): scores[i] = sum_t w_t*leaf_t(doc_i)
+ * for row-major documents; host buffers, copies included. */
+int qr_score_dataset(qr_scorer *s, const float *docs_rowmajor, size_t N, size_t F, double *scores);
+/* Same with device-resident documents and scores (no copies). */
+int qr_score_dataset_device(qr_scorer *s, const float *docs_rowmajor_device, size_t N, size_t F,
+                            double *scores_device);
+/* Waits for the scorer's stream (qr_score_dataset_device is asynchronous). */
+int qr_scorer_sync(qr_scorer *s);
+/* Replaces `double ranker(float *v)` (src/scoring/ranker.cc:23-25, called by quickscore.cc:103). */
+int qr_score_document(qr_scorer *s, const float *doc, size_t F, double *score);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

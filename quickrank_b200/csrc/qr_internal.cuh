@@ -1,0 +1,131 @@
+// quickrank_b200 — internal declarations shared by the .cu translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/quickrank_b200.h"
+
+namespace qr {
+
+void set_error(const char *fmt, ...);
+
+#define QR_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      qr::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr,                  \
+                    cudaGetErrorString(_e));                                            \
+      return QR_ECUDA;                                                                  \
+    }                                                                                   \
+  } while (0)
+
+#define QR_TRY(expr)            \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != QR_OK) return _rc; \
+  } while (0)
+
+constexpr int kPanelBytes = 16;   // one 128-bit load = one document's bins for one panel
+constexpr int kNumPhases = 6;
+enum Phase { PH_PSEUDO = 0, PH_HIST = 1, PH_SCAN = 2, PH_PARTITION = 3, PH_LEAF = 4, PH_RANK = 5 };
+
+// Best split of one node, written by the scan kernels and read back by the host
+// (replaces the tail of RegressionTree::split, rt.cc:297-318 of the reference).
+struct SplitResult {
+  double score;       // best lsum^2/lcnt + rsum^2/rcnt, -1 if none
+  double sum;         // node sum of pseudo-responses (feature 0, last bin)
+  double squares;     // squares_sum_
+  double deviance;    // squares - sum^2/n
+  uint64_t n;         // node size (feature 0, last bin)
+  uint64_t lcount;    // left size at the best split
+  uint32_t feature;
+  uint32_t threshold_idx;
+  uint32_t valid;
+  uint32_t pad;
+};
+
+struct HostNode {
+  uint32_t lo = 0, n = 0;   // segment [lo, lo+n) of the id buffer `buf`
+  int buf = 0;
+  int hist = -1;            // histogram slot, -1 once released
+  int left = -1, right = -1;
+  SplitResult res{};
+  double value = 0.0;       // leaf output
+  bool is_leaf() const { return left < 0; }
+};
+
+struct Comm;  // NCCL plumbing (qr_comm.cu)
+
+}  // namespace qr
+
+struct qr_ctx {
+  qr_params p{};
+  int device = 0;
+  size_t N = 0, F = 0, Q = 0;
+  size_t cutoff = 0;             // SIZE_MAX when "no cutoff"
+  bool lambda = false, oblivious = false, exact = false;
+  cudaStream_t stream = nullptr;
+
+  // binning (host copies for XML / split thresholds)
+  std::vector<std::vector<float>> thr;
+  std::vector<uint32_t> thr_off;  // prefix over features, size F+1
+  uint32_t ncells = 0;
+  uint32_t max_thr = 0;
+  int bin_bytes = 1;              // 1: u8 bins, 2: u16 bins
+  int fpp = 16;                   // features per 16-byte panel
+  uint32_t npanels = 0;
+  uint32_t max_panel_cells = 0;
+
+  // device state
+  uint4 *d_panels = nullptr;      // [npanels][N]
+  uint32_t *d_thr_off = nullptr;  // [F+1]
+  float *d_labels = nullptr;      // [N]
+  double *d_gain = nullptr;       // [N] pow(2, label)
+  uint32_t *d_qoff = nullptr;     // [Q+1]
+  double *d_idcg = nullptr;       // [Q]
+  double *d_invlg = nullptr;      // [maxlen] 1/log2(i+2)
+  double *d_lg = nullptr;         // [maxlen] log2((float)i+2)
+  double *d_scores = nullptr, *d_lambda = nullptr, *d_weight = nullptr;  // [N]
+  long long *d_lamq = nullptr;    // [N] fixed-point pseudo-responses (FAST mode)
+  unsigned long long *d_maxabs = nullptr;  // bits of max |lambda|
+  int *d_qexp = nullptr;          // fixed-point exponent chosen for this tree
+  uint32_t *d_rankpos = nullptr;  // [N] position (within its query) of the doc at each rank
+  double *d_qndcg = nullptr;      // [Q]
+  double *d_metric = nullptr;     // [1]
+  uint32_t *d_ids[2] = {nullptr, nullptr};  // [N] node document lists (ping-pong)
+  uint32_t *d_leaf_of_doc = nullptr;        // [N]
+  uint32_t *d_blockcnt = nullptr;           // partition scratch
+  double *d_partials = nullptr;             // reduction scratch
+  unsigned long long *d_hist_sum = nullptr; // [nslots][ncells] int64 (FAST) or double (REFERENCE)
+  uint32_t *d_hist_cnt = nullptr;           // [nslots][ncells]
+  int nslots = 0;
+  std::vector<int> free_slots;
+  double *d_fbest_score = nullptr;          // [2][F]
+  uint32_t *d_fbest_t = nullptr;            // [2][F]
+  qr::SplitResult *d_res = nullptr;         // [2]
+  qr::SplitResult *h_res = nullptr;         // pinned [2]
+  double *d_leafval = nullptr;              // [maxleaves]
+  double *h_leafval = nullptr;              // pinned
+  double *d_obv_scores = nullptr;           // [ncells] oblivious level sums
+  uint32_t maxlen = 0;                      // longest query
+
+  bool ranking_valid = false;  // d_rankpos/d_qndcg match d_scores
+  bool has_tree = false;
+  std::vector<qr::HostNode> nodes;  // last fitted tree
+  std::vector<int> leaves;          // node ids in DFS order
+  double rho = 0, sigma = 0;
+  uint32_t nsplits = 0;
+
+  uint64_t launches = 0;
+  bool profiling = false;
+  double phase_ms[qr::kNumPhases] = {0};
+  uint64_t phase_launches[qr::kNumPhases] = {0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+  qr::Comm *comm = nullptr;
+  size_t N_global = 0, Q_global = 0;
+};

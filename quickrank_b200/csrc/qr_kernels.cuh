@@ -1,0 +1,1053 @@
+// quickrank_b200 — device kernels of the training hot path (sm_100a).
+//
+// Every kernel names the reference loop it replaces (paths relative to the reference root,
+// hpclab/quickrank @ c569a59).  Compiled with -fmad=false: every fused multiply-add below is an
+// explicit fma() placed where the reference's Release build (g++ 13.3, FMA target) fuses one, so
+// results can be compared bit for bit with the oracle (see oracle/qr_oracle.c header).
+#pragma once
+
+#include <cfloat>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qr_internal.cuh"
+
+namespace qr {
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+
+// ------------------------------------------------------------------------------------------
+// Bin access.  Panels: d_panels[p * N + doc] is one uint4 holding the bins of document `doc` for
+// the FPP = 16 / sizeof(BinT) consecutive features of panel p ("feature columns ... laid out for
+// coalesced 128-bit loads": consecutive lanes read consecutive documents of one panel).
+// ------------------------------------------------------------------------------------------
+template <typename BinT>
+__device__ __forceinline__ uint32_t load_bin(const uint4 *panels, size_t N, uint32_t f, uint32_t doc) {
+  constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
+  const BinT *row = reinterpret_cast<const BinT *>(panels + (size_t) (f / FPP) * N + doc);
+  return row[f % FPP];
+}
+
+// rotate the 16 bytes of v right by rb bytes: result byte k = input byte (k + rb) & 15
+__device__ __forceinline__ uint4 rotate_bytes(uint4 v, uint32_t rb) {
+  if (rb & 4u) { uint32_t t = v.x; v.x = v.y; v.y = v.z; v.z = v.w; v.w = t; }
+  if (rb & 8u) { uint32_t t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
+  const uint32_t sel = 0x3210u + 0x1111u * (rb & 3u);
+  uint4 r;
+  r.x = __byte_perm(v.x, v.y, sel);
+  r.y = __byte_perm(v.y, v.z, sel);
+  r.z = __byte_perm(v.z, v.w, sel);
+  r.w = __byte_perm(v.w, v.x, sel);
+  return r;
+}
+
+template <typename BinT>
+__device__ __forceinline__ uint32_t extract_bin(const uint4 &v, int j) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};  // j is a compile-time constant after unrolling
+  if (sizeof(BinT) == 1) return (w[j >> 2] >> ((j & 3) * 8)) & 0xffu;
+  return (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
+}
+
+// ------------------------------------------------------------------------------------------
+// Init: threshold lists and bin map (Mart::init mart.cc:117-176, RTRootHistogram
+// rtnode_histogram.cc:227-253).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t flip_float_bits(uint32_t x) {  // radix.cc:28-30
+  return x ^ ((uint32_t) (-(int32_t) (x >> 31)) | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t unflip_float_bits(uint32_t x) {  // radix.cc:31-33
+  return x ^ (((x >> 31) - 1u) | 0x80000000u);
+}
+
+__global__ void flip_keys_kernel(const float *x, uint32_t *keys, size_t n, int *bad) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = x[i];
+  if (!(fabsf(v) <= FLT_MAX)) *bad = 1;  // NaN or +-inf: the reference's stmap is undefined for them
+  keys[i] = flip_float_bits(__float_as_uint(v));
+}
+
+// flag[i] = 1 where a new distinct value starts: the reference keeps u[k] and appends v when
+// u[k] < v (mart.cc:148-151); on an ascending list that is v[i-1] < v[i].
+__global__ void distinct_flags_kernel(const uint32_t *sorted_keys, float *vals, uint8_t *flags, size_t n) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = __uint_as_float(unflip_float_bits(sorted_keys[i]));
+  vals[i] = v;
+  flags[i] = (i == 0) ? 1 : (__uint_as_float(unflip_float_bits(sorted_keys[i - 1])) < v);
+}
+
+__global__ void transpose_kernel(const float *rowmajor, float *colmajor, size_t N, size_t F) {
+  __shared__ float tile[32][33];
+  size_t f0 = (size_t) blockIdx.x * 32, d0 = (size_t) blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    size_t d = d0 + r, f = f0 + threadIdx.x;
+    if (d < N && f < F) tile[r][threadIdx.x] = rowmajor[d * F + f];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    size_t f = f0 + r, d = d0 + threadIdx.x;
+    if (d < N && f < F) colmajor[f * N + d] = tile[threadIdx.x][r];
+  }
+}
+
+// bin(f, doc) = smallest t with x <= thr[f][t] (rtnode_histogram.cc:241-251).  One thread builds
+// one document's 16-byte panel row.
+template <typename BinT>
+__global__ void binning_kernel(const float *colmajor, size_t N, uint32_t F, const float *thr,
+                               const uint32_t *thr_off, uint4 *panels, uint32_t npanels) {
+  constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
+  size_t d = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t p = blockIdx.y;
+  if (d >= N || p >= npanels) return;
+  union { uint4 v; BinT b[FPP]; } row;
+  row.v = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (uint32_t j = 0; j < FPP; ++j) {
+    uint32_t f = p * FPP + j;
+    if (f < F) {
+      float x = colmajor[(size_t) f * N + d];
+      const float *t = thr + thr_off[f];
+      uint32_t lo = 0, hi = thr_off[f + 1] - thr_off[f] - 1;  // last threshold is FLT_MAX >= x
+      while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (x <= t[mid]) hi = mid; else lo = mid + 1;
+      }
+      row.b[j] = (BinT) lo;
+    }
+  }
+  panels[(size_t) p * N + d] = row.v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-query ranking: std::sort(idx, comp = score[i] > score[j]) with libstdc++'s introsort,
+// reproduced move for move so that tied scores land where the reference puts them
+// (QueryResults::indexing_of_sorted_labels, queryresults.cc:37-53; SURVEY.md section 7.1 "Sort").
+// One warp per query.  Queries whose scores are pairwise distinct have a unique sorted order and
+// are ranked in parallel by counting; only queries with ties take the sequential replica.
+// Also evaluates DCG/NDCG of the query (dcg.cc:33-57, ndcg.cc:49-58).
+// ------------------------------------------------------------------------------------------
+struct SortView {
+  const double *s;
+  uint32_t *idx;
+  __device__ __forceinline__ bool comp(uint32_t a, uint32_t b) const { return s[a] > s[b]; }
+};
+
+__device__ void sv_adjust_heap(const SortView &v, int first, int hole, int len, uint32_t value) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (v.comp(v.idx[first + child], v.idx[first + child - 1])) child--;
+    v.idx[first + hole] = v.idx[first + child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    v.idx[first + hole] = v.idx[first + child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > top && v.comp(v.idx[first + parent], value)) {
+    v.idx[first + hole] = v.idx[first + parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  v.idx[first + hole] = value;
+}
+
+__device__ void sv_heap_sort(const SortView &v, int first, int last) {
+  int len = last - first;
+  if (len >= 2) {
+    int parent = (len - 2) / 2;
+    for (;;) {
+      uint32_t val = v.idx[first + parent];
+      sv_adjust_heap(v, first, parent, len, val);
+      if (parent == 0) break;
+      parent--;
+    }
+  }
+  while (last - first > 1) {
+    --last;
+    uint32_t val = v.idx[last];
+    v.idx[last] = v.idx[first];
+    sv_adjust_heap(v, first, 0, last - first, val);
+  }
+}
+
+__device__ void sv_unguarded_linear_insert(const SortView &v, int last) {
+  uint32_t val = v.idx[last];
+  int next = last - 1;
+  while (v.comp(val, v.idx[next])) {
+    v.idx[last] = v.idx[next];
+    last = next;
+    --next;
+  }
+  v.idx[last] = val;
+}
+
+__device__ void sv_insertion_sort(const SortView &v, int first, int last) {
+  if (first == last) return;
+  for (int i = first + 1; i != last; ++i) {
+    if (v.comp(v.idx[i], v.idx[first])) {
+      uint32_t val = v.idx[i];
+      for (int k = i; k > first; --k) v.idx[k] = v.idx[k - 1];
+      v.idx[first] = val;
+    } else {
+      sv_unguarded_linear_insert(v, i);
+    }
+  }
+}
+
+// sequential; executed by one lane
+__device__ void sv_std_sort(const SortView &v, int n) {
+  if (n <= 0) return;
+  int lg = 0;
+  for (int t = n; t > 1; t >>= 1) ++lg;
+  // __introsort_loop with an explicit stack (sub-ranges are disjoint, so their order is free)
+  int st_first[64], st_last[64], st_depth[64];
+  int sp = 0;
+  st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * lg; sp = 1;
+  while (sp > 0) {
+    --sp;
+    int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+    while (last - first > 16) {
+      if (depth == 0) { sv_heap_sort(v, first, last); break; }
+      --depth;
+      int mid = first + (last - first) / 2;
+      {  // __move_median_to_first(first, first+1, mid, last-1)
+        int a = first + 1, b = mid, c = last - 1, pick;
+        uint32_t va = v.idx[a], vb = v.idx[b], vc = v.idx[c];
+        if (v.comp(va, vb)) {
+          if (v.comp(vb, vc)) pick = b;
+          else if (v.comp(va, vc)) pick = c;
+          else pick = a;
+        } else if (v.comp(va, vc)) pick = a;
+        else if (v.comp(vb, vc)) pick = c;
+        else pick = b;
+        uint32_t t = v.idx[first]; v.idx[first] = v.idx[pick]; v.idx[pick] = t;
+      }
+      int lo = first + 1, hi = last;
+      const uint32_t pivot = v.idx[first];
+      for (;;) {  // __unguarded_partition(first+1, last, first)
+        while (v.comp(v.idx[lo], pivot)) ++lo;
+        --hi;
+        while (v.comp(pivot, v.idx[hi])) --hi;
+        if (!(lo < hi)) break;
+        uint32_t t = v.idx[lo]; v.idx[lo] = v.idx[hi]; v.idx[hi] = t;
+        ++lo;
+      }
+      if (sp < 64) { st_first[sp] = lo; st_last[sp] = last; st_depth[sp] = depth; ++sp; }
+      last = lo;
+    }
+  }
+  if (n > 16) {
+    sv_insertion_sort(v, 0, 16);
+    for (int i = 16; i != n; ++i) sv_unguarded_linear_insert(v, i);
+  } else {
+    sv_insertion_sort(v, 0, n);
+  }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+rank_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
+            const double *__restrict__ gain, const uint32_t *__restrict__ qoff,
+            const double *__restrict__ idcg, const double *__restrict__ lg, uint32_t Q,
+            uint32_t maxlen, size_t cutoff, uint32_t *__restrict__ rankpos,
+            double *__restrict__ qndcg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t q = blockIdx.x * WARPS + warp;
+  if (q >= Q) return;
+  double *s = reinterpret_cast<double *>(smem_raw) + (size_t) warp * maxlen;
+  uint32_t *idx = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t) WARPS * maxlen) +
+                  (size_t) warp * maxlen;
+  const uint32_t off = qoff[q], n = qoff[q + 1] - off;
+  for (uint32_t i = lane; i < n; i += 32) s[i] = scores[off + i];
+  __syncwarp();
+  // parallel rank-by-counting, valid when no two scores are equal
+  bool tie = false;
+  for (uint32_t i = lane; i < n; i += 32) {
+    const double si = s[i];
+    uint32_t gt = 0, eq = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+      const double sj = s[j];
+      gt += sj > si;
+      eq += sj == si;
+    }
+    if (eq > 1 || si != si) tie = true;
+    else idx[gt] = i;
+  }
+  tie = __any_sync(0xffffffffu, tie);
+  if (tie) {
+    __syncwarp();
+    for (uint32_t i = lane; i < n; i += 32) idx[i] = i;  // queryresults.cc:50-51
+    __syncwarp();
+    if (lane == 0) {
+      SortView v{s, idx};
+      sv_std_sort(v, (int) n);
+    }
+  }
+  __syncwarp();
+  for (uint32_t i = lane; i < n; i += 32) rankpos[off + i] = idx[i];
+  if (lane == 0) {
+    double r = 0.0;
+    if (n > 0) {
+      const double id = idcg[q];
+      if (id > 0) {                                   // ndcg.cc:54-57
+        const uint32_t size = cutoff < n ? (uint32_t) cutoff : n;
+        double dcg = 0.0;
+        for (uint32_t i = 0; i < size; ++i)           // dcg.cc:36-37
+          dcg += (gain[off + idx[i]] - 1.0) / lg[i];
+        r = dcg / id;
+      }
+    }
+    qndcg[q] = r;
+  }
+}
+
+// mean over queries (metric.h:96-105).  REFERENCE: sequential sum in query order.
+__global__ void ndcg_mean_kernel(const double *qndcg, uint32_t Q, uint32_t Qdiv, bool exact, double *out) {
+  __shared__ double part[1024];
+  if (exact) {
+    // one warp, values fetched 32 at a time, summed in order by every lane
+    if (threadIdx.x >= 32) return;
+    double acc = 0.0;
+    for (uint32_t base = 0; base < Q; base += 32) {
+      uint32_t i = base + lane_id();
+      double v = i < Q ? qndcg[i] : 0.0;
+      uint32_t cnt = min(32u, Q - base);
+      for (uint32_t k = 0; k < cnt; ++k) acc += __shfl_sync(0xffffffffu, v, k);
+    }
+    if (threadIdx.x == 0) out[0] = Qdiv ? acc / (double) Qdiv : 0.0;
+    return;
+  }
+  // deterministic: contiguous chunk per thread, then a fixed-shape tree
+  uint32_t per = (Q + blockDim.x - 1) / blockDim.x;
+  uint32_t b = threadIdx.x * per, e = min(Q, b + per);
+  double acc = 0.0;
+  for (uint32_t i = b; i < e; ++i) acc += qndcg[i];
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t st = blockDim.x >> 1; st > 0; st >>= 1) {
+    if (threadIdx.x < st) part[threadIdx.x] += part[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = Qdiv ? part[0] / (double) Qdiv : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// LambdaMART pseudo-responses (LambdaMart::compute_pseudoresponses, lambdamart.cc:62-152, with
+// Ndcg::jacobian, ndcg.cc:60-92, evaluated on the fly instead of materialised).
+//
+// One warp per query.  All visited pairs have one member among the top c = min(cutoff, n) ranks
+// ("heavy" ranks).  Pair terms are computed once per sweep by the lane that owns the other member
+// and handed to the heavy rank's lane through shared memory; every document then adds its terms
+// in exactly the order the reference's j/k loops produce them:
+//   heavy X:  [j<X, label_j>label_X: -]  [k=0..n-1, label_X>label_k: +]  [j>X, label_j>label_X: -]
+//   light b:  [a<c, label_a>label_b: -]  [a<c, label_b>label_a: +]
+// ------------------------------------------------------------------------------------------
+constexpr int kHG = 16;           // heavy ranks handled per sweep
+constexpr int kStageStride = kHG + 1;  // double2 units; +1 avoids bank conflicts
+
+struct PairTerm { double rho, d; };
+
+__device__ __forceinline__ PairTerm pair_term(const double *s, const double *g, const double *invlg,
+                                              double idcg, uint32_t c, uint32_t hi, uint32_t lo) {
+  const uint32_t i = hi < lo ? hi : lo, j = hi < lo ? lo : hi;
+  const double disc = (j < c) ? (invlg[j] - invlg[i]) : (-invlg[i]);       // ndcg.cc:76-86
+  const double jac = disc * (g[i] - g[j]) / idcg;
+  PairTerm t;
+  t.d = fabs(jac);                                                          // lambdamart.cc:130
+  t.rho = 1.0 / (1.0 + exp(s[hi] - s[lo]));                                 // lambdamart.cc:132-134
+  return t;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+lambda_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
+              const double *__restrict__ gain, const uint32_t *__restrict__ qoff,
+              const double *__restrict__ idcg_q, const double *__restrict__ invlg,
+              const uint32_t *__restrict__ rankpos, uint32_t Q, uint32_t maxlen, size_t cutoff,
+              double *lam, double *wgt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t q = blockIdx.x * WARPS + warp;
+  if (q >= Q) return;
+  // per-warp carve-up: s[maxlen] g[maxlen] (double) | stage[32][kStageStride] (double2) | lab[maxlen] pos[maxlen]
+  const size_t per_warp = (size_t) maxlen * 24 + (size_t) 32 * kStageStride * 16;
+  unsigned char *base = smem_raw + (size_t) warp * per_warp;
+  double *s = reinterpret_cast<double *>(base);
+  double *g = s + maxlen;
+  double2 *stage = reinterpret_cast<double2 *>(g + maxlen);
+  float *lab = reinterpret_cast<float *>(stage + 32 * kStageStride);
+  uint32_t *pos = reinterpret_cast<uint32_t *>(lab + maxlen);
+
+  const uint32_t off = qoff[q], n = qoff[q + 1] - off;
+  for (uint32_t r = lane; r < n; r += 32) {
+    const uint32_t p = rankpos[off + r], d = off + p;
+    s[r] = scores[d];
+    g[r] = gain[d];
+    lab[r] = labels[d];
+    pos[r] = d;
+    lam[d] = 0.0;                                   // lambdamart.cc:77-78
+    wgt[d] = 0.0;
+  }
+  __syncwarp();
+  if (n == 0) return;
+  const double idcg = idcg_q[q];
+  if (!(idcg > 0.0)) return;                        // ndcg.cc:69-70: jacobian stays zero
+  const uint32_t c = cutoff < n ? (uint32_t) cutoff : n;
+
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    for (uint32_t h0 = 0; h0 < c; h0 += kHG) {
+      const uint32_t hc = min((uint32_t) kHG, c - h0);
+      const bool heavy_lane = lane < hc;
+      const uint32_t X = h0 + lane;                 // this lane's heavy rank (if heavy_lane)
+      const float labX = heavy_lane ? lab[X] : 0.f;
+      double aL = 0.0, aW = 0.0;
+      if (sweep == 1 && heavy_lane) { aL = lam[pos[X]]; aW = wgt[pos[X]]; }
+
+      if (sweep == 0) {
+        // S1: b < X with label_b > label_X  ->  p[X] -= lambda(b, X)
+        for (uint32_t cb = 0; cb < h0 + hc; cb += 32) {
+          const uint32_t b = cb + lane;
+          uint32_t mymask = 0;
+#pragma unroll
+          for (int x = 0; x < kHG; ++x) {
+            const uint32_t Xx = h0 + x;
+            bool app = (x < (int) hc) && b < Xx && b < n && lab[b] > lab[Xx];
+            if (app) {
+              PairTerm t = pair_term(s, g, invlg, idcg, c, b, Xx);
+              stage[lane * kStageStride + x] = make_double2(t.rho, t.d);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, app);
+            if ((int) lane == x) mymask = m;
+          }
+          __syncwarp();
+          while (mymask) {
+            const int bi = __ffs(mymask) - 1;
+            mymask &= mymask - 1;
+            const double2 t = stage[bi * kStageStride + lane];
+            aL = fma(-t.x, t.y, aL);                             // lambdamart.cc:138
+            aW = fma((1.0 - t.x) * t.x, t.y, aW);                // lambdamart.cc:140
+          }
+          __syncwarp();
+        }
+      }
+      // S2 (sweep 0): all b with label_X > label_b  ->  p[X] += lambda(X, b); light b: p[b] -= ...
+      // S3 (sweep 1): b > X with label_b > label_X  ->  p[X] -= lambda(b, X); light b: p[b] += ...
+      const uint32_t cb0 = sweep == 0 ? 0u : (h0 & ~31u);
+      for (uint32_t cb = cb0; cb < n; cb += 32) {
+        const uint32_t b = cb + lane;
+        const bool bvalid = b < n;
+        const bool light = bvalid && b >= c;
+        const float labb = bvalid ? lab[b] : 0.f;
+        double bL = 0.0, bW = 0.0;
+        if (light) { bL = lam[pos[b]]; bW = wgt[pos[b]]; }
+        uint32_t mymask = 0;
+#pragma unroll
+        for (int x = 0; x < kHG; ++x) {
+          const uint32_t Xx = h0 + x;
+          bool app = false;
+          if (x < (int) hc && bvalid && b != Xx) {
+            const float lx = lab[Xx];
+            app = sweep == 0 ? (lx > labb) : (b > Xx && labb > lx);
+          }
+          if (app) {
+            PairTerm t = sweep == 0 ? pair_term(s, g, invlg, idcg, c, Xx, b)
+                                    : pair_term(s, g, invlg, idcg, c, b, Xx);
+            stage[lane * kStageStride + x] = make_double2(t.rho, t.d);
+            if (light) {
+              // lambdamart.cc:137-140 seen from the non-heavy member of the pair
+              bL = fma(sweep == 0 ? -t.rho : t.rho, t.d, bL);
+              bW = fma((1.0 - t.rho) * t.rho, t.d, bW);
+            }
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, app);
+          if ((int) lane == x) mymask = m;
+        }
+        if (light) { lam[pos[b]] = bL; wgt[pos[b]] = bW; }
+        __syncwarp();
+        while (mymask) {
+          const int bi = __ffs(mymask) - 1;
+          mymask &= mymask - 1;
+          const double2 t = stage[bi * kStageStride + lane];
+          aL = fma(sweep == 0 ? t.x : -t.x, t.y, aL);
+          aW = fma((1.0 - t.x) * t.x, t.y, aW);
+        }
+        __syncwarp();
+      }
+      if (heavy_lane) { lam[pos[X]] = aL; wgt[pos[X]] = aW; }
+      __syncwarp();
+      (void) labX;
+    }
+  }
+}
+
+// MART residuals (Mart::compute_pseudoresponses, mart.cc:418-431)
+__global__ void mart_pseudo_kernel(const double *scores, const float *labels, size_t N, double *lam) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) lam[i] = (double) labels[i] - scores[i];
+}
+
+// ---- fixed-point view of the pseudo-responses (FAST histogram mode) -----------------------
+__global__ void maxabs_kernel(const double *lam, size_t N, unsigned long long *maxbits) {
+  double m = 0.0;
+  for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (size_t) gridDim.x * blockDim.x)
+    m = fmax(m, fabs(lam[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane_id() == 0 && m > 0.0) atomicMax(maxbits, (unsigned long long) __double_as_longlong(m));
+}
+
+// qexp = 2^k scale such that N_total * max|q| < 2^62
+__global__ void choose_scale_kernel(const unsigned long long *maxbits, int log2n_ceil, int *qexp) {
+  double m = __longlong_as_double((long long) *maxbits);
+  int e = 0;
+  if (m > 0.0) frexp(m, &e);        // m = f * 2^e, f in [0.5, 1)
+  *qexp = (62 - log2n_ceil) - e;    // |lam * 2^qexp| < 2^(62 - log2n)
+}
+
+__global__ void quantize_kernel(const double *lam, size_t N, const int *qexp, long long *lamq) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) lamq[i] = __double2ll_rn(ldexp(lam[i], *qexp));
+}
+
+// ------------------------------------------------------------------------------------------
+// Histograms.  cell(f, t) = thr_off[f] + t.
+// FAST: RTNodeHistogram::update / RTNodeHistogram(parent, sampleids, ...) scatter loops
+// (rtnode_histogram.cc:51-58, 183-191) as 64-bit fixed-point atomics staged in shared memory,
+// one block per (panel, document slice); lanes walk the 16 features of a row in rotated order so
+// that the 32 lanes of a warp hit different features' bins.
+// ------------------------------------------------------------------------------------------
+template <typename BinT, bool DENSE, bool SMEM>
+__global__ void __launch_bounds__(256)
+hist_fast_kernel(const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ ids,
+                 uint32_t lo, uint32_t n, const long long *__restrict__ lamq,
+                 const uint32_t *__restrict__ thr_off, uint32_t F, unsigned long long *gsum,
+                 uint32_t *gcnt, uint32_t docs_per_block) {
+  constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t s_base[FPP];
+  const uint32_t p = blockIdx.y;
+  const uint32_t f0 = p * FPP;
+  const uint32_t nf = min(FPP, F - f0);
+  const uint32_t cell0 = thr_off[f0];
+  const uint32_t cells = thr_off[f0 + nf] - cell0;
+  unsigned long long *s_sum = reinterpret_cast<unsigned long long *>(smem_raw);
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_sum + (SMEM ? cells : 0));
+  if (threadIdx.x < FPP)
+    s_base[threadIdx.x] = threadIdx.x < nf ? thr_off[f0 + threadIdx.x] - cell0 : 0u;
+  if (SMEM) {
+    for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) { s_sum[i] = 0ull; s_cnt[i] = 0u; }
+  }
+  __syncthreads();
+  const uint32_t begin = blockIdx.x * docs_per_block;
+  const uint32_t end = min(n, begin + docs_per_block);
+  const uint32_t rot = lane_id() & (FPP - 1);
+  const uint4 *prow = panels + (size_t) p * N;
+  unsigned long long *sum_base = SMEM ? s_sum : gsum + cell0;
+  uint32_t *cnt_base = SMEM ? s_cnt : gcnt + cell0;
+  for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
+    const uint32_t d = DENSE ? lo + i : ids[lo + i];
+    const uint4 row = rotate_bytes(prow[d], rot * (uint32_t) sizeof(BinT));
+    const unsigned long long qv = (unsigned long long) lamq[d];
+#pragma unroll
+    for (int j = 0; j < (int) FPP; ++j) {
+      const uint32_t slot = (j + rot) & (FPP - 1);
+      if (slot < nf) {
+        const uint32_t cell = s_base[slot] + extract_bin<BinT>(row, j);
+        atomicAdd(sum_base + cell, qv);
+        atomicAdd(cnt_base + cell, 1u);
+      }
+    }
+  }
+  if (SMEM) {
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) {
+      const uint32_t cn = s_cnt[i];
+      if (cn) {
+        atomicAdd(gsum + cell0 + i, s_sum[i]);
+        atomicAdd(gcnt + cell0 + i, cn);
+      }
+    }
+  }
+}
+
+// REFERENCE order: one warp per feature walks the node's documents in list order; documents of a
+// 32-wide chunk that fall in the same bin are added one after the other in document order
+// (__match_any_sync ranks them), so every per-bin FP64 sum sees its addends in the sequence the
+// reference's loop does (rtnode_histogram.cc:51-58).  Then the sequential inclusive prefix over
+// bins (rtnode_histogram.cc:59-62).  gsum/gcnt rows must be zero on entry.
+template <typename BinT, bool DENSE>
+__global__ void __launch_bounds__(128)
+hist_exact_kernel(const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ ids,
+                  uint32_t lo, uint32_t n, const double *__restrict__ lam,
+                  const uint32_t *__restrict__ thr_off, uint32_t F, double *gsum, uint32_t *gcnt) {
+  const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= F) return;
+  const uint32_t lane = lane_id();
+  double *sum = gsum + thr_off[f];
+  uint32_t *cnt = gcnt + thr_off[f];
+  const uint32_t cells = thr_off[f + 1] - thr_off[f];
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    const bool act = i < n;
+    uint32_t b = 0xffffffffu;   // inactive lanes share a bin no document can have
+    double v = 0.0;
+    if (act) {
+      const uint32_t d = DENSE ? lo + i : ids[lo + i];
+      b = load_bin<BinT>(panels, N, f, d);
+      v = lam[d];
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, b);
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t maxr = act ? __popc(peers) : 0u;
+    for (int o = 16; o > 0; o >>= 1) maxr = max(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
+    for (uint32_t r = 0; r < maxr; ++r) {
+      if (act && rank == r) { sum[b] += v; cnt[b] += 1u; }
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    for (uint32_t t = 1; t < cells; ++t) { sum[t] += sum[t - 1]; cnt[t] += cnt[t - 1]; }
+  }
+}
+
+// squares_sum_ (rtnode_histogram.cc:65-69, 199-203), sequential in list order.  One warp.
+template <bool DENSE>
+__global__ void squares_exact_kernel(const double *__restrict__ lam, const uint32_t *__restrict__ ids,
+                                     uint32_t lo, uint32_t n, bool fused, double *out) {
+  const uint32_t lane = lane_id();
+  double acc = 0.0;
+  for (uint32_t base = 0; base < n; base += 32) {
+    const uint32_t i = base + lane;
+    double v = 0.0;
+    if (i < n) v = lam[DENSE ? lo + i : ids[lo + i]];
+    const uint32_t cntk = min(32u, n - base);
+    if (fused) {
+      for (uint32_t k = 0; k < cntk; ++k) { const double vk = __shfl_sync(0xffffffffu, v, k); acc = fma(vk, vk, acc); }
+    } else {
+      for (uint32_t k = 0; k < cntk; ++k) { const double vk = __shfl_sync(0xffffffffu, v, k); acc = __dadd_rn(acc, __dmul_rn(vk, vk)); }
+    }
+  }
+  if (lane == 0) out[0] = acc;
+}
+
+// FAST: deterministic two-level sum of squares (fixed grid, fixed tree shape).
+template <bool DENSE>
+__global__ void __launch_bounds__(256)
+squares_fast_kernel(const double *__restrict__ lam, const uint32_t *__restrict__ ids, uint32_t lo,
+                    uint32_t n, double *partials) {
+  __shared__ double part[256];
+  const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+  const uint32_t b = blockIdx.x * per, e = min(n, b + per);
+  double acc = 0.0;
+  for (uint32_t i = b + threadIdx.x; i < e; i += 256) {
+    const double v = lam[DENSE ? lo + i : ids[lo + i]];
+    acc = fma(v, v, acc);
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  for (uint32_t st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) part[threadIdx.x] += part[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partials[blockIdx.x] = part[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// Finalize: cumulative histograms, right = parent - left (rtnode_histogram.cc:59-62, 79-85,
+// 209-216) and the split scan of every (feature, threshold) (rt.cc:257-292).  One block per
+// feature.  mode 0: node `L` alone (root); mode 1: children L (built from samples) and
+// R = P - L.  Per-feature winners go to fbest_*[child][f].
+// ------------------------------------------------------------------------------------------
+struct FinalizeArgs {
+  unsigned long long *hsum;   // all slots
+  uint32_t *hcnt;
+  uint32_t ncells;
+  int slotP, slotL, slotR;
+  int mode;
+  uint32_t minls;
+  const int *qexp;            // FAST: fixed-point exponent
+  double *fbest_score;        // [2][F]
+  uint32_t *fbest_t;          // [2][F]
+  uint32_t F;
+};
+
+__device__ __forceinline__ double cell_value(bool exact, unsigned long long raw, double inv) {
+  return exact ? __longlong_as_double((long long) raw) : (double) (long long) raw * inv;
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256)
+finalize_kernel(FinalizeArgs a, const uint32_t *__restrict__ thr_off) {
+  const uint32_t f = blockIdx.x;
+  const uint32_t c0 = thr_off[f], cells = thr_off[f + 1] - c0;
+  unsigned long long *Ls = a.hsum + (size_t) a.slotL * a.ncells + c0;
+  uint32_t *Lc = a.hcnt + (size_t) a.slotL * a.ncells + c0;
+  __shared__ long long w_sum[8];
+  __shared__ uint32_t w_cnt[8];
+  __shared__ long long carry_sum;
+  __shared__ uint32_t carry_cnt;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+
+  if (!EXACT) {
+    // inclusive scan of the raw (per-bin) fixed-point sums and counts, tiles of 256 bins
+    if (threadIdx.x == 0) { carry_sum = 0; carry_cnt = 0; }
+    __syncthreads();
+    for (uint32_t t0 = 0; t0 < cells; t0 += 256) {
+      const uint32_t t = t0 + threadIdx.x;
+      long long v = t < cells ? (long long) Ls[t] : 0;
+      uint32_t cv = t < cells ? Lc[t] : 0u;
+      for (int o = 1; o < 32; o <<= 1) {
+        long long pv = __shfl_up_sync(0xffffffffu, v, o);
+        uint32_t pc = __shfl_up_sync(0xffffffffu, cv, o);
+        if ((int) lane >= o) { v += pv; cv += pc; }
+      }
+      if (lane == 31) { w_sum[warp] = v; w_cnt[warp] = cv; }
+      __syncthreads();
+      long long add = carry_sum;
+      uint32_t addc = carry_cnt;
+      for (uint32_t w = 0; w < warp; ++w) { add += w_sum[w]; addc += w_cnt[w]; }
+      v += add; cv += addc;
+      if (t < cells) { Ls[t] = (unsigned long long) v; Lc[t] = cv; }
+      __syncthreads();
+      if (threadIdx.x == 255) { carry_sum = v; carry_cnt = cv; }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  const double inv = EXACT ? 1.0 : ldexp(1.0, -*a.qexp);
+
+  for (int child = 0; child < (a.mode == 0 ? 1 : 2); ++child) {
+    unsigned long long *S = Ls;
+    uint32_t *C = Lc;
+    if (child == 1) {
+      const unsigned long long *Ps = a.hsum + (size_t) a.slotP * a.ncells + c0;
+      const uint32_t *Pc = a.hcnt + (size_t) a.slotP * a.ncells + c0;
+      S = a.hsum + (size_t) a.slotR * a.ncells + c0;
+      C = a.hcnt + (size_t) a.slotR * a.ncells + c0;
+      for (uint32_t t = threadIdx.x; t < cells; t += 256) {
+        if (EXACT) {
+          const double pv = __longlong_as_double((long long) Ps[t]);
+          const double lv = __longlong_as_double((long long) Ls[t]);
+          S[t] = (unsigned long long) __double_as_longlong(pv - lv);   // rtnode_histogram.cc:82
+        } else {
+          S[t] = Ps[t] - Ls[t];
+        }
+        C[t] = Pc[t] - Lc[t];
+      }
+      __syncthreads();
+    }
+    // split scan (rt.cc:272-291): strict '>' in ascending t, start value -1
+    const double s = cell_value(EXACT, S[cells - 1], inv);
+    const uint32_t cn = C[cells - 1];
+    double best = -1.0;
+    uint32_t best_t = 0xffffffffu;
+    for (uint32_t t = threadIdx.x; t < cells; t += 256) {
+      const uint32_t lc = C[t], rc = cn - lc;
+      if (lc >= a.minls && rc >= a.minls) {
+        const double ls = cell_value(EXACT, S[t], inv);
+        const double rs = s - ls;
+        const double score = ls * ls / (double) lc + rs * rs / (double) rc;
+        if (score > best) { best = score; best_t = t; }
+      }
+    }
+    // block arg-max, ties to the smaller t
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const uint32_t ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+      if (ob > best || (ob == best && ot < best_t)) { best = ob; best_t = ot; }
+    }
+    __shared__ double wb[8];
+    __shared__ uint32_t wt[8];
+    if (lane == 0) { wb[warp] = best; wt[warp] = best_t; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (wb[w] > best || (wb[w] == best && wt[w] < best_t)) { best = wb[w]; best_t = wt[w]; }
+      a.fbest_score[child * a.F + f] = best;
+      a.fbest_t[child * a.F + f] = best_t;
+    }
+    __syncthreads();
+  }
+}
+
+// Arg-max over features (first maximum wins: rt.cc:297-306 with GCC's static schedule) and the
+// node statistics of RTNode(sampleids, hist) (rtnode.h:97-107).
+struct Finalize2Args {
+  const unsigned long long *hsum;
+  const uint32_t *hcnt;
+  uint32_t ncells;
+  int slotL, slotR, mode;
+  const int *qexp;
+  const double *fbest_score;
+  const uint32_t *fbest_t;
+  uint32_t F;
+  const double *sq_partials;   // left (or root) squares partials
+  uint32_t n_partials;
+  double parent_squares;
+  SplitResult *res;            // [2]
+};
+
+template <bool EXACT>
+__global__ void finalize2_kernel(Finalize2Args a, const uint32_t *__restrict__ thr_off) {
+  if (threadIdx.x != 0) return;
+  const double inv = EXACT ? 1.0 : ldexp(1.0, -*a.qexp);
+  double sqL = 0.0;
+  for (uint32_t i = 0; i < a.n_partials; ++i) sqL += a.sq_partials[i];
+  for (int child = 0; child < (a.mode == 0 ? 1 : 2); ++child) {
+    const int slot = child == 0 ? a.slotL : a.slotR;
+    const unsigned long long *S = a.hsum + (size_t) slot * a.ncells;
+    const uint32_t *C = a.hcnt + (size_t) slot * a.ncells;
+    double best = -1.0;
+    uint32_t bf = 0xffffffffu, bt = 0xffffffffu;
+    for (uint32_t f = 0; f < a.F; ++f) {
+      const double sc = a.fbest_score[child * a.F + f];
+      if (sc > best) { best = sc; bf = f; bt = a.fbest_t[child * a.F + f]; }
+    }
+    SplitResult r;
+    const uint32_t last0 = thr_off[1] - 1;
+    r.n = C[last0];
+    r.sum = cell_value(EXACT, S[last0], inv);
+    r.squares = child == 0 ? sqL : a.parent_squares - sqL;      // rtnode_histogram.cc:86,207
+    r.deviance = r.squares - r.sum * r.sum / (double) r.n;       // rtnode.h:106
+    r.score = best;
+    r.valid = best != -1.0;
+    r.feature = bf;
+    r.threshold_idx = bt;
+    r.lcount = r.valid ? C[thr_off[bf] + bt] : 0;
+    r.pad = 0;
+    a.res[child] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stable partition of a node's document list by bin(f*, doc) <= t*  (rt.cc:325-334; equal to the
+// reference's float test because thresholds are ascending, SURVEY.md section 7.1 "Bins").
+// ------------------------------------------------------------------------------------------
+constexpr uint32_t kPartItems = 2048;  // documents per block
+
+template <typename BinT, bool DENSE>
+__global__ void __launch_bounds__(256)
+partition_count_kernel(const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ src,
+                       uint32_t lo, uint32_t n, uint32_t f, uint32_t t, uint32_t *blockcnt) {
+  const uint32_t b0 = blockIdx.x * kPartItems, e = min(n, b0 + kPartItems);
+  uint32_t c = 0;
+  for (uint32_t i = b0 + threadIdx.x; i < e; i += 256) {
+    const uint32_t d = DENSE ? lo + i : src[lo + i];
+    c += load_bin<BinT>(panels, N, f, d) <= t;
+  }
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  __shared__ uint32_t w[8];
+  if (lane_id() == 0) w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int k = 0; k < 8; ++k) s += w[k];
+    blockcnt[blockIdx.x] = s;
+  }
+}
+
+template <typename BinT, bool DENSE>
+__global__ void __launch_bounds__(256)
+partition_scatter_kernel(const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ src,
+                         uint32_t *__restrict__ dst, uint32_t lo, uint32_t n, uint32_t f, uint32_t t,
+                         const uint32_t *__restrict__ blockcnt, uint32_t lcount) {
+  __shared__ uint32_t red[8];
+  __shared__ uint32_t s_left_base;
+  __shared__ uint32_t wcnt[8];
+  // exclusive prefix of the per-block left counts
+  uint32_t acc = 0;
+  for (uint32_t b = threadIdx.x; b < blockIdx.x; b += 256) acc += blockcnt[b];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int k = 0; k < 8; ++k) s += red[k];
+    s_left_base = s;
+  }
+  __syncthreads();
+  const uint32_t b0 = blockIdx.x * kPartItems, e = min(n, b0 + kPartItems);
+  uint32_t left_run = s_left_base;                 // lefts before the current round
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  for (uint32_t r0 = b0; r0 < e; r0 += 256) {
+    const uint32_t i = r0 + threadIdx.x;
+    const bool act = i < e;
+    uint32_t d = 0;
+    bool goes_left = false;
+    if (act) {
+      d = DENSE ? lo + i : src[lo + i];
+      goes_left = load_bin<BinT>(panels, N, f, d) <= t;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, goes_left);
+    if (lane == 0) wcnt[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t before = 0, total = 0;
+    for (uint32_t w = 0; w < 8; ++w) { if (w < warp) before += wcnt[w]; total += wcnt[w]; }
+    const uint32_t lrank = left_run + before + __popc(bal & ((1u << lane) - 1u));
+    if (act) {
+      if (goes_left) dst[lo + lrank] = d;
+      else dst[lo + lcount + (i - lrank)] = d;     // rights before i = i - lefts before i
+    }
+    left_run += total;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Leaf outputs (RegressionTree::update_output, rt.cc:165-207) and score update
+// (Mart::update_modelscores, mart.cc:459-468).
+// ------------------------------------------------------------------------------------------
+struct LeafSeg { uint32_t lo, n; int buf; int pad; };
+
+__global__ void __launch_bounds__(256)
+leaf_fit_kernel(const LeafSeg *__restrict__ segs, const uint32_t *__restrict__ ids0,
+                const uint32_t *__restrict__ ids1, bool root_only, const double *__restrict__ lam,
+                const double *__restrict__ wgt, bool exact, double *leafval,
+                uint32_t *__restrict__ leaf_of_doc) {
+  const uint32_t leaf = blockIdx.x;
+  const LeafSeg sg = segs[leaf];
+  const uint32_t *ids = sg.buf ? ids1 : ids0;
+  __shared__ double p1[256], p2[256];
+  // leaf assignment (DFS leaf index per document)
+  for (uint32_t i = threadIdx.x; i < sg.n; i += 256) {
+    const uint32_t d = root_only ? sg.lo + i : ids[sg.lo + i];
+    leaf_of_doc[d] = leaf;
+  }
+  double s1 = 0.0, s2 = 0.0;
+  if (exact) {
+    if (threadIdx.x >= 32) return;
+    const uint32_t lane = lane_id();
+    for (uint32_t base = 0; base < sg.n; base += 32) {
+      const uint32_t i = base + lane;
+      double v = 0.0, w = 0.0;
+      if (i < sg.n) {
+        const uint32_t d = root_only ? sg.lo + i : ids[sg.lo + i];
+        v = lam[d];
+        if (wgt) w = wgt[d];
+      }
+      const uint32_t cntk = min(32u, sg.n - base);
+      for (uint32_t k = 0; k < cntk; ++k) {
+        s1 += __shfl_sync(0xffffffffu, v, k);
+        s2 += __shfl_sync(0xffffffffu, w, k);
+      }
+    }
+  } else {
+    for (uint32_t i = threadIdx.x; i < sg.n; i += 256) {
+      const uint32_t d = root_only ? sg.lo + i : ids[sg.lo + i];
+      s1 += lam[d];
+      if (wgt) s2 += wgt[d];
+    }
+    p1[threadIdx.x] = s1; p2[threadIdx.x] = s2;
+    __syncthreads();
+    for (uint32_t st = 128; st > 0; st >>= 1) {
+      if (threadIdx.x < st) { p1[threadIdx.x] += p1[threadIdx.x + st]; p2[threadIdx.x] += p2[threadIdx.x + st]; }
+      __syncthreads();
+    }
+    s1 = p1[0]; s2 = p2[0];
+  }
+  if (threadIdx.x == 0) {
+    if (wgt) leafval[leaf] = s2 >= DBL_EPSILON ? s1 / s2 : 0.0;   // rt.cc:200
+    else leafval[leaf] = s1 / (double) sg.n;                      // rt.cc:178
+  }
+}
+
+__global__ void update_scores_kernel(const uint32_t *__restrict__ leaf_of_doc,
+                                     const double *__restrict__ leafval, double weight, size_t N,
+                                     double *scores) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) scores[i] = fma(weight, leafval[leaf_of_doc[i]], scores[i]);   // mart.cc:466 (fused)
+}
+
+// scores[i] += weight * tree(doc_i) for an arbitrary tree expressed on this context's bins
+// (Dart::update_modelscores, dart.cc:634-650).
+struct DevTree { const int32_t *feature; const uint32_t *tidx; const int32_t *left, *right; const double *value; };
+
+template <typename BinT>
+__global__ void apply_tree_kernel(const uint4 *__restrict__ panels, size_t N, DevTree t, double weight,
+                                  double *scores) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  int32_t nd = 0;
+  while (t.feature[nd] >= 0)
+    nd = load_bin<BinT>(panels, N, (uint32_t) t.feature[nd], (uint32_t) i) <= t.tidx[nd] ? t.left[nd] : t.right[nd];
+  scores[i] = fma(weight, t.value[nd], scores[i]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Oblivious trees (ObliviousRT::fit / fill, ot.cc:32-201): per level, sum the split gain of every
+// (f, t) over the level's nodes in node order; a cell is invalid as soon as one node violates the
+// minimum leaf support; the single best cell (> 0, first maximum) splits every node.
+// ------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void obv_level_kernel(const unsigned long long *__restrict__ hsum, const uint32_t *__restrict__ hcnt,
+                                 uint32_t ncells, const int *__restrict__ slots, uint32_t nnodes,
+                                 const uint32_t *__restrict__ thr_off, uint32_t F, uint32_t minls,
+                                 const int *qexp, double *cell_score) {
+  const uint32_t f = blockIdx.x;
+  const uint32_t c0 = thr_off[f], cells = thr_off[f + 1] - c0;
+  const double inv = EXACT ? 1.0 : ldexp(1.0, -*qexp);
+  const double invalid = -DBL_MAX;
+  for (uint32_t t = threadIdx.x; t < cells; t += blockDim.x) {
+    double acc = 0.0;
+    for (uint32_t k = 0; k < nnodes; ++k) {
+      const unsigned long long *S = hsum + (size_t) slots[k] * ncells + c0;
+      const uint32_t *C = hcnt + (size_t) slots[k] * ncells + c0;
+      if (acc != invalid) {
+        const uint32_t cn = C[cells - 1], lc = C[t], rc = cn - lc;
+        if (lc >= minls && rc >= minls) {
+          const double s = cell_value(EXACT, S[cells - 1], inv);
+          const double ls = cell_value(EXACT, S[t], inv);
+          const double rs = s - ls;
+          acc += ls * ls / (double) lc + rs * rs / (double) rc;   // ot.cc:194-195
+        } else {
+          acc = invalid;
+        }
+      }
+    }
+    cell_score[c0 + t] = acc;
+  }
+}
+
+// first maximum strictly greater than 0 (ot.cc:72-96); also gathers each node's left count
+__global__ void obv_argmax_kernel(const double *__restrict__ cell_score, const uint32_t *__restrict__ thr_off,
+                                  uint32_t F, const uint32_t *__restrict__ hcnt, uint32_t ncells,
+                                  const int *__restrict__ slots, uint32_t nnodes, SplitResult *res,
+                                  uint64_t *lcounts) {
+  __shared__ double sb[256];
+  __shared__ uint32_t sc[256];
+  const uint32_t total = thr_off[F];
+  double best = 0.0;
+  uint32_t bc = 0xffffffffu;
+  const uint32_t per = (total + blockDim.x - 1) / blockDim.x;
+  const uint32_t b = threadIdx.x * per, e = min(total, b + per);
+  for (uint32_t c = b; c < e; ++c) {
+    const double v = cell_score[c];
+    if (v != -DBL_MAX && v > best) { best = v; bc = c; }
+  }
+  sb[threadIdx.x] = best; sc[threadIdx.x] = bc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (uint32_t k = 1; k < blockDim.x; ++k)
+      if (sb[k] > best) { best = sb[k]; bc = sc[k]; }   // chunks ascend with k: first maximum wins
+    SplitResult r{};
+    r.score = best;
+    r.valid = bc != 0xffffffffu && best != 0.0;
+    if (r.valid) {
+      uint32_t f = 0;
+      while (thr_off[f + 1] <= bc) ++f;
+      r.feature = f;
+      r.threshold_idx = bc - thr_off[f];
+      for (uint32_t k = 0; k < nnodes; ++k)
+        lcounts[k] = hcnt[(size_t) slots[k] * ncells + bc];
+    }
+    res[0] = r;
+  }
+}
+
+}  // namespace qr

@@ -1,0 +1,256 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same seeded
+inputs.  Bit-exact for indices (bins, ranks, split feature / threshold index, doc->leaf); floating
+point within the tolerance written at each assert (north_star: 1e-5 relative on leaf outputs and
+NDCG@k; most checks here are far tighter, and exact where the arithmetic order is replicated)."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from quickrank_b200 import api, synth
+import qr_testlib as common
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5  # north_star tolerance for leaf outputs / NDCG
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(1e-300, np.maximum(np.abs(a), np.abs(b))))) if a.size else 0.0
+
+
+@pytest.mark.parametrize("gridded,nthr", [(True, 0), (False, 0), (False, 32), (True, 300)])
+def test_binning_matches_oracle(gridded, nthr):
+    x, l, off = common.dataset(n=2500, f=19, q=25, gridded=gridded)
+    ob = po.Binning(np.ascontiguousarray(x.T), nthr)
+    with api.Trainer(x, l, off, nthresholds=nthr) as tr:
+        obins = ob.bins()
+        for f in range(x.shape[1]):
+            assert np.array_equal(tr.thresholds(f), ob.thresholds(f)), "thresholds of feature %d" % f
+            assert np.array_equal(tr.get_bins(f), obins[f]), "bins of feature %d" % f
+
+
+def test_binning_colmajor_entry_point():
+    x, l, off = common.dataset(n=1200, f=9, q=12)
+    ob = po.Binning(np.ascontiguousarray(x.T), 0)
+    with api.Trainer(np.ascontiguousarray(x.T), l, off, layout="colmajor") as tr:
+        for f in range(x.shape[1]):
+            assert np.array_equal(tr.get_bins(f), ob.bins()[f])
+
+
+@pytest.mark.parametrize("levels", [1, 3, 9, 100000])
+def test_ranking_reproduces_std_sort(levels):
+    rng = np.random.default_rng(levels)
+    x, l, off = common.dataset(n=4000, f=5, q=45, qlen=(1, 200))
+    s = rng.integers(0, levels, size=len(l)).astype(np.float64) / 7.0
+    with api.Trainer(x, l, off) as tr:
+        tr.set_scores(s)
+        got = tr.get_ranking()
+    for q in range(len(off) - 1):
+        a, b = int(off[q]), int(off[q + 1])
+        assert np.array_equal(got[a:b], po.sort_desc(s[a:b])), "query %d (n=%d)" % (q, b - a)
+
+
+@pytest.mark.parametrize("cutoff", [10, 3, 0])
+@pytest.mark.parametrize("mode", [api.HIST_REFERENCE, api.HIST_FAST])
+def test_ndcg_matches_oracle(cutoff, mode):
+    rng = np.random.default_rng(5)
+    x, l, off = common.dataset(n=3000, f=5, q=40, qlen=(1, 150))
+    s = np.round(rng.normal(size=len(l)), 1)
+    want = po.ndcg_dataset(l, s, off, cutoff)
+    with api.Trainer(x, l, off, cutoff=cutoff, hist_mode=mode) as tr:
+        tr.set_scores(s)
+        got = tr.evaluate_dataset()
+    if mode == api.HIST_REFERENCE:
+        assert got == want
+    else:
+        assert abs(got - want) <= 1e-12 * abs(want)
+
+
+@pytest.mark.parametrize("cutoff", [10, 5, 40, 0])
+def test_lambdas_match_oracle(cutoff):
+    rng = np.random.default_rng(cutoff + 1)
+    x, l, off = common.dataset(n=2500, f=5, q=30, qlen=(1, 120))
+    with api.Trainer(x, l, off, cutoff=cutoff) as tr:
+        # all-zero scores: exp(0) == 1 exactly, so the result is bit-identical to the reference
+        tr.set_scores(np.zeros(len(l)))
+        tr.compute_pseudoresponses()
+        lam, w = tr.get_pseudoresponses()
+        olam, ow = po.lambdas(np.zeros(len(l)), l, off, cutoff)
+        assert np.array_equal(lam, olam) and np.array_equal(w, ow)
+        # tie-heavy and generic scores: same order of accumulation, exp() may differ in the last ulp
+        for s in (common.tie_heavy_scores(len(l), rng), rng.normal(size=len(l))):
+            tr.set_scores(s)
+            tr.compute_pseudoresponses()
+            lam, w = tr.get_pseudoresponses()
+            olam, ow = po.lambdas(s, l, off, cutoff)
+            scale = np.max(np.abs(olam))
+            assert np.max(np.abs(lam - olam)) <= 1e-13 * scale
+            assert np.max(np.abs(w - ow)) <= 1e-13 * max(1e-300, np.max(np.abs(ow)))
+
+
+def test_mart_pseudoresponses():
+    rng = np.random.default_rng(2)
+    x, l, off = common.dataset(n=1500, f=5, q=15)
+    s = rng.normal(size=len(l))
+    with api.Trainer(x, l, off, algo="MART") as tr:
+        tr.set_scores(s)
+        tr.compute_pseudoresponses()
+        lam, _ = tr.get_pseudoresponses()
+    assert np.array_equal(lam, l.astype(np.float64) - s)
+
+
+def _gradients(x, l, off, seed, cutoff=10):
+    rng = np.random.default_rng(seed)
+    s = rng.normal(size=len(l)) * 0.3
+    return po.lambdas(s, l, off, cutoff)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n=3000, f=20, q=30, gridded=True, nthr=0, leaves=12, minls=1),
+    dict(n=3000, f=20, q=30, gridded=False, nthr=0, leaves=8, minls=1),     # u16 bins, one per value
+    dict(n=5000, f=33, q=50, gridded=False, nthr=64, leaves=32, minls=5),
+    dict(n=800, f=7, q=9, gridded=True, nthr=0, leaves=64, minls=1),        # many tiny nodes: tie rules
+])
+def test_fit_tree_reference_mode_is_bit_exact(cfg):
+    x, l, off = common.dataset(n=cfg["n"], f=cfg["f"], q=cfg["q"], gridded=cfg["gridded"])
+    lam, w = _gradients(x, l, off, 3)
+    ob = po.Binning(np.ascontiguousarray(x.T), cfg["nthr"])
+    want = ob.fit_tree(lam, w, nleaves=cfg["leaves"], minls=cfg["minls"])
+    with api.Trainer(x, l, off, nleaves=cfg["leaves"], minleafsupport=cfg["minls"],
+                     nthresholds=cfg["nthr"], hist_mode=api.HIST_REFERENCE) as tr:
+        tr.set_pseudoresponses(lam, w)
+        got = tr.fit_regressor_on_gradient()
+        leaf = tr.get_leaf_assignment()
+    assert common.same_structure(got, want), common.describe_tree_diff(got, want)
+    assert np.array_equal(got["value"], want["value"]), common.describe_tree_diff(got, want)
+    assert np.array_equal(got["count"], want["count"])
+    assert np.array_equal(got["deviance"][got["feature"] >= 0], want["deviance"][want["feature"] >= 0])
+    assert np.array_equal(leaf, want["leaf_of_doc"])
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n=3000, f=20, q=30, gridded=True, nthr=0, leaves=12, minls=1),
+    dict(n=3000, f=20, q=30, gridded=False, nthr=0, leaves=8, minls=1),
+    dict(n=6000, f=40, q=60, gridded=True, nthr=0, leaves=24, minls=20),
+])
+def test_fit_tree_fast_mode(cfg):
+    """Fixed-point accumulation: same split indices and doc->leaf map wherever the oracle's own
+    best and runner-up differ by more than rounding; leaf outputs within 1e-5 relative."""
+    x, l, off = common.dataset(n=cfg["n"], f=cfg["f"], q=cfg["q"], gridded=cfg["gridded"])
+    lam, w = _gradients(x, l, off, 4)
+    ob = po.Binning(np.ascontiguousarray(x.T), cfg["nthr"])
+    want = ob.fit_tree(lam, w, nleaves=cfg["leaves"], minls=cfg["minls"])
+    with api.Trainer(x, l, off, nleaves=cfg["leaves"], minleafsupport=cfg["minls"],
+                     nthresholds=cfg["nthr"], hist_mode=api.HIST_FAST) as tr:
+        tr.set_pseudoresponses(lam, w)
+        got = tr.fit_regressor_on_gradient()
+        leaf = tr.get_leaf_assignment()
+        got2 = tr.fit_regressor_on_gradient()   # determinism: same answer twice
+    assert common.same_structure(got, got2) and np.array_equal(got["value"], got2["value"])
+    assert np.array_equal(leaf, want["leaf_of_doc"]), common.describe_tree_diff(got, want)
+    assert np.array_equal(got["count"], want["count"])
+    lv = common.leaves_mask(want)
+    assert rel_err(got["value"][lv], want["value"][lv]) <= REL
+    assert common.same_structure(got, want), common.describe_tree_diff(got, want)
+
+
+@pytest.mark.parametrize("algo,depth", [("OBVLAMBDAMART", 4), ("OBVMART", 3)])
+@pytest.mark.parametrize("mode", [api.HIST_REFERENCE, api.HIST_FAST])
+def test_oblivious_tree(algo, depth, mode):
+    x, l, off = common.dataset(n=4000, f=15, q=40)
+    lam, w = _gradients(x, l, off, 6)
+    if algo == "OBVMART":
+        w = None
+    ob = po.Binning(np.ascontiguousarray(x.T), 0)
+    want = ob.fit_tree(lam, w, nleaves=1 << depth, minls=1, depth=depth)
+    with api.Trainer(x, l, off, algo=algo, treedepth=depth, hist_mode=mode) as tr:
+        tr.set_pseudoresponses(lam, w if w is not None else np.zeros_like(lam))
+        got = tr.fit_regressor_on_gradient()
+        leaf = tr.get_leaf_assignment()
+    assert common.same_structure(got, want), common.describe_tree_diff(got, want)
+    assert np.array_equal(leaf, want["leaf_of_doc"])
+    lv = common.leaves_mask(want)
+    if mode == api.HIST_REFERENCE:
+        assert np.array_equal(got["value"][lv], want["value"][lv])
+    else:
+        assert rel_err(got["value"][lv], want["value"][lv]) <= REL
+
+
+@pytest.mark.parametrize("algo", ["LAMBDAMART", "MART", "OBVLAMBDAMART"])
+@pytest.mark.parametrize("mode", [api.HIST_REFERENCE, api.HIST_FAST])
+def test_boosting_loop_follows_oracle(algo, mode):
+    """Free-running training (mart.cc:307-347): tree structure identical, metric within 1e-5."""
+    T = 12
+    x, l, off = common.dataset(n=4000, f=24, q=40)
+    depth = 3 if algo.startswith("OBV") else 0
+    want_trees, want_metric, want_scores = po.train(algo, x, l, off, T, nleaves=10, depth=depth, cutoff=10)
+    with api.Trainer(x, l, off, algo=algo, nleaves=10, treedepth=max(depth, 1), hist_mode=mode) as tr:
+        for m in range(T):
+            tree, metric = tr.boost_iteration()
+            assert common.same_structure(tree, want_trees[m]), \
+                "tree %d: %s" % (m, common.describe_tree_diff(tree, want_trees[m]))
+            lv = common.leaves_mask(tree)
+            assert rel_err(tree["value"][lv], want_trees[m]["value"][lv]) <= REL
+            assert abs(metric - want_metric[m]) <= REL * abs(want_metric[m])
+        assert rel_err(tr.get_scores(), want_scores) <= REL
+
+
+def test_stepwise_hooks_equal_fused_iteration():
+    x, l, off = common.dataset(n=2000, f=10, q=20)
+    with api.Trainer(x, l, off) as a, api.Trainer(x, l, off) as b:
+        for _ in range(3):
+            a.compute_pseudoresponses()
+            ta = a.fit_regressor_on_gradient()
+            a.update_modelscores()
+            ma = a.evaluate_dataset()
+            tb, mb = b.boost_iteration()
+            assert common.same_structure(ta, tb) and np.array_equal(ta["value"], tb["value"])
+            assert ma == mb
+        assert np.array_equal(a.get_scores(), b.get_scores())
+
+
+def test_apply_tree_adds_and_subtracts():
+    x, l, off = common.dataset(n=2000, f=10, q=20)
+    with api.Trainer(x, l, off) as tr:
+        tree, _ = tr.boost_iteration()
+        s1 = tr.get_scores()
+        tr.apply_tree(tree, -0.1)          # DART-style removal (dart.cc:634-650)
+        s0 = tr.get_scores()
+        assert np.max(np.abs(s0)) <= 1e-15
+        tr.apply_tree(tree, 0.1)
+        assert np.array_equal(tr.get_scores(), s1)
+        col = np.ascontiguousarray(x.T)
+        assert np.array_equal(po.update_scores(tree, col, 0.1, np.zeros(len(l))), s1)
+
+
+def test_scoring_matches_oracle_bit_for_bit():
+    x, l, off = common.dataset(n=3000, f=30, q=30)
+    trees, weights = synth.random_ensemble(40, 16, 30, seed=3)
+    want = po.score_dataset(trees, weights, x)
+    with api.Scorer(trees, weights, 30) as sc:
+        got = sc.score_dataset(x)
+        one = sc.score_document(x[17])
+    assert np.array_equal(got, want)
+    assert one == want[17]
+
+
+def test_scoring_a_trained_model():
+    x, l, off = common.dataset(n=2500, f=12, q=25)
+    with api.Trainer(x, l, off, hist_mode=api.HIST_REFERENCE) as tr:
+        trees = [tr.boost_iteration()[0] for _ in range(5)]
+        train_scores = tr.get_scores()
+    with api.Scorer(trees, [0.1] * 5, 12) as sc:
+        got = sc.score_dataset(x)
+    assert np.array_equal(got, po.score_dataset(trees, [0.1] * 5, x))
+    assert rel_err(got, train_scores) <= 1e-12
+
+
+def test_errors_are_reported():
+    x, l, off = common.dataset(n=500, f=4, q=5)
+    bad = x.copy()
+    bad[3, 1] = np.nan
+    with pytest.raises(api.QrError):
+        api.Trainer(bad, l, off)
+    with pytest.raises(api.QrError):
+        api.Trainer(x, l, off[:-1])
