@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path (BASELINE.json metric: LambdaMART trees/sec; config 2).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one boosting iteration of Mart::learn's loop (reference mart.cc:331-347):
+pseudo-responses -> root histogram -> tree fit -> leaf outputs -> score update -> NDCG@10, on the
+synthetic config-2 workload (1M docs x 136 features x 10k queries, 64 leaves).  With N > 1 the
+SAME 1M documents are sharded by query over the ranks, one process per GPU (torchrun; strong
+scaling, as BASELINE.json's north_star asks: trees/sec on the 1M-doc input at 1/2/4/8 GPUs), and
+the per-bin histograms are all-reduced over NCCL.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each field means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOAD = dict(n_docs=1_000_000, n_features=136, n_queries=10_000, leaves=64, cutoff=10,
+                shrinkage=0.1, nthresholds=0, minls=1, seed=20260102)
+METRIC = "lambdamart_trees_per_sec"
+UNIT = "trees/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            c = [v.strip() for v in r.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_shard(rank, world, w=WORKLOAD):
+    """The rank's contiguous range of queries of the one global dataset, balanced by document count
+    (lambdas need whole queries: lambdamart.cc:71-151)."""
+    from quickrank_b200 import synth
+    x, labels, qoff = synth.make_dataset(w["n_docs"], w["n_features"], w["n_queries"], seed=w["seed"])
+    if world == 1:
+        return x, labels, qoff
+    from quickrank_b200.sharding import query_shards
+    q0, q1 = query_shards(qoff, world)[rank]
+    d0, d1 = int(qoff[q0]), int(qoff[q1])
+    return (np.ascontiguousarray(x[d0:d1]), np.ascontiguousarray(labels[d0:d1]),
+            (qoff[q0:q1 + 1] - qoff[q0]).astype(np.uint64))
+
+
+def hist_bytes_per_tree(n, f, rho, bin_bytes=1):
+    """Algorithmic bytes of the histogram kernels for one tree:
+    root: every bin once + lambda once; children: bins + doc id + gathered lambda."""
+    return n * (f * bin_bytes + 8) + rho * n * (f * bin_bytes + 4 + 8)
+
+
+def tree_bytes(n, f, rho, sigma, leaves, cells):
+    h = cells * 12
+    return (28 * n + hist_bytes_per_tree(n, f, rho) + sigma * n * (1 + 4 + 4) + 6 * h * (leaves - 1)
+            + 20 * n + 20 * n + 12 * n)
+
+
+def run_ours(args):
+    from quickrank_b200 import api
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    if api.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback on the hot path)")
+    w = WORKLOAD
+    x, labels, qoff = make_shard(rank, world)
+
+    t0 = time.perf_counter()
+    tr = api.Trainer(x, labels, qoff, algo="LAMBDAMART", nleaves=w["leaves"], minleafsupport=w["minls"],
+                     nthresholds=w["nthresholds"], cutoff=w["cutoff"], shrinkage=w["shrinkage"],
+                     hist_mode=api.HIST_FAST, device=local_rank)
+    init_s = time.perf_counter() - t0
+    if world > 1:
+        import torch
+        idt = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        tr.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    for _ in range(max(args.warmup, 3)):
+        tr.boost_iteration(want_tree=False, want_metric=True)
+    launches0 = tr.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    tr.timer_start()
+    rho_sum = sigma_sum = 0.0
+    for _ in range(args.steps):
+        tr.boost_iteration(want_tree=False, want_metric=True)
+        r, s, _ns = tr.last_tree_stats()
+        rho_sum += r
+        sigma_sum += s
+    ms = tr.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = tr.launch_count() - launches0
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = 1000.0 / ms_per_step  # trees/s of the whole job (all ranks grow the same tree)
+
+    # ---- end to end through the hook-level C ABI with host buffers ----
+    d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tr.compute_pseudoresponses()
+        tree = tr.fit_regressor_on_gradient(want_tree=True)      # flat tree copied to host arrays
+        tr.update_modelscores()
+        _m = tr.evaluate_dataset()                               # metric read back
+        d2h += sum(tree[k].nbytes for k in tree if hasattr(tree[k], "nbytes")) + 8
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (histogram build), per-phase CUDA events ----
+    prof_steps = min(args.steps, 5)
+    tr.set_profiling(True)
+    tr.phase_times(reset=True)
+    rho_p = 0.0
+    for _ in range(prof_steps):
+        tr.boost_iteration(want_tree=False, want_metric=True)
+        rho_p += tr.last_tree_stats()[0]
+    pms, pln = tr.phase_times()
+    tr.set_profiling(False)
+    peak, peak_src = load_peaks()
+    n, f = len(labels), w["n_features"]
+    hb = hist_bytes_per_tree(n, f, rho_p / prof_steps)
+    hist_ms = pms["hist"] / prof_steps
+    achieved = hb / (hist_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "hist_fast_kernel (histogram build, root + child nodes)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_tree": int(hb), "kernel_ms_per_tree": round(hist_ms, 4),
+                "phase_ms_per_tree": {k: round(v / prof_steps, 4) for k, v in pms.items()},
+                "whole_tree_gbs": round(tree_bytes(n, f, rho_sum / args.steps, sigma_sum / args.steps,
+                                                   w["leaves"], 0) / (ms_per_step * 1e-3) / 1e9, 1)}
+
+    out = None
+    if rank == 0:
+        cpu = cpu_baseline(args, quick=True) if world == 1 and not args.no_cpu_baseline else None
+        out = {
+            "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "LambdaMART 64 leaves, synthetic %d docs x %d feat x %d queries, "
+                                   "NDCG@10, 256-level features (u8 bins), shrinkage 0.1 (BASELINE.json configs[1])"
+                                   % (w["n_docs"], w["n_features"], w["n_queries"]),
+                       "docs_per_gpu": int(len(labels)), "global_docs": w["n_docs"],
+                       "hist_mode": "fixed-point int64 (FAST)", "parallelism": "query-sharded dp%d" % world,
+                       "l2": "inputs larger than L2 (136 MB bin matrix + 40 MB state per step)"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": int(d2h / args.steps),
+                    "note": "hook-level C ABI per step (pseudo-responses, fit -> host tree, score update, "
+                            "NDCG -> host); the dataset upload + binning happen once in qr_ctx_create, "
+                            "as Mart::init does, and are reported in init_s / init_h2d_bytes"},
+            "init_s": round(init_s, 3), "init_h2d_bytes": int(x.nbytes + labels.nbytes + qoff.nbytes),
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+        }
+        if cpu:
+            out["cpu_baseline"] = cpu
+    tr.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_steps(x, labels, qoff, warmup, steps, w=WORKLOAD):
+    """Times the reference's own loop body on the host cores.  Uses the unmodified reference
+    (oracle/_ref) when it is built, else the C restatement (oracle/qr_oracle.c)."""
+    from oracle import pyref
+    nthreads = cpu_threads()
+    os.environ.setdefault("OMP_NUM_THREADS", str(nthreads))
+    if pyref.available():
+        s = pyref.RefSession("LAMBDAMART", x, labels, qoff, ntrees=warmup + steps + 1,
+                             shrinkage=w["shrinkage"], nthresholds=w["nthresholds"], nleaves=w["leaves"],
+                             minleafsupport=w["minls"], cutoff=w["cutoff"])
+        t0 = time.perf_counter()
+        s.init()
+        init_s = time.perf_counter() - t0
+
+        def step():
+            s.compute_pseudoresponses()
+            s.fit_tree(True)
+            s.evaluate()
+        kind = "reference"
+    else:
+        from oracle import pyoracle as po
+        col = np.ascontiguousarray(x.T)
+        t0 = time.perf_counter()
+        ob = po.Binning(col, w["nthresholds"])
+        init_s = time.perf_counter() - t0
+        state = {"scores": np.zeros(len(labels))}
+
+        def step():
+            lam, wt = po.lambdas(state["scores"], labels, qoff, w["cutoff"])
+            tree = ob.fit_tree(lam, wt, nleaves=w["leaves"], minls=w["minls"])
+            state["scores"] = po.update_scores(tree, col, w["shrinkage"], state["scores"])
+            po.ndcg_dataset(labels, state["scores"], qoff, w["cutoff"])
+        kind = "port"
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return dt / steps, init_s, kind, nthreads
+
+
+def cpu_baseline(args, quick=True):
+    """Bounded CPU sample of the same workload (rank 0, N=1 only)."""
+    w = WORKLOAD
+    from quickrank_b200 import synth
+    n = w["n_docs"]
+    x, labels, qoff = synth.make_dataset(n, w["n_features"], w["n_queries"], seed=w["seed"])
+    sec_per_tree, init_s, kind, nthreads = reference_steps(x, labels, qoff, 1, 3)
+    return {"value": round(1.0 / sec_per_tree, 4), "unit": UNIT, "cores": nthreads, "kind": kind,
+            "sample": "full config-2 workload (%d docs), 1 warm-up + 3 timed boosting iterations; init "
+                      "(transpose, argsort, binning) %.1f s excluded as in the reference's own Training Time"
+                      % (n, init_s)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    w = WORKLOAD
+    from quickrank_b200 import synth
+    x, labels, qoff = synth.make_dataset(w["n_docs"], w["n_features"], w["n_queries"], seed=w["seed"])
+    warm = min(max(args.warmup, 1), 3)
+    steps = min(args.steps, 20)
+    sec_per_tree, init_s, kind, nthreads = reference_steps(x, labels, qoff, warm, steps)
+    value = 1.0 / sec_per_tree
+    return {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
+        "ms_per_step": round(sec_per_tree * 1e3, 3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "LambdaMART 64 leaves, synthetic %d docs x %d feat x %d queries, NDCG@10 "
+                               "(BASELINE.json configs[1]) on the host CPU" % (w["n_docs"], w["n_features"], w["n_queries"])},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": nthreads, "kind": kind,
+                         "sample": "full workload, %d timed iterations (capped at 20), init %.1f s excluded" % (steps, init_s)},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -151,6 +151,11 @@ uint64_t qr_launch_count(qr_ctx *ctx);
  * score update, [5] ranking/NDCG; also returns per-phase launch counts (either may be NULL). */
 int qr_phase_times(qr_ctx *ctx, double ms[6], uint64_t launches[6], int reset);
 int qr_set_profiling(qr_ctx *ctx, int enabled);
+/* CUDA-event stopwatch on the context's stream (the stream every kernel of the context is
+ * launched on): start records an event, stop records a second one, synchronises and returns the
+ * elapsed device time in milliseconds. */
+int qr_timer_start(qr_ctx *ctx);
+int qr_timer_stop(qr_ctx *ctx, double *ms);
 
 /* ---- multi-GPU (one process per GPU; documents sharded by query) ------ */
 #define QR_COMM_ID_BYTES 128

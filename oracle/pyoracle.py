@@ -66,6 +66,7 @@ def lib():
         L.qro_fit_tree.restype = C.POINTER(Tree)
         L.qro_fit_tree.argtypes = [C.POINTER(Bins), dp, dp, sz, sz, sz, u32p]
         L.qro_tree_free.argtypes = [C.POINTER(Tree)]
+        L.qro_split_scores.argtypes = [C.POINTER(Bins), dp, u64p, sz, sz, u32p, u32p, sz, dp]
         L.qro_update_scores.argtypes = [C.POINTER(Tree), fp, sz, C.c_double, dp]
         L.qro_score_dataset.argtypes = [C.POINTER(C.POINTER(Tree)), dp, sz, fp, sz, sz, dp]
         L.qro_train.argtypes = [C.c_int, fp, fp, u64p, sz, sz, sz, sz, C.c_double, sz, sz, sz, sz,
@@ -194,6 +195,17 @@ class Binning:
         lib().qro_tree_free(tp)
         d["leaf_of_doc"] = leaf
         return d
+
+    def split_scores(self, lam, ids, minls, cands):
+        """Reference split score of each (feature, threshold_idx) candidate on the node `ids`."""
+        lam = np.ascontiguousarray(lam, np.float64)
+        ids = np.ascontiguousarray(ids, np.uint64)
+        cf = np.ascontiguousarray([c[0] for c in cands], np.uint32)
+        ct = np.ascontiguousarray([c[1] for c in cands], np.uint32)
+        out = np.zeros(len(cands), np.float64)
+        lib().qro_split_scores(self.h, _p(lam, C.c_double), _p(ids, C.c_uint64), len(ids), minls,
+                               _p(cf, C.c_uint32), _p(ct, C.c_uint32), len(cands), _p(out, C.c_double))
+        return out
 
     def close(self):
         if self.h:

@@ -743,6 +743,34 @@ qro_tree *qro_fit_tree(const qro_bins *b, const double *lab, const double *w, si
   return t;
 }
 
+void qro_split_scores(const qro_bins *b, const double *lab, const uint64_t *ids64, size_t n,
+                      size_t minls, const uint32_t *cand_f, const uint32_t *cand_t, size_t ncand,
+                      double *out) {
+  for (size_t k = 0; k < ncand; ++k) {
+    const size_t f = cand_f[k], t = cand_t[k], ts = b->thr_size[f];
+    const uint32_t *bin = b->bins + f * b->N;
+    double *s = (double *) calloc(ts, sizeof(double));
+    size_t *c = (size_t *) calloc(ts, sizeof(size_t));
+    for (size_t i = 0; i < n; ++i) {
+      const size_t d = (size_t) ids64[i];
+      s[bin[d]] += lab[d];
+      c[bin[d]]++;
+    }
+    for (size_t j = 1; j < ts; ++j) {
+      s[j] += s[j - 1];
+      c[j] += c[j - 1];
+    }
+    const size_t lc = c[t], rc = c[ts - 1] - lc;
+    out[k] = -1.0;
+    if (t < ts && lc >= minls && rc >= minls) {
+      const double ls = s[t], rs = s[ts - 1] - ls;
+      out[k] = ls * ls / (double) lc + rs * rs / (double) rc;
+    }
+    free(s);
+    free(c);
+  }
+}
+
 void qro_tree_free(qro_tree *t) {
   if (!t) return;
   free(t->feature);

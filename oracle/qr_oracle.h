@@ -79,6 +79,14 @@ qro_tree *qro_fit_tree(const qro_bins *b, const double *lambdas, const double *w
                        size_t nleaves, size_t minls, size_t depth, uint32_t *leaf_of_doc);
 void qro_tree_free(qro_tree *t);
 
+/* Tie audit: the reference's split score lsum^2/lcnt + rsum^2/rcnt (rt.cc:272-283) of `ncand`
+ * candidate (feature, threshold index) pairs on the node made of documents ids[0..n) (ascending),
+ * with the histogram built from those samples in list order (rtnode_histogram.cc:51-63).
+ * out[k] = -1 when the candidate violates the minimum leaf support. */
+void qro_split_scores(const qro_bins *b, const double *lambdas, const uint64_t *ids, size_t n,
+                      size_t minls, const uint32_t *cand_f, const uint32_t *cand_t, size_t ncand,
+                      double *out);
+
 /* scores[i] += shrinkage * tree(doc_i), walking the raw float columns (mart.cc:459-468) */
 void qro_update_scores(const qro_tree *t, const float *colmajor, size_t N, double shrinkage,
                        double *scores);

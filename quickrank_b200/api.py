@@ -89,6 +89,8 @@ def lib():
         L.qr_launch_count.argtypes = [vp]
         L.qr_phase_times.argtypes = [vp, dp, u64p, C.c_int]
         L.qr_set_profiling.argtypes = [vp, C.c_int]
+        L.qr_timer_start.argtypes = [vp]
+        L.qr_timer_stop.argtypes = [vp, dp]
         L.qr_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
         L.qr_ctx_comm_init.argtypes = [vp, C.POINTER(C.c_ubyte), C.c_int, C.c_int]
         L.qr_scorer_create.argtypes = [C.POINTER(FlatTree), dp, sz, sz, C.c_int, C.POINTER(vp)]
@@ -271,6 +273,14 @@ class Trainer:
 
     def set_profiling(self, on):
         _check(lib().qr_set_profiling(self.h, int(on)))
+
+    def timer_start(self):
+        _check(lib().qr_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        _check(lib().qr_timer_stop(self.h, C.byref(ms)))
+        return ms.value
 
     def phase_times(self, reset=False):
         ms = (C.c_double * 6)()

@@ -124,7 +124,7 @@ struct qr_ctx {
   bool profiling = false;
   double phase_ms[qr::kNumPhases] = {0};
   uint64_t phase_launches[qr::kNumPhases] = {0};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
 
   qr::Comm *comm = nullptr;
   size_t N_global = 0, Q_global = 0;

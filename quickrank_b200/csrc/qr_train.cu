@@ -211,6 +211,8 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   QR_CUDA(cudaEventCreate(&c->ev0));
   QR_CUDA(cudaEventCreate(&c->ev1));
+  QR_CUDA(cudaEventCreate(&c->ev_t0));
+  QR_CUDA(cudaEventCreate(&c->ev_t1));
 
   // features -> device column-major (VerticalDataset layout), then bins; floats are released
   float *d_col = nullptr;
@@ -813,6 +815,8 @@ int qr_ctx_destroy(qr_ctx *c) {
   if (c->h_leafval) cudaFreeHost(c->h_leafval);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return QR_OK;
@@ -957,6 +961,20 @@ int qr_phase_times(qr_ctx *c, double ms[6], uint64_t launches[6], int reset) {
     if (launches) launches[i] = c->phase_launches[i];
     if (reset) { c->phase_ms[i] = 0; c->phase_launches[i] = 0; }
   }
+  return QR_OK;
+}
+int qr_timer_start(qr_ctx *c) {
+  QR_CHECK_CTX(c);
+  QR_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+  return QR_OK;
+}
+int qr_timer_stop(qr_ctx *c, double *ms) {
+  QR_CHECK_CTX(c);
+  QR_CUDA(cudaEventRecord(c->ev_t1, c->stream));
+  QR_CUDA(cudaEventSynchronize(c->ev_t1));
+  float f = 0;
+  QR_CUDA(cudaEventElapsedTime(&f, c->ev_t0, c->ev_t1));
+  if (ms) *ms = f;
   return QR_OK;
 }
 int qr_set_profiling(qr_ctx *c, int enabled) {

@@ -33,3 +33,56 @@ def describe_tree_diff(a, b):
 
 def leaves_mask(t):
     return t["feature"] < 0
+
+
+def audit_tree(got, want, binning, bins, lam, minls, rel=1e-12):
+    """Tie audit (hard parts 2 and 6).
+
+    Walks the two pre-order trees together.  Where the split (feature, threshold index) differs,
+    the mismatch is tolerated only if the ORACLE's own score of the two candidates on that node
+    differs by less than `rel` relative, i.e. the reference's choice was decided by rounding.
+    Returns (tolerated, docs_compared): the number of tolerated ties and a boolean mask of the
+    documents whose path never crossed a tolerated node (their leaves must agree exactly)."""
+    n_docs = bins.shape[1]
+    clean = np.ones(n_docs, bool)
+    tolerated = 0
+    stack = [(0, 0, np.arange(n_docs))]
+    while stack:
+        ig, iw, ids = stack.pop()
+        fg, fw = int(got["feature"][ig]), int(want["feature"][iw])
+        if fg < 0 and fw < 0:
+            continue
+        tg = int(got["threshold_idx"][ig]) if fg >= 0 else -1
+        tw = int(want["threshold_idx"][iw]) if fw >= 0 else -1
+        if fg == fw and tg == tw:
+            left = bins[fg, ids] <= tg
+            stack.append((int(got["right"][ig]), int(want["right"][iw]), ids[~left]))
+            stack.append((int(got["left"][ig]), int(want["left"][iw]), ids[left]))
+            continue
+        if fg < 0 or fw < 0:
+            raise AssertionError("node %d/%d: one side is a leaf, the other splits (%d,%d) vs (%d,%d)"
+                                 % (ig, iw, fg, tg, fw, tw))
+        sc = binning.split_scores(lam, ids, minls, [(fg, tg), (fw, tw)])
+        gap = abs(sc[0] - sc[1]) / max(abs(sc[1]), 1e-300)
+        if not (sc[0] >= 0 and gap <= rel):
+            raise AssertionError(
+                "node %d (%d docs): got split (f=%d,t=%d) score %.17g, oracle (f=%d,t=%d) score %.17g, "
+                "relative gap %.3g > %.1g" % (iw, len(ids), fg, tg, sc[0], fw, tw, sc[1], gap, rel))
+        tolerated += 1
+        clean[ids] = False
+    return tolerated, clean
+
+
+def tree_outputs(tree, bins):
+    """Leaf output of every document, walking the flat tree on bins."""
+    n = bins.shape[1]
+    node = np.zeros(n, np.int64)
+    active = tree["feature"][node] >= 0
+    while active.any():
+        f = tree["feature"][node[active]]
+        t = tree["threshold_idx"][node[active]]
+        idx = np.nonzero(active)[0]
+        go_left = bins[f, idx] <= t
+        node[idx] = np.where(go_left, tree["left"][node[idx]], tree["right"][node[idx]])
+        active = tree["feature"][node] >= 0
+    return tree["value"][node]

@@ -133,13 +133,16 @@ def test_fit_tree_reference_mode_is_bit_exact(cfg):
     dict(n=3000, f=20, q=30, gridded=True, nthr=0, leaves=12, minls=1),
     dict(n=3000, f=20, q=30, gridded=False, nthr=0, leaves=8, minls=1),
     dict(n=6000, f=40, q=60, gridded=True, nthr=0, leaves=24, minls=20),
+    dict(n=20000, f=30, q=200, gridded=True, nthr=0, leaves=32, minls=1),
 ])
 def test_fit_tree_fast_mode(cfg):
-    """Fixed-point accumulation: same split indices and doc->leaf map wherever the oracle's own
-    best and runner-up differ by more than rounding; leaf outputs within 1e-5 relative."""
+    """Fixed-point accumulation: same split indices and doc->leaf map, except where the oracle's own
+    best and the GPU's choice score within 1e-12 relative of each other on that node (the reference
+    broke that tie by rounding; see qr_testlib.audit_tree); leaf outputs within 1e-5 relative."""
     x, l, off = common.dataset(n=cfg["n"], f=cfg["f"], q=cfg["q"], gridded=cfg["gridded"])
     lam, w = _gradients(x, l, off, 4)
     ob = po.Binning(np.ascontiguousarray(x.T), cfg["nthr"])
+    bins = ob.bins()
     want = ob.fit_tree(lam, w, nleaves=cfg["leaves"], minls=cfg["minls"])
     with api.Trainer(x, l, off, nleaves=cfg["leaves"], minleafsupport=cfg["minls"],
                      nthresholds=cfg["nthr"], hist_mode=api.HIST_FAST) as tr:
@@ -148,11 +151,15 @@ def test_fit_tree_fast_mode(cfg):
         leaf = tr.get_leaf_assignment()
         got2 = tr.fit_regressor_on_gradient()   # determinism: same answer twice
     assert common.same_structure(got, got2) and np.array_equal(got["value"], got2["value"])
-    assert np.array_equal(leaf, want["leaf_of_doc"]), common.describe_tree_diff(got, want)
-    assert np.array_equal(got["count"], want["count"])
-    lv = common.leaves_mask(want)
-    assert rel_err(got["value"][lv], want["value"][lv]) <= REL
-    assert common.same_structure(got, want), common.describe_tree_diff(got, want)
+    ties, clean = common.audit_tree(got, want, ob, bins, lam, cfg["minls"])
+    assert ties <= 3, "%d rounding-decided ties in one tree" % ties
+    if ties == 0:
+        assert np.array_equal(leaf, want["leaf_of_doc"])
+        assert np.array_equal(got["count"], want["count"])
+    # the tree as a function of the training documents
+    og, ow = common.tree_outputs(got, bins), common.tree_outputs(want, bins)
+    assert rel_err(og[clean], ow[clean]) <= REL
+    assert clean.mean() > 0.9
 
 
 @pytest.mark.parametrize("algo,depth", [("OBVLAMBDAMART", 4), ("OBVMART", 3)])
@@ -179,13 +186,60 @@ def test_oblivious_tree(algo, depth, mode):
 
 @pytest.mark.parametrize("algo", ["LAMBDAMART", "MART", "OBVLAMBDAMART"])
 @pytest.mark.parametrize("mode", [api.HIST_REFERENCE, api.HIST_FAST])
-def test_boosting_loop_follows_oracle(algo, mode):
-    """Free-running training (mart.cc:307-347): tree structure identical, metric within 1e-5."""
-    T = 12
+def test_boosting_loop_stagewise(algo, mode):
+    """Mart::learn's loop body (mart.cc:331-347), iteration by iteration from the oracle's state:
+    lambdas within 1e-13, split indices identical up to audited rounding ties, leaf outputs, scores
+    and NDCG@10 within 1e-5 relative."""
+    T = 10
     x, l, off = common.dataset(n=4000, f=24, q=40)
+    col = np.ascontiguousarray(x.T)
     depth = 3 if algo.startswith("OBV") else 0
-    want_trees, want_metric, want_scores = po.train(algo, x, l, off, T, nleaves=10, depth=depth, cutoff=10)
+    lam_algo = "LAMBDA" in algo
+    ob = po.Binning(col, 0)
+    bins = ob.bins()
+    scores = np.zeros(len(l))
+    ties_total = 0
     with api.Trainer(x, l, off, algo=algo, nleaves=10, treedepth=max(depth, 1), hist_mode=mode) as tr:
+        for m in range(T):
+            if lam_algo:
+                lam, w = po.lambdas(scores, l, off, 10)
+            else:
+                lam, w = l.astype(np.float64) - scores, None
+            want = ob.fit_tree(lam, w, nleaves=(1 << depth) if depth else 10, minls=1, depth=depth)
+            tr.set_scores(scores)
+            tr.compute_pseudoresponses()
+            glam, gw = tr.get_pseudoresponses()
+            assert np.max(np.abs(glam - lam)) <= 1e-13 * np.max(np.abs(lam))
+            got = tr.fit_regressor_on_gradient()
+            if depth:
+                assert common.same_structure(got, want), common.describe_tree_diff(got, want)
+                ties, clean = 0, np.ones(len(l), bool)
+            else:
+                ties, clean = common.audit_tree(got, want, ob, bins, lam, 1)
+            ties_total += ties
+            og, ow = common.tree_outputs(got, bins), common.tree_outputs(want, bins)
+            assert rel_err(og[clean], ow[clean]) <= REL, "tree %d" % m
+            tr.update_modelscores()
+            new_scores = po.update_scores(want, col, 0.1, scores)
+            gs = tr.get_scores()
+            assert np.max(np.abs(gs[clean] - new_scores[clean])) <= REL * np.max(np.abs(new_scores))
+            if ties == 0:
+                metric = tr.evaluate_dataset()
+                want_metric = po.ndcg_dataset(l, new_scores, off, 10)
+                assert abs(metric - want_metric) <= REL * want_metric
+            scores = new_scores
+    assert ties_total <= T
+
+
+@pytest.mark.parametrize("algo", ["LAMBDAMART", "MART"])
+@pytest.mark.parametrize("mode", [api.HIST_REFERENCE, api.HIST_FAST])
+def test_boosting_loop_free_running(algo, mode):
+    """Free-running training with a minimum leaf support that keeps nodes large (no rounding-decided
+    ties): identical split sequence, NDCG@10 trajectory and final scores within 1e-5 relative."""
+    T = 12
+    x, l, off = common.dataset(n=6000, f=24, q=60)
+    want_trees, want_metric, want_scores = po.train(algo, x, l, off, T, nleaves=8, minls=100, cutoff=10)
+    with api.Trainer(x, l, off, algo=algo, nleaves=8, minleafsupport=100, hist_mode=mode) as tr:
         for m in range(T):
             tree, metric = tr.boost_iteration()
             assert common.same_structure(tree, want_trees[m]), \
@@ -193,7 +247,7 @@ def test_boosting_loop_follows_oracle(algo, mode):
             lv = common.leaves_mask(tree)
             assert rel_err(tree["value"][lv], want_trees[m]["value"][lv]) <= REL
             assert abs(metric - want_metric[m]) <= REL * abs(want_metric[m])
-        assert rel_err(tr.get_scores(), want_scores) <= REL
+        assert np.max(np.abs(tr.get_scores() - want_scores)) <= REL * np.max(np.abs(want_scores))
 
 
 def test_stepwise_hooks_equal_fused_iteration():
