@@ -38,39 +38,56 @@ def leaves_mask(t):
 def audit_tree(got, want, binning, bins, lam, minls, rel=1e-12):
     """Tie audit (hard parts 2 and 6).
 
-    Walks the two pre-order trees together.  Where the split (feature, threshold index) differs,
-    the mismatch is tolerated only if the ORACLE's own score of the two candidates on that node
-    differs by less than `rel` relative, i.e. the reference's choice was decided by rounding.
-    Returns (tolerated, docs_compared): the number of tolerated ties and a boolean mask of the
-    documents whose path never crossed a tolerated node (their leaves must agree exactly)."""
+    Walks the two pre-order trees together over the training documents.  Where the split
+    (feature, threshold index) differs, the mismatch is tolerated only if
+      (a) both candidates cut the node's documents into the SAME two sets (possibly mirrored): a tie
+          in exact arithmetic, which the reference breaks by the rounding noise of its cumulative
+          sums (plateaus of empty bins in a right child = parent - left, mirrored single-document
+          cuts, ...).  The walk continues below with the children matched by document set; or
+      (b) the ORACLE's own scores of the two candidates on that node differ by less than `rel`
+          relative (a near-tie the reference decided by rounding).  The walk stops there.
+    Anything else raises.  Returns (equivalent, near, clean): counts of (a) and (b) and the mask
+    of documents whose path never crossed a (b) node."""
     n_docs = bins.shape[1]
     clean = np.ones(n_docs, bool)
-    tolerated = 0
+    equivalent = near = 0
     stack = [(0, 0, np.arange(n_docs))]
     while stack:
         ig, iw, ids = stack.pop()
         fg, fw = int(got["feature"][ig]), int(want["feature"][iw])
         if fg < 0 and fw < 0:
             continue
-        tg = int(got["threshold_idx"][ig]) if fg >= 0 else -1
-        tw = int(want["threshold_idx"][iw]) if fw >= 0 else -1
-        if fg == fw and tg == tw:
-            left = bins[fg, ids] <= tg
-            stack.append((int(got["right"][ig]), int(want["right"][iw]), ids[~left]))
-            stack.append((int(got["left"][ig]), int(want["left"][iw]), ids[left]))
-            continue
         if fg < 0 or fw < 0:
-            raise AssertionError("node %d/%d: one side is a leaf, the other splits (%d,%d) vs (%d,%d)"
-                                 % (ig, iw, fg, tg, fw, tw))
+            raise AssertionError("node %d/%d (%d docs): one side is a leaf, the other splits on %d"
+                                 % (ig, iw, len(ids), max(fg, fw)))
+        tg, tw = int(got["threshold_idx"][ig]), int(want["threshold_idx"][iw])
+        lg = bins[fg, ids] <= tg
+        kids_g = (int(got["left"][ig]), int(got["right"][ig]))
+        kids_w = (int(want["left"][iw]), int(want["right"][iw]))
+        if fg == fw and tg == tw:
+            stack.append((kids_g[1], kids_w[1], ids[~lg]))
+            stack.append((kids_g[0], kids_w[0], ids[lg]))
+            continue
+        lw = bins[fw, ids] <= tw
+        if np.array_equal(lg, lw):
+            equivalent += 1
+            stack.append((kids_g[1], kids_w[1], ids[~lg]))
+            stack.append((kids_g[0], kids_w[0], ids[lg]))
+            continue
+        if np.array_equal(lg, ~lw):
+            equivalent += 1
+            stack.append((kids_g[1], kids_w[0], ids[~lg]))
+            stack.append((kids_g[0], kids_w[1], ids[lg]))
+            continue
         sc = binning.split_scores(lam, ids, minls, [(fg, tg), (fw, tw)])
         gap = abs(sc[0] - sc[1]) / max(abs(sc[1]), 1e-300)
         if not (sc[0] >= 0 and gap <= rel):
             raise AssertionError(
                 "node %d (%d docs): got split (f=%d,t=%d) score %.17g, oracle (f=%d,t=%d) score %.17g, "
                 "relative gap %.3g > %.1g" % (iw, len(ids), fg, tg, sc[0], fw, tw, sc[1], gap, rel))
-        tolerated += 1
+        near += 1
         clean[ids] = False
-    return tolerated, clean
+    return equivalent, near, clean
 
 
 def tree_outputs(tree, bins):

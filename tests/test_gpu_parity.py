@@ -151,15 +151,14 @@ def test_fit_tree_fast_mode(cfg):
         leaf = tr.get_leaf_assignment()
         got2 = tr.fit_regressor_on_gradient()   # determinism: same answer twice
     assert common.same_structure(got, got2) and np.array_equal(got["value"], got2["value"])
-    ties, clean = common.audit_tree(got, want, ob, bins, lam, cfg["minls"])
-    assert ties <= 3, "%d rounding-decided ties in one tree" % ties
-    if ties == 0:
+    equiv, near, clean = common.audit_tree(got, want, ob, bins, lam, cfg["minls"])
+    assert near <= 1, "%d rounding-decided near-ties in one tree" % near
+    if equiv == 0 and near == 0:
         assert np.array_equal(leaf, want["leaf_of_doc"])
         assert np.array_equal(got["count"], want["count"])
     # the tree as a function of the training documents
     og, ow = common.tree_outputs(got, bins), common.tree_outputs(want, bins)
     assert rel_err(og[clean], ow[clean]) <= REL
-    assert clean.mean() > 0.9
 
 
 @pytest.mark.parametrize("algo,depth", [("OBVLAMBDAMART", 4), ("OBVMART", 3)])
@@ -198,7 +197,7 @@ def test_boosting_loop_stagewise(algo, mode):
     ob = po.Binning(col, 0)
     bins = ob.bins()
     scores = np.zeros(len(l))
-    ties_total = 0
+    near_total = 0
     with api.Trainer(x, l, off, algo=algo, nleaves=10, treedepth=max(depth, 1), hist_mode=mode) as tr:
         for m in range(T):
             if lam_algo:
@@ -215,8 +214,8 @@ def test_boosting_loop_stagewise(algo, mode):
                 assert common.same_structure(got, want), common.describe_tree_diff(got, want)
                 ties, clean = 0, np.ones(len(l), bool)
             else:
-                ties, clean = common.audit_tree(got, want, ob, bins, lam, 1)
-            ties_total += ties
+                _equiv, ties, clean = common.audit_tree(got, want, ob, bins, lam, 1)
+            near_total += ties
             og, ow = common.tree_outputs(got, bins), common.tree_outputs(want, bins)
             assert rel_err(og[clean], ow[clean]) <= REL, "tree %d" % m
             tr.update_modelscores()
@@ -228,25 +227,32 @@ def test_boosting_loop_stagewise(algo, mode):
                 want_metric = po.ndcg_dataset(l, new_scores, off, 10)
                 assert abs(metric - want_metric) <= REL * want_metric
             scores = new_scores
-    assert ties_total <= T
+    assert near_total <= 2
 
 
 @pytest.mark.parametrize("algo", ["LAMBDAMART", "MART"])
 @pytest.mark.parametrize("mode", [api.HIST_REFERENCE, api.HIST_FAST])
 def test_boosting_loop_free_running(algo, mode):
-    """Free-running training with a minimum leaf support that keeps nodes large (no rounding-decided
-    ties): identical split sequence, NDCG@10 trajectory and final scores within 1e-5 relative."""
+    """Free-running training with a minimum leaf support that keeps nodes large: every tree cuts the
+    training documents exactly as the oracle's does (split indices identical except inside audited
+    exact-arithmetic ties), NDCG@10 trajectory and final scores within 1e-5 relative."""
     T = 12
     x, l, off = common.dataset(n=6000, f=24, q=60)
+    col = np.ascontiguousarray(x.T)
+    ob = po.Binning(col, 0)
+    bins = ob.bins()
     want_trees, want_metric, want_scores = po.train(algo, x, l, off, T, nleaves=8, minls=100, cutoff=10)
+    scores = np.zeros(len(l))
     with api.Trainer(x, l, off, algo=algo, nleaves=8, minleafsupport=100, hist_mode=mode) as tr:
         for m in range(T):
+            lam = po.lambdas(scores, l, off, 10)[0] if algo == "LAMBDAMART" else l.astype(np.float64) - scores
             tree, metric = tr.boost_iteration()
-            assert common.same_structure(tree, want_trees[m]), \
-                "tree %d: %s" % (m, common.describe_tree_diff(tree, want_trees[m]))
-            lv = common.leaves_mask(tree)
-            assert rel_err(tree["value"][lv], want_trees[m]["value"][lv]) <= REL
+            _equiv, near, _clean = common.audit_tree(tree, want_trees[m], ob, bins, lam, 100)
+            assert near == 0, "tree %d" % m
+            og, ow = common.tree_outputs(tree, bins), common.tree_outputs(want_trees[m], bins)
+            assert rel_err(og, ow) <= REL
             assert abs(metric - want_metric[m]) <= REL * abs(want_metric[m])
+            scores = po.update_scores(want_trees[m], col, 0.1, scores)
         assert np.max(np.abs(tr.get_scores() - want_scores)) <= REL * np.max(np.abs(want_scores))
 
 
