@@ -20,15 +20,11 @@ int comm_allreduce_max_u64(Comm *, unsigned long long *, size_t, cudaStream_t) {
   set_error("multi-GPU support is not built yet");
   return QR_ECOMM;
 }
-int comm_reduce_hist(qr_ctx *, unsigned long long *, uint32_t *, uint32_t *) {
+int comm_reduce_tasks(qr_ctx *, uint32_t) {
   set_error("multi-GPU support is not built yet");
   return QR_ECOMM;
 }
-int comm_local_lcount(qr_ctx *, int) {
-  set_error("multi-GPU support is not built yet");
-  return QR_ECOMM;
-}
-int comm_leaf_fit(qr_ctx *, const LeafSeg *, uint32_t, bool) {
+int comm_leaf_values(qr_ctx *, uint32_t) {
   set_error("multi-GPU support is not built yet");
   return QR_ECOMM;
 }

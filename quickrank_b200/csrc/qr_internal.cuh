@@ -40,7 +40,7 @@ struct SplitResult {
   double sum;         // node sum of pseudo-responses (feature 0, last bin)
   double squares;     // squares_sum_
   double deviance;    // squares - sum^2/n
-  uint64_t n;         // node size (feature 0, last bin)
+  uint64_t n;         // node size (feature 0, last bin); global when several ranks train together
   uint64_t lcount;    // left size at the best split
   uint32_t feature;
   uint32_t threshold_idx;
@@ -49,16 +49,20 @@ struct SplitResult {
 };
 
 struct HostNode {
-  uint32_t lo = 0, n = 0;   // segment [lo, lo+n) of the id buffer `buf`
-  int buf = 0;
+  uint32_t lo = 0, n = 0;   // segment [lo, lo+n) of the id buffer `buf` (local documents)
+  int buf = 0;              // 0 / 1: id buffer; 2: identity list (root)
   int hist = -1;            // histogram slot, -1 once released
   int left = -1, right = -1;
+  bool expanded = false;    // children (and their split scans) have been computed
+  bool pushed = false;      // the heap replay split this node (it is an internal node of the tree)
   SplitResult res{};
   double value = 0.0;       // leaf output
   bool is_leaf() const { return left < 0; }
 };
 
-struct Comm;  // NCCL plumbing (qr_comm.cu)
+struct Comm;      // NCCL plumbing (qr_comm.cu)
+struct NodeTask;  // qr_tree_kernels.cuh
+struct LeafSeg;
 
 }  // namespace qr
 
@@ -99,18 +103,26 @@ struct qr_ctx {
   uint32_t *d_ids[2] = {nullptr, nullptr};  // [N] node document lists (ping-pong)
   uint32_t *d_leaf_of_doc = nullptr;        // [N]
   uint32_t *d_blockcnt = nullptr;           // partition scratch
-  double *d_partials = nullptr;             // reduction scratch
+  double *d_partials = nullptr;             // squares partials [max_tasks][kSqParts]
   unsigned long long *d_hist_sum = nullptr; // [nslots][ncells] int64 (FAST) or double (REFERENCE)
   uint32_t *d_hist_cnt = nullptr;           // [nslots][ncells]
   int nslots = 0;
   std::vector<int> free_slots;
-  double *d_fbest_score = nullptr;          // [2][F]
-  uint32_t *d_fbest_t = nullptr;            // [2][F]
-  qr::SplitResult *d_res = nullptr;         // [2]
-  qr::SplitResult *h_res = nullptr;         // pinned [2]
+  uint32_t max_tasks = 0;                   // node expansions per round
+  qr::NodeTask *d_tasks = nullptr, *h_tasks = nullptr;   // [max_tasks] (host copy pinned)
+  uint32_t *d_lcount = nullptr, *h_lcount = nullptr;     // [max_tasks] local left counts
+  double *d_fbest_score = nullptr;          // [max_tasks][2][F]
+  uint32_t *d_fbest_t = nullptr;            // [max_tasks][2][F]
+  qr::SplitResult *d_res = nullptr;         // [max_tasks][2]
+  qr::SplitResult *h_res = nullptr;         // pinned
+  qr::LeafSeg *d_segs = nullptr, *h_segs = nullptr;      // [maxleaves]
+  double2 *d_leaf_partials = nullptr;       // [N / kLeafItems + maxleaves]
+  double2 *d_leafsum = nullptr;             // [maxleaves] (sum lambda, sum weight)
   double *d_leafval = nullptr;              // [maxleaves]
   double *h_leafval = nullptr;              // pinned
   double *d_obv_scores = nullptr;           // [ncells] oblivious level sums
+  int *d_obv_slots = nullptr;               // [max_tasks]
+  uint64_t *d_obv_lcounts = nullptr, *h_obv_lcounts = nullptr;  // [max_tasks]
   uint32_t maxlen = 0;                      // longest query
 
   bool ranking_valid = false;  // d_rankpos/d_qndcg match d_scores
@@ -118,7 +130,7 @@ struct qr_ctx {
   std::vector<qr::HostNode> nodes;  // last fitted tree
   std::vector<int> leaves;          // node ids in DFS order
   double rho = 0, sigma = 0;
-  uint32_t nsplits = 0;
+  uint32_t nsplits = 0, nrounds = 0;
 
   uint64_t launches = 0;
   bool profiling = false;

@@ -514,540 +514,5 @@ __global__ void quantize_kernel(const double *lam, size_t N, const int *qexp, lo
   if (i < N) lamq[i] = __double2ll_rn(ldexp(lam[i], *qexp));
 }
 
-// ------------------------------------------------------------------------------------------
-// Histograms.  cell(f, t) = thr_off[f] + t.
-// FAST: RTNodeHistogram::update / RTNodeHistogram(parent, sampleids, ...) scatter loops
-// (rtnode_histogram.cc:51-58, 183-191) as 64-bit fixed-point atomics staged in shared memory,
-// one block per (panel, document slice); lanes walk the 16 features of a row in rotated order so
-// that the 32 lanes of a warp hit different features' bins.
-// ------------------------------------------------------------------------------------------
-template <typename BinT, bool DENSE, bool SMEM>
-__global__ void __launch_bounds__(256)
-hist_fast_kernel(const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ ids,
-                 uint32_t lo, uint32_t n, const long long *__restrict__ lamq,
-                 const uint32_t *__restrict__ thr_off, uint32_t F, unsigned long long *gsum,
-                 uint32_t *gcnt, uint32_t docs_per_block) {
-  constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_base[FPP];
-  const uint32_t p = blockIdx.y;
-  const uint32_t f0 = p * FPP;
-  const uint32_t nf = min(FPP, F - f0);
-  const uint32_t cell0 = thr_off[f0];
-  const uint32_t cells = thr_off[f0 + nf] - cell0;
-  unsigned long long *s_sum = reinterpret_cast<unsigned long long *>(smem_raw);
-  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_sum + (SMEM ? cells : 0));
-  if (threadIdx.x < FPP)
-    s_base[threadIdx.x] = threadIdx.x < nf ? thr_off[f0 + threadIdx.x] - cell0 : 0u;
-  if (SMEM) {
-    for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) { s_sum[i] = 0ull; s_cnt[i] = 0u; }
-  }
-  __syncthreads();
-  const uint32_t begin = blockIdx.x * docs_per_block;
-  const uint32_t end = min(n, begin + docs_per_block);
-  const uint32_t rot = lane_id() & (FPP - 1);
-  const uint4 *prow = panels + (size_t) p * N;
-  unsigned long long *sum_base = SMEM ? s_sum : gsum + cell0;
-  uint32_t *cnt_base = SMEM ? s_cnt : gcnt + cell0;
-  for (uint32_t i = begin + threadIdx.x; i < end; i += blockDim.x) {
-    const uint32_t d = DENSE ? lo + i : ids[lo + i];
-    const uint4 row = rotate_bytes(prow[d], rot * (uint32_t) sizeof(BinT));
-    const unsigned long long qv = (unsigned long long) lamq[d];
-#pragma unroll
-    for (int j = 0; j < (int) FPP; ++j) {
-      const uint32_t slot = (j + rot) & (FPP - 1);
-      if (slot < nf) {
-        const uint32_t cell = s_base[slot] + extract_bin<BinT>(row, j);
-        atomicAdd(sum_base + cell, qv);
-        atomicAdd(cnt_base + cell, 1u);
-      }
-    }
-  }
-  if (SMEM) {
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) {
-      const uint32_t cn = s_cnt[i];
-      if (cn) {
-        atomicAdd(gsum + cell0 + i, s_sum[i]);
-        atomicAdd(gcnt + cell0 + i, cn);
-      }
-    }
-  }
-}
-
-// REFERENCE order: one warp per feature walks the node's documents in list order; documents of a
-// 32-wide chunk that fall in the same bin are added one after the other in document order
-// (__match_any_sync ranks them), so every per-bin FP64 sum sees its addends in the sequence the
-// reference's loop does (rtnode_histogram.cc:51-58).  Then the sequential inclusive prefix over
-// bins (rtnode_histogram.cc:59-62).  gsum/gcnt rows must be zero on entry.
-template <typename BinT, bool DENSE>
-__global__ void __launch_bounds__(128)
-hist_exact_kernel(const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ ids,
-                  uint32_t lo, uint32_t n, const double *__restrict__ lam,
-                  const uint32_t *__restrict__ thr_off, uint32_t F, double *gsum, uint32_t *gcnt) {
-  const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (f >= F) return;
-  const uint32_t lane = lane_id();
-  double *sum = gsum + thr_off[f];
-  uint32_t *cnt = gcnt + thr_off[f];
-  const uint32_t cells = thr_off[f + 1] - thr_off[f];
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t i = base + lane;
-    const bool act = i < n;
-    uint32_t b = 0xffffffffu;   // inactive lanes share a bin no document can have
-    double v = 0.0;
-    if (act) {
-      const uint32_t d = DENSE ? lo + i : ids[lo + i];
-      b = load_bin<BinT>(panels, N, f, d);
-      v = lam[d];
-    }
-    const uint32_t peers = __match_any_sync(0xffffffffu, b);
-    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    uint32_t maxr = act ? __popc(peers) : 0u;
-    for (int o = 16; o > 0; o >>= 1) maxr = max(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
-    for (uint32_t r = 0; r < maxr; ++r) {
-      if (act && rank == r) { sum[b] += v; cnt[b] += 1u; }
-      __syncwarp();
-    }
-  }
-  __syncwarp();
-  if (lane == 0) {
-    for (uint32_t t = 1; t < cells; ++t) { sum[t] += sum[t - 1]; cnt[t] += cnt[t - 1]; }
-  }
-}
-
-// squares_sum_ (rtnode_histogram.cc:65-69, 199-203), sequential in list order.  One warp.
-template <bool DENSE>
-__global__ void squares_exact_kernel(const double *__restrict__ lam, const uint32_t *__restrict__ ids,
-                                     uint32_t lo, uint32_t n, bool fused, double *out) {
-  const uint32_t lane = lane_id();
-  double acc = 0.0;
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t i = base + lane;
-    double v = 0.0;
-    if (i < n) v = lam[DENSE ? lo + i : ids[lo + i]];
-    const uint32_t cntk = min(32u, n - base);
-    if (fused) {
-      for (uint32_t k = 0; k < cntk; ++k) { const double vk = __shfl_sync(0xffffffffu, v, k); acc = fma(vk, vk, acc); }
-    } else {
-      for (uint32_t k = 0; k < cntk; ++k) { const double vk = __shfl_sync(0xffffffffu, v, k); acc = __dadd_rn(acc, __dmul_rn(vk, vk)); }
-    }
-  }
-  if (lane == 0) out[0] = acc;
-}
-
-// FAST: deterministic two-level sum of squares (fixed grid, fixed tree shape).
-template <bool DENSE>
-__global__ void __launch_bounds__(256)
-squares_fast_kernel(const double *__restrict__ lam, const uint32_t *__restrict__ ids, uint32_t lo,
-                    uint32_t n, double *partials) {
-  __shared__ double part[256];
-  const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
-  const uint32_t b = blockIdx.x * per, e = min(n, b + per);
-  double acc = 0.0;
-  for (uint32_t i = b + threadIdx.x; i < e; i += 256) {
-    const double v = lam[DENSE ? lo + i : ids[lo + i]];
-    acc = fma(v, v, acc);
-  }
-  part[threadIdx.x] = acc;
-  __syncthreads();
-  for (uint32_t st = 128; st > 0; st >>= 1) {
-    if (threadIdx.x < st) part[threadIdx.x] += part[threadIdx.x + st];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) partials[blockIdx.x] = part[0];
-}
-
-// ------------------------------------------------------------------------------------------
-// Finalize: cumulative histograms, right = parent - left (rtnode_histogram.cc:59-62, 79-85,
-// 209-216) and the split scan of every (feature, threshold) (rt.cc:257-292).  One block per
-// feature.  mode 0: node `L` alone (root); mode 1: children L (built from samples) and
-// R = P - L.  Per-feature winners go to fbest_*[child][f].
-// ------------------------------------------------------------------------------------------
-struct FinalizeArgs {
-  unsigned long long *hsum;   // all slots
-  uint32_t *hcnt;
-  uint32_t ncells;
-  int slotP, slotL, slotR;
-  int mode;
-  uint32_t minls;
-  const int *qexp;            // FAST: fixed-point exponent
-  double *fbest_score;        // [2][F]
-  uint32_t *fbest_t;          // [2][F]
-  uint32_t F;
-};
-
-__device__ __forceinline__ double cell_value(bool exact, unsigned long long raw, double inv) {
-  return exact ? __longlong_as_double((long long) raw) : (double) (long long) raw * inv;
-}
-
-template <bool EXACT>
-__global__ void __launch_bounds__(256)
-finalize_kernel(FinalizeArgs a, const uint32_t *__restrict__ thr_off) {
-  const uint32_t f = blockIdx.x;
-  const uint32_t c0 = thr_off[f], cells = thr_off[f + 1] - c0;
-  unsigned long long *Ls = a.hsum + (size_t) a.slotL * a.ncells + c0;
-  uint32_t *Lc = a.hcnt + (size_t) a.slotL * a.ncells + c0;
-  __shared__ long long w_sum[8];
-  __shared__ uint32_t w_cnt[8];
-  __shared__ long long carry_sum;
-  __shared__ uint32_t carry_cnt;
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-
-  if (!EXACT) {
-    // inclusive scan of the raw (per-bin) fixed-point sums and counts, tiles of 256 bins
-    if (threadIdx.x == 0) { carry_sum = 0; carry_cnt = 0; }
-    __syncthreads();
-    for (uint32_t t0 = 0; t0 < cells; t0 += 256) {
-      const uint32_t t = t0 + threadIdx.x;
-      long long v = t < cells ? (long long) Ls[t] : 0;
-      uint32_t cv = t < cells ? Lc[t] : 0u;
-      for (int o = 1; o < 32; o <<= 1) {
-        long long pv = __shfl_up_sync(0xffffffffu, v, o);
-        uint32_t pc = __shfl_up_sync(0xffffffffu, cv, o);
-        if ((int) lane >= o) { v += pv; cv += pc; }
-      }
-      if (lane == 31) { w_sum[warp] = v; w_cnt[warp] = cv; }
-      __syncthreads();
-      long long add = carry_sum;
-      uint32_t addc = carry_cnt;
-      for (uint32_t w = 0; w < warp; ++w) { add += w_sum[w]; addc += w_cnt[w]; }
-      v += add; cv += addc;
-      if (t < cells) { Ls[t] = (unsigned long long) v; Lc[t] = cv; }
-      __syncthreads();
-      if (threadIdx.x == 255) { carry_sum = v; carry_cnt = cv; }
-      __syncthreads();
-    }
-  }
-  __syncthreads();
-  const double inv = EXACT ? 1.0 : ldexp(1.0, -*a.qexp);
-
-  for (int child = 0; child < (a.mode == 0 ? 1 : 2); ++child) {
-    unsigned long long *S = Ls;
-    uint32_t *C = Lc;
-    if (child == 1) {
-      const unsigned long long *Ps = a.hsum + (size_t) a.slotP * a.ncells + c0;
-      const uint32_t *Pc = a.hcnt + (size_t) a.slotP * a.ncells + c0;
-      S = a.hsum + (size_t) a.slotR * a.ncells + c0;
-      C = a.hcnt + (size_t) a.slotR * a.ncells + c0;
-      for (uint32_t t = threadIdx.x; t < cells; t += 256) {
-        if (EXACT) {
-          const double pv = __longlong_as_double((long long) Ps[t]);
-          const double lv = __longlong_as_double((long long) Ls[t]);
-          S[t] = (unsigned long long) __double_as_longlong(pv - lv);   // rtnode_histogram.cc:82
-        } else {
-          S[t] = Ps[t] - Ls[t];
-        }
-        C[t] = Pc[t] - Lc[t];
-      }
-      __syncthreads();
-    }
-    // split scan (rt.cc:272-291): strict '>' in ascending t, start value -1
-    const double s = cell_value(EXACT, S[cells - 1], inv);
-    const uint32_t cn = C[cells - 1];
-    double best = -1.0;
-    uint32_t best_t = 0xffffffffu;
-    for (uint32_t t = threadIdx.x; t < cells; t += 256) {
-      const uint32_t lc = C[t], rc = cn - lc;
-      if (lc >= a.minls && rc >= a.minls) {
-        const double ls = cell_value(EXACT, S[t], inv);
-        const double rs = s - ls;
-        const double score = ls * ls / (double) lc + rs * rs / (double) rc;
-        if (score > best) { best = score; best_t = t; }
-      }
-    }
-    // block arg-max, ties to the smaller t
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const uint32_t ot = __shfl_xor_sync(0xffffffffu, best_t, o);
-      if (ob > best || (ob == best && ot < best_t)) { best = ob; best_t = ot; }
-    }
-    __shared__ double wb[8];
-    __shared__ uint32_t wt[8];
-    if (lane == 0) { wb[warp] = best; wt[warp] = best_t; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; ++w)
-        if (wb[w] > best || (wb[w] == best && wt[w] < best_t)) { best = wb[w]; best_t = wt[w]; }
-      a.fbest_score[child * a.F + f] = best;
-      a.fbest_t[child * a.F + f] = best_t;
-    }
-    __syncthreads();
-  }
-}
-
-// Arg-max over features (first maximum wins: rt.cc:297-306 with GCC's static schedule) and the
-// node statistics of RTNode(sampleids, hist) (rtnode.h:97-107).
-struct Finalize2Args {
-  const unsigned long long *hsum;
-  const uint32_t *hcnt;
-  uint32_t ncells;
-  int slotL, slotR, mode;
-  const int *qexp;
-  const double *fbest_score;
-  const uint32_t *fbest_t;
-  uint32_t F;
-  const double *sq_partials;   // left (or root) squares partials
-  uint32_t n_partials;
-  double parent_squares;
-  SplitResult *res;            // [2]
-};
-
-template <bool EXACT>
-__global__ void finalize2_kernel(Finalize2Args a, const uint32_t *__restrict__ thr_off) {
-  if (threadIdx.x != 0) return;
-  const double inv = EXACT ? 1.0 : ldexp(1.0, -*a.qexp);
-  double sqL = 0.0;
-  for (uint32_t i = 0; i < a.n_partials; ++i) sqL += a.sq_partials[i];
-  for (int child = 0; child < (a.mode == 0 ? 1 : 2); ++child) {
-    const int slot = child == 0 ? a.slotL : a.slotR;
-    const unsigned long long *S = a.hsum + (size_t) slot * a.ncells;
-    const uint32_t *C = a.hcnt + (size_t) slot * a.ncells;
-    double best = -1.0;
-    uint32_t bf = 0xffffffffu, bt = 0xffffffffu;
-    for (uint32_t f = 0; f < a.F; ++f) {
-      const double sc = a.fbest_score[child * a.F + f];
-      if (sc > best) { best = sc; bf = f; bt = a.fbest_t[child * a.F + f]; }
-    }
-    SplitResult r;
-    const uint32_t last0 = thr_off[1] - 1;
-    r.n = C[last0];
-    r.sum = cell_value(EXACT, S[last0], inv);
-    r.squares = child == 0 ? sqL : a.parent_squares - sqL;      // rtnode_histogram.cc:86,207
-    r.deviance = r.squares - r.sum * r.sum / (double) r.n;       // rtnode.h:106
-    r.score = best;
-    r.valid = best != -1.0;
-    r.feature = bf;
-    r.threshold_idx = bt;
-    r.lcount = r.valid ? C[thr_off[bf] + bt] : 0;
-    r.pad = 0;
-    a.res[child] = r;
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Stable partition of a node's document list by bin(f*, doc) <= t*  (rt.cc:325-334; equal to the
-// reference's float test because thresholds are ascending, SURVEY.md section 7.1 "Bins").
-// ------------------------------------------------------------------------------------------
-constexpr uint32_t kPartItems = 2048;  // documents per block
-
-template <typename BinT, bool DENSE>
-__global__ void __launch_bounds__(256)
-partition_count_kernel(const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ src,
-                       uint32_t lo, uint32_t n, uint32_t f, uint32_t t, uint32_t *blockcnt) {
-  const uint32_t b0 = blockIdx.x * kPartItems, e = min(n, b0 + kPartItems);
-  uint32_t c = 0;
-  for (uint32_t i = b0 + threadIdx.x; i < e; i += 256) {
-    const uint32_t d = DENSE ? lo + i : src[lo + i];
-    c += load_bin<BinT>(panels, N, f, d) <= t;
-  }
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  __shared__ uint32_t w[8];
-  if (lane_id() == 0) w[threadIdx.x >> 5] = c;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t s = 0;
-    for (int k = 0; k < 8; ++k) s += w[k];
-    blockcnt[blockIdx.x] = s;
-  }
-}
-
-template <typename BinT, bool DENSE>
-__global__ void __launch_bounds__(256)
-partition_scatter_kernel(const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ src,
-                         uint32_t *__restrict__ dst, uint32_t lo, uint32_t n, uint32_t f, uint32_t t,
-                         const uint32_t *__restrict__ blockcnt, uint32_t lcount) {
-  __shared__ uint32_t red[8];
-  __shared__ uint32_t s_left_base;
-  __shared__ uint32_t wcnt[8];
-  // exclusive prefix of the per-block left counts
-  uint32_t acc = 0;
-  for (uint32_t b = threadIdx.x; b < blockIdx.x; b += 256) acc += blockcnt[b];
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane_id() == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t s = 0;
-    for (int k = 0; k < 8; ++k) s += red[k];
-    s_left_base = s;
-  }
-  __syncthreads();
-  const uint32_t b0 = blockIdx.x * kPartItems, e = min(n, b0 + kPartItems);
-  uint32_t left_run = s_left_base;                 // lefts before the current round
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  for (uint32_t r0 = b0; r0 < e; r0 += 256) {
-    const uint32_t i = r0 + threadIdx.x;
-    const bool act = i < e;
-    uint32_t d = 0;
-    bool goes_left = false;
-    if (act) {
-      d = DENSE ? lo + i : src[lo + i];
-      goes_left = load_bin<BinT>(panels, N, f, d) <= t;
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, goes_left);
-    if (lane == 0) wcnt[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t before = 0, total = 0;
-    for (uint32_t w = 0; w < 8; ++w) { if (w < warp) before += wcnt[w]; total += wcnt[w]; }
-    const uint32_t lrank = left_run + before + __popc(bal & ((1u << lane) - 1u));
-    if (act) {
-      if (goes_left) dst[lo + lrank] = d;
-      else dst[lo + lcount + (i - lrank)] = d;     // rights before i = i - lefts before i
-    }
-    left_run += total;
-    __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Leaf outputs (RegressionTree::update_output, rt.cc:165-207) and score update
-// (Mart::update_modelscores, mart.cc:459-468).
-// ------------------------------------------------------------------------------------------
-struct LeafSeg { uint32_t lo, n; int buf; int pad; };
-
-__global__ void __launch_bounds__(256)
-leaf_fit_kernel(const LeafSeg *__restrict__ segs, const uint32_t *__restrict__ ids0,
-                const uint32_t *__restrict__ ids1, bool root_only, const double *__restrict__ lam,
-                const double *__restrict__ wgt, bool exact, double *leafval,
-                uint32_t *__restrict__ leaf_of_doc) {
-  const uint32_t leaf = blockIdx.x;
-  const LeafSeg sg = segs[leaf];
-  const uint32_t *ids = sg.buf ? ids1 : ids0;
-  __shared__ double p1[256], p2[256];
-  // leaf assignment (DFS leaf index per document)
-  for (uint32_t i = threadIdx.x; i < sg.n; i += 256) {
-    const uint32_t d = root_only ? sg.lo + i : ids[sg.lo + i];
-    leaf_of_doc[d] = leaf;
-  }
-  double s1 = 0.0, s2 = 0.0;
-  if (exact) {
-    if (threadIdx.x >= 32) return;
-    const uint32_t lane = lane_id();
-    for (uint32_t base = 0; base < sg.n; base += 32) {
-      const uint32_t i = base + lane;
-      double v = 0.0, w = 0.0;
-      if (i < sg.n) {
-        const uint32_t d = root_only ? sg.lo + i : ids[sg.lo + i];
-        v = lam[d];
-        if (wgt) w = wgt[d];
-      }
-      const uint32_t cntk = min(32u, sg.n - base);
-      for (uint32_t k = 0; k < cntk; ++k) {
-        s1 += __shfl_sync(0xffffffffu, v, k);
-        s2 += __shfl_sync(0xffffffffu, w, k);
-      }
-    }
-  } else {
-    for (uint32_t i = threadIdx.x; i < sg.n; i += 256) {
-      const uint32_t d = root_only ? sg.lo + i : ids[sg.lo + i];
-      s1 += lam[d];
-      if (wgt) s2 += wgt[d];
-    }
-    p1[threadIdx.x] = s1; p2[threadIdx.x] = s2;
-    __syncthreads();
-    for (uint32_t st = 128; st > 0; st >>= 1) {
-      if (threadIdx.x < st) { p1[threadIdx.x] += p1[threadIdx.x + st]; p2[threadIdx.x] += p2[threadIdx.x + st]; }
-      __syncthreads();
-    }
-    s1 = p1[0]; s2 = p2[0];
-  }
-  if (threadIdx.x == 0) {
-    if (wgt) leafval[leaf] = s2 >= DBL_EPSILON ? s1 / s2 : 0.0;   // rt.cc:200
-    else leafval[leaf] = s1 / (double) sg.n;                      // rt.cc:178
-  }
-}
-
-__global__ void update_scores_kernel(const uint32_t *__restrict__ leaf_of_doc,
-                                     const double *__restrict__ leafval, double weight, size_t N,
-                                     double *scores) {
-  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) scores[i] = fma(weight, leafval[leaf_of_doc[i]], scores[i]);   // mart.cc:466 (fused)
-}
-
-// scores[i] += weight * tree(doc_i) for an arbitrary tree expressed on this context's bins
-// (Dart::update_modelscores, dart.cc:634-650).
-struct DevTree { const int32_t *feature; const uint32_t *tidx; const int32_t *left, *right; const double *value; };
-
-template <typename BinT>
-__global__ void apply_tree_kernel(const uint4 *__restrict__ panels, size_t N, DevTree t, double weight,
-                                  double *scores) {
-  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  int32_t nd = 0;
-  while (t.feature[nd] >= 0)
-    nd = load_bin<BinT>(panels, N, (uint32_t) t.feature[nd], (uint32_t) i) <= t.tidx[nd] ? t.left[nd] : t.right[nd];
-  scores[i] = fma(weight, t.value[nd], scores[i]);
-}
-
-// ------------------------------------------------------------------------------------------
-// Oblivious trees (ObliviousRT::fit / fill, ot.cc:32-201): per level, sum the split gain of every
-// (f, t) over the level's nodes in node order; a cell is invalid as soon as one node violates the
-// minimum leaf support; the single best cell (> 0, first maximum) splits every node.
-// ------------------------------------------------------------------------------------------
-template <bool EXACT>
-__global__ void obv_level_kernel(const unsigned long long *__restrict__ hsum, const uint32_t *__restrict__ hcnt,
-                                 uint32_t ncells, const int *__restrict__ slots, uint32_t nnodes,
-                                 const uint32_t *__restrict__ thr_off, uint32_t F, uint32_t minls,
-                                 const int *qexp, double *cell_score) {
-  const uint32_t f = blockIdx.x;
-  const uint32_t c0 = thr_off[f], cells = thr_off[f + 1] - c0;
-  const double inv = EXACT ? 1.0 : ldexp(1.0, -*qexp);
-  const double invalid = -DBL_MAX;
-  for (uint32_t t = threadIdx.x; t < cells; t += blockDim.x) {
-    double acc = 0.0;
-    for (uint32_t k = 0; k < nnodes; ++k) {
-      const unsigned long long *S = hsum + (size_t) slots[k] * ncells + c0;
-      const uint32_t *C = hcnt + (size_t) slots[k] * ncells + c0;
-      if (acc != invalid) {
-        const uint32_t cn = C[cells - 1], lc = C[t], rc = cn - lc;
-        if (lc >= minls && rc >= minls) {
-          const double s = cell_value(EXACT, S[cells - 1], inv);
-          const double ls = cell_value(EXACT, S[t], inv);
-          const double rs = s - ls;
-          acc += ls * ls / (double) lc + rs * rs / (double) rc;   // ot.cc:194-195
-        } else {
-          acc = invalid;
-        }
-      }
-    }
-    cell_score[c0 + t] = acc;
-  }
-}
-
-// first maximum strictly greater than 0 (ot.cc:72-96); also gathers each node's left count
-__global__ void obv_argmax_kernel(const double *__restrict__ cell_score, const uint32_t *__restrict__ thr_off,
-                                  uint32_t F, const uint32_t *__restrict__ hcnt, uint32_t ncells,
-                                  const int *__restrict__ slots, uint32_t nnodes, SplitResult *res,
-                                  uint64_t *lcounts) {
-  __shared__ double sb[256];
-  __shared__ uint32_t sc[256];
-  const uint32_t total = thr_off[F];
-  double best = 0.0;
-  uint32_t bc = 0xffffffffu;
-  const uint32_t per = (total + blockDim.x - 1) / blockDim.x;
-  const uint32_t b = threadIdx.x * per, e = min(total, b + per);
-  for (uint32_t c = b; c < e; ++c) {
-    const double v = cell_score[c];
-    if (v != -DBL_MAX && v > best) { best = v; bc = c; }
-  }
-  sb[threadIdx.x] = best; sc[threadIdx.x] = bc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (uint32_t k = 1; k < blockDim.x; ++k)
-      if (sb[k] > best) { best = sb[k]; bc = sc[k]; }   // chunks ascend with k: first maximum wins
-    SplitResult r{};
-    r.score = best;
-    r.valid = bc != 0xffffffffu && best != 0.0;
-    if (r.valid) {
-      uint32_t f = 0;
-      while (thr_off[f + 1] <= bc) ++f;
-      r.feature = f;
-      r.threshold_idx = bc - thr_off[f];
-      for (uint32_t k = 0; k < nnodes; ++k)
-        lcounts[k] = hcnt[(size_t) slots[k] * ncells + bc];
-    }
-    res[0] = r;
-  }
-}
 
 }  // namespace qr

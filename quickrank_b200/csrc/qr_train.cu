@@ -14,7 +14,7 @@
 #include <cub/cub.cuh>
 
 #include "qr_comm.cuh"
-#include "qr_kernels.cuh"
+#include "qr_tree_kernels.cuh"
 
 namespace qr {
 
@@ -285,16 +285,17 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_ids[0], N));
   QR_TRY(dev_alloc(&c->d_ids[1], N));
   QR_TRY(dev_alloc(&c->d_leaf_of_doc, N));
-  QR_TRY(dev_alloc(&c->d_blockcnt, (N + kPartItems - 1) / kPartItems + 1));
-  QR_TRY(dev_alloc(&c->d_partials, 1024));
   QR_CUDA(cudaMemset(c->d_scores, 0, N * sizeof(double)));
   QR_CUDA(cudaMemset(c->d_lambda, 0, N * sizeof(double)));
   QR_CUDA(cudaMemset(c->d_weight, 0, N * sizeof(double)));
   QR_CUDA(cudaMemset(c->d_leaf_of_doc, 0, N * sizeof(uint32_t)));
   QR_CUDA(cudaMemset(c->d_qexp, 0, sizeof(int)));
 
-  const size_t maxleaves = c->oblivious ? ((size_t) 1 << params->treedepth) : params->nleaves;
-  c->nslots = (int) (c->oblivious ? 3 * maxleaves / 2 + 4 : 2 * maxleaves + 4);
+  const size_t maxleaves = c->oblivious ? ((size_t) 1 << params->treedepth) : std::max<size_t>(params->nleaves, 1);
+  c->max_tasks = (uint32_t) maxleaves + 1;
+  // every expansion holds two child histograms until the node is popped or the tree is finished;
+  // speculative expansions (qr_tree_host.cuh) can double the number of live nodes
+  c->nslots = (int) (4 * maxleaves + 8);
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
   const size_t hist_bytes = (size_t) c->nslots * c->ncells * 12;
@@ -306,22 +307,34 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_hist_sum, (size_t) c->nslots * c->ncells));
   QR_TRY(dev_alloc(&c->d_hist_cnt, (size_t) c->nslots * c->ncells));
   for (int i = c->nslots - 1; i >= 0; --i) c->free_slots.push_back(i);
-  QR_TRY(dev_alloc(&c->d_fbest_score, 2 * F));
-  QR_TRY(dev_alloc(&c->d_fbest_t, 2 * F));
-  QR_TRY(dev_alloc(&c->d_res, 2));
-  QR_CUDA(cudaMallocHost((void **) &c->h_res, 2 * sizeof(SplitResult)));
+  const size_t mt = c->max_tasks;
+  QR_TRY(dev_alloc(&c->d_blockcnt, (N + kPartItems - 1) / kPartItems + mt + 1));
+  QR_TRY(dev_alloc(&c->d_partials, mt * kSqParts));
+  QR_TRY(dev_alloc(&c->d_tasks, mt));
+  QR_CUDA(cudaMallocHost((void **) &c->h_tasks, mt * sizeof(NodeTask)));
+  QR_TRY(dev_alloc(&c->d_lcount, mt));
+  QR_CUDA(cudaMallocHost((void **) &c->h_lcount, mt * sizeof(uint32_t)));
+  QR_TRY(dev_alloc(&c->d_fbest_score, mt * 2 * F));
+  QR_TRY(dev_alloc(&c->d_fbest_t, mt * 2 * F));
+  QR_TRY(dev_alloc(&c->d_res, mt * 2));
+  QR_CUDA(cudaMallocHost((void **) &c->h_res, mt * 2 * sizeof(SplitResult)));
+  QR_TRY(dev_alloc(&c->d_segs, maxleaves + 1));
+  QR_CUDA(cudaMallocHost((void **) &c->h_segs, (maxleaves + 1) * sizeof(LeafSeg)));
+  QR_TRY(dev_alloc(&c->d_leaf_partials, (N + kLeafItems - 1) / kLeafItems + maxleaves + 1));
+  QR_TRY(dev_alloc(&c->d_leafsum, maxleaves + 1));
   QR_TRY(dev_alloc(&c->d_leafval, maxleaves + 1));
   QR_CUDA(cudaMallocHost((void **) &c->h_leafval, (maxleaves + 1) * sizeof(double)));
   QR_TRY(dev_alloc(&c->d_obv_scores, c->ncells));
+  QR_TRY(dev_alloc(&c->d_obv_slots, mt));
+  QR_TRY(dev_alloc(&c->d_obv_lcounts, mt));
+  QR_CUDA(cudaMallocHost((void **) &c->h_obv_lcounts, mt * sizeof(uint64_t)));
 
   // opt in to large dynamic shared memory where needed
   const size_t hist_smem = (size_t) c->max_panel_cells * 12;
   if (hist_smem <= 200 * 1024) {
     const int bytes = (int) hist_smem;
-    cudaFuncSetAttribute(hist_fast_kernel<uint8_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(hist_fast_kernel<uint8_t, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(hist_fast_kernel<uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(hist_fast_kernel<uint16_t, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   }
   QR_CUDA(cudaGetLastError());
   return QR_OK;
@@ -392,380 +405,7 @@ static int evaluate(qr_ctx *c, double *metric) {
   return QR_OK;
 }
 
-// ------------------------------------------------------------------------------------------
-// tree growth
-// ------------------------------------------------------------------------------------------
-template <typename F>
-static int dispatch_bins(const qr_ctx *c, F &&fn) {
-  return c->bin_bytes == 1 ? fn(uint8_t()) : fn(uint16_t());
-}
-
-static int alloc_slot(qr_ctx *c) {
-  if (c->free_slots.empty()) return -1;
-  int s = c->free_slots.back();
-  c->free_slots.pop_back();
-  return s;
-}
-static void release_slot(qr_ctx *c, int &s) {
-  if (s >= 0) c->free_slots.push_back(s);
-  s = -1;
-}
-
-static int prepare_fixed_point(qr_ctx *c) {
-  if (c->exact) return QR_OK;
-  PhaseTimer pt(c, PH_HIST);
-  QR_CUDA(cudaMemsetAsync(c->d_maxabs, 0, sizeof(unsigned long long), c->stream));
-  QR_LAUNCH(c, PH_HIST, maxabs_kernel, 296, 256, 0, c->d_lambda, c->N, c->d_maxabs);
-  if (c->comm) QR_TRY(comm_allreduce_max_u64(c->comm, c->d_maxabs, 1, c->stream));
-  QR_LAUNCH(c, PH_HIST, choose_scale_kernel, 1, 1, 0, c->d_maxabs, ceil_log2(c->N_global) + 1, c->d_qexp);
-  QR_LAUNCH(c, PH_HIST, quantize_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_lambda, c->N,
-            c->d_qexp, c->d_lamq);
-  return QR_OK;
-}
-
-// histogram of the documents ids[buf][lo, lo+n) (dense: documents lo..lo+n-1) into `slot`
-// (+ squares partials into d_partials; returns their count)
-static int build_hist(qr_ctx *c, int slot, bool dense, int buf, uint32_t lo, uint32_t n, bool root,
-                      uint32_t *n_partials) {
-  unsigned long long *hs = c->d_hist_sum + (size_t) slot * c->ncells;
-  uint32_t *hc = c->d_hist_cnt + (size_t) slot * c->ncells;
-  const uint32_t *ids = c->d_ids[buf];
-  PhaseTimer pt(c, PH_HIST);
-  QR_CUDA(cudaMemsetAsync(hs, 0, (size_t) c->ncells * 8, c->stream));
-  QR_CUDA(cudaMemsetAsync(hc, 0, (size_t) c->ncells * 4, c->stream));
-  const uint32_t F = (uint32_t) c->F;
-  if (c->exact) {
-    const unsigned grid = (F + 3) / 4;
-    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
-      using B = decltype(tag);
-      if (dense) QR_LAUNCH(c, PH_HIST, (hist_exact_kernel<B, true>), grid, 128, 0, c->d_panels, c->N, ids, lo, n, c->d_lambda, c->d_thr_off, F, (double *) hs, hc);
-      else QR_LAUNCH(c, PH_HIST, (hist_exact_kernel<B, false>), grid, 128, 0, c->d_panels, c->N, ids, lo, n, c->d_lambda, c->d_thr_off, F, (double *) hs, hc);
-      return QR_OK;
-    }));
-    // root: unfused (rtnode_histogram.cc:199-203 in the oracle build); children: fused (:65-69)
-    if (dense) QR_LAUNCH(c, PH_HIST, squares_exact_kernel<true>, 1, 32, 0, c->d_lambda, ids, lo, n, !root, c->d_partials);
-    else QR_LAUNCH(c, PH_HIST, squares_exact_kernel<false>, 1, 32, 0, c->d_lambda, ids, lo, n, !root, c->d_partials);
-    *n_partials = 1;
-    return QR_OK;
-  }
-  const uint32_t want_slices = std::max<uint32_t>(1, (148u * 4u + c->npanels - 1) / c->npanels);
-  uint32_t dpb = std::max<uint32_t>(2048u, (n + want_slices - 1) / want_slices);
-  dpb = (dpb + 255u) & ~255u;
-  const uint32_t slices = std::max<uint32_t>(1, (n + dpb - 1) / dpb);
-  const size_t smem = (size_t) c->max_panel_cells * 12;
-  const bool use_smem = smem <= 200 * 1024;
-  dim3 grid(slices, c->npanels);
-  QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
-    using B = decltype(tag);
-    if (use_smem) {
-      if (dense) QR_LAUNCH(c, PH_HIST, (hist_fast_kernel<B, true, true>), grid, 256, smem, c->d_panels, c->N, ids, lo, n, c->d_lamq, c->d_thr_off, F, hs, hc, dpb);
-      else QR_LAUNCH(c, PH_HIST, (hist_fast_kernel<B, false, true>), grid, 256, smem, c->d_panels, c->N, ids, lo, n, c->d_lamq, c->d_thr_off, F, hs, hc, dpb);
-    } else {
-      if (dense) QR_LAUNCH(c, PH_HIST, (hist_fast_kernel<B, true, false>), grid, 256, 0, c->d_panels, c->N, ids, lo, n, c->d_lamq, c->d_thr_off, F, hs, hc, dpb);
-      else QR_LAUNCH(c, PH_HIST, (hist_fast_kernel<B, false, false>), grid, 256, 0, c->d_panels, c->N, ids, lo, n, c->d_lamq, c->d_thr_off, F, hs, hc, dpb);
-    }
-    return QR_OK;
-  }));
-  const uint32_t sq_blocks = std::min<uint32_t>(64u, std::max<uint32_t>(1u, n / 4096u));
-  if (dense) QR_LAUNCH(c, PH_HIST, squares_fast_kernel<true>, sq_blocks, 256, 0, c->d_lambda, ids, lo, n, c->d_partials);
-  else QR_LAUNCH(c, PH_HIST, squares_fast_kernel<false>, sq_blocks, 256, 0, c->d_lambda, ids, lo, n, c->d_partials);
-  *n_partials = sq_blocks;
-  return QR_OK;
-}
-
-// multi-GPU: sum the freshly built (per-bin, not yet cumulative) histogram and the squares over ranks
-static int reduce_hist(qr_ctx *c, int slot, uint32_t *n_partials) {
-  if (!c->comm) return QR_OK;
-  unsigned long long *hs = c->d_hist_sum + (size_t) slot * c->ncells;
-  uint32_t *hc = c->d_hist_cnt + (size_t) slot * c->ncells;
-  return comm_reduce_hist(c, hs, hc, n_partials);
-}
-
-// cumulative + right = parent - left + split scan; results land in c->h_res[0..1]
-static int finalize_nodes(qr_ctx *c, int mode, int slotP, int slotL, int slotR, uint32_t n_partials,
-                          double parent_squares) {
-  PhaseTimer pt(c, PH_SCAN);
-  FinalizeArgs a;
-  a.hsum = c->d_hist_sum; a.hcnt = c->d_hist_cnt; a.ncells = c->ncells;
-  a.slotP = slotP; a.slotL = slotL; a.slotR = slotR; a.mode = mode;
-  a.minls = c->p.minleafsupport; a.qexp = c->d_qexp;
-  a.fbest_score = c->d_fbest_score; a.fbest_t = c->d_fbest_t; a.F = (uint32_t) c->F;
-  Finalize2Args b;
-  b.hsum = c->d_hist_sum; b.hcnt = c->d_hist_cnt; b.ncells = c->ncells;
-  b.slotL = slotL; b.slotR = slotR; b.mode = mode; b.qexp = c->d_qexp;
-  b.fbest_score = c->d_fbest_score; b.fbest_t = c->d_fbest_t; b.F = (uint32_t) c->F;
-  b.sq_partials = c->d_partials; b.n_partials = n_partials; b.parent_squares = parent_squares;
-  b.res = c->d_res;
-  if (c->exact) {
-    QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, (unsigned) c->F, 256, 0, a, c->d_thr_off);
-    QR_LAUNCH(c, PH_SCAN, finalize2_kernel<true>, 1, 32, 0, b, c->d_thr_off);
-  } else {
-    QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, (unsigned) c->F, 256, 0, a, c->d_thr_off);
-    QR_LAUNCH(c, PH_SCAN, finalize2_kernel<false>, 1, 32, 0, b, c->d_thr_off);
-  }
-  QR_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, 2 * sizeof(SplitResult), cudaMemcpyDeviceToHost, c->stream));
-  QR_CUDA(cudaStreamSynchronize(c->stream));
-  return QR_OK;
-}
-
-static int partition_node(qr_ctx *c, bool dense, int buf, uint32_t lo, uint32_t n, uint32_t f, uint32_t t,
-                          uint32_t lcount, int dst_buf) {
-  PhaseTimer pt(c, PH_PARTITION);
-  const unsigned blocks = (n + kPartItems - 1) / kPartItems;
-  const uint32_t *src = c->d_ids[buf];
-  uint32_t *dst = c->d_ids[dst_buf];
-  return dispatch_bins(c, [&](auto tag) -> int {
-    using B = decltype(tag);
-    if (dense) {
-      QR_LAUNCH(c, PH_PARTITION, (partition_count_kernel<B, true>), blocks, 256, 0, c->d_panels, c->N, src, lo, n, f, t, c->d_blockcnt);
-      QR_LAUNCH(c, PH_PARTITION, (partition_scatter_kernel<B, true>), blocks, 256, 0, c->d_panels, c->N, src, dst, lo, n, f, t, c->d_blockcnt, lcount);
-    } else {
-      QR_LAUNCH(c, PH_PARTITION, (partition_count_kernel<B, false>), blocks, 256, 0, c->d_panels, c->N, src, lo, n, f, t, c->d_blockcnt);
-      QR_LAUNCH(c, PH_PARTITION, (partition_scatter_kernel<B, false>), blocks, 256, 0, c->d_panels, c->N, src, dst, lo, n, f, t, c->d_blockcnt, lcount);
-    }
-    return QR_OK;
-  });
-}
-
-// host replica of MaxHeap<RTNode*> (maxheap.h:31-106): same sift rules, so equal keys pop in
-// the same order as in the reference
-struct NodeHeap {
-  struct Item { double key; int val; };
-  std::vector<Item> arr;
-  size_t size = 0;
-  NodeHeap() { arr.push_back({DBL_MAX, -1}); }
-  void push(double key, int val) {
-    ++size;
-    if (arr.size() <= size) arr.resize(size + 1);
-    size_t p = size;
-    while (key > arr[p >> 1].key) { arr[p] = arr[p >> 1]; p >>= 1; }
-    arr[p] = {key, val};
-  }
-  int top() const { return arr[1].val; }
-  void pop() {
-    const Item last = arr[size--];
-    size_t child, p = 1;
-    while ((p << 1) <= size) {
-      child = p << 1;
-      if (child < size && arr[child + 1].key > arr[child].key) ++child;
-      if (last.key < arr[child].key) arr[p] = arr[child];
-      else break;
-      p = child;
-    }
-    arr[p] = last;
-  }
-};
-
-// the documents of node i live in ids[buf][lo, lo+n); the root is the identity list
-static bool node_dense(const qr_ctx *c, int i) { return i == 0; }
-
-// RegressionTree::split (rt.cc:209-362) for node i whose best split is already known
-static int split_node(qr_ctx *c, int i, bool build_child_hists) {
-  HostNode nd = c->nodes[i];
-  const uint32_t f = nd.res.feature, t = nd.res.threshold_idx;
-  const uint32_t lc = (uint32_t) nd.res.lcount;
-  const bool dense = node_dense(c, i);
-  const int dst_buf = dense ? 0 : 1 - nd.buf;
-  QR_TRY(partition_node(c, dense, nd.buf, nd.lo, nd.n, f, t, lc, dst_buf));
-  HostNode L, R;
-  L.lo = nd.lo; L.n = lc; L.buf = dst_buf;
-  R.lo = nd.lo + lc; R.n = nd.n - lc; R.buf = dst_buf;
-  if (build_child_hists) {
-    L.hist = alloc_slot(c);
-    R.hist = alloc_slot(c);
-    if (L.hist < 0 || R.hist < 0) { set_error("internal: histogram pool exhausted"); return QR_ECUDA; }
-    uint32_t n_part = 0;
-    QR_TRY(build_hist(c, L.hist, false, L.buf, L.lo, L.n, false, &n_part));
-    QR_TRY(reduce_hist(c, L.hist, &n_part));
-    QR_TRY(finalize_nodes(c, 1, nd.hist, L.hist, R.hist, n_part, nd.res.squares));
-    L.res = c->h_res[0];
-    R.res = c->h_res[1];
-    if (c->comm) { L.n = (uint32_t) 0 + L.n; }  // local sizes stay local; res.n is global
-  }
-  const int li = (int) c->nodes.size();
-  c->nodes.push_back(L);
-  c->nodes.push_back(R);
-  c->nodes[i].left = li;
-  c->nodes[i].right = li + 1;
-  c->rho += (double) lc / (double) c->N;
-  c->sigma += (double) nd.n / (double) c->N;
-  c->nsplits++;
-  return QR_OK;
-}
-
-static int fit_leafwise(qr_ctx *c) {
-  const size_t nleaves = c->p.nleaves;
-  NodeHeap heap;
-  size_t taken = 0;
-  auto can_split = [&](int i) {
-    const SplitResult &r = c->nodes[i].res;
-    return r.deviance > 0.0 && r.valid;        // rt.cc:212, 312
-  };
-  if (can_split(0)) {
-    QR_TRY(split_node(c, 0, true));
-    heap.push(c->nodes[c->nodes[0].left].res.deviance, c->nodes[0].left);     // rt.cc:59-60
-    heap.push(c->nodes[c->nodes[0].right].res.deviance, c->nodes[0].right);
-  }
-  while (heap.size != 0 && (nleaves == 0 || taken + heap.size < nleaves)) {   // rt.cc:64-65
-    const int i = heap.top();
-    heap.pop();
-    if (can_split(i)) {
-      QR_TRY(split_node(c, i, true));
-      heap.push(c->nodes[c->nodes[i].left].res.deviance, c->nodes[i].left);
-      heap.push(c->nodes[c->nodes[i].right].res.deviance, c->nodes[i].right);
-    } else {
-      ++taken;                                                                // rt.cc:78-79
-    }
-    release_slot(c, c->nodes[i].hist);                                        // rt.cc:83-84
-  }
-  return QR_OK;
-}
-
-static int fit_oblivious(qr_ctx *c) {
-  const uint32_t depth = c->p.treedepth;
-  std::vector<int> level{0};
-  int *d_slots = nullptr;
-  uint64_t *d_lcounts = nullptr, *h_lcounts = nullptr;
-  const size_t maxnodes = (size_t) 1 << depth;
-  QR_TRY(dev_alloc(&d_slots, maxnodes));
-  QR_TRY(dev_alloc(&d_lcounts, maxnodes));
-  QR_CUDA(cudaMallocHost((void **) &h_lcounts, maxnodes * sizeof(uint64_t)));
-  int rc = QR_OK;
-  for (uint32_t d = 0; d < depth && rc == QR_OK; ++d) {
-    std::vector<int> slots;
-    for (int i : level) slots.push_back(c->nodes[i].hist);
-    auto body = [&]() -> int {
-      {
-        PhaseTimer pt(c, PH_SCAN);
-        QR_CUDA(cudaMemcpyAsync(d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        if (c->exact) QR_LAUNCH(c, PH_SCAN, obv_level_kernel<true>, (unsigned) c->F, 256, 0, c->d_hist_sum, c->d_hist_cnt, c->ncells, d_slots, (uint32_t) slots.size(), c->d_thr_off, (uint32_t) c->F, c->p.minleafsupport, c->d_qexp, c->d_obv_scores);
-        else QR_LAUNCH(c, PH_SCAN, obv_level_kernel<false>, (unsigned) c->F, 256, 0, c->d_hist_sum, c->d_hist_cnt, c->ncells, d_slots, (uint32_t) slots.size(), c->d_thr_off, (uint32_t) c->F, c->p.minleafsupport, c->d_qexp, c->d_obv_scores);
-        QR_LAUNCH(c, PH_SCAN, obv_argmax_kernel, 1, 256, 0, c->d_obv_scores, c->d_thr_off, (uint32_t) c->F, c->d_hist_cnt, c->ncells, d_slots, (uint32_t) slots.size(), c->d_res, d_lcounts);
-        QR_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, sizeof(SplitResult), cudaMemcpyDeviceToHost, c->stream));
-        QR_CUDA(cudaMemcpyAsync(h_lcounts, d_lcounts, slots.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
-        QR_CUDA(cudaStreamSynchronize(c->stream));
-      }
-      return QR_OK;
-    };
-    rc = body();
-    if (rc != QR_OK) break;
-    const SplitResult best = c->h_res[0];
-    if (!best.valid) break;                                   // ot.cc:96
-    std::vector<int> next;
-    for (size_t k = 0; k < level.size() && rc == QR_OK; ++k) {
-      const int i = level[k];
-      c->nodes[i].res.feature = best.feature;
-      c->nodes[i].res.threshold_idx = best.threshold_idx;
-      c->nodes[i].res.lcount = h_lcounts[k];
-      c->nodes[i].res.valid = 1;
-      if (c->comm) rc = comm_local_lcount(c, i);              // local left size for the partition
-      if (rc == QR_OK) rc = split_node(c, i, d != depth - 1); // ot.cc:127
-      if (rc != QR_OK) break;
-      next.push_back(c->nodes[i].left);
-      next.push_back(c->nodes[i].right);
-      release_slot(c, c->nodes[i].hist);                      // ot.cc:157-160 (and the root's copy)
-    }
-    level.swap(next);
-  }
-  cudaFree(d_slots);
-  cudaFree(d_lcounts);
-  cudaFreeHost(h_lcounts);
-  return rc;
-}
-
-static void collect_leaves(qr_ctx *c, int i) {
-  if (c->nodes[i].is_leaf()) { c->leaves.push_back(i); return; }
-  collect_leaves(c, c->nodes[i].left);      // rtnode.cc:34-46: left to right
-  collect_leaves(c, c->nodes[i].right);
-}
-
-static void flatten(const qr_ctx *c, int i, qr_flat_tree *t, uint32_t *next) {
-  const HostNode &nd = c->nodes[i];
-  const uint32_t id = (*next)++;
-  const bool leaf = nd.is_leaf();
-  t->feature[id] = leaf ? -1 : (int32_t) nd.res.feature;
-  t->threshold_idx[id] = leaf ? 0xffffffffu : nd.res.threshold_idx;
-  t->threshold[id] = leaf ? 0.f : c->thr[nd.res.feature][nd.res.threshold_idx];   // rt.cc:317-318
-  t->left[id] = t->right[id] = -1;
-  if (t->value) t->value[id] = leaf ? nd.value : (nd.res.n ? nd.res.sum / (double) nd.res.n : 0.0);  // rtnode.h:105
-  if (t->deviance) t->deviance[id] = nd.res.deviance;
-  if (t->count) t->count[id] = nd.res.n;
-  if (!leaf) {
-    t->left[id] = (int32_t) *next;
-    flatten(c, nd.left, t, next);
-    t->right[id] = (int32_t) *next;
-    flatten(c, nd.right, t, next);
-  }
-}
-
-static int fit_tree(qr_ctx *c, qr_flat_tree *out) {
-  // release histograms still held by the previous tree
-  for (auto &nd : c->nodes) release_slot(c, nd.hist);
-  c->nodes.clear();
-  c->leaves.clear();
-  c->rho = c->sigma = 0;
-  c->nsplits = 0;
-  c->has_tree = false;
-
-  QR_TRY(prepare_fixed_point(c));
-  HostNode root;
-  root.lo = 0; root.n = (uint32_t) c->N; root.buf = 0;
-  root.hist = alloc_slot(c);
-  uint32_t n_part = 0;
-  QR_TRY(build_hist(c, root.hist, true, 0, 0, (uint32_t) c->N, true, &n_part));   // mart.cc:335
-  QR_TRY(reduce_hist(c, root.hist, &n_part));
-  QR_TRY(finalize_nodes(c, 0, -1, root.hist, -1, n_part, 0.0));
-  root.res = c->h_res[0];
-  c->nodes.push_back(root);
-
-  QR_TRY(c->oblivious ? fit_oblivious(c) : fit_leafwise(c));
-
-  // leaves in DFS order, leaf outputs, doc -> leaf map
-  collect_leaves(c, 0);
-  const size_t nl = c->leaves.size();
-  std::vector<LeafSeg> segs(nl);
-  for (size_t k = 0; k < nl; ++k) {
-    const HostNode &nd = c->nodes[c->leaves[k]];
-    segs[k] = LeafSeg{nd.lo, nd.n, nd.buf, 0};
-  }
-  {
-    PhaseTimer pt(c, PH_LEAF);
-    LeafSeg *d_segs = nullptr;
-    QR_TRY(dev_alloc(&d_segs, nl));
-    QR_CUDA(cudaMemcpyAsync(d_segs, segs.data(), nl * sizeof(LeafSeg), cudaMemcpyHostToDevice, c->stream));
-    const bool root_only = nl == 1;
-    if (c->comm) {
-      QR_TRY(comm_leaf_fit(c, d_segs, (uint32_t) nl, root_only));
-    } else {
-      QR_LAUNCH(c, PH_LEAF, leaf_fit_kernel, (unsigned) nl, 256, 0, d_segs, c->d_ids[0], c->d_ids[1], root_only,
-                c->d_lambda, c->lambda ? c->d_weight : nullptr, c->exact, c->d_leafval, c->d_leaf_of_doc);
-    }
-    QR_CUDA(cudaMemcpyAsync(c->h_leafval, c->d_leafval, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    QR_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_segs);
-  }
-  for (size_t k = 0; k < nl; ++k) c->nodes[c->leaves[k]].value = c->h_leafval[k];
-  c->has_tree = true;
-
-  if (out) {
-    const uint32_t nn = (uint32_t) c->nodes.size();
-    if (out->capacity < nn) { set_error("qr_flat_tree capacity %u < %u nodes", out->capacity, nn); return QR_EINVAL; }
-    uint32_t next = 0;
-    flatten(c, 0, out, &next);
-    out->nnodes = nn;
-    out->nleaves = (uint32_t) nl;
-  }
-  return QR_OK;
-}
-
-static int update_modelscores(qr_ctx *c, double weight) {
-  if (!c->has_tree) { set_error("qr_update_modelscores: no fitted tree"); return QR_EINVAL; }
-  PhaseTimer pt(c, PH_LEAF);
-  QR_LAUNCH(c, PH_LEAF, update_scores_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_leaf_of_doc,
-            c->d_leafval, weight, c->N, c->d_scores);
-  c->ranking_valid = false;
-  return QR_OK;
-}
+#include "qr_tree_host.cuh"
 
 }  // namespace qr
 
@@ -809,10 +449,15 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_scores, c->d_lambda, c->d_weight, c->d_lamq, c->d_maxabs, c->d_qexp, c->d_rankpos,
                   c->d_qndcg, c->d_metric, c->d_ids[0], c->d_ids[1], c->d_leaf_of_doc, c->d_blockcnt,
                   c->d_partials, c->d_hist_sum, c->d_hist_cnt, c->d_fbest_score, c->d_fbest_t, c->d_res,
-                  c->d_leafval, c->d_obv_scores};
+                  c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
+                  c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);
+  if (c->h_tasks) cudaFreeHost(c->h_tasks);
+  if (c->h_lcount) cudaFreeHost(c->h_lcount);
+  if (c->h_segs) cudaFreeHost(c->h_segs);
+  if (c->h_obv_lcounts) cudaFreeHost(c->h_obv_lcounts);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);

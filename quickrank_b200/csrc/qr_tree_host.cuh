@@ -1,0 +1,458 @@
+// quickrank_b200 — host side of tree growth (included by qr_train.cu inside namespace qr).
+//
+// The reference grows a tree one node at a time (RegressionTree::fit, rt.cc:49-163): pop the
+// frontier node with the largest deviance from a max-heap, split it, push its children.  Here the
+// SAME sequence of pops and pushes is replayed on the host with a replica of the reference's heap
+// (maxheap.h:31-106), but the expensive part of a split — partition, child histograms, split scan
+// of both children — is done for several frontier nodes per kernel launch ("rounds").  That is
+// legal because what a split produces depends only on the node, not on when it is split: the heap
+// order merely decides WHICH nodes end up being split within the leaf budget.  A round expands the
+// node the replay is blocked on plus the other frontier nodes that can still be reached with the
+// remaining budget; expansions that the replay never reaches are simply dropped.
+#pragma once
+
+template <typename Fn>
+static int dispatch_bins(const qr_ctx *c, Fn &&fn) {
+  return c->bin_bytes == 1 ? fn(uint8_t()) : fn(uint16_t());
+}
+
+static int alloc_slot(qr_ctx *c) {
+  if (c->free_slots.empty()) return -1;
+  int s = c->free_slots.back();
+  c->free_slots.pop_back();
+  return s;
+}
+static void release_slot(qr_ctx *c, int &s) {
+  if (s >= 0) c->free_slots.push_back(s);
+  s = -1;
+}
+
+static int prepare_fixed_point(qr_ctx *c) {
+  if (c->exact) return QR_OK;
+  PhaseTimer pt(c, PH_HIST);
+  QR_CUDA(cudaMemsetAsync(c->d_maxabs, 0, sizeof(unsigned long long), c->stream));
+  QR_LAUNCH(c, PH_HIST, maxabs_kernel, 296, 256, 0, c->d_lambda, c->N, c->d_maxabs);
+  if (c->comm) QR_TRY(comm_allreduce_max_u64(c->comm, c->d_maxabs, 1, c->stream));
+  QR_LAUNCH(c, PH_HIST, choose_scale_kernel, 1, 1, 0, c->d_maxabs, ceil_log2(c->N_global) + 1, c->d_qexp);
+  QR_LAUNCH(c, PH_HIST, quantize_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_lambda, c->N,
+            c->d_qexp, c->d_lamq);
+  return QR_OK;
+}
+
+// host replica of MaxHeap<RTNode*> (maxheap.h:31-106): same sift rules, so equal keys pop in
+// the same order as in the reference
+struct NodeHeap {
+  struct Item { double key; int val; };
+  std::vector<Item> arr;
+  size_t size = 0;
+  NodeHeap() { arr.push_back({DBL_MAX, -1}); }
+  void push(double key, int val) {
+    ++size;
+    if (arr.size() <= size) arr.resize(size + 1);
+    size_t p = size;
+    while (key > arr[p >> 1].key) { arr[p] = arr[p >> 1]; p >>= 1; }
+    arr[p] = {key, val};
+  }
+  int top() const { return arr[1].val; }
+  void pop() {
+    const Item last = arr[size--];
+    size_t child, p = 1;
+    while ((p << 1) <= size) {
+      child = p << 1;
+      if (child < size && arr[child + 1].key > arr[child].key) ++child;
+      if (last.key < arr[child].key) arr[p] = arr[child];
+      else break;
+      p = child;
+    }
+    arr[p] = last;
+  }
+};
+
+// Launches the histogram + finalize kernels for the tasks already uploaded to c->d_tasks.
+static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices) {
+  const uint32_t F = (uint32_t) c->F;
+  {
+    PhaseTimer pt(c, PH_HIST);
+    QR_LAUNCH(c, PH_HIST, zero_slots_kernel, dim3(std::max<uint32_t>(1, std::min<uint32_t>(32, (c->ncells + 1023) / 1024)), k),
+              256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells);
+    if (c->exact) {
+      QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+        using B = decltype(tag);
+        QR_LAUNCH(c, PH_HIST, hist_exact_kernel<B>, dim3((F + 3) / 4, k), 128, 0, c->d_tasks, c->d_lcount,
+                  c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lambda, c->d_thr_off, F, c->d_hist_sum,
+                  c->d_hist_cnt, c->ncells);
+        return QR_OK;
+      }));
+      QR_LAUNCH(c, PH_HIST, squares_exact_kernel, k, 32, 0, c->d_tasks, c->d_lcount, c->d_lambda, c->d_ids[0],
+                c->d_ids[1], c->d_partials);
+    } else {
+      const size_t smem = (size_t) c->max_panel_cells * 12;
+      const bool use_smem = smem <= 200 * 1024;
+      QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+        using B = decltype(tag);
+        if (use_smem)
+          QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true>), dim3(total_slices, c->npanels), 256, smem, c->d_tasks, k,
+                    c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F,
+                    c->d_hist_sum, c->d_hist_cnt, c->ncells);
+        else
+          QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false>), dim3(total_slices, c->npanels), 256, 0, c->d_tasks, k,
+                    c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F,
+                    c->d_hist_sum, c->d_hist_cnt, c->ncells);
+        return QR_OK;
+      }));
+      QR_LAUNCH(c, PH_HIST, squares_fast_kernel, dim3(kSqParts, k), 256, 0, c->d_tasks, c->d_lcount, c->d_lambda,
+                c->d_ids[0], c->d_ids[1], c->d_partials);
+    }
+    if (c->comm) QR_TRY(comm_reduce_tasks(c, k));
+  }
+  {
+    PhaseTimer pt(c, PH_SCAN);
+    const uint32_t n_sq = c->exact ? 1u : kSqParts;
+    if (c->exact) {
+      QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3(F, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
+                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t);
+      QR_LAUNCH(c, PH_SCAN, finalize2_kernel<true>, k, 128, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells,
+                c->d_thr_off, F, c->d_qexp, c->d_fbest_score, c->d_fbest_t, c->d_partials, n_sq, c->d_res);
+    } else {
+      QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3(F, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
+                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t);
+      QR_LAUNCH(c, PH_SCAN, finalize2_kernel<false>, k, 128, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells,
+                c->d_thr_off, F, c->d_qexp, c->d_fbest_score, c->d_fbest_t, c->d_partials, n_sq, c->d_res);
+    }
+    QR_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, (size_t) 2 * k * sizeof(SplitResult), cudaMemcpyDeviceToHost, c->stream));
+    if (c->comm) QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    QR_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  return QR_OK;
+}
+
+// documents per histogram slice so that a round's grid is about four waves of blocks
+static uint32_t pick_hist_dpb(const qr_ctx *c, uint64_t total_docs) {
+  const uint32_t want_slices = std::max<uint32_t>(1, (148u * 4u + c->npanels - 1) / c->npanels);
+  uint64_t dpb = std::max<uint64_t>(1024u, (total_docs + want_slices - 1) / want_slices);
+  dpb = (dpb + 255u) & ~(uint64_t) 255u;
+  return (uint32_t) std::min<uint64_t>(dpb, 1u << 20);
+}
+
+// root histogram refresh (mart.cc:335) + root node statistics and best split
+static int build_root(qr_ctx *c) {
+  HostNode root;
+  root.lo = 0; root.n = (uint32_t) c->N; root.buf = 2;
+  root.hist = alloc_slot(c);
+  NodeTask &t = c->h_tasks[0];
+  memset(&t, 0, sizeof(t));
+  t.lo = 0; t.n = root.n; t.src = 2; t.dst = 0; t.whole = 1; t.build_left = 1;
+  t.slotP = -1; t.slotB = root.hist; t.slotD = -1;
+  t.hist_dpb = pick_hist_dpb(c, root.n);
+  t.hist_blk0 = 0; t.part_blk0 = 0; t.sq0 = 0; t.fused_sq = 0;
+  const uint32_t slices = std::max<uint32_t>(1, (root.n + t.hist_dpb - 1) / t.hist_dpb);
+  QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
+  QR_TRY(launch_hist_and_scan(c, 1, slices));
+  root.res = c->h_res[0];
+  c->nodes.push_back(root);
+  return QR_OK;
+}
+
+// RegressionTree::split (rt.cc:209-362) for every node in `S` (their best splits are known)
+static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_hists) {
+  const uint32_t k = (uint32_t) S.size();
+  if (k == 0) return QR_OK;
+  if (k > c->max_tasks) { set_error("internal: %u tasks > capacity %u", k, c->max_tasks); return QR_ECUDA; }
+  uint64_t built_total = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    const HostNode &nd = c->nodes[S[j]];
+    const uint64_t lc = nd.res.lcount, rc = nd.res.n - nd.res.lcount;
+    const bool build_left = c->exact ? true : lc <= rc;
+    // local sizes are only known exactly on a single GPU; with several ranks bound by the node size
+    built_total += c->comm ? nd.n : (build_left ? lc : rc);
+  }
+  const uint32_t dpb = pick_hist_dpb(c, built_total);
+  uint32_t part_blk = 0, hist_blk = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    HostNode &nd = c->nodes[S[j]];
+    NodeTask &t = c->h_tasks[j];
+    memset(&t, 0, sizeof(t));
+    const uint64_t lc = nd.res.lcount, rc = nd.res.n - nd.res.lcount;
+    t.lo = nd.lo; t.n = nd.n; t.src = (uint32_t) nd.buf; t.dst = nd.buf == 2 ? 0u : (uint32_t) (1 - nd.buf);
+    t.f = nd.res.feature; t.t = nd.res.threshold_idx;
+    t.build_left = c->exact ? 1u : (lc <= rc ? 1u : 0u);
+    t.whole = 0;
+    t.slotP = nd.hist;
+    t.slotB = t.slotD = -1;
+    if (build_child_hists) {
+      t.slotB = alloc_slot(c);
+      t.slotD = alloc_slot(c);
+      if (t.slotB < 0 || t.slotD < 0) { set_error("internal: histogram pool exhausted"); return QR_ECUDA; }
+    }
+    t.part_blk0 = part_blk;
+    part_blk += std::max<uint32_t>(1, (nd.n + kPartItems - 1) / kPartItems);
+    t.hist_blk0 = hist_blk;
+    t.hist_dpb = dpb;
+    const uint64_t built_n = c->comm ? nd.n : (t.build_left ? lc : rc);
+    hist_blk += std::max<uint32_t>(1, (uint32_t) ((built_n + dpb - 1) / dpb));
+    t.sq0 = j * kSqParts;
+    t.fused_sq = 1;
+    t.parent_squares = nd.res.squares;
+  }
+  QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
+  {
+    PhaseTimer pt(c, PH_PARTITION);
+    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+      using B = decltype(tag);
+      QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
+                c->d_ids[0], c->d_ids[1], c->d_blockcnt);
+      QR_LAUNCH(c, PH_PARTITION, part_prefix_kernel, k, 256, 0, c->d_tasks, c->d_blockcnt, c->d_lcount);
+      QR_LAUNCH(c, PH_PARTITION, part_scatter_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
+                c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_blockcnt, c->d_lcount);
+      return QR_OK;
+    }));
+  }
+  if (build_child_hists) {
+    QR_TRY(launch_hist_and_scan(c, k, hist_blk));
+  } else if (c->comm) {
+    QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    QR_CUDA(cudaStreamSynchronize(c->stream));
+  }
+  for (uint32_t j = 0; j < k; ++j) {
+    const int i = S[j];
+    const NodeTask &t = c->h_tasks[j];
+    const HostNode nd = c->nodes[i];
+    const uint32_t lc_local = c->comm ? c->h_lcount[j] : (uint32_t) nd.res.lcount;
+    HostNode L, R;
+    L.lo = nd.lo; L.n = lc_local; L.buf = (int) t.dst;
+    R.lo = nd.lo + lc_local; R.n = nd.n - lc_local; R.buf = (int) t.dst;
+    if (build_child_hists) {
+      L.hist = t.build_left ? t.slotB : t.slotD;
+      R.hist = t.build_left ? t.slotD : t.slotB;
+      L.res = c->h_res[2 * j];
+      R.res = c->h_res[2 * j + 1];
+    } else {
+      // last oblivious level (ot.cc:142-149): plain leaves, no histogram, deviance left at 0
+      L.res = SplitResult{}; R.res = SplitResult{};
+      L.res.n = nd.res.lcount; R.res.n = nd.res.n - nd.res.lcount;
+      L.res.score = R.res.score = -1.0;
+    }
+    const int li = (int) c->nodes.size();
+    c->nodes.push_back(L);
+    c->nodes.push_back(R);
+    c->nodes[i].left = li;
+    c->nodes[i].right = li + 1;
+    c->nodes[i].expanded = true;
+  }
+  c->nrounds++;
+  return QR_OK;
+}
+
+static bool can_split(const qr_ctx *c, int i) {
+  const SplitResult &r = c->nodes[i].res;
+  return r.deviance > 0.0 && r.valid;   // rt.cc:212, 312
+}
+
+// replay of RegressionTree::fit (rt.cc:49-84)
+static int fit_leafwise(qr_ctx *c) {
+  const size_t nleaves = c->p.nleaves;
+  NodeHeap heap;
+  size_t taken = 0;
+  bool root_done = false;
+  auto push_children = [&](int i) {
+    c->nodes[i].pushed = true;
+    const HostNode &nd = c->nodes[i];
+    heap.push(c->nodes[nd.left].res.deviance, nd.left);      // rt.cc:59-60, 72-73
+    heap.push(c->nodes[nd.right].res.deviance, nd.right);
+    c->rho += (double) c->nodes[nd.left].res.n / (double) c->N_global;
+    c->sigma += (double) nd.res.n / (double) c->N_global;
+    c->nsplits++;
+  };
+  for (;;) {
+    int need = -1;
+    if (!root_done) {
+      if (can_split(c, 0)) {
+        if (!c->nodes[0].expanded) need = 0;
+        else { push_children(0); root_done = true; }
+      } else {
+        root_done = true;
+      }
+    }
+    if (need < 0 && root_done) {
+      while (heap.size != 0 && (nleaves == 0 || taken + heap.size < nleaves)) {   // rt.cc:64-65
+        const int i = heap.top();
+        if (can_split(c, i)) {
+          if (!c->nodes[i].expanded) { need = i; break; }
+          heap.pop();
+          push_children(i);
+        } else {
+          heap.pop();
+          ++taken;                                                            // rt.cc:78-79
+        }
+        release_slot(c, c->nodes[i].hist);                                    // rt.cc:83-84
+      }
+    }
+    if (need < 0) break;
+    // expansion set: the blocking node plus the frontier nodes still reachable with the budget
+    std::vector<int> S{need};
+    if (need != 0) {
+      const size_t budget = nleaves == 0 ? heap.size : nleaves - taken - heap.size;   // successes left
+      std::vector<std::pair<double, int>> cand;
+      for (size_t p = 1; p <= heap.size; ++p) {
+        const int i = heap.arr[p].val;
+        if (i != need && can_split(c, i) && !c->nodes[i].expanded) cand.push_back({heap.arr[p].key, i});
+      }
+      std::sort(cand.begin(), cand.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) {
+        return a.first > b.first || (a.first == b.first && a.second < b.second);
+      });
+      for (size_t q = 0; q < cand.size() && S.size() < budget && S.size() < c->max_tasks; ++q) S.push_back(cand[q].second);
+    }
+    QR_TRY(expand_nodes(c, S, true));
+  }
+  return QR_OK;
+}
+
+static int fit_oblivious(qr_ctx *c) {
+  const uint32_t depth = c->p.treedepth;
+  std::vector<int> level{0};
+  for (uint32_t d = 0; d < depth; ++d) {
+    std::vector<int> slots;
+    for (int i : level) slots.push_back(c->nodes[i].hist);
+    const uint32_t nn = (uint32_t) slots.size();
+    {
+      PhaseTimer pt(c, PH_SCAN);
+      QR_CUDA(cudaMemcpyAsync(c->d_obv_slots, slots.data(), nn * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      if (c->exact) QR_LAUNCH(c, PH_SCAN, obv_level_kernel<true>, (unsigned) c->F, 256, 0, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_obv_slots, nn, c->d_thr_off, (uint32_t) c->F, c->p.minleafsupport, c->d_qexp, c->d_obv_scores);
+      else QR_LAUNCH(c, PH_SCAN, obv_level_kernel<false>, (unsigned) c->F, 256, 0, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_obv_slots, nn, c->d_thr_off, (uint32_t) c->F, c->p.minleafsupport, c->d_qexp, c->d_obv_scores);
+      QR_LAUNCH(c, PH_SCAN, obv_argmax_kernel, 1, 256, 0, c->d_obv_scores, c->d_thr_off, (uint32_t) c->F, c->d_hist_cnt, c->ncells, c->d_obv_slots, nn, c->d_res, c->d_obv_lcounts);
+      QR_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, sizeof(SplitResult), cudaMemcpyDeviceToHost, c->stream));
+      QR_CUDA(cudaMemcpyAsync(c->h_obv_lcounts, c->d_obv_lcounts, nn * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+      QR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    const SplitResult best = c->h_res[0];
+    if (!best.valid) break;                                   // ot.cc:96
+    for (uint32_t k = 0; k < nn; ++k) {
+      SplitResult &r = c->nodes[level[k]].res;
+      r.feature = best.feature;
+      r.threshold_idx = best.threshold_idx;
+      r.lcount = c->h_obv_lcounts[k];
+      r.valid = 1;
+    }
+    QR_TRY(expand_nodes(c, level, d != depth - 1));           // ot.cc:99-161; no histograms on the last level (:127)
+    std::vector<int> next;
+    for (int i : level) {
+      next.push_back(c->nodes[i].left);
+      next.push_back(c->nodes[i].right);
+      c->rho += (double) c->nodes[c->nodes[i].left].res.n / (double) c->N_global;
+      c->sigma += (double) c->nodes[i].res.n / (double) c->N_global;
+      c->nsplits++;
+      release_slot(c, c->nodes[i].hist);                      // ot.cc:157-160
+    }
+    level.swap(next);
+  }
+  return QR_OK;
+}
+
+static void collect_leaves(qr_ctx *c, int i) {
+  if (c->nodes[i].is_leaf()) { c->leaves.push_back(i); return; }
+  collect_leaves(c, c->nodes[i].left);      // rtnode.cc:34-46: left to right
+  collect_leaves(c, c->nodes[i].right);
+}
+
+// a node that was expanded speculatively but never popped by the replay stays a leaf
+static void prune_unreached(qr_ctx *c, const std::vector<char> &is_split) {
+  for (size_t i = 0; i < c->nodes.size(); ++i)
+    if (!is_split[i]) { c->nodes[i].left = c->nodes[i].right = -1; }
+}
+
+static void flatten(const qr_ctx *c, int i, qr_flat_tree *t, uint32_t *next) {
+  const HostNode &nd = c->nodes[i];
+  const uint32_t id = (*next)++;
+  const bool leaf = nd.is_leaf();
+  t->feature[id] = leaf ? -1 : (int32_t) nd.res.feature;
+  t->threshold_idx[id] = leaf ? 0xffffffffu : nd.res.threshold_idx;
+  t->threshold[id] = leaf ? 0.f : c->thr[nd.res.feature][nd.res.threshold_idx];   // rt.cc:317-318
+  t->left[id] = t->right[id] = -1;
+  if (t->value) t->value[id] = leaf ? nd.value : (nd.res.n ? nd.res.sum / (double) nd.res.n : 0.0);  // rtnode.h:105
+  if (t->deviance) t->deviance[id] = nd.res.deviance;
+  if (t->count) t->count[id] = nd.res.n;
+  if (!leaf) {
+    t->left[id] = (int32_t) *next;
+    flatten(c, nd.left, t, next);
+    t->right[id] = (int32_t) *next;
+    flatten(c, nd.right, t, next);
+  }
+}
+
+static uint32_t count_reachable(const qr_ctx *c, int i) {
+  const HostNode &nd = c->nodes[i];
+  return nd.is_leaf() ? 1u : 1u + count_reachable(c, nd.left) + count_reachable(c, nd.right);
+}
+
+static int fit_leaves(qr_ctx *c) {
+  const size_t nl = c->leaves.size();
+  PhaseTimer pt(c, PH_LEAF);
+  uint32_t blk = 0;
+  for (size_t k = 0; k < nl; ++k) {
+    const HostNode &nd = c->nodes[c->leaves[k]];
+    c->h_segs[k] = LeafSeg{nd.lo, nd.n, (uint32_t) nd.buf, blk};
+    blk += (nd.n + kLeafItems - 1) / kLeafItems;
+  }
+  QR_CUDA(cudaMemcpyAsync(c->d_segs, c->h_segs, nl * sizeof(LeafSeg), cudaMemcpyHostToDevice, c->stream));
+  const double *w = c->lambda ? c->d_weight : nullptr;
+  if (c->exact && !c->comm) {
+    QR_LAUNCH(c, PH_LEAF, leaf_exact_kernel, (unsigned) nl, 32, 0, c->d_segs, c->d_ids[0], c->d_ids[1], c->d_lambda,
+              w, c->d_leafval, c->d_leaf_of_doc);
+  } else {
+    if (blk > 0)
+      QR_LAUNCH(c, PH_LEAF, leaf_partial_kernel, blk, 256, 0, c->d_segs, (uint32_t) nl, c->d_ids[0], c->d_ids[1],
+                c->d_lambda, w, c->d_leaf_partials, c->d_leaf_of_doc);
+    QR_LAUNCH(c, PH_LEAF, leaf_final_kernel, (unsigned) ((nl + 63) / 64), 64, 0, c->d_segs, (uint32_t) nl,
+              c->d_leaf_partials, c->lambda, c->d_leafsum, c->d_leafval);
+    if (c->comm) QR_TRY(comm_leaf_values(c, (uint32_t) nl));
+  }
+  QR_CUDA(cudaMemcpyAsync(c->h_leafval, c->d_leafval, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  QR_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t k = 0; k < nl; ++k) c->nodes[c->leaves[k]].value = c->h_leafval[k];
+  return QR_OK;
+}
+
+static int fit_tree(qr_ctx *c, qr_flat_tree *out) {
+  // release histograms still held by the previous tree
+  for (auto &nd : c->nodes) release_slot(c, nd.hist);
+  c->nodes.clear();
+  c->leaves.clear();
+  c->rho = c->sigma = 0;
+  c->nsplits = 0;
+  c->nrounds = 0;
+  c->has_tree = false;
+
+  QR_TRY(prepare_fixed_point(c));
+  QR_TRY(build_root(c));
+  QR_TRY(c->oblivious ? fit_oblivious(c) : fit_leafwise(c));
+
+  if (!c->oblivious) {
+    // keep only the splits the replay actually performed: children are linked at expansion time,
+    // a node is an internal node of the final tree iff the replay pushed its children
+    std::vector<char> is_split(c->nodes.size(), 0);
+    for (size_t i = 0; i < c->nodes.size(); ++i) is_split[i] = c->nodes[i].pushed;
+    prune_unreached(c, is_split);
+  }
+  collect_leaves(c, 0);
+  QR_TRY(fit_leaves(c));
+  c->has_tree = true;
+
+  if (out) {
+    const uint32_t nn = count_reachable(c, 0);
+    if (out->capacity < nn) { set_error("qr_flat_tree capacity %u < %u nodes", out->capacity, nn); return QR_EINVAL; }
+    uint32_t next = 0;
+    flatten(c, 0, out, &next);
+    out->nnodes = nn;
+    out->nleaves = (uint32_t) c->leaves.size();
+  }
+  return QR_OK;
+}
+
+static int update_modelscores(qr_ctx *c, double weight) {
+  if (!c->has_tree) { set_error("qr_update_modelscores: no fitted tree"); return QR_EINVAL; }
+  PhaseTimer pt(c, PH_LEAF);
+  QR_LAUNCH(c, PH_LEAF, update_scores_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_leaf_of_doc,
+            c->d_leafval, weight, c->N, c->d_scores);
+  c->ranking_valid = false;
+  return QR_OK;
+}
