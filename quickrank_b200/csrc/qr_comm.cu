@@ -20,7 +20,7 @@ int comm_allreduce_max_u64(Comm *, unsigned long long *, size_t, cudaStream_t) {
   set_error("multi-GPU support is not built yet");
   return QR_ECOMM;
 }
-int comm_reduce_tasks(qr_ctx *, uint32_t) {
+int comm_reduce_tasks(qr_ctx *, uint32_t, bool) {
   set_error("multi-GPU support is not built yet");
   return QR_ECOMM;
 }

@@ -103,7 +103,15 @@ struct qr_ctx {
   uint32_t *d_ids[2] = {nullptr, nullptr};  // [N] node document lists (ping-pong)
   uint32_t *d_leaf_of_doc = nullptr;        // [N]
   uint32_t *d_blockcnt = nullptr;           // partition scratch
-  double *d_partials = nullptr;             // squares partials [max_tasks][kSqParts]
+  double *d_partials = nullptr;             // REFERENCE: squares per task [max_tasks]
+  ulonglong2 *d_sq128 = nullptr;            // FAST: exact squares per histogram slice [max_slices]
+  uint32_t max_slices = 0;
+  uint32_t *d_task_done = nullptr;          // [max_tasks] finalize completion counters
+  unsigned long long *d_part_status = nullptr;  // one-pass partition look-back words
+  uint32_t *d_ticket = nullptr;             // one-pass partition block tickets
+  uint32_t ticket_base = 0, part_epoch = 0;
+  uint32_t *d_root_cnt = nullptr;           // [ncells] per-bin document counts of the whole dataset
+  uint4 *d_hot_rows = nullptr;              // [npanels] most frequent bin of each feature, packed like a panel row
   unsigned long long *d_hist_sum = nullptr; // [nslots][ncells] int64 (FAST) or double (REFERENCE)
   uint32_t *d_hist_cnt = nullptr;           // [nslots][ncells]
   int nslots = 0;
@@ -113,6 +121,8 @@ struct qr_ctx {
   uint32_t *d_lcount = nullptr, *h_lcount = nullptr;     // [max_tasks] local left counts
   double *d_fbest_score = nullptr;          // [max_tasks][2][F]
   uint32_t *d_fbest_t = nullptr;            // [max_tasks][2][F]
+  uint32_t *d_fbest_lc = nullptr;           // [max_tasks][2][F] left count at each feature's best split
+  ulonglong2 *d_totals = nullptr;           // [max_tasks][2] (node size, node sum bits)
   qr::SplitResult *d_res = nullptr;         // [max_tasks][2]
   qr::SplitResult *h_res = nullptr;         // pinned
   qr::LeafSeg *d_segs = nullptr, *h_segs = nullptr;      // [maxleaves]

@@ -127,80 +127,82 @@ __global__ void binning_kernel(const float *colmajor, size_t N, uint32_t F, cons
 // are ranked in parallel by counting; only queries with ties take the sequential replica.
 // Also evaluates DCG/NDCG of the query (dcg.cc:33-57, ndcg.cc:49-58).
 // ------------------------------------------------------------------------------------------
-struct SortView {
-  const double *s;
-  uint32_t *idx;
-  __device__ __forceinline__ bool comp(uint32_t a, uint32_t b) const { return s[a] > s[b]; }
-};
+// (score, position) pairs are sorted in place: one 16-byte shared-memory access per element moved
+// or compared instead of an index load followed by a dependent score load.
+struct __align__(16) SortElem { double key; uint32_t id; uint32_t pad; };
 
-__device__ void sv_adjust_heap(const SortView &v, int first, int hole, int len, uint32_t value) {
+__device__ __forceinline__ bool se_comp(const SortElem &a, const SortElem &b) { return a.key > b.key; }
+
+__device__ void se_adjust_heap(SortElem *v, int first, int hole, int len, SortElem value) {
   const int top = hole;
   int child = hole;
   while (child < (len - 1) / 2) {
     child = 2 * (child + 1);
-    if (v.comp(v.idx[first + child], v.idx[first + child - 1])) child--;
-    v.idx[first + hole] = v.idx[first + child];
+    if (se_comp(v[first + child], v[first + child - 1])) child--;
+    v[first + hole] = v[first + child];
     hole = child;
   }
   if ((len & 1) == 0 && child == (len - 2) / 2) {
     child = 2 * (child + 1);
-    v.idx[first + hole] = v.idx[first + child - 1];
+    v[first + hole] = v[first + child - 1];
     hole = child - 1;
   }
   int parent = (hole - 1) / 2;
-  while (hole > top && v.comp(v.idx[first + parent], value)) {
-    v.idx[first + hole] = v.idx[first + parent];
+  while (hole > top && se_comp(v[first + parent], value)) {
+    v[first + hole] = v[first + parent];
     hole = parent;
     parent = (hole - 1) / 2;
   }
-  v.idx[first + hole] = value;
+  v[first + hole] = value;
 }
 
-__device__ void sv_heap_sort(const SortView &v, int first, int last) {
+__device__ void se_heap_sort(SortElem *v, int first, int last) {
   int len = last - first;
   if (len >= 2) {
     int parent = (len - 2) / 2;
     for (;;) {
-      uint32_t val = v.idx[first + parent];
-      sv_adjust_heap(v, first, parent, len, val);
+      const SortElem val = v[first + parent];
+      se_adjust_heap(v, first, parent, len, val);
       if (parent == 0) break;
       parent--;
     }
   }
   while (last - first > 1) {
     --last;
-    uint32_t val = v.idx[last];
-    v.idx[last] = v.idx[first];
-    sv_adjust_heap(v, first, 0, last - first, val);
+    const SortElem val = v[last];
+    v[last] = v[first];
+    se_adjust_heap(v, first, 0, last - first, val);
   }
 }
 
-__device__ void sv_unguarded_linear_insert(const SortView &v, int last) {
-  uint32_t val = v.idx[last];
+__device__ __forceinline__ void se_unguarded_linear_insert(SortElem *v, int last) {
+  const SortElem val = v[last];
   int next = last - 1;
-  while (v.comp(val, v.idx[next])) {
-    v.idx[last] = v.idx[next];
+  SortElem nv = v[next];
+  while (se_comp(val, nv)) {
+    v[last] = nv;
     last = next;
     --next;
+    nv = v[next];
   }
-  v.idx[last] = val;
+  v[last] = val;
 }
 
-__device__ void sv_insertion_sort(const SortView &v, int first, int last) {
+__device__ void se_insertion_sort(SortElem *v, int first, int last) {
   if (first == last) return;
   for (int i = first + 1; i != last; ++i) {
-    if (v.comp(v.idx[i], v.idx[first])) {
-      uint32_t val = v.idx[i];
-      for (int k = i; k > first; --k) v.idx[k] = v.idx[k - 1];
-      v.idx[first] = val;
+    if (se_comp(v[i], v[first])) {
+      const SortElem val = v[i];
+      for (int k = i; k > first; --k) v[k] = v[k - 1];
+      v[first] = val;
     } else {
-      sv_unguarded_linear_insert(v, i);
+      se_unguarded_linear_insert(v, i);
     }
   }
 }
 
 // sequential; executed by one lane
-__device__ void sv_std_sort(const SortView &v, int n) {
+__device__ void se_std_sort(SortElem *v, int n) {
   if (n <= 0) return;
   int lg = 0;
   for (int t = n; t > 1; t >>= 1) ++lg;
@@ -212,29 +214,30 @@ __device__ void sv_std_sort(const SortView &v, int n) {
     --sp;
     int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
     while (last - first > 16) {
-      if (depth == 0) { sv_heap_sort(v, first, last); break; }
+      if (depth == 0) { se_heap_sort(v, first, last); break; }
       --depth;
-      int mid = first + (last - first) / 2;
+      const int mid = first + (last - first) / 2;
       {  // __move_median_to_first(first, first+1, mid, last-1)
-        int a = first + 1, b = mid, c = last - 1, pick;
-        uint32_t va = v.idx[a], vb = v.idx[b], vc = v.idx[c];
-        if (v.comp(va, vb)) {
-          if (v.comp(vb, vc)) pick = b;
-          else if (v.comp(va, vc)) pick = c;
+        const int a = first + 1, b = mid, c = last - 1;
+        int pick;
+        const SortElem va = v[a], vb = v[b], vc = v[c];
+        if (se_comp(va, vb)) {
+          if (se_comp(vb, vc)) pick = b;
+          else if (se_comp(va, vc)) pick = c;
           else pick = a;
-        } else if (v.comp(va, vc)) pick = a;
-        else if (v.comp(vb, vc)) pick = c;
+        } else if (se_comp(va, vc)) pick = a;
+        else if (se_comp(vb, vc)) pick = c;
         else pick = b;
-        uint32_t t = v.idx[first]; v.idx[first] = v.idx[pick]; v.idx[pick] = t;
+        const SortElem t = v[first]; v[first] = v[pick]; v[pick] = t;
       }
       int lo = first + 1, hi = last;
-      const uint32_t pivot = v.idx[first];
+      const SortElem pivot = v[first];
       for (;;) {  // __unguarded_partition(first+1, last, first)
-        while (v.comp(v.idx[lo], pivot)) ++lo;
+        while (se_comp(v[lo], pivot)) ++lo;
         --hi;
-        while (v.comp(pivot, v.idx[hi])) --hi;
+        while (se_comp(pivot, v[hi])) --hi;
         if (!(lo < hi)) break;
-        uint32_t t = v.idx[lo]; v.idx[lo] = v.idx[hi]; v.idx[hi] = t;
+        const SortElem t = v[lo]; v[lo] = v[hi]; v[hi] = t;
         ++lo;
       }
       if (sp < 64) { st_first[sp] = lo; st_last[sp] = last; st_depth[sp] = depth; ++sp; }
@@ -242,12 +245,15 @@ __device__ void sv_std_sort(const SortView &v, int n) {
     }
   }
   if (n > 16) {
-    sv_insertion_sort(v, 0, 16);
-    for (int i = 16; i != n; ++i) sv_unguarded_linear_insert(v, i);
+    se_insertion_sort(v, 0, 16);
+    for (int i = 16; i != n; ++i) se_unguarded_linear_insert(v, i);
   } else {
-    sv_insertion_sort(v, 0, n);
+    se_insertion_sort(v, 0, n);
   }
 }
+
+// per-warp shared memory of rank_kernel: SortElem[maxlen] | uint32 idx[maxlen]
+__host__ __device__ inline size_t rank_smem_per_warp(uint32_t maxlen) { return (size_t) maxlen * 20; }
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -260,19 +266,23 @@ rank_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t q = blockIdx.x * WARPS + warp;
   if (q >= Q) return;
-  double *s = reinterpret_cast<double *>(smem_raw) + (size_t) warp * maxlen;
-  uint32_t *idx = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(smem_raw) + (size_t) WARPS * maxlen) +
+  SortElem *el = reinterpret_cast<SortElem *>(smem_raw) + (size_t) warp * maxlen;
+  uint32_t *idx = reinterpret_cast<uint32_t *>(reinterpret_cast<SortElem *>(smem_raw) + (size_t) WARPS * maxlen) +
                   (size_t) warp * maxlen;
   const uint32_t off = qoff[q], n = qoff[q + 1] - off;
-  for (uint32_t i = lane; i < n; i += 32) s[i] = scores[off + i];
+  for (uint32_t i = lane; i < n; i += 32) {   // queryresults.cc:50-51: identity, then sort
+    SortElem e;
+    e.key = scores[off + i]; e.id = i; e.pad = 0;
+    el[i] = e;
+  }
   __syncwarp();
   // parallel rank-by-counting, valid when no two scores are equal
   bool tie = false;
   for (uint32_t i = lane; i < n; i += 32) {
-    const double si = s[i];
+    const double si = el[i].key;
     uint32_t gt = 0, eq = 0;
     for (uint32_t j = 0; j < n; ++j) {
-      const double sj = s[j];
+      const double sj = el[j].key;
       gt += sj > si;
       eq += sj == si;
     }
@@ -282,12 +292,9 @@ rank_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
   tie = __any_sync(0xffffffffu, tie);
   if (tie) {
     __syncwarp();
-    for (uint32_t i = lane; i < n; i += 32) idx[i] = i;  // queryresults.cc:50-51
+    if (lane == 0) se_std_sort(el, (int) n);
     __syncwarp();
-    if (lane == 0) {
-      SortView v{s, idx};
-      sv_std_sort(v, (int) n);
-    }
+    for (uint32_t i = lane; i < n; i += 32) idx[i] = el[i].id;
   }
   __syncwarp();
   for (uint32_t i = lane; i < n; i += 32) rankpos[off + i] = idx[i];
@@ -348,13 +355,14 @@ __global__ void ndcg_mean_kernel(const double *qndcg, uint32_t Q, uint32_t Qdiv,
 //   heavy X:  [j<X, label_j>label_X: -]  [k=0..n-1, label_X>label_k: +]  [j>X, label_j>label_X: -]
 //   light b:  [a<c, label_a>label_b: -]  [a<c, label_b>label_a: +]
 // ------------------------------------------------------------------------------------------
-constexpr int kHG = 16;           // heavy ranks handled per sweep
-constexpr int kStageStride = kHG + 1;  // double2 units; +1 avoids bank conflicts
+constexpr int kHG = 16;           // heavy ranks handled per sweep (upper bound; the host passes min(kHG, cutoff))
 
 struct PairTerm { double rho, d; };
 
-__device__ __forceinline__ PairTerm pair_term(const double *s, const double *g, const double *invlg,
-                                              double idcg, uint32_t c, uint32_t hi, uint32_t lo) {
+// kept out of line: exp() and two FP64 divisions inline at every call site blow the loop body past
+// the instruction cache
+__device__ __noinline__ PairTerm pair_term(const double *s, const double *g, const double *invlg,
+                                           double idcg, uint32_t c, uint32_t hi, uint32_t lo) {
   const uint32_t i = hi < lo ? hi : lo, j = hi < lo ? lo : hi;
   const double disc = (j < c) ? (invlg[j] - invlg[i]) : (-invlg[i]);       // ndcg.cc:76-86
   const double jac = disc * (g[i] - g[j]) / idcg;
@@ -364,24 +372,28 @@ __device__ __forceinline__ PairTerm pair_term(const double *s, const double *g, 
   return t;
 }
 
+// per-warp shared memory of lambda_kernel: s[maxlen] g[maxlen] (double) | stage[hg][32] (double2)
+// | lab[maxlen] (float) pos[maxlen] (uint32)
+__host__ __device__ inline size_t lambda_smem_per_warp(uint32_t maxlen, uint32_t hg) {
+  return (size_t) maxlen * 24 + (size_t) hg * 32 * 16;
+}
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 lambda_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
               const double *__restrict__ gain, const uint32_t *__restrict__ qoff,
               const double *__restrict__ idcg_q, const double *__restrict__ invlg,
               const uint32_t *__restrict__ rankpos, uint32_t Q, uint32_t maxlen, size_t cutoff,
-              double *lam, double *wgt) {
+              uint32_t hg, double *lam, double *wgt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t q = blockIdx.x * WARPS + warp;
   if (q >= Q) return;
-  // per-warp carve-up: s[maxlen] g[maxlen] (double) | stage[32][kStageStride] (double2) | lab[maxlen] pos[maxlen]
-  const size_t per_warp = (size_t) maxlen * 24 + (size_t) 32 * kStageStride * 16;
-  unsigned char *base = smem_raw + (size_t) warp * per_warp;
+  unsigned char *base = smem_raw + (size_t) warp * lambda_smem_per_warp(maxlen, hg);
   double *s = reinterpret_cast<double *>(base);
   double *g = s + maxlen;
-  double2 *stage = reinterpret_cast<double2 *>(g + maxlen);
-  float *lab = reinterpret_cast<float *>(stage + 32 * kStageStride);
+  double2 *stage = reinterpret_cast<double2 *>(g + maxlen);   // stage[x * 32 + lane]
+  float *lab = reinterpret_cast<float *>(stage + (size_t) hg * 32);
   uint32_t *pos = reinterpret_cast<uint32_t *>(lab + maxlen);
 
   const uint32_t off = qoff[q], n = qoff[q + 1] - off;
@@ -401,11 +413,10 @@ lambda_kernel(const double *__restrict__ scores, const float *__restrict__ label
   const uint32_t c = cutoff < n ? (uint32_t) cutoff : n;
 
   for (int sweep = 0; sweep < 2; ++sweep) {
-    for (uint32_t h0 = 0; h0 < c; h0 += kHG) {
-      const uint32_t hc = min((uint32_t) kHG, c - h0);
+    for (uint32_t h0 = 0; h0 < c; h0 += hg) {
+      const uint32_t hc = min(hg, c - h0);
       const bool heavy_lane = lane < hc;
       const uint32_t X = h0 + lane;                 // this lane's heavy rank (if heavy_lane)
-      const float labX = heavy_lane ? lab[X] : 0.f;
       double aL = 0.0, aW = 0.0;
       if (sweep == 1 && heavy_lane) { aL = lam[pos[X]]; aW = wgt[pos[X]]; }
 
@@ -413,23 +424,24 @@ lambda_kernel(const double *__restrict__ scores, const float *__restrict__ label
         // S1: b < X with label_b > label_X  ->  p[X] -= lambda(b, X)
         for (uint32_t cb = 0; cb < h0 + hc; cb += 32) {
           const uint32_t b = cb + lane;
+          const float labb = b < n ? lab[b] : 0.f;
           uint32_t mymask = 0;
-#pragma unroll
-          for (int x = 0; x < kHG; ++x) {
+#pragma unroll 1
+          for (uint32_t x = 0; x < hc; ++x) {
             const uint32_t Xx = h0 + x;
-            bool app = (x < (int) hc) && b < Xx && b < n && lab[b] > lab[Xx];
+            const bool app = b < Xx && labb > lab[Xx];
             if (app) {
-              PairTerm t = pair_term(s, g, invlg, idcg, c, b, Xx);
-              stage[lane * kStageStride + x] = make_double2(t.rho, t.d);
+              const PairTerm t = pair_term(s, g, invlg, idcg, c, b, Xx);
+              stage[x * 32 + lane] = make_double2(t.rho, t.d);
             }
             const uint32_t m = __ballot_sync(0xffffffffu, app);
-            if ((int) lane == x) mymask = m;
+            if (lane == x) mymask = m;
           }
           __syncwarp();
           while (mymask) {
             const int bi = __ffs(mymask) - 1;
             mymask &= mymask - 1;
-            const double2 t = stage[bi * kStageStride + lane];
+            const double2 t = stage[lane * 32 + bi];
             aL = fma(-t.x, t.y, aL);                             // lambdamart.cc:138
             aW = fma((1.0 - t.x) * t.x, t.y, aW);                // lambdamart.cc:140
           }
@@ -447,18 +459,18 @@ lambda_kernel(const double *__restrict__ scores, const float *__restrict__ label
         double bL = 0.0, bW = 0.0;
         if (light) { bL = lam[pos[b]]; bW = wgt[pos[b]]; }
         uint32_t mymask = 0;
-#pragma unroll
-        for (int x = 0; x < kHG; ++x) {
+#pragma unroll 1
+        for (uint32_t x = 0; x < hc; ++x) {
           const uint32_t Xx = h0 + x;
           bool app = false;
-          if (x < (int) hc && bvalid && b != Xx) {
+          if (bvalid && b != Xx) {
             const float lx = lab[Xx];
             app = sweep == 0 ? (lx > labb) : (b > Xx && labb > lx);
           }
           if (app) {
-            PairTerm t = sweep == 0 ? pair_term(s, g, invlg, idcg, c, Xx, b)
-                                    : pair_term(s, g, invlg, idcg, c, b, Xx);
-            stage[lane * kStageStride + x] = make_double2(t.rho, t.d);
+            const PairTerm t = sweep == 0 ? pair_term(s, g, invlg, idcg, c, Xx, b)
+                                          : pair_term(s, g, invlg, idcg, c, b, Xx);
+            stage[x * 32 + lane] = make_double2(t.rho, t.d);
             if (light) {
               // lambdamart.cc:137-140 seen from the non-heavy member of the pair
               bL = fma(sweep == 0 ? -t.rho : t.rho, t.d, bL);
@@ -466,14 +478,14 @@ lambda_kernel(const double *__restrict__ scores, const float *__restrict__ label
             }
           }
           const uint32_t m = __ballot_sync(0xffffffffu, app);
-          if ((int) lane == x) mymask = m;
+          if (lane == x) mymask = m;
         }
         if (light) { lam[pos[b]] = bL; wgt[pos[b]] = bW; }
         __syncwarp();
         while (mymask) {
           const int bi = __ffs(mymask) - 1;
           mymask &= mymask - 1;
-          const double2 t = stage[bi * kStageStride + lane];
+          const double2 t = stage[lane * 32 + bi];
           aL = fma(sweep == 0 ? t.x : -t.x, t.y, aL);
           aW = fma((1.0 - t.x) * t.x, t.y, aW);
         }
@@ -481,7 +493,6 @@ lambda_kernel(const double *__restrict__ scores, const float *__restrict__ label
       }
       if (heavy_lane) { lam[pos[X]] = aL; wgt[pos[X]] = aW; }
       __syncwarp();
-      (void) labX;
     }
   }
 }

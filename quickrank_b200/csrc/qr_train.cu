@@ -177,6 +177,8 @@ static int build_binning(qr_ctx *c, const float *d_col) {
   return QR_OK;
 }
 
+static int init_root_counts(qr_ctx *c);
+
 static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t F, const float *labels,
                              const uint64_t *qoffsets, size_t Q, const qr_params *params, qr_ctx **out) {
   if (!feat || !labels || !qoffsets || !params || !out || N == 0 || F == 0 || Q == 0) {
@@ -309,13 +311,23 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   for (int i = c->nslots - 1; i >= 0; --i) c->free_slots.push_back(i);
   const size_t mt = c->max_tasks;
   QR_TRY(dev_alloc(&c->d_blockcnt, (N + kPartItems - 1) / kPartItems + mt + 1));
-  QR_TRY(dev_alloc(&c->d_partials, mt * kSqParts));
+  QR_TRY(dev_alloc(&c->d_partials, mt));
+  c->max_slices = 4096 + (uint32_t) mt;
+  QR_TRY(dev_alloc(&c->d_sq128, c->max_slices));
+  QR_TRY(dev_alloc(&c->d_task_done, mt));
+  QR_CUDA(cudaMemset(c->d_task_done, 0, mt * sizeof(uint32_t)));
+  QR_TRY(dev_alloc(&c->d_part_status, (N + kPartItems - 1) / kPartItems + mt + 1));
+  QR_CUDA(cudaMemset(c->d_part_status, 0, ((N + kPartItems - 1) / kPartItems + mt + 1) * sizeof(unsigned long long)));
+  QR_TRY(dev_alloc(&c->d_ticket, 1));
+  QR_CUDA(cudaMemset(c->d_ticket, 0, sizeof(uint32_t)));
   QR_TRY(dev_alloc(&c->d_tasks, mt));
   QR_CUDA(cudaMallocHost((void **) &c->h_tasks, mt * sizeof(NodeTask)));
   QR_TRY(dev_alloc(&c->d_lcount, mt));
   QR_CUDA(cudaMallocHost((void **) &c->h_lcount, mt * sizeof(uint32_t)));
   QR_TRY(dev_alloc(&c->d_fbest_score, mt * 2 * F));
   QR_TRY(dev_alloc(&c->d_fbest_t, mt * 2 * F));
+  QR_TRY(dev_alloc(&c->d_fbest_lc, mt * 2 * F));
+  QR_TRY(dev_alloc(&c->d_totals, mt * 2));
   QR_TRY(dev_alloc(&c->d_res, mt * 2));
   QR_CUDA(cudaMallocHost((void **) &c->h_res, mt * 2 * sizeof(SplitResult)));
   QR_TRY(dev_alloc(&c->d_segs, maxleaves + 1));
@@ -330,12 +342,16 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_CUDA(cudaMallocHost((void **) &c->h_obv_lcounts, mt * sizeof(uint64_t)));
 
   // opt in to large dynamic shared memory where needed
-  const size_t hist_smem = (size_t) c->max_panel_cells * 12;
+  const size_t hist_smem = (size_t) c->fpp * c->max_thr * 12;
   if (hist_smem <= 200 * 1024) {
     const int bytes = (int) hist_smem;
-    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   }
+  QR_CUDA(cudaGetLastError());
+  QR_TRY(init_root_counts(c));
   QR_CUDA(cudaGetLastError());
   return QR_OK;
 }
@@ -349,7 +365,7 @@ constexpr int kLambdaWarps = 4;
 static int ensure_ranking(qr_ctx *c) {
   if (c->ranking_valid) return QR_OK;
   PhaseTimer pt(c, PH_RANK);
-  const size_t smem = (size_t) kRankWarps * c->maxlen * 12;
+  const size_t smem = (size_t) kRankWarps * rank_smem_per_warp(c->maxlen);
   if (smem > 200 * 1024) { set_error("longest query (%u documents) exceeds the ranking kernel's shared-memory budget", c->maxlen); return QR_ELIMIT; }
   static bool attr_set = false;
   if (!attr_set || smem > 48 * 1024) {
@@ -373,13 +389,14 @@ static int compute_pseudo(qr_ctx *c) {
   }
   QR_TRY(ensure_ranking(c));
   PhaseTimer pt(c, PH_PSEUDO);
-  const size_t smem = (size_t) kLambdaWarps * ((size_t) c->maxlen * 24 + (size_t) 32 * kStageStride * 16);
+  const uint32_t hg = (uint32_t) std::min<size_t>(kHG, std::max<size_t>(1, std::min<size_t>(c->cutoff, c->maxlen)));
+  const size_t smem = (size_t) kLambdaWarps * lambda_smem_per_warp(c->maxlen, hg);
   if (smem > 200 * 1024) { set_error("longest query (%u documents) exceeds the lambda kernel's shared-memory budget", c->maxlen); return QR_ELIMIT; }
   cudaFuncSetAttribute(lambda_kernel<kLambdaWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
   const unsigned grid = (unsigned) ((c->Q + kLambdaWarps - 1) / kLambdaWarps);
   QR_LAUNCH(c, PH_PSEUDO, lambda_kernel<kLambdaWarps>, grid, kLambdaWarps * 32, smem, c->d_scores,
             c->d_labels, c->d_gain, c->d_qoff, c->d_idcg, c->d_invlg, c->d_rankpos, (uint32_t) c->Q,
-            c->maxlen, c->cutoff, c->d_lambda, c->d_weight);
+            c->maxlen, c->cutoff, hg, c->d_lambda, c->d_weight);
   return QR_OK;
 }
 
@@ -450,7 +467,8 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_qndcg, c->d_metric, c->d_ids[0], c->d_ids[1], c->d_leaf_of_doc, c->d_blockcnt,
                   c->d_partials, c->d_hist_sum, c->d_hist_cnt, c->d_fbest_score, c->d_fbest_t, c->d_res,
                   c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
-                  c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts};
+                  c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done, c->d_part_status,
+                  c->d_ticket, c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_hot_rows};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);

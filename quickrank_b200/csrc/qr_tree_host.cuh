@@ -69,12 +69,15 @@ struct NodeHeap {
 };
 
 // Launches the histogram + finalize kernels for the tasks already uploaded to c->d_tasks.
-static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices) {
+// `slots_ready`: the slots were already cleared by the one-pass partition kernel.
+static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, bool slots_ready) {
   const uint32_t F = (uint32_t) c->F;
   {
     PhaseTimer pt(c, PH_HIST);
-    QR_LAUNCH(c, PH_HIST, zero_slots_kernel, dim3(std::max<uint32_t>(1, std::min<uint32_t>(32, (c->ncells + 1023) / 1024)), k),
-              256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells);
+    const bool static_counts = root && !c->exact && c->d_root_cnt != nullptr;
+    if (!slots_ready)
+      QR_LAUNCH(c, PH_HIST, prep_slots_kernel, dim3(std::max<uint32_t>(1, std::min<uint32_t>(32, (c->ncells + 1023) / 1024)), k),
+                256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells, static_counts ? c->d_root_cnt : nullptr);
     if (c->exact) {
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
@@ -86,39 +89,38 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices) {
       QR_LAUNCH(c, PH_HIST, squares_exact_kernel, k, 32, 0, c->d_tasks, c->d_lcount, c->d_lambda, c->d_ids[0],
                 c->d_ids[1], c->d_partials);
     } else {
-      const size_t smem = (size_t) c->max_panel_cells * 12;
+      const size_t smem = (size_t) c->fpp * c->max_thr * 12;
       const bool use_smem = smem <= 200 * 1024;
+      if (total_slices > c->max_slices) { set_error("internal: %u histogram slices > capacity", total_slices); return QR_ECUDA; }
+#define QR_HIST_LAUNCH(SMEMF, COUNTF)                                                                        \
+  QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), 256,            \
+            SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
+            c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->d_hot_rows, c->max_thr)
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
-        if (use_smem)
-          QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true>), dim3(total_slices, c->npanels), 256, smem, c->d_tasks, k,
-                    c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F,
-                    c->d_hist_sum, c->d_hist_cnt, c->ncells);
-        else
-          QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false>), dim3(total_slices, c->npanels), 256, 0, c->d_tasks, k,
-                    c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F,
-                    c->d_hist_sum, c->d_hist_cnt, c->ncells);
+        if (use_smem) {
+          if (static_counts) QR_HIST_LAUNCH(true, false);
+          else QR_HIST_LAUNCH(true, true);
+        } else {
+          if (static_counts) QR_HIST_LAUNCH(false, false);
+          else QR_HIST_LAUNCH(false, true);
+        }
         return QR_OK;
       }));
-      QR_LAUNCH(c, PH_HIST, squares_fast_kernel, dim3(kSqParts, k), 256, 0, c->d_tasks, c->d_lcount, c->d_lambda,
-                c->d_ids[0], c->d_ids[1], c->d_partials);
+#undef QR_HIST_LAUNCH
     }
-    if (c->comm) QR_TRY(comm_reduce_tasks(c, k));
+    if (c->comm) QR_TRY(comm_reduce_tasks(c, k, root));
   }
   {
     PhaseTimer pt(c, PH_SCAN);
-    const uint32_t n_sq = c->exact ? 1u : kSqParts;
-    if (c->exact) {
-      QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3(F, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
-                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t);
-      QR_LAUNCH(c, PH_SCAN, finalize2_kernel<true>, k, 128, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells,
-                c->d_thr_off, F, c->d_qexp, c->d_fbest_score, c->d_fbest_t, c->d_partials, n_sq, c->d_res);
-    } else {
-      QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3(F, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
-                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t);
-      QR_LAUNCH(c, PH_SCAN, finalize2_kernel<false>, k, 128, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells,
-                c->d_thr_off, F, c->d_qexp, c->d_fbest_score, c->d_fbest_t, c->d_partials, n_sq, c->d_res);
-    }
+    if (c->exact)
+      QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3((F + kFinFeat - 1) / kFinFeat, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
+                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
+                c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res);
+    else
+      QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3((F + kFinFeat - 1) / kFinFeat, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
+                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
+                c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res);
     QR_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, (size_t) 2 * k * sizeof(SplitResult), cudaMemcpyDeviceToHost, c->stream));
     if (c->comm) QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     QR_CUDA(cudaStreamSynchronize(c->stream));
@@ -126,11 +128,12 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices) {
   return QR_OK;
 }
 
-// documents per histogram slice so that a round's grid is about four waves of blocks
+// documents per histogram slice so that a round's grid is one full wave: four blocks of the
+// histogram kernel fit on an SM (shared-memory limit), 148 SMs
 static uint32_t pick_hist_dpb(const qr_ctx *c, uint64_t total_docs) {
-  const uint32_t want_slices = std::max<uint32_t>(1, (148u * 4u + c->npanels - 1) / c->npanels);
-  uint64_t dpb = std::max<uint64_t>(1024u, (total_docs + want_slices - 1) / want_slices);
-  dpb = (dpb + 255u) & ~(uint64_t) 255u;
+  const uint32_t want_slices = std::max<uint32_t>(1, (148u * 4u) / c->npanels);
+  uint64_t dpb = std::max<uint64_t>(4096u, (total_docs + want_slices - 1) / want_slices);
+  dpb = (dpb + 511u) & ~(uint64_t) 511u;
   return (uint32_t) std::min<uint64_t>(dpb, 1u << 20);
 }
 
@@ -146,10 +149,71 @@ static int build_root(qr_ctx *c) {
   t.hist_dpb = pick_hist_dpb(c, root.n);
   t.hist_blk0 = 0; t.part_blk0 = 0; t.sq0 = 0; t.fused_sq = 0;
   const uint32_t slices = std::max<uint32_t>(1, (root.n + t.hist_dpb - 1) / t.hist_dpb);
+  t.hist_nblk = slices;
   QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
-  QR_TRY(launch_hist_and_scan(c, 1, slices));
+  QR_TRY(launch_hist_and_scan(c, 1, slices, true, false));
   root.res = c->h_res[0];
   c->nodes.push_back(root);
+  return QR_OK;
+}
+
+// Per-bin document counts of the whole dataset (they do not depend on the pseudo-responses, so the
+// root refresh of every tree reuses them; the reference notes the same at rtnode_histogram.cc:149).
+static int init_root_counts(qr_ctx *c) {
+  if (c->exact) return QR_OK;
+  QR_CUDA(cudaMemsetAsync(c->d_lamq, 0, c->N * sizeof(long long), c->stream));
+  HostNode root;
+  root.n = (uint32_t) c->N;
+  const int slot = alloc_slot(c);
+  NodeTask &t = c->h_tasks[0];
+  memset(&t, 0, sizeof(t));
+  t.n = root.n; t.src = 2; t.whole = 1; t.build_left = 1;
+  t.slotP = -1; t.slotB = slot; t.slotD = -1;
+  t.hist_dpb = pick_hist_dpb(c, root.n);
+  t.hist_nblk = std::max<uint32_t>(1, (root.n + t.hist_dpb - 1) / t.hist_dpb);
+  QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
+  QR_LAUNCH(c, PH_HIST, prep_slots_kernel, dim3(32, 1), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells,
+            (const uint32_t *) nullptr);
+  const size_t smem = (size_t) c->fpp * c->max_thr * 12;
+  const bool use_smem = smem <= 200 * 1024;
+  const uint32_t F = (uint32_t) c->F;
+  QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+    using B = decltype(tag);
+    if (use_smem)
+      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(t.hist_nblk, c->npanels), 256, smem, c->d_tasks, 1u,
+                c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
+                c->d_hist_cnt, c->ncells, c->d_sq128, (const uint4 *) nullptr, c->max_thr);
+    else
+      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(t.hist_nblk, c->npanels), 256, 0, c->d_tasks, 1u,
+                c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
+                c->d_hist_cnt, c->ncells, c->d_sq128, (const uint4 *) nullptr, c->max_thr);
+    return QR_OK;
+  }));
+  QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
+  QR_CUDA(cudaMemcpyAsync(c->d_root_cnt, c->d_hist_cnt + (size_t) slot * c->ncells, c->ncells * sizeof(uint32_t),
+                          cudaMemcpyDeviceToDevice, c->stream));
+  // most frequent bin of every feature (hist_limb_kernel skips it and recovers it by subtraction)
+  std::vector<uint32_t> cnt(c->ncells), hot(c->F);
+  QR_CUDA(cudaMemcpyAsync(cnt.data(), c->d_root_cnt, c->ncells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  QR_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t f = 0; f < c->F; ++f) {
+    uint32_t best = 0;
+    for (uint32_t t = c->thr_off[f]; t < c->thr_off[f + 1]; ++t)
+      if (cnt[t] > cnt[c->thr_off[f] + best]) best = t - c->thr_off[f];
+    hot[f] = best;
+  }
+  // pack them like a panel row (one element per feature slot)
+  std::vector<unsigned char> rows((size_t) c->npanels * 16, 0);
+  for (size_t f = 0; f < c->F; ++f) {
+    const size_t pnl = f / c->fpp, j = f % c->fpp;
+    if (c->bin_bytes == 1) rows[pnl * 16 + j] = (unsigned char) hot[f];
+    else { const uint16_t v = (uint16_t) hot[f]; memcpy(&rows[pnl * 16 + 2 * j], &v, 2); }
+  }
+  QR_TRY(dev_alloc(&c->d_hot_rows, c->npanels));
+  QR_CUDA(cudaMemcpy(c->d_hot_rows, rows.data(), rows.size(), cudaMemcpyHostToDevice));
+  QR_CUDA(cudaStreamSynchronize(c->stream));
+  int s2 = slot;
+  release_slot(c, s2);
   return QR_OK;
 }
 
@@ -189,26 +253,38 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     t.hist_blk0 = hist_blk;
     t.hist_dpb = dpb;
     const uint64_t built_n = c->comm ? nd.n : (t.build_left ? lc : rc);
-    hist_blk += std::max<uint32_t>(1, (uint32_t) ((built_n + dpb - 1) / dpb));
-    t.sq0 = j * kSqParts;
+    t.hist_nblk = std::max<uint32_t>(1, (uint32_t) ((built_n + dpb - 1) / dpb));
+    hist_blk += t.hist_nblk;
+    t.lcount = (uint32_t) lc;
+    t.lc_known = c->comm ? 0u : 1u;
+    t.sq0 = j;
     t.fused_sq = 1;
     t.parent_squares = nd.res.squares;
   }
   QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
+  const bool onepass = c->comm == nullptr;
   {
     PhaseTimer pt(c, PH_PARTITION);
     QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
       using B = decltype(tag);
-      QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
-                c->d_ids[0], c->d_ids[1], c->d_blockcnt);
-      QR_LAUNCH(c, PH_PARTITION, part_prefix_kernel, k, 256, 0, c->d_tasks, c->d_blockcnt, c->d_lcount);
-      QR_LAUNCH(c, PH_PARTITION, part_scatter_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
-                c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_blockcnt, c->d_lcount);
+      if (onepass) {
+        c->part_epoch++;
+        QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
+                  c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
+                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells);
+        c->ticket_base += part_blk;
+      } else {
+        QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
+                  c->d_ids[0], c->d_ids[1], c->d_blockcnt);
+        QR_LAUNCH(c, PH_PARTITION, part_prefix_kernel, k, 256, 0, c->d_tasks, c->d_blockcnt, c->d_lcount);
+        QR_LAUNCH(c, PH_PARTITION, part_scatter_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
+                  c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_blockcnt, c->d_lcount);
+      }
       return QR_OK;
     }));
   }
   if (build_child_hists) {
-    QR_TRY(launch_hist_and_scan(c, k, hist_blk));
+    QR_TRY(launch_hist_and_scan(c, k, hist_blk, false, onepass));
   } else if (c->comm) {
     QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     QR_CUDA(cudaStreamSynchronize(c->stream));

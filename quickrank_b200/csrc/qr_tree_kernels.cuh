@@ -21,8 +21,12 @@ struct NodeTask {
   uint32_t part_blk0;    // first flat partition block of this task
   uint32_t hist_blk0;    // first flat histogram slice of this task
   uint32_t hist_dpb;     // documents per histogram slice
+  uint32_t hist_nblk;    // histogram slices of this task
   uint32_t sq0;          // first squares partial of this task
   uint32_t fused_sq;     // REFERENCE: 1 = fma chain (child ctor), 0 = mul+add (root update)
+  uint32_t lcount;       // local left count when the host knows it (single GPU), see lc_known
+  uint32_t lc_known;     // 0: kernels read the count computed by part_prefix_kernel instead
+  uint32_t pad0;
   double parent_squares;
 };
 
@@ -41,6 +45,10 @@ __device__ __forceinline__ uint32_t find_task_by(const NodeTask *tasks, uint32_t
 }
 
 // segment (in buffer `dst`, or identity when whole && src == 2) whose histogram is built
+__device__ __forceinline__ uint32_t task_lcount(const NodeTask &t, const uint32_t *lcount, uint32_t task) {
+  return t.whole ? 0u : (t.lc_known ? t.lcount : lcount[task]);
+}
+
 __device__ __forceinline__ void built_segment(const NodeTask &t, uint32_t lcount, uint32_t &begin,
                                               uint32_t &len) {
   if (t.whole) { begin = t.lo; len = t.n; }
@@ -48,14 +56,18 @@ __device__ __forceinline__ void built_segment(const NodeTask &t, uint32_t lcount
   else { begin = t.lo + lcount; len = t.n - lcount; }
 }
 
-__global__ void zero_slots_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum,
-                                  uint32_t *hcnt, uint32_t ncells) {
-  const int slot = tasks[blockIdx.y].slotB;
-  unsigned long long *s = hsum + (size_t) slot * ncells;
-  uint32_t *c = hcnt + (size_t) slot * ncells;
+// Clears the histogram slot each task builds into.  For the root refresh the per-bin counts never
+// change from tree to tree ("count doesn't change, so no need to re-compute",
+// rtnode_histogram.cc:149): they are copied from the table made at init instead of being recounted.
+__global__ void prep_slots_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum,
+                                  uint32_t *hcnt, uint32_t ncells, const uint32_t *__restrict__ root_cnt) {
+  const NodeTask t = tasks[blockIdx.y];
+  unsigned long long *s = hsum + (size_t) t.slotB * ncells;
+  uint32_t *c = hcnt + (size_t) t.slotB * ncells;
+  const bool copy = t.whole && root_cnt != nullptr;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += gridDim.x * blockDim.x) {
     s[i] = 0ull;
-    c[i] = 0u;
+    c[i] = copy ? root_cnt[i] : 0u;
   }
 }
 
@@ -163,6 +175,96 @@ part_scatter_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const u
   }
 }
 
+// Single-pass variant (used when the host knows every task's left count, i.e. on one GPU):
+// blocks take a ticket, count their own lefts, publish the count and obtain the number of lefts
+// in the preceding blocks of the same task by decoupled look-back; the list order is preserved.
+// Each block also clears its share of the histogram slot the task is about to build into.
+// status word: epoch << 32 | flag << 30 | count   (flag 1: block aggregate, 2: inclusive prefix)
+template <typename BinT>
+__global__ void __launch_bounds__(256)
+partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint4 *__restrict__ panels,
+                         size_t N, const uint32_t *__restrict__ ids0, const uint32_t *__restrict__ ids1,
+                         uint32_t *out0, uint32_t *out1, unsigned long long *status, uint32_t *ticket,
+                         uint32_t ticket_base, uint32_t epoch, unsigned long long *hsum, uint32_t *hcnt,
+                         uint32_t ncells) {
+  __shared__ uint32_t s_vb, s_task, s_prefix;
+  __shared__ uint32_t wc[8][8];
+  if (threadIdx.x == 0) {
+    s_vb = atomicAdd(ticket, 1u) - ticket_base;
+    s_task = find_task_by(tasks, ntasks, s_vb, false);
+  }
+  __syncthreads();
+  const uint32_t vb = s_vb;
+  const NodeTask t = tasks[s_task];
+  const uint32_t lb = vb - t.part_blk0;
+  const uint32_t nb = max(1u, (t.n + kPartItems - 1) / kPartItems);
+  if (t.slotB >= 0) {
+    const uint32_t chunk = (ncells + nb - 1) / nb;
+    const uint32_t z0 = lb * chunk, z1 = min(ncells, z0 + chunk);
+    unsigned long long *zs = hsum + (size_t) t.slotB * ncells;
+    uint32_t *zc = hcnt + (size_t) t.slotB * ncells;
+    for (uint32_t i = z0 + threadIdx.x; i < z1; i += 256) { zs[i] = 0ull; zc[i] = 0u; }
+  }
+  const uint32_t *src = t.src == 1 ? ids1 : ids0;
+  uint32_t *dst = t.dst == 1 ? out1 : out0;
+  const uint32_t b0 = lb * kPartItems, e = min(t.n, b0 + kPartItems);
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  uint32_t d[8], wr[8];
+  uint32_t flags = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const uint32_t i = b0 + r * 256 + threadIdx.x;
+    bool left = false;
+    d[r] = 0;
+    if (i < e) {
+      d[r] = t.src == 2 ? t.lo + i : src[t.lo + i];
+      left = load_bin<BinT>(panels, N, t.f, d[r]) <= t.t;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, left);
+    if (lane == 0) wc[r][warp] = __popc(bal);
+    wr[r] = __popc(bal & ((1u << lane) - 1u));
+    flags |= (left ? 1u : 0u) << r;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (int r = 0; r < 8; ++r)
+      for (int w = 0; w < 8; ++w) total += wc[r][w];
+    volatile unsigned long long *st = status;
+    const unsigned long long ep = (unsigned long long) epoch << 32;
+    uint32_t prefix = 0;
+    if (lb == 0) {
+      st[vb] = ep | (2ull << 30) | total;
+    } else {
+      st[vb] = ep | (1ull << 30) | total;
+      for (uint32_t j = vb - 1;; --j) {
+        unsigned long long v;
+        do { v = st[j]; } while ((v >> 32) != epoch || ((v >> 30) & 3ull) == 0ull);
+        prefix += (uint32_t) (v & 0x3fffffffull);
+        if (((v >> 30) & 3ull) == 2ull || j == t.part_blk0) break;
+      }
+      st[vb] = ep | (2ull << 30) | (prefix + total);
+    }
+    s_prefix = prefix;
+  }
+  __syncthreads();
+  uint32_t run = s_prefix;
+  const uint32_t lc = t.lcount;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    uint32_t before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { const uint32_t c = wc[r][w]; if (w < (int) warp) before += c; tot += c; }
+    const uint32_t i = b0 + r * 256 + threadIdx.x;
+    if (i < e) {
+      const uint32_t lrank = run + before + wr[r];
+      if ((flags >> r) & 1u) dst[t.lo + lrank] = d[r];
+      else dst[t.lo + lc + (i - lrank)] = d[r];
+    }
+    run += tot;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // FAST histograms: RTNodeHistogram::update / RTNodeHistogram(parent, sampleids, ...) scatter loops
 // (rtnode_histogram.cc:51-58, 183-191) in 64-bit fixed point.  Shared memory has no native 64-bit
@@ -172,37 +274,85 @@ part_scatter_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const u
 // the lanes of a warp hit different features' cells.  Integer sums are order-independent: the
 // result is deterministic and identical for any slicing (and any number of GPUs).
 // ------------------------------------------------------------------------------------------
-template <typename BinT, bool SMEM>
-__global__ void __launch_bounds__(256)
+// 128-bit unsigned accumulator for the exact sum of squared fixed-point pseudo-responses
+struct U128 { unsigned long long lo, hi; };
+__device__ __forceinline__ void u128_add(U128 &a, unsigned long long lo, unsigned long long hi) {
+  a.lo += lo;
+  a.hi += hi + (a.lo < lo);
+}
+
+// one document's panel row into the block's limb histogram.  Shared-memory cells are addressed as
+// slot * stride + bin (stride = widest feature of the panel), so no table look-up is needed; `hotx`
+// is the row XORed with the panel's most-frequent bins: a zero element means "hot bin, skip" —
+// those documents are recovered at the end as (block total) - (all other cells), exactly, because
+// the sums are integers.  Half of the features at a time keeps the register footprint at 64.
+template <typename BinT, bool COUNT>
+__device__ __forceinline__ void hist_add_row_smem(const uint4 &row, const uint4 &hotx, long long q, uint32_t rot,
+                                                  uint32_t nf, uint32_t stride, uint32_t *s_lo, int32_t *s_hi,
+                                                  uint32_t *s_cnt) {
+  constexpr int FPP = kPanelBytes / sizeof(BinT);
+  constexpr int H = FPP < 8 ? FPP : 8;
+  const uint32_t qlo = (uint32_t) q;
+  const int32_t qhi = (int32_t) (q >> 32);
+#pragma unroll
+  for (int h0 = 0; h0 < FPP; h0 += H) {
+    uint32_t cell[H], old[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const uint32_t slot = (h0 + j + rot) & (FPP - 1);
+      const bool on = slot < nf && extract_bin<BinT>(hotx, h0 + j) != 0u;
+      cell[j] = on ? slot * stride + extract_bin<BinT>(row, h0 + j) : 0xffffffffu;
+      if (on) old[j] = atomicAdd(s_lo + cell[j], qlo);
+    }
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      if (cell[j] != 0xffffffffu) {
+        const int32_t carry = (old[j] + qlo) < old[j];
+        atomicAdd(s_hi + cell[j], qhi + carry);
+        if (COUNT) atomicAdd(s_cnt + cell[j], 1u);
+      }
+    }
+  }
+}
+
+template <typename BinT, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(256, 4)
 hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint32_t *__restrict__ lcount,
                  const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ ids0,
                  const uint32_t *__restrict__ ids1, const long long *__restrict__ lamq,
                  const uint32_t *__restrict__ thr_off, uint32_t F, unsigned long long *hsum,
-                 uint32_t *hcnt, uint32_t ncells) {
+                 uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials,
+                 const uint4 *__restrict__ hot_rows, uint32_t stride) {
   constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ uint32_t s_base[FPP];
+  __shared__ uint32_t s_base[FPP + 1];
   __shared__ uint32_t s_task;
+  __shared__ U128 s_sq[8];
+  __shared__ long long s_totq[8];
+  __shared__ uint32_t s_totn[8];
   if (threadIdx.x == 0) s_task = find_task_by(tasks, ntasks, blockIdx.x, true);
   __syncthreads();
   const NodeTask t = tasks[s_task];
   uint32_t seg0, seglen;
-  built_segment(t, t.whole ? 0u : lcount[s_task], seg0, seglen);
+  built_segment(t, task_lcount(t, lcount, s_task), seg0, seglen);
   const uint32_t begin = (blockIdx.x - t.hist_blk0) * t.hist_dpb;
-  if (begin >= seglen) return;
+  const uint32_t p = blockIdx.y;
+  if (begin >= seglen) {
+    if (p == 0 && threadIdx.x == 0) sq_partials[blockIdx.x] = make_ulonglong2(0ull, 0ull);
+    return;
+  }
   const uint32_t end = min(seglen, begin + t.hist_dpb);
 
-  const uint32_t p = blockIdx.y;
   const uint32_t f0 = p * FPP;
   const uint32_t nf = min(FPP, F - f0);
   const uint32_t cell0 = thr_off[f0];
-  const uint32_t cells = thr_off[f0 + nf] - cell0;
+  const uint32_t scells = SMEM ? FPP * stride : 0u;   // shared-memory cells (uniform stride)
   uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw);
-  int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + (SMEM ? cells : 0));
-  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_hi + (SMEM ? cells : 0));
-  if (threadIdx.x < FPP) s_base[threadIdx.x] = threadIdx.x < nf ? thr_off[f0 + threadIdx.x] - cell0 : 0u;
+  int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + scells);
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_hi + scells);
+  if (threadIdx.x <= FPP) s_base[threadIdx.x] = thr_off[f0 + min(threadIdx.x, nf)] - cell0;
   if (SMEM)
-    for (uint32_t i = threadIdx.x; i < cells; i += 256) { s_lo[i] = 0u; s_hi[i] = 0; s_cnt[i] = 0u; }
+    for (uint32_t i = threadIdx.x; i < scells; i += 256) { s_lo[i] = 0u; s_hi[i] = 0; if (COUNT) s_cnt[i] = 0u; }
   __syncthreads();
 
   unsigned long long *gs = hsum + (size_t) t.slotB * ncells + cell0;
@@ -210,49 +360,113 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
   const bool identity = t.whole && t.src == 2;
   const uint32_t *ids = (t.whole ? t.src : t.dst) == 1 ? ids1 : ids0;
   const uint32_t rot = lane_id() & (FPP - 1);
+  const uint32_t rotb = rot * (uint32_t) sizeof(BinT);
   const uint4 *prow = panels + (size_t) p * N;
-  for (uint32_t i = begin + threadIdx.x; i < end; i += 256) {
-    const uint32_t d = identity ? seg0 + i : ids[seg0 + i];
-    const uint4 row = rotate_bytes(prow[d], rot * (uint32_t) sizeof(BinT));
-    const long long q = lamq[d];
+  // the panel's most frequent bins, rotated like the rows; all-ones elements never match a bin
+  const bool bypass = SMEM && hot_rows != nullptr;
+  const uint4 hot = bypass ? rotate_bytes(hot_rows[p], rotb) : make_uint4(0u, 0u, 0u, 0u);
+  U128 sq{0ull, 0ull};
+  long long totq = 0;      // sum of the fixed-point pseudo-responses of this thread's documents
+  uint32_t totn = 0;
+  // two documents per iteration: their loads are independent, which doubles the memory-level
+  // parallelism of the gather
+  for (uint32_t i = begin + threadIdx.x; i < end; i += 512) {
+    const uint32_t i1 = i + 256;
+    const bool has1 = i1 < end;
+    const uint32_t d0 = identity ? seg0 + i : ids[seg0 + i];
+    const uint32_t d1 = has1 ? (identity ? seg0 + i1 : ids[seg0 + i1]) : d0;
+    const uint4 raw0 = prow[d0];
+    const uint4 raw1 = prow[d1];
+    const long long q0 = lamq[d0];
+    const long long q1 = lamq[d1];
+    totq += q0 + (has1 ? q1 : 0ll);
+    totn += has1 ? 2u : 1u;
+    if (p == 0) {   // squares_sum_ (rtnode_histogram.cc:65-69) as an exact integer
+      const unsigned long long a0 = (unsigned long long) (q0 < 0 ? -q0 : q0);
+      u128_add(sq, a0 * a0, __umul64hi(a0, a0));
+      if (has1) {
+        const unsigned long long a1 = (unsigned long long) (q1 < 0 ? -q1 : q1);
+        u128_add(sq, a1 * a1, __umul64hi(a1, a1));
+      }
+    }
     if (SMEM) {
-      const uint32_t qlo = (uint32_t) q;
-      const int32_t qhi = (int32_t) (q >> 32);
-      uint32_t cell[FPP], old[FPP];
-#pragma unroll
-      for (int j = 0; j < (int) FPP; ++j) {
-        const uint32_t slot = (j + rot) & (FPP - 1);
-        cell[j] = slot < nf ? s_base[slot] + extract_bin<BinT>(row, j) : 0xffffffffu;
-        if (cell[j] != 0xffffffffu) old[j] = atomicAdd(s_lo + cell[j], qlo);
-      }
-#pragma unroll
-      for (int j = 0; j < (int) FPP; ++j) {
-        if (cell[j] != 0xffffffffu) {
-          const int32_t carry = (old[j] + qlo) < old[j];
-          atomicAdd(s_hi + cell[j], qhi + carry);
-          atomicAdd(s_cnt + cell[j], 1u);
-        }
-      }
+      const uint4 r0 = rotate_bytes(raw0, rotb), r1 = rotate_bytes(raw1, rotb);
+      const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+      const uint4 x0 = bypass ? make_uint4(r0.x ^ hot.x, r0.y ^ hot.y, r0.z ^ hot.z, r0.w ^ hot.w) : ones;
+      const uint4 x1 = bypass ? make_uint4(r1.x ^ hot.x, r1.y ^ hot.y, r1.z ^ hot.z, r1.w ^ hot.w) : ones;
+      hist_add_row_smem<BinT, COUNT>(r0, x0, q0, rot, nf, stride, s_lo, s_hi, s_cnt);
+      if (has1) hist_add_row_smem<BinT, COUNT>(r1, x1, q1, rot, nf, stride, s_lo, s_hi, s_cnt);
     } else {
 #pragma unroll
-      for (int j = 0; j < (int) FPP; ++j) {
-        const uint32_t slot = (j + rot) & (FPP - 1);
-        if (slot < nf) {
-          const uint32_t c = s_base[slot] + extract_bin<BinT>(row, j);
-          atomicAdd(gs + c, (unsigned long long) q);
-          atomicAdd(gc + c, 1u);
+      for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !has1) break;
+        const uint4 row = rotate_bytes(k ? raw1 : raw0, rotb);
+        const long long q = k ? q1 : q0;
+#pragma unroll
+        for (int j = 0; j < (int) FPP; ++j) {
+          const uint32_t slot = (j + rot) & (FPP - 1);
+          if (slot < nf) {
+            const uint32_t c = s_base[slot] + extract_bin<BinT>(row, j);
+            atomicAdd(gs + c, (unsigned long long) q);
+            if (COUNT) atomicAdd(gc + c, 1u);
+          }
         }
       }
     }
   }
+  if (p == 0) {   // block total of the squares: integer, so any reduction shape gives the same value
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long ol = __shfl_xor_sync(0xffffffffu, sq.lo, o);
+      const unsigned long long oh = __shfl_xor_sync(0xffffffffu, sq.hi, o);
+      u128_add(sq, ol, oh);
+    }
+    if (lane_id() == 0) s_sq[threadIdx.x >> 5] = sq;
+  }
+  if (bypass) {
+    for (int o = 16; o > 0; o >>= 1) {
+      totq += __shfl_xor_sync(0xffffffffu, totq, o);
+      totn += __shfl_xor_sync(0xffffffffu, totn, o);
+    }
+    if (lane_id() == 0) { s_totq[threadIdx.x >> 5] = totq; s_totn[threadIdx.x >> 5] = totn; }
+  }
+  if (SMEM || p == 0) __syncthreads();
+  if (p == 0 && threadIdx.x == 0) {
+    U128 tot = s_sq[0];
+    for (int w = 1; w < 8; ++w) u128_add(tot, s_sq[w].lo, s_sq[w].hi);
+    sq_partials[blockIdx.x] = make_ulonglong2(tot.lo, tot.hi);
+  }
   if (SMEM) {
-    __syncthreads();
-    for (uint32_t i = threadIdx.x; i < cells; i += 256) {
-      const uint32_t cn = s_cnt[i];
-      if (cn) {
+    // flush: one warp per feature slot walks the slot's cells; the hot cell (never touched above)
+    // receives block total minus the others
+    long long bq = 0;
+    uint32_t bn = 0;
+    if (bypass)
+      for (int w = 0; w < 8; ++w) { bq += s_totq[w]; bn += s_totn[w]; }
+    const BinT *hotb = reinterpret_cast<const BinT *>(hot_rows + p);
+    for (uint32_t slot = threadIdx.x >> 5; slot < nf; slot += 8) {
+      const uint32_t width = s_base[slot + 1] - s_base[slot];
+      long long oq = 0;
+      uint32_t on = 0;
+      for (uint32_t b = lane_id(); b < width; b += 32) {
+        const uint32_t i = slot * stride + b;
         const long long v = ((long long) s_hi[i] << 32) + (long long) s_lo[i];
-        atomicAdd(gs + i, (unsigned long long) v);
-        atomicAdd(gc + i, cn);
+        const uint32_t cn = COUNT ? s_cnt[i] : 0u;
+        if (v != 0) atomicAdd(gs + s_base[slot] + b, (unsigned long long) v);
+        if (COUNT && cn) atomicAdd(gc + s_base[slot] + b, cn);
+        oq += v;
+        on += cn;
+      }
+      if (bypass) {
+        for (int o = 16; o > 0; o >>= 1) {
+          oq += __shfl_xor_sync(0xffffffffu, oq, o);
+          on += __shfl_xor_sync(0xffffffffu, on, o);
+        }
+        if (lane_id() == 0) {
+          const uint32_t hb = hotb[slot];
+          const long long hv = bq - oq;
+          if (hv != 0) atomicAdd(gs + s_base[slot] + hb, (unsigned long long) hv);
+          if (COUNT && bn != on) atomicAdd(gc + s_base[slot] + hb, bn - on);
+        }
       }
     }
   }
@@ -274,7 +488,7 @@ hist_exact_kernel(const NodeTask *__restrict__ tasks, const uint32_t *__restrict
   if (f >= F) return;
   const NodeTask t = tasks[blockIdx.y];
   uint32_t seg0, n;
-  built_segment(t, t.whole ? 0u : lcount[blockIdx.y], seg0, n);
+  built_segment(t, task_lcount(t, lcount, blockIdx.y), seg0, n);
   const bool identity = t.whole && t.src == 2;
   const uint32_t *ids = (t.whole ? t.src : t.dst) == 1 ? ids1 : ids0;
   const uint32_t lane = lane_id();
@@ -311,7 +525,7 @@ __global__ void squares_exact_kernel(const NodeTask *__restrict__ tasks, const u
                                      const uint32_t *__restrict__ ids1, double *partials) {
   const NodeTask t = tasks[blockIdx.x];
   uint32_t seg0, n;
-  built_segment(t, t.whole ? 0u : lcount[blockIdx.x], seg0, n);
+  built_segment(t, task_lcount(t, lcount, blockIdx.x), seg0, n);
   const bool identity = t.whole && t.src == 2;
   const uint32_t *ids = (t.whole ? t.src : t.dst) == 1 ? ids1 : ids0;
   const uint32_t lane = lane_id();
@@ -338,7 +552,7 @@ squares_fast_kernel(const NodeTask *__restrict__ tasks, const uint32_t *__restri
   __shared__ double part[256];
   const NodeTask t = tasks[blockIdx.y];
   uint32_t seg0, n;
-  built_segment(t, t.whole ? 0u : lcount[blockIdx.y], seg0, n);
+  built_segment(t, task_lcount(t, lcount, blockIdx.y), seg0, n);
   const bool identity = t.whole && t.src == 2;
   const uint32_t *ids = (t.whole ? t.src : t.dst) == 1 ? ids1 : ids0;
   const uint32_t per = (n + kSqParts - 1) / kSqParts;
@@ -366,159 +580,255 @@ __device__ __forceinline__ double cell_value(bool exact, unsigned long long raw,
   return exact ? __longlong_as_double((long long) raw) : (double) (long long) raw * inv;
 }
 
+constexpr uint32_t kFinFeat = 8;   // features (= warps) per finalize block
+
 template <bool EXACT>
 __global__ void __launch_bounds__(256)
 finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, uint32_t *hcnt,
                 uint32_t ncells, const uint32_t *__restrict__ thr_off, uint32_t F, uint32_t minls,
-                const int *__restrict__ qexp, double *fbest_score, uint32_t *fbest_t) {
-  const uint32_t f = blockIdx.x, task = blockIdx.y;
+                const int *__restrict__ qexp, double *fbest_score, uint32_t *fbest_t, uint32_t *fbest_lc,
+                ulonglong2 *totals, const ulonglong2 *__restrict__ sq128,
+                const double *__restrict__ sq_exact, uint32_t *task_done, SplitResult *res) {
+  const uint32_t task = blockIdx.y;
   const NodeTask t = tasks[task];
-  const uint32_t c0 = thr_off[f], cells = thr_off[f + 1] - c0;
-  unsigned long long *Bs = hsum + (size_t) t.slotB * ncells + c0;
-  uint32_t *Bc = hcnt + (size_t) t.slotB * ncells + c0;
-  __shared__ long long w_sum[8];
-  __shared__ uint32_t w_cnt[8];
-  __shared__ long long carry_sum;
-  __shared__ uint32_t carry_cnt;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t f = blockIdx.x * kFinFeat + warp;
+  const double inv = EXACT ? 1.0 : ldexp(1.0, -*qexp);
+  const int nchild = t.whole ? 1 : 2;
   __shared__ double wb[8];
-  __shared__ uint32_t wt[8];
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  __shared__ uint32_t wt[8], wt2[8], wl2[8];
+  __shared__ uint32_t s_last;
 
-  if (!EXACT) {
-    // inclusive scan of the per-bin fixed-point sums and counts, tiles of 256 bins
-    if (threadIdx.x == 0) { carry_sum = 0; carry_cnt = 0; }
-    __syncthreads();
-    for (uint32_t t0 = 0; t0 < cells; t0 += 256) {
-      const uint32_t k = t0 + threadIdx.x;
-      long long v = k < cells ? (long long) Bs[k] : 0;
-      uint32_t cv = k < cells ? Bc[k] : 0u;
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long pv = __shfl_up_sync(0xffffffffu, v, o);
-        const uint32_t pc = __shfl_up_sync(0xffffffffu, cv, o);
-        if ((int) lane >= o) { v += pv; cv += pc; }
+  // one warp per feature; no block-level synchronisation on this path.  Features with at most
+  // kFinChunks * 32 cells are processed entirely in registers: every load is issued up front.
+  if (f < F) {
+    const uint32_t c0 = thr_off[f], cells = thr_off[f + 1] - c0;
+    unsigned long long *Bs = hsum + (size_t) t.slotB * ncells + c0;
+    uint32_t *Bc = hcnt + (size_t) t.slotB * ncells + c0;
+    const bool two = nchild == 2;
+    const unsigned long long *Ps = two ? hsum + (size_t) t.slotP * ncells + c0 : Bs;
+    const uint32_t *Pc = two ? hcnt + (size_t) t.slotP * ncells + c0 : Bc;
+    unsigned long long *Ds = two ? hsum + (size_t) t.slotD * ncells + c0 : Bs;
+    uint32_t *Dc = two ? hcnt + (size_t) t.slotD * ncells + c0 : Bc;
+    constexpr int kFinChunks = 9;
+    if (cells <= kFinChunks * 32) {
+      unsigned long long bs[kFinChunks], ps[kFinChunks];
+      uint32_t bc[kFinChunks], pc[kFinChunks];
+#pragma unroll
+      for (int ch = 0; ch < kFinChunks; ++ch) {
+        const uint32_t k = ch * 32 + lane;
+        const bool in = k < cells;
+        bs[ch] = in ? Bs[k] : 0ull;
+        bc[ch] = in ? Bc[k] : 0u;
+        ps[ch] = (in && two) ? Ps[k] : 0ull;
+        pc[ch] = (in && two) ? Pc[k] : 0u;
       }
-      if (lane == 31) { w_sum[warp] = v; w_cnt[warp] = cv; }
-      __syncthreads();
-      long long add = carry_sum;
-      uint32_t addc = carry_cnt;
-      for (uint32_t w = 0; w < warp; ++w) { add += w_sum[w]; addc += w_cnt[w]; }
-      v += add; cv += addc;
-      if (k < cells) { Bs[k] = (unsigned long long) v; Bc[k] = cv; }
-      __syncthreads();
-      if (threadIdx.x == 255) { carry_sum = v; carry_cnt = cv; }
-      __syncthreads();
-    }
-  }
-  __syncthreads();
-  const double inv = EXACT ? 1.0 : ldexp(1.0, -*qexp);
-  const int nchild = t.whole ? 1 : 2;
-
-  for (int pass = 0; pass < nchild; ++pass) {
-    unsigned long long *S = Bs;
-    uint32_t *C = Bc;
-    if (pass == 1) {
-      const unsigned long long *Ps = hsum + (size_t) t.slotP * ncells + c0;
-      const uint32_t *Pc = hcnt + (size_t) t.slotP * ncells + c0;
-      S = hsum + (size_t) t.slotD * ncells + c0;
-      C = hcnt + (size_t) t.slotD * ncells + c0;
-      for (uint32_t k = threadIdx.x; k < cells; k += 256) {
-        if (EXACT) {
-          const double pv = __longlong_as_double((long long) Ps[k]);
-          const double bv = __longlong_as_double((long long) Bs[k]);
-          S[k] = (unsigned long long) __double_as_longlong(pv - bv);   // rtnode_histogram.cc:82
-        } else {
-          S[k] = Ps[k] - Bs[k];
+      if (!EXACT) {   // inclusive prefix over bins (rtnode_histogram.cc:59-62), exact in fixed point
+        long long carry = 0;
+        uint32_t carryc = 0;
+#pragma unroll
+        for (int ch = 0; ch < kFinChunks; ++ch) {
+          long long v = (long long) bs[ch];
+          uint32_t cv = bc[ch];
+          for (int o = 1; o < 32; o <<= 1) {
+            const long long pv = __shfl_up_sync(0xffffffffu, v, o);
+            const uint32_t pcv = __shfl_up_sync(0xffffffffu, cv, o);
+            if ((int) lane >= o) { v += pv; cv += pcv; }
+          }
+          v += carry; cv += carryc;
+          bs[ch] = (unsigned long long) v; bc[ch] = cv;
+          carry = __shfl_sync(0xffffffffu, v, 31);
+          carryc = __shfl_sync(0xffffffffu, cv, 31);
         }
-        C[k] = Pc[k] - Bc[k];
+#pragma unroll
+        for (int ch = 0; ch < kFinChunks; ++ch) {
+          const uint32_t k = ch * 32 + lane;
+          if (k < cells) { Bs[k] = bs[ch]; Bc[k] = bc[ch]; }
+        }
       }
-      __syncthreads();
-    }
-    // split scan (rt.cc:272-291): strict '>' in ascending t, start value -1
-    const double s = cell_value(EXACT, S[cells - 1], inv);
-    const uint32_t cn = C[cells - 1];
-    double best = -1.0;
-    uint32_t best_t = 0xffffffffu;
-    for (uint32_t k = threadIdx.x; k < cells; k += 256) {
-      const uint32_t lc = C[k], rc = cn - lc;
-      if (lc >= minls && rc >= minls) {
-        const double ls = cell_value(EXACT, S[k], inv);
-        const double rs = s - ls;
-        const double score = ls * ls / (double) lc + rs * rs / (double) rc;
-        if (score > best) { best = score; best_t = k; }
+      const uint32_t lastk = cells - 1;
+      for (int pass = 0; pass < nchild; ++pass) {
+        if (pass == 1) {   // derived child = parent - built (rtnode_histogram.cc:79-85, 209-216)
+#pragma unroll
+          for (int ch = 0; ch < kFinChunks; ++ch) {
+            const uint32_t k = ch * 32 + lane;
+            if (EXACT) {
+              const double pv = __longlong_as_double((long long) ps[ch]);
+              const double bv = __longlong_as_double((long long) bs[ch]);
+              bs[ch] = (unsigned long long) __double_as_longlong(pv - bv);   // rtnode_histogram.cc:82
+            } else {
+              bs[ch] = ps[ch] - bs[ch];
+            }
+            bc[ch] = pc[ch] - bc[ch];
+            if (k < cells) { Ds[k] = bs[ch]; Dc[k] = bc[ch]; }
+          }
+        }
+        // totals live in the lane/chunk that owns the last cell
+        unsigned long long sraw = 0;
+        uint32_t cn = 0;
+#pragma unroll
+        for (int ch = 0; ch < kFinChunks; ++ch)
+          if ((uint32_t) ch == lastk / 32) {
+            sraw = __shfl_sync(0xffffffffu, bs[ch], lastk % 32);
+            cn = __shfl_sync(0xffffffffu, bc[ch], lastk % 32);
+          }
+        const double s = cell_value(EXACT, sraw, inv);
+        // split scan (rt.cc:272-291): strict '>' in ascending t, start value -1
+        double best = -1.0;
+        uint32_t best_t = 0xffffffffu, best_lc = 0;
+#pragma unroll
+        for (int ch = 0; ch < kFinChunks; ++ch) {
+          const uint32_t k = ch * 32 + lane;
+          const uint32_t lc = bc[ch], rc = cn - lc;
+          if (k < cells && lc >= minls && rc >= minls) {
+            const double ls = cell_value(EXACT, bs[ch], inv);
+            const double rs = s - ls;
+            const double score = ls * ls / (double) lc + rs * rs / (double) rc;
+            if (score > best) { best = score; best_t = k; best_lc = lc; }
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) {   // arg-max, ties to the smaller t
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const uint32_t ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+          const uint32_t ol = __shfl_xor_sync(0xffffffffu, best_lc, o);
+          if (ob > best || (ob == best && ot < best_t)) { best = ob; best_t = ot; best_lc = ol; }
+        }
+        if (lane == 0) {
+          // pass 0 scanned the built child, pass 1 the derived one; child 0 = left
+          const int child = t.whole ? 0 : ((pass == 0) == (t.build_left != 0) ? 0 : 1);
+          const size_t o = ((size_t) task * 2 + child) * F + f;
+          fbest_score[o] = best;
+          fbest_t[o] = best_t;
+          fbest_lc[o] = best_lc;
+          // node size and sum are read from feature 0's last bin (rtnode.h:99-104)
+          if (f == 0) totals[(size_t) task * 2 + child] = make_ulonglong2((unsigned long long) cn, sraw);
+        }
+      }
+    } else {
+      if (!EXACT) {
+        long long carry = 0;
+        uint32_t carryc = 0;
+        for (uint32_t base = 0; base < cells; base += 32) {
+          const uint32_t k = base + lane;
+          long long v = k < cells ? (long long) Bs[k] : 0;
+          uint32_t cv = k < cells ? Bc[k] : 0u;
+          for (int o = 1; o < 32; o <<= 1) {
+            const long long pv = __shfl_up_sync(0xffffffffu, v, o);
+            const uint32_t pcv = __shfl_up_sync(0xffffffffu, cv, o);
+            if ((int) lane >= o) { v += pv; cv += pcv; }
+          }
+          v += carry; cv += carryc;
+          if (k < cells) { Bs[k] = (unsigned long long) v; Bc[k] = cv; }
+          carry = __shfl_sync(0xffffffffu, v, 31);
+          carryc = __shfl_sync(0xffffffffu, cv, 31);
+        }
+      }
+      __syncwarp();
+      for (int pass = 0; pass < nchild; ++pass) {
+        unsigned long long *S = Bs;
+        uint32_t *C = Bc;
+        if (pass == 1) {
+          S = Ds;
+          C = Dc;
+          for (uint32_t k = lane; k < cells; k += 32) {
+            if (EXACT) {
+              const double pv = __longlong_as_double((long long) Ps[k]);
+              const double bv = __longlong_as_double((long long) Bs[k]);
+              S[k] = (unsigned long long) __double_as_longlong(pv - bv);
+            } else {
+              S[k] = Ps[k] - Bs[k];
+            }
+            C[k] = Pc[k] - Bc[k];
+          }
+          __syncwarp();
+        }
+        const unsigned long long sraw = S[cells - 1];
+        const double s = cell_value(EXACT, sraw, inv);
+        const uint32_t cn = C[cells - 1];
+        double best = -1.0;
+        uint32_t best_t = 0xffffffffu, best_lc = 0;
+        for (uint32_t k = lane; k < cells; k += 32) {
+          const uint32_t lc = C[k], rc = cn - lc;
+          if (lc >= minls && rc >= minls) {
+            const double ls = cell_value(EXACT, S[k], inv);
+            const double rs = s - ls;
+            const double score = ls * ls / (double) lc + rs * rs / (double) rc;
+            if (score > best) { best = score; best_t = k; best_lc = lc; }
+          }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const uint32_t ot = __shfl_xor_sync(0xffffffffu, best_t, o);
+          const uint32_t ol = __shfl_xor_sync(0xffffffffu, best_lc, o);
+          if (ob > best || (ob == best && ot < best_t)) { best = ob; best_t = ot; best_lc = ol; }
+        }
+        if (lane == 0) {
+          const int child = t.whole ? 0 : ((pass == 0) == (t.build_left != 0) ? 0 : 1);
+          const size_t o = ((size_t) task * 2 + child) * F + f;
+          fbest_score[o] = best;
+          fbest_t[o] = best_t;
+          fbest_lc[o] = best_lc;
+          if (f == 0) totals[(size_t) task * 2 + child] = make_ulonglong2((unsigned long long) cn, sraw);
+        }
       }
     }
-    for (int o = 16; o > 0; o >>= 1) {   // arg-max, ties to the smaller t
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const uint32_t ot = __shfl_xor_sync(0xffffffffu, best_t, o);
-      if (ob > best || (ob == best && ot < best_t)) { best = ob; best_t = ot; }
-    }
-    if (lane == 0) { wb[warp] = best; wt[warp] = best_t; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; ++w)
-        if (wb[w] > best || (wb[w] == best && wt[w] < best_t)) { best = wb[w]; best_t = wt[w]; }
-      // pass 0 scanned the built child, pass 1 the derived one; child 0 = left
-      const int child = t.whole ? 0 : ((pass == 0) == (t.build_left != 0) ? 0 : 1);
-      fbest_score[((size_t) task * 2 + child) * F + f] = best;
-      fbest_t[((size_t) task * 2 + child) * F + f] = best_t;
-    }
-    __syncthreads();
   }
-}
 
-// Arg-max over features (first maximum wins: rt.cc:297-306 with GCC's static schedule) and the
-// node statistics of RTNode(sampleids, hist) (rtnode.h:97-107).  One block per task.
-template <bool EXACT>
-__global__ void __launch_bounds__(128)
-finalize2_kernel(const NodeTask *__restrict__ tasks, const unsigned long long *__restrict__ hsum,
-                 const uint32_t *__restrict__ hcnt, uint32_t ncells, const uint32_t *__restrict__ thr_off,
-                 uint32_t F, const int *__restrict__ qexp, const double *__restrict__ fbest_score,
-                 const uint32_t *__restrict__ fbest_t, const double *__restrict__ sq_partials, uint32_t n_sq,
-                 SplitResult *res) {
-  const uint32_t task = blockIdx.x;
-  const NodeTask t = tasks[task];
-  const double inv = EXACT ? 1.0 : ldexp(1.0, -*qexp);
-  __shared__ double wb[4];
-  __shared__ uint32_t wf[4];
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  const int nchild = t.whole ? 1 : 2;
+  // The last block of a task to finish reduces the per-feature winners: arg-max over features
+  // (first maximum wins: rt.cc:297-306 with GCC's static schedule) and the node statistics of
+  // RTNode(sampleids, hist) (rtnode.h:97-107).
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(task_done + task, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double sqB = 0.0;
+  if (EXACT) {
+    sqB = sq_exact[t.sq0];
+  } else {
+    U128 tot{0ull, 0ull};
+    for (uint32_t i = 0; i < t.hist_nblk; ++i) { const ulonglong2 v = sq128[t.hist_blk0 + i]; u128_add(tot, v.x, v.y); }
+    const double inv2 = ldexp(1.0, -2 * *qexp);
+    sqB = ((double) tot.hi * 18446744073709551616.0 + (double) tot.lo) * inv2;
+  }
   for (int child = 0; child < nchild; ++child) {
-    // first maximum over features: strict '>' in ascending f
+    const volatile double *fs = fbest_score + ((size_t) task * 2 + child) * F;
+    const volatile uint32_t *ft = fbest_t + ((size_t) task * 2 + child) * F;
+    const volatile uint32_t *fl = fbest_lc + ((size_t) task * 2 + child) * F;
     double best = -1.0;
-    uint32_t bf = 0xffffffffu;
-    for (uint32_t f = threadIdx.x; f < F; f += 128) {
-      const double sc = fbest_score[((size_t) task * 2 + child) * F + f];
-      if (sc > best) { best = sc; bf = f; }
+    uint32_t bf = 0xffffffffu, bt = 0xffffffffu, blc = 0;
+    for (uint32_t ff = threadIdx.x; ff < F; ff += 256) {
+      const double sc = fs[ff];
+      if (sc > best) { best = sc; bf = ff; bt = ft[ff]; blc = fl[ff]; }
     }
     for (int o = 16; o > 0; o >>= 1) {
       const double ob = __shfl_xor_sync(0xffffffffu, best, o);
       const uint32_t of = __shfl_xor_sync(0xffffffffu, bf, o);
-      if (ob > best || (ob == best && of < bf)) { best = ob; bf = of; }
+      const uint32_t ot = __shfl_xor_sync(0xffffffffu, bt, o);
+      const uint32_t ol = __shfl_xor_sync(0xffffffffu, blc, o);
+      if (ob > best || (ob == best && of < bf)) { best = ob; bf = of; bt = ot; blc = ol; }
     }
-    if (lane == 0) { wb[warp] = best; wf[warp] = bf; }
+    if (lane == 0) { wb[warp] = best; wt[warp] = bf; wt2[warp] = bt; wl2[warp] = blc; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < 4; ++w)
-        if (wb[w] > best || (wb[w] == best && wf[w] < bf)) { best = wb[w]; bf = wf[w]; }
-      double sqB = 0.0;
-      for (uint32_t i = 0; i < n_sq; ++i) sqB += sq_partials[t.sq0 + i];
+      for (int w = 1; w < 8; ++w)
+        if (wb[w] > best || (wb[w] == best && wt[w] < bf)) { best = wb[w]; bf = wt[w]; bt = wt2[w]; blc = wl2[w]; }
       const bool built = t.whole || ((child == 0) == (t.build_left != 0));
-      const int slot = built ? t.slotB : t.slotD;
-      const unsigned long long *S = hsum + (size_t) slot * ncells;
-      const uint32_t *C = hcnt + (size_t) slot * ncells;
+      const volatile ulonglong2 *tv = totals + (size_t) task * 2 + child;
       SplitResult r;
-      const uint32_t last0 = thr_off[1] - 1;
-      r.n = C[last0];
-      r.sum = cell_value(EXACT, S[last0], inv);
+      r.n = tv->x;
+      r.sum = cell_value(EXACT, tv->y, inv);
       r.squares = built ? sqB : t.parent_squares - sqB;          // rtnode_histogram.cc:86,207
       r.deviance = r.squares - r.sum * r.sum / (double) r.n;      // rtnode.h:106
       r.score = best;
       r.valid = best != -1.0;
       r.feature = bf;
-      r.threshold_idx = r.valid ? fbest_t[((size_t) task * 2 + child) * F + bf] : 0xffffffffu;
-      r.lcount = r.valid ? C[thr_off[bf] + r.threshold_idx] : 0;
+      r.threshold_idx = r.valid ? bt : 0xffffffffu;
+      r.lcount = r.valid ? blc : 0;
       r.pad = 0;
       res[(size_t) task * 2 + child] = r;
+      if (child == nchild - 1) task_done[task] = 0u;   // ready for the next round
     }
     __syncthreads();
   }
