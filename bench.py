@@ -137,18 +137,19 @@ def run_ours(args):
     w = WORKLOAD
     x, labels, qoff = make_shard(rank, world)
 
-    t0 = time.perf_counter()
-    tr = api.Trainer(x, labels, qoff, algo="LAMBDAMART", nleaves=w["leaves"], minleafsupport=w["minls"],
-                     nthresholds=w["nthresholds"], cutoff=w["cutoff"], shrinkage=w["shrinkage"],
-                     hist_mode=api.HIST_FAST, device=local_rank)
-    init_s = time.perf_counter() - t0
+    comm = None
     if world > 1:
         import torch
         idt = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        tr.comm_init(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        comm = (bytes(idt.cpu().numpy().tobytes()), rank, world)
+    t0 = time.perf_counter()
+    tr = api.Trainer(x, labels, qoff, algo="LAMBDAMART", nleaves=w["leaves"], minleafsupport=w["minls"],
+                     nthresholds=w["nthresholds"], cutoff=w["cutoff"], shrinkage=w["shrinkage"],
+                     hist_mode=api.HIST_FAST, device=local_rank, comm=comm)
+    init_s = time.perf_counter() - t0
 
     def barrier():
         if dist is not None:

@@ -144,6 +144,10 @@ int qr_get_ranking(qr_ctx *ctx, uint32_t *position_of_rank);    /* per query, as
 /* measured per-tree quantities for the roofline formula:
  * rho = sum over splits of n_left / N, sigma = sum over splits of n_node / N */
 int qr_last_tree_stats(qr_ctx *ctx, double *rho, double *sigma, uint32_t *nsplits);
+/* growth rounds of the last tree (batched node expansions, see quickrank_b200/csrc/qr_tree_host.cuh)
+ * and beta = documents whose histogram rows were actually accumulated / N (root included): with the
+ * smaller-child rule of the fixed-point mode this is below 1 + rho */
+int qr_last_tree_rounds(qr_ctx *ctx, uint32_t *rounds, double *beta);
 /* number of kernel launches issued by this context so far */
 uint64_t qr_launch_count(qr_ctx *ctx);
 /* device time (ms, CUDA events on the context's stream) spent per phase since the last reset:
@@ -161,9 +165,14 @@ int qr_timer_stop(qr_ctx *ctx, double *ms);
 #define QR_COMM_ID_BYTES 128
 /* rank 0 creates the id, the host broadcasts it by any means (torch.distributed, MPI, a file). */
 int qr_comm_unique_id(unsigned char id[QR_COMM_ID_BYTES]);
-/* Joins the context to a world of `world` contexts; afterwards histograms, leaf sums and the
- * metric are all-reduced over NCCL so that every rank grows the identical tree. */
-int qr_ctx_comm_init(qr_ctx *ctx, const unsigned char id[QR_COMM_ID_BYTES], int rank, int world);
+/* Creates the training context of rank `rank` of `world`: this process holds a contiguous range of
+ * whole queries (its documents only); thresholds are computed over the union of all ranks' feature
+ * values, and afterwards histograms, squares, leaf sums and the metric are all-reduced over NCCL so
+ * that every rank grows the identical tree.  `rowmajor` selects the feature layout (0: column-major
+ * as qr_ctx_create, 1: row-major as qr_ctx_create_rowmajor).  Collective: every rank must call it. */
+int qr_ctx_create_sharded(const float *feat, int rowmajor, size_t N, size_t F, const float *labels,
+                          const uint64_t *qoffsets, size_t Q, const qr_params *params,
+                          const unsigned char id[QR_COMM_ID_BYTES], int rank, int world, qr_ctx **out);
 
 /* ---- scoring ------------------------------------------------------------------------------- */
 

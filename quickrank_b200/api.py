@@ -85,6 +85,7 @@ def lib():
         L.qr_get_bins.argtypes = [vp, sz, u32p]
         L.qr_get_ranking.argtypes = [vp, u32p]
         L.qr_last_tree_stats.argtypes = [vp, dp, dp, u32p]
+        L.qr_last_tree_rounds.argtypes = [vp, u32p, dp]
         L.qr_launch_count.restype = C.c_uint64
         L.qr_launch_count.argtypes = [vp]
         L.qr_phase_times.argtypes = [vp, dp, u64p, C.c_int]
@@ -92,7 +93,8 @@ def lib():
         L.qr_timer_start.argtypes = [vp]
         L.qr_timer_stop.argtypes = [vp, dp]
         L.qr_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
-        L.qr_ctx_comm_init.argtypes = [vp, C.POINTER(C.c_ubyte), C.c_int, C.c_int]
+        L.qr_ctx_create_sharded.argtypes = [fp, C.c_int, sz, sz, fp, u64p, sz, C.POINTER(Params),
+                                            C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.POINTER(vp)]
         L.qr_scorer_create.argtypes = [C.POINTER(FlatTree), dp, sz, sz, C.c_int, C.POINTER(vp)]
         L.qr_scorer_destroy.argtypes = [vp]
         L.qr_score_dataset.argtypes = [vp, fp, sz, sz, dp]
@@ -150,7 +152,9 @@ class Trainer:
 
     def __init__(self, x, labels, qoff, algo="LAMBDAMART", nleaves=10, treedepth=3, minleafsupport=1,
                  nthresholds=0, cutoff=10, shrinkage=0.1, hist_mode=HIST_FAST, device=-1,
-                 layout="rowmajor"):
+                 layout="rowmajor", comm=None):
+        """comm = (id_bytes, rank, world) makes this the context of one rank of a sharded run
+        (x, labels, qoff are then the rank's own whole queries)."""
         L = lib()
         self.labels = np.ascontiguousarray(labels, np.float32)
         self.qoff = np.ascontiguousarray(qoff, np.uint64)
@@ -169,6 +173,13 @@ class Trainer:
         self.shrinkage = shrinkage
         self.max_nodes = 2 * ((1 << treedepth) if algo.startswith("OBV") else max(1, nleaves)) + 1
         self.h = C.c_void_p()
+        if comm is not None:
+            cid, rank, world = comm
+            buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(cid)
+            _check(L.qr_ctx_create_sharded(_p(x, C.c_float), int(layout == "rowmajor"), self.N, self.F,
+                                           _p(self.labels, C.c_float), _p(self.qoff, C.c_uint64), self.Q,
+                                           C.byref(p), buf, rank, world, C.byref(self.h)))
+            return
         fn = L.qr_ctx_create_rowmajor if layout == "rowmajor" else L.qr_ctx_create
         _check(fn(_p(x, C.c_float), self.N, self.F, _p(self.labels, C.c_float),
                   _p(self.qoff, C.c_uint64), self.Q, C.byref(p), C.byref(self.h)))
@@ -268,6 +279,11 @@ class Trainer:
         _check(lib().qr_last_tree_stats(self.h, C.byref(rho), C.byref(sigma), C.byref(ns)))
         return rho.value, sigma.value, ns.value
 
+    def last_tree_rounds(self):
+        r, b = C.c_uint32(), C.c_double()
+        _check(lib().qr_last_tree_rounds(self.h, C.byref(r), C.byref(b)))
+        return r.value, b.value
+
     def launch_count(self):
         return int(lib().qr_launch_count(self.h))
 
@@ -287,10 +303,6 @@ class Trainer:
         ln = (C.c_uint64 * 6)()
         _check(lib().qr_phase_times(self.h, ms, ln, int(reset)))
         return dict(zip(PHASES, list(ms))), dict(zip(PHASES, [int(v) for v in ln]))
-
-    def comm_init(self, comm_id: bytes, rank: int, world: int):
-        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(comm_id)
-        _check(lib().qr_ctx_comm_init(self.h, buf, rank, world))
 
 
 def comm_unique_id() -> bytes:

@@ -139,7 +139,7 @@ struct qr_ctx {
   bool has_tree = false;
   std::vector<qr::HostNode> nodes;  // last fitted tree
   std::vector<int> leaves;          // node ids in DFS order
-  double rho = 0, sigma = 0;
+  double rho = 0, sigma = 0, beta = 0;
   uint32_t nsplits = 0, nrounds = 0;
 
   uint64_t launches = 0;

@@ -96,10 +96,12 @@ static int build_binning(qr_ctx *c, const float *d_col) {
   const size_t tmp_bytes = std::max(tmp_sort, tmp_sel);
   QR_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
 
-  c->thr.assign(F, std::vector<float>());
+  // phase A: per feature, the distinct values of the local documents (ascending in the
+  // reference's radix order) and the first / last value of that order
+  struct Local { std::vector<float> uniq; int over = 0; float fmin = 0, fmax = 0; };
+  std::vector<Local> loc(F);
   const size_t nth = (size_t) c->p.nthresholds;
   const unsigned blocks = (unsigned) ((N + 255) / 256);
-  uint32_t max_bin = 0;
   for (size_t f = 0; f < F; ++f) {
     const float *x = d_col + f * N;
     flip_keys_kernel<<<blocks, 256, 0, st>>>(x, d_keys, N, d_bad);
@@ -110,32 +112,95 @@ static int build_binning(qr_ctx *c, const float *d_col) {
     QR_CUDA(cub::DeviceSelect::Flagged(d_tmp, tb, d_vals, d_flags, d_uniq, d_num, (int) N, st));
     int nu = 0;
     QR_CUDA(cudaMemcpyAsync(&nu, d_num, sizeof(int), cudaMemcpyDeviceToHost, st));
+    QR_CUDA(cudaMemcpyAsync(&loc[f].fmin, d_vals, sizeof(float), cudaMemcpyDeviceToHost, st));
+    QR_CUDA(cudaMemcpyAsync(&loc[f].fmax, d_vals + (N - 1), sizeof(float), cudaMemcpyDeviceToHost, st));
     QR_CUDA(cudaStreamSynchronize(st));
-    std::vector<float> &t = c->thr[f];
-    if (nth == 0 || (size_t) nu <= nth) {        // mart.cc:155-158: distinct values + FLT_MAX
-      t.resize((size_t) nu + 1);
-      QR_CUDA(cudaMemcpy(t.data(), d_uniq, (size_t) nu * sizeof(float), cudaMemcpyDeviceToHost));
-      t[nu] = FLT_MAX;
-      max_bin = std::max<uint32_t>(max_bin, (uint32_t) (nu - 1));
-    } else {                                     // mart.cc:159-169: equal width, float accumulation
-      float fmin = 0, fmax = 0;
-      QR_CUDA(cudaMemcpy(&fmin, d_vals, sizeof(float), cudaMemcpyDeviceToHost));
-      QR_CUDA(cudaMemcpy(&fmax, d_vals + (N - 1), sizeof(float), cudaMemcpyDeviceToHost));
-      t.resize(nth + 1);
-      float cur = fmin;
-      const float step = (float) std::fabs((double) (fmax - cur)) / (float) nth;
-      for (size_t j = 0; j != nth; cur += step) t[j++] = cur;
-      t[nth] = FLT_MAX;
-      max_bin = std::max<uint32_t>(max_bin, (uint32_t) nth);
+    if (nth != 0 && (size_t) nu > nth) {
+      loc[f].over = 1;   // more distinct values than thresholds already locally: equal-width mode
+    } else {
+      loc[f].uniq.resize((size_t) nu);
+      QR_CUDA(cudaMemcpy(loc[f].uniq.data(), d_uniq, (size_t) nu * sizeof(float), cudaMemcpyDeviceToHost));
     }
   }
   int bad = 0;
   QR_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
   cudaFree(d_keys); cudaFree(d_keys_out); cudaFree(d_vals); cudaFree(d_uniq);
   cudaFree(d_flags); cudaFree(d_num); cudaFree(d_bad); cudaFree(d_tmp);
+
+  // phase B (several ranks): every rank must end up with the thresholds of the WHOLE dataset
+  if (c->comm) {
+    auto key = [](float v) { uint32_t b; memcpy(&b, &v, 4); return b ^ ((uint32_t) (-(int32_t) (b >> 31)) | 0x80000000u); };
+    struct Head { int bad, over, count; float fmin, fmax; };
+    std::vector<Head> head(F);
+    size_t total = 0;
+    for (size_t f = 0; f < F; ++f) {
+      head[f] = Head{bad, loc[f].over, (int) loc[f].uniq.size(), loc[f].fmin, loc[f].fmax};
+      total += loc[f].uniq.size();
+    }
+    std::vector<unsigned char> all_head;
+    QR_TRY(comm_allgather_host(c->comm, head.data(), F * sizeof(Head), &all_head, st));
+    const int world = comm_world(c->comm);
+    const size_t head_stride = all_head.size() / world;
+    size_t max_total = 0;
+    for (int r = 0; r < world; ++r) {
+      const Head *h = reinterpret_cast<const Head *>(all_head.data() + r * head_stride);
+      size_t t = 0;
+      for (size_t f = 0; f < F; ++f) t += (size_t) h[f].count;
+      max_total = std::max(max_total, t);
+    }
+    std::vector<float> flatv(std::max<size_t>(max_total, 1), 0.f);
+    size_t o = 0;
+    for (size_t f = 0; f < F; ++f) { std::copy(loc[f].uniq.begin(), loc[f].uniq.end(), flatv.begin() + o); o += loc[f].uniq.size(); }
+    std::vector<unsigned char> all_vals;
+    QR_TRY(comm_allgather_host(c->comm, flatv.data(), flatv.size() * sizeof(float), &all_vals, st));
+    const size_t val_stride = all_vals.size() / world;
+    std::vector<size_t> cursor(world, 0);
+    for (size_t f = 0; f < F; ++f) {
+      std::vector<float> merged;
+      Local g;
+      bool first = true;
+      for (int r = 0; r < world; ++r) {
+        const Head &h = reinterpret_cast<const Head *>(all_head.data() + r * head_stride)[f];
+        const float *v = reinterpret_cast<const float *>(all_vals.data() + r * val_stride) + cursor[r];
+        bad |= h.bad;
+        g.over |= h.over;
+        if (first || key(h.fmin) < key(g.fmin)) g.fmin = h.fmin;
+        if (first || key(h.fmax) > key(g.fmax)) g.fmax = h.fmax;
+        first = false;
+        merged.insert(merged.end(), v, v + h.count);
+        cursor[r] += (size_t) h.count;
+      }
+      if (!g.over) {
+        std::sort(merged.begin(), merged.end(), [&](float a, float b) { return key(a) < key(b); });
+        for (float v : merged)
+          if (g.uniq.empty() || g.uniq.back() < v) g.uniq.push_back(v);   // mart.cc:148-151
+        if (nth != 0 && g.uniq.size() > nth) { g.over = 1; g.uniq.clear(); }
+      }
+      loc[f] = std::move(g);
+    }
+  }
   if (bad) {
     set_error("feature matrix contains NaN or infinite values (the reference's bin map is undefined for them)");
     return QR_EINVAL;
+  }
+
+  // phase C: threshold lists
+  c->thr.assign(F, std::vector<float>());
+  uint32_t max_bin = 0;
+  for (size_t f = 0; f < F; ++f) {
+    std::vector<float> &t = c->thr[f];
+    if (!loc[f].over) {                          // mart.cc:155-158: distinct values + FLT_MAX
+      t = loc[f].uniq;
+      t.push_back(FLT_MAX);
+      max_bin = std::max<uint32_t>(max_bin, (uint32_t) (t.size() - 2));
+    } else {                                     // mart.cc:159-169: equal width, float accumulation
+      t.resize(nth + 1);
+      float cur = loc[f].fmin;
+      const float step = (float) std::fabs((double) (loc[f].fmax - cur)) / (float) nth;
+      for (size_t j = 0; j != nth; cur += step) t[j++] = cur;
+      t[nth] = FLT_MAX;
+      max_bin = std::max<uint32_t>(max_bin, (uint32_t) nth);
+    }
   }
   if (max_bin > 65535u) {
     set_error("a feature has %u occupied bins; this build stores bins in at most 16 bits "
@@ -180,7 +245,8 @@ static int build_binning(qr_ctx *c, const float *d_col) {
 static int init_root_counts(qr_ctx *c);
 
 static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t F, const float *labels,
-                             const uint64_t *qoffsets, size_t Q, const qr_params *params, qr_ctx **out) {
+                             const uint64_t *qoffsets, size_t Q, const qr_params *params,
+                             const unsigned char *comm_id, int rank, int world, qr_ctx **out) {
   if (!feat || !labels || !qoffsets || !params || !out || N == 0 || F == 0 || Q == 0) {
     set_error("qr_ctx_create: null or empty argument");
     return QR_EINVAL;
@@ -215,6 +281,21 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_CUDA(cudaEventCreate(&c->ev1));
   QR_CUDA(cudaEventCreate(&c->ev_t0));
   QR_CUDA(cudaEventCreate(&c->ev_t1));
+
+  if (comm_id != nullptr && world > 1) {
+    if (c->exact) { set_error("reference-order accumulation (QR_HIST_REFERENCE) is single-GPU only"); return QR_EINVAL; }
+    QR_TRY(comm_create(comm_id, rank, world, &c->comm));
+    unsigned long long nq[2] = {(unsigned long long) N, (unsigned long long) Q};
+    unsigned long long *d_nq = nullptr;
+    QR_TRY(dev_alloc(&d_nq, 2));
+    QR_CUDA(cudaMemcpyAsync(d_nq, nq, sizeof(nq), cudaMemcpyHostToDevice, c->stream));
+    QR_TRY(comm_allreduce_sum_u64(c->comm, d_nq, 2, c->stream));
+    QR_CUDA(cudaMemcpyAsync(nq, d_nq, sizeof(nq), cudaMemcpyDeviceToHost, c->stream));
+    QR_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_nq);
+    c->N_global = (size_t) nq[0];
+    c->Q_global = (size_t) nq[1];
+  }
 
   // features -> device column-major (VerticalDataset layout), then bins; floats are released
   float *d_col = nullptr;
@@ -444,7 +525,7 @@ int qr_device_count(void) {
 int qr_ctx_create(const float *feat, size_t N, size_t F, const float *labels, const uint64_t *qoff,
                   size_t Q, const qr_params *params, qr_ctx **out) {
   if (out) *out = nullptr;
-  int rc = ctx_create_common(feat, false, N, F, labels, qoff, Q, params, out);
+  int rc = ctx_create_common(feat, false, N, F, labels, qoff, Q, params, nullptr, 0, 1, out);
   if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
   return rc;
 }
@@ -452,7 +533,17 @@ int qr_ctx_create(const float *feat, size_t N, size_t F, const float *labels, co
 int qr_ctx_create_rowmajor(const float *feat, size_t N, size_t F, const float *labels,
                            const uint64_t *qoff, size_t Q, const qr_params *params, qr_ctx **out) {
   if (out) *out = nullptr;
-  int rc = ctx_create_common(feat, true, N, F, labels, qoff, Q, params, out);
+  int rc = ctx_create_common(feat, true, N, F, labels, qoff, Q, params, nullptr, 0, 1, out);
+  if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
+  return rc;
+}
+
+int qr_ctx_create_sharded(const float *feat, int rowmajor, size_t N, size_t F, const float *labels,
+                          const uint64_t *qoff, size_t Q, const qr_params *params,
+                          const unsigned char id[QR_COMM_ID_BYTES], int rank, int world, qr_ctx **out) {
+  if (out) *out = nullptr;
+  if (!id) { set_error("qr_ctx_create_sharded: null communicator id"); return QR_EINVAL; }
+  int rc = ctx_create_common(feat, rowmajor != 0, N, F, labels, qoff, Q, params, id, rank, world, out);
   if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
   return rc;
 }
@@ -614,6 +705,12 @@ int qr_last_tree_stats(qr_ctx *c, double *rho, double *sigma, uint32_t *nsplits)
   if (rho) *rho = c->rho;
   if (sigma) *sigma = c->sigma;
   if (nsplits) *nsplits = c->nsplits;
+  return QR_OK;
+}
+int qr_last_tree_rounds(qr_ctx *c, uint32_t *rounds, double *beta) {
+  QR_CHECK_CTX(c);
+  if (rounds) *rounds = c->nrounds;
+  if (beta) *beta = c->beta;
   return QR_OK;
 }
 uint64_t qr_launch_count(qr_ctx *c) { return c ? c->launches : 0; }

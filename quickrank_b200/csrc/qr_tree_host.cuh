@@ -91,7 +91,7 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
     } else {
       const size_t smem = (size_t) c->fpp * c->max_thr * 12;
       const bool use_smem = smem <= 200 * 1024;
-      if (total_slices > c->max_slices) { set_error("internal: %u histogram slices > capacity", total_slices); return QR_ECUDA; }
+      if (total_slices > c->max_slices - c->max_tasks) { set_error("internal: %u histogram slices > capacity", total_slices); return QR_ECUDA; }
 #define QR_HIST_LAUNCH(SMEMF, COUNTF)                                                                        \
   QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), 256,            \
             SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
@@ -192,6 +192,7 @@ static int init_root_counts(qr_ctx *c) {
   QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
   QR_CUDA(cudaMemcpyAsync(c->d_root_cnt, c->d_hist_cnt + (size_t) slot * c->ncells, c->ncells * sizeof(uint32_t),
                           cudaMemcpyDeviceToDevice, c->stream));
+  if (c->comm) QR_TRY(comm_allreduce_sum_u32(c->comm, c->d_root_cnt, c->ncells, c->stream));
   // most frequent bin of every feature (hist_limb_kernel skips it and recovers it by subtraction)
   std::vector<uint32_t> cnt(c->ncells), hot(c->F);
   QR_CUDA(cudaMemcpyAsync(cnt.data(), c->d_root_cnt, c->ncells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -255,6 +256,7 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     const uint64_t built_n = c->comm ? nd.n : (t.build_left ? lc : rc);
     t.hist_nblk = std::max<uint32_t>(1, (uint32_t) ((built_n + dpb - 1) / dpb));
     hist_blk += t.hist_nblk;
+    if (build_child_hists) c->beta += (double) (t.build_left ? lc : rc) / (double) c->N_global;
     t.lcount = (uint32_t) lc;
     t.lc_known = c->comm ? 0u : 1u;
     t.sq0 = j;
@@ -494,6 +496,7 @@ static int fit_tree(qr_ctx *c, qr_flat_tree *out) {
   c->nodes.clear();
   c->leaves.clear();
   c->rho = c->sigma = 0;
+  c->beta = 1.0;
   c->nsplits = 0;
   c->nrounds = 0;
   c->has_tree = false;

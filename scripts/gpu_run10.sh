@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python scripts/probe.py --trees 10 > gpurun_out/probe_fast.log 2>&1; tail -10 gpurun_out/probe_fast.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --settle 0 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+python scripts/summarize_launches.py gpurun_out/launches.csv
+timeout 600 python bench.py --steps 20 --no-cpu-baseline 2>&1 | cut -c1-1500

@@ -18,6 +18,7 @@ ap.add_argument("--trees", type=int, default=8)
 ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--algo", default="LAMBDAMART")
 ap.add_argument("--depth", type=int, default=6)
+ap.add_argument("--settle", type=int, default=0)
 a = ap.parse_args()
 
 t0 = time.time()
@@ -27,6 +28,10 @@ t0 = time.time()
 tr = api.Trainer(x, l, off, algo=a.algo, nleaves=a.leaves, treedepth=a.depth, nthresholds=0, cutoff=10,
                  hist_mode=a.mode)
 print("init %.2fs" % (time.time() - t0), flush=True)
+for i in range(a.settle):
+    tr.boost_iteration(want_tree=False, want_metric=False)
+    if i % 10 == 9:
+        print("settle iter %d: stats %s rounds/beta %s" % (i, tr.last_tree_stats(), tr.last_tree_rounds()), flush=True)
 for i in range(3):
     t0 = time.time()
     tree, m = tr.boost_iteration()
@@ -41,7 +46,7 @@ ms, ln = tr.phase_times()
 print("profiled (sync per phase): %.2f ms/tree" % (dt * 1e3))
 for k in ms:
     print("  %-10s %8.3f ms/tree  %6.1f launches/tree" % (k, ms[k] / a.trees, ln[k] / a.trees))
-print("stats rho/sigma/splits", tr.last_tree_stats())
+print("stats rho/sigma/splits", tr.last_tree_stats(), "rounds/beta", tr.last_tree_rounds())
 tr.set_profiling(False)
 t0 = time.time()
 for i in range(a.trees):

@@ -1,0 +1,76 @@
+"""Two-rank training over NCCL (one process per GPU, documents sharded by query) must grow the
+same trees as one GPU: histogram sums are fixed-point integers, so the all-reduced totals do not
+depend on the number of ranks."""
+import multiprocessing as mp
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import qr_testlib as common
+
+pytestmark = pytest.mark.gpu
+
+T = 6
+
+
+def _worker(rank, world, q, out_q, algo, kw):
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from quickrank_b200 import api
+    from quickrank_b200.sharding import query_shards
+    x, l, off = common.dataset(n=20000, f=24, q=200, seed=21)
+    if rank == 0:
+        cid = api.comm_unique_id()
+        for _ in range(world - 1):
+            q.put(cid)
+    else:
+        cid = q.get()
+    q0, q1 = query_shards(off, world)[rank]
+    d0, d1 = int(off[q0]), int(off[q1])
+    tr = api.Trainer(x[d0:d1], l[d0:d1], (off[q0:q1 + 1] - off[q0]).astype(np.uint64), algo=algo, device=rank,
+                     comm=(cid, rank, world), **kw)
+    trees, metrics = [], []
+    for _ in range(T):
+        t, m = tr.boost_iteration()
+        trees.append(t)
+        metrics.append(m)
+    scores = tr.get_scores()
+    tr.close()
+    out_q.put((rank, trees, metrics, d0, d1, scores))
+
+
+@pytest.mark.parametrize("algo,kw", [("LAMBDAMART", dict(nleaves=16)), ("MART", dict(nleaves=8)),
+                                     ("OBVLAMBDAMART", dict(treedepth=3))])
+def test_two_ranks_grow_the_single_gpu_trees(algo, kw):
+    from quickrank_b200 import api
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    x, l, off = common.dataset(n=20000, f=24, q=200, seed=21)
+    with api.Trainer(x, l, off, algo=algo, **kw) as tr:
+        want = [tr.boost_iteration() for _ in range(T)]
+        want_scores = tr.get_scores()
+    ctx = mp.get_context("spawn")
+    q, out_q = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, q, out_q, algo, kw)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted([out_q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got_scores = np.zeros(len(l))
+    for rank, trees, metrics, d0, d1, scores in results:
+        got_scores[d0:d1] = scores
+        for m in range(T):
+            wt, wm = want[m]
+            assert common.same_structure(trees[m], wt), "rank %d tree %d: %s" % (rank, m, common.describe_tree_diff(trees[m], wt))
+            assert np.array_equal(trees[m]["count"], wt["count"])
+            lv = common.leaves_mask(wt)
+            assert np.max(np.abs(trees[m]["value"][lv] - wt["value"][lv])) <= 1e-12 * np.max(np.abs(wt["value"][lv]))
+            assert abs(metrics[m] - wm) <= 1e-12
+    assert np.max(np.abs(got_scores - want_scores)) <= 1e-12 * np.max(np.abs(want_scores))
+    # both ranks hold the identical model
+    for m in range(T):
+        assert common.same_structure(results[0][1][m], results[1][1][m])
+        assert np.array_equal(results[0][1][m]["value"], results[1][1][m]["value"])
