@@ -3,7 +3,7 @@
 // Every kernel names the reference loop it replaces (paths relative to the reference root,
 // hpclab/quickrank @ c569a59).  Compiled with -fmad=false: every fused multiply-add below is an
 // explicit fma() placed where the reference's Release build (g++ 13.3, FMA target) fuses one, so
-// results can be compared bit for bit with the oracle (see oracle/qr_oracle.c header).
+// results can be compared bit for bit with the reference build ("Floating-point contract").
 #pragma once
 
 #include <cfloat>
