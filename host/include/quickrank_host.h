@@ -1,0 +1,371 @@
+// quickrank_b200 host layer — the C++ side that sits above the C ABI (include/quickrank_b200.h).
+//
+// It mirrors the slice of the reference's API that surrounds the hot path (hpclab/quickrank @
+// c569a59; paths below are relative to the reference root) with the same names, argument meaning
+// and error behaviour (message on std::cerr, then exit(EXIT_FAILURE)):
+//   quickrank::data::Dataset / VerticalDataset        include/data/dataset.h, vertical_dataset.h
+//   quickrank::metric::ir::Metric / Dcg / Ndcg         include/metric/ir/{metric,dcg,ndcg}.h
+//   quickrank::learning::LTR_Algorithm                 include/learning/ltr_algorithm.h
+//   quickrank::learning::forests::Mart / LambdaMart / ObliviousMart / ObliviousLambdaMart
+//                                                      include/learning/forests/*.h
+//   RTNode / RegressionTree / Ensemble                 include/learning/tree/*.h
+//   quickrank::io::Svml                                include/io/svml.h
+// The bodies of the protected Mart hooks (init, clear, compute_pseudoresponses,
+// fit_regressor_on_gradient, update_modelscores) and of score_dataset call the CUDA library; the
+// boosting loop, the ensemble, early stopping, checkpoints and the XML model format stay on the
+// host exactly as in the reference.  Written from scratch; nothing here is reference code.
+#ifndef QUICKRANK_B200_HOST_H
+#define QUICKRANK_B200_HOST_H
+
+#include <cstddef>
+#include <cstdint>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "quickrank_b200.h"
+
+namespace quickrank {
+
+typedef float Label;        // include/types.h:28-32
+typedef double Score;
+typedef float Feature;
+typedef size_t QueryID;
+typedef double MetricScore;
+
+namespace data {
+
+class QueryResults {
+ public:
+  QueryResults(size_t n_results, Label *labels, Feature *features)
+      : num_results_(n_results), labels_(labels), features_(features) {}
+  size_t num_results() const { return num_results_; }
+  Label *labels() const { return labels_; }
+  Feature *features() const { return features_; }
+  // std::sort of positions by score, descending (queryresults.cc:47-53)
+  void indexing_of_sorted_labels(const Score *scores, size_t *dest) const;
+  void sorted_labels(const Score *scores, Label *dest, size_t cutoff) const;
+
+ private:
+  size_t num_results_;
+  Label *labels_;
+  Feature *features_;
+};
+
+// Row-major (documents x features) dataset; documents of a query are contiguous.
+class Dataset {
+ public:
+  Dataset(size_t n_instances, size_t n_features);
+  virtual ~Dataset();
+  Dataset(const Dataset &) = delete;
+  Dataset &operator=(const Dataset &) = delete;
+
+  Feature *at(size_t document_id, size_t feature_id) { return data_ + document_id * num_features_ + feature_id; }
+  const Feature *data() const { return data_; }
+  const Label *labels() const { return labels_; }
+  Label getLabel(size_t document_id) const { return labels_[document_id]; }
+  size_t offset(size_t i) const { return offsets_[i]; }
+  const std::vector<uint64_t> &offsets() const { return offsets_; }
+  std::unique_ptr<QueryResults> getQueryResults(size_t i) const;
+  void addInstance(QueryID q_id, Label i_label, const std::vector<Feature> &i_features);
+  size_t num_features() const { return num_features_; }
+  size_t num_queries() const { return num_queries_; }
+  size_t num_instances() const { return num_instances_; }
+
+ private:
+  size_t num_features_, num_queries_ = 0, num_instances_ = 0, max_instances_;
+  Feature *data_ = nullptr;
+  Label *labels_ = nullptr;
+  std::vector<uint64_t> offsets_;
+  QueryID last_instance_id_ = 0;
+};
+
+// Column-major view used during training.  The reference materialises the transpose on the host
+// (vertical_dataset.cc:29-70); here the device does it, so this class only carries the shape, the
+// labels and the query offsets, and produces a host transpose lazily if someone asks for at().
+class VerticalDataset {
+ public:
+  explicit VerticalDataset(std::shared_ptr<Dataset> h_dataset);
+  size_t num_features() const { return src_->num_features(); }
+  size_t num_queries() const { return src_->num_queries(); }
+  size_t num_instances() const { return src_->num_instances(); }
+  size_t offset(size_t i) const { return src_->offset(i); }
+  Label getLabel(size_t document_id) const { return src_->getLabel(document_id); }
+  std::unique_ptr<QueryResults> getQueryResults(size_t i) const { return src_->getQueryResults(i); }
+  Feature *at(size_t document_id, size_t feature_id);   // data_[feature_id * N + document_id]
+  std::shared_ptr<Dataset> horizontal() const { return src_; }
+
+ private:
+  std::shared_ptr<Dataset> src_;
+  std::vector<Feature> col_;
+};
+
+}  // namespace data
+
+namespace metric {
+namespace ir {
+
+class Metric {
+ public:
+  static const size_t NO_CUTOFF = SIZE_MAX;
+  explicit Metric(size_t k = NO_CUTOFF) { set_cutoff(k); }
+  virtual ~Metric() {}
+  virtual std::string name() const = 0;
+  size_t cutoff() const { return cutoff_; }
+  void set_cutoff(size_t k) { cutoff_ = k == 0 ? NO_CUTOFF : k; }
+  virtual MetricScore evaluate_result_list(const data::QueryResults *rl, const Score *scores) const = 0;
+  // mean over queries, sequential (metric.h:77-106)
+  virtual MetricScore evaluate_dataset(const std::shared_ptr<data::Dataset> dataset, const Score *scores) const;
+  friend std::ostream &operator<<(std::ostream &os, const Metric &m) { return m.put(os); }
+
+ private:
+  size_t cutoff_;
+  virtual std::ostream &put(std::ostream &os) const = 0;
+};
+
+class Dcg : public Metric {
+ public:
+  explicit Dcg(size_t k = NO_CUTOFF) : Metric(k) {}
+  std::string name() const override { return "DCG"; }
+  MetricScore evaluate_result_list(const data::QueryResults *rl, const Score *scores) const override;
+  MetricScore compute_dcg(const Label *labels, size_t len) const;
+
+ private:
+  std::ostream &put(std::ostream &os) const override;
+};
+
+class Ndcg : public Dcg {
+ public:
+  explicit Ndcg(size_t k = NO_CUTOFF) : Dcg(k) {}
+  std::string name() const override { return "NDCG"; }
+  MetricScore evaluate_result_list(const data::QueryResults *rl, const Score *scores) const override;
+  MetricScore compute_idcg(const data::QueryResults *rl) const;
+
+ private:
+  std::ostream &put(std::ostream &os) const override;
+};
+
+}  // namespace ir
+}  // namespace metric
+
+namespace io {
+
+class Svml {
+ public:
+  // SVMLight / LETOR text: "<label> qid:<id> <fid>:<val> ... [# comment]" (svml.cc:38-161)
+  std::unique_ptr<data::Dataset> read_horizontal(const std::string &filename);
+  void write(std::shared_ptr<data::Dataset> dataset, const std::string &filename);
+};
+
+}  // namespace io
+}  // namespace quickrank
+
+// ---- tree structures (global namespace, as in the reference) -------------------------------------
+
+static const size_t uint_max = (size_t) -1;
+
+class RTNode {
+ public:
+  float threshold = 0.0f;
+  double deviance = 0.0;
+  double avglabel = 0.0;
+  size_t nsampleids = 0;
+  RTNode *left = nullptr;
+  RTNode *right = nullptr;
+
+  explicit RTNode(double prediction) { avglabel = prediction; }
+  RTNode(float new_threshold, size_t new_featureidx, size_t new_featureid, RTNode *new_left, RTNode *new_right)
+      : threshold(new_threshold), left(new_left), right(new_right), featureidx(new_featureidx),
+        featureid(new_featureid) {}
+  ~RTNode() { delete left; delete right; }
+  void set_feature(size_t fidx, size_t fid) { featureidx = fidx; featureid = fid; }
+  size_t get_feature_id() const { return featureid; }
+  size_t get_feature_idx() const { return featureidx; }
+  bool is_leaf() const { return featureidx == uint_max; }
+  // rtnode.h:134-152
+  quickrank::Score score_instance(const quickrank::Feature *d, const size_t next_fx_offset) const {
+    return featureidx == uint_max ? avglabel
+                                  : (d[featureidx * next_fx_offset] <= threshold ? left->score_instance(d, next_fx_offset)
+                                                                                 : right->score_instance(d, next_fx_offset));
+  }
+  size_t count_nodes() const { return is_leaf() ? 1 : 1 + left->count_nodes() + right->count_nodes(); }
+
+ private:
+  size_t featureidx = uint_max;
+  size_t featureid = uint_max;
+};
+
+// The product of fit_regressor_on_gradient: owns nothing but the root pointer until the ensemble
+// takes it (mart.cc:342), like the reference's RegressionTree.
+class RegressionTree {
+ public:
+  RegressionTree() {}
+  explicit RegressionTree(RTNode *r) : root(r) {}
+  RTNode *get_proot() const { return root; }
+  // flat pre-order form <-> pointer graph
+  static RTNode *from_flat(const qr_flat_tree &t);
+  static void to_flat(const RTNode *root, std::vector<int32_t> &feature, std::vector<float> &threshold,
+                      std::vector<int32_t> &left, std::vector<int32_t> &right, std::vector<double> &value);
+
+ private:
+  RTNode *root = nullptr;
+};
+
+class Ensemble {
+ public:
+  Ensemble() {}
+  ~Ensemble();
+  Ensemble(const Ensemble &) = delete;
+  void set_capacity(size_t n) { trees_.reserve(n); }
+  void push(RTNode *root, double weight, float maxlabel);
+  void pop();
+  size_t get_size() const { return trees_.size(); }
+  bool is_notempty() const { return !trees_.empty(); }
+  RTNode *getTree(int index) const { return trees_[index].root; }
+  double getWeight(int index) const { return trees_[index].weight; }
+  // ensemble.cc:111-118
+  quickrank::Score score_instance(const quickrank::Feature *d, size_t offset = 1) const;
+  std::vector<double> get_weights() const;
+  bool update_ensemble_weights(std::vector<double> &weights);
+  void write_xml(std::ostream &os, int indent) const;   // <ensemble>...</ensemble> (ensemble.cc:133-147)
+
+ private:
+  struct weighted_tree { RTNode *root; double weight; float maxlabel; };
+  std::vector<weighted_tree> trees_;
+};
+
+namespace quickrank {
+namespace learning {
+
+class LTR_Algorithm {
+ public:
+  LTR_Algorithm() {}
+  virtual ~LTR_Algorithm() {}
+  LTR_Algorithm(const LTR_Algorithm &) = delete;
+  virtual std::string name() const = 0;
+  virtual void learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_ptr<data::Dataset> validation_dataset,
+                     std::shared_ptr<metric::ir::Metric> metric, size_t partial_save,
+                     const std::string model_filename) = 0;
+  // fills scores[N] for a row-major dataset (ltr_algorithm.cc:44-52)
+  virtual void score_dataset(std::shared_ptr<data::Dataset> dataset, Score *scores) const;
+  virtual Score score_document(const Feature *d) const = 0;
+  // <name>.T<iter>.xml for partial saves (ltr_algorithm.cc:54-65)
+  virtual void save(std::string model_filename, int suffix = -1) const;
+  static std::shared_ptr<LTR_Algorithm> load_model_from_file(std::string model_filename);
+  virtual void write_xml_model(std::ostream &os) const = 0;
+  friend std::ostream &operator<<(std::ostream &os, const LTR_Algorithm &a) { return a.put(os); }
+
+ private:
+  virtual std::ostream &put(std::ostream &os) const = 0;
+};
+
+namespace forests {
+
+struct XmlModel;  // parsed <ranker> document (quickrank_host.cc)
+
+class Mart : public LTR_Algorithm {
+ public:
+  // same parameter list as the reference (mart.h:52-66)
+  Mart(size_t ntrees, double shrinkage, size_t nthresholds, size_t ntreeleaves, size_t minleafsupport,
+       float subsample, float max_features, size_t valid_iterations, float collapse_leaves_factor)
+      : ntrees_(ntrees), shrinkage_(shrinkage), nthresholds_(nthresholds), nleaves_(ntreeleaves),
+        minleafsupport_(minleafsupport), subsample_(subsample), max_features_(max_features),
+        valid_iterations_(valid_iterations), collapse_leaves_factor_(collapse_leaves_factor) {}
+  explicit Mart(const XmlModel &model);
+  virtual ~Mart();
+
+  void learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_ptr<data::Dataset> validation_dataset,
+             std::shared_ptr<metric::ir::Metric> training_metric, size_t partial_save,
+             const std::string output_basename) override;
+  Score score_document(const Feature *d) const override { return ensemble_model_.score_instance(d, 1); }
+  void score_dataset(std::shared_ptr<data::Dataset> dataset, Score *scores) const override;
+  std::string name() const override { return NAME_; }
+  void write_xml_model(std::ostream &os) const override;
+  std::vector<double> get_weights() const { return ensemble_model_.get_weights(); }
+  const Ensemble &ensemble() const { return ensemble_model_; }
+  // histogram accumulation mode of the CUDA library (QR_HIST_FAST / QR_HIST_REFERENCE)
+  void set_hist_mode(uint32_t m) { hist_mode_ = m; }
+  void set_device(int d) { device_ = d; }
+  static const std::string NAME_;
+
+ protected:
+  // the hooks of mart.h:118-147
+  virtual void init(std::shared_ptr<data::VerticalDataset> training_dataset);
+  virtual void clear(size_t num_features);
+  virtual void compute_pseudoresponses(std::shared_ptr<data::VerticalDataset> training_dataset,
+                                       metric::ir::Metric *metric, bool *sample_presence);
+  virtual std::unique_ptr<RegressionTree> fit_regressor_on_gradient(
+      std::shared_ptr<data::VerticalDataset> training_dataset, size_t *sampleids);
+  virtual void update_modelscores(std::shared_ptr<data::Dataset> dataset, Score *scores, RegressionTree *tree);
+  virtual void update_modelscores(std::shared_ptr<data::VerticalDataset> dataset, Score *scores, RegressionTree *tree);
+  virtual MetricScore evaluate_training(metric::ir::Metric *metric);
+  virtual uint32_t algo_id() const { return QR_ALGO_MART; }
+  virtual size_t tree_depth() const { return 0; }
+  virtual void write_xml_info(std::ostream &os) const;
+  std::ostream &put(std::ostream &os) const override;
+  void die(const char *what) const;   // cerr + exit(EXIT_FAILURE), the reference's error convention
+
+  Ensemble ensemble_model_;
+  size_t ntrees_;
+  double shrinkage_;
+  size_t nthresholds_;
+  size_t nleaves_;
+  size_t minleafsupport_;
+  float subsample_;
+  float max_features_;
+  size_t valid_iterations_;
+  float collapse_leaves_factor_;
+  MetricScore best_metric_on_training_ = 0, best_metric_on_validation_ = 0;
+  size_t best_model_ = 0;
+  uint32_t hist_mode_ = QR_HIST_FAST;
+  int device_ = -1;
+  size_t metric_cutoff_ = 10;
+  qr_ctx *ctx_ = nullptr;         // training set on the GPU (Mart::init .. Mart::clear)
+  qr_ctx *valid_ctx_ = nullptr;   // validation set binned with the training thresholds
+};
+
+class LambdaMart : public Mart {
+ public:
+  using Mart::Mart;
+  std::string name() const override { return NAME_; }
+  static const std::string NAME_;
+
+ protected:
+  uint32_t algo_id() const override { return QR_ALGO_LAMBDAMART; }
+};
+
+class ObliviousMart : public Mart {
+ public:
+  ObliviousMart(size_t ntrees, double shrinkage, size_t nthresholds, size_t treedepth, size_t minleafsupport,
+                float subsample, float max_features, size_t esr, float collapse_leaves_factor)
+      : Mart(ntrees, shrinkage, nthresholds, (size_t) 1 << treedepth, minleafsupport, subsample, max_features, esr,
+             collapse_leaves_factor), treedepth_(treedepth) {}
+  explicit ObliviousMart(const XmlModel &model);
+  std::string name() const override { return NAME_; }
+  static const std::string NAME_;
+
+ protected:
+  uint32_t algo_id() const override { return QR_ALGO_OBVMART; }
+  size_t tree_depth() const override { return treedepth_; }
+  void write_xml_info(std::ostream &os) const override;
+  std::ostream &put(std::ostream &os) const override;
+  size_t treedepth_;
+};
+
+class ObliviousLambdaMart : public ObliviousMart {
+ public:
+  using ObliviousMart::ObliviousMart;
+  std::string name() const override { return NAME_; }
+  static const std::string NAME_;
+
+ protected:
+  uint32_t algo_id() const override { return QR_ALGO_OBVLAMBDAMART; }
+};
+
+}  // namespace forests
+}  // namespace learning
+}  // namespace quickrank
+
+#endif

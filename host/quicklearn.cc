@@ -1,0 +1,123 @@
+// quicklearn (B200): the command-line front end of the reference (src/quicklearn.cc, src/driver/driver.cc)
+// for the algorithms whose hot path runs on the GPU.  Same option names and defaults
+// (quicklearn.cc:97-140): LAMBDAMART, 1000 trees, shrinkage 0.1, --num-thresholds 0 (= one per distinct
+// value), min leaf support 1, end-after-rounds 100, 10 leaves, depth 3, NDCG@10, partial save 100.
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <string>
+
+#include "quickrank_host.h"
+
+using namespace quickrank;
+
+static void usage() {
+  std::cout << "quicklearn (quickrank_b200): LambdaMART / MART / oblivious variants on NVIDIA B200\n"
+               "  --algo <MART|LAMBDAMART|OBVMART|OBVLAMBDAMART>   (default LAMBDAMART)\n"
+               "  --train <svml file> [--valid <svml file>] [--test <svml file>]\n"
+               "  --model-out <xml> | --model-in <xml>  [--restart-train]\n"
+               "  --num-trees N (1000)  --shrinkage X (0.1)  --num-thresholds N (0 = unlimited)\n"
+               "  --min-leaf-support N (1)  --end-after-rounds N (100)  --num-leaves N (10)  --tree-depth N (3)\n"
+               "  --train-metric NDCG  --train-cutoff K (10)  --test-metric NDCG  --test-cutoff K (10)\n"
+               "  --partial N (100)  --scores <file>\n"
+               "  --hist-mode <fast|reference> (fast)  --device N\n";
+}
+
+int main(int argc, char **argv) {
+  std::map<std::string, std::string> opt;
+  for (int i = 1; i < argc; ++i) {
+    std::string a = argv[i];
+    if (a == "-h" || a == "--help") { usage(); return EXIT_SUCCESS; }
+    if (a.rfind("--", 0) != 0) { std::cerr << "!!! Unexpected argument " << a << std::endl; return EXIT_FAILURE; }
+    a = a.substr(2);
+    if (a == "restart-train") { opt[a] = "1"; continue; }
+    if (i + 1 >= argc) { std::cerr << "!!! Option --" << a << " needs a value" << std::endl; return EXIT_FAILURE; }
+    opt[a] = argv[++i];
+  }
+  auto get = [&](const char *k, const char *def) { auto it = opt.find(k); return it == opt.end() ? std::string(def) : it->second; };
+  auto geti = [&](const char *k, size_t def) { auto it = opt.find(k); return it == opt.end() ? def : (size_t) strtoull(it->second.c_str(), nullptr, 10); };
+
+  const std::string algo = get("algo", "LAMBDAMART");
+  const size_t ntrees = geti("num-trees", 1000), nthr = geti("num-thresholds", 0), minls = geti("min-leaf-support", 1);
+  const size_t esr = geti("end-after-rounds", 100), nleaves = geti("num-leaves", 10), depth = geti("tree-depth", 3);
+  const double shrinkage = strtod(get("shrinkage", "0.1").c_str(), nullptr);
+  const size_t partial = geti("partial", 100);
+
+  std::shared_ptr<learning::LTR_Algorithm> ranker;
+  learning::forests::Mart *mart = nullptr;
+  if (opt.count("model-in") && !opt.count("restart-train")) {
+    std::cout << "# Loading model from file " << opt["model-in"] << std::endl;
+    ranker = learning::LTR_Algorithm::load_model_from_file(opt["model-in"]);
+    if (!ranker) { std::cerr << "!!! Model type not supported for loading" << std::endl; return EXIT_FAILURE; }
+  } else if (algo == "MART") {
+    ranker.reset(mart = new learning::forests::Mart(ntrees, shrinkage, nthr, nleaves, minls, 1.0f, 1.0f, esr, 0.0f));
+  } else if (algo == "LAMBDAMART") {
+    ranker.reset(mart = new learning::forests::LambdaMart(ntrees, shrinkage, nthr, nleaves, minls, 1.0f, 1.0f, esr, 0.0f));
+  } else if (algo == "OBVMART") {
+    ranker.reset(mart = new learning::forests::ObliviousMart(ntrees, shrinkage, nthr, depth, minls, 1.0f, 1.0f, esr, 0.0f));
+  } else if (algo == "OBVLAMBDAMART") {
+    ranker.reset(mart = new learning::forests::ObliviousLambdaMart(ntrees, shrinkage, nthr, depth, minls, 1.0f, 1.0f, esr, 0.0f));
+  } else {
+    std::cerr << "!!! Algorithm " << algo << " is not accelerated by this build (see DESIGN.md, out of scope)." << std::endl;
+    return EXIT_FAILURE;
+  }
+  if (!mart) mart = dynamic_cast<learning::forests::Mart *>(ranker.get());
+  if (mart) {
+    mart->set_hist_mode(get("hist-mode", "fast") == "reference" ? QR_HIST_REFERENCE : QR_HIST_FAST);
+    if (opt.count("device")) mart->set_device(atoi(opt["device"].c_str()));
+  }
+  std::cout << "#" << std::endl << *ranker << "#" << std::endl;
+
+  if (get("train-metric", "NDCG") != "NDCG" || get("test-metric", "NDCG") != "NDCG") {
+    std::cerr << "!!! Only NDCG is supported by the GPU engine." << std::endl;
+    return EXIT_FAILURE;
+  }
+  auto load = [](const std::string &file) {
+    io::Svml reader;
+    auto t0 = std::chrono::high_resolution_clock::now();
+    std::shared_ptr<data::Dataset> ds = reader.read_horizontal(file);
+    double s = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    std::cout << "#\t Reading time: " << std::setprecision(2) << s << " s." << std::endl
+              << "#\t Dataset size: " << ds->num_instances() << " x " << ds->num_features()
+              << " (instances x features)" << std::endl
+              << "#\t Num queries: " << ds->num_queries() << std::endl;
+    return ds;
+  };
+
+  if (opt.count("train")) {
+    std::shared_ptr<metric::ir::Metric> train_metric(new metric::ir::Ndcg(geti("train-cutoff", 10)));
+    std::cout << "# Reading training dataset: " << opt["train"] << std::endl;
+    auto train = load(opt["train"]);
+    std::shared_ptr<data::Dataset> valid;
+    if (opt.count("valid")) {
+      std::cout << "# Reading validation dataset: " << opt["valid"] << std::endl;
+      valid = load(opt["valid"]);
+    }
+    std::cout << "#" << std::endl << "# training scorer: " << *train_metric << std::endl;
+    ranker->learn(train, valid, train_metric, partial, get("model-out", ""));
+    if (opt.count("model-out")) {
+      std::cout << "# Writing model to file: " << opt["model-out"] << std::endl;
+      ranker->save(opt["model-out"]);
+    }
+  }
+  if (opt.count("test")) {
+    std::shared_ptr<metric::ir::Metric> test_metric(new metric::ir::Ndcg(geti("test-cutoff", 10)));
+    std::cout << "# Reading test dataset: " << opt["test"] << std::endl;
+    auto test = load(opt["test"]);
+    std::vector<Score> scores(test->num_instances());
+    ranker->score_dataset(test, scores.data());
+    const MetricScore m = test_metric->evaluate_dataset(test, scores.data());
+    std::cout << std::endl << *test_metric << " on test data = " << std::setprecision(4) << m << std::endl << std::endl;
+    if (opt.count("scores")) {
+      std::ofstream os(opt["scores"]);
+      os << std::setprecision(15);
+      for (size_t i = 0; i < test->num_instances(); ++i) os << scores[i] << std::endl;
+      std::cout << "# Scores written to file: " << opt["scores"] << std::endl;
+    }
+  }
+  return EXIT_SUCCESS;
+}

@@ -1,0 +1,790 @@
+// quickrank_b200 host layer — implementation.  See host/include/quickrank_host.h.
+#include "quickrank_host.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iomanip>
+#include <map>
+#include <sstream>
+
+namespace quickrank {
+
+// ------------------------------------------------------------------------------------------------
+// data
+// ------------------------------------------------------------------------------------------------
+namespace data {
+
+void QueryResults::indexing_of_sorted_labels(const Score *scores, size_t *dest) const {
+  for (size_t i = 0; i < num_results_; ++i) dest[i] = i;
+  // libstdc++ std::sort with a strict "greater" comparator: the same call the reference makes
+  // (queryresults.cc:47-53), hence the same permutation of tied scores
+  std::sort(dest, dest + num_results_, [scores](int i, int j) { return scores[i] > scores[j]; });
+}
+
+void QueryResults::sorted_labels(const Score *scores, Label *dest, size_t cutoff) const {
+  std::vector<size_t> idx(num_results_);
+  indexing_of_sorted_labels(scores, idx.data());
+  for (size_t i = 0; i < num_results_ && i < cutoff; ++i) dest[i] = labels_[idx[i]];
+}
+
+Dataset::Dataset(size_t n_instances, size_t n_features) : num_features_(n_features), max_instances_(n_instances) {
+  void *p = nullptr, *q = nullptr;
+  if (posix_memalign(&p, 64, std::max<size_t>(64, max_instances_ * num_features_ * sizeof(Feature))) != 0 ||
+      posix_memalign(&q, 64, std::max<size_t>(64, max_instances_ * sizeof(Label))) != 0) {
+    std::cerr << "!!! Impossible to allocate memory for dataset storage." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  data_ = (Feature *) p;
+  labels_ = (Label *) q;
+  std::memset(data_, 0, max_instances_ * num_features_ * sizeof(Feature));
+  offsets_.push_back(0);
+}
+
+Dataset::~Dataset() {
+  free(data_);
+  free(labels_);
+}
+
+void Dataset::addInstance(QueryID q_id, Label i_label, const std::vector<Feature> &i_features) {
+  if (i_features.size() > num_features_ || num_instances_ == max_instances_) {
+    std::cerr << "!!! Impossible to add a new instance to the dataset." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  labels_[num_instances_] = i_label;
+  std::copy(i_features.begin(), i_features.end(), data_ + num_instances_ * num_features_);
+  if (num_instances_ == 0 || last_instance_id_ != q_id) {
+    num_queries_++;
+    offsets_.push_back(0);
+    last_instance_id_ = q_id;
+  }
+  num_instances_++;
+  offsets_.back() = num_instances_;
+}
+
+std::unique_ptr<QueryResults> Dataset::getQueryResults(size_t i) const {
+  const size_t n = offsets_[i + 1] - offsets_[i];
+  return std::unique_ptr<QueryResults>(
+      new QueryResults(n, labels_ + offsets_[i], data_ + offsets_[i] * num_features_));
+}
+
+VerticalDataset::VerticalDataset(std::shared_ptr<Dataset> h_dataset) : src_(h_dataset) {}
+
+Feature *VerticalDataset::at(size_t document_id, size_t feature_id) {
+  if (col_.empty()) {   // host transpose only on demand; training transposes on the device
+    const size_t n = src_->num_instances(), f = src_->num_features();
+    col_.resize(n * f);
+    for (size_t i = 0; i < n; ++i)
+      for (size_t j = 0; j < f; ++j) col_[j * n + i] = src_->data()[i * f + j];
+  }
+  return col_.data() + feature_id * src_->num_instances() + document_id;
+}
+
+}  // namespace data
+
+// ------------------------------------------------------------------------------------------------
+// metric (host evaluation of arbitrary score vectors: used outside the training loop)
+// ------------------------------------------------------------------------------------------------
+namespace metric {
+namespace ir {
+
+MetricScore Metric::evaluate_dataset(const std::shared_ptr<data::Dataset> dataset, const Score *scores) const {
+  if (dataset->num_queries() == 0) return 0.0;
+  MetricScore avg = 0.0;
+  for (size_t q = 0; q < dataset->num_queries(); q++) {
+    std::unique_ptr<data::QueryResults> r = dataset->getQueryResults(q);
+    avg += evaluate_result_list(r.get(), scores);
+    scores += r->num_results();
+  }
+  return avg / (MetricScore) dataset->num_queries();
+}
+
+MetricScore Dcg::compute_dcg(const Label *labels, size_t len) const {
+  const size_t size = std::min(cutoff(), len);
+  double dcg = 0.0;
+  for (size_t i = 0; i < size; ++i) dcg += (std::pow(2.0, (double) labels[i]) - 1.0) / std::log2((double) ((float) i + 2.0f));
+  return dcg;
+}
+
+MetricScore Dcg::evaluate_result_list(const data::QueryResults *rl, const Score *scores) const {
+  const size_t size = std::min(cutoff(), rl->num_results());
+  if (size == 0) return 0.0;
+  std::vector<Label> sorted_l(size);
+  rl->sorted_labels(scores, sorted_l.data(), cutoff());
+  return compute_dcg(sorted_l.data(), size);
+}
+
+std::ostream &Dcg::put(std::ostream &os) const {
+  if (cutoff() != Metric::NO_CUTOFF) return os << name() << "@" << cutoff();
+  return os << name();
+}
+
+MetricScore Ndcg::compute_idcg(const data::QueryResults *rl) const {
+  std::vector<Label> copy(rl->labels(), rl->labels() + rl->num_results());
+  std::sort(copy.begin(), copy.end(), std::greater<int>());   // ndcg.cc:40-41 (int comparison)
+  return compute_dcg(copy.data(), copy.size());
+}
+
+MetricScore Ndcg::evaluate_result_list(const data::QueryResults *rl, const Score *scores) const {
+  if (rl->num_results() == 0) return 0.0;
+  const MetricScore idcg = compute_idcg(rl);
+  return idcg > 0 ? Dcg::evaluate_result_list(rl, scores) / idcg : 0.0;
+}
+
+std::ostream &Ndcg::put(std::ostream &os) const {
+  if (cutoff() != Metric::NO_CUTOFF) return os << name() << "@" << cutoff();
+  return os << name();
+}
+
+}  // namespace ir
+}  // namespace metric
+
+// ------------------------------------------------------------------------------------------------
+// SVMLight I/O
+// ------------------------------------------------------------------------------------------------
+namespace io {
+
+std::unique_ptr<data::Dataset> Svml::read_horizontal(const std::string &filename) {
+  FILE *f = fopen(filename.c_str(), "r");
+  if (!f) {
+    std::cerr << "!!! Error while opening file " << filename << "." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  std::vector<QueryID> qids;
+  std::vector<Label> labels;
+  std::vector<std::vector<std::pair<size_t, Feature>>> rows;
+  size_t maxfid = 0;
+  char *line = nullptr;
+  size_t cap = 0;
+  ssize_t nread;
+  while ((nread = getline(&line, &cap, f)) > 0) {
+    char *p = line;
+    while (*p == ' ' || *p == '\t') ++p;
+    if (*p == '#' || *p == '\n' || *p == '\0' || *p == '\r') continue;
+    char *hash = strchr(p, '#');
+    if (hash) *hash = '\0';
+    char *end = nullptr;
+    const Label rel = (Label) strtod(p, &end);
+    if (end == p) exit(2);
+    p = end;
+    while (*p == ' ' || *p == '\t') ++p;
+    if (strncmp(p, "qid:", 4) != 0) exit(2);
+    const QueryID qid = (QueryID) strtoull(p + 4, &end, 10);
+    p = end;
+    std::vector<std::pair<size_t, Feature>> row;
+    for (;;) {
+      while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') ++p;
+      if (*p == '\0') break;
+      const size_t fid = (size_t) strtoull(p, &end, 10);
+      if (end == p || *end != ':') exit(4);
+      p = end + 1;
+      const Feature v = strtof(p, &end);
+      if (end == p || fid == 0) exit(4);
+      p = end;
+      row.emplace_back(fid, v);
+      maxfid = std::max(maxfid, fid);
+    }
+    qids.push_back(qid);
+    labels.push_back(rel);
+    rows.push_back(std::move(row));
+  }
+  free(line);
+  fclose(f);
+  std::unique_ptr<data::Dataset> ds(new data::Dataset(rows.size(), maxfid));
+  std::vector<Feature> dense(maxfid);
+  for (size_t i = 0; i < rows.size(); ++i) {
+    std::fill(dense.begin(), dense.end(), 0.0f);
+    for (auto &kv : rows[i]) dense[kv.first - 1] = kv.second;
+    ds->addInstance(qids[i], labels[i], dense);
+  }
+  return ds;
+}
+
+void Svml::write(std::shared_ptr<data::Dataset> dataset, const std::string &filename) {
+  std::ofstream out(filename, std::ofstream::out | std::ofstream::trunc);
+  out << std::setprecision(std::numeric_limits<float>::max_digits10);
+  for (size_t q = 0; q < dataset->num_queries(); q++) {
+    auto r = dataset->getQueryResults(q);
+    const Feature *x = r->features();
+    for (size_t i = 0; i < r->num_results(); ++i) {
+      out << r->labels()[i] << " qid:" << q + 1;
+      for (size_t f = 0; f < dataset->num_features(); ++f) out << " " << f + 1 << ":" << x[i * dataset->num_features() + f];
+      out << std::endl;
+    }
+  }
+}
+
+}  // namespace io
+}  // namespace quickrank
+
+// ------------------------------------------------------------------------------------------------
+// trees
+// ------------------------------------------------------------------------------------------------
+static RTNode *from_flat_rec(const qr_flat_tree &t, int32_t i) {
+  if (t.feature[i] < 0) {
+    RTNode *n = new RTNode(t.value[i]);
+    if (t.count) n->nsampleids = (size_t) t.count[i];
+    if (t.deviance) n->deviance = t.deviance[i];
+    return n;
+  }
+  RTNode *l = from_flat_rec(t, t.left[i]);
+  RTNode *r = from_flat_rec(t, t.right[i]);
+  // featureid = featureidx + 1 (rt.cc:350-352)
+  RTNode *n = new RTNode(t.threshold[i], (size_t) t.feature[i], (size_t) t.feature[i] + 1, l, r);
+  n->avglabel = t.value ? t.value[i] : 0.0;
+  if (t.count) n->nsampleids = (size_t) t.count[i];
+  if (t.deviance) n->deviance = t.deviance[i];
+  return n;
+}
+
+RTNode *RegressionTree::from_flat(const qr_flat_tree &t) { return t.nnodes ? from_flat_rec(t, 0) : nullptr; }
+
+void RegressionTree::to_flat(const RTNode *n, std::vector<int32_t> &feature, std::vector<float> &threshold,
+                             std::vector<int32_t> &left, std::vector<int32_t> &right, std::vector<double> &value) {
+  const int32_t id = (int32_t) feature.size();
+  feature.push_back(n->is_leaf() ? -1 : (int32_t) n->get_feature_idx());
+  threshold.push_back(n->threshold);
+  left.push_back(-1);
+  right.push_back(-1);
+  value.push_back(n->avglabel);
+  if (!n->is_leaf()) {
+    left[id] = (int32_t) feature.size();
+    to_flat(n->left, feature, threshold, left, right, value);
+    right[id] = (int32_t) feature.size();
+    to_flat(n->right, feature, threshold, left, right, value);
+  }
+}
+
+Ensemble::~Ensemble() {
+  for (auto &t : trees_) delete t.root;
+}
+
+void Ensemble::push(RTNode *root, double weight, float maxlabel) { trees_.push_back({root, weight, maxlabel}); }
+
+void Ensemble::pop() {
+  delete trees_.back().root;
+  trees_.pop_back();
+}
+
+quickrank::Score Ensemble::score_instance(const quickrank::Feature *d, size_t offset) const {
+  double sum = 0.0;
+  for (auto &t : trees_) sum += t.root->score_instance(d, offset) * t.weight;
+  return sum;
+}
+
+std::vector<double> Ensemble::get_weights() const {
+  std::vector<double> w;
+  for (auto &t : trees_) w.push_back(t.weight);
+  return w;
+}
+
+bool Ensemble::update_ensemble_weights(std::vector<double> &weights) {
+  if (weights.size() != trees_.size()) {
+    std::cerr << "# ## ERROR!! Ensemble size does not match size of the weight vector in updating the weights"
+              << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  for (size_t i = 0; i < trees_.size(); ++i) trees_[i].weight = weights[i];
+  return true;
+}
+
+// --- XML (tab indentation, no declaration; schema of mart.cc:470-491, ensemble.cc:133-147,
+//     rtnode.cc:48-77) ---
+static std::string fmt_g(double v, int digits) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%.*g", digits, v);
+  return buf;
+}
+
+static void tabs(std::ostream &os, int n) {
+  for (int i = 0; i < n; ++i) os << '\t';
+}
+
+static void write_node(std::ostream &os, const RTNode *n, int indent, const char *pos) {
+  tabs(os, indent);
+  os << "<split";
+  if (pos) os << " pos=\"" << pos << "\"";
+  os << ">\n";
+  if (n->is_leaf()) {
+    tabs(os, indent + 1);
+    os << "<output>" << fmt_g(n->avglabel, std::numeric_limits<double>::max_digits10) << "</output>\n";
+  } else {
+    tabs(os, indent + 1);
+    os << "<feature>" << n->get_feature_id() << "</feature>\n";
+    tabs(os, indent + 1);
+    os << "<threshold>" << fmt_g((double) n->threshold, std::numeric_limits<float>::max_digits10) << "</threshold>\n";
+    write_node(os, n->left, indent + 1, "left");
+    write_node(os, n->right, indent + 1, "right");
+  }
+  tabs(os, indent);
+  os << "</split>\n";
+}
+
+void Ensemble::write_xml(std::ostream &os, int indent) const {
+  tabs(os, indent);
+  os << "<ensemble>\n";
+  for (size_t i = 0; i < trees_.size(); ++i) {
+    tabs(os, indent + 1);
+    os << "<tree id=\"" << i + 1 << "\" weight=\"" << fmt_g(trees_[i].weight, 17) << "\">\n";
+    write_node(os, trees_[i].root, indent + 2, nullptr);
+    tabs(os, indent + 1);
+    os << "</tree>\n";
+  }
+  tabs(os, indent);
+  os << "</ensemble>\n";
+}
+
+namespace quickrank {
+namespace learning {
+namespace forests {
+
+// Minimal reader for the model schema: elements, attributes, text.  No entities beyond the five
+// predefined ones are ever written by either implementation.
+struct XmlNode {
+  std::string name, text;
+  std::map<std::string, std::string> attr;
+  std::vector<std::unique_ptr<XmlNode>> kids;
+  const XmlNode *child(const std::string &n) const {
+    for (auto &k : kids) if (k->name == n) return k.get();
+    return nullptr;
+  }
+  std::string child_text(const std::string &n, const std::string &def = "") const {
+    const XmlNode *c = child(n);
+    return c ? c->text : def;
+  }
+};
+
+struct XmlModel {
+  std::unique_ptr<XmlNode> root;   // <ranker>
+};
+
+static bool parse_xml(const std::string &s, XmlModel *out) {
+  std::vector<XmlNode *> stack;
+  std::unique_ptr<XmlNode> top;
+  size_t i = 0;
+  const size_t n = s.size();
+  while (i < n) {
+    if (s[i] != '<') {
+      const size_t e = s.find('<', i);
+      const std::string t = s.substr(i, (e == std::string::npos ? n : e) - i);
+      if (!stack.empty()) {
+        const size_t a = t.find_first_not_of(" \t\r\n");
+        if (a != std::string::npos) stack.back()->text += t.substr(a, t.find_last_not_of(" \t\r\n") - a + 1);
+      }
+      i = e == std::string::npos ? n : e;
+      continue;
+    }
+    if (s.compare(i, 2, "<?") == 0) { i = s.find("?>", i); if (i == std::string::npos) return false; i += 2; continue; }
+    if (s.compare(i, 4, "<!--") == 0) { i = s.find("-->", i); if (i == std::string::npos) return false; i += 3; continue; }
+    const size_t e = s.find('>', i);
+    if (e == std::string::npos) return false;
+    if (s[i + 1] == '/') {
+      if (stack.empty()) return false;
+      stack.pop_back();
+      i = e + 1;
+      continue;
+    }
+    std::string tag = s.substr(i + 1, e - i - 1);
+    const bool selfclose = !tag.empty() && tag.back() == '/';
+    if (selfclose) tag.pop_back();
+    std::unique_ptr<XmlNode> node(new XmlNode());
+    size_t p = 0;
+    while (p < tag.size() && !isspace((unsigned char) tag[p])) ++p;
+    node->name = tag.substr(0, p);
+    while (p < tag.size()) {
+      while (p < tag.size() && isspace((unsigned char) tag[p])) ++p;
+      const size_t eq = tag.find('=', p);
+      if (eq == std::string::npos) break;
+      const std::string key = tag.substr(p, eq - p);
+      const char q = tag[eq + 1];
+      const size_t qe = tag.find(q, eq + 2);
+      if (qe == std::string::npos) return false;
+      node->attr[key] = tag.substr(eq + 2, qe - eq - 2);
+      p = qe + 1;
+    }
+    XmlNode *raw = node.get();
+    if (stack.empty()) top = std::move(node);
+    else stack.back()->kids.push_back(std::move(node));
+    if (!selfclose) stack.push_back(raw);
+    i = e + 1;
+  }
+  if (!top || !stack.empty()) return false;
+  out->root = std::move(top);
+  return true;
+}
+
+// RTNode::parse_xml (rtnode.cc:79-117): featureidx = feature - 1
+static RTNode *parse_split(const XmlNode &sp) {
+  const XmlNode *out = sp.child("output");
+  if (out) return new RTNode(strtod(out->text.c_str(), nullptr));
+  const unsigned fid = (unsigned) strtoul(sp.child_text("feature", "0").c_str(), nullptr, 10);
+  const float thr = strtof(sp.child_text("threshold", "0").c_str(), nullptr);
+  RTNode *l = nullptr, *r = nullptr;
+  for (auto &k : sp.kids) {
+    if (k->name != "split") continue;
+    auto it = k->attr.find("pos");
+    if (it != k->attr.end() && it->second == "left") l = parse_split(*k);
+    else r = parse_split(*k);
+  }
+  if (!l || !r) { delete l; delete r; return nullptr; }
+  return new RTNode(thr, (size_t) fid - 1, (size_t) fid, l, r);
+}
+
+const std::string Mart::NAME_ = "MART";
+const std::string LambdaMart::NAME_ = "LAMBDAMART";
+const std::string ObliviousMart::NAME_ = "OBVMART";
+const std::string ObliviousLambdaMart::NAME_ = "OBVLAMBDAMART";
+
+void Mart::die(const char *what) const {
+  std::cerr << "!!! " << what << ": " << qr_last_error() << std::endl;
+  exit(EXIT_FAILURE);
+}
+
+// Mart(const pugi::xml_document&) (mart.cc:37-89)
+Mart::Mart(const XmlModel &model) {
+  const XmlNode *info = model.root->child("info");
+  const XmlNode *ens = model.root->child("ensemble");
+  auto geti = [&](const char *k) { return (size_t) strtoull(info ? info->child_text(k, "0").c_str() : "0", nullptr, 10); };
+  ntrees_ = geti("trees");
+  nleaves_ = geti("leaves");
+  minleafsupport_ = geti("leafsupport");
+  nthresholds_ = geti("discretization");
+  valid_iterations_ = geti("estop");
+  shrinkage_ = info ? strtod(info->child_text("shrinkage", "0").c_str(), nullptr) : 0.0;
+  subsample_ = info && info->child("subsample") ? strtof(info->child_text("subsample").c_str(), nullptr) : 1.0f;
+  max_features_ = info && info->child("max_features") ? strtof(info->child_text("max_features").c_str(), nullptr) : 1.0f;
+  collapse_leaves_factor_ = 0;
+  ensemble_model_.set_capacity(ntrees_);
+  if (ens)
+    for (auto &t : ens->kids) {
+      if (t->name != "tree") continue;
+      const XmlNode *sp = t->child("split");
+      RTNode *root = sp ? parse_split(*sp) : nullptr;
+      if (!root) {
+        std::cerr << "!!! Unable to parse tree from XML model." << std::endl;
+        exit(EXIT_FAILURE);
+      }
+      auto w = t->attr.find("weight");
+      ensemble_model_.push(root, w != t->attr.end() ? strtod(w->second.c_str(), nullptr) : 1.0, -1);
+    }
+}
+
+ObliviousMart::ObliviousMart(const XmlModel &model) : Mart(model) {
+  const XmlNode *info = model.root->child("info");
+  treedepth_ = info ? (size_t) strtoull(info->child_text("depth", "0").c_str(), nullptr, 10) : 0;
+}
+
+Mart::~Mart() {
+  if (ctx_) qr_ctx_destroy(ctx_);
+  if (valid_ctx_) qr_ctx_destroy(valid_ctx_);
+}
+
+std::ostream &Mart::put(std::ostream &os) const {
+  os << "# Ranker: " << name() << std::endl
+     << "# max no. of trees = " << ntrees_ << std::endl
+     << "# no. of tree leaves = " << nleaves_ << std::endl
+     << "# shrinkage = " << shrinkage_ << std::endl
+     << "# min leaf support = " << minleafsupport_ << std::endl;
+  if (nthresholds_) os << "# no. of thresholds = " << nthresholds_ << std::endl;
+  else os << "# no. of thresholds = unlimited" << std::endl;
+  if (valid_iterations_) os << "# no. of no gain rounds before early stop = " << valid_iterations_ << std::endl;
+  os << "# engine = quickrank_b200 (CUDA sm_100a), histogram mode = "
+     << (hist_mode_ == QR_HIST_REFERENCE ? "reference order" : "fixed point") << std::endl;
+  return os;
+}
+
+std::ostream &ObliviousMart::put(std::ostream &os) const {
+  os << "# Ranker: " << name() << std::endl
+     << "# max no. of trees = " << ntrees_ << std::endl
+     << "# max tree depth = " << treedepth_ << std::endl
+     << "# shrinkage = " << shrinkage_ << std::endl
+     << "# min leaf support = " << minleafsupport_ << std::endl;
+  if (nthresholds_) os << "# no. of thresholds = " << nthresholds_ << std::endl;
+  else os << "# no. of thresholds = unlimited" << std::endl;
+  if (valid_iterations_) os << "# no. of no gain rounds before early stop = " << valid_iterations_ << std::endl;
+  return os;
+}
+
+// ---- the hooks: every body is a call into the CUDA library ------------------------------------
+
+void Mart::init(std::shared_ptr<data::VerticalDataset> training_dataset) {
+  qr_params p;
+  std::memset(&p, 0, sizeof(p));
+  p.algo = algo_id();
+  p.nleaves = (uint32_t) nleaves_;
+  p.treedepth = (uint32_t) tree_depth();
+  p.minleafsupport = (uint32_t) minleafsupport_;
+  p.nthresholds = nthresholds_;
+  p.ndcg_cutoff = metric_cutoff_ == metric::ir::Metric::NO_CUTOFF ? 0 : metric_cutoff_;
+  p.shrinkage = shrinkage_;
+  p.hist_mode = hist_mode_;
+  p.device = device_;
+  auto h = training_dataset->horizontal();
+  if (qr_ctx_create_rowmajor(h->data(), h->num_instances(), h->num_features(), h->labels(), h->offsets().data(),
+                             h->num_queries(), &p, &ctx_) != QR_OK)
+    die("Impossible to initialise the GPU training context");
+}
+
+void Mart::clear(size_t) {
+  if (ctx_) qr_ctx_destroy(ctx_);
+  if (valid_ctx_) qr_ctx_destroy(valid_ctx_);
+  ctx_ = valid_ctx_ = nullptr;
+}
+
+void Mart::compute_pseudoresponses(std::shared_ptr<data::VerticalDataset>, metric::ir::Metric *, bool *sample_presence) {
+  if (sample_presence) {
+    std::cerr << "!!! Document sub-sampling is not supported by the GPU engine." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  if (qr_compute_pseudoresponses(ctx_) != QR_OK) die("compute_pseudoresponses");
+}
+
+std::unique_ptr<RegressionTree> Mart::fit_regressor_on_gradient(std::shared_ptr<data::VerticalDataset>, size_t *) {
+  const uint32_t cap = 2 * (uint32_t) std::max<size_t>(nleaves_, 1) + 1;
+  std::vector<int32_t> feature(cap), left(cap), right(cap);
+  std::vector<uint32_t> tidx(cap);
+  std::vector<float> thr(cap);
+  std::vector<double> value(cap), dev(cap);
+  std::vector<uint64_t> count(cap);
+  qr_flat_tree t;
+  t.capacity = cap; t.nnodes = t.nleaves = 0;
+  t.feature = feature.data(); t.threshold_idx = tidx.data(); t.threshold = thr.data();
+  t.left = left.data(); t.right = right.data(); t.value = value.data(); t.deviance = dev.data(); t.count = count.data();
+  if (qr_fit_tree(ctx_, &t) != QR_OK) die("fit_regressor_on_gradient");
+  return std::unique_ptr<RegressionTree>(new RegressionTree(RegressionTree::from_flat(t)));
+}
+
+void Mart::update_modelscores(std::shared_ptr<data::VerticalDataset>, Score *, RegressionTree *) {
+  if (qr_update_modelscores(ctx_, shrinkage_) != QR_OK) die("update_modelscores");
+}
+
+// validation set: the new tree is applied on the device to the validation context
+void Mart::update_modelscores(std::shared_ptr<data::Dataset>, Score *, RegressionTree *tree) {
+  std::vector<int32_t> feature, left, right;
+  std::vector<float> thr;
+  std::vector<double> value;
+  RegressionTree::to_flat(tree->get_proot(), feature, thr, left, right, value);
+  std::vector<uint32_t> tidx(feature.size(), 0);
+  for (size_t i = 0; i < feature.size(); ++i) {
+    if (feature[i] < 0) continue;
+    const float *tv = nullptr;
+    size_t tn = 0;
+    if (qr_get_thresholds(ctx_, (size_t) feature[i], &tv, &tn) != QR_OK) die("update_modelscores");
+    const float *it = std::find(tv, tv + tn, thr[i]);
+    tidx[i] = (uint32_t) (it - tv);
+  }
+  qr_flat_tree t;
+  t.capacity = t.nnodes = (uint32_t) feature.size();
+  t.nleaves = 0;
+  t.feature = feature.data(); t.threshold_idx = tidx.data(); t.threshold = thr.data();
+  t.left = left.data(); t.right = right.data(); t.value = value.data(); t.deviance = nullptr; t.count = nullptr;
+  if (qr_apply_tree(valid_ctx_, &t, shrinkage_) != QR_OK) die("update_modelscores (validation)");
+}
+
+MetricScore Mart::evaluate_training(metric::ir::Metric *) {
+  double m = 0;
+  if (qr_evaluate(ctx_, &m) != QR_OK) die("evaluate_dataset");
+  return m;
+}
+
+// Mart::learn (mart.cc:208-416): same loop, same stdout table
+void Mart::learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_ptr<data::Dataset> validation_dataset,
+                 std::shared_ptr<metric::ir::Metric> scorer, size_t partial_save, const std::string output_basename) {
+  if (scorer->name() != "NDCG") {
+    std::cerr << "!!! The GPU engine optimises NDCG only (got " << scorer->name() << ")." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  if (subsample_ != 1.0f || max_features_ != 1.0f || collapse_leaves_factor_ != 0.0f) {
+    std::cerr << "!!! subsample, max_features and collapse_leaves_factor are not supported by the GPU engine."
+              << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  std::cout << "# Initialization";
+  std::cout.flush();
+  auto t0 = std::chrono::high_resolution_clock::now();
+  metric_cutoff_ = scorer->cutoff();
+  std::shared_ptr<data::VerticalDataset> vertical_training(new data::VerticalDataset(training_dataset));
+  best_metric_on_validation_ = std::numeric_limits<double>::lowest();
+  best_metric_on_training_ = std::numeric_limits<double>::lowest();
+  best_model_ = 0;
+  ensemble_model_.set_capacity(ntrees_);
+  init(vertical_training);
+  if (validation_dataset) {
+    if (qr_ctx_create_eval(ctx_, validation_dataset->data(), validation_dataset->num_instances(),
+                           validation_dataset->num_features(), validation_dataset->labels(),
+                           validation_dataset->offsets().data(), validation_dataset->num_queries(), &valid_ctx_) != QR_OK)
+      die("Impossible to initialise the GPU validation context");
+  }
+  if (ensemble_model_.is_notempty()) {   // restart from a loaded model (mart.cc:237-253)
+    best_model_ = ensemble_model_.get_size() - 1;
+    std::vector<Score> s(training_dataset->num_instances());
+    score_dataset(training_dataset, s.data());
+    if (qr_set_scores(ctx_, s.data()) != QR_OK) die("restart");
+    best_metric_on_training_ = evaluate_training(scorer.get());
+    if (validation_dataset) {
+      std::vector<Score> v(validation_dataset->num_instances());
+      score_dataset(validation_dataset, v.data());
+      if (qr_set_scores(valid_ctx_, v.data()) != QR_OK) die("restart");
+      if (qr_evaluate(valid_ctx_, &best_metric_on_validation_) != QR_OK) die("restart");
+    }
+  }
+  double init_time = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+  std::cout << ": " << std::setprecision(2) << init_time << " s." << std::endl;
+
+  std::cout << std::fixed << std::setprecision(4);
+  std::cout << "# Training:" << std::endl;
+  std::cout << "# -------------------------" << std::endl;
+  std::cout << "# iter. training validation" << std::endl;
+  std::cout << "# -------------------------" << std::endl;
+  if (ensemble_model_.is_notempty()) {
+    std::cout << std::setw(7) << ensemble_model_.get_size() << std::setw(9) << best_metric_on_training_;
+    if (validation_dataset) std::cout << std::setw(9) << best_metric_on_validation_;
+    std::cout << " *" << std::endl;
+  }
+  auto t1 = std::chrono::high_resolution_clock::now();
+  for (size_t m = ensemble_model_.get_size(); m < ntrees_; ++m) {
+    if (validation_dataset && (valid_iterations_ && m > best_model_ + valid_iterations_)) break;
+    compute_pseudoresponses(vertical_training, scorer.get(), nullptr);
+    // (the root-histogram refresh of mart.cc:335 happens inside fit_regressor_on_gradient)
+    std::unique_ptr<RegressionTree> tree = fit_regressor_on_gradient(vertical_training, nullptr);
+    ensemble_model_.push(tree->get_proot(), shrinkage_, 0);
+    update_modelscores(vertical_training, nullptr, tree.get());
+    const MetricScore metric_on_training = evaluate_training(scorer.get());
+    std::cout << std::setw(7) << m + 1 << std::setw(9) << metric_on_training;
+    if (validation_dataset) {
+      update_modelscores(validation_dataset, nullptr, tree.get());
+      MetricScore metric_on_validation = 0;
+      if (qr_evaluate(valid_ctx_, &metric_on_validation) != QR_OK) die("evaluate_dataset (validation)");
+      std::cout << std::setw(9) << metric_on_validation;
+      if (metric_on_validation > best_metric_on_validation_) {
+        best_metric_on_training_ = metric_on_training;
+        best_metric_on_validation_ = metric_on_validation;
+        best_model_ = ensemble_model_.get_size() - 1;
+        std::cout << " *";
+      }
+    } else if (metric_on_training > best_metric_on_training_) {
+      best_metric_on_training_ = metric_on_training;
+      best_model_ = ensemble_model_.get_size() - 1;
+      std::cout << " *";
+    }
+    std::cout << std::endl;
+    if (partial_save != 0 && !output_basename.empty() && (m + 1) % partial_save == 0) save(output_basename, (int) (m + 1));
+  }
+  if (validation_dataset)   // roll back to the best model on validation (mart.cc:390-395)
+    while (ensemble_model_.is_notempty() && ensemble_model_.get_size() > best_model_ + 1) ensemble_model_.pop();
+  double train_time = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t1).count();
+  std::cout << std::endl;
+  std::cout << *scorer << " on training data = " << best_metric_on_training_ << std::endl;
+  if (validation_dataset) std::cout << *scorer << " on validation data = " << best_metric_on_validation_ << std::endl;
+  clear(vertical_training->num_features());
+  std::cout << std::endl;
+  std::cout << "#\t Training Time: " << std::setprecision(2) << train_time << " s." << std::endl;
+}
+
+// LTR_Algorithm::score_dataset (ltr_algorithm.cc:44-52) on the GPU
+void Mart::score_dataset(std::shared_ptr<data::Dataset> dataset, Score *scores) const {
+  const size_t nt = ensemble_model_.get_size();
+  std::vector<std::vector<int32_t>> feature(nt), left(nt), right(nt);
+  std::vector<std::vector<float>> thr(nt);
+  std::vector<std::vector<double>> value(nt);
+  std::vector<qr_flat_tree> flat(nt);
+  std::vector<double> weights(nt);
+  for (size_t i = 0; i < nt; ++i) {
+    RegressionTree::to_flat(ensemble_model_.getTree((int) i), feature[i], thr[i], left[i], right[i], value[i]);
+    qr_flat_tree &t = flat[i];
+    t.capacity = t.nnodes = (uint32_t) feature[i].size();
+    t.nleaves = 0;
+    t.feature = feature[i].data(); t.threshold_idx = nullptr; t.threshold = thr[i].data();
+    t.left = left[i].data(); t.right = right[i].data(); t.value = value[i].data(); t.deviance = nullptr; t.count = nullptr;
+    weights[i] = ensemble_model_.getWeight((int) i);
+  }
+  qr_scorer *sc = nullptr;
+  if (qr_scorer_create(flat.data(), weights.data(), nt, dataset->num_features(), device_, &sc) != QR_OK) die("score_dataset");
+  if (qr_score_dataset(sc, dataset->data(), dataset->num_instances(), dataset->num_features(), scores) != QR_OK)
+    die("score_dataset");
+  qr_scorer_destroy(sc);
+}
+
+void Mart::write_xml_info(std::ostream &os) const {
+  os << "\t\t<type>" << name() << "</type>\n"
+     << "\t\t<trees>" << ntrees_ << "</trees>\n"
+     << "\t\t<leaves>" << nleaves_ << "</leaves>\n"
+     << "\t\t<shrinkage>" << fmt_g(shrinkage_, 17) << "</shrinkage>\n"
+     << "\t\t<leafsupport>" << minleafsupport_ << "</leafsupport>\n"
+     << "\t\t<discretization>" << nthresholds_ << "</discretization>\n"
+     << "\t\t<estop>" << valid_iterations_ << "</estop>\n"
+     << "\t\t<subsample>" << fmt_g(subsample_, 9) << "</subsample>\n"
+     << "\t\t<max_features>" << fmt_g(max_features_, 9) << "</max_features>\n"
+     << "\t\t<collapse_leaves_factor>" << fmt_g(collapse_leaves_factor_, 9) << "</collapse_leaves_factor>\n";
+}
+
+// obliviousmart.cc:74-81 (the reference writes the discretisation into <estop> as well)
+void ObliviousMart::write_xml_info(std::ostream &os) const {
+  os << "\t\t<type>" << name() << "</type>\n"
+     << "\t\t<trees>" << ntrees_ << "</trees>\n"
+     << "\t\t<leaves>" << nleaves_ << "</leaves>\n"
+     << "\t\t<depth>" << treedepth_ << "</depth>\n"
+     << "\t\t<shrinkage>" << fmt_g(shrinkage_, 17) << "</shrinkage>\n"
+     << "\t\t<leafsupport>" << minleafsupport_ << "</leafsupport>\n"
+     << "\t\t<discretization>" << nthresholds_ << "</discretization>\n"
+     << "\t\t<estop>" << nthresholds_ << "</estop>\n";
+}
+
+void Mart::write_xml_model(std::ostream &os) const {
+  os << "<ranker>\n\t<info>\n";
+  write_xml_info(os);
+  os << "\t</info>\n";
+  ensemble_model_.write_xml(os, 1);
+  os << "</ranker>\n";
+}
+
+}  // namespace forests
+
+void LTR_Algorithm::score_dataset(std::shared_ptr<data::Dataset> dataset, Score *scores) const {
+  const Feature *d = dataset->data();
+  for (size_t i = 0; i < dataset->num_instances(); i++) scores[i] = score_document(d + i * dataset->num_features());
+}
+
+void LTR_Algorithm::save(std::string output_basename, int iteration) const {
+  if (output_basename.empty()) return;
+  std::string filename(output_basename);
+  if (iteration != -1) filename += ".T" + std::to_string(iteration) + ".xml";
+  std::ofstream f(filename);
+  if (!f) {
+    std::cerr << "!!! Impossible to write model file " << filename << "." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  write_xml_model(f);
+}
+
+// ltr_algorithm.cc:67-128: dispatch on <info><type>
+std::shared_ptr<LTR_Algorithm> LTR_Algorithm::load_model_from_file(std::string model_filename) {
+  if (model_filename.empty()) {
+    std::cerr << "!!! Model filename is empty." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  std::ifstream f(model_filename);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  forests::XmlModel model;
+  if (!f || !forests::parse_xml(ss.str(), &model) || model.root->name != "ranker") {
+    std::cerr << "!!! Model " + model_filename + " is not parsed correctly." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  const forests::XmlNode *info = model.root->child("info");
+  const std::string type = info ? info->child_text("type") : "";
+  if (type == forests::Mart::NAME_) return std::shared_ptr<LTR_Algorithm>(new forests::Mart(model));
+  if (type == forests::LambdaMart::NAME_) return std::shared_ptr<LTR_Algorithm>(new forests::LambdaMart(model));
+  if (type == forests::ObliviousMart::NAME_) return std::shared_ptr<LTR_Algorithm>(new forests::ObliviousMart(model));
+  if (type == forests::ObliviousLambdaMart::NAME_)
+    return std::shared_ptr<LTR_Algorithm>(new forests::ObliviousLambdaMart(model));
+  return nullptr;
+}
+
+}  // namespace learning
+}  // namespace quickrank

@@ -102,6 +102,14 @@ int qr_ctx_create(const float *feat_colmajor, size_t N, size_t F, const float *l
 int qr_ctx_create_rowmajor(const float *feat_rowmajor, size_t N, size_t F, const float *labels,
                            const uint64_t *qoffsets, size_t Q, const qr_params *params,
                            qr_ctx **out);
+/* Evaluation-only context for a second dataset (validation / test set): its documents are binned
+ * with the THRESHOLDS OF `train`, so that qr_apply_tree walks the same splits the float test
+ * `x <= threshold` would (SURVEY.md section 7.1 "Bins").  Replaces scores_on_validation_ together with
+ * Mart::update_modelscores(Dataset...) (mart.cc:447-457) and Metric::evaluate_dataset(Dataset...)
+ * (metric.h:77-91) of the validation branch of Mart::learn (mart.cc:354-359): use qr_apply_tree,
+ * qr_evaluate, qr_get_scores / qr_set_scores on it.  Row-major features. */
+int qr_ctx_create_eval(qr_ctx *train, const float *feat_rowmajor, size_t N, size_t F, const float *labels,
+                       const uint64_t *qoffsets, size_t Q, qr_ctx **out);
 /* Replaces Mart::clear (mart.cc:178-206). */
 int qr_ctx_destroy(qr_ctx *ctx);
 

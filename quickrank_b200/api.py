@@ -69,6 +69,7 @@ def lib():
         L.qr_device_count.restype = C.c_int
         for name in ("qr_ctx_create", "qr_ctx_create_rowmajor"):
             getattr(L, name).argtypes = [fp, sz, sz, fp, u64p, sz, C.POINTER(Params), C.POINTER(vp)]
+        L.qr_ctx_create_eval.argtypes = [vp, fp, sz, sz, fp, u64p, sz, C.POINTER(vp)]
         L.qr_ctx_destroy.argtypes = [vp]
         L.qr_get_thresholds.argtypes = [vp, sz, C.POINTER(fp), C.POINTER(sz)]
         L.qr_compute_pseudoresponses.argtypes = [vp]
@@ -183,6 +184,20 @@ class Trainer:
         fn = L.qr_ctx_create_rowmajor if layout == "rowmajor" else L.qr_ctx_create
         _check(fn(_p(x, C.c_float), self.N, self.F, _p(self.labels, C.c_float),
                   _p(self.qoff, C.c_uint64), self.Q, C.byref(p), C.byref(self.h)))
+
+    def eval_context(self, x, labels, qoff):
+        """Validation / test set binned with this trainer's thresholds (qr_ctx_create_eval)."""
+        ev = Trainer.__new__(Trainer)
+        ev.labels = np.ascontiguousarray(labels, np.float32)
+        ev.qoff = np.ascontiguousarray(qoff, np.uint64)
+        x = np.ascontiguousarray(x, np.float32)
+        ev.N, ev.F = x.shape
+        ev.Q = len(ev.qoff) - 1
+        ev.params, ev.shrinkage, ev.max_nodes = self.params, self.shrinkage, self.max_nodes
+        ev.h = C.c_void_p()
+        _check(lib().qr_ctx_create_eval(self.h, _p(x, C.c_float), ev.N, ev.F, _p(ev.labels, C.c_float),
+                                        _p(ev.qoff, C.c_uint64), ev.Q, C.byref(ev.h)))
+        return ev
 
     def close(self):
         if self.h:

@@ -72,6 +72,7 @@ struct qr_ctx {
   size_t N = 0, F = 0, Q = 0;
   size_t cutoff = 0;             // SIZE_MAX when "no cutoff"
   bool lambda = false, oblivious = false, exact = false;
+  bool eval_only = false;        // validation / test set binned with another context's thresholds
   cudaStream_t stream = nullptr;
 
   // binning (host copies for XML / split thresholds)

@@ -74,9 +74,29 @@ static int ceil_log2(size_t n) {
 // ------------------------------------------------------------------------------------------
 // Init: thresholds + bin map
 // ------------------------------------------------------------------------------------------
-static int build_binning(qr_ctx *c, const float *d_col) {
+static int finish_binning(qr_ctx *c, const float *d_col, uint32_t max_bin);
+
+static int build_binning(qr_ctx *c, const float *d_col, const qr_ctx *thr_from) {
   const size_t N = c->N, F = c->F;
   cudaStream_t st = c->stream;
+  if (thr_from) {   // evaluation context: reuse the training thresholds, only the bin map is new
+    c->thr = thr_from->thr;
+    uint32_t max_bin = 0;
+    for (size_t f = 0; f < F; ++f) max_bin = std::max<uint32_t>(max_bin, (uint32_t) c->thr[f].size() - 1);
+    int *d_bad = nullptr;
+    QR_TRY(dev_alloc(&d_bad, 1));
+    QR_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    uint32_t *d_scratch = nullptr;
+    QR_TRY(dev_alloc(&d_scratch, N));
+    for (size_t f = 0; f < F; ++f)
+      flip_keys_kernel<<<(unsigned) ((N + 255) / 256), 256, 0, st>>>(d_col + f * N, d_scratch, N, d_bad);
+    int bad = 0;
+    QR_CUDA(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(d_bad);
+    cudaFree(d_scratch);
+    if (bad) { set_error("feature matrix contains NaN or infinite values"); return QR_EINVAL; }
+    return finish_binning(c, d_col, max_bin);
+  }
   uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
   float *d_vals = nullptr, *d_uniq = nullptr;
   uint8_t *d_flags = nullptr;
@@ -202,6 +222,13 @@ static int build_binning(qr_ctx *c, const float *d_col) {
       max_bin = std::max<uint32_t>(max_bin, (uint32_t) nth);
     }
   }
+  return finish_binning(c, d_col, max_bin);
+}
+
+// phase D: bin width, cell layout, device copies of the thresholds, the panel matrix
+static int finish_binning(qr_ctx *c, const float *d_col, uint32_t max_bin) {
+  const size_t N = c->N, F = c->F;
+  cudaStream_t st = c->stream;
   if (max_bin > 65535u) {
     set_error("a feature has %u occupied bins; this build stores bins in at most 16 bits "
               "(use --num-thresholds)", max_bin + 1);
@@ -246,7 +273,8 @@ static int init_root_counts(qr_ctx *c);
 
 static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t F, const float *labels,
                              const uint64_t *qoffsets, size_t Q, const qr_params *params,
-                             const unsigned char *comm_id, int rank, int world, qr_ctx **out) {
+                             const unsigned char *comm_id, int rank, int world, const qr_ctx *thr_from,
+                             qr_ctx **out) {
   if (!feat || !labels || !qoffsets || !params || !out || N == 0 || F == 0 || Q == 0) {
     set_error("qr_ctx_create: null or empty argument");
     return QR_EINVAL;
@@ -312,7 +340,8 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   } else {
     QR_CUDA(cudaMemcpyAsync(d_col, feat, N * F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
-  int rc = build_binning(c, d_col);
+  c->eval_only = thr_from != nullptr;
+  int rc = build_binning(c, d_col, thr_from);
   cudaFree(d_col);
   if (rc != QR_OK) return rc;
 
@@ -376,6 +405,11 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
 
   const size_t maxleaves = c->oblivious ? ((size_t) 1 << params->treedepth) : std::max<size_t>(params->nleaves, 1);
   c->max_tasks = (uint32_t) maxleaves + 1;
+  if (c->eval_only) {   // no tree growth on this context: no histogram pool
+    QR_TRY(dev_alloc(&c->d_leafval, maxleaves + 1));
+    QR_CUDA(cudaGetLastError());
+    return QR_OK;
+  }
   // every expansion holds two child histograms until the node is popped or the tree is finished;
   // speculative expansions (qr_tree_host.cuh) can double the number of live nodes
   c->nslots = (int) (4 * maxleaves + 8);
@@ -525,7 +559,7 @@ int qr_device_count(void) {
 int qr_ctx_create(const float *feat, size_t N, size_t F, const float *labels, const uint64_t *qoff,
                   size_t Q, const qr_params *params, qr_ctx **out) {
   if (out) *out = nullptr;
-  int rc = ctx_create_common(feat, false, N, F, labels, qoff, Q, params, nullptr, 0, 1, out);
+  int rc = ctx_create_common(feat, false, N, F, labels, qoff, Q, params, nullptr, 0, 1, nullptr, out);
   if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
   return rc;
 }
@@ -533,7 +567,7 @@ int qr_ctx_create(const float *feat, size_t N, size_t F, const float *labels, co
 int qr_ctx_create_rowmajor(const float *feat, size_t N, size_t F, const float *labels,
                            const uint64_t *qoff, size_t Q, const qr_params *params, qr_ctx **out) {
   if (out) *out = nullptr;
-  int rc = ctx_create_common(feat, true, N, F, labels, qoff, Q, params, nullptr, 0, 1, out);
+  int rc = ctx_create_common(feat, true, N, F, labels, qoff, Q, params, nullptr, 0, 1, nullptr, out);
   if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
   return rc;
 }
@@ -543,7 +577,19 @@ int qr_ctx_create_sharded(const float *feat, int rowmajor, size_t N, size_t F, c
                           const unsigned char id[QR_COMM_ID_BYTES], int rank, int world, qr_ctx **out) {
   if (out) *out = nullptr;
   if (!id) { set_error("qr_ctx_create_sharded: null communicator id"); return QR_EINVAL; }
-  int rc = ctx_create_common(feat, rowmajor != 0, N, F, labels, qoff, Q, params, id, rank, world, out);
+  int rc = ctx_create_common(feat, rowmajor != 0, N, F, labels, qoff, Q, params, id, rank, world, nullptr, out);
+  if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
+  return rc;
+}
+
+int qr_ctx_create_eval(qr_ctx *train, const float *feat_rowmajor, size_t N, size_t F, const float *labels,
+                       const uint64_t *qoff, size_t Q, qr_ctx **out) {
+  if (out) *out = nullptr;
+  if (!train) { set_error("qr_ctx_create_eval: null training context"); return QR_EINVAL; }
+  if (F != train->F) { set_error("dataset has %zu features, the training set has %zu", F, train->F); return QR_EINVAL; }
+  qr_params p = train->p;
+  p.device = train->device;
+  int rc = ctx_create_common(feat_rowmajor, true, N, F, labels, qoff, Q, &p, nullptr, 0, 1, train, out);
   if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
   return rc;
 }
@@ -590,13 +636,20 @@ int qr_get_thresholds(qr_ctx *c, size_t f, const float **thr, size_t *n) {
   return QR_OK;
 }
 
+#define QR_CHECK_TRAINABLE(c)                                                                        \
+  do {                                                                                              \
+    if ((c)->eval_only) { set_error("this is an evaluation-only context (qr_ctx_create_eval)"); return QR_EINVAL; } \
+  } while (0)
+
 int qr_compute_pseudoresponses(qr_ctx *c) {
   QR_CHECK_CTX(c);
+  QR_CHECK_TRAINABLE(c);
   return compute_pseudo(c);
 }
 
 int qr_fit_tree(qr_ctx *c, qr_flat_tree *out) {
   QR_CHECK_CTX(c);
+  QR_CHECK_TRAINABLE(c);
   return fit_tree(c, out);
 }
 
@@ -641,6 +694,7 @@ int qr_evaluate(qr_ctx *c, double *metric) {
 
 int qr_boost_iteration(qr_ctx *c, qr_flat_tree *tree, double *metric) {
   QR_CHECK_CTX(c);
+  QR_CHECK_TRAINABLE(c);
   QR_TRY(compute_pseudo(c));                       // mart.cc:331
   QR_TRY(fit_tree(c, tree));                       // mart.cc:335-339
   QR_TRY(update_modelscores(c, c->p.shrinkage));   // mart.cc:342-345

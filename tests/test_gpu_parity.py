@@ -306,6 +306,25 @@ def test_scoring_a_trained_model():
     assert rel_err(got, train_scores) <= 1e-12
 
 
+def test_validation_context_uses_training_thresholds():
+    """qr_ctx_create_eval: a second dataset binned with the training thresholds; applying a tree to it
+    equals walking the float features (the validation branch of Mart::learn, mart.cc:354-359)."""
+    x, l, off = common.dataset(n=3000, f=12, q=30, seed=3)
+    xv, lv, offv = common.dataset(n=1700, f=12, q=17, seed=4, gridded=False)   # values outside the training grid
+    with api.Trainer(x, l, off, nleaves=12) as tr:
+        ev = tr.eval_context(xv, lv, offv)
+        want = np.zeros(len(lv))
+        for _ in range(4):
+            tree, _m = tr.boost_iteration()
+            ev.apply_tree(tree, 0.1)
+            want = po.update_scores(tree, np.ascontiguousarray(xv.T), 0.1, want)
+            assert np.array_equal(ev.get_scores(), want)
+            assert abs(ev.evaluate_dataset() - po.ndcg_dataset(lv, want, offv, 10)) <= 1e-12
+        with pytest.raises(api.QrError):
+            ev.boost_iteration()
+        ev.close()
+
+
 def test_errors_are_reported():
     x, l, off = common.dataset(n=500, f=4, q=5)
     bad = x.copy()
