@@ -129,11 +129,13 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
 }
 
 // documents per histogram slice so that a round's grid is one full wave: four blocks of the
-// histogram kernel fit on an SM (shared-memory limit), 148 SMs
+// histogram kernel fit on an SM (shared-memory limit), 148 SMs.  Small rounds get small slices: the
+// kernel needs ~32 resident warps per SM to hide the latency of its returning shared atomics, and a
+// round of a few ten-thousand documents in 4096-document slices would leave most SMs with one block.
 static uint32_t pick_hist_dpb(const qr_ctx *c, uint64_t total_docs) {
   const uint32_t want_slices = std::max<uint32_t>(1, (148u * 4u) / c->npanels);
-  uint64_t dpb = std::max<uint64_t>(4096u, (total_docs + want_slices - 1) / want_slices);
-  dpb = (dpb + 511u) & ~(uint64_t) 511u;
+  uint64_t dpb = std::max<uint64_t>(512u, (total_docs + want_slices - 1) / want_slices);
+  dpb = (dpb + 255u) & ~(uint64_t) 255u;
   return (uint32_t) std::min<uint64_t>(dpb, 1u << 20);
 }
 

@@ -202,26 +202,38 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
     flags |= (left ? 1u : 0u) << r;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
+    // warp-wide decoupled look-back: 32 predecessors of the same task per step
     uint32_t total = 0;
-    for (int r = 0; r < 8; ++r)
-      for (int w = 0; w < 8; ++w) total += wc[r][w];
+    for (int i = (int) lane; i < 64; i += 32) total += wc[i >> 3][i & 7];
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     volatile unsigned long long *st = status;
     const unsigned long long ep = (unsigned long long) epoch << 32;
     uint32_t prefix = 0;
     if (lb == 0) {
-      st[vb] = ep | (2ull << 30) | total;
+      if (lane == 0) st[vb] = ep | (2ull << 30) | total;
     } else {
-      st[vb] = ep | (1ull << 30) | total;
-      for (uint32_t j = vb - 1;; --j) {
-        unsigned long long v;
-        do { v = st[j]; } while ((v >> 32) != epoch || ((v >> 30) & 3ull) == 0ull);
-        prefix += (uint32_t) (v & 0x3fffffffull);
-        if (((v >> 30) & 3ull) == 2ull || j == t.part_blk0) break;
+      if (lane == 0) st[vb] = ep | (1ull << 30) | total;
+      int hi = (int) vb - 1;                       // newest predecessor not yet accounted for
+      const int first = (int) t.part_blk0;
+      for (;;) {
+        const int j = hi - (int) lane;
+        unsigned long long v = 0;
+        const bool in = j >= first;
+        if (in) {
+          do { v = st[j]; } while ((v >> 32) != epoch || ((v >> 30) & 3ull) == 0ull);
+        }
+        const uint32_t incl = __ballot_sync(0xffffffffu, in && ((v >> 30) & 3ull) == 2ull);
+        const int stop = incl ? __ffs(incl) - 1 : 32;   // first lane (closest predecessor) with an inclusive prefix
+        uint32_t part = (in && (int) lane <= stop) ? (uint32_t) (v & 0x3fffffffull) : 0u;
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        prefix += part;
+        if (incl || hi - 32 < first) break;
+        hi -= 32;
       }
-      st[vb] = ep | (2ull << 30) | (prefix + total);
+      if (lane == 0) st[vb] = ep | (2ull << 30) | (prefix + total);
     }
-    s_prefix = prefix;
+    if (lane == 0) s_prefix = prefix;
   }
   __syncthreads();
   uint32_t run = s_prefix;

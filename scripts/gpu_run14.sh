@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+tail -4 gpurun_out/pytest_gpu.log
+timeout 600 python scripts/probe.py --trees 10 --settle 40 > gpurun_out/probe_fast.log 2>&1; tail -9 gpurun_out/probe_fast.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --settle 40 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+python scripts/summarize_launches.py gpurun_out/launches.csv | head -12
