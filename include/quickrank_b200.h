@@ -196,6 +196,11 @@ int qr_score_dataset_device(qr_scorer *s, const float *docs_rowmajor_device, siz
                             double *scores_device);
 /* Waits for the scorer's stream (qr_score_dataset_device is asynchronous). */
 int qr_scorer_sync(qr_scorer *s);
+/* kernel launches issued by this scorer so far */
+uint64_t qr_scorer_launch_count(qr_scorer *s);
+/* CUDA-event stopwatch on the scorer's stream: stop == 0 records the start event, stop != 0 records
+ * the end event, synchronises and returns the elapsed device time in milliseconds */
+int qr_scorer_timer(qr_scorer *s, int stop, double *ms);
 /* Replaces `double ranker(float *v)` (src/scoring/ranker.cc:23-25, called by quickscore.cc:103). */
 int qr_score_document(qr_scorer *s, const float *doc, size_t F, double *score);
 

@@ -101,6 +101,9 @@ def lib():
         L.qr_score_dataset.argtypes = [vp, fp, sz, sz, dp]
         L.qr_score_dataset_device.argtypes = [vp, vp, sz, sz, vp]
         L.qr_scorer_sync.argtypes = [vp]
+        L.qr_scorer_launch_count.restype = C.c_uint64
+        L.qr_scorer_launch_count.argtypes = [vp]
+        L.qr_scorer_timer.argtypes = [vp, C.c_int, dp]
         L.qr_score_document.argtypes = [vp, fp, sz, dp]
         _lib = L
     return _lib
@@ -363,6 +366,17 @@ class Scorer:
 
     def sync(self):
         _check(lib().qr_scorer_sync(self.h))
+
+    def launch_count(self):
+        return int(lib().qr_scorer_launch_count(self.h))
+
+    def timer_start(self):
+        _check(lib().qr_scorer_timer(self.h, 0, None))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        _check(lib().qr_scorer_timer(self.h, 1, C.byref(ms)))
+        return ms.value
 
     def score_document(self, d):
         d = np.ascontiguousarray(d, np.float32)

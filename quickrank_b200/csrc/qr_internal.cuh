@@ -125,7 +125,10 @@ struct qr_ctx {
   uint32_t *d_fbest_lc = nullptr;           // [max_tasks][2][F] left count at each feature's best split
   ulonglong2 *d_totals = nullptr;           // [max_tasks][2] (node size, node sum bits)
   qr::SplitResult *d_res = nullptr;         // [max_tasks][2]
-  qr::SplitResult *h_res = nullptr;         // pinned
+  qr::SplitResult *h_res = nullptr;         // pinned + mapped: finalize_kernel writes it directly
+  qr::SplitResult *d_res_mapped = nullptr;  // device view of h_res
+  uint32_t *h_flags = nullptr, *d_flags_mapped = nullptr;   // [max_tasks] per-task "result published" round ids
+  uint32_t round_id = 0;
   qr::LeafSeg *d_segs = nullptr, *h_segs = nullptr;      // [maxleaves]
   double2 *d_leaf_partials = nullptr;       // [N / kLeafItems + maxleaves]
   double2 *d_leafsum = nullptr;             // [maxleaves] (sum lambda, sum weight)

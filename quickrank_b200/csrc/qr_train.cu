@@ -4,6 +4,7 @@
 // the max-heap of frontier nodes keyed by deviance (maxheap.h:31-106) and the node bookkeeping.
 // All per-document and per-bin work runs in the kernels of qr_kernels.cuh.
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -444,7 +445,11 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_fbest_lc, mt * 2 * F));
   QR_TRY(dev_alloc(&c->d_totals, mt * 2));
   QR_TRY(dev_alloc(&c->d_res, mt * 2));
-  QR_CUDA(cudaMallocHost((void **) &c->h_res, mt * 2 * sizeof(SplitResult)));
+  QR_CUDA(cudaHostAlloc((void **) &c->h_res, mt * 2 * sizeof(SplitResult), cudaHostAllocMapped));
+  QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_res_mapped, c->h_res, 0));
+  QR_CUDA(cudaHostAlloc((void **) &c->h_flags, mt * sizeof(uint32_t), cudaHostAllocMapped));
+  QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_flags_mapped, c->h_flags, 0));
+  memset(c->h_flags, 0, mt * sizeof(uint32_t));
   QR_TRY(dev_alloc(&c->d_segs, maxleaves + 1));
   QR_CUDA(cudaMallocHost((void **) &c->h_segs, (maxleaves + 1) * sizeof(LeafSeg)));
   QR_TRY(dev_alloc(&c->d_leaf_partials, (N + kLeafItems - 1) / kLeafItems + maxleaves + 1));
@@ -610,6 +615,7 @@ int qr_ctx_destroy(qr_ctx *c) {
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);
   if (c->h_tasks) cudaFreeHost(c->h_tasks);
+  if (c->h_flags) cudaFreeHost(c->h_flags);
   if (c->h_lcount) cudaFreeHost(c->h_lcount);
   if (c->h_segs) cudaFreeHost(c->h_segs);
   if (c->h_obv_lcounts) cudaFreeHost(c->h_obv_lcounts);

@@ -113,17 +113,42 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
   }
   {
     PhaseTimer pt(c, PH_SCAN);
+    // results are written straight into mapped pinned host memory and announced through per-task
+    // flags the host polls: no device-to-host copy and no stream synchronisation on the round path
+    c->round_id++;
     if (c->exact)
       QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3((F + kFinFeat - 1) / kFinFeat, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
                 c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
-                c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res);
+                c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
+                c->d_flags_mapped, c->round_id);
     else
       QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3((F + kFinFeat - 1) / kFinFeat, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
                 c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
-                c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res);
-    QR_CUDA(cudaMemcpyAsync(c->h_res, c->d_res, (size_t) 2 * k * sizeof(SplitResult), cudaMemcpyDeviceToHost, c->stream));
-    if (c->comm) QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    QR_CUDA(cudaStreamSynchronize(c->stream));
+                c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
+                c->d_flags_mapped, c->round_id);
+    if (c->comm) {
+      QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      QR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    // wait for the k flags (bounded spin; a launch failure surfaces through cudaStreamQuery)
+    volatile uint32_t *flags = c->h_flags;
+    uint64_t spins = 0;
+    for (uint32_t j = 0; j < k; ++j) {
+      while (flags[j] != c->round_id) {
+        if ((++spins & 0xfffff) == 0) {
+          cudaError_t e = cudaStreamQuery(c->stream);
+          if (e != cudaSuccess && e != cudaErrorNotReady) {
+            set_error("finalize failed: %s", cudaGetErrorString(e));
+            return QR_ECUDA;
+          }
+          if (e == cudaSuccess && flags[j] != c->round_id) {
+            set_error("internal: finalize finished without publishing task %u", j);
+            return QR_ECUDA;
+          }
+        }
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
   }
   return QR_OK;
 }

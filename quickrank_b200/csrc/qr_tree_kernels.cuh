@@ -569,7 +569,8 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
                 uint32_t ncells, const uint32_t *__restrict__ thr_off, uint32_t F, uint32_t minls,
                 const int *__restrict__ qexp, double *fbest_score, uint32_t *fbest_t, uint32_t *fbest_lc,
                 ulonglong2 *totals, const ulonglong2 *__restrict__ sq128,
-                const double *__restrict__ sq_exact, uint32_t *task_done, SplitResult *res) {
+                const double *__restrict__ sq_exact, uint32_t *task_done, SplitResult *res,
+                volatile uint32_t *host_flags, uint32_t round_id) {
   const uint32_t task = blockIdx.y;
   const NodeTask t = tasks[task];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -809,7 +810,13 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
       r.lcount = r.valid ? blc : 0;
       r.pad = 0;
       res[(size_t) task * 2 + child] = r;
-      if (child == nchild - 1) task_done[task] = 0u;   // ready for the next round
+      if (child == nchild - 1) {
+        task_done[task] = 0u;   // ready for the next round
+        if (host_flags) {       // res lives in mapped host memory: publish it to the polling host thread
+          __threadfence_system();
+          host_flags[task] = round_id;
+        }
+      }
     }
     __syncthreads();
   }
