@@ -353,9 +353,13 @@ class Scorer:
     def __exit__(self, *a):
         self.close()
 
-    def score_dataset(self, x):
+    def score_dataset(self, x, out=None):
+        """Row-major host documents -> scores (LTR_Algorithm::score_dataset).  `out` may be a
+        caller-owned float64 array (e.g. page-locked) to receive the scores."""
         x = np.ascontiguousarray(x, np.float32)
-        out = np.empty(x.shape[0], np.float64)
+        if out is None:
+            out = np.empty(x.shape[0], np.float64)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.shape[0] == x.shape[0]
         _check(lib().qr_score_dataset(self.h, _p(x, C.c_float), x.shape[0], x.shape[1],
                                       _p(out, C.c_double)))
         return out

@@ -12,9 +12,11 @@
 // (one byte when a feature has <= 255 distinct thresholds, two otherwise): then
 //     x <= threshold_k   <=>   code(x) <= k        (k = rank of the threshold in the sorted list)
 // exactly, NaN included (code = list size, never <= k: the reference's `<=` is false for NaN).
-// A 700-feature document shrinks from 2.8 KB of floats to 700 bytes, so a tile of 256 documents
-// lives in shared memory next to a chunk of the ensemble; every thread owns one document, walks
-// kIlp trees at a time (independent dependent-load chains) and adds their leaves in tree order.
+// A 700-feature document shrinks from 2.8 KB of floats to 700 bytes, so a tile of documents lives in
+// shared memory next to two buffers of ensemble chunks (bulk asynchronous copies, one being
+// walked while the next arrives); 1, 2 or 4 threads share a document, each walking its own trees of
+// the chunk, and add the weighted leaves in tree order.  The walk is bound by shared-memory
+// wavefronts (one 8-byte node + one code per level, both at data-dependent addresses), not by HBM.
 #include <algorithm>
 #include <cstring>
 #include <map>
@@ -24,26 +26,28 @@
 
 namespace qr {
 
-// 8-byte node: internal {slot, code, left, right} (children relative to the tree's first node);
-// leaf {0xFFFF, 0, leaf index (relative to the tree's first leaf), 0}
+// 8-byte internal node.  Leaves are not nodes: a child reference with bit 0 set IS the leaf.
+//   lo = (threshold rank << 16) | slot          so that  code <= rank  <=>  (code << 16) <= lo
+//   hi = left | (right << 16), each a child reference:
+//        bit 0 clear: byte offset of the child node from the chunk's first node (a multiple of 8)
+//        bit 0 set  : (index of the leaf's weight*output product in the chunk's table) << 1 | 1
 struct __align__(8) CodeNode {
-  uint16_t slot, code, left, right;
+  uint32_t lo, hi;
 };
 
-constexpr int kTpd = 4;                 // threads per document: each walks every kTpd-th tree of a chunk
-constexpr int kChunkTrees = 16;         // trees per chunk (<= kTpd * kWalks)
-constexpr int kWalks = kChunkTrees / kTpd;   // concurrent walks per thread (independent load chains)
-constexpr int kMaxDocs = 256;           // documents per block (kMaxDocs * kTpd = 1024 threads)
+constexpr int kChunkTrees = 16;         // tree slots per chunk (unused slots hold a leaf-only tree worth +0.0)
+constexpr uint32_t kMaxChunkNodes = 8191, kMaxChunkLeaves = 32767;
 
 // One chunk of the ensemble as a single contiguous blob, fetched with ONE bulk asynchronous copy
-// (cp.async.bulk -> UBLKCP) into one of two shared-memory buffers while the other is being walked.
+// (cp.async.bulk -> UBLKCP) into one of two shared-memory buffers while the other is being walked:
+//   [ChunkHeader | CodeNode nodes[] | double product[]]      product[0] = +0.0 (unused tree slots)
+// product[] holds weight_t * leaf output, rounded once exactly as `leaf * weight` is in
+// ensemble.cc:116 (the reference build does not fuse that multiply into the sum).
 struct ChunkHeader {
-  uint32_t ntrees, nodes_off, leaves_off, pad;      // byte offsets inside the blob
-  uint16_t node_first[kChunkTrees + 1];             // first node of each tree (index into the blob's nodes)
-  uint16_t leaf_first[kChunkTrees + 1];             // first leaf of each tree
-  uint32_t pad2[3];
-  double weight[kChunkTrees];
+  uint32_t prod_off, pad[3];            // byte offset of product[] inside the blob
+  uint16_t root[kChunkTrees];           // child reference of each tree's root
 };
+constexpr uint32_t kNodesOff = sizeof(ChunkHeader);
 static_assert(sizeof(ChunkHeader) % 16 == 0, "chunk header must keep 16-byte alignment");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -72,39 +76,107 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
 }
 
-// code(x) for every (document, used feature): binary search in the feature's sorted thresholds
+// code(x) for every (document, used feature): binary search in the feature's sorted thresholds.
+// A block re-codes a tile of kEncDocs documents.  Rows are fetched coalesced into shared memory;
+// then every warp takes one feature at a time with lane = document, so that the 32 searches of a
+// warp walk the SAME threshold list (a handful of L1 lines per step instead of 32 scattered ones);
+// the codes go back through shared memory so that the global rows are written coalesced.
+constexpr int kEncDocs = 32, kEncSlots = 512, kEncThreads = 512;
+// shared-memory rows hold `cols` = min(nslots, kEncSlots) entries, padded to an odd number of words
+__host__ __device__ inline uint32_t enc_x_words(uint32_t cols) { return cols | 1u; }
+__host__ __device__ inline uint32_t enc_code_words(uint32_t cols, uint32_t code_bytes) { return ((cols * code_bytes + 3u) / 4u) | 1u; }
+
 template <typename CodeT>
-__global__ void encode_kernel(const float *__restrict__ docs, size_t n0, size_t n, size_t F,
-                              const uint32_t *__restrict__ slot_feature, const uint32_t *__restrict__ thr_off,
-                              const float *__restrict__ thr, uint32_t nslots, uint32_t stride, CodeT *codes) {
-  const size_t idx = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * nslots) return;
-  const size_t d = idx / nslots;
-  const uint32_t s = (uint32_t) (idx % nslots);
-  const float x = docs[(n0 + d) * F + slot_feature[s]];
-  const float *t = thr + thr_off[s];
-  uint32_t lo = 0, hi = thr_off[s + 1] - thr_off[s];   // first k with t[k] >= x  ==  #thresholds < x
-  while (lo < hi) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (t[mid] >= x) hi = mid; else lo = mid + 1;
+__global__ void __launch_bounds__(kEncThreads)
+encode_kernel(const float *__restrict__ docs, size_t n0, size_t n, size_t F, const uint32_t *__restrict__ slot_feature,
+              const uint32_t *__restrict__ thr_off, const float *__restrict__ thr, uint32_t nslots, uint32_t stride,
+              CodeT *__restrict__ codes) {
+  extern __shared__ __align__(16) unsigned char enc_raw[];
+  const uint32_t cols = min(nslots, (uint32_t) kEncSlots);
+  const uint32_t xw = enc_x_words(cols), cw = enc_code_words(cols, (uint32_t) sizeof(CodeT));
+  float *xs = reinterpret_cast<float *>(enc_raw);                     // [kEncDocs][xw]
+  uint32_t *cs = reinterpret_cast<uint32_t *>(enc_raw) + kEncDocs * xw;   // [kEncDocs][cw] words of packed codes
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = kEncThreads / 32;
+  const size_t d0 = (size_t) blockIdx.x * kEncDocs;
+  const uint32_t nd = (uint32_t) min((size_t) kEncDocs, n - d0);
+  for (uint32_t c0 = 0; c0 < nslots; c0 += kEncSlots) {
+    const uint32_t cn = min((uint32_t) kEncSlots, nslots - c0);
+    for (uint32_t r = warp; r < nd; r += nwarps) {
+      const float *row = docs + (n0 + d0 + r) * F;
+      for (uint32_t j = lane; j < cn; j += 32u) xs[r * xw + j] = row[slot_feature[c0 + j]];
+    }
+    __syncthreads();
+    for (uint32_t j = warp; j < cn; j += nwarps) {
+      const uint32_t t0 = thr_off[c0 + j], len = thr_off[c0 + j + 1] - t0;
+      const float *t = thr + t0;
+      if (lane < nd) {
+        const float x = xs[lane * xw + j];
+        // number of thresholds < x (all of them for NaN: the reference's `x <= t` is then false everywhere)
+        uint32_t pos = 0;
+        for (uint32_t step = len ? 1u << (31 - __clz(len)) : 0u; step; step >>= 1) {
+          const uint32_t np = pos + step;
+          if (np <= len && !(t[np - 1] >= x)) pos = np;
+        }
+        reinterpret_cast<CodeT *>(cs + lane * cw)[j] = (CodeT) pos;
+      }
+    }
+    __syncthreads();
+    const uint32_t words = (cn * (uint32_t) sizeof(CodeT) + 3u) / 4u;
+    for (uint32_t r = warp; r < nd; r += nwarps) {
+      const uint32_t *src = cs + r * cw;
+      uint32_t *dst = reinterpret_cast<uint32_t *>(codes + (d0 + r) * stride + c0);
+      for (uint32_t wd = lane; wd < words; wd += 32u) dst[wd] = src[wd];
+    }
+    __syncthreads();
   }
-  codes[d * stride + s] = (CodeT) lo;
 }
 
-// TILE: the block's documents are staged in shared memory (rows padded to an odd number of 32-bit
-// words so that the lanes of a warp, which read different documents, hit different banks).
-template <typename CodeT, bool TILE>
-__global__ void __launch_bounds__(kMaxDocs * kTpd)
+__device__ __forceinline__ uint2 lds_u64(uint32_t a) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+template <typename CodeT> __device__ __forceinline__ uint32_t lds_code(uint32_t row, uint32_t slot);
+template <> __device__ __forceinline__ uint32_t lds_code<uint8_t>(uint32_t row, uint32_t slot) { return lds_u8(row + slot); }
+template <> __device__ __forceinline__ uint32_t lds_code<uint16_t>(uint32_t row, uint32_t slot) { return lds_u16(row + 2u * slot); }
+
+// TPD threads share a document and walk every TPD-th tree of a chunk.  TILE: the block's documents
+// are staged in shared memory (rows padded to an odd number of 32-bit words so that the lanes of a
+// warp, which read different documents, hit different banks); otherwise the codes are read from
+// global memory.
+template <typename CodeT, int TPD, bool TILE>
+__global__ void __launch_bounds__(1024)
 score_codes_kernel(const CodeT *__restrict__ codes, size_t n, uint32_t stride, uint32_t tile_words,
                    const unsigned char *__restrict__ chunks, uint32_t chunk_bytes, uint32_t nchunks,
                    uint32_t docs_per_block, double *__restrict__ scores) {
+  static_assert(kChunkTrees % TPD == 0, "a chunk is walked in whole groups of TPD trees");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[2];
-  unsigned char *s_buf[2] = {smem_raw, smem_raw + chunk_bytes};
-  uint32_t *s_tile = reinterpret_cast<uint32_t *>(smem_raw + 2 * (size_t) chunk_bytes);
+  const uint32_t s_base = smem_u32(smem_raw);
+  const uint32_t s_tile = s_base + 2u * chunk_bytes;
 
-  const uint32_t sub = threadIdx.x % kTpd;                 // which trees of a chunk this thread walks
-  const uint32_t ldoc = threadIdx.x / kTpd;                // document within the block
+  const uint32_t sub = threadIdx.x % TPD;                  // which trees of a group this thread walks
+  const uint32_t ldoc = threadIdx.x / TPD;                 // document within the block
   const size_t d0 = (size_t) blockIdx.x * docs_per_block;
   const size_t d = d0 + ldoc;
   const uint32_t ndocs = (uint32_t) min((size_t) docs_per_block, n - d0);
@@ -117,21 +189,21 @@ score_codes_kernel(const CodeT *__restrict__ codes, size_t n, uint32_t stride, u
   __syncthreads();
   if (threadIdx.x == 0 && nchunks > 0) {
     mbar_expect_tx(&s_bar[0], chunk_bytes);
-    bulk_copy_g2s(s_buf[0], chunks, chunk_bytes, &s_bar[0]);
+    bulk_copy_g2s(smem_raw, chunks, chunk_bytes, &s_bar[0]);
   }
-  const CodeT *my;
+  // rows past the end of the dataset walk document d0 and are not stored
+  const uint32_t row = ldoc < ndocs ? ldoc : 0u;
+  const uint32_t my = s_tile + row * tile_words * 4u;
+  const CodeT *myg = codes + (d0 + row) * stride;
   if (TILE) {
     // word-wise copy into rows of tile_words (odd) 32-bit words
     const uint32_t row_words = stride * (uint32_t) sizeof(CodeT) / 4;
     const uint32_t *src = reinterpret_cast<const uint32_t *>(codes + d0 * stride);
-    for (uint32_t i = threadIdx.x; i < ndocs * row_words; i += blockDim.x)
-      s_tile[(i / row_words) * tile_words + (i % row_words)] = src[i];
-    my = reinterpret_cast<const CodeT *>(s_tile + (size_t) ldoc * tile_words);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(smem_raw + 2 * (size_t) chunk_bytes);
+    for (uint32_t r = threadIdx.x / 32u; r < ndocs; r += blockDim.x / 32u)
+      for (uint32_t w = threadIdx.x % 32u; w < row_words; w += 32u) dst[r * tile_words + w] = src[r * row_words + w];
     __syncthreads();
-  } else {
-    my = codes + (d < n ? d : 0) * stride;
   }
-  const bool active = d < n;
   double sum = 0.0;
   for (uint32_t c = 0; c < nchunks; ++c) {
     const uint32_t b = c & 1u;
@@ -140,60 +212,37 @@ score_codes_kernel(const CodeT *__restrict__ codes, size_t n, uint32_t stride, u
     if (threadIdx.x == 0 && c + 1 < nchunks) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       mbar_expect_tx(&s_bar[b ^ 1u], chunk_bytes);
-      bulk_copy_g2s(s_buf[b ^ 1u], chunks + (size_t) (c + 1) * chunk_bytes, chunk_bytes, &s_bar[b ^ 1u]);
+      bulk_copy_g2s(smem_raw + (size_t) (b ^ 1u) * chunk_bytes, chunks + (size_t) (c + 1) * chunk_bytes, chunk_bytes,
+                    &s_bar[b ^ 1u]);
     }
     mbar_wait(&s_bar[b], (c >> 1) & 1u);
-    const ChunkHeader *h = reinterpret_cast<const ChunkHeader *>(s_buf[b]);
-    const CodeNode *nodes = reinterpret_cast<const CodeNode *>(s_buf[b] + h->nodes_off);
-    const double *leaves = reinterpret_cast<const double *>(s_buf[b] + h->leaves_off);
-    const uint32_t nt = h->ntrees;
-    // this thread's walks: trees sub, sub + kTpd, ...
-    double val[kWalks];
-    {
-      uint32_t base[kWalks];
-      CodeNode nd[kWalks];
-      bool live[kWalks];
-#pragma unroll
-      for (int k = 0; k < kWalks; ++k) {
-        const uint32_t t = sub + k * kTpd;
-        live[k] = active && t < nt;
-        base[k] = live[k] ? h->node_first[t] : 0u;
-        nd[k] = nodes[base[k]];
-        if (!live[k]) nd[k].slot = 0xFFFFu;
+    const uint32_t buf = s_base + b * chunk_bytes;
+    const uint32_t nodes = buf + kNodesOff;
+    const uint32_t prod = buf + lds_u32(buf);
+    const uint32_t roots = buf + (uint32_t) offsetof(ChunkHeader, root) + 2u * sub;
+#pragma unroll 1
+    for (uint32_t g = 0; g < (uint32_t) kChunkTrees; g += TPD) {
+      uint32_t cur = lds_u16(roots + 2u * g);
+      while (!(cur & 1u)) {
+        const uint2 nd = lds_u64(nodes + cur);
+        const uint32_t slot = nd.x & 0xFFFFu;
+        const uint32_t code = TILE ? lds_code<CodeT>(my, slot) : (uint32_t) myg[slot];
+        cur = (code << 16) <= nd.x ? (nd.y & 0xFFFFu) : (nd.y >> 16);   // rtnode.h:141-144
       }
-      bool any = true;
-      while (any) {      // the walks advance together; finished ones idle on their leaf
-        any = false;
+      const double val = lds_f64(prod + ((cur & 0xFFFEu) << 2));
+      // ordered accumulation (ensemble.cc:116): the TPD lanes of a document add the group's products in
+      // tree order; each lane performs every addition, so all of them hold the same running sum
+      if (TPD == 1) {
+        sum = __dadd_rn(sum, val);
+      } else {
+        const uint32_t gbase = (threadIdx.x & 31u) & ~(uint32_t) (TPD - 1);
 #pragma unroll
-        for (int k = 0; k < kWalks; ++k) {
-          if (nd[k].slot != 0xFFFFu) {
-            const uint32_t code = my[nd[k].slot];
-            nd[k] = nodes[base[k] + (code <= nd[k].code ? nd[k].left : nd[k].right)];   // rtnode.h:141-144
-            any = true;
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kWalks; ++k) {
-        const uint32_t t = sub + k * kTpd;
-        val[k] = live[k] ? __dmul_rn(leaves[h->leaf_first[t] + nd[k].left], h->weight[t]) : 0.0;   // ensemble.cc:116
-      }
-    }
-    // ordered accumulation: the kTpd lanes of a document add the chunk's products in tree order
-    // (each lane performs every addition, so all of them hold the same running sum)
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gbase = lane & ~(uint32_t) (kTpd - 1);
-#pragma unroll
-    for (int k = 0; k < kWalks; ++k) {
-#pragma unroll
-      for (int j = 0; j < kTpd; ++j) {
-        const double v = __shfl_sync(0xffffffffu, val[k], gbase + j);
-        if ((uint32_t) (k * kTpd + j) < nt) sum = __dadd_rn(sum, v);
+        for (int j = 0; j < TPD; ++j) sum = __dadd_rn(sum, __shfl_sync(0xffffffffu, val, gbase + j));
       }
     }
     __syncthreads();   // every thread is done with buffer b before it is refilled
   }
-  if (active && sub == 0) scores[d] = sum;
+  if (ldoc < ndocs && sub == 0) scores[d] = sum;
 }
 
 }  // namespace qr
@@ -211,9 +260,68 @@ struct qr_scorer {
   size_t batch_docs = 0;
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
+  // qr_score_dataset (host buffers): two staging slices, uploads on their own stream
+  float *d_in[2] = {nullptr, nullptr};
+  double *d_out[2] = {nullptr, nullptr};
+  size_t io_docs = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
 };
 
 using namespace qr;
+
+// shared-memory row length in 32-bit words: the global row, padded to an odd word count
+static uint32_t score_tile_words(const qr_scorer *s) {
+  const uint32_t w = s->stride * (uint32_t) s->code_bytes / 4;
+  return w | 1u;
+}
+
+// Launch shape: TPD threads per document and documents per block.  Narrow rows leave room for many
+// documents per SM, so one or two threads per document already fill the SM with warps; wide rows
+// (hundreds of bytes) need TPD = 4 to reach the same warp count from the few hundred documents
+// that fit.  docs == 0: not even 32 rows fit next to the two chunk buffers, the kernel then reads
+// the codes from global memory.
+struct ScoreShape { int tpd; uint32_t docs; };
+static ScoreShape score_shape(const qr_scorer *s) {
+  const size_t budget = 220 * 1024, fixed = 2 * (size_t) s->chunk_bytes + 1024, row = (size_t) score_tile_words(s) * 4;
+  ScoreShape sh{4, 0};
+  if (budget <= fixed) return sh;
+  const size_t fit = (budget - fixed) / row / 32 * 32;
+  if (fit < 32) return sh;
+  double best = -1;
+  const int tpds[] = {1, 2, 4};
+  for (int tpd : tpds) {
+    for (uint32_t docs = 1024 / tpd; docs >= 32; docs /= 2) {
+      if (docs > fit) continue;
+      // resident warps per SM: blocks limited by shared memory and by 2048 threads
+      const size_t smem = fixed + docs * row;
+      const size_t blocks = std::min<size_t>(std::min<size_t>(227 * 1024 / smem, 2048 / (docs * tpd)), 32);
+      const double warps = (double) blocks * docs * tpd / 32;
+      // more resident warps first; then fewer threads per document (less exchange), bigger blocks
+      const double score = std::min(warps, 64.0) * 1000 - tpd * 10 + docs / 1024.0;
+      if (score > best) { best = score; sh.tpd = tpd; sh.docs = docs; }
+    }
+  }
+  return sh;
+}
+
+template <typename CodeT, int TPD, bool TILE>
+static cudaError_t score_launch(qr_scorer *s, size_t n, uint32_t dpb, uint32_t tile_words, size_t smem, double *scores) {
+  cudaFuncSetAttribute(score_codes_kernel<CodeT, TPD, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  const unsigned sg = (unsigned) ((n + dpb - 1) / dpb);
+  score_codes_kernel<CodeT, TPD, TILE><<<sg, dpb * TPD, smem, s->stream>>>(
+      (const CodeT *) s->d_codes, n, s->stride, tile_words, s->d_chunks, s->chunk_bytes, s->nchunks, dpb, scores);
+  return cudaGetLastError();
+}
+
+template <typename CodeT>
+static cudaError_t score_dispatch(qr_scorer *s, const ScoreShape &sh, size_t n, uint32_t dpb, uint32_t tile_words, size_t smem,
+                                  double *scores) {
+  if (sh.docs == 0) return score_launch<CodeT, 4, false>(s, n, dpb, tile_words, smem, scores);
+  if (sh.tpd == 1) return score_launch<CodeT, 1, true>(s, n, dpb, tile_words, smem, scores);
+  if (sh.tpd == 2) return score_launch<CodeT, 2, true>(s, n, dpb, tile_words, smem, scores);
+  return score_launch<CodeT, 4, true>(s, n, dpb, tile_words, smem, scores);
+}
 
 extern "C" {
 
@@ -263,72 +371,65 @@ int qr_scorer_create(const qr_flat_tree *trees, const double *weights, size_t nt
   }
   if (max_thr > 65535) { set_error("a feature has %zu distinct thresholds; at most 65535 are supported", max_thr); return QR_ELIMIT; }
 
-  // chunk blobs: up to kChunkTrees whole trees each, at most ~16 KB of nodes + leaves (a single
+  // chunk blobs: up to kChunkTrees whole trees each, at most ~16 KB of nodes + products (a single
   // larger tree gets a chunk of its own); every blob is padded to the size of the largest one
-  const size_t soft_payload = std::max<size_t>(16 * 1024, max_tree_nodes * 16);
-  struct Chunk { size_t t0, t1, nodes, leaves; };
+  const size_t soft_payload = std::max<size_t>(16 * 1024, (max_tree_nodes + 1) * 8);
+  struct Chunk { size_t t0, t1, inner, leaves; };
   std::vector<Chunk> plan;
   {
     Chunk cur{0, 0, 0, 0};
     for (size_t t = 0; t < ntrees; ++t) {
       size_t nl = 0;
       for (uint32_t i = 0; i < trees[t].nnodes; ++i) nl += trees[t].feature[i] < 0;
-      const size_t nn = trees[t].nnodes;
-      if (cur.t1 > cur.t0 && (cur.t1 - cur.t0 >= (size_t) kChunkTrees || (cur.nodes + nn) * 8 + (cur.leaves + nl) * 8 > soft_payload ||
-                              cur.nodes + nn > 65535)) {
+      const size_t ni = trees[t].nnodes - nl;
+      if (cur.t1 > cur.t0 && (cur.t1 - cur.t0 >= (size_t) kChunkTrees || (cur.inner + ni + cur.leaves + nl) * 8 > soft_payload ||
+                              cur.inner + ni > kMaxChunkNodes || cur.leaves + nl + 1 > kMaxChunkLeaves)) {
         plan.push_back(cur);
         cur = Chunk{t, t, 0, 0};
       }
       cur.t1 = t + 1;
-      cur.nodes += nn;
+      cur.inner += ni;
       cur.leaves += nl;
     }
     if (cur.t1 > cur.t0) plan.push_back(cur);
   }
-  size_t chunk_bytes = sizeof(ChunkHeader);
-  for (auto &c : plan) chunk_bytes = std::max(chunk_bytes, sizeof(ChunkHeader) + ((c.nodes * 8 + 15) & ~(size_t) 15) + c.leaves * 8);
+  size_t chunk_bytes = sizeof(ChunkHeader) + 8;
+  for (auto &c : plan) chunk_bytes = std::max(chunk_bytes, sizeof(ChunkHeader) + (c.inner + c.leaves + 1) * 8);
   chunk_bytes = (chunk_bytes + 127) & ~(size_t) 127;
   std::vector<unsigned char> blob(plan.size() * chunk_bytes, 0);
   for (size_t ci = 0; ci < plan.size(); ++ci) {
     const Chunk &c = plan[ci];
     unsigned char *base = blob.data() + ci * chunk_bytes;
     ChunkHeader *h = reinterpret_cast<ChunkHeader *>(base);
-    h->ntrees = (uint32_t) (c.t1 - c.t0);
-    h->nodes_off = (uint32_t) sizeof(ChunkHeader);
-    h->leaves_off = (uint32_t) (sizeof(ChunkHeader) + ((c.nodes * 8 + 15) & ~(size_t) 15));
-    CodeNode *nodes = reinterpret_cast<CodeNode *>(base + h->nodes_off);
-    double *leaves = reinterpret_cast<double *>(base + h->leaves_off);
-    size_t no = 0, lo = 0;
+    h->prod_off = (uint32_t) (sizeof(ChunkHeader) + c.inner * 8);
+    CodeNode *nodes = reinterpret_cast<CodeNode *>(base + kNodesOff);
+    double *product = reinterpret_cast<double *>(base + h->prod_off);
+    product[0] = 0.0;
+    for (int k = 0; k < kChunkTrees; ++k) h->root[k] = 1;       // unused slot: leaf reference to product[0]
+    size_t no = 0, lo = 1;
     for (size_t t = c.t0; t < c.t1; ++t) {
       const qr_flat_tree &ft = trees[t];
-      const size_t k = t - c.t0;
-      h->node_first[k] = (uint16_t) no;
-      h->leaf_first[k] = (uint16_t) lo;
-      h->weight[k] = weights[t];
-      std::vector<uint32_t> leaf_index(ft.nnodes, 0);
-      uint32_t nl = 0;
-      for (uint32_t i = 0; i < ft.nnodes; ++i)
-        if (ft.feature[i] < 0) leaf_index[i] = nl++;
+      // child reference of every node of this tree
+      std::vector<uint16_t> ref(ft.nnodes);
       for (uint32_t i = 0; i < ft.nnodes; ++i) {
-        CodeNode cn;
-        if (ft.feature[i] >= 0) {
-          const uint32_t sidx = slot_of[(uint32_t) ft.feature[i]];
-          const float *tb = thr_flat.data() + thr_off[sidx], *te = thr_flat.data() + thr_off[sidx + 1];
-          cn.slot = (uint16_t) sidx;
-          cn.code = (uint16_t) (std::lower_bound(tb, te, ft.threshold[i]) - tb);   // rank of this threshold
-          cn.left = (uint16_t) ft.left[i];
-          cn.right = (uint16_t) ft.right[i];
-        } else {
-          cn.slot = 0xFFFFu; cn.code = 0; cn.left = (uint16_t) leaf_index[i]; cn.right = 0;
-          leaves[lo + leaf_index[i]] = ft.value[i];
+        if (ft.feature[i] >= 0) ref[i] = (uint16_t) (8 * no++);
+        else {
+          const volatile double prod = ft.value[i] * weights[t];   // rounded on its own (ensemble.cc:116)
+          product[lo] = prod;
+          ref[i] = (uint16_t) ((lo++ << 1) | 1u);
         }
-        nodes[no + i] = cn;
       }
-      no += ft.nnodes;
-      lo += nl;
+      h->root[t - c.t0] = ref[0];
+      for (uint32_t i = 0; i < ft.nnodes; ++i) {
+        if (ft.feature[i] < 0) continue;
+        const uint32_t sidx = slot_of[(uint32_t) ft.feature[i]];
+        const float *tb = thr_flat.data() + thr_off[sidx], *te = thr_flat.data() + thr_off[sidx + 1];
+        const uint32_t rank = (uint32_t) (std::lower_bound(tb, te, ft.threshold[i]) - tb);   // rank of this threshold
+        CodeNode &cn = nodes[ref[i] / 8];
+        cn.lo = (rank << 16) | sidx;
+        cn.hi = (uint32_t) ref[ft.left[i]] | ((uint32_t) ref[ft.right[i]] << 16);
+      }
     }
-    h->node_first[c.t1 - c.t0] = (uint16_t) no;
-    h->leaf_first[c.t1 - c.t0] = (uint16_t) lo;
   }
 
   qr_scorer *s = new qr_scorer();
@@ -362,26 +463,17 @@ int qr_scorer_destroy(qr_scorer *s) {
   if (!s) return QR_OK;
   cudaSetDevice(s->device);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  void *ptrs[] = {s->d_chunks, s->d_slot_feature, s->d_thr_off, s->d_thr, s->d_codes};
+  if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+  void *ptrs[] = {s->d_chunks, s->d_slot_feature, s->d_thr_off, s->d_thr, s->d_codes, s->d_in[0], s->d_in[1], s->d_out[0], s->d_out[1]};
   for (void *p : ptrs) if (p) cudaFree(p);
+  for (int b = 0; b < 2; ++b) {
+    if (s->ev_in[b]) cudaEventDestroy(s->ev_in[b]);
+    if (s->ev_free[b]) cudaEventDestroy(s->ev_free[b]);
+  }
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
   return QR_OK;
-}
-
-// shared-memory row length in 32-bit words: the global row, padded to an odd word count
-static uint32_t score_tile_words(const qr_scorer *s) {
-  const uint32_t w = s->stride * (uint32_t) s->code_bytes / 4;
-  return w | 1u;
-}
-
-// documents per block: as many (<= kMaxDocs, multiple of 8) as fit next to the two chunk buffers;
-// 0 = not even 32 documents fit, the kernel then reads the codes from global memory
-static uint32_t score_docs_per_block(const qr_scorer *s) {
-  const size_t budget = 220 * 1024, fixed = 2 * (size_t) s->chunk_bytes, row = (size_t) score_tile_words(s) * 4;
-  if (budget <= fixed) return 0;
-  const size_t docs = (budget - fixed) / row / 8 * 8;
-  return docs >= 32 ? (uint32_t) std::min<size_t>(docs, kMaxDocs) : 0;
 }
 
 int qr_score_dataset_device(qr_scorer *s, const float *docs, size_t N, size_t F, double *scores) {
@@ -390,7 +482,7 @@ int qr_score_dataset_device(qr_scorer *s, const float *docs, size_t N, size_t F,
   cudaSetDevice(s->device);
   if (N == 0) return QR_OK;
   const size_t doc_bytes = (size_t) s->stride * s->code_bytes;
-  const size_t batch = std::min<size_t>(N, std::max<size_t>(kMaxDocs, ((size_t) 1 << 30) / doc_bytes / kMaxDocs * kMaxDocs));
+  const size_t batch = std::min<size_t>(N, std::max<size_t>(1024, ((size_t) 1 << 30) / doc_bytes / 1024 * 1024));
   if (s->batch_docs < batch) {
     if (s->d_codes) cudaFree(s->d_codes);
     s->d_codes = nullptr;
@@ -398,32 +490,32 @@ int qr_score_dataset_device(qr_scorer *s, const float *docs, size_t N, size_t F,
     QR_CUDA(cudaMemsetAsync(s->d_codes, 0, batch * doc_bytes, s->stream));
     s->batch_docs = batch;
   }
-  const uint32_t tile_docs = score_docs_per_block(s);
-  const bool tile = tile_docs != 0;
-  const uint32_t dpb = tile ? tile_docs : 64;
+  const ScoreShape sh = score_shape(s);
+  const bool tile = sh.docs != 0;
+  const uint32_t dpb = tile ? sh.docs : 64;
   const uint32_t tile_words = score_tile_words(s);
   const size_t smem = 2 * (size_t) s->chunk_bytes + (tile ? (size_t) dpb * tile_words * 4 : 0);
   if (smem > 224 * 1024) { set_error("a chunk of the ensemble (%u bytes) does not fit in shared memory", s->chunk_bytes); return QR_ELIMIT; }
   for (size_t n0 = 0; n0 < N; n0 += batch) {
     const size_t n = std::min(batch, N - n0);
-    const size_t work = n * std::max<uint32_t>(s->nslots, 1);
-    const unsigned eg = (unsigned) ((work + 255) / 256);
-    const unsigned sg = (unsigned) ((n + dpb - 1) / dpb);
-#define QR_SCORE_LAUNCH(T, TILE)                                                                              \
-  do {                                                                                                        \
-    if (s->nslots)                                                                                            \
-      encode_kernel<T><<<eg, 256, 0, s->stream>>>(docs, n0, n, F, s->d_slot_feature, s->d_thr_off, s->d_thr,  \
-                                                   s->nslots, s->stride, (T *) s->d_codes);                  \
-    cudaFuncSetAttribute(score_codes_kernel<T, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem); \
-    score_codes_kernel<T, TILE><<<sg, dpb * kTpd, smem, s->stream>>>(                                         \
-        (const T *) s->d_codes, n, s->stride, tile_words, s->d_chunks, s->chunk_bytes, s->nchunks, dpb,       \
-        scores + n0);                                                                                         \
-    s->launches += 2;                                                                                         \
-  } while (0)
-    if (s->code_bytes == 1) { if (tile) QR_SCORE_LAUNCH(uint8_t, true); else QR_SCORE_LAUNCH(uint8_t, false); }
-    else { if (tile) QR_SCORE_LAUNCH(uint16_t, true); else QR_SCORE_LAUNCH(uint16_t, false); }
-#undef QR_SCORE_LAUNCH
-    QR_CUDA(cudaGetLastError());
+    if (s->nslots) {
+      const unsigned eg = (unsigned) ((n + kEncDocs - 1) / kEncDocs);
+      const uint32_t cols = std::min<uint32_t>(s->nslots, kEncSlots);
+      const size_t esm = (size_t) kEncDocs * 4 * (enc_x_words(cols) + enc_code_words(cols, (uint32_t) s->code_bytes));
+      if (s->code_bytes == 1) {
+        cudaFuncSetAttribute(encode_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) esm);
+        encode_kernel<uint8_t><<<eg, kEncThreads, esm, s->stream>>>(docs, n0, n, F, s->d_slot_feature, s->d_thr_off, s->d_thr,
+                                                                    s->nslots, s->stride, (uint8_t *) s->d_codes);
+      } else {
+        cudaFuncSetAttribute(encode_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) esm);
+        encode_kernel<uint16_t><<<eg, kEncThreads, esm, s->stream>>>(docs, n0, n, F, s->d_slot_feature, s->d_thr_off, s->d_thr,
+                                                                     s->nslots, s->stride, (uint16_t *) s->d_codes);
+      }
+      s->launches += 1;
+    }
+    QR_CUDA(s->code_bytes == 1 ? score_dispatch<uint8_t>(s, sh, n, dpb, tile_words, smem, scores + n0)
+                               : score_dispatch<uint16_t>(s, sh, n, dpb, tile_words, smem, scores + n0));
+    s->launches += 1;
   }
   return QR_OK;
 }
@@ -451,29 +543,57 @@ int qr_scorer_timer(qr_scorer *s, int stop, double *ms) {
   return QR_OK;
 }
 
+// Host buffers (the reference's Dataset::data_): the documents stream through the device in slices,
+// the upload of slice k+1 (copy stream) overlapping the encode + walk of slice k (compute stream).
 int qr_score_dataset(qr_scorer *s, const float *docs, size_t N, size_t F, double *scores) {
   if (!s || !docs || !scores) { set_error("qr_score_dataset: null argument"); return QR_EINVAL; }
+  if (F != s->F) { set_error("dataset has %zu features, the model was built for %zu", F, s->F); return QR_EINVAL; }
   cudaSetDevice(s->device);
   if (N == 0) return QR_OK;
-  // host buffers: stream the documents through the device in batches
-  const size_t batch = std::min<size_t>(N, std::max<size_t>(1, ((size_t) 1 << 30) / (F * sizeof(float))));
-  float *d_docs = nullptr;
-  double *d_scores = nullptr;
-  QR_CUDA(cudaMalloc((void **) &d_docs, batch * F * sizeof(float)));
-  QR_CUDA(cudaMalloc((void **) &d_scores, batch * sizeof(double)));
+  // slice: ~1/8 of the dataset, between 16 Ki documents and 256 MB of floats
+  const size_t max_docs = std::max<size_t>(1, ((size_t) 256 << 20) / (F * sizeof(float)));
+  const size_t slice = std::min(N, std::min(max_docs, std::max<size_t>(16384, (N + 7) / 8)));
+  if (s->io_docs < slice) {
+    for (int b = 0; b < 2; ++b) {
+      if (s->d_in[b]) cudaFree(s->d_in[b]);
+      if (s->d_out[b]) cudaFree(s->d_out[b]);
+      s->d_in[b] = nullptr;
+      s->d_out[b] = nullptr;
+    }
+    s->io_docs = 0;
+    for (int b = 0; b < 2; ++b) {
+      QR_CUDA(cudaMalloc((void **) &s->d_in[b], slice * F * sizeof(float)));
+      QR_CUDA(cudaMalloc((void **) &s->d_out[b], slice * sizeof(double)));
+    }
+    s->io_docs = slice;
+  }
+  if (!s->copy_stream) {
+    QR_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      QR_CUDA(cudaEventCreateWithFlags(&s->ev_in[b], cudaEventDisableTiming));
+      QR_CUDA(cudaEventCreateWithFlags(&s->ev_free[b], cudaEventDisableTiming));
+    }
+  }
   int rc = QR_OK;
-  for (size_t n0 = 0; n0 < N && rc == QR_OK; n0 += batch) {
-    const size_t n = std::min(batch, N - n0);
-    cudaError_t e = cudaMemcpyAsync(d_docs, docs + n0 * F, n * F * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+  size_t k = 0;
+  for (size_t n0 = 0; n0 < N && rc == QR_OK; n0 += slice, ++k) {
+    const size_t n = std::min(slice, N - n0);
+    const int b = (int) (k & 1);
+    // the copy stream may overwrite d_in[b] only after the walk of slice k-2 has consumed it
+    if (k >= 2) QR_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_free[b], 0));
+    cudaError_t e = cudaMemcpyAsync(s->d_in[b], docs + n0 * F, n * F * sizeof(float), cudaMemcpyHostToDevice, s->copy_stream);
     if (e != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(e)); rc = QR_ECUDA; break; }
-    rc = qr_score_dataset_device(s, d_docs, n, F, d_scores);
+    QR_CUDA(cudaEventRecord(s->ev_in[b], s->copy_stream));
+    QR_CUDA(cudaStreamWaitEvent(s->stream, s->ev_in[b], 0));
+    rc = qr_score_dataset_device(s, s->d_in[b], n, F, s->d_out[b]);
     if (rc != QR_OK) break;
-    e = cudaMemcpyAsync(scores + n0, d_scores, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    QR_CUDA(cudaEventRecord(s->ev_free[b], s->stream));
+    e = cudaMemcpyAsync(scores + n0, s->d_out[b], n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
     if (e != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(e)); rc = QR_ECUDA; }
   }
-  cudaFree(d_docs);
-  cudaFree(d_scores);
+  cudaError_t e = cudaStreamSynchronize(s->copy_stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess && rc == QR_OK) { set_error("scoring failed: %s", cudaGetErrorString(e)); rc = QR_ECUDA; }
   return rc;
 }
 

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -k "scoring or score or host_cli" > gpurun_out/pytest_gpu.log 2>&1
+tail -5 gpurun_out/pytest_gpu.log
+timeout 600 python scripts/score_probe.py --n 1000000 --f 136 --trees 1000 2>&1 | tail -2
+timeout 600 python scripts/score_probe.py --n 1000000 --f 700 --trees 5000 2>&1 | tail -2
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/score_launches.csv python scripts/score_probe.py --n 1000000 --f 136 --trees 1000 > /dev/null 2>&1
+grep -E "encode|score_codes" gpurun_out/score_launches.csv | tail -4
