@@ -112,7 +112,6 @@ struct qr_ctx {
   uint32_t *d_ticket = nullptr;             // one-pass partition block tickets
   uint32_t ticket_base = 0, part_epoch = 0;
   uint32_t *d_root_cnt = nullptr;           // [ncells] per-bin document counts of the whole dataset
-  uint4 *d_hot_rows = nullptr;              // [npanels] most frequent bin of each feature, packed like a panel row
   unsigned long long *d_hist_sum = nullptr; // [nslots][ncells] int64 (FAST) or double (REFERENCE)
   uint32_t *d_hist_cnt = nullptr;           // [nslots][ncells]
   int nslots = 0;

@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <atomic>
 #include <cfloat>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -272,6 +274,20 @@ static int finish_binning(qr_ctx *c, const float *d_col, uint32_t max_bin) {
 
 static int init_root_counts(qr_ctx *c);
 
+// QR_INIT_TIMING=1: wall-clock breakdown of qr_ctx_create on stderr (development aid)
+struct InitClock {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  InitClock() : on(getenv("QR_INIT_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(const char *what) {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[qr init] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t F, const float *labels,
                              const uint64_t *qoffsets, size_t Q, const qr_params *params,
                              const unsigned char *comm_id, int rank, int world, const qr_ctx *thr_from,
@@ -283,6 +299,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   if (N >= ((size_t) 1 << 31)) { set_error("N >= 2^31 documents per GPU is not supported"); return QR_ELIMIT; }
   if (qoffsets[0] != 0 || qoffsets[Q] != N) { set_error("query offsets must start at 0 and end at N"); return QR_EINVAL; }
   if (params->algo > QR_ALGO_OBVLAMBDAMART) { set_error("unknown algo %u", params->algo); return QR_EINVAL; }
+  InitClock clk;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     set_error("no CUDA device available (this library has no CPU fallback)");
@@ -306,6 +323,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   if (!c->oblivious && params->nleaves < 1) { delete c; set_error("nleaves must be >= 1"); return QR_EINVAL; }
   *out = c;  // destroyed by the caller on failure paths below via qr_ctx_destroy
   QR_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  clk.lap("cuda context + stream");
   QR_CUDA(cudaEventCreate(&c->ev0));
   QR_CUDA(cudaEventCreate(&c->ev1));
   QR_CUDA(cudaEventCreate(&c->ev_t0));
@@ -342,9 +360,11 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     QR_CUDA(cudaMemcpyAsync(d_col, feat, N * F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
   c->eval_only = thr_from != nullptr;
+  clk.lap("feature upload (+transpose)");
   int rc = build_binning(c, d_col, thr_from);
   cudaFree(d_col);
   if (rc != QR_OK) return rc;
+  clk.lap("thresholds + binning");
 
   // labels, gains, query offsets, ideal DCG per query, discount tables (host glibc, once)
   std::vector<uint32_t> qoff(Q + 1);
@@ -372,6 +392,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
       idcg[q] = dcg;
     }
   }
+  clk.lap("host gain/idcg tables");
   QR_TRY(dev_alloc(&c->d_labels, N));
   QR_TRY(dev_alloc(&c->d_gain, N));
   QR_TRY(dev_alloc(&c->d_qoff, Q + 1));
@@ -471,8 +492,10 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   }
   QR_CUDA(cudaGetLastError());
+  clk.lap("state + pools");
   QR_TRY(init_root_counts(c));
   QR_CUDA(cudaGetLastError());
+  clk.lap("root counts");
   return QR_OK;
 }
 
@@ -610,7 +633,7 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_partials, c->d_hist_sum, c->d_hist_cnt, c->d_fbest_score, c->d_fbest_t, c->d_res,
                   c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
                   c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done, c->d_part_status,
-                  c->d_ticket, c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_hot_rows};
+                  c->d_ticket, c->d_root_cnt, c->d_fbest_lc, c->d_totals};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);

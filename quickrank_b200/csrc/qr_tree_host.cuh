@@ -93,9 +93,9 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
       const bool use_smem = smem <= 200 * 1024;
       if (total_slices > c->max_slices - c->max_tasks) { set_error("internal: %u histogram slices > capacity", total_slices); return QR_ECUDA; }
 #define QR_HIST_LAUNCH(SMEMF, COUNTF)                                                                        \
-  QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), 256,            \
+  QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), kHistThreads,   \
             SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
-            c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->d_hot_rows, c->max_thr)
+            c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr)
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
         if (use_smem) {
@@ -153,13 +153,12 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
   return QR_OK;
 }
 
-// documents per histogram slice so that a round's grid is one full wave: four blocks of the
-// histogram kernel fit on an SM (shared-memory limit), 148 SMs.  Small rounds get small slices: the
-// kernel needs ~32 resident warps per SM to hide the latency of its returning shared atomics, and a
-// round of a few ten-thousand documents in 4096-document slices would leave most SMs with one block.
+// documents per histogram slice so that a round's grid is about one block per SM (148 SMs): every
+// block ends by flushing its shared-memory histogram with global atomics, a fixed cost that small
+// rounds cannot amortise over more blocks; measured in scripts/hist_mb2.cu.
 static uint32_t pick_hist_dpb(const qr_ctx *c, uint64_t total_docs) {
-  const uint32_t want_slices = std::max<uint32_t>(1, (148u * 4u) / c->npanels);
-  uint64_t dpb = std::max<uint64_t>(512u, (total_docs + want_slices - 1) / want_slices);
+  const uint32_t want_slices = std::max<uint32_t>(1, 148u / c->npanels);
+  uint64_t dpb = std::max<uint64_t>(2u * kHistThreads, (total_docs + want_slices - 1) / want_slices);
   dpb = (dpb + 255u) & ~(uint64_t) 255u;
   return (uint32_t) std::min<uint64_t>(dpb, 1u << 20);
 }
@@ -207,38 +206,19 @@ static int init_root_counts(qr_ctx *c) {
   QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
     using B = decltype(tag);
     if (use_smem)
-      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(t.hist_nblk, c->npanels), 256, smem, c->d_tasks, 1u,
+      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, smem, c->d_tasks, 1u,
                 c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, (const uint4 *) nullptr, c->max_thr);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr);
     else
-      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(t.hist_nblk, c->npanels), 256, 0, c->d_tasks, 1u,
+      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, 0, c->d_tasks, 1u,
                 c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, (const uint4 *) nullptr, c->max_thr);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr);
     return QR_OK;
   }));
   QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
   QR_CUDA(cudaMemcpyAsync(c->d_root_cnt, c->d_hist_cnt + (size_t) slot * c->ncells, c->ncells * sizeof(uint32_t),
                           cudaMemcpyDeviceToDevice, c->stream));
   if (c->comm) QR_TRY(comm_allreduce_sum_u32(c->comm, c->d_root_cnt, c->ncells, c->stream));
-  // most frequent bin of every feature (hist_limb_kernel skips it and recovers it by subtraction)
-  std::vector<uint32_t> cnt(c->ncells), hot(c->F);
-  QR_CUDA(cudaMemcpyAsync(cnt.data(), c->d_root_cnt, c->ncells * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  QR_CUDA(cudaStreamSynchronize(c->stream));
-  for (size_t f = 0; f < c->F; ++f) {
-    uint32_t best = 0;
-    for (uint32_t t = c->thr_off[f]; t < c->thr_off[f + 1]; ++t)
-      if (cnt[t] > cnt[c->thr_off[f] + best]) best = t - c->thr_off[f];
-    hot[f] = best;
-  }
-  // pack them like a panel row (one element per feature slot)
-  std::vector<unsigned char> rows((size_t) c->npanels * 16, 0);
-  for (size_t f = 0; f < c->F; ++f) {
-    const size_t pnl = f / c->fpp, j = f % c->fpp;
-    if (c->bin_bytes == 1) rows[pnl * 16 + j] = (unsigned char) hot[f];
-    else { const uint16_t v = (uint16_t) hot[f]; memcpy(&rows[pnl * 16 + 2 * j], &v, 2); }
-  }
-  QR_TRY(dev_alloc(&c->d_hot_rows, c->npanels));
-  QR_CUDA(cudaMemcpy(c->d_hot_rows, rows.data(), rows.size(), cudaMemcpyHostToDevice));
   QR_CUDA(cudaStreamSynchronize(c->stream));
   int s2 = slot;
   release_slot(c, s2);

@@ -258,59 +258,84 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
 // (rtnode_histogram.cc:51-58, 183-191) in 64-bit fixed point.  Shared memory has no native 64-bit
 // add, so each cell is two 32-bit limbs updated with native shared atomics: the low limb's atomic
 // returns the old value, which tells this very addition whether it carried into the high limb.
-// One block per (document slice, panel); lanes walk the panel's features in rotated order so that
-// the lanes of a warp hit different features' cells.  Integer sums are order-independent: the
-// result is deterministic and identical for any slicing (and any number of GPUs).
+// One block per (document slice, panel).  Integer sums are order-independent: the result is
+// deterministic and identical for any slicing (and any number of GPUs).
+//
+// Shared-memory layout and lane schedule (measured with scripts/hist_mb2.cu: the update loop runs
+// at the shared-atomic issue rate, 16 lanes per clock per SM):
+//  * cells are BIN-major: word index = bin * FPP + slot (slot = feature within the panel), three
+//    word arrays (low limb | high limb | count);
+//  * at step j lane L updates slot j ^ (L mod FPP): the 32 lanes of a warp touch every slot of the
+//    panel twice per step, so no two lanes of a half-warp share a bank (bank = (bin & 1) * 16 +
+//    slot for 8-bit bins) whatever the bins are, and at most two lanes can meet on one address;
+//  * the row is permuted once per document (element j <- element j ^ rot) so that every extract
+//    below has a compile-time position; there are no branches in the update loop;
+//  * the rows of iteration t+1 are already in flight while iteration t updates shared memory.
 // ------------------------------------------------------------------------------------------
-// one document's panel row into the block's limb histogram.  Shared-memory cells are addressed as
-// slot * stride + bin (stride = widest feature of the panel), so no table look-up is needed; `hotx`
-// is the row XORed with the panel's most-frequent bins: a zero element means "hot bin, skip" —
-// those documents are recovered at the end as (block total) - (all other cells), exactly, because
-// the sums are integers.  Half of the features at a time keeps the register footprint at 64.
+// element j of the result = element j ^ r of v (elements of sizeof(BinT) bytes)
+template <typename BinT>
+__device__ __forceinline__ uint4 xor_permute(uint4 v, uint32_t r, uint32_t sel) {
+  constexpr uint32_t WB = sizeof(BinT) == 1 ? 4u : 2u;   // bit of r that swaps neighbouring words
+  if (r & WB) { uint32_t t = v.x; v.x = v.y; v.y = t; t = v.z; v.z = v.w; v.w = t; }
+  if (r & (WB << 1)) { uint32_t t = v.x; v.x = v.z; v.z = t; t = v.y; v.y = v.w; v.w = t; }
+  uint4 o;
+  o.x = __byte_perm(v.x, 0, sel); o.y = __byte_perm(v.y, 0, sel);
+  o.z = __byte_perm(v.z, 0, sel); o.w = __byte_perm(v.w, 0, sel);
+  return o;
+}
+template <typename BinT>
+__device__ __forceinline__ uint32_t xor_permute_selector(uint32_t r) {
+  if (sizeof(BinT) == 1) return 0x3210u ^ (0x1111u * (r & 3u));
+  return (r & 1u) ? 0x1032u : 0x3210u;
+}
+
+// one document's (permuted) panel row into the block's limb histogram; cinc = 1 for a real
+// document, 0 for the padding document of a thread's last, half-filled iteration (whose q is 0)
 template <typename BinT, bool COUNT>
-__device__ __forceinline__ void hist_add_row_smem(const uint4 &row, const uint4 &hotx, long long q, uint32_t rot,
-                                                  uint32_t nf, uint32_t stride, uint32_t *s_lo, int32_t *s_hi,
-                                                  uint32_t *s_cnt) {
+__device__ __forceinline__ void hist_add_row_smem(const uint4 &x, long long q, uint32_t cinc, unsigned char *rbp,
+                                                  uint32_t hi_off, uint32_t cnt_off) {
   constexpr int FPP = kPanelBytes / sizeof(BinT);
   constexpr int H = FPP < 8 ? FPP : 8;
+  constexpr int SH = sizeof(BinT) == 1 ? 6 : 5;            // log2(4 * FPP): bytes per bin row
   const uint32_t qlo = (uint32_t) q;
-  const int32_t qhi = (int32_t) (q >> 32);
+  const uint32_t qhi = (uint32_t) (q >> 32);
+  const uint32_t rb = (uint32_t) (uintptr_t) rbp;           // only the low bits matter (xor below)
 #pragma unroll
   for (int h0 = 0; h0 < FPP; h0 += H) {
-    uint32_t cell[H], old[H];
+    unsigned char *addr[H];
+    uint32_t old[H];
 #pragma unroll
     for (int j = 0; j < H; ++j) {
-      const uint32_t slot = (h0 + j + rot) & (FPP - 1);
-      const bool on = slot < nf && extract_bin<BinT>(hotx, h0 + j) != 0u;
-      cell[j] = on ? slot * stride + extract_bin<BinT>(row, h0 + j) : 0xffffffffu;
-      if (on) old[j] = atomicAdd(s_lo + cell[j], qlo);
+      const uint32_t xb = extract_bin<BinT>(x, h0 + j);
+      addr[j] = rbp + ((xb << SH) + ((rb ^ (uint32_t) ((h0 + j) * 4)) - rb));
+      old[j] = atomicAdd(reinterpret_cast<uint32_t *>(addr[j]), qlo);
     }
 #pragma unroll
     for (int j = 0; j < H; ++j) {
-      if (cell[j] != 0xffffffffu) {
-        const int32_t carry = (old[j] + qlo) < old[j];
-        atomicAdd(s_hi + cell[j], qhi + carry);
-        if (COUNT) atomicAdd(s_cnt + cell[j], 1u);
-      }
+      const uint32_t carry = (old[j] + qlo) < old[j];
+      atomicAdd(reinterpret_cast<uint32_t *>(addr[j] + hi_off), qhi + carry);
+      if (COUNT) atomicAdd(reinterpret_cast<uint32_t *>(addr[j] + cnt_off), cinc);
     }
   }
 }
 
+// One block per SM (kHistThreads threads, one 16-feature limb histogram): every resident histogram is
+// flushed with global atomics at the end of its block, so fewer, fatter blocks cut that cost; the
+// update loop itself is bound by the shared-atomic issue rate, not by occupancy (scripts/hist_mb2.cu).
+constexpr uint32_t kHistThreads = 512;
+
 template <typename BinT, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(kHistThreads, 2)
 hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint32_t *__restrict__ lcount,
                  const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ ids0,
                  const uint32_t *__restrict__ ids1, const long long *__restrict__ lamq,
                  const uint32_t *__restrict__ thr_off, uint32_t F, unsigned long long *hsum,
-                 uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials,
-                 const uint4 *__restrict__ hot_rows, uint32_t stride) {
+                 uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials, uint32_t stride) {
   constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ uint32_t s_base[FPP + 1];
   __shared__ uint32_t s_task;
-  __shared__ U128 s_sq[8];
-  __shared__ long long s_totq[8];
-  __shared__ uint32_t s_totn[8];
+  __shared__ U128 s_sq[kHistThreads / 32];
   if (threadIdx.x == 0) s_task = find_task_by(tasks, ntasks, blockIdx.x, true);
   __syncthreads();
   const NodeTask t = tasks[s_task];
@@ -327,70 +352,74 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
   const uint32_t f0 = p * FPP;
   const uint32_t nf = min(FPP, F - f0);
   const uint32_t cell0 = thr_off[f0];
-  const uint32_t scells = SMEM ? FPP * stride : 0u;   // shared-memory cells (uniform stride)
-  uint32_t *s_lo = reinterpret_cast<uint32_t *>(smem_raw);
-  int32_t *s_hi = reinterpret_cast<int32_t *>(s_lo + scells);
-  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(s_hi + scells);
+  const uint32_t scells = SMEM ? FPP * stride : 0u;   // shared-memory cells, bin-major
   if (threadIdx.x <= FPP) s_base[threadIdx.x] = thr_off[f0 + min(threadIdx.x, nf)] - cell0;
-  if (SMEM)
-    for (uint32_t i = threadIdx.x; i < scells; i += 256) { s_lo[i] = 0u; s_hi[i] = 0; if (COUNT) s_cnt[i] = 0u; }
+  if (SMEM) {
+    uint4 *z = reinterpret_cast<uint4 *>(smem_raw);
+    const uint32_t nz = scells * (COUNT ? 3u : 2u) / 4u;   // scells is a multiple of 8
+    for (uint32_t i = threadIdx.x; i < nz; i += kHistThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+  }
   __syncthreads();
 
   unsigned long long *gs = hsum + (size_t) t.slotB * ncells + cell0;
   uint32_t *gc = hcnt + (size_t) t.slotB * ncells + cell0;
   const bool identity = t.whole && t.src == 2;
-  const uint32_t *ids = (t.whole ? t.src : t.dst) == 1 ? ids1 : ids0;
-  const uint32_t rot = lane_id() & (FPP - 1);
-  const uint32_t rotb = rot * (uint32_t) sizeof(BinT);
+  const uint32_t *ids = ((t.whole ? t.src : t.dst) == 1 ? ids1 : ids0) + seg0;
   const uint4 *prow = panels + (size_t) p * N;
-  // the panel's most frequent bins, rotated like the rows; all-ones elements never match a bin
-  const bool bypass = SMEM && hot_rows != nullptr;
-  const uint4 hot = bypass ? rotate_bytes(hot_rows[p], rotb) : make_uint4(0u, 0u, 0u, 0u);
   U128 sq{0ull, 0ull};
-  long long totq = 0;      // sum of the fixed-point pseudo-responses of this thread's documents
-  uint32_t totn = 0;
-  // two documents per iteration: their loads are independent, which doubles the memory-level
-  // parallelism of the gather
-  for (uint32_t i = begin + threadIdx.x; i < end; i += 512) {
-    const uint32_t i1 = i + 256;
-    const bool has1 = i1 < end;
-    const uint32_t d0 = identity ? seg0 + i : ids[seg0 + i];
-    const uint32_t d1 = has1 ? (identity ? seg0 + i1 : ids[seg0 + i1]) : d0;
-    const uint4 raw0 = prow[d0];
-    const uint4 raw1 = prow[d1];
-    const long long q0 = lamq[d0];
-    const long long q1 = lamq[d1];
-    totq += q0 + (has1 ? q1 : 0ll);
-    totn += has1 ? 2u : 1u;
-    if (p == 0) {   // squares_sum_ (rtnode_histogram.cc:65-69) as an exact integer
-      const unsigned long long a0 = (unsigned long long) (q0 < 0 ? -q0 : q0);
-      u128_add(sq, a0 * a0, __umul64hi(a0, a0));
-      if (has1) {
+  if (SMEM) {
+    const uint32_t rot = lane_id() & (FPP - 1);
+    const uint32_t sel = xor_permute_selector<BinT>(rot);
+    unsigned char *rbp = smem_raw + rot * 4u;
+    const uint32_t hi_off = scells * 4u, cnt_off = scells * 8u;
+    uint32_t i = begin + threadIdx.x;
+    uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
+    long long q0 = 0, q1 = 0;
+    bool v0 = i < end, v1 = i + kHistThreads < end;
+    if (v0) { const uint32_t d = identity ? seg0 + i : ids[i]; c0 = prow[d]; q0 = lamq[d]; }
+    if (v1) { const uint32_t d = identity ? seg0 + i + kHistThreads : ids[i + kHistThreads]; c1 = prow[d]; q1 = lamq[d]; }
+    bool w0 = i + 2 * kHistThreads < end, w1 = i + 3 * kHistThreads < end;
+    uint32_t nd0 = 0, nd1 = 0;   // documents of the NEXT iteration
+    if (w0) nd0 = identity ? seg0 + i + 2 * kHistThreads : ids[i + 2 * kHistThreads];
+    if (w1) nd1 = identity ? seg0 + i + 3 * kHistThreads : ids[i + 3 * kHistThreads];
+    while (v0) {
+      uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
+      long long nq0 = 0, nq1 = 0;
+      if (w0) { n0 = prow[nd0]; nq0 = lamq[nd0]; }
+      if (w1) { n1 = prow[nd1]; nq1 = lamq[nd1]; }
+      i += 2 * kHistThreads;
+      const bool z0 = i + 2 * kHistThreads < end, z1 = i + 3 * kHistThreads < end;
+      if (z0) nd0 = identity ? seg0 + i + 2 * kHistThreads : ids[i + 2 * kHistThreads];
+      if (z1) nd1 = identity ? seg0 + i + 3 * kHistThreads : ids[i + 3 * kHistThreads];
+      if (p == 0) {   // squares_sum_ (rtnode_histogram.cc:65-69) as an exact integer
+        const unsigned long long a0 = (unsigned long long) (q0 < 0 ? -q0 : q0);
         const unsigned long long a1 = (unsigned long long) (q1 < 0 ? -q1 : q1);
+        u128_add(sq, a0 * a0, __umul64hi(a0, a0));
         u128_add(sq, a1 * a1, __umul64hi(a1, a1));
       }
+      const uint4 x0 = xor_permute<BinT>(c0, rot, sel), x1 = xor_permute<BinT>(c1, rot, sel);
+      hist_add_row_smem<BinT, COUNT>(x0, q0, 1u, rbp, hi_off, cnt_off);
+      hist_add_row_smem<BinT, COUNT>(x1, q1, v1 ? 1u : 0u, rbp, hi_off, cnt_off);
+      c0 = n0; c1 = n1; q0 = nq0; q1 = nq1; v0 = w0; v1 = w1; w0 = z0; w1 = z1;
     }
-    if (SMEM) {
-      const uint4 r0 = rotate_bytes(raw0, rotb), r1 = rotate_bytes(raw1, rotb);
-      const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
-      const uint4 x0 = bypass ? make_uint4(r0.x ^ hot.x, r0.y ^ hot.y, r0.z ^ hot.z, r0.w ^ hot.w) : ones;
-      const uint4 x1 = bypass ? make_uint4(r1.x ^ hot.x, r1.y ^ hot.y, r1.z ^ hot.z, r1.w ^ hot.w) : ones;
-      hist_add_row_smem<BinT, COUNT>(r0, x0, q0, rot, nf, stride, s_lo, s_hi, s_cnt);
-      if (has1) hist_add_row_smem<BinT, COUNT>(r1, x1, q1, rot, nf, stride, s_lo, s_hi, s_cnt);
-    } else {
+  } else {
+    const uint32_t rot = lane_id() & (FPP - 1);
+    const uint32_t rotb = rot * (uint32_t) sizeof(BinT);
+    for (uint32_t i = begin + threadIdx.x; i < end; i += kHistThreads) {
+      const uint32_t d = identity ? seg0 + i : ids[i];
+      const uint4 row = rotate_bytes(prow[d], rotb);
+      const long long q = lamq[d];
+      if (p == 0) {
+        const unsigned long long a = (unsigned long long) (q < 0 ? -q : q);
+        u128_add(sq, a * a, __umul64hi(a, a));
+      }
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (k == 1 && !has1) break;
-        const uint4 row = rotate_bytes(k ? raw1 : raw0, rotb);
-        const long long q = k ? q1 : q0;
-#pragma unroll
-        for (int j = 0; j < (int) FPP; ++j) {
-          const uint32_t slot = (j + rot) & (FPP - 1);
-          if (slot < nf) {
-            const uint32_t c = s_base[slot] + extract_bin<BinT>(row, j);
-            atomicAdd(gs + c, (unsigned long long) q);
-            if (COUNT) atomicAdd(gc + c, 1u);
-          }
+      for (int j = 0; j < (int) FPP; ++j) {
+        const uint32_t slot = (j + rot) & (FPP - 1);
+        if (slot < nf) {
+          const uint32_t c = s_base[slot] + extract_bin<BinT>(row, j);
+          atomicAdd(gs + c, (unsigned long long) q);
+          if (COUNT) atomicAdd(gc + c, 1u);
         }
       }
     }
@@ -403,51 +432,24 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
     }
     if (lane_id() == 0) s_sq[threadIdx.x >> 5] = sq;
   }
-  if (bypass) {
-    for (int o = 16; o > 0; o >>= 1) {
-      totq += __shfl_xor_sync(0xffffffffu, totq, o);
-      totn += __shfl_xor_sync(0xffffffffu, totn, o);
-    }
-    if (lane_id() == 0) { s_totq[threadIdx.x >> 5] = totq; s_totn[threadIdx.x >> 5] = totn; }
-  }
   if (SMEM || p == 0) __syncthreads();
   if (p == 0 && threadIdx.x == 0) {
     U128 tot = s_sq[0];
-    for (int w = 1; w < 8; ++w) u128_add(tot, s_sq[w].lo, s_sq[w].hi);
+    for (int w = 1; w < (int) kHistThreads / 32; ++w) u128_add(tot, s_sq[w].lo, s_sq[w].hi);
     sq_partials[blockIdx.x] = make_ulonglong2(tot.lo, tot.hi);
   }
   if (SMEM) {
-    // flush: one warp per feature slot walks the slot's cells; the hot cell (never touched above)
-    // receives block total minus the others
-    long long bq = 0;
-    uint32_t bn = 0;
-    if (bypass)
-      for (int w = 0; w < 8; ++w) { bq += s_totq[w]; bn += s_totn[w]; }
-    const BinT *hotb = reinterpret_cast<const BinT *>(hot_rows + p);
-    for (uint32_t slot = threadIdx.x >> 5; slot < nf; slot += 8) {
-      const uint32_t width = s_base[slot + 1] - s_base[slot];
-      long long oq = 0;
-      uint32_t on = 0;
-      for (uint32_t b = lane_id(); b < width; b += 32) {
-        const uint32_t i = slot * stride + b;
-        const long long v = ((long long) s_hi[i] << 32) + (long long) s_lo[i];
-        const uint32_t cn = COUNT ? s_cnt[i] : 0u;
-        if (v != 0) atomicAdd(gs + s_base[slot] + b, (unsigned long long) v);
-        if (COUNT && cn) atomicAdd(gc + s_base[slot] + b, cn);
-        oq += v;
-        on += cn;
-      }
-      if (bypass) {
-        for (int o = 16; o > 0; o >>= 1) {
-          oq += __shfl_xor_sync(0xffffffffu, oq, o);
-          on += __shfl_xor_sync(0xffffffffu, on, o);
-        }
-        if (lane_id() == 0) {
-          const uint32_t hb = hotb[slot];
-          const long long hv = bq - oq;
-          if (hv != 0) atomicAdd(gs + s_base[slot] + hb, (unsigned long long) hv);
-          if (COUNT && bn != on) atomicAdd(gc + s_base[slot] + hb, bn - on);
-        }
+    // flush: consecutive threads read consecutive shared cells (cell = bin * FPP + slot)
+    const uint32_t *s_lo = reinterpret_cast<const uint32_t *>(smem_raw);
+    const uint32_t *s_hi = s_lo + scells, *s_cnt = s_hi + scells;
+    for (uint32_t i = threadIdx.x; i < scells; i += kHistThreads) {
+      const uint32_t slot = i & (FPP - 1), bin = i / FPP;
+      const long long v = ((long long) (int32_t) s_hi[i] << 32) + (long long) s_lo[i];
+      const uint32_t cn = COUNT ? s_cnt[i] : 0u;
+      // padding slots of the last panel collect the zero bins of their all-zero columns: dropped
+      if (slot < nf && bin < s_base[slot + 1] - s_base[slot]) {
+        if (v != 0) atomicAdd(gs + s_base[slot] + bin, (unsigned long long) v);
+        if (COUNT && cn) atomicAdd(gc + s_base[slot] + bin, cn);
       }
     }
   }
