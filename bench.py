@@ -57,7 +57,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -105,6 +105,30 @@ def make_shard(rank, world, w=WORKLOAD):
     d0, d1 = int(qoff[q0]), int(qoff[q1])
     return (np.ascontiguousarray(x[d0:d1]), np.ascontiguousarray(labels[d0:d1]),
             (qoff[q0:q1 + 1] - qoff[q0]).astype(np.uint64))
+
+
+def comm2(rank, world, dist):
+    """A second NCCL communicator id for the end-to-end context (N > 1)."""
+    if world == 1:
+        return None
+    import torch
+    from quickrank_b200 import api
+    idt = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(idt, 0)
+    return (bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/hist_full_summary.json, written by scripts/ncu_summary.py)."""
+    p = os.path.join(ROOT, "profiles", "hist_full_summary.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d.get("dram_bytes_per_launch"), "profiles/hist_full_summary.json (%s)" % d.get("capture", "")
+    return None, "no ncu capture committed"
 
 
 def hist_bytes_per_tree(n, f, rho, bin_bytes=1):
@@ -162,14 +186,16 @@ def run_ours(args):
     # scores (documents that shared every leaf so far) and ranking takes the sequential std::sort
     # replica; afterwards (97% of the run) ties are gone.  `--settle` untimed trees put the timed
     # region in that steady state; --settle 0 times the start of the run instead.
+    # clocks are sampled from the settle trees on: the same workload runs before and inside the timed
+    # region, so every sample is a sample under load even when the timed region itself is short
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.settle):
         tr.boost_iteration(want_tree=False, want_metric=True)
     for _ in range(max(args.warmup, 3)):
         tr.boost_iteration(want_tree=False, want_metric=True)
     launches0 = tr.launch_count()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     tr.timer_start()
     rho_sum = sigma_sum = 0.0
@@ -190,47 +216,70 @@ def run_ours(args):
     ms_per_step = ms / args.steps
     value = 1000.0 / ms_per_step  # trees/s of the whole job (all ranks grow the same tree)
 
-    # ---- end to end through the hook-level C ABI with host buffers ----
+    # ---- end to end: the whole job through the C ABI, starting from HOST buffers ----
+    # A new context is created from the host feature matrix (host->device copy of the dataset, threshold
+    # extraction and binning = Mart::init), then `e2e_trees` boosting iterations run through the hook-level
+    # entry points, each copying the fitted tree and the metric back to host buffers — what quicklearn does
+    # for a whole training run.  Everything is inside the timed region (wall clock around the calls, which
+    # end with the device-to-host copy of the last metric).
+    e2e_trees = args.e2e_trees
     d2h = 0
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        tr.compute_pseudoresponses()
-        tree = tr.fit_regressor_on_gradient(want_tree=True)      # flat tree copied to host arrays
-        tr.update_modelscores()
-        _m = tr.evaluate_dataset()                               # metric read back
+    tr2 = api.Trainer(x, labels, qoff, algo="LAMBDAMART", nleaves=w["leaves"], minleafsupport=w["minls"],
+                      nthresholds=w["nthresholds"], cutoff=w["cutoff"], shrinkage=w["shrinkage"],
+                      hist_mode=api.HIST_FAST, device=local_rank, comm=comm2(rank, world, dist))
+    e2e_init_s = time.perf_counter() - t0
+    for _ in range(e2e_trees):
+        tr2.compute_pseudoresponses()
+        tree = tr2.fit_regressor_on_gradient(want_tree=True)      # flat tree copied to host arrays
+        tr2.update_modelscores()
+        _m = tr2.evaluate_dataset()                               # metric read back
         d2h += sum(tree[k].nbytes for k in tree if hasattr(tree[k], "nbytes")) + 8
     e2e_s = time.perf_counter() - t0
+    tr2.close()
     barrier()
     if dist is not None:
         import torch
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = args.steps / e2e_s
+    e2e_value = e2e_trees / e2e_s
+    h2d_job = int(x.nbytes + labels.nbytes + qoff.nbytes)
 
-    # ---- roofline of the dominant kernel (histogram build), per-phase CUDA events ----
-    prof_steps = min(args.steps, 5)
+    # ---- roofline of the dominant kernel (hist_limb_kernel), CUDA events around every launch ----
+    prof_steps = min(args.steps, 10)
     tr.set_profiling(True)
     tr.phase_times(reset=True)
-    rho_p = 0.0
+    tr.hist_kernel_time(reset=True)
     for _ in range(prof_steps):
         tr.boost_iteration(want_tree=False, want_metric=True)
-        rho_p += tr.last_tree_stats()[0]
     pms, pln = tr.phase_times()
+    hk_ms, hk_launches, hk_docs = tr.hist_kernel_time()
     tr.set_profiling(False)
     peak, peak_src = load_peaks()
     n, f = len(labels), w["n_features"]
-    hb = hist_bytes_per_tree(n, f, rho_p / prof_steps)
-    hist_ms = pms["hist"] / prof_steps
-    achieved = hb / (hist_ms * 1e-3) / 1e9
+    # algorithmic bytes of one launch: every accumulated document contributes its
+    # F bin bytes + its fixed-point pseudo-response (8) [+ its id (4) when the list is gathered]
+    root_docs = float(n) * prof_steps
+    alg_bytes = hk_docs * (f * 1 + 8) + (hk_docs - root_docs) * 4
+    bytes_per_launch = alg_bytes / max(hk_launches, 1)
+    us_per_launch = hk_ms * 1e3 / max(hk_launches, 1)
+    achieved = alg_bytes / (hk_ms * 1e-3) / 1e9
+    traffic, traffic_src = load_traffic()
     roofline = {"bound": "hbm", "kernel": "hist_limb_kernel (histogram build, root + child nodes)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_tree": int(hb), "kernel_ms_per_tree": round(hist_ms, 4),
-                "phase_ms_per_tree": {k: round(v / prof_steps, 4) for k, v in pms.items()},
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(bytes_per_launch), "us_per_launch": round(us_per_launch, 2),
+                "launches_per_tree": round(hk_launches / prof_steps, 2),
+                "docs_per_launch": int(hk_docs / max(hk_launches, 1)),
+                "kernel_ms_per_tree": round(hk_ms / prof_steps, 4),
+                "kernel_share_of_step": round(hk_ms / prof_steps / ms_per_step, 3),
+                "phase_ms_per_tree_with_sync": {k: round(v / prof_steps, 4) for k, v in pms.items()},
                 "whole_tree_gbs": round(tree_bytes(n, f, rho_sum / args.steps, sigma_sum / args.steps,
-                                                   w["leaves"], 0) / (ms_per_step * 1e-3) / 1e9, 1)}
+                                                   w["leaves"], 0) / (ms_per_step * 1e-3) / 1e9, 1),
+                "note": "bound in practice by the shared-memory atomic issue rate (16 lanes/clk/SM), "
+                        "see DESIGN.md section 4"}
 
     tr.close()
     scoring = run_scoring(args, x, rank, world, local_rank, dist, barrier)
@@ -252,11 +301,14 @@ def run_ours(args):
                        "trees_before_timed_region": args.settle + max(args.warmup, 3),
                        "l2": "inputs larger than L2 (136 MB bin matrix + 40 MB state per step)"},
             "clocks": clocks,
-            "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": int(d2h / args.steps),
-                    "note": "hook-level C ABI per step (pseudo-responses, fit -> host tree, score update, "
-                            "NDCG -> host); the dataset upload + binning happen once in qr_ctx_create, "
-                            "as Mart::init does, and are reported in init_s / init_h2d_bytes"},
+            "e2e": {"value": round(e2e_value, 3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d_job / e2e_trees), "d2h_bytes_per_step": int(d2h / e2e_trees),
+                    "trees": e2e_trees, "job_s": round(e2e_s, 3), "init_s": round(e2e_init_s, 3),
+                    "h2d_bytes_job": h2d_job,
+                    "note": "whole training job from host buffers: qr_ctx_create (dataset host->device, "
+                            "thresholds, binning = Mart::init) + %d boosting iterations through the hook-level "
+                            "C ABI, each copying the fitted tree and NDCG@10 to the host; the first ~25 trees "
+                            "(tied scores, sequential sort replica) are inside" % e2e_trees},
             "init_s": round(init_s, 3), "init_h2d_bytes": int(x.nbytes + labels.nbytes + qoff.nbytes),
             "gpu_launches": int(launches),
             "roofline": roofline,
@@ -465,6 +517,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-trees", type=int, default=1000,
+                    help="boosting iterations of the end-to-end job (BASELINE.json configs[1]: 1000 trees)")
     ap.add_argument("--settle", type=int, default=30,
                     help="untimed boosting iterations before the warm-up (see run_ours)")
     args = ap.parse_args()

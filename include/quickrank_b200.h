@@ -163,6 +163,10 @@ uint64_t qr_launch_count(qr_ctx *ctx);
  * score update, [5] ranking/NDCG; also returns per-phase launch counts (either may be NULL). */
 int qr_phase_times(qr_ctx *ctx, double ms[6], uint64_t launches[6], int reset);
 int qr_set_profiling(qr_ctx *ctx, int enabled);
+/* while profiling is enabled every launch of the histogram kernel (the dominant kernel of the path) is
+ * bracketed by its own pair of CUDA events: accumulated device time (ms), number of launches and
+ * number of documents whose bin rows those launches accumulated, since the last reset */
+int qr_hist_kernel_time(qr_ctx *ctx, double *ms, uint64_t *launches, double *docs, int reset);
 /* CUDA-event stopwatch on the context's stream (the stream every kernel of the context is
  * launched on): start records an event, stop records a second one, synchronises and returns the
  * elapsed device time in milliseconds. */

@@ -91,6 +91,7 @@ def lib():
         L.qr_launch_count.argtypes = [vp]
         L.qr_phase_times.argtypes = [vp, dp, u64p, C.c_int]
         L.qr_set_profiling.argtypes = [vp, C.c_int]
+        L.qr_hist_kernel_time.argtypes = [vp, dp, u64p, dp, C.c_int]
         L.qr_timer_start.argtypes = [vp]
         L.qr_timer_stop.argtypes = [vp, dp]
         L.qr_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
@@ -315,6 +316,12 @@ class Trainer:
         ms = C.c_double()
         _check(lib().qr_timer_stop(self.h, C.byref(ms)))
         return ms.value
+
+    def hist_kernel_time(self, reset=False):
+        """(ms, launches, documents) of the histogram kernel since the last reset (profiling mode only)."""
+        ms, ln, docs = C.c_double(), C.c_uint64(), C.c_double()
+        _check(lib().qr_hist_kernel_time(self.h, C.byref(ms), C.byref(ln), C.byref(docs), int(reset)))
+        return ms.value, int(ln.value), docs.value
 
     def phase_times(self, reset=False):
         ms = (C.c_double * 6)()

@@ -150,6 +150,10 @@ struct qr_ctx {
   double phase_ms[qr::kNumPhases] = {0};
   uint64_t phase_launches[qr::kNumPhases] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around each histogram-kernel launch while profiling
+  double histk_ms = 0;
+  uint64_t histk_launches = 0;
+  double histk_docs = 0;                          // documents accumulated by those launches
 
   qr::Comm *comm = nullptr;
   size_t N_global = 0, Q_global = 0;

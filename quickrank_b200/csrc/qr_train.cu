@@ -328,6 +328,8 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_CUDA(cudaEventCreate(&c->ev1));
   QR_CUDA(cudaEventCreate(&c->ev_t0));
   QR_CUDA(cudaEventCreate(&c->ev_t1));
+  QR_CUDA(cudaEventCreate(&c->ev_k0));
+  QR_CUDA(cudaEventCreate(&c->ev_k1));
 
   if (comm_id != nullptr && world > 1) {
     if (c->exact) { set_error("reference-order accumulation (QR_HIST_REFERENCE) is single-GPU only"); return QR_EINVAL; }
@@ -646,6 +648,8 @@ int qr_ctx_destroy(qr_ctx *c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->ev_k0) cudaEventDestroy(c->ev_k0);
+  if (c->ev_k1) cudaEventDestroy(c->ev_k1);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return QR_OK;
@@ -804,6 +808,14 @@ int qr_phase_times(qr_ctx *c, double ms[6], uint64_t launches[6], int reset) {
     if (launches) launches[i] = c->phase_launches[i];
     if (reset) { c->phase_ms[i] = 0; c->phase_launches[i] = 0; }
   }
+  return QR_OK;
+}
+int qr_hist_kernel_time(qr_ctx *c, double *ms, uint64_t *launches, double *docs, int reset) {
+  QR_CHECK_CTX(c);
+  if (ms) *ms = c->histk_ms;
+  if (launches) *launches = c->histk_launches;
+  if (docs) *docs = c->histk_docs;
+  if (reset) { c->histk_ms = 0; c->histk_launches = 0; c->histk_docs = 0; }
   return QR_OK;
 }
 int qr_timer_start(qr_ctx *c) {

@@ -70,7 +70,8 @@ struct NodeHeap {
 
 // Launches the histogram + finalize kernels for the tasks already uploaded to c->d_tasks.
 // `slots_ready`: the slots were already cleared by the one-pass partition kernel.
-static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, bool slots_ready) {
+static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, bool slots_ready,
+                                double built_docs) {
   const uint32_t F = (uint32_t) c->F;
   {
     PhaseTimer pt(c, PH_HIST);
@@ -96,6 +97,7 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
   QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), kHistThreads,   \
             SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
             c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr)
+      if (c->profiling) cudaEventRecord(c->ev_k0, c->stream);
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
         if (use_smem) {
@@ -108,6 +110,15 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
         return QR_OK;
       }));
 #undef QR_HIST_LAUNCH
+      if (c->profiling) {
+        cudaEventRecord(c->ev_k1, c->stream);
+        cudaEventSynchronize(c->ev_k1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1);
+        c->histk_ms += ms;
+        c->histk_launches++;
+        c->histk_docs += built_docs;
+      }
     }
     if (c->comm) QR_TRY(comm_reduce_tasks(c, k, root));
   }
@@ -177,7 +188,7 @@ static int build_root(qr_ctx *c) {
   const uint32_t slices = std::max<uint32_t>(1, (root.n + t.hist_dpb - 1) / t.hist_dpb);
   t.hist_nblk = slices;
   QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
-  QR_TRY(launch_hist_and_scan(c, 1, slices, true, false));
+  QR_TRY(launch_hist_and_scan(c, 1, slices, true, false, (double) root.n));
   root.res = c->h_res[0];
   c->nodes.push_back(root);
   return QR_OK;
@@ -293,7 +304,7 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     }));
   }
   if (build_child_hists) {
-    QR_TRY(launch_hist_and_scan(c, k, hist_blk, false, onepass));
+    QR_TRY(launch_hist_and_scan(c, k, hist_blk, false, onepass, (double) built_total));
   } else if (c->comm) {
     QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     QR_CUDA(cudaStreamSynchronize(c->stream));
