@@ -63,6 +63,10 @@ struct HostNode {
 struct Comm;      // NCCL plumbing (qr_comm.cu)
 struct NodeTask;  // qr_tree_kernels.cuh
 struct LeafSeg;
+struct RoundHdr;
+struct GrowState;
+struct GrowOut;
+struct DevNode;
 
 }  // namespace qr
 
@@ -154,6 +158,17 @@ struct qr_ctx {
   double histk_ms = 0;
   uint64_t histk_launches = 0;
   double histk_docs = 0;                          // documents accumulated by those launches
+
+  // device-driven leaf-wise growth (qr_grow.cuh)
+  bool device_growth = false;               // single GPU, leaf-wise, fixed-point mode
+  qr::RoundHdr *d_hdr = nullptr;            // [2] double-buffered round header
+  qr::GrowState *d_grow = nullptr, *h_grow = nullptr;
+  qr::GrowOut *h_grow_out = nullptr, *d_grow_out = nullptr;   // mapped pinned
+  qr::DevNode *d_nodes = nullptr, *h_nodes = nullptr;         // [max_nodes]; host copy pinned
+  uint32_t max_nodes = 0;
+  uint32_t root_dpb = 0;
+  size_t grow_smem = 0;                     // dynamic shared memory of grow_step_kernel
+  void *d_grow_arrays[7] = {nullptr};       // heap/slots/candidate arrays owned by the grow state
 
   qr::Comm *comm = nullptr;
   size_t N_global = 0, Q_global = 0;

@@ -459,7 +459,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_CUDA(cudaMemset(c->d_part_status, 0, ((N + kPartItems - 1) / kPartItems + mt + 1) * sizeof(unsigned long long)));
   QR_TRY(dev_alloc(&c->d_ticket, 1));
   QR_CUDA(cudaMemset(c->d_ticket, 0, sizeof(uint32_t)));
-  QR_TRY(dev_alloc(&c->d_tasks, mt));
+  QR_TRY(dev_alloc(&c->d_tasks, 2 * mt));   // double-buffered by the device-driven growth
   QR_CUDA(cudaMallocHost((void **) &c->h_tasks, mt * sizeof(NodeTask)));
   QR_TRY(dev_alloc(&c->d_lcount, mt));
   QR_CUDA(cudaMallocHost((void **) &c->h_lcount, mt * sizeof(uint32_t)));
@@ -483,6 +483,45 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_obv_slots, mt));
   QR_TRY(dev_alloc(&c->d_obv_lcounts, mt));
   QR_CUDA(cudaMallocHost((void **) &c->h_obv_lcounts, mt * sizeof(uint64_t)));
+
+  // device-side growth controller (qr_grow.cuh)
+  // opt-in (QR_DEVICE_GROWTH=1): measured on B200 at config 2 the device-side replay costs ~20 us per
+  // round (one GPU thread is a slow place for a heap), about what the host round trip costs, and the
+  // upper-bound grids add a little: 2.1 ms/tree against 1.75 ms/tree for the host-driven rounds.
+  c->device_growth = !c->oblivious && !c->exact && c->comm == nullptr && getenv("QR_DEVICE_GROWTH") != nullptr;
+  c->max_nodes = (uint32_t) (2 * c->nslots + 8);
+  c->grow_smem = grow_smem_bytes(c->max_nodes, (uint32_t) c->nslots, c->max_tasks);
+  if (c->grow_smem > 200 * 1024) c->device_growth = false;   // very large trees: host-driven rounds
+  if (c->device_growth) {
+    cudaFuncSetAttribute(grow_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(c->grow_smem, 48 * 1024));
+    GrowState gs{};
+    gs.nleaves = (uint32_t) maxleaves; gs.max_tasks = c->max_tasks; gs.max_nodes = c->max_nodes;
+    gs.nslots = (uint32_t) c->nslots; gs.exact = 0;
+    gs.n_global = (double) c->N_global;
+    QR_TRY(dev_alloc(&c->d_nodes, c->max_nodes));
+    QR_CUDA(cudaMallocHost((void **) &c->h_nodes, c->max_nodes * sizeof(DevNode)));
+    QR_TRY(dev_alloc(&gs.heap_key, c->max_nodes + 1));
+    QR_TRY(dev_alloc(&gs.heap_val, c->max_nodes + 1));
+    QR_TRY(dev_alloc(&gs.free_slots, (size_t) c->nslots));
+    QR_TRY(dev_alloc(&gs.S, mt));
+    QR_TRY(dev_alloc(&gs.cand_key, c->max_nodes));
+    QR_TRY(dev_alloc(&gs.cand_val, c->max_nodes));
+    QR_TRY(dev_alloc(&gs.stack, c->max_nodes));
+    gs.nodes = c->d_nodes;
+    void *arrs[7] = {gs.heap_key, gs.heap_val, gs.free_slots, gs.S, gs.cand_key, gs.cand_val, gs.stack};
+    memcpy(c->d_grow_arrays, arrs, sizeof(arrs));
+    gs.want_slices = std::max<uint32_t>(1, 148u / c->npanels);
+    gs.max_slices = c->max_slices - c->max_tasks;
+    gs.min_dpb = 2u * kHistThreads;
+    c->h_grow = new GrowState(gs);
+    QR_TRY(dev_alloc(&c->d_grow, 1));
+    QR_CUDA(cudaMemcpy(c->d_grow, &gs, sizeof(gs), cudaMemcpyHostToDevice));
+    QR_TRY(dev_alloc(&c->d_hdr, 2));
+    QR_CUDA(cudaMemset(c->d_hdr, 0, 2 * sizeof(RoundHdr)));
+    QR_CUDA(cudaHostAlloc((void **) &c->h_grow_out, sizeof(GrowOut), cudaHostAllocMapped));
+    QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_grow_out, c->h_grow_out, 0));
+    memset((void *) c->h_grow_out, 0, sizeof(GrowOut));
+  }
 
   // opt in to large dynamic shared memory where needed
   const size_t hist_smem = (size_t) c->fpp * c->max_thr * 12;
@@ -635,7 +674,9 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_partials, c->d_hist_sum, c->d_hist_cnt, c->d_fbest_score, c->d_fbest_t, c->d_res,
                   c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
                   c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done, c->d_part_status,
-                  c->d_ticket, c->d_root_cnt, c->d_fbest_lc, c->d_totals};
+                  c->d_ticket, c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_hdr, c->d_grow, c->d_nodes,
+                  c->d_grow_arrays[0], c->d_grow_arrays[1], c->d_grow_arrays[2], c->d_grow_arrays[3],
+                  c->d_grow_arrays[4], c->d_grow_arrays[5], c->d_grow_arrays[6]};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);
@@ -644,6 +685,9 @@ int qr_ctx_destroy(qr_ctx *c) {
   if (c->h_lcount) cudaFreeHost(c->h_lcount);
   if (c->h_segs) cudaFreeHost(c->h_segs);
   if (c->h_obv_lcounts) cudaFreeHost(c->h_obv_lcounts);
+  if (c->h_nodes) cudaFreeHost(c->h_nodes);
+  delete c->h_grow;
+  if (c->h_grow_out) cudaFreeHost((void *) c->h_grow_out);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);

@@ -96,7 +96,8 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
 #define QR_HIST_LAUNCH(SMEMF, COUNTF)                                                                        \
   QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), kHistThreads,   \
             SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
-            c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr)
+            c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr,             \
+            (const RoundHdr *) nullptr)
       if (c->profiling) cudaEventRecord(c->ev_k0, c->stream);
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
@@ -131,12 +132,12 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
       QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3((F + kFinFeat - 1) / kFinFeat, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
                 c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
                 c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id);
+                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr);
     else
       QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3((F + kFinFeat - 1) / kFinFeat, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
                 c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
                 c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id);
+                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr);
     if (c->comm) {
       QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       QR_CUDA(cudaStreamSynchronize(c->stream));
@@ -219,11 +220,11 @@ static int init_root_counts(qr_ctx *c) {
     if (use_smem)
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, smem, c->d_tasks, 1u,
                 c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr);
     else
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, 0, c->d_tasks, 1u,
                 c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr);
     return QR_OK;
   }));
   QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
@@ -291,7 +292,7 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
         c->part_epoch++;
         QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
                   c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
-                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells);
+                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr);
         c->ticket_base += part_blk;
       } else {
         QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
@@ -497,14 +498,135 @@ static int fit_leaves(qr_ctx *c) {
   } else {
     if (blk > 0)
       QR_LAUNCH(c, PH_LEAF, leaf_partial_kernel, blk, 256, 0, c->d_segs, (uint32_t) nl, c->d_ids[0], c->d_ids[1],
-                c->d_lambda, w, c->d_leaf_partials, c->d_leaf_of_doc);
+                c->d_lambda, w, c->d_leaf_partials, c->d_leaf_of_doc, (const RoundHdr *) nullptr);
     QR_LAUNCH(c, PH_LEAF, leaf_final_kernel, (unsigned) ((nl + 63) / 64), 64, 0, c->d_segs, (uint32_t) nl,
-              c->d_leaf_partials, c->lambda, c->d_leafsum, c->d_leafval);
+              c->d_leaf_partials, c->lambda, c->d_leafsum, c->d_leafval, (const RoundHdr *) nullptr);
     if (c->comm) QR_TRY(comm_leaf_values(c, (uint32_t) nl));
   }
   QR_CUDA(cudaMemcpyAsync(c->h_leafval, c->d_leafval, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   QR_CUDA(cudaStreamSynchronize(c->stream));
   for (size_t k = 0; k < nl; ++k) c->nodes[c->leaves[k]].value = c->h_leafval[k];
+  return QR_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Device-driven leaf-wise growth (qr_grow.cuh): the host only keeps launches queued.
+// ------------------------------------------------------------------------------------------
+static int enqueue_device_round(qr_ctx *c, uint32_t round, bool root) {
+  const uint32_t F = (uint32_t) c->F;
+  const uint32_t mt = c->max_tasks;
+  RoundHdr *hdr = c->d_hdr + (round & 1u), *next_hdr = c->d_hdr + ((round + 1u) & 1u);
+  NodeTask *tasks = c->d_tasks + (size_t) (round & 1u) * mt, *next_tasks = c->d_tasks + (size_t) ((round + 1u) & 1u) * mt;
+  const size_t smem = (size_t) c->fpp * c->max_thr * 12;
+  const bool use_smem = smem <= 200 * 1024;
+  const uint32_t want_slices = c->h_grow->want_slices;
+  if (root) {
+    const uint32_t slices = std::max<uint32_t>(1, ((uint32_t) c->N + c->root_dpb - 1) / c->root_dpb);
+    QR_LAUNCH(c, PH_HIST, prep_slots_kernel, dim3(std::max<uint32_t>(1, std::min<uint32_t>(32, (c->ncells + 1023) / 1024)), 1),
+              256, 0, tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_root_cnt);
+    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+      using B = decltype(tag);
+      if (use_smem)
+        QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, false>), dim3(slices, c->npanels), kHistThreads, smem, tasks, 1u,
+                  c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr);
+      else
+        QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, false>), dim3(slices, c->npanels), kHistThreads, 0, tasks, 1u,
+                  c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr);
+      return QR_OK;
+    }));
+  } else {
+    const uint32_t part_grid = (uint32_t) ((c->N + kPartItems - 1) / kPartItems) + mt;
+    const uint32_t hist_grid = want_slices + mt;
+    c->part_epoch++;
+    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+      using B = decltype(tag);
+      QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_grid, 256, 0, tasks, 0u, c->d_panels, c->N,
+                c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket, 0u, c->part_epoch,
+                c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) hdr);
+      if (use_smem)
+        QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(hist_grid, c->npanels), kHistThreads, smem, tasks, 0u,
+                  c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr);
+      else
+        QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(hist_grid, c->npanels), kHistThreads, 0, tasks, 0u,
+                  c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr);
+      return QR_OK;
+    }));
+  }
+  QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3((F + kFinFeat - 1) / kFinFeat, root ? 1u : mt), 256, 0, tasks,
+            c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score,
+            c->d_fbest_t, c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res,
+            (volatile uint32_t *) nullptr, 0u, (const RoundHdr *) hdr);
+  QR_LAUNCH(c, PH_SCAN, grow_step_kernel, 1, kGrowThreads, c->grow_smem, c->d_grow, hdr, next_hdr, tasks, next_tasks,
+            c->d_res, c->d_ticket, c->d_segs, c->d_grow_out);
+  return QR_OK;
+}
+
+static int fit_leafwise_device(qr_ctx *c, bool want_nodes) {
+  constexpr uint32_t kAhead = 2;   // rounds kept queued beyond the last completed grow_step
+  GrowOut *go = c->h_grow_out;
+  go->steps = 0; go->done = 0; go->error = 0;
+  std::atomic_thread_fence(std::memory_order_seq_cst);
+  c->root_dpb = pick_hist_dpb(c, c->N);
+  QR_LAUNCH(c, PH_HIST, grow_init_kernel, 1, 1, 0, c->d_grow, c->d_hdr, c->d_tasks, (uint32_t) c->N, c->root_dpb, c->d_ticket);
+  QR_TRY(enqueue_device_round(c, 0, true));
+  uint32_t enq = 0;   // growth rounds enqueued (the round after grow_step number enq + 1)
+  uint64_t spins = 0;
+  for (;;) {
+    while (!go->done && enq >= go->steps + kAhead) {
+      if ((++spins & 0xfffff) == 0) {
+        cudaError_t e = cudaStreamQuery(c->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) { set_error("tree growth failed: %s", cudaGetErrorString(e)); return QR_ECUDA; }
+        if (e == cudaSuccess && !go->done && enq >= go->steps + kAhead) {
+          set_error("internal: growth rounds finished without progress (steps %u, enqueued %u)", go->steps, enq);
+          return QR_ECUDA;
+        }
+      }
+    }
+    if (go->done) break;
+    ++enq;
+    QR_TRY(enqueue_device_round(c, enq, false));
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (go->error) {
+    set_error(go->error == 1 ? "internal: histogram pool exhausted" : go->error == 2 ? "internal: node table full"
+                                                                                    : "internal: histogram slice table full");
+    return QR_ECUDA;
+  }
+  c->rho = go->rho; c->sigma = go->sigma; c->beta = go->beta; c->nsplits = go->nsplits; c->nrounds = go->nrounds;
+  // leaf outputs (rt.cc:165-207): the segments were written by the last grow_step
+  const RoundHdr *hdr = c->d_hdr + ((go->steps) & 1u);   // header written by the last step
+  {
+    PhaseTimer pt(c, PH_LEAF);
+    const size_t maxleaves = std::max<size_t>(c->p.nleaves, 1);
+    const uint32_t leaf_grid = (uint32_t) ((c->N + kLeafItems - 1) / kLeafItems + maxleaves);
+    const double *w = c->lambda ? c->d_weight : nullptr;
+    QR_LAUNCH(c, PH_LEAF, leaf_partial_kernel, leaf_grid, 256, 0, c->d_segs, 0u, c->d_ids[0], c->d_ids[1], c->d_lambda, w,
+              c->d_leaf_partials, c->d_leaf_of_doc, hdr);
+    QR_LAUNCH(c, PH_LEAF, leaf_final_kernel, (unsigned) ((maxleaves + 63) / 64), 64, 0, c->d_segs, 0u, c->d_leaf_partials,
+              c->lambda, c->d_leafsum, c->d_leafval, hdr);
+  }
+  c->nodes.clear();
+  c->leaves.clear();
+  if (want_nodes) {   // the caller wants the tree on the host
+    const uint32_t nn = go->nnodes, nl = go->nleaves;
+    QR_CUDA(cudaMemcpyAsync(c->h_nodes, c->d_nodes, nn * sizeof(DevNode), cudaMemcpyDeviceToHost, c->stream));
+    QR_CUDA(cudaMemcpyAsync(c->h_leafval, c->d_leafval, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    QR_CUDA(cudaStreamSynchronize(c->stream));
+    c->nodes.resize(nn);
+    for (uint32_t i = 0; i < nn; ++i) {
+      const DevNode &d = c->h_nodes[i];
+      HostNode &h = c->nodes[i];
+      h.lo = d.lo; h.n = d.n; h.buf = d.buf; h.hist = -1; h.left = d.left; h.right = d.right;
+      h.expanded = d.expanded != 0; h.pushed = d.pushed != 0; h.res = d.res;
+    }
+    collect_leaves(c, 0);
+    for (size_t k = 0; k < c->leaves.size(); ++k) c->nodes[c->leaves[k]].value = c->h_leafval[k];
+  }
   return QR_OK;
 }
 
@@ -520,6 +642,23 @@ static int fit_tree(qr_ctx *c, qr_flat_tree *out) {
   c->has_tree = false;
 
   QR_TRY(prepare_fixed_point(c));
+  if (c->device_growth && !c->profiling) {
+    QR_TRY(fit_leafwise_device(c, out != nullptr));
+    c->has_tree = true;
+    if (out) {
+      const uint32_t nn = count_reachable(c, 0);
+      if (out->capacity < nn) { set_error("qr_flat_tree capacity %u < %u nodes", out->capacity, nn); return QR_EINVAL; }
+      uint32_t next = 0;
+      flatten(c, 0, out, &next);
+      out->nnodes = nn;
+      out->nleaves = (uint32_t) c->leaves.size();
+    }
+    return QR_OK;
+  }
+  if (c->device_growth) {   // the device-driven path leaves the partition ticket counter at an arbitrary value
+    QR_CUDA(cudaMemsetAsync(c->d_ticket, 0, sizeof(uint32_t), c->stream));
+    c->ticket_base = 0;
+  }
   QR_TRY(build_root(c));
   QR_TRY(c->oblivious ? fit_oblivious(c) : fit_leafwise(c));
 

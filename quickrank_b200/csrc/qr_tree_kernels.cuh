@@ -6,6 +6,7 @@
 
 #include "qr_kernels.cuh"
 #include "qr_task.cuh"
+#include "qr_grow.cuh"
 
 namespace qr {
 
@@ -162,15 +163,19 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
                          size_t N, const uint32_t *__restrict__ ids0, const uint32_t *__restrict__ ids1,
                          uint32_t *out0, uint32_t *out1, unsigned long long *status, uint32_t *ticket,
                          uint32_t ticket_base, uint32_t epoch, unsigned long long *hsum, uint32_t *hcnt,
-                         uint32_t ncells) {
+                         uint32_t ncells, const RoundHdr *__restrict__ hdr) {
   __shared__ uint32_t s_vb, s_task, s_prefix;
   __shared__ uint32_t wc[8][8];
+  // device-driven growth (qr_grow.cuh): the grid is an upper bound, the header has the real counts
+  const uint32_t nblocks = hdr ? hdr->part_blocks : 0xffffffffu;
+  if (hdr) ntasks = hdr->ntasks;
   if (threadIdx.x == 0) {
     s_vb = atomicAdd(ticket, 1u) - ticket_base;
-    s_task = find_task_by(tasks, ntasks, s_vb, false);
+    s_task = s_vb < nblocks ? find_task_by(tasks, ntasks, s_vb, false) : 0u;
   }
   __syncthreads();
   const uint32_t vb = s_vb;
+  if (vb >= nblocks) return;
   const NodeTask t = tasks[s_task];
   const uint32_t lb = vb - t.part_blk0;
   const uint32_t nb = max(1u, (t.n + kPartItems - 1) / kPartItems);
@@ -330,12 +335,17 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
                  const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ ids0,
                  const uint32_t *__restrict__ ids1, const long long *__restrict__ lamq,
                  const uint32_t *__restrict__ thr_off, uint32_t F, unsigned long long *hsum,
-                 uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials, uint32_t stride) {
+                 uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials, uint32_t stride,
+                 const RoundHdr *__restrict__ hdr) {
   constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ uint32_t s_base[FPP + 1];
   __shared__ uint32_t s_task;
   __shared__ U128 s_sq[kHistThreads / 32];
+  if (hdr) {   // device-driven growth: upper-bound grid
+    if (blockIdx.x >= hdr->hist_slices) return;
+    ntasks = hdr->ntasks;
+  }
   if (threadIdx.x == 0) s_task = find_task_by(tasks, ntasks, blockIdx.x, true);
   __syncthreads();
   const NodeTask t = tasks[s_task];
@@ -572,8 +582,9 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
                 const int *__restrict__ qexp, double *fbest_score, uint32_t *fbest_t, uint32_t *fbest_lc,
                 ulonglong2 *totals, const ulonglong2 *__restrict__ sq128,
                 const double *__restrict__ sq_exact, uint32_t *task_done, SplitResult *res,
-                volatile uint32_t *host_flags, uint32_t round_id) {
+                volatile uint32_t *host_flags, uint32_t round_id, const RoundHdr *__restrict__ hdr) {
   const uint32_t task = blockIdx.y;
+  if (hdr && task >= hdr->ntasks) return;   // device-driven growth: upper-bound grid
   const NodeTask t = tasks[task];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t f = blockIdx.x * kFinFeat + warp;
@@ -828,17 +839,20 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
 // Leaf outputs (RegressionTree::update_output, rt.cc:165-207) and score update
 // (Mart::update_modelscores, mart.cc:459-468).
 // ------------------------------------------------------------------------------------------
-struct LeafSeg { uint32_t lo, n; uint32_t buf; uint32_t blk0; };  // buf 2 = identity (unsplit root)
 
-constexpr uint32_t kLeafItems = 4096;   // documents per block of the FAST leaf pass
 
 // FAST: per (leaf, chunk) partial sums with a fixed tree shape; also writes the doc -> leaf map.
 __global__ void __launch_bounds__(256)
 leaf_partial_kernel(const LeafSeg *__restrict__ segs, uint32_t nleaves, const uint32_t *__restrict__ ids0,
                     const uint32_t *__restrict__ ids1, const double *__restrict__ lam,
-                    const double *__restrict__ wgt, double2 *partials, uint32_t *__restrict__ leaf_of_doc) {
+                    const double *__restrict__ wgt, double2 *partials, uint32_t *__restrict__ leaf_of_doc,
+                    const RoundHdr *__restrict__ hdr) {
   __shared__ uint32_t s_leaf;
   __shared__ double p1[256], p2[256];
+  if (hdr) {   // device-driven growth: upper-bound grid, counts in the header
+    if (blockIdx.x >= hdr->leaf_blocks) return;
+    nleaves = hdr->nleaves;
+  }
   if (threadIdx.x == 0) {
     uint32_t lo = 0, hi = nleaves - 1;
     while (lo < hi) {
@@ -870,7 +884,8 @@ leaf_partial_kernel(const LeafSeg *__restrict__ segs, uint32_t nleaves, const ui
 
 __global__ void leaf_final_kernel(const LeafSeg *__restrict__ segs, uint32_t nleaves,
                                   const double2 *__restrict__ partials, bool newton, double2 *leafsum,
-                                  double *leafval) {
+                                  double *leafval, const RoundHdr *__restrict__ hdr) {
+  if (hdr) nleaves = hdr->nleaves;
   const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
   if (leaf >= nleaves) return;
   const LeafSeg sg = segs[leaf];
