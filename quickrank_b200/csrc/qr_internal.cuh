@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/quickrank_b200.h"
+#include "qr_task.cuh"
 
 namespace qr {
 
@@ -61,7 +62,6 @@ struct HostNode {
 };
 
 struct Comm;      // NCCL plumbing (qr_comm.cu)
-struct NodeTask;  // qr_tree_kernels.cuh
 struct LeafSeg;
 struct RoundHdr;
 struct GrowState;
@@ -122,6 +122,7 @@ struct qr_ctx {
   std::vector<int> free_slots;
   uint32_t max_tasks = 0;                   // node expansions per round
   qr::NodeTask *d_tasks = nullptr, *h_tasks = nullptr;   // [max_tasks] (host copy pinned)
+  qr::TaskPack pack{};                      // task records of a small round, passed as kernel parameters
   uint32_t *d_lcount = nullptr, *h_lcount = nullptr;     // [max_tasks] local left counts
   double *d_fbest_score = nullptr;          // [max_tasks][2][F]
   uint32_t *d_fbest_t = nullptr;            // [max_tasks][2][F]

@@ -28,6 +28,11 @@ struct NodeTask {
   double parent_squares;
 };
 
+// Small rounds carry their task records inside the kernel parameters (constant bank): no
+// host-to-device copy sits between the host's decision and the round's first kernel.
+constexpr uint32_t kPackTasks = 12;
+struct TaskPack { uint32_t n; uint32_t pad; NodeTask t[kPackTasks]; };
+
 constexpr uint32_t kPartItems = 2048;   // documents per partition block
 constexpr uint32_t kSqParts = 16;       // squares partials per task (FAST)
 

@@ -463,9 +463,9 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_CUDA(cudaMallocHost((void **) &c->h_tasks, mt * sizeof(NodeTask)));
   QR_TRY(dev_alloc(&c->d_lcount, mt));
   QR_CUDA(cudaMallocHost((void **) &c->h_lcount, mt * sizeof(uint32_t)));
-  QR_TRY(dev_alloc(&c->d_fbest_score, mt * 2 * F));
-  QR_TRY(dev_alloc(&c->d_fbest_t, mt * 2 * F));
-  QR_TRY(dev_alloc(&c->d_fbest_lc, mt * 2 * F));
+  QR_TRY(dev_alloc(&c->d_fbest_score, mt * 2 * F * kFinParts));
+  QR_TRY(dev_alloc(&c->d_fbest_t, mt * 2 * F * kFinParts));
+  QR_TRY(dev_alloc(&c->d_fbest_lc, mt * 2 * F * kFinParts));
   QR_TRY(dev_alloc(&c->d_totals, mt * 2));
   QR_TRY(dev_alloc(&c->d_res, mt * 2));
   QR_CUDA(cudaHostAlloc((void **) &c->h_res, mt * 2 * sizeof(SplitResult), cudaHostAllocMapped));

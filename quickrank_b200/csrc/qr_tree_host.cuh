@@ -70,9 +70,23 @@ struct NodeHeap {
 
 // Launches the histogram + finalize kernels for the tasks already uploaded to c->d_tasks.
 // `slots_ready`: the slots were already cleared by the one-pass partition kernel.
+// QR_TRACE=1: GPU timeline of the growth rounds (events between the kernels of a round), printed per tree
+struct RoundTrace {
+  std::vector<cudaEvent_t> ev;   // 4 per round: start, after partition, after histogram, after finalize
+  size_t used = 0;
+  cudaEvent_t next() {
+    if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
+    return ev[used++];
+  }
+};
+static RoundTrace g_trace;
+static const bool g_trace_on = getenv("QR_TRACE") != nullptr;
+#define QR_TRACE_MARK(c) do { if (g_trace_on) cudaEventRecord(g_trace.next(), (c)->stream); } while (0)
+
 static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, bool slots_ready,
                                 double built_docs) {
   const uint32_t F = (uint32_t) c->F;
+  if (root) { QR_TRACE_MARK(c); QR_TRACE_MARK(c); }
   {
     PhaseTimer pt(c, PH_HIST);
     const bool static_counts = root && !c->exact && c->d_root_cnt != nullptr;
@@ -97,7 +111,7 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
   QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), kHistThreads,   \
             SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
             c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr,             \
-            (const RoundHdr *) nullptr)
+            (const RoundHdr *) nullptr, c->pack)
       if (c->profiling) cudaEventRecord(c->ev_k0, c->stream);
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
@@ -123,21 +137,23 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
     }
     if (c->comm) QR_TRY(comm_reduce_tasks(c, k, root));
   }
+  QR_TRACE_MARK(c);
   {
     PhaseTimer pt(c, PH_SCAN);
     // results are written straight into mapped pinned host memory and announced through per-task
     // flags the host polls: no device-to-host copy and no stream synchronisation on the round path
     c->round_id++;
     if (c->exact)
-      QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3((F + kFinFeat - 1) / kFinFeat, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
+      QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3(fin_blocks(F), k), kFinWarps * 32, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
                 c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
                 c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr);
+                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack);
     else
-      QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3((F + kFinFeat - 1) / kFinFeat, k), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
+      QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3(fin_blocks(F), k), kFinWarps * 32, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
                 c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
                 c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr);
+                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack);
+    QR_TRACE_MARK(c);
     if (c->comm) {
       QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       QR_CUDA(cudaStreamSynchronize(c->stream));
@@ -220,11 +236,11 @@ static int init_root_counts(qr_ctx *c) {
     if (use_smem)
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, smem, c->d_tasks, 1u,
                 c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr, c->pack);
     else
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, 0, c->d_tasks, 1u,
                 c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr, c->pack);
     return QR_OK;
   }));
   QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
@@ -282,8 +298,16 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     t.fused_sq = 1;
     t.parent_squares = nd.res.squares;
   }
-  QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
+  QR_TRACE_MARK(c);
   const bool onepass = c->comm == nullptr;
+  c->pack.n = 0;
+  if (onepass && !c->exact && build_child_hists && k <= kPackTasks) {
+    // small round: the task records travel in the kernel parameters
+    c->pack.n = k;
+    memcpy(c->pack.t, c->h_tasks, k * sizeof(NodeTask));
+  } else {
+    QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
+  }
   {
     PhaseTimer pt(c, PH_PARTITION);
     QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
@@ -292,7 +316,7 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
         c->part_epoch++;
         QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
                   c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
-                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr);
+                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack);
         c->ticket_base += part_blk;
       } else {
         QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
@@ -304,12 +328,14 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
       return QR_OK;
     }));
   }
+  QR_TRACE_MARK(c);
   if (build_child_hists) {
     QR_TRY(launch_hist_and_scan(c, k, hist_blk, false, onepass, (double) built_total));
   } else if (c->comm) {
     QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     QR_CUDA(cudaStreamSynchronize(c->stream));
   }
+  c->pack.n = 0;
   for (uint32_t j = 0; j < k; ++j) {
     const int i = S[j];
     const NodeTask &t = c->h_tasks[j];
@@ -530,11 +556,11 @@ static int enqueue_device_round(qr_ctx *c, uint32_t round, bool root) {
       if (use_smem)
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, false>), dim3(slices, c->npanels), kHistThreads, smem, tasks, 1u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr);
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack);
       else
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, false>), dim3(slices, c->npanels), kHistThreads, 0, tasks, 1u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr);
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack);
       return QR_OK;
     }));
   } else {
@@ -545,22 +571,22 @@ static int enqueue_device_round(qr_ctx *c, uint32_t round, bool root) {
       using B = decltype(tag);
       QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_grid, 256, 0, tasks, 0u, c->d_panels, c->N,
                 c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket, 0u, c->part_epoch,
-                c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) hdr);
+                c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) hdr, c->pack);
       if (use_smem)
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(hist_grid, c->npanels), kHistThreads, smem, tasks, 0u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr);
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack);
       else
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(hist_grid, c->npanels), kHistThreads, 0, tasks, 0u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr);
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack);
       return QR_OK;
     }));
   }
-  QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3((F + kFinFeat - 1) / kFinFeat, root ? 1u : mt), 256, 0, tasks,
+  QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3(fin_blocks(F), root ? 1u : mt), kFinWarps * 32, 0, tasks,
             c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score,
             c->d_fbest_t, c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res,
-            (volatile uint32_t *) nullptr, 0u, (const RoundHdr *) hdr);
+            (volatile uint32_t *) nullptr, 0u, (const RoundHdr *) hdr, c->pack);
   QR_LAUNCH(c, PH_SCAN, grow_step_kernel, 1, kGrowThreads, c->grow_smem, c->d_grow, hdr, next_hdr, tasks, next_tasks,
             c->d_res, c->d_ticket, c->d_segs, c->d_grow_out);
   return QR_OK;
@@ -672,6 +698,22 @@ static int fit_tree(qr_ctx *c, qr_flat_tree *out) {
   collect_leaves(c, 0);
   QR_TRY(fit_leaves(c));
   c->has_tree = true;
+  if (g_trace_on && g_trace.used >= 4) {
+    cudaStreamSynchronize(c->stream);
+    double tp = 0, th = 0, tf = 0, tg = 0;
+    const size_t nr = g_trace.used / 4;
+    for (size_t r = 0; r < nr; ++r) {
+      float a = 0, b = 0, d = 0, g = 0;
+      cudaEventElapsedTime(&a, g_trace.ev[4 * r], g_trace.ev[4 * r + 1]);
+      cudaEventElapsedTime(&b, g_trace.ev[4 * r + 1], g_trace.ev[4 * r + 2]);
+      cudaEventElapsedTime(&d, g_trace.ev[4 * r + 2], g_trace.ev[4 * r + 3]);
+      if (r + 1 < nr) cudaEventElapsedTime(&g, g_trace.ev[4 * r + 3], g_trace.ev[4 * r + 4]);
+      tp += a; th += b; tf += d; tg += g;
+      if (getenv("QR_TRACE_ROUNDS")) fprintf(stderr, "[trace] round %2zu: partition %6.1f hist %6.1f finalize %6.1f gap-to-next %6.1f us\n", r, a * 1e3, b * 1e3, d * 1e3, g * 1e3);
+    }
+    fprintf(stderr, "[trace] %zu rounds: partition %.0f hist %.0f finalize %.0f gaps %.0f us\n", nr, tp * 1e3, th * 1e3, tf * 1e3, tg * 1e3);
+    g_trace.used = 0;
+  }
 
   if (out) {
     const uint32_t nn = count_reachable(c, 0);

@@ -163,7 +163,8 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
                          size_t N, const uint32_t *__restrict__ ids0, const uint32_t *__restrict__ ids1,
                          uint32_t *out0, uint32_t *out1, unsigned long long *status, uint32_t *ticket,
                          uint32_t ticket_base, uint32_t epoch, unsigned long long *hsum, uint32_t *hcnt,
-                         uint32_t ncells, const RoundHdr *__restrict__ hdr) {
+                         uint32_t ncells, const RoundHdr *__restrict__ hdr, const __grid_constant__ TaskPack pack) {
+  if (pack.n) tasks = pack.t;
   __shared__ uint32_t s_vb, s_task, s_prefix;
   __shared__ uint32_t wc[8][8];
   // device-driven growth (qr_grow.cuh): the grid is an upper bound, the header has the real counts
@@ -336,7 +337,8 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
                  const uint32_t *__restrict__ ids1, const long long *__restrict__ lamq,
                  const uint32_t *__restrict__ thr_off, uint32_t F, unsigned long long *hsum,
                  uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials, uint32_t stride,
-                 const RoundHdr *__restrict__ hdr) {
+                 const RoundHdr *__restrict__ hdr, const __grid_constant__ TaskPack pack) {
+  if (pack.n) tasks = pack.t;
   constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ uint32_t s_base[FPP + 1];
@@ -573,75 +575,105 @@ __device__ __forceinline__ double cell_value(bool exact, unsigned long long raw,
   return exact ? __longlong_as_double((long long) raw) : (double) (long long) raw * inv;
 }
 
-constexpr uint32_t kFinFeat = 8;   // features (= warps) per finalize block
+constexpr uint32_t kFinWarps = 9;   // warps per finalize block
+// Each feature is shared by kFinParts warps: every one of them forms the whole cumulative histogram
+// (cheap), but evaluates the split score — two FP64 divisions per cell and child — only for its own
+// third of the bins.  A (task, feature) is ~2300 dependent instructions for a single warp, and small
+// growth rounds have far fewer (task, feature) pairs than the GPU has schedulers, so the serial
+// chain, not throughput, sets the kernel's duration.
+constexpr uint32_t kFinParts = 3;
+__host__ __device__ inline uint32_t fin_blocks(uint32_t F) { return (F * kFinParts + kFinWarps - 1) / kFinWarps; }
 
 template <bool EXACT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kFinWarps * 32)
 finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, uint32_t *hcnt,
                 uint32_t ncells, const uint32_t *__restrict__ thr_off, uint32_t F, uint32_t minls,
                 const int *__restrict__ qexp, double *fbest_score, uint32_t *fbest_t, uint32_t *fbest_lc,
                 ulonglong2 *totals, const ulonglong2 *__restrict__ sq128,
                 const double *__restrict__ sq_exact, uint32_t *task_done, SplitResult *res,
-                volatile uint32_t *host_flags, uint32_t round_id, const RoundHdr *__restrict__ hdr) {
+                volatile uint32_t *host_flags, uint32_t round_id, const RoundHdr *__restrict__ hdr,
+                const __grid_constant__ TaskPack pack) {
+  if (pack.n) tasks = pack.t;
   const uint32_t task = blockIdx.y;
   if (hdr && task >= hdr->ntasks) return;   // device-driven growth: upper-bound grid
   const NodeTask t = tasks[task];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  const uint32_t f = blockIdx.x * kFinFeat + warp;
+  const uint32_t gw = blockIdx.x * kFinWarps + warp;
+  const uint32_t f = gw / kFinParts, part = gw % kFinParts;
   const double inv = EXACT ? 1.0 : ldexp(1.0, -*qexp);
   const int nchild = t.whole ? 1 : 2;
-  __shared__ double wb[8];
-  __shared__ uint32_t wt[8], wt2[8], wl2[8];
+  __shared__ double wb[kFinWarps];
+  __shared__ uint32_t wt[kFinWarps], wt2[kFinWarps], wl2[kFinWarps];
   __shared__ uint32_t s_last;
 
-  // one warp per feature; no block-level synchronisation on this path.  Features with at most
-  // kFinChunks * 32 cells are processed entirely in registers: every load is issued up front.
-  if (f < F) {
-    const uint32_t c0 = thr_off[f], cells = thr_off[f + 1] - c0;
-    unsigned long long *Bs = hsum + (size_t) t.slotB * ncells + c0;
-    uint32_t *Bc = hcnt + (size_t) t.slotB * ncells + c0;
-    const bool two = nchild == 2;
-    const unsigned long long *Ps = two ? hsum + (size_t) t.slotP * ncells + c0 : Bs;
-    const uint32_t *Pc = two ? hcnt + (size_t) t.slotP * ncells + c0 : Bc;
-    unsigned long long *Ds = two ? hsum + (size_t) t.slotD * ncells + c0 : Bs;
-    uint32_t *Dc = two ? hcnt + (size_t) t.slotD * ncells + c0 : Bc;
-    constexpr int kFinChunks = 9;
-    if (cells <= kFinChunks * 32) {
-      unsigned long long bs[kFinChunks], ps[kFinChunks];
-      uint32_t bc[kFinChunks], pc[kFinChunks];
+  // Features with at most kFinChunks * 32 cells are processed entirely in registers: every load is
+  // issued up front.  The kFinParts warps of a feature sit in the same block (kFinWarps is a multiple
+  // of kFinParts): they all read the raw bins of the built child before any of them overwrites its
+  // share with the cumulative values, hence the block barrier between loading and storing.
+  static_assert(kFinWarps % kFinParts == 0, "the warps sharing a feature must share a block");
+  constexpr int kFinChunks = 9;
+  static_assert(kFinChunks % kFinParts == 0, "chunks are dealt to the parts in equal contiguous runs");
+  constexpr int kOwn = kFinChunks / kFinParts;
+  const bool active = f < F;
+  const uint32_t c0 = active ? thr_off[f] : 0u, cells = active ? thr_off[f + 1] - c0 : 0u;
+  unsigned long long *Bs = hsum + (size_t) t.slotB * ncells + c0;
+  uint32_t *Bc = hcnt + (size_t) t.slotB * ncells + c0;
+  const bool two = nchild == 2;
+  const unsigned long long *Ps = two ? hsum + (size_t) t.slotP * ncells + c0 : Bs;
+  const uint32_t *Pc = two ? hcnt + (size_t) t.slotP * ncells + c0 : Bc;
+  unsigned long long *Ds = two ? hsum + (size_t) t.slotD * ncells + c0 : Bs;
+  uint32_t *Dc = two ? hcnt + (size_t) t.slotD * ncells + c0 : Bc;
+  const bool regpath = active && cells <= kFinChunks * 32;
+  unsigned long long bs[kFinChunks], ps[kFinChunks];
+  uint32_t bc[kFinChunks], pc[kFinChunks];
+  const uint32_t lastk = cells - 1;
+  unsigned long long plast = 0ull, blast = 0ull;
+  uint32_t pclast = 0u, bclast = 0u;
+  if (regpath) {
 #pragma unroll
-      for (int ch = 0; ch < kFinChunks; ++ch) {
-        const uint32_t k = ch * 32 + lane;
-        const bool in = k < cells;
-        bs[ch] = in ? Bs[k] : 0ull;
-        bc[ch] = in ? Bc[k] : 0u;
-        ps[ch] = (in && two) ? Ps[k] : 0ull;
-        pc[ch] = (in && two) ? Pc[k] : 0u;
-      }
+    for (int ch = 0; ch < kFinChunks; ++ch) {
+      const uint32_t k = ch * 32 + lane;
+      const bool own = (uint32_t) (ch / kOwn) == part;
+      const bool in = k < cells && (!EXACT || own);   // FAST: the prefix needs every bin of the built child
+      bs[ch] = in ? Bs[k] : 0ull;
+      bc[ch] = in ? Bc[k] : 0u;
+      ps[ch] = (in && two && own) ? Ps[k] : 0ull;
+      pc[ch] = (in && two && own) ? Pc[k] : 0u;
+    }
+    // last bins (node totals): parent's from memory, built child's from memory (EXACT) or the prefix
+    plast = two ? Ps[lastk] : 0ull;
+    pclast = two ? Pc[lastk] : 0u;
+    blast = EXACT ? Bs[lastk] : 0ull;
+    bclast = EXACT ? Bc[lastk] : 0u;
+  }
+  __syncthreads();
+  if (active) {
+    if (regpath) {
+      // chunk ch holds cells ch * 32 + lane (coalesced).  The nine 5-step warp scans are independent
+      // (their shuffles overlap); the running carry between chunks is added afterwards
       if (!EXACT) {   // inclusive prefix over bins (rtnode_histogram.cc:59-62), exact in fixed point
-        long long carry = 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+          for (int ch = 0; ch < kFinChunks; ++ch) {
+            const unsigned long long pv = __shfl_up_sync(0xffffffffu, bs[ch], o);
+            const uint32_t pcv = __shfl_up_sync(0xffffffffu, bc[ch], o);
+            if ((int) lane >= o) { bs[ch] += pv; bc[ch] += pcv; }
+          }
+        }
+        unsigned long long carry = 0;
         uint32_t carryc = 0;
 #pragma unroll
         for (int ch = 0; ch < kFinChunks; ++ch) {
-          long long v = (long long) bs[ch];
-          uint32_t cv = bc[ch];
-          for (int o = 1; o < 32; o <<= 1) {
-            const long long pv = __shfl_up_sync(0xffffffffu, v, o);
-            const uint32_t pcv = __shfl_up_sync(0xffffffffu, cv, o);
-            if ((int) lane >= o) { v += pv; cv += pcv; }
-          }
-          v += carry; cv += carryc;
-          bs[ch] = (unsigned long long) v; bc[ch] = cv;
-          carry = __shfl_sync(0xffffffffu, v, 31);
-          carryc = __shfl_sync(0xffffffffu, cv, 31);
-        }
-#pragma unroll
-        for (int ch = 0; ch < kFinChunks; ++ch) {
+          const unsigned long long tot = __shfl_sync(0xffffffffu, bs[ch], 31);
+          const uint32_t totc = __shfl_sync(0xffffffffu, bc[ch], 31);
+          bs[ch] += carry; bc[ch] += carryc;
+          carry += tot; carryc += totc;
           const uint32_t k = ch * 32 + lane;
-          if (k < cells) { Bs[k] = bs[ch]; Bc[k] = bc[ch]; }
+          if (k < cells && (uint32_t) (ch / kOwn) == part) { Bs[k] = bs[ch]; Bc[k] = bc[ch]; }
         }
+        blast = carry; bclast = carryc;   // bins past the last one are empty: the running total is the node total
       }
-      const uint32_t lastk = cells - 1;
       for (int pass = 0; pass < nchild; ++pass) {
         if (pass == 1) {   // derived child = parent - built (rtnode_histogram.cc:79-85, 209-216)
 #pragma unroll
@@ -655,18 +687,18 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
               bs[ch] = ps[ch] - bs[ch];
             }
             bc[ch] = pc[ch] - bc[ch];
-            if (k < cells) { Ds[k] = bs[ch]; Dc[k] = bc[ch]; }
+            if (k < cells && (uint32_t) (ch / kOwn) == part) { Ds[k] = bs[ch]; Dc[k] = bc[ch]; }
           }
         }
-        // totals live in the lane/chunk that owns the last cell
-        unsigned long long sraw = 0;
-        uint32_t cn = 0;
-#pragma unroll
-        for (int ch = 0; ch < kFinChunks; ++ch)
-          if ((uint32_t) ch == lastk / 32) {
-            sraw = __shfl_sync(0xffffffffu, bs[ch], lastk % 32);
-            cn = __shfl_sync(0xffffffffu, bc[ch], lastk % 32);
-          }
+        // node totals = last bin of the child being scanned
+        unsigned long long sraw = blast;
+        uint32_t cn = bclast;
+        if (pass == 1) {
+          if (EXACT) sraw = (unsigned long long) __double_as_longlong(__longlong_as_double((long long) plast) -
+                                                                      __longlong_as_double((long long) blast));
+          else sraw = plast - blast;
+          cn = pclast - bclast;
+        }
         const double s = cell_value(EXACT, sraw, inv);
         // split scan (rt.cc:272-291): strict '>' in ascending t, start value -1
         double best = -1.0;
@@ -675,7 +707,7 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
         for (int ch = 0; ch < kFinChunks; ++ch) {
           const uint32_t k = ch * 32 + lane;
           const uint32_t lc = bc[ch], rc = cn - lc;
-          if (k < cells && lc >= minls && rc >= minls) {
+          if ((uint32_t) (ch / kOwn) == part && k < cells && lc >= minls && rc >= minls) {
             const double ls = cell_value(EXACT, bs[ch], inv);
             const double rs = s - ls;
             const double score = ls * ls / (double) lc + rs * rs / (double) rc;
@@ -691,14 +723,21 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
         if (lane == 0) {
           // pass 0 scanned the built child, pass 1 the derived one; child 0 = left
           const int child = t.whole ? 0 : ((pass == 0) == (t.build_left != 0) ? 0 : 1);
-          const size_t o = ((size_t) task * 2 + child) * F + f;
+          const size_t o = (((size_t) task * 2 + child) * F + f) * kFinParts + part;
           fbest_score[o] = best;
           fbest_t[o] = best_t;
           fbest_lc[o] = best_lc;
           // node size and sum are read from feature 0's last bin (rtnode.h:99-104)
-          if (f == 0) totals[(size_t) task * 2 + child] = make_ulonglong2((unsigned long long) cn, sraw);
+          if (f == 0 && part == 0) totals[(size_t) task * 2 + child] = make_ulonglong2((unsigned long long) cn, sraw);
         }
       }
+    } else if (part != 0) {
+      // wide features (more than kFinChunks * 32 bins) are handled whole by part 0
+      if (lane == 0)
+        for (int child = 0; child < nchild; ++child) {
+          const size_t o = (((size_t) task * 2 + child) * F + f) * kFinParts + part;
+          fbest_score[o] = -1.0; fbest_t[o] = 0xffffffffu; fbest_lc[o] = 0;
+        }
     } else {
       if (!EXACT) {
         long long carry = 0;
@@ -759,7 +798,7 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
         }
         if (lane == 0) {
           const int child = t.whole ? 0 : ((pass == 0) == (t.build_left != 0) ? 0 : 1);
-          const size_t o = ((size_t) task * 2 + child) * F + f;
+          const size_t o = (((size_t) task * 2 + child) * F + f) * kFinParts;
           fbest_score[o] = best;
           fbest_t[o] = best_t;
           fbest_lc[o] = best_lc;
@@ -787,13 +826,16 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
     const double inv2 = ldexp(1.0, -2 * *qexp);
     sqB = ((double) tot.hi * 18446744073709551616.0 + (double) tot.lo) * inv2;
   }
+  // entries are ordered by (feature, part) = (feature, ascending threshold range): the first maximum
+  // in that order is the reference's winner
+  const uint32_t FP = F * kFinParts;
   for (int child = 0; child < nchild; ++child) {
-    const volatile double *fs = fbest_score + ((size_t) task * 2 + child) * F;
-    const volatile uint32_t *ft = fbest_t + ((size_t) task * 2 + child) * F;
-    const volatile uint32_t *fl = fbest_lc + ((size_t) task * 2 + child) * F;
+    const volatile double *fs = fbest_score + ((size_t) task * 2 + child) * FP;
+    const volatile uint32_t *ft = fbest_t + ((size_t) task * 2 + child) * FP;
+    const volatile uint32_t *fl = fbest_lc + ((size_t) task * 2 + child) * FP;
     double best = -1.0;
     uint32_t bf = 0xffffffffu, bt = 0xffffffffu, blc = 0;
-    for (uint32_t ff = threadIdx.x; ff < F; ff += 256) {
+    for (uint32_t ff = threadIdx.x; ff < FP; ff += kFinWarps * 32) {
       const double sc = fs[ff];
       if (sc > best) { best = sc; bf = ff; bt = ft[ff]; blc = fl[ff]; }
     }
@@ -807,7 +849,7 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
     if (lane == 0) { wb[warp] = best; wt[warp] = bf; wt2[warp] = bt; wl2[warp] = blc; }
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; ++w)
+      for (int w = 1; w < (int) kFinWarps; ++w)
         if (wb[w] > best || (wb[w] == best && wt[w] < bf)) { best = wb[w]; bf = wt[w]; bt = wt2[w]; blc = wl2[w]; }
       const bool built = t.whole || ((child == 0) == (t.build_left != 0));
       const volatile ulonglong2 *tv = totals + (size_t) task * 2 + child;
@@ -818,7 +860,7 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
       r.deviance = r.squares - r.sum * r.sum / (double) r.n;      // rtnode.h:106
       r.score = best;
       r.valid = best != -1.0;
-      r.feature = bf;
+      r.feature = bf == 0xffffffffu ? bf : bf / kFinParts;
       r.threshold_idx = r.valid ? bt : 0xffffffffu;
       r.lcount = r.valid ? blc : 0;
       r.pad = 0;
