@@ -229,6 +229,9 @@ class Ensemble {
   quickrank::Score score_instance(const quickrank::Feature *d, size_t offset = 1) const;
   std::vector<double> get_weights() const;
   bool update_ensemble_weights(std::vector<double> &weights);
+  // ensemble.cc:149-188: set the weights, optionally dropping the trees whose weight became 0
+  bool update_ensemble_weights(std::vector<double> &weights, bool remove);
+  bool filter_out_zero_weighted_trees();
   void write_xml(std::ostream &os, int indent) const;   // <ensemble>...</ensemble> (ensemble.cc:133-147)
 
  private:
@@ -362,6 +365,69 @@ class ObliviousLambdaMart : public ObliviousMart {
 
  protected:
   uint32_t algo_id() const override { return QR_ALGO_OBVLAMBDAMART; }
+};
+
+// DART on top of LambdaMART (dart.h:34-199, dart.cc).  The dropout selection, the weight
+// normalisation and the bookkeeping of Dart::learn (dart.cc:172-602) are host logic and are
+// replicated here, std::rand() stream included; everything that touches documents — pseudo-responses,
+// tree fit, adding / subtracting the contribution of a set of trees to all scores
+// (Dart::update_modelscores, dart.cc:634-687), NDCG — runs on the GPU through the C ABI.
+// Supported: sample type UNIFORM / TOP_FIFTY, normalisation TREE / NONE / WEIGHTED / FOREST /
+// TREE_BOOST3, adaptive type FIXED (the reference's defaults and BASELINE.json config 5); the
+// contribution-based and line-search variants are rejected at construction.
+class Dart : public LambdaMart {
+ public:
+  enum class SamplingType { UNIFORM, WEIGHTED, WEIGHTED_INV, COUNT2, COUNT3, COUNT2N, COUNT3N, TOP_FIFTY, CONTR,
+                            CONTR_INV, WCONTR, WCONTR_INV, TOP_WCONTR, LESS_WCONTR };
+  enum class NormalizationType { TREE, NONE, WEIGHTED, FOREST, TREE_ADAPTIVE, LINESEARCH, TREE_BOOST3, CONTR, WCONTR,
+                                 LMART_ADAPTIVE };
+  enum class AdaptiveType { FIXED, PLUS1_DIV2, PLUSHALF_DIV2, PLUSONETHIRD_DIV2, PLUSHALF_RESET, PLUSHALF_RESET_LB1_UB5,
+                            PLUSHALF_RESET_LB1_UB10, PLUSHALF_RESET_LB1_UBRD };
+  // same parameter list as the reference (dart.h:62-70)
+  Dart(size_t ntrees, double shrinkage, size_t nthresholds, size_t ntreeleaves, size_t minleafsupport, float subsample,
+       float max_features, size_t valid_iterations, float collapse_leaves_factor, SamplingType sample_type,
+       NormalizationType normalize_type, AdaptiveType adaptive_rate, double rate_drop, double skip_drop, bool keep_drop,
+       bool best_on_train, double random_keep, double drop_on_best);
+  explicit Dart(const XmlModel &model);
+  void learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_ptr<data::Dataset> validation_dataset,
+             std::shared_ptr<metric::ir::Metric> training_metric, size_t partial_save,
+             const std::string output_basename) override;
+  std::string name() const override { return NAME_; }
+  static const std::string NAME_;
+  static SamplingType get_sampling_type(std::string name);
+  static NormalizationType get_normalization_type(std::string name);
+  static AdaptiveType get_adaptive_type(std::string name);
+  static std::string get_sampling_type(SamplingType t);
+  static std::string get_normalization_type(NormalizationType t);
+  static std::string get_adaptive_type(AdaptiveType t);
+  // every metric value Dart::learn asked for, in call order (parity tap for the tests)
+  const std::vector<MetricScore> &metric_trace() const { return metric_trace_; }
+
+ protected:
+  void write_xml_info(std::ostream &os) const override;
+  std::ostream &put(std::ostream &os) const override;
+  // Dart::update_modelscores (dart.cc:634-687): scores += sign * weight_t * tree_t(doc) for t in trees
+  void update_modelscores_trees(qr_ctx *ctx, bool add, const std::vector<int> &trees);
+  std::vector<int> select_trees_to_dropout(std::vector<double> &weights, size_t trees_to_dropout);
+  void normalize_trees_restore_drop(std::vector<double> &weights, const std::vector<int> &dropped_trees,
+                                    double last_tree_weight);
+  int get_number_of_trees_to_dropout(std::vector<double> &dropout_factor_per_iter, int dropped_before_cleaning);
+  void rescore_on_device(qr_ctx *ctx, std::shared_ptr<data::Dataset> dataset);
+  void check_supported() const;
+
+  SamplingType sample_type = SamplingType::UNIFORM;
+  NormalizationType normalize_type = NormalizationType::TREE;
+  AdaptiveType adaptive_type = AdaptiveType::FIXED;
+  double rate_drop = 0.1, skip_drop = 0.0;
+  bool keep_drop = false, best_on_train = false;
+  double random_keep = 0.0;
+  bool drop_on_best = false;
+
+ private:
+  struct DeviceTree;                                  // flat form of one ensemble tree on this run's bins
+  std::vector<std::shared_ptr<DeviceTree>> flat_;     // parallel to ensemble_model_
+  std::shared_ptr<DeviceTree> make_flat(const RTNode *root) const;
+  std::vector<MetricScore> metric_trace_;
 };
 
 }  // namespace forests

@@ -34,7 +34,7 @@ int main(int argc, char **argv) {
     if (a == "-h" || a == "--help") { usage(); return EXIT_SUCCESS; }
     if (a.rfind("--", 0) != 0) { std::cerr << "!!! Unexpected argument " << a << std::endl; return EXIT_FAILURE; }
     a = a.substr(2);
-    if (a == "restart-train") { opt[a] = "1"; continue; }
+    if (a == "restart-train" || a == "keep-drop" || a == "best-on-train" || a == "drop-on-best") { opt[a] = "1"; continue; }
     if (i + 1 >= argc) { std::cerr << "!!! Option --" << a << " needs a value" << std::endl; return EXIT_FAILURE; }
     opt[a] = argv[++i];
   }
@@ -61,6 +61,16 @@ int main(int argc, char **argv) {
     ranker.reset(mart = new learning::forests::ObliviousMart(ntrees, shrinkage, nthr, depth, minls, 1.0f, 1.0f, esr, 0.0f));
   } else if (algo == "OBVLAMBDAMART") {
     ranker.reset(mart = new learning::forests::ObliviousLambdaMart(ntrees, shrinkage, nthr, depth, minls, 1.0f, 1.0f, esr, 0.0f));
+  } else if (algo == "DART") {
+    using learning::forests::Dart;
+    ranker.reset(mart = new Dart(ntrees, shrinkage, nthr, nleaves, minls, 1.0f, 1.0f, esr, 0.0f,
+                                 Dart::get_sampling_type(get("sample-type", "UNIFORM")),
+                                 Dart::get_normalization_type(get("normalize-type", "TREE")),
+                                 Dart::get_adaptive_type(get("adaptive-type", "FIXED")),
+                                 strtod(get("rate-drop", "0.1").c_str(), nullptr),
+                                 strtod(get("skip-drop", "0").c_str(), nullptr), opt.count("keep-drop") != 0,
+                                 opt.count("best-on-train") != 0, strtod(get("random-keep", "0").c_str(), nullptr),
+                                 opt.count("drop-on-best") ? 1.0 : 0.0));
   } else {
     std::cerr << "!!! Algorithm " << algo << " is not accelerated by this build (see DESIGN.md, out of scope)." << std::endl;
     return EXIT_FAILURE;

@@ -11,6 +11,7 @@
 #include <functional>
 #include <iomanip>
 #include <map>
+#include <numeric>
 #include <sstream>
 
 namespace quickrank {
@@ -290,6 +291,22 @@ bool Ensemble::update_ensemble_weights(std::vector<double> &weights) {
     exit(EXIT_FAILURE);
   }
   for (size_t i = 0; i < trees_.size(); ++i) trees_[i].weight = weights[i];
+  return true;
+}
+
+bool Ensemble::filter_out_zero_weighted_trees() {   // ensemble.cc:149-169
+  size_t kept = 0;
+  for (size_t i = 0; i < trees_.size(); ++i) {
+    if (trees_[i].weight == 0) delete trees_[i].root;
+    else trees_[kept++] = trees_[i];
+  }
+  trees_.resize(kept);
+  return true;
+}
+
+bool Ensemble::update_ensemble_weights(std::vector<double> &weights, bool remove) {   // ensemble.cc:171-188
+  update_ensemble_weights(weights);
+  if (remove) return filter_out_zero_weighted_trees();
   return true;
 }
 
@@ -743,6 +760,457 @@ void Mart::write_xml_model(std::ostream &os) const {
   os << "</ranker>\n";
 }
 
+
+// ------------------------------------------------------------------------------------------
+// DART (dart.cc).  Host logic only; documents are touched on the GPU.
+// ------------------------------------------------------------------------------------------
+const std::string Dart::NAME_ = "DART";
+
+static const std::vector<std::string> kDartSampling = {"UNIFORM", "WEIGHTED", "WEIGHTED_INV", "TOP_FIFTY", "CONTR",
+                                                       "CONTR_INV", "WCONTR", "WCONTR_INV", "TOP_WCONTR", "LESS_WCONTR"};
+static const std::vector<std::string> kDartNormalization = {"TREE", "NONE", "WEIGHTED", "FOREST", "TREE_ADAPTIVE",
+                                                            "LINESEARCH", "TREE_BOOST3", "CONTR", "WCONTR", "LMART_ADAPTIVE"};
+static const std::vector<std::string> kDartAdaptive = {"FIXED", "PLUS1_DIV2", "PLUSHALF_DIV2", "PLUSONETHIRD_DIV2",
+                                                       "PLUSHALF_RESET", "PLUSHALF_RESET_LB1_UB5",
+                                                       "PLUSHALF_RESET_LB1_UB10", "PLUSHALF_RESET_LB1_UBRD"};
+// the reference maps names to enum values through the index in these tables (dart.h:130-170);
+// its sampling table skips the COUNT* enumerators, so only the names whose index equals the
+// enumerator are usable there too — the ones this build supports all are
+static int dart_index(const std::vector<std::string> &names, std::string name, const char *what) {
+  std::transform(name.begin(), name.end(), name.begin(), ::toupper);
+  for (size_t i = 0; i < names.size(); ++i)
+    if (names[i] == name) return (int) i;
+  std::cerr << "!!! Unknown DART " << what << " " << name << std::endl;
+  exit(EXIT_FAILURE);
+}
+Dart::SamplingType Dart::get_sampling_type(std::string name) {
+  const int i = dart_index(kDartSampling, name, "sample type");
+  if (kDartSampling[i] == "UNIFORM") return SamplingType::UNIFORM;
+  if (kDartSampling[i] == "TOP_FIFTY") return SamplingType::TOP_FIFTY;
+  if (kDartSampling[i] == "WEIGHTED") return SamplingType::WEIGHTED;
+  return SamplingType::CONTR;   // any unsupported one: rejected by check_supported()
+}
+Dart::NormalizationType Dart::get_normalization_type(std::string name) {
+  return (NormalizationType) dart_index(kDartNormalization, name, "normalization type");
+}
+Dart::AdaptiveType Dart::get_adaptive_type(std::string name) {
+  return (AdaptiveType) dart_index(kDartAdaptive, name, "adaptive type");
+}
+std::string Dart::get_sampling_type(SamplingType t) {
+  switch (t) {
+    case SamplingType::UNIFORM: return "UNIFORM";
+    case SamplingType::TOP_FIFTY: return "TOP_FIFTY";
+    case SamplingType::WEIGHTED: return "WEIGHTED";
+    default: return "CONTR";
+  }
+}
+std::string Dart::get_normalization_type(NormalizationType t) { return kDartNormalization[(size_t) t]; }
+std::string Dart::get_adaptive_type(AdaptiveType t) { return kDartAdaptive[(size_t) t]; }
+
+Dart::Dart(size_t ntrees, double shrinkage, size_t nthresholds, size_t ntreeleaves, size_t minleafsupport, float subsample,
+           float max_features, size_t valid_iterations, float collapse_leaves_factor, SamplingType st,
+           NormalizationType nt, AdaptiveType at, double rd, double sd, bool kd, bool bot, double rk, double dob)
+    : LambdaMart(ntrees, shrinkage, nthresholds, ntreeleaves, minleafsupport, subsample, max_features, valid_iterations,
+                 collapse_leaves_factor),
+      sample_type(st), normalize_type(nt), adaptive_type(at), rate_drop(rd), skip_drop(sd), keep_drop(kd),
+      best_on_train(bot), random_keep(rk), drop_on_best(dob != 0.0) {
+  check_supported();
+}
+
+// Dart(const pugi::xml_document&) (dart.cc:54-98)
+Dart::Dart(const XmlModel &model) : LambdaMart(model) {
+  const XmlNode *info = model.root->child("info");
+  if (info) {
+    sample_type = get_sampling_type(info->child_text("sample_type", "UNIFORM"));
+    normalize_type = get_normalization_type(info->child_text("normalize_type", "TREE"));
+    adaptive_type = get_adaptive_type(info->child_text("adaptive_type", "FIXED"));
+    rate_drop = strtod(info->child_text("rate_drop", "0.1").c_str(), nullptr);
+    skip_drop = strtod(info->child_text("skip_drop", "0").c_str(), nullptr);
+    best_on_train = info->child_text("best_on_train", "false") == "true";
+    random_keep = strtod(info->child_text("random_keep", "0").c_str(), nullptr);
+    drop_on_best = info->child_text("drop_on_best", "false") == "true";
+  }
+}
+
+void Dart::check_supported() const {
+  const bool st_ok = sample_type == SamplingType::UNIFORM || sample_type == SamplingType::TOP_FIFTY;
+  const bool nt_ok = normalize_type == NormalizationType::TREE || normalize_type == NormalizationType::NONE ||
+                     normalize_type == NormalizationType::WEIGHTED || normalize_type == NormalizationType::FOREST ||
+                     normalize_type == NormalizationType::TREE_BOOST3;
+  if (!st_ok || !nt_ok || adaptive_type != AdaptiveType::FIXED) {
+    std::cerr << "!!! This DART variant (sample type " << get_sampling_type(sample_type) << ", normalization "
+              << get_normalization_type(normalize_type) << ", adaptive type " << get_adaptive_type(adaptive_type)
+              << ") is not supported by the GPU engine: UNIFORM|TOP_FIFTY x TREE|NONE|WEIGHTED|FOREST|TREE_BOOST3 x FIXED."
+              << std::endl;
+    exit(EXIT_FAILURE);
+  }
+}
+
+void Dart::write_xml_info(std::ostream &os) const {   // dart.cc:108-133
+  os << "\t\t<type>" << name() << "</type>\n"
+     << "\t\t<trees>" << ntrees_ << "</trees>\n"
+     << "\t\t<leaves>" << nleaves_ << "</leaves>\n"
+     << "\t\t<shrinkage>" << fmt_g(shrinkage_, 17) << "</shrinkage>\n"
+     << "\t\t<leafsupport>" << minleafsupport_ << "</leafsupport>\n"
+     << "\t\t<discretization>" << nthresholds_ << "</discretization>\n"
+     << "\t\t<estop>" << valid_iterations_ << "</estop>\n"
+     << "\t\t<sample_type>" << get_sampling_type(sample_type) << "</sample_type>\n"
+     << "\t\t<normalize_type>" << get_normalization_type(normalize_type) << "</normalize_type>\n"
+     << "\t\t<adaptive_type>" << get_adaptive_type(adaptive_type) << "</adaptive_type>\n"
+     << "\t\t<rate_drop>" << fmt_g(rate_drop, 17) << "</rate_drop>\n"
+     << "\t\t<skip_drop>" << fmt_g(skip_drop, 17) << "</skip_drop>\n"
+     << "\t\t<best_on_train>" << (best_on_train ? "true" : "false") << "</best_on_train>\n"
+     << "\t\t<random_keep>" << fmt_g(random_keep, 17) << "</random_keep>\n"
+     << "\t\t<drop_on_best>" << (drop_on_best ? "true" : "false") << "</drop_on_best>\n";
+}
+
+std::ostream &Dart::put(std::ostream &os) const {   // dart.cc:142-170
+  os << "# Ranker: " << name() << std::endl
+     << "# max no. of trees = " << ntrees_ << std::endl
+     << "# no. of tree leaves = " << nleaves_ << std::endl
+     << "# shrinkage = " << shrinkage_ << std::endl
+     << "# min leaf support = " << minleafsupport_ << std::endl;
+  if (nthresholds_) os << "# no. of thresholds = " << nthresholds_ << std::endl;
+  else os << "# no. of thresholds = unlimited" << std::endl;
+  if (valid_iterations_) os << "# no. of no gain rounds before early stop = " << valid_iterations_ << std::endl;
+  os << "# sample type = " << get_sampling_type(sample_type) << std::endl
+     << "# normalization type = " << get_normalization_type(normalize_type) << std::endl
+     << "# adaptive type = " << get_adaptive_type(adaptive_type) << std::endl
+     << "# rate drop = " << rate_drop << std::endl
+     << "# skip drop = " << skip_drop << std::endl
+     << "# keep drop = " << keep_drop << std::endl
+     << "# best on train = " << best_on_train << std::endl
+     << "# keep dropout at random = " << random_keep << std::endl
+     << "# keep dropout based on best = " << drop_on_best << std::endl;
+  return os;
+}
+
+struct Dart::DeviceTree {
+  std::vector<int32_t> feature, left, right;
+  std::vector<uint32_t> tidx;
+  std::vector<float> thr;
+  std::vector<double> value;
+  qr_flat_tree flat() {
+    qr_flat_tree t;
+    t.capacity = t.nnodes = (uint32_t) feature.size();
+    t.nleaves = 0;
+    t.feature = feature.data(); t.threshold_idx = tidx.data(); t.threshold = thr.data();
+    t.left = left.data(); t.right = right.data(); t.value = value.data(); t.deviance = nullptr; t.count = nullptr;
+    return t;
+  }
+};
+
+// a tree of the ensemble expressed on this run's bins (threshold value -> threshold index)
+std::shared_ptr<Dart::DeviceTree> Dart::make_flat(const RTNode *root) const {
+  auto d = std::make_shared<DeviceTree>();
+  RegressionTree::to_flat(root, d->feature, d->thr, d->left, d->right, d->value);
+  d->tidx.assign(d->feature.size(), 0);
+  for (size_t i = 0; i < d->feature.size(); ++i) {
+    if (d->feature[i] < 0) continue;
+    const float *tv = nullptr;
+    size_t tn = 0;
+    if (qr_get_thresholds(ctx_, (size_t) d->feature[i], &tv, &tn) != QR_OK) die("DART: thresholds");
+    // smallest index whose threshold is >= the node's: x <= thr  <=>  bin(x) <= that index
+    const float *it = std::lower_bound(tv, tv + tn, d->thr[i]);
+    d->tidx[i] = (uint32_t) (it - tv);
+  }
+  return d;
+}
+
+void Dart::update_modelscores_trees(qr_ctx *ctx, bool add, const std::vector<int> &trees) {
+  const double sign = add ? 1.0 : -1.0;
+  for (int t : trees) {
+    qr_flat_tree ft = flat_[(size_t) t]->flat();
+    if (qr_apply_tree(ctx, &ft, sign * ensemble_model_.getWeight(t)) != QR_OK) die("DART: update_modelscores");
+  }
+}
+
+// full rescoring of a dataset with the current ensemble (score_dataset in dart.cc:552-558)
+void Dart::rescore_on_device(qr_ctx *ctx, std::shared_ptr<data::Dataset> dataset) {
+  std::vector<Score> zero(dataset->num_instances(), 0.0);
+  if (qr_set_scores(ctx, zero.data()) != QR_OK) die("DART: rescore");
+  std::vector<int> all;
+  // Ensemble::score_instance sums weight * tree in index order (ensemble.cc:111-118); so does this loop
+  for (size_t t = 0; t < ensemble_model_.get_size(); ++t) all.push_back((int) t);
+  update_modelscores_trees(ctx, true, all);
+}
+
+// dart.cc:708-736 (UNIFORM / TOP_FIFTY)
+std::vector<int> Dart::select_trees_to_dropout(std::vector<double> &weights, size_t trees_to_dropout) {
+  if (trees_to_dropout == 0) return std::vector<int>();
+  std::vector<int> dropped;
+  size_t size = weights.size();
+  if (sample_type == SamplingType::TOP_FIFTY) size = (size_t) round(size / 2);
+  std::vector<int> idx(size);
+  std::iota(idx.begin(), idx.end(), 0);
+  // libstdc++'s std::random_shuffle(first, last, rng): for i in 1..n-1 swap(i, rng(i + 1)), with the
+  // reference's generator (dart.cc:725-729); written out because std::random_shuffle is gone in C++17
+  for (size_t i = 1; i < idx.size(); ++i) {
+    const size_t j = (size_t) (int) (std::rand() / (1.0 + RAND_MAX) * (int) (i + 1));
+    if (i != j) std::swap(idx[i], idx[j]);
+  }
+  for (size_t i = 0; dropped.size() < trees_to_dropout && i < idx.size(); ++i)
+    if (weights[(size_t) idx[i]] > 0) dropped.push_back(idx[i]);
+  return dropped;
+}
+
+// dart.cc:856-905
+void Dart::normalize_trees_restore_drop(std::vector<double> &weights, const std::vector<int> &dropped_trees,
+                                        double /*last_tree_weight*/) {
+  const size_t k = dropped_trees.size();
+  if (normalize_type == NormalizationType::TREE || normalize_type == NormalizationType::TREE_BOOST3) {
+    const double alpha = normalize_type == NormalizationType::TREE_BOOST3 ? 3 : 1;
+    weights.push_back((shrinkage_ * alpha) / ((shrinkage_ * alpha) + k));
+    const double norm = (double) k / (k + (shrinkage_ * alpha));
+    for (int idx : dropped_trees) weights[(size_t) idx] *= norm;
+  } else if (normalize_type == NormalizationType::NONE) {
+    weights.push_back(shrinkage_);
+  } else if (normalize_type == NormalizationType::WEIGHTED) {
+    double sum = 0;
+    for (int t : dropped_trees) sum += weights[(size_t) t];
+    const double sumWithLast = sum + shrinkage_;
+    const double norm = sum / sumWithLast;
+    weights.push_back(shrinkage_ / sumWithLast);
+    for (int t : dropped_trees) weights[(size_t) t] *= norm;
+  } else if (normalize_type == NormalizationType::FOREST) {
+    weights.push_back(shrinkage_ / (1 + shrinkage_));
+    const double norm = 1 / (1 + shrinkage_);
+    for (int idx : dropped_trees) weights[(size_t) idx] *= norm;
+  }
+}
+
+// dart.cc:1095-1181 (FIXED)
+int Dart::get_number_of_trees_to_dropout(std::vector<double> &dropout_factor_per_iter, int dropped_before_cleaning) {
+  const double prob_skip_dropout = (double) rand() / (double) (RAND_MAX);
+  const int model_size = (int) ensemble_model_.get_size() - dropped_before_cleaning;
+  double trees_to_dropout = 0;
+  if (prob_skip_dropout > skip_drop && model_size > 0) {
+    if (rate_drop >= 1) {
+      if ((rate_drop * 2) <= model_size) trees_to_dropout = rate_drop;
+    } else {
+      trees_to_dropout = rate_drop * model_size;
+    }
+  }
+  trees_to_dropout = trees_to_dropout > model_size / 2 ? model_size / 2 : trees_to_dropout;   // integer division, as there
+  dropout_factor_per_iter.push_back(trees_to_dropout);
+  return (int) round(trees_to_dropout);
+}
+
+// Dart::learn (dart.cc:172-602)
+void Dart::learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_ptr<data::Dataset> validation_dataset,
+                 std::shared_ptr<metric::ir::Metric> scorer, size_t partial_save, const std::string output_basename) {
+  if (scorer->name() != "NDCG") {
+    std::cerr << "!!! The GPU engine optimises NDCG only (got " << scorer->name() << ")." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  if (subsample_ != 1.0f || max_features_ != 1.0f || collapse_leaves_factor_ != 0.0f) {
+    std::cerr << "!!! subsample, max_features and collapse_leaves_factor are not supported by the GPU engine."
+              << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  check_supported();
+  std::cout << "# Initialization";
+  std::cout.flush();
+  std::srand(0);   // dart.cc:181
+  auto t0 = std::chrono::high_resolution_clock::now();
+  metric_cutoff_ = scorer->cutoff();
+  metric_trace_.clear();
+  std::shared_ptr<data::VerticalDataset> vertical_training(new data::VerticalDataset(training_dataset));
+  best_metric_on_validation_ = std::numeric_limits<double>::lowest();
+  best_metric_on_training_ = std::numeric_limits<double>::lowest();
+  best_model_ = 0;
+  size_t best_iter_ = 0;
+  std::vector<double> best_weights;
+  ensemble_model_.set_capacity(ntrees_ + valid_iterations_);
+  init(vertical_training);
+  if (validation_dataset &&
+      qr_ctx_create_eval(ctx_, validation_dataset->data(), validation_dataset->num_instances(),
+                         validation_dataset->num_features(), validation_dataset->labels(),
+                         validation_dataset->offsets().data(), validation_dataset->num_queries(), &valid_ctx_) != QR_OK)
+    die("Impossible to initialise the GPU validation context");
+  auto eval = [&](qr_ctx *ctx) {
+    double m = 0;
+    if (qr_evaluate(ctx, &m) != QR_OK) die("evaluate_dataset");
+    metric_trace_.push_back(m);
+    return m;
+  };
+  flat_.clear();
+  if (ensemble_model_.is_notempty()) {   // restart from a loaded model (dart.cc:206-226)
+    for (size_t t = 0; t < ensemble_model_.get_size(); ++t) flat_.push_back(make_flat(ensemble_model_.getTree((int) t)));
+    best_model_ = ensemble_model_.get_size() - 1;
+    best_iter_ = best_model_;
+    best_weights = ensemble_model_.get_weights();
+    rescore_on_device(ctx_, training_dataset);
+    best_metric_on_training_ = eval(ctx_);
+    if (validation_dataset) {
+      rescore_on_device(valid_ctx_, validation_dataset);
+      best_metric_on_validation_ = eval(valid_ctx_);
+    }
+  }
+  double init_time = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+  std::cout << ": " << std::setprecision(2) << init_time << " s." << std::endl;
+  std::cout << std::fixed << std::setprecision(4);
+  std::cout << "# Training:" << std::endl;
+  std::cout << "# -------------------------" << std::endl;
+  std::cout << "# iter. training validation" << std::endl;
+  std::cout << "# -------------------------" << std::endl;
+  if (ensemble_model_.is_notempty()) {
+    std::cout << std::setw(7) << ensemble_model_.get_size() << std::setw(9) << best_metric_on_training_;
+    if (validation_dataset) std::cout << std::setw(9) << best_metric_on_validation_;
+    std::cout << " *" << std::endl;
+  }
+  auto t1 = std::chrono::high_resolution_clock::now();
+  MetricScore metric_on_training = std::numeric_limits<double>::lowest();
+  MetricScore metric_on_validation = std::numeric_limits<double>::lowest();
+  size_t dropped_before_cleaning = 0;
+  size_t m = (size_t) -1;
+  size_t last_iteration_global_scoring = 0;
+  std::vector<double> dropout_factor_per_iter;
+  while ((ensemble_model_.get_size() - dropped_before_cleaning) < ntrees_) {
+    ++m;
+    if (validation_dataset && (valid_iterations_ && m > best_iter_ + valid_iterations_)) break;
+    std::vector<double> orig_weights = ensemble_model_.get_weights();
+    const int trees_to_dropout = get_number_of_trees_to_dropout(dropout_factor_per_iter, (int) dropped_before_cleaning);
+    const double prob_random_keep = (double) rand() / (double) (RAND_MAX);
+    const bool random_keep_iter = trees_to_dropout > 0 && prob_random_keep <= random_keep;
+    double metric_on_training_dropout = 0, metric_on_validation_dropout = 0;
+    std::vector<int> dropped_trees;
+    bool dropout_better_than_full = false;
+    std::vector<double> dropped_weights(orig_weights);
+    if (trees_to_dropout > 0) {
+      dropped_trees = select_trees_to_dropout(orig_weights, (size_t) trees_to_dropout);
+      // subtract the dropped trees from the scores (train and validation)
+      update_modelscores_trees(ctx_, false, dropped_trees);
+      metric_on_training_dropout = eval(ctx_);
+      if (validation_dataset) {
+        update_modelscores_trees(valid_ctx_, false, dropped_trees);
+        metric_on_validation_dropout = eval(valid_ctx_);
+        if (metric_on_validation_dropout > metric_on_validation) dropout_better_than_full = true;
+      } else if (metric_on_training_dropout > metric_on_training) {
+        dropout_better_than_full = true;
+      }
+      for (int idx : dropped_trees) dropped_weights[(size_t) idx] = 0;
+      ensemble_model_.update_ensemble_weights(dropped_weights, false);
+    }
+    compute_pseudoresponses(vertical_training, scorer.get(), nullptr);
+    std::unique_ptr<RegressionTree> tree = fit_regressor_on_gradient(vertical_training, nullptr);
+    // (update_contribution_scores, dart.cc:378, only feeds the CONTR normalisations, which are rejected)
+    // get_weight_last_tree (dart.cc:944-975) for the supported normalisations
+    const double tree_weight = normalize_type == NormalizationType::TREE_BOOST3
+                                   ? (shrinkage_ * 3) / ((shrinkage_ * 3) + dropped_trees.size())
+                                   : shrinkage_;
+    ensemble_model_.push(tree->get_proot(), tree_weight, 0);
+    flat_.push_back(make_flat(tree->get_proot()));
+    const int lastTreeIndex = (int) ensemble_model_.get_size() - 1;
+    std::vector<int> lastTree = {lastTreeIndex};
+    update_modelscores_trees(ctx_, true, lastTree);
+    const double metric_on_training_fit = eval(ctx_);
+    double metric_on_validation_fit = std::numeric_limits<double>::lowest();
+    if (validation_dataset) {
+      update_modelscores_trees(valid_ctx_, true, lastTree);
+      metric_on_validation_fit = eval(valid_ctx_);
+    }
+    bool fit_after_dropout_improvement = false;
+    if (trees_to_dropout > 0) {
+      double reference_metric_training = metric_on_training, reference_metric_validation = metric_on_validation;
+      if (drop_on_best) {
+        reference_metric_training = best_metric_on_training_;
+        reference_metric_validation = best_metric_on_validation_;
+      }
+      if (validation_dataset) {
+        if (metric_on_validation_fit > reference_metric_validation) fit_after_dropout_improvement = true;
+      } else if (metric_on_training_fit > reference_metric_training) {
+        fit_after_dropout_improvement = true;
+      }
+    }
+    if (keep_drop && (fit_after_dropout_improvement || random_keep_iter)) {
+      dropped_before_cleaning += (size_t) trees_to_dropout;
+      metric_on_training = metric_on_training_fit;
+      metric_on_validation = metric_on_validation_fit;
+    } else {
+      // back to the scores before the new tree, normalise, then add the dropped trees and the new one
+      update_modelscores_trees(ctx_, false, lastTree);
+      if (validation_dataset) update_modelscores_trees(valid_ctx_, false, lastTree);
+      if (trees_to_dropout > 0) {
+        normalize_trees_restore_drop(orig_weights, dropped_trees, tree_weight);
+        ensemble_model_.update_ensemble_weights(orig_weights, false);
+      }
+      dropped_trees.push_back((int) ensemble_model_.get_size() - 1);
+      update_modelscores_trees(ctx_, true, dropped_trees);
+      metric_on_training = eval(ctx_);
+      if (validation_dataset) {
+        update_modelscores_trees(valid_ctx_, true, dropped_trees);
+        metric_on_validation = eval(valid_ctx_);
+      }
+    }
+    std::cout << std::setw(7) << m + 1 << std::setw(9) << metric_on_training;
+    bool best_improved = false;
+    if (validation_dataset && !best_on_train) {
+      std::cout << std::setw(9) << metric_on_validation;
+      if (metric_on_validation > best_metric_on_validation_) best_improved = true;
+    } else if (metric_on_training > best_metric_on_training_) {
+      best_improved = true;
+    }
+    bool best_vali_improved = false;
+    if (validation_dataset && best_on_train && metric_on_validation > best_metric_on_validation_) {
+      best_vali_improved = true;
+      best_metric_on_validation_ = metric_on_validation;
+    }
+    if (best_improved) {
+      best_metric_on_training_ = metric_on_training;
+      if (!best_on_train) best_metric_on_validation_ = metric_on_validation;
+      best_iter_ = m;
+      std::cout << " *";
+      // trees whose weight is 0 (kept dropouts) leave the ensemble
+      {
+        std::vector<std::shared_ptr<DeviceTree>> kept;
+        for (size_t t = 0; t < ensemble_model_.get_size(); ++t)
+          if (ensemble_model_.getWeight((int) t) != 0) kept.push_back(flat_[t]);
+        flat_.swap(kept);
+      }
+      ensemble_model_.filter_out_zero_weighted_trees();
+      best_weights = ensemble_model_.get_weights();
+      best_model_ = ensemble_model_.get_size();
+      dropped_before_cleaning = 0;
+    }
+    std::string improved = best_vali_improved ? " *" : "  ";
+    std::cout << "\t[ " << metric_on_training_dropout << " - " << metric_on_training_fit << " - " << metric_on_training
+              << " | " << metric_on_validation_dropout << (dropout_better_than_full ? " *" : "  ") << " - "
+              << metric_on_validation_fit << (fit_after_dropout_improvement ? " *" : "  ") << " - " << metric_on_validation
+              << improved << "]";
+    std::cout << " \t" << trees_to_dropout << " Dropped Trees - Ensemble size: "
+              << ensemble_model_.get_size() - dropped_before_cleaning;
+    if (keep_drop && fit_after_dropout_improvement) std::cout << " - Keep Dropout";
+    else if (random_keep_iter) std::cout << " - Keep Dropout (RANDOM)";
+    else if (trees_to_dropout > 0) std::cout << " - Dropout";
+    if (best_improved) {
+      std::cout << " - CLEANED";
+      if ((m - last_iteration_global_scoring) > 10) {
+        rescore_on_device(ctx_, training_dataset);
+        if (validation_dataset) rescore_on_device(valid_ctx_, validation_dataset);
+        std::cout << " (update)";
+        last_iteration_global_scoring = m;
+      }
+    }
+    std::cout << std::endl;
+    if (partial_save != 0 && !output_basename.empty() &&
+        (ensemble_model_.get_size() - dropped_before_cleaning) % partial_save == 0)
+      save(output_basename, (int) (ensemble_model_.get_size() - dropped_before_cleaning));
+  }
+  if (validation_dataset) {   // roll back to the best model on validation (dart.cc:575-581)
+    while (ensemble_model_.is_notempty() && ensemble_model_.get_size() > best_model_) { ensemble_model_.pop(); flat_.pop_back(); }
+    ensemble_model_.update_ensemble_weights(best_weights, true);
+  }
+  double train_time = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t1).count();
+  std::cout << std::endl;
+  std::cout << *scorer << " on training data = " << best_metric_on_training_ << std::endl;
+  if (validation_dataset) std::cout << *scorer << " on validation data = " << best_metric_on_validation_ << std::endl;
+  flat_.clear();
+  clear(vertical_training->num_features());
+  std::cout << std::endl;
+  std::cout << "#\t Training Time: " << std::setprecision(2) << train_time << " s." << std::endl;
+}
+
 }  // namespace forests
 
 void LTR_Algorithm::score_dataset(std::shared_ptr<data::Dataset> dataset, Score *scores) const {
@@ -783,6 +1251,7 @@ std::shared_ptr<LTR_Algorithm> LTR_Algorithm::load_model_from_file(std::string m
   if (type == forests::ObliviousMart::NAME_) return std::shared_ptr<LTR_Algorithm>(new forests::ObliviousMart(model));
   if (type == forests::ObliviousLambdaMart::NAME_)
     return std::shared_ptr<LTR_Algorithm>(new forests::ObliviousLambdaMart(model));
+  if (type == forests::Dart::NAME_) return std::shared_ptr<LTR_Algorithm>(new forests::Dart(model));
   return nullptr;
 }
 
