@@ -919,10 +919,14 @@ std::shared_ptr<Dart::DeviceTree> Dart::make_flat(const RTNode *root) const {
 
 void Dart::update_modelscores_trees(qr_ctx *ctx, bool add, const std::vector<int> &trees) {
   const double sign = add ? 1.0 : -1.0;
+  std::vector<qr_flat_tree> ft;
+  std::vector<double> w;
   for (int t : trees) {
-    qr_flat_tree ft = flat_[(size_t) t]->flat();
-    if (qr_apply_tree(ctx, &ft, sign * ensemble_model_.getWeight(t)) != QR_OK) die("DART: update_modelscores");
+    ft.push_back(flat_[(size_t) t]->flat());
+    w.push_back(sign * ensemble_model_.getWeight(t));
   }
+  // one pass over the documents for the whole set; per document the trees are applied in this order
+  if (qr_apply_trees(ctx, ft.data(), w.data(), ft.size()) != QR_OK) die("DART: update_modelscores");
 }
 
 // full rescoring of a dataset with the current ensemble (score_dataset in dart.cc:552-558)

@@ -132,6 +132,11 @@ int qr_update_modelscores(qr_ctx *ctx, double weight);
 /* scores[i] += weight * tree(doc_i) for an arbitrary tree of this context's binning (DART's
  * add/subtract passes, dart.cc:634-687; weight carries the sign). */
 int qr_apply_tree(qr_ctx *ctx, const qr_flat_tree *tree, double weight);
+/* The same for a set of trees in ONE pass over the documents: for every document the trees are
+ * applied in array order, scores[i] = fma(weights[t], tree_t(doc_i), scores[i]) — the per-document
+ * sequence of operations of Dart::update_modelscores' loop over `trees_to_update` (dart.cc:634-650),
+ * which visits the documents once per tree instead. */
+int qr_apply_trees(qr_ctx *ctx, const qr_flat_tree *trees, const double *weights, size_t ntrees);
 
 /* Replaces Metric::evaluate_dataset(VerticalDataset, scores) for Ndcg (metric.h:93-106,
  * ndcg.cc:49-58) on the training scores held by the context. */

@@ -76,6 +76,7 @@ def lib():
         L.qr_fit_tree.argtypes = [vp, C.POINTER(FlatTree)]
         L.qr_update_modelscores.argtypes = [vp, C.c_double]
         L.qr_apply_tree.argtypes = [vp, C.POINTER(FlatTree), C.c_double]
+        L.qr_apply_trees.argtypes = [vp, C.POINTER(FlatTree), dp, C.c_size_t]
         L.qr_evaluate.argtypes = [vp, dp]
         L.qr_boost_iteration.argtypes = [vp, C.POINTER(FlatTree), dp]
         L.qr_get_scores.argtypes = [vp, dp]
@@ -242,6 +243,12 @@ class Trainer:
     def apply_tree(self, tree, weight):
         tb = TreeBuffer.from_dict(tree)
         _check(lib().qr_apply_tree(self.h, C.byref(tb.t), weight))
+
+    def apply_trees(self, trees, weights):
+        bufs = [TreeBuffer.from_dict(t) for t in trees]
+        arr = (FlatTree * len(bufs))(*[b.t for b in bufs])
+        w = np.ascontiguousarray(weights, np.float64)
+        _check(lib().qr_apply_trees(self.h, arr, _p(w, C.c_double), len(bufs)))
 
     def evaluate_dataset(self):
         m = C.c_double()

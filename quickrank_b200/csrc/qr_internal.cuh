@@ -171,6 +171,9 @@ struct qr_ctx {
   size_t grow_smem = 0;                     // dynamic shared memory of grow_step_kernel
   void *d_grow_arrays[7] = {nullptr};       // heap/slots/candidate arrays owned by the grow state
 
+  void *d_apply = nullptr, *h_apply = nullptr;   // staging of qr_apply_trees (device / pinned host)
+  size_t apply_cap = 0;
+
   qr::Comm *comm = nullptr;
   size_t N_global = 0, Q_global = 0;
 };

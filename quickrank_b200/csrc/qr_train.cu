@@ -686,6 +686,8 @@ int qr_ctx_destroy(qr_ctx *c) {
   if (c->h_segs) cudaFreeHost(c->h_segs);
   if (c->h_obv_lcounts) cudaFreeHost(c->h_obv_lcounts);
   if (c->h_nodes) cudaFreeHost(c->h_nodes);
+  if (c->d_apply) cudaFree(c->d_apply);
+  if (c->h_apply) cudaFreeHost(c->h_apply);
   delete c->h_grow;
   if (c->h_grow_out) cudaFreeHost((void *) c->h_grow_out);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -760,6 +762,60 @@ int qr_apply_tree(qr_ctx *c, const qr_flat_tree *t, double weight) {
   });
   cudaStreamSynchronize(c->stream);
   cudaFree(d_feat); cudaFree(d_left); cudaFree(d_right); cudaFree(d_tidx); cudaFree(d_val);
+  c->ranking_valid = false;
+  return rc;
+}
+
+int qr_apply_trees(qr_ctx *c, const qr_flat_tree *trees, const double *weights, size_t ntrees) {
+  QR_CHECK_CTX(c);
+  if (ntrees == 0) return QR_OK;
+  if (!trees || !weights) { set_error("qr_apply_trees: null argument"); return QR_EINVAL; }
+  size_t total = 0;
+  for (size_t t = 0; t < ntrees; ++t) {
+    const qr_flat_tree &ft = trees[t];
+    if (ft.nnodes == 0) { set_error("qr_apply_trees: empty tree %zu", t); return QR_EINVAL; }
+    for (uint32_t i = 0; i < ft.nnodes; ++i)
+      if (ft.feature[i] >= 0 && ((size_t) ft.feature[i] >= c->F || ft.threshold_idx[i] >= c->thr[ft.feature[i]].size())) {
+        set_error("qr_apply_trees: node %u of tree %zu does not belong to this context's binning", i, t);
+        return QR_EINVAL;
+      }
+    total += ft.nnodes;
+  }
+  // one staging buffer: nodes | roots | weights
+  const size_t bytes = total * sizeof(PackedNode) + ntrees * sizeof(uint32_t) + ntrees * sizeof(double) + 16;
+  if (bytes > c->apply_cap) {
+    if (c->d_apply) cudaFree(c->d_apply);
+    if (c->h_apply) cudaFreeHost(c->h_apply);
+    c->apply_cap = std::max<size_t>(bytes * 2, 1 << 16);
+    QR_CUDA(cudaMalloc(&c->d_apply, c->apply_cap));
+    QR_CUDA(cudaMallocHost(&c->h_apply, c->apply_cap));
+  } else {
+    QR_CUDA(cudaStreamSynchronize(c->stream));   // the previous pass may still be reading the staging copy
+  }
+  unsigned char *h = (unsigned char *) c->h_apply;
+  double *hw = (double *) h;                                           // weights first (8-byte aligned)
+  PackedNode *hn = (PackedNode *) (h + ntrees * sizeof(double));
+  uint32_t *hr = (uint32_t *) (hn + total);
+  size_t o = 0;
+  for (size_t t = 0; t < ntrees; ++t) {
+    const qr_flat_tree &ft = trees[t];
+    hr[t] = (uint32_t) o;
+    hw[t] = weights[t];
+    for (uint32_t i = 0; i < ft.nnodes; ++i)
+      hn[o + i] = PackedNode{ft.feature[i], ft.feature[i] >= 0 ? ft.threshold_idx[i] : 0u, ft.left[i], ft.right[i], ft.value[i]};
+    o += ft.nnodes;
+  }
+  QR_CUDA(cudaMemcpyAsync(c->d_apply, c->h_apply, bytes, cudaMemcpyHostToDevice, c->stream));
+  unsigned char *d = (unsigned char *) c->d_apply;
+  const double *dw = (const double *) d;
+  const PackedNode *dn = (const PackedNode *) (d + ntrees * sizeof(double));
+  const uint32_t *dr = (const uint32_t *) (dn + total);
+  int rc = dispatch_bins(c, [&](auto tag) -> int {
+    using B = decltype(tag);
+    QR_LAUNCH(c, PH_LEAF, apply_trees_kernel<B>, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_panels, c->N, dn, dr, dw,
+              (uint32_t) ntrees, c->d_scores);
+    return QR_OK;
+  });
   c->ranking_valid = false;
   return rc;
 }

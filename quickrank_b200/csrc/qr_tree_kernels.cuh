@@ -992,6 +992,26 @@ __global__ void apply_tree_kernel(const uint4 *__restrict__ panels, size_t N, De
   scores[i] = fma(weight, t.value[nd], scores[i]);
 }
 
+// The same for a packed set of trees: one pass over the documents, trees in array order.
+struct PackedNode { int32_t feature; uint32_t tidx; int32_t left, right; double value; };
+
+template <typename BinT>
+__global__ void apply_trees_kernel(const uint4 *__restrict__ panels, size_t N, const PackedNode *__restrict__ nodes,
+                                   const uint32_t *__restrict__ root_of, const double *__restrict__ weights,
+                                   uint32_t ntrees, double *scores) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double s = scores[i];
+  for (uint32_t t = 0; t < ntrees; ++t) {
+    const PackedNode *tn = nodes + root_of[t];
+    int32_t nd = 0;
+    while (tn[nd].feature >= 0)
+      nd = load_bin<BinT>(panels, N, (uint32_t) tn[nd].feature, (uint32_t) i) <= tn[nd].tidx ? tn[nd].left : tn[nd].right;
+    s = fma(weights[t], tn[nd].value, s);   // dart.cc:644-646 (fused like mart.cc:466)
+  }
+  scores[i] = s;
+}
+
 // ------------------------------------------------------------------------------------------
 // Oblivious trees (ObliviousRT::fit / fill, ot.cc:32-201): per level, sum the split gain of every
 // (f, t) over the level's nodes in node order; a cell is invalid as soon as one node violates the

@@ -284,6 +284,24 @@ def test_apply_tree_adds_and_subtracts():
         assert np.array_equal(po.update_scores(tree, col, 0.1, np.zeros(len(l))), s1)
 
 
+def test_apply_trees_equals_one_tree_at_a_time():
+    """qr_apply_trees walks a set of trees in one pass over the documents; per document the operations
+    are those of Dart::update_modelscores' tree-by-tree loop (dart.cc:634-650), so the scores are
+    bit-identical to applying the trees one after the other."""
+    x, l, off = common.dataset(n=5000, f=14, q=50)
+    with api.Trainer(x, l, off, nleaves=8) as tr:
+        trees = [tr.boost_iteration()[0] for _ in range(5)]
+        base = tr.get_scores()
+        w = [-0.1, 0.07, -0.033, 0.2, 0.011]
+        tr.apply_trees(trees, w)
+        batched = tr.get_scores()
+        tr.set_scores(base)
+        for t, wt in zip(trees, w):
+            tr.apply_tree(t, wt)
+        assert np.array_equal(tr.get_scores(), batched)
+        assert not np.array_equal(batched, base)
+
+
 def test_scoring_matches_oracle_bit_for_bit():
     x, l, off = common.dataset(n=3000, f=30, q=30)
     trees, weights = synth.random_ensemble(40, 16, 30, seed=3)
