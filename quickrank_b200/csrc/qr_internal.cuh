@@ -171,6 +171,8 @@ struct qr_ctx {
   size_t grow_smem = 0;                     // dynamic shared memory of grow_step_kernel
   void *d_grow_arrays[7] = {nullptr};       // heap/slots/candidate arrays owned by the grow state
 
+  uint32_t *d_part_done = nullptr, *d_panel_done = nullptr;   // counters of the fused round kernel
+  bool fused_rounds = false, fuse_partition = false;
   void *d_apply = nullptr, *h_apply = nullptr;   // staging of qr_apply_trees (device / pinned host)
   size_t apply_cap = 0;
 

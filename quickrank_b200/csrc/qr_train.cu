@@ -18,6 +18,7 @@
 
 #include "qr_comm.cuh"
 #include "qr_tree_kernels.cuh"
+#include "qr_round_kernel.cuh"
 
 namespace qr {
 
@@ -523,6 +524,18 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     memset((void *) c->h_grow_out, 0, sizeof(GrowOut));
   }
 
+  // counters of the fused round kernel (qr_round_kernel.cuh)
+  QR_TRY(dev_alloc(&c->d_part_done, mt));
+  QR_TRY(dev_alloc(&c->d_panel_done, mt * c->npanels));
+  QR_CUDA(cudaMemset(c->d_part_done, 0, mt * sizeof(uint32_t)));
+  QR_CUDA(cudaMemset(c->d_panel_done, 0, mt * c->npanels * sizeof(uint32_t)));
+  // opt-in (QR_FUSED_ROUNDS=1): measured on B200 at config 2 the fused launch is SLOWER than the three
+  // kernels (2.66 vs 2.45 ms per steady-state tree): its blocks carry the histogram role's 512 threads,
+  // 48 KB of shared memory and 64-register budget, so the partition role runs at 2 blocks per SM instead
+  // of 6 and the split scan spills; see DESIGN.md section 4.
+  c->fused_rounds = !c->exact && c->comm == nullptr && getenv("QR_FUSED_ROUNDS") != nullptr;
+  c->fuse_partition = getenv("QR_FUSE_PARTITION") != nullptr;
+
   // opt in to large dynamic shared memory where needed
   const size_t hist_smem = (size_t) c->fpp * c->max_thr * 12;
   if (hist_smem <= 200 * 1024) {
@@ -531,6 +544,8 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(round_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(round_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   }
   QR_CUDA(cudaGetLastError());
   clk.lap("state + pools");
@@ -675,6 +690,7 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
                   c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done, c->d_part_status,
                   c->d_ticket, c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_hdr, c->d_grow, c->d_nodes,
+                  c->d_part_done, c->d_panel_done,
                   c->d_grow_arrays[0], c->d_grow_arrays[1], c->d_grow_arrays[2], c->d_grow_arrays[3],
                   c->d_grow_arrays[4], c->d_grow_arrays[5], c->d_grow_arrays[6]};
   for (void *p : ptrs) if (p) cudaFree(p);

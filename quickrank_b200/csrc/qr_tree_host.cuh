@@ -83,6 +83,30 @@ static RoundTrace g_trace;
 static const bool g_trace_on = getenv("QR_TRACE") != nullptr;
 #define QR_TRACE_MARK(c) do { if (g_trace_on) cudaEventRecord(g_trace.next(), (c)->stream); } while (0)
 
+// wait for the k per-task flags of the current round (bounded spin; a launch failure surfaces through
+// cudaStreamQuery)
+static int wait_round_flags(qr_ctx *c, uint32_t k) {
+  volatile uint32_t *flags = c->h_flags;
+  uint64_t spins = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    while (flags[j] != c->round_id) {
+      if ((++spins & 0xfffff) == 0) {
+        cudaError_t e = cudaStreamQuery(c->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) {
+          set_error("growth round failed: %s", cudaGetErrorString(e));
+          return QR_ECUDA;
+        }
+        if (e == cudaSuccess && flags[j] != c->round_id) {
+          set_error("internal: growth round finished without publishing task %u", j);
+          return QR_ECUDA;
+        }
+      }
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return QR_OK;
+}
+
 static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, bool slots_ready,
                                 double built_docs) {
   const uint32_t F = (uint32_t) c->F;
@@ -158,25 +182,7 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
       QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       QR_CUDA(cudaStreamSynchronize(c->stream));
     }
-    // wait for the k flags (bounded spin; a launch failure surfaces through cudaStreamQuery)
-    volatile uint32_t *flags = c->h_flags;
-    uint64_t spins = 0;
-    for (uint32_t j = 0; j < k; ++j) {
-      while (flags[j] != c->round_id) {
-        if ((++spins & 0xfffff) == 0) {
-          cudaError_t e = cudaStreamQuery(c->stream);
-          if (e != cudaSuccess && e != cudaErrorNotReady) {
-            set_error("finalize failed: %s", cudaGetErrorString(e));
-            return QR_ECUDA;
-          }
-          if (e == cudaSuccess && flags[j] != c->round_id) {
-            set_error("internal: finalize finished without publishing task %u", j);
-            return QR_ECUDA;
-          }
-        }
-      }
-    }
-    std::atomic_thread_fence(std::memory_order_acquire);
+    QR_TRY(wait_round_flags(c, k));
   }
   return QR_OK;
 }
@@ -308,6 +314,37 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
   } else {
     QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
   }
+  // one launch for the whole round (qr_round_kernel.cuh) when the per-phase breakdown is not asked for
+  const size_t fused_smem = (size_t) c->fpp * c->max_thr * 12;
+  const bool fused = c->fused_rounds && onepass && build_child_hists && !c->profiling && !g_trace_on &&
+                     fused_smem <= 200 * 1024 && hist_blk <= c->max_slices - c->max_tasks;
+  if (fused) {
+    c->part_epoch++;
+    c->round_id++;
+    // QR_FUSE_PARTITION=1 also chains the partition inside the launch; by default it stays a kernel of its
+    // own: its 256-thread blocks without shared memory fit 6 to an SM, the round kernel's blocks only 2
+    const bool fuse_partition = c->fuse_partition;
+    const uint32_t fused_part = fuse_partition ? part_blk : 0u;
+    const uint32_t grid = fused_part + hist_blk * c->npanels;
+    RoundCounters rc{c->d_part_done, c->d_panel_done, c->d_task_done};
+    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+      using B = decltype(tag);
+      if (!fuse_partition) {
+        QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
+                  c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
+                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack);
+        c->ticket_base += part_blk;
+      }
+      QR_LAUNCH(c, PH_HIST, round_kernel<B>, grid, kRoundThreads, fused_smem, c->d_tasks, k, fused_part, hist_blk, c->d_panels,
+                c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, (uint32_t) c->F, c->npanels, c->d_hist_sum,
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, c->d_part_status, c->d_ticket, c->ticket_base,
+                c->part_epoch, rc, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t, c->d_fbest_lc,
+                c->d_totals, c->d_res_mapped, c->d_flags_mapped, c->round_id, c->pack);
+      return QR_OK;
+    }));
+    c->ticket_base += grid;
+    QR_TRY(wait_round_flags(c, k));
+  } else {
   {
     PhaseTimer pt(c, PH_PARTITION);
     QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
@@ -334,6 +371,7 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
   } else if (c->comm) {
     QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     QR_CUDA(cudaStreamSynchronize(c->stream));
+  }
   }
   c->pack.n = 0;
   for (uint32_t j = 0; j < k; ++j) {

@@ -385,3 +385,26 @@ def test_device_growth_equals_host_growth(algo, leaves, minls, monkeypatch):
         if a is not None:
             for k in ("feature", "threshold_idx", "left", "right", "value", "count"):
                 assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("fuse_partition", [False, True])
+def test_fused_round_kernel_equals_three_kernels(fuse_partition, monkeypatch):
+    """qr_round_kernel.cuh chains histogram -> split scan (and optionally partition) inside one launch per
+    growth round; same arithmetic as the separate kernels, so identical trees and scores."""
+    x, l, off = common.dataset(n=30000, f=23, q=300)
+    runs = []
+    for fused in (False, True):
+        monkeypatch.delenv("QR_FUSED_ROUNDS", raising=False)
+        monkeypatch.delenv("QR_FUSE_PARTITION", raising=False)
+        if fused:
+            monkeypatch.setenv("QR_FUSED_ROUNDS", "1")
+            if fuse_partition:
+                monkeypatch.setenv("QR_FUSE_PARTITION", "1")
+        with api.Trainer(x, l, off, algo="LAMBDAMART", nleaves=64, cutoff=10, hist_mode=api.HIST_FAST) as tr:
+            trees = [tr.boost_iteration()[0] for _ in range(5)]
+            runs.append((trees, tr.get_scores(), tr.get_leaf_assignment()))
+    (ta, sa, la), (tb, sb, lb) = runs
+    assert np.array_equal(sa, sb) and np.array_equal(la, lb)
+    for a, b in zip(ta, tb):
+        for k in ("feature", "threshold_idx", "left", "right", "value", "count"):
+            assert np.array_equal(a[k], b[k]), k
