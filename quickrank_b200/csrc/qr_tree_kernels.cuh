@@ -602,8 +602,8 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
   const uint32_t f = gw / kFinParts, part = gw % kFinParts;
   const double inv = EXACT ? 1.0 : ldexp(1.0, -*qexp);
   const int nchild = t.whole ? 1 : 2;
-  __shared__ double wb[kFinWarps];
-  __shared__ uint32_t wt[kFinWarps], wt2[kFinWarps], wl2[kFinWarps];
+  __shared__ double wb[2][kFinWarps];
+  __shared__ uint32_t wt[2][kFinWarps], wt2[2][kFinWarps], wl2[2][kFinWarps];
   __shared__ uint32_t s_last;
 
   // Features with at most kFinChunks * 32 cells are processed entirely in registers: every load is
@@ -817,63 +817,78 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // every load of this tail is issued before anything waits on one: squares partials, node totals and
+  // the per-feature winners of BOTH children travel together (the tail is a chain of L2 round trips)
+  const uint32_t FP = F * kFinParts;
   double sqB = 0.0;
-  if (EXACT) {
-    sqB = sq_exact[t.sq0];
-  } else {
-    U128 tot{0ull, 0ull};
-    for (uint32_t i = 0; i < t.hist_nblk; ++i) { const ulonglong2 v = sq128[t.hist_blk0 + i]; u128_add(tot, v.x, v.y); }
-    const double inv2 = ldexp(1.0, -2 * *qexp);
-    sqB = ((double) tot.hi * 18446744073709551616.0 + (double) tot.lo) * inv2;
+  if (threadIdx.x < 2) {
+    if (EXACT) {
+      sqB = sq_exact[t.sq0];
+    } else {
+      U128 tot{0ull, 0ull};
+      for (uint32_t i = 0; i < t.hist_nblk; ++i) { const ulonglong2 v = sq128[t.hist_blk0 + i]; u128_add(tot, v.x, v.y); }
+      const double inv2 = ldexp(1.0, -2 * *qexp);
+      sqB = ((double) tot.hi * 18446744073709551616.0 + (double) tot.lo) * inv2;
+    }
+  }
+  ulonglong2 tv = make_ulonglong2(0ull, 0ull);
+  if ((int) threadIdx.x < nchild) {
+    const volatile ulonglong2 *tp = totals + (size_t) task * 2 + threadIdx.x;
+    tv.x = tp->x; tv.y = tp->y;
   }
   // entries are ordered by (feature, part) = (feature, ascending threshold range): the first maximum
   // in that order is the reference's winner
-  const uint32_t FP = F * kFinParts;
-  for (int child = 0; child < nchild; ++child) {
-    const volatile double *fs = fbest_score + ((size_t) task * 2 + child) * FP;
-    const volatile uint32_t *ft = fbest_t + ((size_t) task * 2 + child) * FP;
-    const volatile uint32_t *fl = fbest_lc + ((size_t) task * 2 + child) * FP;
-    double best = -1.0;
-    uint32_t bf = 0xffffffffu, bt = 0xffffffffu, blc = 0;
-    for (uint32_t ff = threadIdx.x; ff < FP; ff += kFinWarps * 32) {
-      const double sc = fs[ff];
-      if (sc > best) { best = sc; bf = ff; bt = ft[ff]; blc = fl[ff]; }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const uint32_t of = __shfl_xor_sync(0xffffffffu, bf, o);
-      const uint32_t ot = __shfl_xor_sync(0xffffffffu, bt, o);
-      const uint32_t ol = __shfl_xor_sync(0xffffffffu, blc, o);
-      if (ob > best || (ob == best && of < bf)) { best = ob; bf = of; bt = ot; blc = ol; }
-    }
-    if (lane == 0) { wb[warp] = best; wt[warp] = bf; wt2[warp] = bt; wl2[warp] = blc; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < (int) kFinWarps; ++w)
-        if (wb[w] > best || (wb[w] == best && wt[w] < bf)) { best = wb[w]; bf = wt[w]; bt = wt2[w]; blc = wl2[w]; }
-      const bool built = t.whole || ((child == 0) == (t.build_left != 0));
-      const volatile ulonglong2 *tv = totals + (size_t) task * 2 + child;
-      SplitResult r;
-      r.n = tv->x;
-      r.sum = cell_value(EXACT, tv->y, inv);
-      r.squares = built ? sqB : t.parent_squares - sqB;          // rtnode_histogram.cc:86,207
-      r.deviance = r.squares - r.sum * r.sum / (double) r.n;      // rtnode.h:106
-      r.score = best;
-      r.valid = best != -1.0;
-      r.feature = bf == 0xffffffffu ? bf : bf / kFinParts;
-      r.threshold_idx = r.valid ? bt : 0xffffffffu;
-      r.lcount = r.valid ? blc : 0;
-      r.pad = 0;
-      res[(size_t) task * 2 + child] = r;
-      if (child == nchild - 1) {
-        task_done[task] = 0u;   // ready for the next round
-        if (host_flags) {       // res lives in mapped host memory: publish it to the polling host thread
-          __threadfence_system();
-          host_flags[task] = round_id;
-        }
+  double best[2] = {-1.0, -1.0};
+  uint32_t bf[2] = {0xffffffffu, 0xffffffffu}, bt[2] = {0xffffffffu, 0xffffffffu}, blc[2] = {0u, 0u};
+  for (uint32_t ff = threadIdx.x; ff < FP; ff += kFinWarps * 32) {
+#pragma unroll
+    for (int child = 0; child < 2; ++child) {
+      if (child < nchild) {
+        const size_t o = ((size_t) task * 2 + child) * FP + ff;
+        const double sc = ((const volatile double *) fbest_score)[o];
+        const uint32_t tt = ((const volatile uint32_t *) fbest_t)[o];
+        const uint32_t ll = ((const volatile uint32_t *) fbest_lc)[o];
+        if (sc > best[child]) { best[child] = sc; bf[child] = ff; bt[child] = tt; blc[child] = ll; }
       }
     }
-    __syncthreads();
+  }
+#pragma unroll
+  for (int child = 0; child < 2; ++child) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best[child], o);
+      const uint32_t of = __shfl_xor_sync(0xffffffffu, bf[child], o);
+      const uint32_t ot = __shfl_xor_sync(0xffffffffu, bt[child], o);
+      const uint32_t ol = __shfl_xor_sync(0xffffffffu, blc[child], o);
+      if (ob > best[child] || (ob == best[child] && of < bf[child])) { best[child] = ob; bf[child] = of; bt[child] = ot; blc[child] = ol; }
+    }
+    if (lane == 0) { wb[child][warp] = best[child]; wt[child][warp] = bf[child]; wt2[child][warp] = bt[child]; wl2[child][warp] = blc[child]; }
+  }
+  __syncthreads();
+  if ((int) threadIdx.x < nchild) {   // thread c finishes child c
+    const int child = (int) threadIdx.x;
+    double b = wb[child][0];
+    uint32_t f1 = wt[child][0], t1 = wt2[child][0], l1 = wl2[child][0];
+    for (int w = 1; w < (int) kFinWarps; ++w)
+      if (wb[child][w] > b || (wb[child][w] == b && wt[child][w] < f1)) { b = wb[child][w]; f1 = wt[child][w]; t1 = wt2[child][w]; l1 = wl2[child][w]; }
+    const bool built = t.whole || ((child == 0) == (t.build_left != 0));
+    SplitResult r;
+    r.n = tv.x;
+    r.sum = cell_value(EXACT, tv.y, inv);
+    r.squares = built ? sqB : t.parent_squares - sqB;          // rtnode_histogram.cc:86,207
+    r.deviance = r.squares - r.sum * r.sum / (double) r.n;      // rtnode.h:106
+    r.score = b;
+    r.valid = b != -1.0;
+    r.feature = f1 == 0xffffffffu ? f1 : f1 / kFinParts;
+    r.threshold_idx = r.valid ? t1 : 0xffffffffu;
+    r.lcount = r.valid ? l1 : 0;
+    r.pad = 0;
+    res[(size_t) task * 2 + child] = r;
+    if (host_flags) __threadfence_system();   // res lives in mapped host memory
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    task_done[task] = 0u;   // ready for the next round
+    if (host_flags) host_flags[task] = round_id;   // publish to the polling host thread
   }
 }
 
