@@ -159,6 +159,21 @@ class Svml {
   void write(std::shared_ptr<data::Dataset> dataset, const std::string &filename);
 };
 
+// XML model -> C source of `double ranker(float *v)`, the function quickscore times
+// (src/scoring/ranker.cc is the stub it replaces at link time; quickscore.cc:100-106).
+// generate_conditional_operators.cc:28-115: one nested `v[f] <= thr ? left : right` expression per tree,
+// tree weights printed as float with 3 decimals.
+class GenOpCond {
+ public:
+  void generate_conditional_operators_code(const std::string model_filename, const std::string code_filename);
+};
+// generate_oblivious.cc:137-330: per-tree arrays (weights, leaf outputs, feature ids, thresholds) sorted by
+// tree depth and a `leaf_id` that packs the `v[f] > thr` bits MSB-first.
+class GenOblivious {
+ public:
+  void generate_oblivious_code(const std::string model_filename, const std::string code_filename);
+};
+
 }  // namespace io
 }  // namespace quickrank
 

@@ -41,6 +41,15 @@ int main(int argc, char **argv) {
   auto get = [&](const char *k, const char *def) { auto it = opt.find(k); return it == opt.end() ? std::string(def) : it->second; };
   auto geti = [&](const char *k, size_t def) { auto it = opt.find(k); return it == opt.end() ? def : (size_t) strtoull(it->second.c_str(), nullptr, 10); };
 
+  // code generation (driver.cc:199-223): --model-file m.xml --code-file ranker.cc [--generator condop|oblivious]
+  if (opt.count("model-file") && opt.count("code-file")) {
+    const std::string gen = get("generator", "condop");
+    std::cout << "# Generating code (" << gen << ") from " << opt["model-file"] << " into " << opt["code-file"] << std::endl;
+    if (gen == "condop") io::GenOpCond().generate_conditional_operators_code(opt["model-file"], opt["code-file"]);
+    else if (gen == "oblivious") io::GenOblivious().generate_oblivious_code(opt["model-file"], opt["code-file"]);
+    else { std::cerr << "!!! Generator " << gen << " is not supported (condop, oblivious)." << std::endl; return EXIT_FAILURE; }
+    return EXIT_SUCCESS;
+  }
   const std::string algo = get("algo", "LAMBDAMART");
   const size_t ntrees = geti("num-trees", 1000), nthr = geti("num-thresholds", 0), minls = geti("min-leaf-support", 1);
   const size_t esr = geti("end-after-rounds", 100), nleaves = geti("num-leaves", 10), depth = geti("tree-depth", 3);

@@ -1260,4 +1260,185 @@ std::shared_ptr<LTR_Algorithm> LTR_Algorithm::load_model_from_file(std::string m
 }
 
 }  // namespace learning
+
+// ------------------------------------------------------------------------------------------
+// C code generators (src/io/generate_conditional_operators.cc, src/io/generate_oblivious.cc)
+// ------------------------------------------------------------------------------------------
+namespace io {
+
+using learning::forests::XmlModel;
+using learning::forests::XmlNode;
+
+static std::unique_ptr<XmlNode> load_ranker(const std::string &model_filename) {
+  if (model_filename.empty()) {
+    std::cerr << "!!! Model filename is empty." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  std::ifstream f(model_filename);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  XmlModel model;
+  if (!f || !learning::forests::parse_xml(ss.str(), &model) || !model.root || model.root->name != "ranker") {
+    std::cerr << "!!! Model " + model_filename + " is not parsed correctly." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  return std::move(model.root);
+}
+
+static const XmlNode *child_at(const XmlNode &n, const char *pos) {
+  for (auto &k : n.kids)
+    if (k->name == "split") {
+      auto it = k->attr.find("pos");
+      if (it != k->attr.end() && it->second == pos) return k.get();
+    }
+  return nullptr;
+}
+static bool is_leaf(const XmlNode &n) { return n.child("output") != nullptr; }
+
+// generate_conditional_operators.cc:28-76
+static void node_to_condop(const XmlNode &n, std::ostream &os) {
+  if (is_leaf(n)) { os << n.child_text("output"); return; }
+  const unsigned feature_id = (unsigned) strtoul(n.child_text("feature", "0").c_str(), nullptr, 10);
+  std::string threshold = n.child_text("threshold");
+  if (threshold.find(".") == std::string::npos) threshold += ".0";   // integer-looking values (:50-53)
+  const XmlNode *left = child_at(n, "left"), *right = child_at(n, "right");
+  os << "( v[" << feature_id - 1 << "] <= " << threshold << "f" << " ? ";
+  if (left) node_to_condop(*left, os);
+  os << " : ";
+  if (right) node_to_condop(*right, os);
+  os << " )";
+}
+
+void GenOpCond::generate_conditional_operators_code(const std::string model_filename, const std::string code_filename) {
+  std::unique_ptr<XmlNode> ranker = load_ranker(model_filename);
+  std::stringstream source_code;
+  source_code.setf(std::ios::floatfield, std::ios::fixed);
+  source_code << "double ranker(float* v) {" << std::endl;
+  source_code << "\treturn 0.0 ";
+  const XmlNode *ensemble = ranker->child("ensemble");
+  if (ensemble)
+    for (auto &tree : ensemble->kids) {
+      if (tree->name != "tree") continue;
+      auto w = tree->attr.find("weight");
+      const float tree_weight = w != tree->attr.end() ? (float) strtod(w->second.c_str(), nullptr) : 0.f;
+      const XmlNode *content = tree->child("split");
+      if (content) {
+        source_code << std::endl << "\t\t + " << std::setprecision(3) << tree_weight << "f * ";
+        node_to_condop(*content, source_code);
+      }
+    }
+  source_code << ";" << std::endl << "}" << std::endl;
+  std::ofstream output(code_filename, std::ofstream::out);
+  output << source_code.str();
+}
+
+// generate_oblivious.cc:31-135: the three walks (all leaves left to right; features / thresholds down the
+// left spine — the trees are symmetric)
+static void obv_leaves(const XmlNode &n, std::vector<std::string> &leaves) {
+  if (is_leaf(n)) { leaves.push_back(n.child_text("output")); return; }
+  if (const XmlNode *l = child_at(n, "left")) obv_leaves(*l, leaves);
+  if (const XmlNode *r = child_at(n, "right")) obv_leaves(*r, leaves);
+}
+static void obv_spine(const XmlNode &n, std::vector<unsigned> &features, std::vector<std::string> &thresholds) {
+  if (is_leaf(n)) return;
+  features.push_back((unsigned) strtoul(n.child_text("feature", "0").c_str(), nullptr, 10) - 1);
+  thresholds.push_back(n.child_text("threshold"));
+  if (const XmlNode *l = child_at(n, "left")) obv_spine(*l, features, thresholds);
+}
+
+void GenOblivious::generate_oblivious_code(const std::string model_filename, const std::string code_filename) {
+  std::unique_ptr<XmlNode> ranker = load_ranker(model_filename);
+  std::stringstream source_code;
+  source_code.setf(std::ios::floatfield, std::ios::fixed);
+  const XmlNode *info = ranker->child("info");
+  const unsigned depth = info ? (unsigned) strtoul(info->child_text("depth", "0").c_str(), nullptr, 10) : 0;
+  const unsigned max_leaves = 1u << depth;
+  const XmlNode *ensemble = ranker->child("ensemble");
+  std::vector<float> tree_weights;
+  std::vector<int> tree_depths;
+  std::vector<std::vector<std::string>> tree_outputs, thresholds;
+  std::vector<std::vector<unsigned>> feature_ids;
+  if (ensemble)
+    for (auto &tree : ensemble->kids) {
+      if (tree->name != "tree") continue;
+      auto w = tree->attr.find("weight");
+      tree_weights.push_back(w != tree->attr.end() ? (float) strtod(w->second.c_str(), nullptr) : 0.f);
+      const XmlNode *root = tree->child("split");
+      tree_outputs.emplace_back(); feature_ids.emplace_back(); thresholds.emplace_back();
+      if (root) {
+        obv_leaves(*root, tree_outputs.back());
+        obv_spine(*root, feature_ids.back(), thresholds.back());
+      }
+      // splits along the left spine; the reference's walk (:170-181) never returns less than 1
+      tree_depths.push_back(std::max<int>(1, (int) feature_ids.back().size()));
+    }
+  const int actual_model_size = (int) tree_depths.size();
+  if (actual_model_size == 0) {
+    std::cerr << "!!! The model has no trees." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  // trees in order of depth (:210-216; same std::sort call on the same data, hence the same order)
+  std::vector<size_t> tree_mapping(tree_depths.size());
+  std::iota(tree_mapping.begin(), tree_mapping.end(), 0);
+  std::sort(tree_mapping.begin(), tree_mapping.end(), [&tree_depths](int a, int b) { return tree_depths[a] < tree_depths[b]; });
+  std::vector<size_t> depths_population;   // number of trees of each depth (:219-233)
+  const int max_depth = tree_depths[tree_mapping.back()];
+  int curr_depth = 1;
+  size_t start_position = 0;
+  for (size_t i = 0; i < tree_mapping.size(); i++) {
+    while (tree_depths[tree_mapping[i]] > curr_depth) {
+      depths_population.push_back(i - start_position);
+      curr_depth++;
+      start_position = i;
+    }
+    if (curr_depth == max_depth) break;
+  }
+  depths_population.push_back(tree_mapping.size() - start_position);
+
+  source_code << "#define N " << actual_model_size << " // no. of trees" << std::endl;
+  source_code << "#define M " << depth << " // max tree depth" << std::endl;
+  source_code << "#define F " << max_leaves << " // max number of leaves" << std::endl << std::endl;
+  source_code << std::setprecision(std::numeric_limits<float>::max_digits10);
+  source_code << "const float tree_weights[N] = { ";
+  for (size_t i = 0; i < tree_weights.size(); i++) {
+    if (i != 0) source_code << ", ";
+    source_code << tree_weights[tree_mapping[i]];
+  }
+  source_code << " };" << std::endl << std::endl;
+  auto emit = [&](const char *decl, auto &rows) {
+    source_code << decl << std::endl << '\t';
+    for (size_t i = 0; i < rows.size(); i++) {
+      if (i != 0) source_code << "," << std::endl << '\t';
+      source_code << "\t{ ";
+      for (size_t j = 0; j < rows[tree_mapping[i]].size(); j++) {
+        if (j != 0) source_code << ", ";
+        source_code << rows[tree_mapping[i]][j];
+      }
+      source_code << " }";
+    }
+    source_code << std::endl << "};" << std::endl << std::endl;
+  };
+  emit("const double leaf_outputs[N][F] = { ", tree_outputs);
+  emit("const unsigned int features_ids[N][M] = { ", feature_ids);
+  emit("const float thresholds[N][M] = { ", thresholds);
+  source_code << "#define SHL(n,p) ((n)<<(p))" << std::endl << std::endl;
+  source_code << "unsigned int leaf_id(float *v, unsigned int const *fids, float const *thresh, const unsigned int m) {"
+              << std::endl << "  unsigned int leafidx=0;" << std::endl
+              << "  for (unsigned int i=0; i<m; ++i)" << std::endl
+              << "    leafidx |= SHL( v[fids[i]]>thresh[i], m-1-i);" << std::endl
+              << "  return leafidx;" << std::endl << "}" << std::endl << std::endl;
+  source_code << "double ranker(float *v) {" << std::endl << "  double score = 0.0;" << std::endl << "  int i = 0;" << std::endl;
+  for (int d = 0; d < max_depth; d++) {
+    source_code << "  for (int j = 0; j < " << depths_population[d] << "; ++j) {" << std::endl;
+    source_code << "    score += tree_weights[i] * leaf_outputs[i][leaf_id(v, features_ids[i], thresholds[i], " << d + 1
+                << ")];" << std::endl;
+    source_code << "    i++;" << std::endl;
+    source_code << "  }" << std::endl;
+  }
+  source_code << "  return score;" << std::endl << "}" << std::endl;
+  std::ofstream output(code_filename, std::ofstream::out);
+  output << source_code.str();
+}
+
+}  // namespace io
 }  // namespace quickrank

@@ -78,6 +78,7 @@ def lib():
         L.qref_num_recorded.argtypes = [vp, C.c_int]
         L.qref_recorded_get.argtypes = [vp, C.c_int, u64, dp]
         L.qref_save_model.argtypes = [vp, C.c_char_p]
+        L.qref_generate_code.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
         L.qref_score_with_model.argtypes = [C.c_char_p, fp, u64, u64, dp]
         L.qref_dcg.restype = C.c_double
         L.qref_dcg.argtypes = [fp, dp, u64, u64]
@@ -218,6 +219,11 @@ class RefSession:
 
     def save_model(self, path):
         lib().qref_save_model(self.h, path.encode())
+
+
+def generate_code(xml_path, code_path, kind):
+    """The reference's own XML -> C generators (kind: "condop" | "oblivious")."""
+    lib().qref_generate_code(xml_path.encode(), code_path.encode(), {"condop": 0, "oblivious": 1}[kind])
 
 
 def score_with_model(xml_path, x):

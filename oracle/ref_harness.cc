@@ -26,6 +26,8 @@
 #include "learning/forests/lambdamart.h"
 #include "learning/forests/obliviousmart.h"
 #include "learning/forests/obliviouslambdamart.h"
+#include "io/generate_conditional_operators.h"
+#include "io/generate_oblivious.h"
 #include "learning/forests/dart.h"
 #include "utils/radix.h"
 #include "driver/driver.h"
@@ -411,6 +413,13 @@ void qref_recorded_get(void *h, int kind, uint64_t it, double *out) {
   auto *r = ((Session *) h)->rec();
   auto &v = kind == 0 ? r->lambdas[it] : kind == 1 ? r->weights[it] : r->scores[it];
   memcpy(out, v.data(), v.size() * sizeof(double));
+}
+
+// ---- the reference's C code generators (src/io/generate_*.cc); kind 0: condop, 1: oblivious ----
+int qref_generate_code(const char *model, const char *code, int kind) {
+  if (kind == 0) quickrank::io::GenOpCond().generate_conditional_operators_code(model, code);
+  else quickrank::io::GenOblivious().generate_oblivious_code(model, code);
+  return 0;
 }
 
 // ---- model I/O and scoring through the reference's own code ----

@@ -377,8 +377,15 @@ class xml_node_range {
    public:
     iterator(const std::vector<impl::node_rec *> *v, size_t i, const char *filt)
         : v_(v), i_(i), filt_(filt) { skip(); cur_ = at(); }
-    const xml_node &operator*() const { return cur_; }
-    const xml_node *operator->() const { return &cur_; }
+    // iterator traits and a non-const dereference, as pugixml's xml_node_iterator has them
+    typedef std::ptrdiff_t difference_type;
+    typedef xml_node value_type;
+    typedef xml_node *pointer;
+    typedef xml_node &reference;
+    typedef std::forward_iterator_tag iterator_category;
+    xml_node &operator*() const { return cur_; }
+    xml_node *operator->() const { return &cur_; }
+    iterator operator++(int) { iterator t = *this; ++*this; return t; }
     iterator &operator++() { ++i_; skip(); cur_ = at(); return *this; }
     bool operator!=(const iterator &o) const { return i_ != o.i_; }
     bool operator==(const iterator &o) const { return i_ == o.i_; }
@@ -395,7 +402,7 @@ class xml_node_range {
     const std::vector<impl::node_rec *> *v_;
     size_t i_;
     const char *filt_;
-    xml_node cur_;
+    mutable xml_node cur_;
   };
   xml_node_range(const std::vector<impl::node_rec *> *v, const char *filt)
       : v_(v), filt_(filt ? filt : ""), has_filt_(filt != nullptr) {}
