@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1
-tail -8 gpurun_out/pytest_gpu.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -p no:cacheprovider -k "edge_case" > gpurun_out/pytest_edge.log 2>&1
+tail -30 gpurun_out/pytest_edge.log | cut -c1-220

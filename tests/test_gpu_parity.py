@@ -408,3 +408,67 @@ def test_fused_round_kernel_equals_three_kernels(fuse_partition, monkeypatch):
     for a, b in zip(ta, tb):
         for k in ("feature", "threshold_idx", "left", "right", "value", "count"):
             assert np.array_equal(a[k], b[k]), k
+
+
+def _edge_cases():
+    rng = np.random.default_rng(77)
+    cases = {}
+    # one query only
+    x = (rng.integers(0, 256, size=(300, 5)) / 255.0).astype(np.float32)
+    cases["single_query"] = (x, rng.integers(0, 5, size=300).astype(np.float32), np.array([0, 300], np.uint64))
+    # ragged: queries of 1, 2 and 17 documents (17 = first length libstdc++'s introsort permutes ties), one of 600
+    lens = [1, 2, 17, 1, 600, 3, 16, 40]
+    n = sum(lens)
+    x = (rng.integers(0, 256, size=(n, 7)) / 255.0).astype(np.float32)
+    cases["ragged"] = (x, rng.integers(0, 5, size=n).astype(np.float32), np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64))
+    # a query whose labels are all zero (idcg = 0: contributes 0 to NDCG and no lambdas) next to normal ones
+    lab = rng.integers(0, 4, size=400).astype(np.float32)
+    lab[100:250] = 0
+    x = (rng.integers(0, 256, size=(400, 6)) / 255.0).astype(np.float32)
+    cases["zero_label_query"] = (x, lab, np.array([0, 100, 250, 400], np.uint64))
+    # one feature; and a dataset whose only informative feature is accompanied by constant columns
+    x = (rng.integers(0, 256, size=(500, 1)) / 255.0).astype(np.float32)
+    cases["one_feature"] = (x, (x[:, 0] > 0.5).astype(np.float32) + (x[:, 0] > 0.8), np.array([0, 120, 260, 500], np.uint64))
+    x = np.zeros((500, 4), np.float32)
+    x[:, 2] = (rng.integers(0, 256, size=500) / 255.0).astype(np.float32)
+    cases["constant_columns"] = (x, (x[:, 2] > 0.6).astype(np.float32) * 2, np.array([0, 250, 500], np.uint64))
+    # nothing to learn from: all features constant -> every tree is a single leaf
+    cases["all_constant"] = (np.full((200, 3), 0.5, np.float32), rng.integers(0, 3, size=200).astype(np.float32),
+                             np.array([0, 90, 200], np.uint64))
+    return cases
+
+
+@pytest.mark.parametrize("case", sorted(_edge_cases()))
+@pytest.mark.parametrize("algo,leaves,minls", [("LAMBDAMART", 6, 1), ("MART", 2, 1), ("LAMBDAMART", 8, 1000)])
+def test_edge_case_datasets(case, algo, leaves, minls):
+    """Degenerate and ragged inputs (single query, 1-document queries, all-zero labels, one feature, constant
+    columns, nothing splittable, a minimum leaf support no split can meet): REFERENCE-order accumulation
+    reproduces the oracle's trees node for node, and the metric / scores agree within 1e-5."""
+    x, l, off = _edge_cases()[case]
+    T = 4
+    want_trees, want_metric, want_scores = po.train(algo, x, l, off, T, nleaves=leaves, minls=minls, cutoff=10)
+    col = np.ascontiguousarray(x.T)
+    ob = po.Binning(col, 0)
+    bins = ob.bins()
+    scores = np.zeros(len(l))
+    with api.Trainer(x, l, off, algo=algo, nleaves=leaves, minleafsupport=minls, cutoff=10,
+                     hist_mode=api.HIST_REFERENCE) as tr:
+        for m in range(T):
+            tree, metric = tr.boost_iteration()
+            if m == 0:   # pseudo-responses are bit-identical on the first iteration: so is the tree
+                assert common.same_structure(tree, want_trees[m]), common.describe_tree_diff(tree, want_trees[m])
+            else:        # later: CUDA's and glibc's exp() differ in the last bit; only audited ties may differ
+                lam = po.lambdas(scores, l, off, 10)[0] if algo == "LAMBDAMART" else l.astype(np.float64) - scores
+                _equiv, near, _clean = common.audit_tree(tree, want_trees[m], ob, bins, lam, minls)
+                assert near == 0, "tree %d" % m
+            og, ow = common.tree_outputs(tree, bins), common.tree_outputs(want_trees[m], bins)
+            assert np.allclose(og, ow, rtol=REL, atol=1e-300)
+            assert abs(metric - want_metric[m]) <= REL * max(abs(want_metric[m]), 1e-300)
+            scores = po.update_scores(want_trees[m], col, 0.1, scores)
+        got = tr.get_scores()
+    assert np.max(np.abs(got - want_scores)) <= REL * max(np.max(np.abs(want_scores)), 1e-300)
+    # and the default fixed-point mode runs the same inputs to the same quality
+    with api.Trainer(x, l, off, algo=algo, nleaves=leaves, minleafsupport=minls, cutoff=10, hist_mode=api.HIST_FAST) as tr:
+        for m in range(T):
+            _tree, metric = tr.boost_iteration()
+        assert abs(metric - want_metric[-1]) <= 1e-3 + REL * abs(want_metric[-1])
