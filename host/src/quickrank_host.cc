@@ -13,6 +13,7 @@
 #include <map>
 #include <numeric>
 #include <sstream>
+#include <thread>
 
 namespace quickrank {
 
@@ -150,58 +151,126 @@ std::ostream &Ndcg::put(std::ostream &os) const {
 // ------------------------------------------------------------------------------------------------
 namespace io {
 
+// Svml::read_horizontal (svml.cc:38-161).  Same grammar and error exits (2: malformed label / qid,
+// 4: malformed feature), but the file is read once into memory and its lines are parsed by all host
+// threads (QR_SVML_THREADS, default: hardware concurrency): the reference's getline + sscanf loop takes
+// minutes on a config-2-sized text file, longer than training on the GPU does.
+namespace {
+struct SvmlChunk {
+  std::vector<QueryID> qids;
+  std::vector<Label> labels;
+  std::vector<size_t> row_start;                          // per row, index into fids/vals; one extra entry at the end
+  std::vector<uint32_t> fids;
+  std::vector<Feature> vals;
+  size_t maxfid = 0;
+  int error = 0;
+};
+
+// parses the lines of [p, end); `end` is a line boundary (or the end of the buffer, which is NUL-terminated)
+void parse_svml_range(char *p, char *end, SvmlChunk &out) {
+  while (p < end) {
+    char *eol = (char *) memchr(p, '\n', (size_t) (end - p));
+    if (!eol) eol = end;
+    char *q = p;
+    p = eol < end ? eol + 1 : end;
+    *eol = '\0';
+    while (*q == ' ' || *q == '\t') ++q;
+    if (*q == '#' || *q == '\0' || *q == '\r') continue;
+    char *hash = strchr(q, '#');
+    if (hash) *hash = '\0';
+    char *e = nullptr;
+    const Label rel = (Label) strtod(q, &e);
+    if (e == q) { out.error = 2; return; }
+    q = e;
+    while (*q == ' ' || *q == '\t') ++q;
+    if (strncmp(q, "qid:", 4) != 0) { out.error = 2; return; }
+    const QueryID qid = (QueryID) strtoull(q + 4, &e, 10);
+    q = e;
+    out.row_start.push_back(out.fids.size());
+    for (;;) {
+      while (*q == ' ' || *q == '\t' || *q == '\r') ++q;
+      if (*q == '\0') break;
+      const size_t fid = (size_t) strtoull(q, &e, 10);
+      if (e == q || *e != ':') { out.error = 4; return; }
+      q = e + 1;
+      const Feature v = strtof(q, &e);
+      if (e == q || fid == 0) { out.error = 4; return; }
+      q = e;
+      out.fids.push_back((uint32_t) fid);
+      out.vals.push_back(v);
+      out.maxfid = std::max(out.maxfid, fid);
+    }
+    out.qids.push_back(qid);
+    out.labels.push_back(rel);
+  }
+  out.row_start.push_back(out.fids.size());
+}
+}  // namespace
+
 std::unique_ptr<data::Dataset> Svml::read_horizontal(const std::string &filename) {
-  FILE *f = fopen(filename.c_str(), "r");
+  FILE *f = fopen(filename.c_str(), "rb");
   if (!f) {
     std::cerr << "!!! Error while opening file " << filename << "." << std::endl;
     exit(EXIT_FAILURE);
   }
-  std::vector<QueryID> qids;
-  std::vector<Label> labels;
-  std::vector<std::vector<std::pair<size_t, Feature>>> rows;
-  size_t maxfid = 0;
-  char *line = nullptr;
-  size_t cap = 0;
-  ssize_t nread;
-  while ((nread = getline(&line, &cap, f)) > 0) {
-    char *p = line;
-    while (*p == ' ' || *p == '\t') ++p;
-    if (*p == '#' || *p == '\n' || *p == '\0' || *p == '\r') continue;
-    char *hash = strchr(p, '#');
-    if (hash) *hash = '\0';
-    char *end = nullptr;
-    const Label rel = (Label) strtod(p, &end);
-    if (end == p) exit(2);
-    p = end;
-    while (*p == ' ' || *p == '\t') ++p;
-    if (strncmp(p, "qid:", 4) != 0) exit(2);
-    const QueryID qid = (QueryID) strtoull(p + 4, &end, 10);
-    p = end;
-    std::vector<std::pair<size_t, Feature>> row;
-    for (;;) {
-      while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') ++p;
-      if (*p == '\0') break;
-      const size_t fid = (size_t) strtoull(p, &end, 10);
-      if (end == p || *end != ':') exit(4);
-      p = end + 1;
-      const Feature v = strtof(p, &end);
-      if (end == p || fid == 0) exit(4);
-      p = end;
-      row.emplace_back(fid, v);
-      maxfid = std::max(maxfid, fid);
-    }
-    qids.push_back(qid);
-    labels.push_back(rel);
-    rows.push_back(std::move(row));
+  fseek(f, 0, SEEK_END);
+  const long fsize = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<char> buf((size_t) std::max<long>(fsize, 0) + 1);
+  if (fsize > 0 && fread(buf.data(), 1, (size_t) fsize, f) != (size_t) fsize) {
+    std::cerr << "!!! Error while reading file " << filename << "." << std::endl;
+    exit(EXIT_FAILURE);
   }
-  free(line);
   fclose(f);
-  std::unique_ptr<data::Dataset> ds(new data::Dataset(rows.size(), maxfid));
-  std::vector<Feature> dense(maxfid);
-  for (size_t i = 0; i < rows.size(); ++i) {
-    std::fill(dense.begin(), dense.end(), 0.0f);
-    for (auto &kv : rows[i]) dense[kv.first - 1] = kv.second;
-    ds->addInstance(qids[i], labels[i], dense);
+  buf[(size_t) std::max<long>(fsize, 0)] = '\0';
+  char *base = buf.data(), *end = base + std::max<long>(fsize, 0);
+  unsigned nthreads = std::thread::hardware_concurrency();
+  if (const char *env = getenv("QR_SVML_THREADS")) nthreads = (unsigned) atoi(env);
+  nthreads = std::max(1u, std::min(nthreads, (unsigned) (fsize / (1 << 20)) + 1u));   // >= 1 MB per thread
+  // chunk boundaries on line starts
+  std::vector<char *> cut(nthreads + 1);
+  cut[0] = base;
+  cut[nthreads] = end;
+  for (unsigned t = 1; t < nthreads; ++t) {
+    char *p = base + (size_t) fsize * t / nthreads;
+    char *nl = (char *) memchr(p, '\n', (size_t) (end - p));
+    cut[t] = nl ? nl + 1 : end;
+  }
+  for (unsigned t = 1; t <= nthreads; ++t) cut[t] = std::max(cut[t], cut[t - 1]);
+  std::vector<SvmlChunk> chunks(nthreads);
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(parse_svml_range, cut[t], cut[t + 1], std::ref(chunks[t]));
+    parse_svml_range(cut[0], cut[1], chunks[0]);
+    for (auto &th : pool) th.join();
+  }
+  size_t nrows = 0, maxfid = 0;
+  for (auto &c : chunks) {
+    if (c.error) exit(c.error);   // the reference's exit codes for malformed lines (svml.cc:91,112)
+    nrows += c.qids.size();
+    maxfid = std::max(maxfid, c.maxfid);
+  }
+  std::unique_ptr<data::Dataset> ds(new data::Dataset(nrows, maxfid));
+  // labels and query boundaries in file order (cheap), then every thread scatters its own rows into the
+  // zero-initialised row-major matrix
+  const std::vector<Feature> none;
+  std::vector<size_t> first_row(nthreads + 1, 0);
+  for (unsigned t = 0; t < nthreads; ++t) {
+    for (size_t i = 0; i < chunks[t].qids.size(); ++i) ds->addInstance(chunks[t].qids[i], chunks[t].labels[i], none);
+    first_row[t + 1] = first_row[t] + chunks[t].qids.size();
+  }
+  auto fill = [&](unsigned t) {
+    const SvmlChunk &c = chunks[t];
+    for (size_t i = 0; i < c.qids.size(); ++i) {
+      Feature *row = ds->at(first_row[t] + i, 0);
+      for (size_t k = c.row_start[i]; k < c.row_start[i + 1]; ++k) row[c.fids[k] - 1] = c.vals[k];
+    }
+  };
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(fill, t);
+    fill(0);
+    for (auto &th : pool) th.join();
   }
   return ds;
 }

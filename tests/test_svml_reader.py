@@ -1,0 +1,67 @@
+"""The host SVMLight reader (host/src/quickrank_host.cc, Svml::read_horizontal; reference src/io/svml.cc:38-161):
+same grammar, parsed by all host threads.  CPU only."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CHECK = os.path.join(ROOT, "host", "bin", "svml_check")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(CHECK), reason="host/bin/svml_check not built")
+
+
+def fnv(b):
+    h = 1469598103934665603
+    for c in b:
+        h = ((h ^ c) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def run(path, threads):
+    env = dict(os.environ, QR_SVML_THREADS=str(threads))
+    out = subprocess.run([CHECK, path], capture_output=True, text=True, env=env)
+    assert out.returncode == 0, out.stderr
+    return out.stdout.split()
+
+
+def test_parallel_parse_equals_serial_and_an_independent_parse(tmp_path):
+    rng = np.random.default_rng(2)
+    n, f = 30000, 23
+    x = np.round(rng.random((n, f)), 4).astype(np.float32)
+    x[rng.random((n, f)) < 0.3] = 0.0                     # sparse rows: zero features are omitted
+    labels = rng.integers(0, 5, size=n)
+    qlen = rng.integers(1, 120, size=2000)
+    off = np.concatenate([[0], np.cumsum(qlen)])
+    off = off[off < n].tolist() + [n]
+    path = str(tmp_path / "data.txt")
+    with open(path, "w") as fh:
+        fh.write("# a comment line\n\n")
+        for q in range(len(off) - 1):
+            for i in range(off[q], off[q + 1]):
+                feats = " ".join("%d:%.9g" % (j + 1, x[i, j]) for j in range(f) if x[i, j] != 0 or j == f - 1)
+                eol = "\r\n" if i % 97 == 0 else "\n"
+                fh.write("%d qid:%d %s%s%s" % (labels[i], q + 1, feats, " # doc %d" % i if i % 13 == 0 else "", eol))
+        fh.write("1 qid:%d 1:0.5 %d:0.25" % (len(off), f))   # last line without a newline
+    serial = run(path, 1)
+    for t in (2, 7, 16):
+        assert run(path, t) == serial
+    xx = np.vstack([x, np.zeros((1, f), np.float32)])
+    xx[-1, 0], xx[-1, f - 1] = 0.5, 0.25
+    ll = np.concatenate([labels, [1]]).astype(np.float32)
+    oo = np.array(off + [n + 1], np.uint64)
+    assert serial[:3] == [str(n + 1), str(f), str(len(off))]
+    assert int(serial[3], 16) == fnv(ll.tobytes())
+    assert int(serial[4], 16) == fnv(oo.tobytes())
+    assert int(serial[5], 16) == fnv(np.ascontiguousarray(xx).tobytes())
+
+
+@pytest.mark.parametrize("line,code", [("x qid:1 1:0.5\n", 2), ("1 1:0.5\n", 2), ("1 qid:1 a:0.5\n", 4), ("1 qid:1 0:0.5\n", 4)])
+def test_malformed_lines_exit_like_the_reference(tmp_path, line, code):
+    """svml.cc:91,112: exit(2) for a bad label / qid, exit(4) for a bad feature token."""
+    path = str(tmp_path / "bad.txt")
+    open(path, "w").write("2 qid:1 1:0.1 2:0.2\n" + line)
+    out = subprocess.run([CHECK, path], capture_output=True, text=True)
+    assert out.returncode == code
