@@ -100,6 +100,7 @@ struct qr_ctx {
   double *d_lg = nullptr;         // [maxlen] log2((float)i+2)
   double *d_scores = nullptr, *d_lambda = nullptr, *d_weight = nullptr;  // [N]
   long long *d_lamq = nullptr;    // [N] fixed-point pseudo-responses (FAST mode)
+  long long *d_lamq_c = nullptr;  // [N] the same, compacted by the partition next to the built child's id list
   unsigned long long *d_maxabs = nullptr;  // bits of max |lambda|
   int *d_qexp = nullptr;          // fixed-point exponent chosen for this tree
   uint32_t *d_rankpos = nullptr;  // [N] position (within its query) of the doc at each rank

@@ -414,6 +414,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_lambda, N));
   QR_TRY(dev_alloc(&c->d_weight, N));
   QR_TRY(dev_alloc(&c->d_lamq, N));
+  QR_TRY(dev_alloc(&c->d_lamq_c, N));
   QR_TRY(dev_alloc(&c->d_maxabs, 1));
   QR_TRY(dev_alloc(&c->d_qexp, 1));
   QR_TRY(dev_alloc(&c->d_rankpos, N));
@@ -690,7 +691,7 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
                   c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done, c->d_part_status,
                   c->d_ticket, c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_hdr, c->d_grow, c->d_nodes,
-                  c->d_part_done, c->d_panel_done,
+                  c->d_part_done, c->d_panel_done, c->d_lamq_c,
                   c->d_grow_arrays[0], c->d_grow_arrays[1], c->d_grow_arrays[2], c->d_grow_arrays[3],
                   c->d_grow_arrays[4], c->d_grow_arrays[5], c->d_grow_arrays[6]};
   for (void *p : ptrs) if (p) cudaFree(p);

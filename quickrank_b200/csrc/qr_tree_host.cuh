@@ -135,7 +135,7 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
   QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), kHistThreads,   \
             SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
             c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr,             \
-            (const RoundHdr *) nullptr, c->pack)
+            (const RoundHdr *) nullptr, c->pack, (const long long *) (c->comm ? nullptr : c->d_lamq_c))
       if (c->profiling) cudaEventRecord(c->ev_k0, c->stream);
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
@@ -242,11 +242,11 @@ static int init_root_counts(qr_ctx *c) {
     if (use_smem)
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, smem, c->d_tasks, 1u,
                 c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr, c->pack);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr, c->pack, (const long long *) nullptr);
     else
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, 0, c->d_tasks, 1u,
                 c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr, c->pack);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr, c->pack, (const long long *) nullptr);
     return QR_OK;
   }));
   QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
@@ -332,7 +332,8 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
       if (!fuse_partition) {
         QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
                   c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
-                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack);
+                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack,
+                  (const long long *) c->d_lamq, c->d_lamq_c);
         c->ticket_base += part_blk;
       }
       QR_LAUNCH(c, PH_HIST, round_kernel<B>, grid, kRoundThreads, fused_smem, c->d_tasks, k, fused_part, hist_blk, c->d_panels,
@@ -353,7 +354,8 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
         c->part_epoch++;
         QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
                   c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
-                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack);
+                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack,
+                  (const long long *) c->d_lamq, c->d_lamq_c);
         c->ticket_base += part_blk;
       } else {
         QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
@@ -594,11 +596,11 @@ static int enqueue_device_round(qr_ctx *c, uint32_t round, bool root) {
       if (use_smem)
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, false>), dim3(slices, c->npanels), kHistThreads, smem, tasks, 1u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack);
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq_c);
       else
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, false>), dim3(slices, c->npanels), kHistThreads, 0, tasks, 1u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack);
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq_c);
       return QR_OK;
     }));
   } else {
@@ -609,15 +611,15 @@ static int enqueue_device_round(qr_ctx *c, uint32_t round, bool root) {
       using B = decltype(tag);
       QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_grid, 256, 0, tasks, 0u, c->d_panels, c->N,
                 c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket, 0u, c->part_epoch,
-                c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) hdr, c->pack);
+                c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq, c->d_lamq_c);
       if (use_smem)
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(hist_grid, c->npanels), kHistThreads, smem, tasks, 0u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack);
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq_c);
       else
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(hist_grid, c->npanels), kHistThreads, 0, tasks, 0u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack);
+                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq_c);
       return QR_OK;
     }));
   }

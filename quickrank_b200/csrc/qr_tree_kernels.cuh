@@ -163,7 +163,8 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
                          size_t N, const uint32_t *__restrict__ ids0, const uint32_t *__restrict__ ids1,
                          uint32_t *out0, uint32_t *out1, unsigned long long *status, uint32_t *ticket,
                          uint32_t ticket_base, uint32_t epoch, unsigned long long *hsum, uint32_t *hcnt,
-                         uint32_t ncells, const RoundHdr *__restrict__ hdr, const __grid_constant__ TaskPack pack) {
+                         uint32_t ncells, const RoundHdr *__restrict__ hdr, const __grid_constant__ TaskPack pack,
+                         const long long *__restrict__ lamq, long long *__restrict__ lamq_c) {
   if (pack.n) tasks = pack.t;
   __shared__ uint32_t s_vb, s_task, s_prefix;
   __shared__ uint32_t wc[8][8];
@@ -206,6 +207,17 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
     if (lane == 0) wc[r][warp] = __popc(bal);
     wr[r] = __popc(bal & ((1u << lane) - 1u));
     flags |= (left ? 1u : 0u) << r;
+  }
+  // the fixed-point pseudo-responses of the documents that go to the child whose histogram is built are
+  // copied next to the child's id list, so that the histogram kernel reads them coalesced instead of
+  // gathering 8 bytes per document per panel; issued here, the loads complete during the look-back
+  const bool compact = lamq_c != nullptr && t.slotB >= 0;
+  long long lq[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const uint32_t i = b0 + r * 256 + threadIdx.x;
+    const bool built = (((flags >> r) & 1u) != 0u) == (t.build_left != 0u);
+    lq[r] = (compact && i < e && built) ? lamq[d[r]] : 0ll;
   }
   __syncthreads();
   if (warp == 0) {
@@ -252,8 +264,10 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
     const uint32_t i = b0 + r * 256 + threadIdx.x;
     if (i < e) {
       const uint32_t lrank = run + before + wr[r];
-      if ((flags >> r) & 1u) dst[t.lo + lrank] = d[r];
-      else dst[t.lo + lc + (i - lrank)] = d[r];
+      const bool left = (flags >> r) & 1u;
+      const uint32_t pos = left ? t.lo + lrank : t.lo + lc + (i - lrank);
+      dst[pos] = d[r];
+      if (compact && left == (t.build_left != 0u)) lamq_c[pos] = lq[r];
     }
     run += tot;
   }
@@ -337,7 +351,8 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
                  const uint32_t *__restrict__ ids1, const long long *__restrict__ lamq,
                  const uint32_t *__restrict__ thr_off, uint32_t F, unsigned long long *hsum,
                  uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials, uint32_t stride,
-                 const RoundHdr *__restrict__ hdr, const __grid_constant__ TaskPack pack) {
+                 const RoundHdr *__restrict__ hdr, const __grid_constant__ TaskPack pack,
+                 const long long *__restrict__ lamq_c) {
   if (pack.n) tasks = pack.t;
   constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -384,12 +399,16 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
     const uint32_t sel = xor_permute_selector<BinT>(rot);
     unsigned char *rbp = smem_raw + rot * 4u;
     const uint32_t hi_off = scells * 4u, cnt_off = scells * 8u;
+    // pseudo-responses: gathered by document id, or — when the partition left a compacted copy next to
+    // the id list — read by list position (coalesced)
+    const bool byq = lamq_c != nullptr && !identity;
+    const long long *lq = byq ? lamq_c + seg0 : lamq;
     uint32_t i = begin + threadIdx.x;
     uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
     long long q0 = 0, q1 = 0;
     bool v0 = i < end, v1 = i + kHistThreads < end;
-    if (v0) { const uint32_t d = identity ? seg0 + i : ids[i]; c0 = prow[d]; q0 = lamq[d]; }
-    if (v1) { const uint32_t d = identity ? seg0 + i + kHistThreads : ids[i + kHistThreads]; c1 = prow[d]; q1 = lamq[d]; }
+    if (v0) { const uint32_t d = identity ? seg0 + i : ids[i]; c0 = prow[d]; q0 = lq[byq ? i : d]; }
+    if (v1) { const uint32_t d = identity ? seg0 + i + kHistThreads : ids[i + kHistThreads]; c1 = prow[d]; q1 = lq[byq ? i + kHistThreads : d]; }
     bool w0 = i + 2 * kHistThreads < end, w1 = i + 3 * kHistThreads < end;
     uint32_t nd0 = 0, nd1 = 0;   // documents of the NEXT iteration
     if (w0) nd0 = identity ? seg0 + i + 2 * kHistThreads : ids[i + 2 * kHistThreads];
@@ -397,8 +416,8 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
     while (v0) {
       uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
       long long nq0 = 0, nq1 = 0;
-      if (w0) { n0 = prow[nd0]; nq0 = lamq[nd0]; }
-      if (w1) { n1 = prow[nd1]; nq1 = lamq[nd1]; }
+      if (w0) { n0 = prow[nd0]; nq0 = lq[byq ? i + 2 * kHistThreads : nd0]; }
+      if (w1) { n1 = prow[nd1]; nq1 = lq[byq ? i + 3 * kHistThreads : nd1]; }
       i += 2 * kHistThreads;
       const bool z0 = i + 2 * kHistThreads < end, z1 = i + 3 * kHistThreads < end;
       if (z0) nd0 = identity ? seg0 + i + 2 * kHistThreads : ids[i + 2 * kHistThreads];

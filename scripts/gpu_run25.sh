@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/pytest_gpu.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log
-timeout 100 python scripts/longrun.py 250 2>&1 | tail -2
+timeout 100 python scripts/longrun.py 150 2>&1 | tail -3
+timeout 120 python scripts/probe.py --trees 8 --settle 40 2>&1 | grep -E "unprofiled|warm"
