@@ -174,6 +174,9 @@ def run_ours(args):
                      nthresholds=w["nthresholds"], cutoff=w["cutoff"], shrinkage=w["shrinkage"],
                      hist_mode=api.HIST_FAST, device=local_rank, comm=comm)
     init_s = time.perf_counter() - t0
+    exchange = {"none": "none (one GPU)", "nccl": "NCCL all-reduces per growth round",
+                "peer": "one peer-memory kernel per growth round (CUDA IPC over NVLink: in-place "
+                        "reduce-scatter + all-gather of the built histograms)"}[tr.comm_transport()]
 
     def barrier():
         if dist is not None:
@@ -298,6 +301,7 @@ def run_ours(args):
                                    % (w["n_docs"], w["n_features"], w["n_queries"]),
                        "docs_per_gpu": int(len(labels)), "global_docs": w["n_docs"],
                        "hist_mode": "fixed-point int64 (FAST)", "parallelism": "query-sharded dp%d" % world,
+                       "histogram_exchange": exchange,
                        "trees_before_timed_region": args.settle + max(args.warmup, 3),
                        "l2": "inputs larger than L2 (136 MB bin matrix + 40 MB state per step)"},
             "clocks": clocks,

@@ -184,12 +184,20 @@ int qr_timer_stop(qr_ctx *ctx, double *ms);
 int qr_comm_unique_id(unsigned char id[QR_COMM_ID_BYTES]);
 /* Creates the training context of rank `rank` of `world`: this process holds a contiguous range of
  * whole queries (its documents only); thresholds are computed over the union of all ranks' feature
- * values, and afterwards histograms, squares, leaf sums and the metric are all-reduced over NCCL so
- * that every rank grows the identical tree.  `rowmajor` selects the feature layout (0: column-major
+ * values, and afterwards histograms, squares, leaf sums and the metric are all-reduced (the per-round
+ * histograms through peer memory over NVLink when possible, everything else over NCCL) so that every
+ * rank grows the identical tree.  `rowmajor` selects the feature layout (0: column-major
  * as qr_ctx_create, 1: row-major as qr_ctx_create_rowmajor).  Collective: every rank must call it. */
 int qr_ctx_create_sharded(const float *feat, int rowmajor, size_t N, size_t F, const float *labels,
                           const uint64_t *qoffsets, size_t Q, const qr_params *params,
                           const unsigned char id[QR_COMM_ID_BYTES], int rank, int world, qr_ctx **out);
+
+/* How the per-round histogram exchange of this context travels: 0 = single GPU (no exchange),
+ * 1 = NCCL all-reduces, 2 = one peer-memory kernel per round (every rank maps every other rank's
+ * histogram pool over CUDA IPC and reduces in place through NVLink; chosen automatically when all
+ * ranks can map each other, QR_PEER_REDUCE=0 forces NCCL).  Results are identical either way:
+ * the exchanged sums are integers. */
+int qr_ctx_comm_transport(const qr_ctx *ctx);
 
 /* ---- scoring ------------------------------------------------------------------------------- */
 

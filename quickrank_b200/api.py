@@ -98,6 +98,7 @@ def lib():
         L.qr_comm_unique_id.argtypes = [C.POINTER(C.c_ubyte)]
         L.qr_ctx_create_sharded.argtypes = [fp, C.c_int, sz, sz, fp, u64p, sz, C.POINTER(Params),
                                             C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.POINTER(vp)]
+        L.qr_ctx_comm_transport.argtypes = [vp]
         L.qr_scorer_create.argtypes = [C.POINTER(FlatTree), dp, sz, sz, C.c_int, C.POINTER(vp)]
         L.qr_scorer_destroy.argtypes = [vp]
         L.qr_score_dataset.argtypes = [vp, fp, sz, sz, dp]
@@ -312,6 +313,11 @@ class Trainer:
 
     def launch_count(self):
         return int(lib().qr_launch_count(self.h))
+
+    def comm_transport(self) -> str:
+        """How the per-round histogram exchange travels: 'none' (one GPU), 'nccl', 'peer' (one
+        peer-memory kernel per round over NVLink)."""
+        return ("none", "nccl", "peer")[int(lib().qr_ctx_comm_transport(self.h))]
 
     def set_profiling(self, on):
         _check(lib().qr_set_profiling(self.h, int(on)))

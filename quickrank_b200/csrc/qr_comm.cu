@@ -74,11 +74,37 @@ static int load_nccl() {
     }                                                                                        \
   } while (0)
 
+// ---- peer-memory exchange (NVLink / NVSwitch) -------------------------------------------------
+// Every rank exports its histogram pool and a small signal buffer with CUDA IPC; peers map them, so a
+// kernel on one GPU can load and store the other GPUs' histograms directly.
+constexpr int kMaxPeers = 8;         // one NVSwitch node
+struct PeerSignals {
+  uint32_t flags[kMaxPeers];         // flags[p]: last barrier epoch announced by rank p (stored by p)
+  uint32_t magic;                    // mapping check at set-up
+  uint32_t pad[23];
+  ulonglong2 sq_local[1];            // [max_tasks] this rank's exact squares sums of the current round
+};
+struct PeerTable {
+  unsigned long long *sum[kMaxPeers];  // histogram pools (sums), own pool at [rank]
+  uint32_t *cnt[kMaxPeers];            // histogram pools (counts)
+  PeerSignals *sig[kMaxPeers];
+};
+
 struct Comm {
   int rank = 0, world = 1;
   ncclComm_t nccl = nullptr;
   long long *d_sq_limbs = nullptr;   // [max_tasks][3] 43-bit limbs of the squares sums
   double *d_scratch = nullptr;       // small host<->device staging
+  unsigned long long *d_leafn = nullptr;   // [maxleaves] global leaf sizes (MART mean)
+  size_t leafn_cap = 0;
+  // peer-memory path
+  bool peer_ok = false;
+  PeerTable peers{};
+  PeerSignals *d_sig = nullptr;      // own signal buffer (exported)
+  uint32_t *d_done = nullptr;        // block counter of peer_reduce_kernel
+  uint32_t epoch = 0;                // two barrier epochs per reduce launch
+  void *opened[3 * kMaxPeers] = {nullptr};
+  int nopened = 0;
 };
 
 int comm_rank(const Comm *c) { return c ? c->rank : 0; }
@@ -106,6 +132,10 @@ int comm_create(const unsigned char id[QR_COMM_ID_BYTES], int rank, int world, C
 
 void comm_destroy(Comm *c) {
   if (!c) return;
+  for (int i = 0; i < c->nopened; ++i) cudaIpcCloseMemHandle(c->opened[i]);
+  if (c->d_sig) cudaFree(c->d_sig);
+  if (c->d_done) cudaFree(c->d_done);
+  if (c->d_leafn) cudaFree(c->d_leafn);
   if (c->d_sq_limbs) cudaFree(c->d_sq_limbs);
   if (c->d_scratch) cudaFree(c->d_scratch);
   if (c->nccl) g_nccl.CommDestroy(c->nccl);
@@ -184,10 +214,247 @@ __global__ void sq_unpack_kernel(NodeTask *tasks, const long long *__restrict__ 
   tasks[task].hist_nblk = 1;
 }
 
+// ------------------------------------------------------------------------------------------
+// All-reduce of a growth round's freshly built histograms over peer memory, in ONE kernel per rank:
+//   0. block 0 totals this rank's exact squares partials into its signal buffer, then tells every
+//      peer "my histogram kernel of this round has finished" (the kernel is stream-ordered after it);
+//   1. every block waits for the same announcement from all peers (barrier A);
+//   2. reduce-scatter + all-gather in place: rank r owns the cells [ncells*r/W, ncells*(r+1)/W) of every
+//      task's slot; it loads them from all W pools, adds (64-bit integers and counts: exact, any order)
+//      and stores the totals into all W pools.  In phase 2 nobody else reads or writes those cells;
+//   3. the last block to finish tells the peers and waits for theirs (barrier B): when the kernel ends,
+//      every pool holds the global histograms and no peer is still reading this rank's partials, so
+//      the split scan that follows — and the next round's histogram kernel — need no further fence.
+// Per rank and round this moves 2 x (W-1)/W x k x H bytes over NVLink and costs two flag round trips;
+// the NCCL path it replaces was 2k+1 grouped all-reduces plus two pack/unpack launches.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
+__device__ __forceinline__ void st_flag(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
+
+// bounded spin: a peer that never arrives (crashed process) must not hang the GPU
+__device__ __forceinline__ void wait_flag(const uint32_t *p, uint32_t epoch) {
+  const long long t0 = clock64();
+  while ((int32_t) (ld_flag(p) - epoch) < 0) {
+    if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s
+  }
+}
+
+constexpr uint32_t kPeerThreads = 256;
+
+__global__ void __launch_bounds__(kPeerThreads)
+peer_reduce_kernel(const PeerTable pt, int rank, int world, const NodeTask *__restrict__ tasks, uint32_t k,
+                   uint32_t ncells, uint32_t epoch_a, int with_counts, ulonglong2 *sq128, uint32_t *done,
+                   const __grid_constant__ TaskPack pack) {
+  if (pack.n) tasks = pack.t;
+  __shared__ uint32_t s_last;
+  PeerSignals *mine = pt.sig[rank];
+  const uint32_t tid = threadIdx.x;
+  if (blockIdx.x == 0) {
+    // one warp per task: the slices' 128-bit partials are loaded in parallel and folded with shuffles
+    const uint32_t lane = tid & 31u;
+    for (uint32_t j = tid >> 5; j < k; j += kPeerThreads / 32u) {
+      const uint32_t blk0 = tasks[j].hist_blk0, nblk = tasks[j].hist_nblk;
+      U128 tot{0ull, 0ull};
+      for (uint32_t i = lane; i < nblk; i += 32u) { const ulonglong2 v = sq128[blk0 + i]; u128_add(tot, v.x, v.y); }
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ol = __shfl_xor_sync(0xffffffffu, tot.lo, o);
+        const unsigned long long oh = __shfl_xor_sync(0xffffffffu, tot.hi, o);
+        u128_add(tot, ol, oh);
+      }
+      if (lane == 0) {
+        volatile unsigned long long *o = reinterpret_cast<volatile unsigned long long *>(&mine->sq_local[j]);
+        o[0] = tot.lo; o[1] = tot.hi;
+      }
+    }
+    __syncthreads();
+    if (tid < (uint32_t) world && tid != (uint32_t) rank) {
+      __threadfence_system();
+      st_flag(&pt.sig[tid]->flags[rank], epoch_a);
+    }
+  }
+  // barrier A
+  if (tid < (uint32_t) world && tid != (uint32_t) rank) {
+    wait_flag(&mine->flags[tid], epoch_a);
+    __threadfence_system();
+  }
+  __syncthreads();
+
+  const uint32_t c0 = (uint32_t) ((unsigned long long) ncells * (uint32_t) rank / (uint32_t) world);
+  const uint32_t c1 = (uint32_t) ((unsigned long long) ncells * ((uint32_t) rank + 1u) / (uint32_t) world);
+  const uint32_t span = c1 - c0;
+  const uint32_t total = k * span;
+  for (uint32_t idx = blockIdx.x * kPeerThreads + tid; idx < total; idx += gridDim.x * kPeerThreads) {
+    const uint32_t j = idx / span, i = c0 + (idx - j * span);
+    const size_t off = (size_t) tasks[j].slotB * ncells + i;
+    unsigned long long s = 0ull;
+    uint32_t n = 0u;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p < world) {
+        s += *reinterpret_cast<const volatile unsigned long long *>(pt.sum[p] + off);
+        if (with_counts) n += *reinterpret_cast<const volatile uint32_t *>(pt.cnt[p] + off);
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      if (p < world) {
+        pt.sum[p][off] = s;
+        if (with_counts) pt.cnt[p][off] = n;
+      }
+    }
+  }
+  // squares: every rank adds the same W totals, so all of them hold the same exact value; the total goes
+  // to the task's first slice and the others are zeroed (finalize_kernel sums the task's slices)
+  if (blockIdx.x == 0) {
+    for (uint32_t j = tid; j < k; j += kPeerThreads) {
+      const NodeTask t = tasks[j];
+      U128 tot{0ull, 0ull};
+#pragma unroll
+      for (int p = 0; p < kMaxPeers; ++p) {
+        if (p < world) {
+          const volatile unsigned long long *v = reinterpret_cast<const volatile unsigned long long *>(&pt.sig[p]->sq_local[j]);
+          const unsigned long long lo = v[0], hi = v[1];
+          u128_add(tot, lo, hi);
+        }
+      }
+      sq128[t.hist_blk0] = make_ulonglong2(tot.lo, tot.hi);
+      for (uint32_t i = 1; i < t.hist_nblk; ++i) sq128[t.hist_blk0 + i] = make_ulonglong2(0ull, 0ull);
+    }
+  }
+  // barrier B, by the last block of this rank
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(done, 1u) == gridDim.x - 1u ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  if (tid == 0) { *done = 0u; __threadfence_system(); }
+  __syncthreads();
+  if (tid < (uint32_t) world && tid != (uint32_t) rank) {
+    __threadfence_system();
+    st_flag(&pt.sig[tid]->flags[rank], epoch_a + 1u);
+    wait_flag(&mine->flags[tid], epoch_a + 1u);
+    __threadfence_system();
+  }
+}
+
+struct PeerHello {
+  cudaIpcMemHandle_t sum, cnt, sig;
+  int ok;
+  int device;
+};
+
+// Exports this rank's pools, maps the peers', checks every mapping and agrees with all ranks on whether
+// the peer-memory path is used (all ranks must take the same path: its barriers involve everyone).
+int comm_setup_peers(qr_ctx *ctx) {
+  Comm *c = ctx->comm;
+  if (!c || ctx->d_hist_sum == nullptr) return QR_OK;
+  cudaStream_t st = ctx->stream;
+  const char *env = getenv("QR_PEER_REDUCE");
+  int ok = (env == nullptr || atoi(env) != 0) && c->world <= kMaxPeers;
+  const char *why = ok ? "" : (c->world > kMaxPeers ? "more than 8 ranks" : "QR_PEER_REDUCE=0");
+  const size_t sig_bytes = std::max<size_t>((size_t) 2 << 20, sizeof(PeerSignals) + (size_t) ctx->max_tasks * sizeof(ulonglong2));
+  QR_CUDA(cudaMalloc((void **) &c->d_sig, sig_bytes));
+  QR_CUDA(cudaMalloc((void **) &c->d_done, sizeof(uint32_t)));
+  QR_CUDA(cudaMemsetAsync(c->d_sig, 0, sig_bytes, st));
+  QR_CUDA(cudaMemsetAsync(c->d_done, 0, sizeof(uint32_t), st));
+  // marks the peers will look for through their mappings (the pools are scratch: slots are cleared before use)
+  const uint32_t magic = 0x51b20000u + (uint32_t) c->rank;
+  const unsigned long long magic64 = 0x51b2000051b20000ull + (unsigned long long) c->rank;
+  QR_CUDA(cudaMemcpyAsync(&c->d_sig->magic, &magic, sizeof(magic), cudaMemcpyHostToDevice, st));
+  QR_CUDA(cudaMemcpyAsync(ctx->d_hist_sum, &magic64, sizeof(magic64), cudaMemcpyHostToDevice, st));
+  QR_CUDA(cudaMemcpyAsync(ctx->d_hist_cnt, &magic, sizeof(magic), cudaMemcpyHostToDevice, st));
+  QR_CUDA(cudaStreamSynchronize(st));
+  PeerHello hello;
+  memset(&hello, 0, sizeof(hello));
+  hello.device = ctx->device;
+  if (ok) {
+    if (cudaIpcGetMemHandle(&hello.sum, ctx->d_hist_sum) != cudaSuccess ||
+        cudaIpcGetMemHandle(&hello.cnt, ctx->d_hist_cnt) != cudaSuccess ||
+        cudaIpcGetMemHandle(&hello.sig, c->d_sig) != cudaSuccess) {
+      ok = 0; why = "cudaIpcGetMemHandle failed";
+      cudaGetLastError();
+    }
+  }
+  hello.ok = ok;
+  std::vector<unsigned char> all;
+  QR_TRY(comm_allgather_host(c, &hello, sizeof(hello), &all, st));
+  const PeerHello *hs = reinterpret_cast<const PeerHello *>(all.data());
+  for (int p = 0; p < c->world; ++p) if (!hs[p].ok && ok) { ok = 0; why = "a peer cannot export its memory"; }
+  if (ok) {
+    c->peers.sum[c->rank] = ctx->d_hist_sum;
+    c->peers.cnt[c->rank] = ctx->d_hist_cnt;
+    c->peers.sig[c->rank] = c->d_sig;
+    for (int p = 0; p < c->world && ok; ++p) {
+      if (p == c->rank) continue;
+      void *ptrs[3] = {nullptr, nullptr, nullptr};
+      const cudaIpcMemHandle_t *hd[3] = {&hs[p].sum, &hs[p].cnt, &hs[p].sig};
+      for (int i = 0; i < 3 && ok; ++i) {
+        if (cudaIpcOpenMemHandle(&ptrs[i], *hd[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          ok = 0; why = "cudaIpcOpenMemHandle failed (no peer access between the devices?)";
+          cudaGetLastError();
+        } else {
+          c->opened[c->nopened++] = ptrs[i];
+        }
+      }
+      if (!ok) break;
+      c->peers.sum[p] = (unsigned long long *) ptrs[0];
+      c->peers.cnt[p] = (uint32_t *) ptrs[1];
+      c->peers.sig[p] = (PeerSignals *) ptrs[2];
+      unsigned long long m64 = 0;
+      uint32_t m32a = 0, m32b = 0;
+      if (cudaMemcpy(&m64, c->peers.sum[p], sizeof(m64), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(&m32a, c->peers.cnt[p], sizeof(m32a), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(&m32b, &c->peers.sig[p]->magic, sizeof(m32b), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          m64 != 0x51b2000051b20000ull + (unsigned long long) p || m32a != 0x51b20000u + (uint32_t) p ||
+          m32b != 0x51b20000u + (uint32_t) p) {
+        ok = 0; why = "a mapped peer buffer does not show the peer's mark";
+        cudaGetLastError();
+      }
+    }
+  }
+  // agreement: one rank's failure turns the path off everywhere
+  unsigned long long bad = ok ? 0ull : 1ull, *d_bad = nullptr;
+  QR_CUDA(cudaMalloc((void **) &d_bad, sizeof(bad)));
+  QR_CUDA(cudaMemcpyAsync(d_bad, &bad, sizeof(bad), cudaMemcpyHostToDevice, st));
+  QR_TRY(comm_allreduce_max_u64(c, d_bad, 1, st));
+  unsigned long long any_bad = 1;
+  QR_CUDA(cudaMemcpyAsync(&any_bad, d_bad, sizeof(any_bad), cudaMemcpyDeviceToHost, st));
+  QR_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_bad);
+  c->peer_ok = any_bad == 0ull;
+  if (!c->peer_ok) {
+    if (!ok && env == nullptr)
+      fprintf(stderr, "quickrank_b200: rank %d: peer-memory histogram exchange unavailable (%s); using NCCL all-reduces\n",
+              c->rank, why);
+    for (int i = 0; i < c->nopened; ++i) cudaIpcCloseMemHandle(c->opened[i]);
+    c->nopened = 0;
+  }
+  return QR_OK;
+}
+
+int comm_transport(const Comm *c) { return c == nullptr ? 0 : (c->peer_ok ? 2 : 1); }
+
+static int peer_reduce_tasks(qr_ctx *ctx, uint32_t k, bool root) {
+  Comm *c = ctx->comm;
+  const int with_counts = (root && ctx->d_root_cnt != nullptr) ? 0 : 1;
+  const uint32_t span = ctx->ncells / (uint32_t) c->world + 1u;
+  const uint32_t grid = std::max<uint32_t>(1u, std::min<uint32_t>(2u * 148u, (k * span + kPeerThreads - 1) / kPeerThreads));
+  const uint32_t epoch_a = c->epoch + 1u;
+  c->epoch += 2u;
+  peer_reduce_kernel<<<grid, kPeerThreads, 0, ctx->stream>>>(c->peers, c->rank, c->world, ctx->d_tasks, k, ctx->ncells,
+                                                             epoch_a, with_counts, ctx->d_sq128, c->d_done, ctx->pack);
+  ctx->launches++;
+  QR_CUDA(cudaGetLastError());
+  return QR_OK;
+}
+
 int comm_reduce_tasks(qr_ctx *ctx, uint32_t k, bool root) {
   Comm *c = ctx->comm;
   cudaStream_t st = ctx->stream;
   if (ctx->exact) { set_error("reference-order accumulation is single-GPU only"); return QR_ECOMM; }
+  if (c->peer_ok) return peer_reduce_tasks(ctx, k, root);
   if (!c->d_sq_limbs) QR_CUDA(cudaMalloc((void **) &c->d_sq_limbs, (size_t) ctx->max_tasks * 3 * sizeof(long long)));
   sq_pack_kernel<<<k, 32, 0, st>>>(ctx->d_tasks, ctx->d_sq128, c->d_sq_limbs);
   ctx->launches++;
@@ -226,16 +493,18 @@ int comm_leaf_values(qr_ctx *ctx, uint32_t nleaves) {
   cudaStream_t st = ctx->stream;
   QR_NCCL(g_nccl.AllReduce(ctx->d_leafsum, ctx->d_leafsum, (size_t) nleaves * 2, ncclFloat64, ncclSum, c->nccl, st));
   // global leaf sizes for the MART mean
-  std::vector<unsigned long long> n(nleaves);
+  std::vector<unsigned long long> n(std::max<uint32_t>(nleaves, 1));
   for (uint32_t k = 0; k < nleaves; ++k) n[k] = ctx->nodes[ctx->leaves[k]].res.n;
-  unsigned long long *d_n = nullptr;
-  QR_CUDA(cudaMalloc((void **) &d_n, std::max<size_t>(nleaves, 1) * sizeof(unsigned long long)));
-  QR_CUDA(cudaMemcpyAsync(d_n, n.data(), nleaves * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-  leaf_values_kernel<<<(nleaves + 63) / 64, 64, 0, st>>>(ctx->d_leafsum, d_n, nleaves, ctx->lambda, ctx->d_leafval);
+  if (c->leafn_cap < n.size()) {
+    if (c->d_leafn) cudaFree(c->d_leafn);
+    c->leafn_cap = std::max<size_t>(n.size(), 256);
+    QR_CUDA(cudaMalloc((void **) &c->d_leafn, c->leafn_cap * sizeof(unsigned long long)));
+  }
+  QR_CUDA(cudaMemcpyAsync(c->d_leafn, n.data(), nleaves * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+  leaf_values_kernel<<<(nleaves + 63) / 64, 64, 0, st>>>(ctx->d_leafsum, c->d_leafn, nleaves, ctx->lambda, ctx->d_leafval);
   ctx->launches++;
   QR_CUDA(cudaGetLastError());
-  QR_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_n);
+  QR_CUDA(cudaStreamSynchronize(st));   // `n` is pageable: the copy above must have left it
   return QR_OK;
 }
 

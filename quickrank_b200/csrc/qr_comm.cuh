@@ -24,6 +24,11 @@ int comm_allgather_host(Comm *c, const void *send, size_t bytes, std::vector<uns
 // all-reduce the freshly built per-bin histograms (fixed-point sums + counts) and the squares
 // sums of the first `ntasks` tasks in ctx->d_tasks
 int comm_reduce_tasks(qr_ctx *ctx, uint32_t ntasks, bool root);
+// export this rank's histogram pool over CUDA IPC, map the peers' and agree on the exchange path
+// (peer-memory kernel when every rank can map every other, NCCL all-reduces otherwise)
+int comm_setup_peers(qr_ctx *ctx);
+// 0: single GPU, 1: NCCL all-reduces, 2: peer-memory kernel
+int comm_transport(const Comm *c);
 // all-reduce the per-leaf (sum lambda, sum weight) pairs and recompute the leaf outputs
 int comm_leaf_values(qr_ctx *ctx, uint32_t nleaves);
 

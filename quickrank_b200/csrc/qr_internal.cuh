@@ -125,6 +125,8 @@ struct qr_ctx {
   qr::NodeTask *d_tasks = nullptr, *h_tasks = nullptr;   // [max_tasks] (host copy pinned)
   qr::TaskPack pack{};                      // task records of a small round, passed as kernel parameters
   uint32_t *d_lcount = nullptr, *h_lcount = nullptr;     // [max_tasks] local left counts
+  uint32_t *d_lcount_mapped = nullptr;      // device view of h_lcount (sharded training: written by the partition)
+  bool part_3pass = false;                  // sharded training with the count/prefix/scatter partition (QR_COMM_3PASS=1)
   double *d_fbest_score = nullptr;          // [max_tasks][2][F]
   uint32_t *d_fbest_t = nullptr;            // [max_tasks][2][F]
   uint32_t *d_fbest_lc = nullptr;           // [max_tasks][2][F] left count at each feature's best split

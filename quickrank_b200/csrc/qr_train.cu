@@ -447,8 +447,11 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
               "bin count with --num-thresholds", hist_bytes >> 20, c->nslots, c->ncells);
     return QR_ENOMEM;
   }
-  QR_TRY(dev_alloc(&c->d_hist_sum, (size_t) c->nslots * c->ncells));
-  QR_TRY(dev_alloc(&c->d_hist_cnt, (size_t) c->nslots * c->ncells));
+  // sharded training exports the two pools over CUDA IPC: at least 2 MB each, so that each is an allocation
+  // of its own and not a piece of a page shared with other buffers
+  const size_t pool_cells = std::max<size_t>((size_t) c->nslots * c->ncells, c->comm ? ((size_t) 2 << 20) / 4 : 1);
+  QR_TRY(dev_alloc(&c->d_hist_sum, pool_cells));
+  QR_TRY(dev_alloc(&c->d_hist_cnt, pool_cells));
   for (int i = c->nslots - 1; i >= 0; --i) c->free_slots.push_back(i);
   const size_t mt = c->max_tasks;
   QR_TRY(dev_alloc(&c->d_blockcnt, (N + kPartItems - 1) / kPartItems + mt + 1));
@@ -464,7 +467,10 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_tasks, 2 * mt));   // double-buffered by the device-driven growth
   QR_CUDA(cudaMallocHost((void **) &c->h_tasks, mt * sizeof(NodeTask)));
   QR_TRY(dev_alloc(&c->d_lcount, mt));
-  QR_CUDA(cudaMallocHost((void **) &c->h_lcount, mt * sizeof(uint32_t)));
+  QR_CUDA(cudaHostAlloc((void **) &c->h_lcount, mt * sizeof(uint32_t), cudaHostAllocMapped));
+  memset(c->h_lcount, 0, mt * sizeof(uint32_t));
+  if (c->comm) QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_lcount_mapped, c->h_lcount, 0));
+  c->part_3pass = c->comm != nullptr && getenv("QR_COMM_3PASS") != nullptr;
   QR_TRY(dev_alloc(&c->d_fbest_score, mt * 2 * F * kFinParts));
   QR_TRY(dev_alloc(&c->d_fbest_t, mt * 2 * F * kFinParts));
   QR_TRY(dev_alloc(&c->d_fbest_lc, mt * 2 * F * kFinParts));
@@ -550,6 +556,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   }
   QR_CUDA(cudaGetLastError());
   clk.lap("state + pools");
+  QR_TRY(comm_setup_peers(c));
   QR_TRY(init_root_counts(c));
   QR_CUDA(cudaGetLastError());
   clk.lap("root counts");
@@ -666,6 +673,8 @@ int qr_ctx_create_sharded(const float *feat, int rowmajor, size_t N, size_t F, c
   if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
   return rc;
 }
+
+int qr_ctx_comm_transport(const qr_ctx *c) { return c ? comm_transport(c->comm) : 0; }
 
 int qr_ctx_create_eval(qr_ctx *train, const float *feat_rowmajor, size_t N, size_t F, const float *labels,
                        const uint64_t *qoff, size_t Q, qr_ctx **out) {

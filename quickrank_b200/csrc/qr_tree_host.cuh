@@ -135,7 +135,7 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
   QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), kHistThreads,   \
             SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
             c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr,             \
-            (const RoundHdr *) nullptr, c->pack, (const long long *) (c->comm ? nullptr : c->d_lamq_c))
+            (const RoundHdr *) nullptr, c->pack, (const long long *) (c->part_3pass ? nullptr : c->d_lamq_c))
       if (c->profiling) cudaEventRecord(c->ev_k0, c->stream);
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
@@ -178,10 +178,12 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
                 c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
                 c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack);
     QR_TRACE_MARK(c);
-    if (c->comm) {
+    if (c->comm && c->part_3pass) {
       QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       QR_CUDA(cudaStreamSynchronize(c->stream));
     }
+    // (sharded, one-pass partition: the local left counts were written to mapped host memory by the
+    // partition kernel, two kernels before the flags below)
     QR_TRY(wait_round_flags(c, k));
   }
   return QR_OK;
@@ -272,7 +274,24 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     // local sizes are only known exactly on a single GPU; with several ranks bound by the node size
     built_total += c->comm ? nd.n : (build_left ? lc : rc);
   }
-  const uint32_t dpb = pick_hist_dpb(c, built_total);
+  uint32_t dpb = pick_hist_dpb(c, built_total);
+  if (c->comm) {
+    // the local size of the built child is unknown until the partition has run; queries are sharded without
+    // regard to their content, so it is close to the node's local size times the global ratio.  Slices are
+    // sized for that estimate (plus a margin), their number for the whole local node (slices past the real
+    // end return at once), capped so that a round never launches many waves of empty blocks.
+    uint64_t est_total = 0, node_total = 0;
+    for (uint32_t j = 0; j < k; ++j) {
+      const HostNode &nd = c->nodes[S[j]];
+      const uint64_t lc = nd.res.lcount, rc = nd.res.n - nd.res.lcount;
+      const double ratio = (double) std::min(lc, rc) / (double) std::max<uint64_t>(nd.res.n, 1);
+      est_total += (uint64_t) ((double) nd.n * ratio * 1.25) + 256u;
+      node_total += nd.n;
+    }
+    const uint32_t max_slices = 4u * std::max<uint32_t>(1, 148u / c->npanels) + k;
+    const uint64_t floor_dpb = ((node_total + max_slices - 1) / max_slices + 255u) & ~(uint64_t) 255u;
+    dpb = (uint32_t) std::min<uint64_t>(std::max<uint64_t>(pick_hist_dpb(c, est_total), floor_dpb), 1u << 20);
+  }
   uint32_t part_blk = 0, hist_blk = 0;
   for (uint32_t j = 0; j < k; ++j) {
     HostNode &nd = c->nodes[S[j]];
@@ -305,9 +324,10 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     t.parent_squares = nd.res.squares;
   }
   QR_TRACE_MARK(c);
-  const bool onepass = c->comm == nullptr;
+  const bool onepass = !c->part_3pass;
   c->pack.n = 0;
-  if (onepass && !c->exact && build_child_hists && k <= kPackTasks) {
+  // (sharded training: only with the peer-memory exchange, whose kernel takes the records the same way)
+  if (onepass && !c->exact && (!c->comm || comm_transport(c->comm) == 2) && build_child_hists && k <= kPackTasks) {
     // small round: the task records travel in the kernel parameters
     c->pack.n = k;
     memcpy(c->pack.t, c->h_tasks, k * sizeof(NodeTask));
@@ -333,7 +353,7 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
         QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
                   c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
                   c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack,
-                  (const long long *) c->d_lamq, c->d_lamq_c);
+                  (const long long *) c->d_lamq, c->d_lamq_c, c->d_lcount, c->d_lcount_mapped);
         c->ticket_base += part_blk;
       }
       QR_LAUNCH(c, PH_HIST, round_kernel<B>, grid, kRoundThreads, fused_smem, c->d_tasks, k, fused_part, hist_blk, c->d_panels,
@@ -355,7 +375,7 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
         QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
                   c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
                   c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack,
-                  (const long long *) c->d_lamq, c->d_lamq_c);
+                  (const long long *) c->d_lamq, c->d_lamq_c, c->d_lcount, c->d_lcount_mapped);
         c->ticket_base += part_blk;
       } else {
         QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
@@ -371,7 +391,9 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
   if (build_child_hists) {
     QR_TRY(launch_hist_and_scan(c, k, hist_blk, false, onepass, (double) built_total));
   } else if (c->comm) {
-    QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    // last oblivious level: no split scan follows whose flags could be waited for
+    if (c->part_3pass)
+      QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     QR_CUDA(cudaStreamSynchronize(c->stream));
   }
   }
@@ -611,7 +633,8 @@ static int enqueue_device_round(qr_ctx *c, uint32_t round, bool root) {
       using B = decltype(tag);
       QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_grid, 256, 0, tasks, 0u, c->d_panels, c->N,
                 c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket, 0u, c->part_epoch,
-                c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq, c->d_lamq_c);
+                c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq, c->d_lamq_c,
+                c->d_lcount, (uint32_t *) nullptr);
       if (use_smem)
         QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(hist_grid, c->npanels), kHistThreads, smem, tasks, 0u,
                   c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,

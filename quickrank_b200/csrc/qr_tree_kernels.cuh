@@ -152,7 +152,9 @@ part_scatter_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const u
   }
 }
 
-// Single-pass variant (used when the host knows every task's left count, i.e. on one GPU):
+// Single-pass variant.  On one GPU the host knows every task's left count (lc_known) and the list order
+// is preserved; in sharded training it does not (the split was chosen on all-reduced histograms), the
+// right side is written from the end of the segment and the count is published by the last block:
 // blocks take a ticket, count their own lefts, publish the count and obtain the number of lefts
 // in the preceding blocks of the same task by decoupled look-back; the list order is preserved.
 // Each block also clears its share of the histogram slot the task is about to build into.
@@ -164,7 +166,8 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
                          uint32_t *out0, uint32_t *out1, unsigned long long *status, uint32_t *ticket,
                          uint32_t ticket_base, uint32_t epoch, unsigned long long *hsum, uint32_t *hcnt,
                          uint32_t ncells, const RoundHdr *__restrict__ hdr, const __grid_constant__ TaskPack pack,
-                         const long long *__restrict__ lamq, long long *__restrict__ lamq_c) {
+                         const long long *__restrict__ lamq, long long *__restrict__ lamq_c,
+                         uint32_t *lcount_out, uint32_t *lcount_host) {
   if (pack.n) tasks = pack.t;
   __shared__ uint32_t s_vb, s_task, s_prefix;
   __shared__ uint32_t wc[8][8];
@@ -252,6 +255,12 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
       if (lane == 0) st[vb] = ep | (2ull << 30) | (prefix + total);
     }
     if (lane == 0) s_prefix = prefix;
+    // sharded training: the local left count is not known beforehand; the task's last block publishes it
+    // for the histogram kernel (device) and for the host's node records (mapped host memory)
+    if (lane == 0 && !t.lc_known && lb == nb - 1) {
+      lcount_out[s_task] = prefix + total;
+      if (lcount_host) lcount_host[s_task] = prefix + total;
+    }
   }
   __syncthreads();
   uint32_t run = s_prefix;
@@ -265,7 +274,11 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
     if (i < e) {
       const uint32_t lrank = run + before + wr[r];
       const bool left = (flags >> r) & 1u;
-      const uint32_t pos = left ? t.lo + lrank : t.lo + lc + (i - lrank);
+      // unknown left count: the right side is filled downwards from the end of the segment (it comes out in
+      // descending order: fixed-point histograms do not depend on the order, the FP64 leaf sums only in
+      // their last bits and deterministically)
+      const uint32_t rpos = t.lc_known ? t.lo + lc + (i - lrank) : t.lo + t.n - 1u - (i - lrank);
+      const uint32_t pos = left ? t.lo + lrank : rpos;
       dst[pos] = d[r];
       if (compact && left == (t.build_left != 0u)) lamq_c[pos] = lq[r];
     }

@@ -1,6 +1,7 @@
-"""Two-rank training over NCCL (one process per GPU, documents sharded by query) must grow the
-same trees as one GPU: histogram sums are fixed-point integers, so the all-reduced totals do not
-depend on the number of ranks."""
+"""Two-rank training (one process per GPU, documents sharded by query) must grow the same trees as
+one GPU, whether the per-round histograms are exchanged by the peer-memory kernel (CUDA IPC over
+NVLink) or by NCCL all-reduces: histogram sums are fixed-point integers, so the totals do not
+depend on the number of ranks or on the order of the additions."""
 import multiprocessing as mp
 import os
 import sys
@@ -15,7 +16,8 @@ pytestmark = pytest.mark.gpu
 T = 6
 
 
-def _worker(rank, world, q, out_q, algo, kw):
+def _worker(rank, world, q, out_q, algo, kw, peer):
+    os.environ["QR_PEER_REDUCE"] = "1" if peer else "0"
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from quickrank_b200 import api
     from quickrank_b200.sharding import query_shards
@@ -36,13 +38,15 @@ def _worker(rank, world, q, out_q, algo, kw):
         trees.append(t)
         metrics.append(m)
     scores = tr.get_scores()
+    transport = tr.comm_transport()
     tr.close()
-    out_q.put((rank, trees, metrics, d0, d1, scores))
+    out_q.put((rank, trees, metrics, d0, d1, scores, transport))
 
 
+@pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl"])
 @pytest.mark.parametrize("algo,kw", [("LAMBDAMART", dict(nleaves=16)), ("MART", dict(nleaves=8)),
                                      ("OBVLAMBDAMART", dict(treedepth=3))])
-def test_two_ranks_grow_the_single_gpu_trees(algo, kw):
+def test_two_ranks_grow_the_single_gpu_trees(algo, kw, peer):
     from quickrank_b200 import api
     if api.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -52,7 +56,7 @@ def test_two_ranks_grow_the_single_gpu_trees(algo, kw):
         want_scores = tr.get_scores()
     ctx = mp.get_context("spawn")
     q, out_q = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, q, out_q, algo, kw)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, q, out_q, algo, kw, peer)) for r in range(2)]
     for p in procs:
         p.start()
     results = sorted([out_q.get(timeout=300) for _ in procs], key=lambda r: r[0])
@@ -60,7 +64,10 @@ def test_two_ranks_grow_the_single_gpu_trees(algo, kw):
         p.join(timeout=60)
         assert p.exitcode == 0
     got_scores = np.zeros(len(l))
-    for rank, trees, metrics, d0, d1, scores in results:
+    for rank, trees, metrics, d0, d1, scores, transport in results:
+        # the exchange under test must be the one that ran (the peer-memory path falls back to NCCL, with a
+        # message on stderr, only where the devices cannot map each other's memory)
+        assert transport == ("peer" if peer else "nccl"), transport
         got_scores[d0:d1] = scores
         for m in range(T):
             wt, wm = want[m]
