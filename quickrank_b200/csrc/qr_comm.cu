@@ -77,7 +77,6 @@ static int load_nccl() {
 // ---- peer-memory exchange (NVLink / NVSwitch) -------------------------------------------------
 // Every rank exports its histogram pool and a small signal buffer with CUDA IPC; peers map them, so a
 // kernel on one GPU can load and store the other GPUs' histograms directly.
-constexpr int kMaxPeers = 8;         // one NVSwitch node
 struct PeerSignals {
   uint32_t flags[kMaxPeers];         // flags[p]: last barrier epoch announced by rank p (stored by p)
   uint32_t magic;                    // mapping check at set-up
@@ -88,6 +87,7 @@ struct PeerTable {
   unsigned long long *sum[kMaxPeers];  // histogram pools (sums), own pool at [rank]
   uint32_t *cnt[kMaxPeers];            // histogram pools (counts)
   PeerSignals *sig[kMaxPeers];
+  ulonglong2 *sq[kMaxPeers];           // squares partials (d_sq128)
 };
 
 struct Comm {
@@ -103,7 +103,7 @@ struct Comm {
   PeerSignals *d_sig = nullptr;      // own signal buffer (exported)
   uint32_t *d_done = nullptr;        // block counter of peer_reduce_kernel
   uint32_t epoch = 0;                // two barrier epochs per reduce launch
-  void *opened[3 * kMaxPeers] = {nullptr};
+  void *opened[4 * kMaxPeers] = {nullptr};
   int nopened = 0;
 };
 
@@ -228,17 +228,6 @@ __global__ void sq_unpack_kernel(NodeTask *tasks, const long long *__restrict__ 
 // Per rank and round this moves 2 x (W-1)/W x k x H bytes over NVLink and costs two flag round trips;
 // the NCCL path it replaces was 2k+1 grouped all-reduces plus two pack/unpack launches.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t ld_flag(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
-__device__ __forceinline__ void st_flag(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
-
-// bounded spin: a peer that never arrives (crashed process) must not hang the GPU
-__device__ __forceinline__ void wait_flag(const uint32_t *p, uint32_t epoch) {
-  const long long t0 = clock64();
-  while ((int32_t) (ld_flag(p) - epoch) < 0) {
-    if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s
-  }
-}
-
 constexpr uint32_t kPeerThreads = 256;
 
 __global__ void __launch_bounds__(kPeerThreads)
@@ -267,16 +256,10 @@ peer_reduce_kernel(const PeerTable pt, int rank, int world, const NodeTask *__re
       }
     }
     __syncthreads();
-    if (tid < (uint32_t) world && tid != (uint32_t) rank) {
-      __threadfence_system();
-      st_flag(&pt.sig[tid]->flags[rank], epoch_a);
-    }
+    if (tid < (uint32_t) world && tid != (uint32_t) rank) st_flag(&pt.sig[tid]->flags[rank], epoch_a);
   }
   // barrier A
-  if (tid < (uint32_t) world && tid != (uint32_t) rank) {
-    wait_flag(&mine->flags[tid], epoch_a);
-    __threadfence_system();
-  }
+  if (tid < (uint32_t) world && tid != (uint32_t) rank) wait_flag(&mine->flags[tid], epoch_a);
   __syncthreads();
 
   const uint32_t c0 = (uint32_t) ((unsigned long long) ncells * (uint32_t) rank / (uint32_t) world);
@@ -285,7 +268,7 @@ peer_reduce_kernel(const PeerTable pt, int rank, int world, const NodeTask *__re
   const uint32_t total = k * span;
   for (uint32_t idx = blockIdx.x * kPeerThreads + tid; idx < total; idx += gridDim.x * kPeerThreads) {
     const uint32_t j = idx / span, i = c0 + (idx - j * span);
-    const size_t off = (size_t) tasks[j].slotB * ncells + i;
+    const size_t off = (size_t) build_slot(tasks[j]) * ncells + i;
     unsigned long long s = 0ull;
     uint32_t n = 0u;
 #pragma unroll
@@ -329,18 +312,15 @@ peer_reduce_kernel(const PeerTable pt, int rank, int world, const NodeTask *__re
   }
   __syncthreads();
   if (!s_last) return;
-  if (tid == 0) { *done = 0u; __threadfence_system(); }
-  __syncthreads();
+  if (tid == 0) *done = 0u;   // for the next launch (stream-ordered after this one)
   if (tid < (uint32_t) world && tid != (uint32_t) rank) {
-    __threadfence_system();
     st_flag(&pt.sig[tid]->flags[rank], epoch_a + 1u);
     wait_flag(&mine->flags[tid], epoch_a + 1u);
-    __threadfence_system();
   }
 }
 
 struct PeerHello {
-  cudaIpcMemHandle_t sum, cnt, sig;
+  cudaIpcMemHandle_t sum, cnt, sig, sq;
   int ok;
   int device;
 };
@@ -365,6 +345,7 @@ int comm_setup_peers(qr_ctx *ctx) {
   QR_CUDA(cudaMemcpyAsync(&c->d_sig->magic, &magic, sizeof(magic), cudaMemcpyHostToDevice, st));
   QR_CUDA(cudaMemcpyAsync(ctx->d_hist_sum, &magic64, sizeof(magic64), cudaMemcpyHostToDevice, st));
   QR_CUDA(cudaMemcpyAsync(ctx->d_hist_cnt, &magic, sizeof(magic), cudaMemcpyHostToDevice, st));
+  QR_CUDA(cudaMemcpyAsync(ctx->d_sq128, &magic64, sizeof(magic64), cudaMemcpyHostToDevice, st));
   QR_CUDA(cudaStreamSynchronize(st));
   PeerHello hello;
   memset(&hello, 0, sizeof(hello));
@@ -372,7 +353,8 @@ int comm_setup_peers(qr_ctx *ctx) {
   if (ok) {
     if (cudaIpcGetMemHandle(&hello.sum, ctx->d_hist_sum) != cudaSuccess ||
         cudaIpcGetMemHandle(&hello.cnt, ctx->d_hist_cnt) != cudaSuccess ||
-        cudaIpcGetMemHandle(&hello.sig, c->d_sig) != cudaSuccess) {
+        cudaIpcGetMemHandle(&hello.sig, c->d_sig) != cudaSuccess ||
+        cudaIpcGetMemHandle(&hello.sq, ctx->d_sq128) != cudaSuccess) {
       ok = 0; why = "cudaIpcGetMemHandle failed";
       cudaGetLastError();
     }
@@ -386,11 +368,12 @@ int comm_setup_peers(qr_ctx *ctx) {
     c->peers.sum[c->rank] = ctx->d_hist_sum;
     c->peers.cnt[c->rank] = ctx->d_hist_cnt;
     c->peers.sig[c->rank] = c->d_sig;
+    c->peers.sq[c->rank] = ctx->d_sq128;
     for (int p = 0; p < c->world && ok; ++p) {
       if (p == c->rank) continue;
-      void *ptrs[3] = {nullptr, nullptr, nullptr};
-      const cudaIpcMemHandle_t *hd[3] = {&hs[p].sum, &hs[p].cnt, &hs[p].sig};
-      for (int i = 0; i < 3 && ok; ++i) {
+      void *ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+      const cudaIpcMemHandle_t *hd[4] = {&hs[p].sum, &hs[p].cnt, &hs[p].sig, &hs[p].sq};
+      for (int i = 0; i < 4 && ok; ++i) {
         if (cudaIpcOpenMemHandle(&ptrs[i], *hd[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
           ok = 0; why = "cudaIpcOpenMemHandle failed (no peer access between the devices?)";
           cudaGetLastError();
@@ -402,11 +385,14 @@ int comm_setup_peers(qr_ctx *ctx) {
       c->peers.sum[p] = (unsigned long long *) ptrs[0];
       c->peers.cnt[p] = (uint32_t *) ptrs[1];
       c->peers.sig[p] = (PeerSignals *) ptrs[2];
-      unsigned long long m64 = 0;
+      c->peers.sq[p] = (ulonglong2 *) ptrs[3];
+      unsigned long long m64 = 0, m64b = 0;
       uint32_t m32a = 0, m32b = 0;
       if (cudaMemcpy(&m64, c->peers.sum[p], sizeof(m64), cudaMemcpyDeviceToHost) != cudaSuccess ||
           cudaMemcpy(&m32a, c->peers.cnt[p], sizeof(m32a), cudaMemcpyDeviceToHost) != cudaSuccess ||
           cudaMemcpy(&m32b, &c->peers.sig[p]->magic, sizeof(m32b), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          cudaMemcpy(&m64b, c->peers.sq[p], sizeof(m64b), cudaMemcpyDeviceToHost) != cudaSuccess ||
+          m64b != 0x51b2000051b20000ull + (unsigned long long) p ||
           m64 != 0x51b2000051b20000ull + (unsigned long long) p || m32a != 0x51b20000u + (uint32_t) p ||
           m32b != 0x51b20000u + (uint32_t) p) {
         ok = 0; why = "a mapped peer buffer does not show the peer's mark";
@@ -436,6 +422,23 @@ int comm_setup_peers(qr_ctx *ctx) {
 
 int comm_transport(const Comm *c) { return c == nullptr ? 0 : (c->peer_ok ? 2 : 1); }
 
+// the view finalize_kernel needs to add the peers' staging slots itself (one barrier epoch per round)
+void comm_peer_view(qr_ctx *ctx, bool with_counts, PeerView *pv) {
+  Comm *c = ctx->comm;
+  memset(pv, 0, sizeof(*pv));
+  for (int p = 0; p < c->world; ++p) {
+    pv->sum[p] = c->peers.sum[p];
+    pv->cnt[p] = c->peers.cnt[p];
+    pv->sq[p] = c->peers.sq[p] + ctx->round_sq_off;
+    pv->peer_flags[p] = c->peers.sig[p]->flags;
+  }
+  pv->flags = c->d_sig->flags;
+  pv->rank = c->rank;
+  pv->world = c->world;
+  pv->epoch = ++c->epoch;
+  pv->with_counts = with_counts ? 1 : 0;
+}
+
 static int peer_reduce_tasks(qr_ctx *ctx, uint32_t k, bool root) {
   Comm *c = ctx->comm;
   const int with_counts = (root && ctx->d_root_cnt != nullptr) ? 0 : 1;
@@ -444,7 +447,8 @@ static int peer_reduce_tasks(qr_ctx *ctx, uint32_t k, bool root) {
   const uint32_t epoch_a = c->epoch + 1u;
   c->epoch += 2u;
   peer_reduce_kernel<<<grid, kPeerThreads, 0, ctx->stream>>>(c->peers, c->rank, c->world, ctx->d_tasks, k, ctx->ncells,
-                                                             epoch_a, with_counts, ctx->d_sq128, c->d_done, ctx->pack);
+                                                             epoch_a, with_counts, ctx->d_sq128 + ctx->round_sq_off, c->d_done,
+                                                             ctx->pack);
   ctx->launches++;
   QR_CUDA(cudaGetLastError());
   return QR_OK;

@@ -29,6 +29,8 @@ int comm_reduce_tasks(qr_ctx *ctx, uint32_t ntasks, bool root);
 int comm_setup_peers(qr_ctx *ctx);
 // 0: single GPU, 1: NCCL all-reduces, 2: peer-memory kernel
 int comm_transport(const Comm *c);
+// fills the view finalize_kernel needs for the fused exchange of the current round (takes one barrier epoch)
+void comm_peer_view(qr_ctx *ctx, bool with_counts, PeerView *pv);
 // all-reduce the per-leaf (sum lambda, sum weight) pairs and recompute the leaf outputs
 int comm_leaf_values(qr_ctx *ctx, uint32_t nleaves);
 

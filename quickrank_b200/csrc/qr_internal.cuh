@@ -181,4 +181,12 @@ struct qr_ctx {
 
   qr::Comm *comm = nullptr;
   size_t N_global = 0, Q_global = 0;
+  size_t N_local_max = 0;                   // largest shard (documents) over the ranks
+  // sharded training over peer memory (qr_comm.cu): per-round state of the histogram exchange
+  int stage_slot0 = 0;                      // first of the 2 x max_tasks staging slots (after the nslots pool slots)
+  uint32_t xround = 0;                      // exchange rounds so far (its parity selects the staging set)
+  bool round_fused = false;                 // this round's all-reduce happens inside finalize_kernel
+  uint32_t round_parity = 0, round_sq_off = 0;   // staging set / offset into d_sq128 of this round
+  bool peer_fused = true;                   // QR_PEER_FUSED=0: always the stand-alone exchange kernel
+  uint32_t oneshot_max = 4;                 // fuse when (world - 1) * tasks <= this (QR_PEER_ONESHOT_MAX)
 };

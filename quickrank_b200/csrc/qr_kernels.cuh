@@ -79,7 +79,7 @@ __global__ void distinct_flags_kernel(const uint32_t *sorted_keys, float *vals, 
 
 __global__ void transpose_kernel(const float *rowmajor, float *colmajor, size_t N, size_t F) {
   __shared__ float tile[32][33];
-  size_t f0 = (size_t) blockIdx.x * 32, d0 = (size_t) blockIdx.y * 32;
+  size_t f0 = (size_t) blockIdx.y * 32, d0 = (size_t) blockIdx.x * 32;
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     size_t d = d0 + r, f = f0 + threadIdx.x;
     if (d < N && f < F) tile[r][threadIdx.x] = rowmajor[d * F + f];

@@ -24,9 +24,46 @@ struct NodeTask {
   uint32_t fused_sq;     // REFERENCE: 1 = fma chain (child ctor), 0 = mul+add (root update)
   uint32_t lcount;       // local left count when the host knows it (single GPU), see lc_known
   uint32_t lc_known;     // 0: kernels read the count computed by part_prefix_kernel instead
-  uint32_t pad0;
+  uint32_t stage1;       // sharded training, fused exchange: 1 + the staging slot the built child's LOCAL histogram
+                         // is accumulated in (the split scan adds all ranks' staging slots into slotB); 0: the
+                         // histogram is built in place in slotB
   double parent_squares;
 };
+
+// slot the histogram kernels accumulate the built child into
+__host__ __device__ __forceinline__ int32_t build_slot(const NodeTask &t) { return t.stage1 ? (int32_t) t.stage1 - 1 : t.slotB; }
+
+// ---- peer memory (sharded training on one NVSwitch node) ------------------------------------
+constexpr int kMaxPeers = 8;
+// What the split scan needs to read the peers' freshly built histograms itself (fused all-reduce + scan):
+// every rank maps every other rank's histogram pool, squares partials and flag array over CUDA IPC.
+struct PeerView {
+  const unsigned long long *sum[kMaxPeers];   // histogram pools (sums) of all ranks, own pool at [rank]
+  const uint32_t *cnt[kMaxPeers];             // histogram pools (counts)
+  const ulonglong2 *sq[kMaxPeers];            // squares partials
+  uint32_t *peer_flags[kMaxPeers];            // flag arrays: peer_flags[p][r] = last epoch rank r announced to p
+  uint32_t *flags;                            // own flag array
+  int rank, world;                            // world <= 1: nothing is exchanged inside the kernel
+  uint32_t epoch;
+  int with_counts;                            // 0: the counts are global already (root refresh)
+};
+
+// flags: release store (everything this thread wrote or observed before it, at system scope) / acquire load
+__device__ __forceinline__ uint32_t ld_flag(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_flag(uint32_t *p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// bounded spin: a peer that never arrives (crashed process) must not hang the GPU
+__device__ __forceinline__ void wait_flag(const uint32_t *p, uint32_t epoch) {
+  const long long t0 = clock64();
+  while ((int32_t) (ld_flag(p) - epoch) < 0) {
+    if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s
+  }
+}
 
 // Small rounds carry their task records inside the kernel parameters (constant bank): no
 // host-to-device copy sits between the host's decision and the round's first kernel.

@@ -345,6 +345,16 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     cudaFree(d_nq);
     c->N_global = (size_t) nq[0];
     c->Q_global = (size_t) nq[1];
+    // the largest shard: histogram slices are laid out from quantities every rank knows, so that all ranks
+    // use the same layout (the fused exchange reads the peers' per-slice squares partials)
+    unsigned long long nmax = (unsigned long long) N, *d_nmax = nullptr;
+    QR_TRY(dev_alloc(&d_nmax, 1));
+    QR_CUDA(cudaMemcpyAsync(d_nmax, &nmax, sizeof(nmax), cudaMemcpyHostToDevice, c->stream));
+    QR_TRY(comm_allreduce_max_u64(c->comm, d_nmax, 1, c->stream));
+    QR_CUDA(cudaMemcpyAsync(&nmax, d_nmax, sizeof(nmax), cudaMemcpyDeviceToHost, c->stream));
+    QR_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_nmax);
+    c->N_local_max = (size_t) nmax;
   }
 
   // features -> device column-major (VerticalDataset layout), then bins; floats are released
@@ -354,7 +364,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     float *d_row = nullptr;
     QR_TRY(dev_alloc(&d_row, N * F));
     QR_CUDA(cudaMemcpyAsync(d_row, feat, N * F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    dim3 grid((unsigned) ((F + 31) / 32), (unsigned) ((N + 31) / 32));
+    dim3 grid((unsigned) ((N + 31) / 32), (unsigned) ((F + 31) / 32));   // documents on x: grid.y stops at 65535
     transpose_kernel<<<grid, dim3(32, 8), 0, c->stream>>>(d_row, d_col, N, F);
     QR_CUDA(cudaGetLastError());
     QR_CUDA(cudaStreamSynchronize(c->stream));
@@ -441,15 +451,18 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   c->nslots = (int) (4 * maxleaves + 8);
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  const size_t hist_bytes = (size_t) c->nslots * c->ncells * 12;
+  // sharded training: two sets of staging slots behind the pool (local histograms of a round's built children)
+  c->stage_slot0 = c->nslots;
+  const size_t pool_slots = (size_t) c->nslots + (c->comm ? 2 * (maxleaves + 1) : 0);
+  const size_t hist_bytes = pool_slots * c->ncells * 12;
   if (hist_bytes + (64u << 20) > free_b) {
     set_error("histogram pool needs %zu MB (%d nodes x %u cells); not enough device memory — bound the "
-              "bin count with --num-thresholds", hist_bytes >> 20, c->nslots, c->ncells);
+              "bin count with --num-thresholds", hist_bytes >> 20, (int) pool_slots, c->ncells);
     return QR_ENOMEM;
   }
   // sharded training exports the two pools over CUDA IPC: at least 2 MB each, so that each is an allocation
   // of its own and not a piece of a page shared with other buffers
-  const size_t pool_cells = std::max<size_t>((size_t) c->nslots * c->ncells, c->comm ? ((size_t) 2 << 20) / 4 : 1);
+  const size_t pool_cells = std::max<size_t>(pool_slots * c->ncells, c->comm ? ((size_t) 2 << 20) / 4 : 1);
   QR_TRY(dev_alloc(&c->d_hist_sum, pool_cells));
   QR_TRY(dev_alloc(&c->d_hist_cnt, pool_cells));
   for (int i = c->nslots - 1; i >= 0; --i) c->free_slots.push_back(i);
@@ -457,7 +470,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_blockcnt, (N + kPartItems - 1) / kPartItems + mt + 1));
   QR_TRY(dev_alloc(&c->d_partials, mt));
   c->max_slices = 4096 + (uint32_t) mt;
-  QR_TRY(dev_alloc(&c->d_sq128, c->max_slices));
+  QR_TRY(dev_alloc(&c->d_sq128, std::max<size_t>(c->max_slices, c->comm ? ((size_t) 2 << 20) / sizeof(ulonglong2) : 1)));   // (exported over IPC)
   QR_TRY(dev_alloc(&c->d_task_done, mt));
   QR_CUDA(cudaMemset(c->d_task_done, 0, mt * sizeof(uint32_t)));
   QR_TRY(dev_alloc(&c->d_part_status, (N + kPartItems - 1) / kPartItems + mt + 1));
@@ -471,6 +484,8 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   memset(c->h_lcount, 0, mt * sizeof(uint32_t));
   if (c->comm) QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_lcount_mapped, c->h_lcount, 0));
   c->part_3pass = c->comm != nullptr && getenv("QR_COMM_3PASS") != nullptr;
+  if (const char *e = getenv("QR_PEER_FUSED")) c->peer_fused = atoi(e) != 0;
+  if (const char *e = getenv("QR_PEER_ONESHOT_MAX")) c->oneshot_max = (uint32_t) std::max(0, atoi(e));
   QR_TRY(dev_alloc(&c->d_fbest_score, mt * 2 * F * kFinParts));
   QR_TRY(dev_alloc(&c->d_fbest_t, mt * 2 * F * kFinParts));
   QR_TRY(dev_alloc(&c->d_fbest_lc, mt * 2 * F * kFinParts));

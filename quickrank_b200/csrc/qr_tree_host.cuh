@@ -107,6 +107,24 @@ static int wait_round_flags(qr_ctx *c, uint32_t k) {
   return QR_OK;
 }
 
+// Sharded training over peer memory: decides how this round's built histograms are exchanged, before the
+// round's task records are made.  Small rounds: the split scan itself adds the peers' staging slots (fused,
+// one barrier); wide rounds: the stand-alone in-place reduce-scatter + all-gather kernel (each rank moves
+// 2(W-1)/W of the payload instead of reading W-1 copies of it).  Every rank takes the same decision.
+constexpr uint32_t kSqRegion = 2048;   // squares partials: two regions of d_sq128, alternating by round
+static void begin_exchange_round(qr_ctx *c, uint32_t k) {
+  c->round_fused = false;
+  c->round_sq_off = 0;
+  c->round_parity = 0;
+  if (!c->comm || comm_transport(c->comm) != 2) return;
+  c->round_parity = c->xround++ & 1u;
+  c->round_sq_off = c->round_parity * kSqRegion;
+  c->round_fused = c->peer_fused && (uint32_t) (comm_world(c->comm) - 1) * k <= c->oneshot_max;
+}
+static uint32_t stage_of(const qr_ctx *c, uint32_t j) {
+  return c->round_fused ? 1u + (uint32_t) c->stage_slot0 + c->round_parity * c->max_tasks + j : 0u;
+}
+
 static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, bool slots_ready,
                                 double built_docs) {
   const uint32_t F = (uint32_t) c->F;
@@ -130,11 +148,11 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
     } else {
       const size_t smem = (size_t) c->fpp * c->max_thr * 12;
       const bool use_smem = smem <= 200 * 1024;
-      if (total_slices > c->max_slices - c->max_tasks) { set_error("internal: %u histogram slices > capacity", total_slices); return QR_ECUDA; }
+      if (total_slices > (c->comm ? kSqRegion : c->max_slices - c->max_tasks)) { set_error("internal: %u histogram slices > capacity", total_slices); return QR_ECUDA; }
 #define QR_HIST_LAUNCH(SMEMF, COUNTF)                                                                        \
   QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), kHistThreads,   \
             SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
-            c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr,             \
+            c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128 + c->round_sq_off, c->max_thr, \
             (const RoundHdr *) nullptr, c->pack, (const long long *) (c->part_3pass ? nullptr : c->d_lamq_c))
       if (c->profiling) cudaEventRecord(c->ev_k0, c->stream);
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
@@ -159,7 +177,7 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
         c->histk_docs += built_docs;
       }
     }
-    if (c->comm) QR_TRY(comm_reduce_tasks(c, k, root));
+    if (c->comm && !c->round_fused) QR_TRY(comm_reduce_tasks(c, k, root));
   }
   QR_TRACE_MARK(c);
   {
@@ -167,16 +185,23 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
     // results are written straight into mapped pinned host memory and announced through per-task
     // flags the host polls: no device-to-host copy and no stream synchronisation on the round path
     c->round_id++;
+    PeerView pv{};
+    if (c->round_fused) comm_peer_view(c, !(root && c->d_root_cnt != nullptr), &pv);
     if (c->exact)
       QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3(fin_blocks(F), k), kFinWarps * 32, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
                 c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
                 c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack);
+                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack, pv);
+    else if (c->round_fused)
+      QR_LAUNCH(c, PH_SCAN, (finalize_kernel<false, true>), dim3(fin_blocks(F), k), kFinWarps * 32, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
+                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
+                c->d_fbest_lc, c->d_totals, c->d_sq128 + c->round_sq_off, c->d_partials, c->d_task_done, c->d_res_mapped,
+                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack, pv);
     else
       QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3(fin_blocks(F), k), kFinWarps * 32, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
                 c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
-                c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack);
+                c->d_fbest_lc, c->d_totals, c->d_sq128 + c->round_sq_off, c->d_partials, c->d_task_done, c->d_res_mapped,
+                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack, pv);
     QR_TRACE_MARK(c);
     if (c->comm && c->part_3pass) {
       QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -206,11 +231,15 @@ static int build_root(qr_ctx *c) {
   root.hist = alloc_slot(c);
   NodeTask &t = c->h_tasks[0];
   memset(&t, 0, sizeof(t));
+  begin_exchange_round(c, 1);
   t.lo = 0; t.n = root.n; t.src = 2; t.dst = 0; t.whole = 1; t.build_left = 1;
   t.slotP = -1; t.slotB = root.hist; t.slotD = -1;
-  t.hist_dpb = pick_hist_dpb(c, root.n);
+  t.stage1 = stage_of(c, 0);
+  // sharded: the slicing is derived from the largest shard, so that it is the same on every rank
+  const uint32_t layout_n = c->comm ? (uint32_t) c->N_local_max : root.n;
+  t.hist_dpb = pick_hist_dpb(c, layout_n);
   t.hist_blk0 = 0; t.part_blk0 = 0; t.sq0 = 0; t.fused_sq = 0;
-  const uint32_t slices = std::max<uint32_t>(1, (root.n + t.hist_dpb - 1) / t.hist_dpb);
+  const uint32_t slices = std::max<uint32_t>(1, (layout_n + t.hist_dpb - 1) / t.hist_dpb);
   t.hist_nblk = slices;
   QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
   QR_TRY(launch_hist_and_scan(c, 1, slices, true, false, (double) root.n));
@@ -271,25 +300,29 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     const HostNode &nd = c->nodes[S[j]];
     const uint64_t lc = nd.res.lcount, rc = nd.res.n - nd.res.lcount;
     const bool build_left = c->exact ? true : lc <= rc;
-    // local sizes are only known exactly on a single GPU; with several ranks bound by the node size
-    built_total += c->comm ? nd.n : (build_left ? lc : rc);
+    // local sizes are only known exactly on a single GPU; with several ranks: the expected share
+    built_total += c->comm ? std::min(lc, rc) / (uint64_t) comm_world(c->comm) : (build_left ? lc : rc);
   }
   uint32_t dpb = pick_hist_dpb(c, built_total);
+  if (build_child_hists) begin_exchange_round(c, k);
   if (c->comm) {
-    // the local size of the built child is unknown until the partition has run; queries are sharded without
-    // regard to their content, so it is close to the node's local size times the global ratio.  Slices are
-    // sized for that estimate (plus a margin), their number for the whole local node (slices past the real
-    // end return at once), capped so that a round never launches many waves of empty blocks.
-    uint64_t est_total = 0, node_total = 0;
+    // The local size of the built child is unknown until the partition has run, and the slicing must be the
+    // same on every rank (the fused exchange reads the peers' per-slice squares partials): it is derived
+    // from replicated quantities only.  bound = min(global size of the built child, largest shard) covers
+    // any rank's share; queries are sharded without regard to their content, so the typical share is the
+    // global size / W: slices are sized for that (plus a margin), their number for the bound (slices past
+    // the real end return at once), capped so that a round never launches waves of empty blocks.
+    const uint64_t W = (uint64_t) comm_world(c->comm);
+    uint64_t est_total = 0, bound_total = 0;
     for (uint32_t j = 0; j < k; ++j) {
       const HostNode &nd = c->nodes[S[j]];
-      const uint64_t lc = nd.res.lcount, rc = nd.res.n - nd.res.lcount;
-      const double ratio = (double) std::min(lc, rc) / (double) std::max<uint64_t>(nd.res.n, 1);
-      est_total += (uint64_t) ((double) nd.n * ratio * 1.25) + 256u;
-      node_total += nd.n;
+      const uint64_t built = std::min(nd.res.lcount, nd.res.n - nd.res.lcount);
+      const uint64_t bound = std::min<uint64_t>(built, c->N_local_max);
+      est_total += std::min<uint64_t>(bound, built / W + built / (4 * W) + 256u);
+      bound_total += bound;
     }
     const uint32_t max_slices = 4u * std::max<uint32_t>(1, 148u / c->npanels) + k;
-    const uint64_t floor_dpb = ((node_total + max_slices - 1) / max_slices + 255u) & ~(uint64_t) 255u;
+    const uint64_t floor_dpb = ((bound_total + max_slices - 1) / max_slices + 255u) & ~(uint64_t) 255u;
     dpb = (uint32_t) std::min<uint64_t>(std::max<uint64_t>(pick_hist_dpb(c, est_total), floor_dpb), 1u << 20);
   }
   uint32_t part_blk = 0, hist_blk = 0;
@@ -313,8 +346,9 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     part_blk += std::max<uint32_t>(1, (nd.n + kPartItems - 1) / kPartItems);
     t.hist_blk0 = hist_blk;
     t.hist_dpb = dpb;
-    const uint64_t built_n = c->comm ? nd.n : (t.build_left ? lc : rc);
+    const uint64_t built_n = c->comm ? std::min<uint64_t>(std::min(lc, rc), c->N_local_max) : (t.build_left ? lc : rc);
     t.hist_nblk = std::max<uint32_t>(1, (uint32_t) ((built_n + dpb - 1) / dpb));
+    t.stage1 = build_child_hists ? stage_of(c, j) : 0u;
     hist_blk += t.hist_nblk;
     if (build_child_hists) c->beta += (double) (t.build_left ? lc : rc) / (double) c->N_global;
     t.lcount = (uint32_t) lc;
@@ -649,7 +683,7 @@ static int enqueue_device_round(qr_ctx *c, uint32_t round, bool root) {
   QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3(fin_blocks(F), root ? 1u : mt), kFinWarps * 32, 0, tasks,
             c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score,
             c->d_fbest_t, c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res,
-            (volatile uint32_t *) nullptr, 0u, (const RoundHdr *) hdr, c->pack);
+            (volatile uint32_t *) nullptr, 0u, (const RoundHdr *) hdr, c->pack, PeerView{});
   QR_LAUNCH(c, PH_SCAN, grow_step_kernel, 1, kGrowThreads, c->grow_smem, c->d_grow, hdr, next_hdr, tasks, next_tasks,
             c->d_res, c->d_ticket, c->d_segs, c->d_grow_out);
   return QR_OK;

@@ -39,8 +39,8 @@ __device__ __forceinline__ void built_segment(const NodeTask &t, uint32_t lcount
 __global__ void prep_slots_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum,
                                   uint32_t *hcnt, uint32_t ncells, const uint32_t *__restrict__ root_cnt) {
   const NodeTask t = tasks[blockIdx.y];
-  unsigned long long *s = hsum + (size_t) t.slotB * ncells;
-  uint32_t *c = hcnt + (size_t) t.slotB * ncells;
+  unsigned long long *s = hsum + (size_t) build_slot(t) * ncells;
+  uint32_t *c = hcnt + (size_t) build_slot(t) * ncells;
   const bool copy = t.whole && root_cnt != nullptr;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < ncells; i += gridDim.x * blockDim.x) {
     s[i] = 0ull;
@@ -187,8 +187,8 @@ partition_onepass_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, co
   if (t.slotB >= 0) {
     const uint32_t chunk = (ncells + nb - 1) / nb;
     const uint32_t z0 = lb * chunk, z1 = min(ncells, z0 + chunk);
-    unsigned long long *zs = hsum + (size_t) t.slotB * ncells;
-    uint32_t *zc = hcnt + (size_t) t.slotB * ncells;
+    unsigned long long *zs = hsum + (size_t) build_slot(t) * ncells;
+    uint32_t *zc = hcnt + (size_t) build_slot(t) * ncells;
     for (uint32_t i = z0 + threadIdx.x; i < z1; i += 256) { zs[i] = 0ull; zc[i] = 0u; }
   }
   const uint32_t *src = t.src == 1 ? ids1 : ids0;
@@ -401,8 +401,8 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const uint
   }
   __syncthreads();
 
-  unsigned long long *gs = hsum + (size_t) t.slotB * ncells + cell0;
-  uint32_t *gc = hcnt + (size_t) t.slotB * ncells + cell0;
+  unsigned long long *gs = hsum + (size_t) build_slot(t) * ncells + cell0;
+  uint32_t *gc = hcnt + (size_t) build_slot(t) * ncells + cell0;
   const bool identity = t.whole && t.src == 2;
   const uint32_t *ids = ((t.whole ? t.src : t.dst) == 1 ? ids1 : ids0) + seg0;
   const uint4 *prow = panels + (size_t) p * N;
@@ -616,7 +616,7 @@ constexpr uint32_t kFinWarps = 9;   // warps per finalize block
 constexpr uint32_t kFinParts = 3;
 __host__ __device__ inline uint32_t fin_blocks(uint32_t F) { return (F * kFinParts + kFinWarps - 1) / kFinWarps; }
 
-template <bool EXACT>
+template <bool EXACT, bool PEER = false>
 __global__ void __launch_bounds__(kFinWarps * 32)
 finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, uint32_t *hcnt,
                 uint32_t ncells, const uint32_t *__restrict__ thr_off, uint32_t F, uint32_t minls,
@@ -624,12 +624,26 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
                 ulonglong2 *totals, const ulonglong2 *__restrict__ sq128,
                 const double *__restrict__ sq_exact, uint32_t *task_done, SplitResult *res,
                 volatile uint32_t *host_flags, uint32_t round_id, const RoundHdr *__restrict__ hdr,
-                const __grid_constant__ TaskPack pack) {
+                const __grid_constant__ TaskPack pack, const __grid_constant__ PeerView pv) {
   if (pack.n) tasks = pack.t;
   const uint32_t task = blockIdx.y;
   if (hdr && task >= hdr->ntasks) return;   // device-driven growth: upper-bound grid
   const NodeTask t = tasks[task];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  // Sharded training, fused exchange (all-reduce + split scan in one kernel): every rank accumulated the
+  // built child's LOCAL histogram in a staging slot; this kernel is stream-ordered after that, so its
+  // first block tells the peers "my staging slots of this round are complete", every block waits for the
+  // same word from all peers, and the loads below add the W staging slots (NVLink loads from the peers'
+  // pools) instead of reading one.  Integer sums: every rank obtains the same totals in any order.
+  // Nothing is written to a peer, and staging slots alternate between two sets by round, so no second
+  // barrier is needed (a rank can be at most one round ahead of its slowest peer).
+  const int W = (PEER && !EXACT && pv.world > 1 && t.stage1) ? pv.world : 1;   // PEER = false: compiled out
+  if (W > 1) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < (uint32_t) W && threadIdx.x != (uint32_t) pv.rank)
+      st_flag(pv.peer_flags[threadIdx.x] + pv.rank, pv.epoch);
+    if (threadIdx.x < (uint32_t) W && threadIdx.x != (uint32_t) pv.rank) wait_flag(pv.flags + threadIdx.x, pv.epoch);
+    __syncthreads();
+  }
   const uint32_t gw = blockIdx.x * kFinWarps + warp;
   const uint32_t f = gw / kFinParts, part = gw % kFinParts;
   const double inv = EXACT ? 1.0 : ldexp(1.0, -*qexp);
@@ -650,6 +664,10 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
   const uint32_t c0 = active ? thr_off[f] : 0u, cells = active ? thr_off[f + 1] - c0 : 0u;
   unsigned long long *Bs = hsum + (size_t) t.slotB * ncells + c0;
   uint32_t *Bc = hcnt + (size_t) t.slotB * ncells + c0;
+  // raw (not yet cumulative) bins of the built child: slotB itself, or the staging slot(s)
+  const size_t roff = (size_t) build_slot(t) * ncells + c0;
+  const unsigned long long *Rs = hsum + roff;
+  const uint32_t *Rc = hcnt + roff;
   const bool two = nchild == 2;
   const unsigned long long *Ps = two ? hsum + (size_t) t.slotP * ncells + c0 : Bs;
   const uint32_t *Pc = two ? hcnt + (size_t) t.slotP * ncells + c0 : Bc;
@@ -667,10 +685,33 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
       const uint32_t k = ch * 32 + lane;
       const bool own = (uint32_t) (ch / kOwn) == part;
       const bool in = k < cells && (!EXACT || own);   // FAST: the prefix needs every bin of the built child
-      bs[ch] = in ? Bs[k] : 0ull;
-      bc[ch] = in ? Bc[k] : 0u;
+      bs[ch] = in ? Rs[k] : 0ull;
+      bc[ch] = in ? Rc[k] : 0u;
       ps[ch] = (in && two && own) ? Ps[k] : 0ull;
       pc[ch] = (in && two && own) ? Pc[k] : 0u;
+    }
+    if (W > 1) {
+      // the peers' staging slots, two peers at a time (all loads of a pair are in flight together)
+      for (int q0 = 0; q0 < W - 1; q0 += 2) {
+        const int pa = q0 + (q0 >= pv.rank ? 1 : 0);
+        const bool has_b = q0 + 1 < W - 1;
+        const int pb = has_b ? q0 + 1 + (q0 + 1 >= pv.rank ? 1 : 0) : pa;
+        const volatile unsigned long long *sa = pv.sum[pa] + roff, *sb = pv.sum[pb] + roff;
+        const volatile uint32_t *ca = pv.cnt[pa] + roff, *cb = pv.cnt[pb] + roff;
+        unsigned long long va[kFinChunks], vb[kFinChunks];
+        uint32_t na[kFinChunks], nb[kFinChunks];
+#pragma unroll
+        for (int ch = 0; ch < kFinChunks; ++ch) {
+          const uint32_t k = ch * 32 + lane;
+          const bool in = k < cells;
+          va[ch] = in ? sa[k] : 0ull;
+          vb[ch] = (in && has_b) ? sb[k] : 0ull;
+          na[ch] = (in && pv.with_counts) ? ca[k] : 0u;
+          nb[ch] = (in && has_b && pv.with_counts) ? cb[k] : 0u;
+        }
+#pragma unroll
+        for (int ch = 0; ch < kFinChunks; ++ch) { bs[ch] += va[ch] + vb[ch]; bc[ch] += na[ch] + nb[ch]; }
+      }
     }
     // last bins (node totals): parent's from memory, built child's from memory (EXACT) or the prefix
     plast = two ? Ps[lastk] : 0ull;
@@ -776,8 +817,15 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
         uint32_t carryc = 0;
         for (uint32_t base = 0; base < cells; base += 32) {
           const uint32_t k = base + lane;
-          long long v = k < cells ? (long long) Bs[k] : 0;
-          uint32_t cv = k < cells ? Bc[k] : 0u;
+          long long v = k < cells ? (long long) Rs[k] : 0;
+          uint32_t cv = k < cells ? Rc[k] : 0u;
+          if (W > 1 && k < cells) {
+            for (int p = 0; p < W; ++p) {
+              if (p == pv.rank) continue;
+              v += (long long) *(const volatile unsigned long long *) (pv.sum[p] + roff + k);
+              if (pv.with_counts) cv += *(const volatile uint32_t *) (pv.cnt[p] + roff + k);
+            }
+          }
           for (int o = 1; o < 32; o <<= 1) {
             const long long pv = __shfl_up_sync(0xffffffffu, v, o);
             const uint32_t pcv = __shfl_up_sync(0xffffffffu, cv, o);
@@ -853,7 +901,26 @@ finalize_kernel(const NodeTask *__restrict__ tasks, unsigned long long *hsum, ui
   // the per-feature winners of BOTH children travel together (the tail is a chain of L2 round trips)
   const uint32_t FP = F * kFinParts;
   double sqB = 0.0;
-  if (threadIdx.x < 2) {
+  if (W > 1) {
+    // exact squares of the built child over all ranks: warp 0 folds the W x hist_nblk 128-bit partials
+    if (warp == 0) {
+      U128 tot{0ull, 0ull};
+      const uint32_t items = (uint32_t) W * t.hist_nblk;
+      for (uint32_t it = lane; it < items; it += 32) {
+        const uint32_t p = it / t.hist_nblk, i = it - p * t.hist_nblk;
+        const volatile unsigned long long *v = reinterpret_cast<const volatile unsigned long long *>(pv.sq[p] + t.hist_blk0 + i);
+        const unsigned long long lo = v[0], hi = v[1];
+        u128_add(tot, lo, hi);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ol = __shfl_xor_sync(0xffffffffu, tot.lo, o);
+        const unsigned long long oh = __shfl_xor_sync(0xffffffffu, tot.hi, o);
+        u128_add(tot, ol, oh);
+      }
+      const double inv2 = ldexp(1.0, -2 * *qexp);
+      sqB = ((double) tot.hi * 18446744073709551616.0 + (double) tot.lo) * inv2;
+    }
+  } else if (threadIdx.x < 2) {
     if (EXACT) {
       sqB = sq_exact[t.sq0];
     } else {

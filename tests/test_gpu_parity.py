@@ -472,3 +472,29 @@ def test_edge_case_datasets(case, algo, leaves, minls):
         for m in range(T):
             _tree, metric = tr.boost_iteration()
         assert abs(metric - want_metric[-1]) <= 1e-3 + REL * abs(want_metric[-1])
+
+
+def test_more_than_two_million_documents():
+    """BASELINE configs 3-5 are 2-10 M documents: the row-major entry point (device transpose) and the
+    column-major one must bin and train identically past 2^21 documents (a grid dimension used to
+    overflow there), and the histogram counts must account for every document."""
+    n, f, q = 2_300_000, 3, 23_000
+    rng = np.random.default_rng(5)
+    x = (rng.integers(0, 64, size=(n, f)) / 64.0).astype(np.float32)
+    x[:, 2] = x[:, 0]
+    labels = rng.integers(0, 5, size=n).astype(np.float32)
+    off = (np.arange(q + 1, dtype=np.uint64) * (n // q)).astype(np.uint64)
+    off[-1] = n
+    with api.Trainer(x, labels, off, algo="LAMBDAMART", nleaves=8) as a, \
+            api.Trainer(np.ascontiguousarray(x.T), labels, off, algo="LAMBDAMART", nleaves=8, layout="colmajor") as b:
+        for fi in range(f):
+            assert np.array_equal(a.get_bins(fi), b.get_bins(fi))
+        assert np.array_equal(a.get_bins(0), np.round(x[:, 0] * 64).astype(a.get_bins(0).dtype))
+        for _ in range(2):
+            ta, ma = a.boost_iteration()
+            tb, mb = b.boost_iteration()
+            assert common.same_structure(ta, tb)
+            assert np.array_equal(ta["value"], tb["value"]) and ma == mb
+            assert int(ta["count"][0]) == n
+            assert int(ta["count"][common.leaves_mask(ta)].sum()) == n
+        assert np.array_equal(a.get_scores(), b.get_scores())

@@ -1,6 +1,7 @@
-"""Two-rank training (one process per GPU, documents sharded by query) must grow the same trees as
-one GPU, whether the per-round histograms are exchanged by the peer-memory kernel (CUDA IPC over
-NVLink) or by NCCL all-reduces: histogram sums are fixed-point integers, so the totals do not
+"""Sharded training (one process per GPU, documents sharded by query; 2 ranks, QR_TEST_WORLD for more)
+must grow the same trees as one GPU, whether the per-round histograms are exchanged inside the
+split-scan kernel (peer-memory loads over NVLink), by the stand-alone peer-memory kernel or by NCCL
+all-reduces: histogram sums are fixed-point integers, so the totals do not
 depend on the number of ranks or on the order of the additions."""
 import multiprocessing as mp
 import os
@@ -16,8 +17,20 @@ pytestmark = pytest.mark.gpu
 T = 6
 
 
-def _worker(rank, world, q, out_q, algo, kw, peer):
-    os.environ["QR_PEER_REDUCE"] = "1" if peer else "0"
+MODES = {
+    # name: (environment, expected transport)
+    "peer-auto": ({}, "peer"),                                   # fused for small rounds, stand-alone kernel for wide ones
+    "peer-fused": ({"QR_PEER_ONESHOT_MAX": "100000"}, "peer"),   # every round: all-reduce inside the split-scan kernel
+    "peer-twoshot": ({"QR_PEER_FUSED": "0"}, "peer"),            # every round: the in-place reduce-scatter + all-gather kernel
+    "nccl": ({"QR_PEER_REDUCE": "0"}, "nccl"),
+}
+WORLD = int(os.environ.get("QR_TEST_WORLD", "2"))
+
+
+def _worker(rank, world, q, out_q, algo, kw, mode):
+    for k in ("QR_PEER_REDUCE", "QR_PEER_FUSED", "QR_PEER_ONESHOT_MAX"):
+        os.environ.pop(k, None)
+    os.environ.update(MODES[mode][0])
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from quickrank_b200 import api
     from quickrank_b200.sharding import query_shards
@@ -43,20 +56,20 @@ def _worker(rank, world, q, out_q, algo, kw, peer):
     out_q.put((rank, trees, metrics, d0, d1, scores, transport))
 
 
-@pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl"])
+@pytest.mark.parametrize("mode", list(MODES))
 @pytest.mark.parametrize("algo,kw", [("LAMBDAMART", dict(nleaves=16)), ("MART", dict(nleaves=8)),
                                      ("OBVLAMBDAMART", dict(treedepth=3))])
-def test_two_ranks_grow_the_single_gpu_trees(algo, kw, peer):
+def test_sharded_ranks_grow_the_single_gpu_trees(algo, kw, mode):
     from quickrank_b200 import api
-    if api.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if api.device_count() < WORLD:
+        pytest.skip("needs %d GPUs" % WORLD)
     x, l, off = common.dataset(n=20000, f=24, q=200, seed=21)
     with api.Trainer(x, l, off, algo=algo, **kw) as tr:
         want = [tr.boost_iteration() for _ in range(T)]
         want_scores = tr.get_scores()
     ctx = mp.get_context("spawn")
     q, out_q = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, q, out_q, algo, kw, peer)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, WORLD, q, out_q, algo, kw, mode)) for r in range(WORLD)]
     for p in procs:
         p.start()
     results = sorted([out_q.get(timeout=300) for _ in procs], key=lambda r: r[0])
@@ -67,7 +80,7 @@ def test_two_ranks_grow_the_single_gpu_trees(algo, kw, peer):
     for rank, trees, metrics, d0, d1, scores, transport in results:
         # the exchange under test must be the one that ran (the peer-memory path falls back to NCCL, with a
         # message on stderr, only where the devices cannot map each other's memory)
-        assert transport == ("peer" if peer else "nccl"), transport
+        assert transport == MODES[mode][1], transport
         got_scores[d0:d1] = scores
         for m in range(T):
             wt, wm = want[m]
@@ -77,7 +90,8 @@ def test_two_ranks_grow_the_single_gpu_trees(algo, kw, peer):
             assert np.max(np.abs(trees[m]["value"][lv] - wt["value"][lv])) <= 1e-12 * np.max(np.abs(wt["value"][lv]))
             assert abs(metrics[m] - wm) <= 1e-12
     assert np.max(np.abs(got_scores - want_scores)) <= 1e-12 * np.max(np.abs(want_scores))
-    # both ranks hold the identical model
-    for m in range(T):
-        assert common.same_structure(results[0][1][m], results[1][1][m])
-        assert np.array_equal(results[0][1][m]["value"], results[1][1][m]["value"])
+    # all ranks hold the identical model
+    for r in range(1, WORLD):
+        for m in range(T):
+            assert common.same_structure(results[0][1][m], results[r][1][m])
+            assert np.array_equal(results[0][1][m]["value"], results[r][1][m]["value"])
