@@ -107,19 +107,6 @@ def make_shard(rank, world, w=WORKLOAD):
             (qoff[q0:q1 + 1] - qoff[q0]).astype(np.uint64))
 
 
-def comm2(rank, world, dist):
-    """A second NCCL communicator id for the end-to-end context (N > 1)."""
-    if world == 1:
-        return None
-    import torch
-    from quickrank_b200 import api
-    idt = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    return (bytes(idt.cpu().numpy().tobytes()), rank, world)
-
-
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/hist_full_summary.json, written by scripts/ncu_summary.py)."""
@@ -175,8 +162,10 @@ def run_ours(args):
                      hist_mode=api.HIST_FAST, device=local_rank, comm=comm)
     init_s = time.perf_counter() - t0
     exchange = {"none": "none (one GPU)", "nccl": "NCCL all-reduces per growth round",
-                "peer": "one peer-memory kernel per growth round (CUDA IPC over NVLink: in-place "
-                        "reduce-scatter + all-gather of the built histograms)"}[tr.comm_transport()]
+                "peer": "peer memory over NVLink (CUDA IPC): the all-reduce of a round's built histograms is fused "
+                        "into the split-scan kernel (peer loads, one flag barrier) when (W-1)*nodes <= 4, else one "
+                        "stand-alone in-place reduce-scatter + all-gather kernel; NCCL only per tree (scale, leaf "
+                        "sums, NDCG)"}[tr.comm_transport()]
 
     def barrier():
         if dist is not None:
@@ -231,7 +220,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     tr2 = api.Trainer(x, labels, qoff, algo="LAMBDAMART", nleaves=w["leaves"], minleafsupport=w["minls"],
                       nthresholds=w["nthresholds"], cutoff=w["cutoff"], shrinkage=w["shrinkage"],
-                      hist_mode=api.HIST_FAST, device=local_rank, comm=comm2(rank, world, dist))
+                      hist_mode=api.HIST_FAST, device=local_rank, comm=comm)   # same id: the process's NCCL communicator is reused
     e2e_init_s = time.perf_counter() - t0
     for _ in range(e2e_trees):
         tr2.compute_pseudoresponses()
@@ -312,7 +301,10 @@ def run_ours(args):
                     "note": "whole training job from host buffers: qr_ctx_create (dataset host->device, "
                             "thresholds, binning = Mart::init) + %d boosting iterations through the hook-level "
                             "C ABI, each copying the fitted tree and NDCG@10 to the host; the first ~25 trees "
-                            "(tied scores, sequential sort replica) are inside" % e2e_trees},
+                            "(tied scores, sequential sort replica) are inside" % e2e_trees
+                            + ("" if world == 1 else "; the process's NCCL communicator (bootstrapped once, like the "
+                               "CUDA context, when the first context was made) is reused; the CUDA IPC mapping of "
+                               "the peers' histogram pools is inside")},
             "init_s": round(init_s, 3), "init_h2d_bytes": int(x.nbytes + labels.nbytes + qoff.nbytes),
             "gpu_launches": int(launches),
             "roofline": roofline,

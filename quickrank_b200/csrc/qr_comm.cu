@@ -19,6 +19,8 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
+#include <string>
 
 #include <cfloat>
 
@@ -92,7 +94,8 @@ struct PeerTable {
 
 struct Comm {
   int rank = 0, world = 1;
-  ncclComm_t nccl = nullptr;
+  ncclComm_t nccl = nullptr;         // shared with the other contexts of this process that use the same id
+  std::string key;
   long long *d_sq_limbs = nullptr;   // [max_tasks][3] 43-bit limbs of the squares sums
   double *d_scratch = nullptr;       // small host<->device staging
   unsigned long long *d_leafn = nullptr;   // [maxleaves] global leaf sizes (MART mean)
@@ -110,22 +113,47 @@ struct Comm {
 int comm_rank(const Comm *c) { return c ? c->rank : 0; }
 int comm_world(const Comm *c) { return c ? c->world : 1; }
 
+// NCCL communicators are process-level plumbing (bootstrap + transport set-up take seconds): contexts
+// created with the same id in one process share one communicator, and an idle communicator is kept until
+// a different id is asked for.  (Single caller thread, like everything else here; the contexts of one
+// process issue their collectives one after the other, in the same order on every rank.)
+struct SharedNccl { ncclComm_t comm = nullptr; int refs = 0, rank = 0, world = 0; };
+static std::map<std::string, SharedNccl> g_comms;
+
 int comm_create(const unsigned char id[QR_COMM_ID_BYTES], int rank, int world, Comm **out) {
   *out = nullptr;
   if (world < 1 || rank < 0 || rank >= world) { set_error("bad rank %d / world %d", rank, world); return QR_EINVAL; }
   QR_TRY(load_nccl());
+  const std::string key(reinterpret_cast<const char *>(id), QR_COMM_ID_BYTES);
+  auto it = g_comms.find(key);
+  if (it != g_comms.end() && (it->second.rank != rank || it->second.world != world)) {
+    set_error("communicator id already in use in this process as rank %d of %d", it->second.rank, it->second.world);
+    return QR_EINVAL;
+  }
+  if (it == g_comms.end()) {
+    for (auto jt = g_comms.begin(); jt != g_comms.end();) {   // idle communicators of other ids
+      if (jt->second.refs == 0) { g_nccl.CommDestroy(jt->second.comm); jt = g_comms.erase(jt); }
+      else ++jt;
+    }
+    ncclUniqueId uid;
+    static_assert(sizeof(uid.internal) == QR_COMM_ID_BYTES, "NCCL unique id size");
+    memcpy(uid.internal, id, QR_COMM_ID_BYTES);
+    SharedNccl sh;
+    sh.rank = rank;
+    sh.world = world;
+    ncclResult_t r = g_nccl.CommInitRank(&sh.comm, world, uid, rank);
+    if (r != ncclSuccess) {
+      set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+      return QR_ECOMM;
+    }
+    it = g_comms.emplace(key, sh).first;
+  }
+  it->second.refs++;
   Comm *c = new Comm();
   c->rank = rank;
   c->world = world;
-  ncclUniqueId uid;
-  static_assert(sizeof(uid.internal) == QR_COMM_ID_BYTES, "NCCL unique id size");
-  memcpy(uid.internal, id, QR_COMM_ID_BYTES);
-  ncclResult_t r = g_nccl.CommInitRank(&c->nccl, world, uid, rank);
-  if (r != ncclSuccess) {
-    set_error("ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
-    delete c;
-    return QR_ECOMM;
-  }
+  c->nccl = it->second.comm;
+  c->key = key;
   *out = c;
   return QR_OK;
 }
@@ -138,7 +166,8 @@ void comm_destroy(Comm *c) {
   if (c->d_leafn) cudaFree(c->d_leafn);
   if (c->d_sq_limbs) cudaFree(c->d_sq_limbs);
   if (c->d_scratch) cudaFree(c->d_scratch);
-  if (c->nccl) g_nccl.CommDestroy(c->nccl);
+  auto it = g_comms.find(c->key);
+  if (it != g_comms.end() && it->second.refs > 0) it->second.refs--;   // the communicator stays cached
   delete c;
 }
 
