@@ -175,6 +175,27 @@ class GenOblivious {
 };
 
 }  // namespace io
+
+// Multi-GPU training (one process per GPU): every process loads the dataset, keeps
+// a contiguous range of whole queries (lambdas need all documents of a query, lambdamart.cc:71-151) and
+// creates its training context with qr_ctx_create_sharded; afterwards every process runs the SAME
+// Mart::learn loop — the all-reduced histograms make every decision identical — and rank 0 reports.
+namespace host {
+struct Sharding {
+  int rank = 0, world = 1;
+  int local_rank = 0;            // CUDA device of this process
+  std::string addr = "127.0.0.1";
+  int port = 0;                  // TCP port rank 0 serves the communicator id on
+};
+void set_sharding(const Sharding &s);
+const Sharding &sharding();
+// Contiguous query ranges [q_begin, q_end) per rank, balanced by document count; the rule of
+// quickrank_b200/sharding.py (boundary closest to N*r/world, at least one query per rank).
+std::vector<std::pair<size_t, size_t>> query_shards(const uint64_t *offsets, size_t num_queries, int world);
+// Rank 0 sends `id` (nbytes) to every other rank over TCP (addr:port); the others receive it.
+// Returns false on failure (message on stderr).
+bool exchange_bytes(unsigned char *id, size_t nbytes, const Sharding &s, int timeout_s = 120);
+}  // namespace host
 }  // namespace quickrank
 
 // ---- tree structures (global namespace, as in the reference) -------------------------------------

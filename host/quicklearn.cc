@@ -11,9 +11,57 @@
 #include <map>
 #include <string>
 
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <sstream>
+#include <vector>
+
 #include "quickrank_host.h"
 
 using namespace quickrank;
+
+// Multi-GPU training: `--gpus N` forks N-1 more processes (one per GPU, before any CUDA call); under an
+// external launcher that sets RANK / WORLD_SIZE / LOCAL_RANK (torchrun, mpirun wrappers) the processes are
+// taken as they come.  Rank 0 serves the NCCL communicator id on MASTER_ADDR : QR_COMM_PORT.  Every rank
+// runs the same training loop; only rank 0 prints and writes files.
+static std::vector<pid_t> g_children;
+static int setup_sharding(int gpus) {
+  host::Sharding sh;
+  const char *er = getenv("RANK"), *ew = getenv("WORLD_SIZE");
+  if (er && ew && atoi(ew) > 1) {
+    sh.rank = atoi(er);
+    sh.world = atoi(ew);
+    sh.local_rank = getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : sh.rank;
+    if (getenv("MASTER_ADDR")) sh.addr = getenv("MASTER_ADDR");
+    sh.port = getenv("QR_COMM_PORT") ? atoi(getenv("QR_COMM_PORT")) : (getenv("MASTER_PORT") ? atoi(getenv("MASTER_PORT")) + 17 : 29517);
+  } else if (gpus > 1) {
+    sh.world = gpus;
+    sh.port = getenv("QR_COMM_PORT") ? atoi(getenv("QR_COMM_PORT")) : 20000 + (int) (getpid() % 20000);
+    std::cout.flush();
+    for (int r = 1; r < gpus; ++r) {
+      const pid_t pid = fork();
+      if (pid < 0) { perror("fork"); exit(EXIT_FAILURE); }
+      if (pid == 0) { sh.rank = r; g_children.clear(); break; }
+      g_children.push_back(pid);
+    }
+    sh.local_rank = sh.rank;
+  } else {
+    return 0;
+  }
+  if (sh.rank < 0 || sh.rank >= sh.world) { std::cerr << "!!! Bad RANK / WORLD_SIZE" << std::endl; exit(EXIT_FAILURE); }
+  host::set_sharding(sh);
+  return sh.rank;
+}
+// rank 0 of a self-launched run: the exit status covers the other ranks
+static int finish(int rc) {
+  for (pid_t k : g_children) {
+    int st = 0;
+    waitpid(k, &st, 0);
+    if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) { std::cerr << "!!! A training process failed." << std::endl; rc = EXIT_FAILURE; }
+  }
+  return rc;
+}
 
 static void usage() {
   std::cout << "quicklearn (quickrank_b200): LambdaMART / MART / oblivious variants on NVIDIA B200\n"
@@ -24,7 +72,9 @@ static void usage() {
                "  --min-leaf-support N (1)  --end-after-rounds N (100)  --num-leaves N (10)  --tree-depth N (3)\n"
                "  --train-metric NDCG  --train-cutoff K (10)  --test-metric NDCG  --test-cutoff K (10)\n"
                "  --partial N (100)  --scores <file>\n"
-               "  --hist-mode <fast|reference> (fast)  --device N\n";
+               "  --hist-mode <fast|reference> (fast)  --device N\n"
+               "  --gpus N   train on N GPUs (documents sharded by query, one process per GPU; or launch the\n"
+               "             processes yourself with RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR set)\n";
 }
 
 int main(int argc, char **argv) {
@@ -51,6 +101,21 @@ int main(int argc, char **argv) {
     return EXIT_SUCCESS;
   }
   const std::string algo = get("algo", "LAMBDAMART");
+  int rank = 0;
+  if (opt.count("train")) {
+    const int gpus = (int) geti("gpus", 1);
+    if ((gpus > 1 || (getenv("WORLD_SIZE") && atoi(getenv("WORLD_SIZE")) > 1)) && algo == "DART") {
+      std::cerr << "!!! DART trains on one GPU in this build." << std::endl;
+      return EXIT_FAILURE;
+    }
+    rank = setup_sharding(gpus);
+    if (rank != 0) {   // same loop, no report
+      // (never destroyed: std::cout is flushed once more when the process exits)
+      std::cout.rdbuf((new std::ostringstream())->rdbuf());
+      opt.erase("model-out");
+      opt.erase("scores");
+    }
+  }
   const size_t ntrees = geti("num-trees", 1000), nthr = geti("num-thresholds", 0), minls = geti("min-leaf-support", 1);
   const size_t esr = geti("end-after-rounds", 100), nleaves = geti("num-leaves", 10), depth = geti("tree-depth", 3);
   const double shrinkage = strtod(get("shrinkage", "0.1").c_str(), nullptr);
@@ -90,6 +155,8 @@ int main(int argc, char **argv) {
     if (opt.count("device")) mart->set_device(atoi(opt["device"].c_str()));
   }
   std::cout << "#" << std::endl << *ranker << "#" << std::endl;
+  if (host::sharding().world > 1)
+    std::cout << "# training on " << host::sharding().world << " GPUs (documents sharded by query)" << std::endl << "#" << std::endl;
 
   if (get("train-metric", "NDCG") != "NDCG" || get("test-metric", "NDCG") != "NDCG") {
     std::cerr << "!!! Only NDCG is supported by the GPU engine." << std::endl;
@@ -117,13 +184,13 @@ int main(int argc, char **argv) {
       valid = load(opt["valid"]);
     }
     std::cout << "#" << std::endl << "# training scorer: " << *train_metric << std::endl;
-    ranker->learn(train, valid, train_metric, partial, get("model-out", ""));
+    ranker->learn(train, valid, train_metric, rank == 0 ? partial : 0, get("model-out", ""));
     if (opt.count("model-out")) {
       std::cout << "# Writing model to file: " << opt["model-out"] << std::endl;
       ranker->save(opt["model-out"]);
     }
   }
-  if (opt.count("test")) {
+  if (opt.count("test") && rank == 0) {   // (the other ranks of a multi-GPU run have nothing to report)
     std::shared_ptr<metric::ir::Metric> test_metric(new metric::ir::Ndcg(geti("test-cutoff", 10)));
     std::cout << "# Reading test dataset: " << opt["test"] << std::endl;
     auto test = load(opt["test"]);
@@ -138,5 +205,5 @@ int main(int argc, char **argv) {
       std::cout << "# Scores written to file: " << opt["scores"] << std::endl;
     }
   }
-  return EXIT_SUCCESS;
+  return finish(EXIT_SUCCESS);
 }

@@ -611,6 +611,28 @@ void Mart::init(std::shared_ptr<data::VerticalDataset> training_dataset) {
   p.hist_mode = hist_mode_;
   p.device = device_;
   auto h = training_dataset->horizontal();
+  const host::Sharding &sh = host::sharding();
+  if (sh.world > 1) {
+    // this process's shard: a contiguous range of whole queries; rows are contiguous in the row-major matrix
+    if (h->num_queries() < (size_t) sh.world) {
+      std::cerr << "!!! Cannot shard " << h->num_queries() << " queries over " << sh.world << " GPUs." << std::endl;
+      exit(EXIT_FAILURE);
+    }
+    const auto shards = host::query_shards(h->offsets().data(), h->num_queries(), sh.world);
+    const size_t q0 = shards[sh.rank].first, q1 = shards[sh.rank].second;
+    const uint64_t d0 = h->offsets()[q0], d1 = h->offsets()[q1];
+    std::vector<uint64_t> off(q1 - q0 + 1);
+    for (size_t q = q0; q <= q1; ++q) off[q - q0] = h->offsets()[q] - d0;
+    unsigned char id[QR_COMM_ID_BYTES];
+    std::memset(id, 0, sizeof(id));
+    if (sh.rank == 0 && qr_comm_unique_id(id) != QR_OK) die("Impossible to create the communicator id");
+    if (!host::exchange_bytes(id, sizeof(id), sh)) die("Impossible to exchange the communicator id");
+    if (p.device < 0) p.device = sh.local_rank;
+    if (qr_ctx_create_sharded(h->data() + d0 * h->num_features(), 1, (size_t) (d1 - d0), h->num_features(),
+                              h->labels() + d0, off.data(), q1 - q0, &p, id, sh.rank, sh.world, &ctx_) != QR_OK)
+      die("Impossible to initialise the sharded GPU training context");
+    return;
+  }
   if (qr_ctx_create_rowmajor(h->data(), h->num_instances(), h->num_features(), h->labels(), h->offsets().data(),
                              h->num_queries(), &p, &ctx_) != QR_OK)
     die("Impossible to initialise the GPU training context");
@@ -1510,4 +1532,111 @@ void GenOblivious::generate_oblivious_code(const std::string model_filename, con
 }
 
 }  // namespace io
+}  // namespace quickrank
+
+// ---- multi-GPU plumbing of the host layer -----------------------------------------------------
+#include <arpa/inet.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+namespace quickrank {
+namespace host {
+
+static Sharding g_sharding;
+void set_sharding(const Sharding &s) { g_sharding = s; }
+const Sharding &sharding() { return g_sharding; }
+
+std::vector<std::pair<size_t, size_t>> query_shards(const uint64_t *offsets, size_t nq, int world) {
+  std::vector<size_t> bounds{0};
+  const uint64_t n = offsets[nq];
+  for (int r = 1; r < world; ++r) {
+    const double target = (double) (n * (uint64_t) r) / (double) world;
+    // first index whose offset is >= target
+    size_t q = (size_t) (std::lower_bound(offsets, offsets + nq + 1, target,
+                                          [](uint64_t o, double t) { return (double) o < t; }) - offsets);
+    if (q > 0 && std::fabs((double) offsets[q - 1] - target) <= std::fabs((double) offsets[std::min(q, nq)] - target)) --q;
+    q = std::max(q, bounds.back() + 1);
+    q = std::min(q, nq - (size_t) (world - r));
+    bounds.push_back(q);
+  }
+  bounds.push_back(nq);
+  std::vector<std::pair<size_t, size_t>> out;
+  for (int r = 0; r < world; ++r) out.emplace_back(bounds[r], bounds[r + 1]);
+  return out;
+}
+
+static bool send_all(int fd, const unsigned char *p, size_t n) {
+  while (n) {
+    const ssize_t k = ::send(fd, p, n, MSG_NOSIGNAL);
+    if (k <= 0) return false;
+    p += k; n -= (size_t) k;
+  }
+  return true;
+}
+static bool recv_all(int fd, unsigned char *p, size_t n) {
+  while (n) {
+    const ssize_t k = ::recv(fd, p, n, 0);
+    if (k <= 0) return false;
+    p += k; n -= (size_t) k;
+  }
+  return true;
+}
+
+bool exchange_bytes(unsigned char *id, size_t nbytes, const Sharding &s, int timeout_s) {
+  if (s.world <= 1) return true;
+  sockaddr_in a;
+  std::memset(&a, 0, sizeof(a));
+  a.sin_family = AF_INET;
+  a.sin_port = htons((uint16_t) s.port);
+  if (s.rank == 0) {
+    const int ls = ::socket(AF_INET, SOCK_STREAM, 0);
+    if (ls < 0) { perror("socket"); return false; }
+    int one = 1;
+    setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    a.sin_addr.s_addr = htonl(INADDR_ANY);
+    if (::bind(ls, (sockaddr *) &a, sizeof(a)) != 0 || ::listen(ls, s.world) != 0) {
+      std::cerr << "!!! rank 0 cannot listen on port " << s.port << ": " << strerror(errno) << std::endl;
+      ::close(ls);
+      return false;
+    }
+    timeval tv{timeout_s, 0};
+    setsockopt(ls, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    bool ok = true;
+    for (int k = 1; k < s.world && ok; ++k) {
+      const int fd = ::accept(ls, nullptr, nullptr);
+      if (fd < 0) { std::cerr << "!!! rank 0: a peer did not connect within " << timeout_s << " s" << std::endl; ok = false; break; }
+      ok = send_all(fd, id, nbytes);
+      ::close(fd);
+    }
+    ::close(ls);
+    return ok;
+  }
+  if (inet_pton(AF_INET, s.addr.c_str(), &a.sin_addr) != 1) {
+    std::cerr << "!!! bad rendezvous address " << s.addr << " (dotted IPv4 expected)" << std::endl;
+    return false;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const int fd = ::socket(AF_INET, SOCK_STREAM, 0);
+    if (fd < 0) { perror("socket"); return false; }
+    if (::connect(fd, (sockaddr *) &a, sizeof(a)) == 0) {
+      timeval tv{timeout_s, 0};
+      setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+      const bool ok = recv_all(fd, id, nbytes);
+      ::close(fd);
+      if (!ok) std::cerr << "!!! rank " << s.rank << ": the communicator id did not arrive" << std::endl;
+      return ok;
+    }
+    ::close(fd);
+    if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) {
+      std::cerr << "!!! rank " << s.rank << " cannot reach rank 0 at " << s.addr << ":" << s.port << std::endl;
+      return false;
+    }
+    std::this_thread::sleep_for(std::chrono::milliseconds(20));
+  }
+}
+
+}  // namespace host
 }  // namespace quickrank

@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing of the C++ host (host/): `quicklearn --gpus N` shards the queries with the same
+rule as quickrank_b200/sharding.py, hands the NCCL communicator id to the other processes over TCP and
+grows the same model as one GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import qr_testlib as common
+from quickrank_b200.sharding import query_shards
+from test_host_cli import QL, write_svml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SC = os.path.join(ROOT, "host", "bin", "shard_check")
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_host_query_shards_equal_the_python_rule(seed):
+    rng = np.random.default_rng(seed)
+    nq = int(rng.integers(8, 200))
+    lens = rng.integers(1, 400, size=nq)
+    if seed % 2:
+        lens[rng.integers(0, nq)] = 20000        # one huge query
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    for world in (1, 2, 3, 8):
+        out = subprocess.run([SC, "shards", str(world)] + [str(int(o)) for o in off], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = [tuple(int(v) for v in line.split()) for line in out.stdout.split("\n") if line]
+        assert got == [tuple(s) for s in query_shards(off, world)]
+
+
+def test_communicator_id_rendezvous():
+    port = 21000 + os.getpid() % 20000
+    out = subprocess.run([SC, "rendezvous", "4", str(port)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr + out.stdout
+
+
+@pytest.mark.gpu
+def test_quicklearn_on_two_gpus_grows_the_single_gpu_model(tmp_path):
+    from quickrank_b200 import api, modelxml
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    x, l, off = common.dataset(n=6000, f=12, q=60, seed=8)
+    tr = str(tmp_path / "train.txt")
+    write_svml(tr, x, l, off)
+    models, tables = [], []
+    for gpus in (1, 2):
+        model = str(tmp_path / ("model%d.xml" % gpus))
+        cmd = [QL, "--algo", "LAMBDAMART", "--train", tr, "--num-trees", "6", "--num-leaves", "8", "--model-out", model,
+               "--min-leaf-support", "20", "--gpus", str(gpus)]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr + out.stdout
+        models.append(modelxml.read_model(model))
+        tables.append([line for line in out.stdout.split("\n") if line[:8].strip().isdigit()])
+    assert "training on 2 GPUs" in out.stdout
+    # same stdout table (metrics are printed with 4 decimals) and same trees
+    assert tables[0] == tables[1] and len(tables[0]) == 6
+    (_i1, t1, w1), (_i2, t2, w2) = models
+    assert len(t1) == len(t2) == 6 and np.array_equal(w1, w2)
+    for a, b in zip(t1, t2):
+        for k in ("feature", "threshold", "left", "right"):
+            assert np.array_equal(a[k], b[k]), k
+        lv = a["feature"] < 0
+        assert np.max(np.abs(a["value"][lv] - b["value"][lv])) <= 1e-12 * np.max(np.abs(a["value"][lv]))
