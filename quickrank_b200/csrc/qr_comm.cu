@@ -1,14 +1,18 @@
-// quickrank_b200 — multi-GPU plumbing: one process per GPU, documents sharded by query, NCCL over
-// NVLink for the only exchange steps the path has:
+// quickrank_b200 — multi-GPU plumbing: one process per GPU, documents sharded by query.  The exchange
+// steps the path has:
 //   * once at start: the global list of distinct feature values (thresholds must be identical on
-//     every rank) and the per-bin document counts of the whole dataset;
-//   * per tree: the maximum |pseudo-response| (common fixed-point scale);
-//   * per growth round: the freshly built per-bin histograms (int64 sums + uint32 counts) of the
-//     round's nodes and their squares sums, so that every rank scans the same totals and makes the
-//     same split decisions without any broadcast;
-//   * per tree: per-leaf (sum lambda, sum weight); per evaluation: the sum of per-query NDCG.
-// Histogram sums are integers, so the all-reduced values — and therefore every split — do not
-// depend on the number of ranks or on NCCL's reduction order.
+//     every rank) and the per-bin document counts of the whole dataset (NCCL);
+//   * per tree: the maximum |pseudo-response| (common fixed-point scale), per-leaf (sum lambda, sum
+//     weight), the sum of per-query NDCG (NCCL);
+//   * per growth round — the only exchange on the critical path: the freshly built per-bin histograms
+//     (int64 sums + uint32 counts) of the round's nodes and their exact squares sums, so that every rank
+//     scans the same totals and makes the same split decisions without any broadcast.  This one travels
+//     through PEER MEMORY (every rank maps the other ranks' histogram pools over CUDA IPC): fused into
+//     the split-scan kernel for small rounds (finalize_kernel<false, true>, qr_tree_kernels.cuh), or by
+//     the stand-alone in-place reduce-scatter + all-gather kernel below (peer_reduce_kernel) for wide
+//     ones; grouped NCCL all-reduces remain as the fallback when the devices cannot map each other.
+// Histogram sums are integers, so the totals — and therefore every split — do not depend on the number
+// of ranks, on the exchange path or on the order of the additions.
 //
 // NCCL is resolved with dlopen at run time (libnccl.so.2; inside a PyTorch process this is the
 // copy torch already loaded), so the single-GPU path has no link-time dependency on it.
