@@ -8,7 +8,8 @@ pseudo-responses -> root histogram -> tree fit -> leaf outputs -> score update -
 synthetic config-2 workload (1M docs x 136 features x 10k queries, 64 leaves).  With N > 1 the
 SAME 1M documents are sharded by query over the ranks, one process per GPU (torchrun; strong
 scaling, as BASELINE.json's north_star asks: trees/sec on the 1M-doc input at 1/2/4/8 GPUs), and
-the per-bin histograms are all-reduced over NCCL.
+the per-bin histograms of every growth round are all-reduced over NVLink peer memory (fused into
+the split-scan kernel for small rounds; NCCL for the per-tree scalars).
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for what each field means.
 """
