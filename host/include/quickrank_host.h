@@ -173,6 +173,13 @@ class GenOblivious {
  public:
   void generate_oblivious_code(const std::string model_filename, const std::string code_filename);
 };
+// generate_vpred.cc:92-172: the model as VPRED's text input — number of trees, then per tree its depth and a
+// breadth-first list of "root" / "node" / "leaf" records (ids in visiting order, leaf outputs multiplied
+// by the model's shrinkage), closed by "end".
+class GenVpred {
+ public:
+  void generate_vpred_input(const std::string &ensemble_file, const std::string &output_file);
+};
 
 }  // namespace io
 

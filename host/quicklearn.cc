@@ -91,13 +91,14 @@ int main(int argc, char **argv) {
   auto get = [&](const char *k, const char *def) { auto it = opt.find(k); return it == opt.end() ? std::string(def) : it->second; };
   auto geti = [&](const char *k, size_t def) { auto it = opt.find(k); return it == opt.end() ? def : (size_t) strtoull(it->second.c_str(), nullptr, 10); };
 
-  // code generation (driver.cc:199-223): --model-file m.xml --code-file ranker.cc [--generator condop|oblivious]
+  // code generation (driver.cc:199-223): --model-file m.xml --code-file ranker.cc [--generator condop|oblivious|vpred]
   if (opt.count("model-file") && opt.count("code-file")) {
     const std::string gen = get("generator", "condop");
     std::cout << "# Generating code (" << gen << ") from " << opt["model-file"] << " into " << opt["code-file"] << std::endl;
     if (gen == "condop") io::GenOpCond().generate_conditional_operators_code(opt["model-file"], opt["code-file"]);
     else if (gen == "oblivious") io::GenOblivious().generate_oblivious_code(opt["model-file"], opt["code-file"]);
-    else { std::cerr << "!!! Generator " << gen << " is not supported (condop, oblivious)." << std::endl; return EXIT_FAILURE; }
+    else if (gen == "vpred") io::GenVpred().generate_vpred_input(opt["model-file"], opt["code-file"]);
+    else { std::cerr << "!!! Generator " << gen << " is not supported (condop, oblivious, vpred)." << std::endl; return EXIT_FAILURE; }
     return EXIT_SUCCESS;
   }
   const std::string algo = get("algo", "LAMBDAMART");

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
 #include <functional>
 #include <iomanip>
@@ -1421,6 +1422,71 @@ void GenOpCond::generate_conditional_operators_code(const std::string model_file
   source_code << ";" << std::endl << "}" << std::endl;
   std::ofstream output(code_filename, std::ofstream::out);
   output << source_code.str();
+}
+
+// generate_vpred.cc:43-58: depth of the deepest leaf below a <split> (a node holding <output> counts 1)
+static uint32_t vpred_depth(const XmlNode &split) {
+  uint32_t ld = 0, rd = 0;
+  for (auto &k : split.kids) {
+    if (k->name == "output") return 1;
+    if (k->name == "split") {
+      auto it = k->attr.find("pos");
+      if (it != k->attr.end() && it->second == "left") ld = 1 + vpred_depth(*k);
+      else rd = 1 + vpred_depth(*k);
+    }
+  }
+  return std::max(ld, rd);
+}
+
+// generate_vpred.cc:92-172
+void GenVpred::generate_vpred_input(const std::string &ensemble_file, const std::string &output_file) {
+  if (ensemble_file.empty()) {
+    std::cerr << "!!! Model filename is empty." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  std::unique_ptr<XmlNode> ranker = load_ranker(ensemble_file);
+  std::ofstream output(output_file, std::ofstream::out);
+  const XmlNode *info = ranker->child("info");
+  const double learning_rate = info ? strtod(info->child_text("shrinkage", "0").c_str(), nullptr) : 0.0;
+  std::vector<const XmlNode *> trees;
+  if (const XmlNode *ensemble = ranker->child("ensemble"))
+    for (auto &t : ensemble->kids)
+      if (t->name == "tree") trees.push_back(t.get());
+  output << trees.size() << std::endl;
+  struct Item { const XmlNode *node; uint32_t id, pid; bool left; std::string parent_feature; };
+  for (const XmlNode *tree : trees) {
+    const XmlNode *root = tree->child("split");
+    if (!root) { output << "end" << std::endl; continue; }
+    const uint32_t depth = vpred_depth(*root) - 1;
+    output << depth << std::endl;
+    const uint32_t tree_size = (uint32_t) std::pow(2, depth) - 1;
+    uint32_t local_id = 0;
+    std::deque<Item> queue;
+    for (queue.push_back(Item{root, local_id++, (uint32_t) -1, false, ""}); !queue.empty(); queue.pop_front()) {
+      const Item it = queue.front();
+      if (is_leaf(*it.node)) {
+        const double out = learning_rate * std::stod(it.node->child_text("output"));
+        if (it.id >= tree_size)
+          output << "leaf" << " " << it.id << " " << it.pid << " " << it.left << " " << out << std::endl;
+        else   // a leaf above the last level: listed as a node with its parent's feature (:137-141)
+          output << "node" << " " << it.id << " " << it.pid << " " << (std::stoi(it.parent_feature) - 1) << " "
+                 << it.left << " " << out << std::endl;
+      } else {
+        const std::string feature = it.node->child_text("feature"), theta = it.node->child_text("threshold");
+        if (it.id == 0)
+          output << "root" << " " << it.id << " " << (std::stoi(feature) - 1) << " " << theta << std::endl;
+        else
+          output << "node" << " " << it.id << " " << it.pid << " " << (std::stoi(feature) - 1) << " " << it.left
+                 << " " << theta << std::endl;
+        for (auto &k : it.node->kids)
+          if (k->name == "split") {
+            auto a = k->attr.find("pos");
+            queue.push_back(Item{k.get(), local_id++, it.id, a != k->attr.end() && a->second == "left", feature});
+          }
+      }
+    }
+    output << "end" << std::endl;
+  }
 }
 
 // generate_oblivious.cc:31-135: the three walks (all leaves left to right; features / thresholds down the

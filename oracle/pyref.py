@@ -222,8 +222,8 @@ class RefSession:
 
 
 def generate_code(xml_path, code_path, kind):
-    """The reference's own XML -> C generators (kind: "condop" | "oblivious")."""
-    lib().qref_generate_code(xml_path.encode(), code_path.encode(), {"condop": 0, "oblivious": 1}[kind])
+    """The reference's own XML -> C generators (kind: "condop" | "oblivious" | "vpred")."""
+    lib().qref_generate_code(xml_path.encode(), code_path.encode(), {"condop": 0, "oblivious": 1, "vpred": 2}[kind])
 
 
 def score_with_model(xml_path, x):

@@ -28,6 +28,7 @@
 #include "learning/forests/obliviouslambdamart.h"
 #include "io/generate_conditional_operators.h"
 #include "io/generate_oblivious.h"
+#include "io/generate_vpred.h"
 #include "learning/forests/dart.h"
 #include "utils/radix.h"
 #include "driver/driver.h"
@@ -415,9 +416,10 @@ void qref_recorded_get(void *h, int kind, uint64_t it, double *out) {
   memcpy(out, v.data(), v.size() * sizeof(double));
 }
 
-// ---- the reference's C code generators (src/io/generate_*.cc); kind 0: condop, 1: oblivious ----
+// ---- the reference's C code generators (src/io/generate_*.cc); kind 0: condop, 1: oblivious, 2: vpred ----
 int qref_generate_code(const char *model, const char *code, int kind) {
   if (kind == 0) quickrank::io::GenOpCond().generate_conditional_operators_code(model, code);
+  else if (kind == 2) quickrank::io::GenVpred().generate_vpred_input(model, code);
   else quickrank::io::GenOblivious().generate_oblivious_code(model, code);
   return 0;
 }

@@ -100,3 +100,69 @@ def test_oblivious_generator(tmp_path):
         ref_code = str(tmp_path / "ref_ranker.c")
         pyref.generate_code(model, ref_code, "oblivious")
         assert open(ref_code).read() == src
+
+
+def parse_vpred(text):
+    """Independent reader of the VPRED input format: [(depth, {id: record})] per tree."""
+    lines = text.split("\n")
+    n = int(lines[0])
+    trees, i = [], 1
+    for _ in range(n):
+        depth = int(lines[i]); i += 1
+        recs = {}
+        while lines[i] != "end":
+            parts = lines[i].split()
+            recs[int(parts[1])] = parts
+            i += 1
+        i += 1
+        trees.append((depth, recs))
+    return trees
+
+
+def test_vpred_generator(tmp_path):
+    """generate_vpred.cc:92-172: breadth-first records, leaf outputs multiplied by the model's shrinkage and
+    printed with the stream's default 6 significant digits; unbalanced trees list shallow leaves as 'node'."""
+    trees, weights = synth.random_ensemble(9, 10, 13, seed=6)             # unbalanced leaf-wise trees
+    rng = np.random.default_rng(3)
+    trees += [symmetric_tree(rng, d, 13) for d in (1, 2, 3)]              # complete trees
+    weights = np.concatenate([weights, np.full(3, 0.1)])
+    model, out_file = str(tmp_path / "m.xml"), str(tmp_path / "vpred.txt")
+    modelxml.write_model(model, trees, weights, shrinkage=0.05)
+    out = subprocess.run([QL, "--model-file", model, "--code-file", out_file, "--generator", "vpred"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    text = open(out_file).read()
+    parsed = parse_vpred(text)
+    assert len(parsed) == len(trees)
+    for (depth, recs), t in zip(parsed, trees):
+        # breadth-first ids over the flat pre-order tree
+        order, parent, is_left = [0], {0: 4294967295}, {0: 0}
+        for node in order:
+            if t["feature"][node] >= 0:
+                for child, lf in ((int(t["left"][node]), 1), (int(t["right"][node]), 0)):
+                    parent[child] = order.index(node)
+                    is_left[child] = lf
+                    order.append(child)
+
+        def node_depth(nd):
+            return 0 if t["feature"][nd] < 0 else 1 + max(node_depth(int(t["left"][nd])), node_depth(int(t["right"][nd])))
+        assert depth == node_depth(0)
+        assert sorted(recs) == list(range(len(order)))
+        for bfs_id, node in enumerate(order):
+            r = recs[bfs_id]
+            if t["feature"][node] >= 0:
+                if bfs_id == 0:
+                    assert r[0] == "root" and int(r[2]) == int(t["feature"][node])
+                    assert np.float32(float(r[3])) == t["threshold"][node]
+                else:
+                    assert r[0] == "node" and int(r[2]) == parent[node] and int(r[3]) == int(t["feature"][node])
+                    assert int(r[4]) == is_left[node] and np.float32(float(r[5])) == t["threshold"][node]
+            else:
+                want = "%g" % (0.05 * float("%.17g" % t["value"][node]))
+                if bfs_id >= 2 ** depth - 1:
+                    assert r[0] == "leaf" and int(r[2]) == parent[node] and int(r[3]) == is_left[node] and r[4] == want
+                else:
+                    assert r[0] == "node" and int(r[2]) == parent[node] and int(r[4]) == is_left[node] and r[5] == want
+    if pyref.available():
+        ref_file = str(tmp_path / "ref_vpred.txt")
+        pyref.generate_code(model, ref_file, "vpred")
+        assert open(ref_file).read() == text
