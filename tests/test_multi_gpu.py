@@ -34,7 +34,8 @@ def _worker(rank, world, q, out_q, algo, kw, mode):
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from quickrank_b200 import api
     from quickrank_b200.sharding import query_shards
-    x, l, off = common.dataset(n=20000, f=24, q=200, seed=21)
+    kw = dict(kw)
+    x, l, off = common.dataset(n=20000, f=24, q=200, seed=21, **kw.pop("_data", {}))
     if rank == 0:
         cid = api.comm_unique_id()
         for _ in range(world - 1):
@@ -56,15 +57,23 @@ def _worker(rank, world, q, out_q, algo, kw, mode):
     out_q.put((rank, trees, metrics, d0, d1, scores, transport))
 
 
+CASES = [("LAMBDAMART", dict(nleaves=16)), ("MART", dict(nleaves=8)), ("OBVLAMBDAMART", dict(treedepth=3)),
+         # continuous features: thousands of thresholds per feature (16-bit bins, histograms accumulated in
+         # global memory, the split scan's path for wide features) ...
+         ("LAMBDAMART", dict(nleaves=12, _data=dict(gridded=False))),
+         # ... and the reference's equal-width thresholds over the GLOBAL value range (mart.cc:159-169)
+         ("LAMBDAMART", dict(nleaves=12, nthresholds=64, _data=dict(gridded=False)))]
+
+
 @pytest.mark.parametrize("mode", list(MODES))
-@pytest.mark.parametrize("algo,kw", [("LAMBDAMART", dict(nleaves=16)), ("MART", dict(nleaves=8)),
-                                     ("OBVLAMBDAMART", dict(treedepth=3))])
+@pytest.mark.parametrize("algo,kw", CASES, ids=["lambdamart", "mart", "oblivious", "continuous", "equal-width"])
 def test_sharded_ranks_grow_the_single_gpu_trees(algo, kw, mode):
     from quickrank_b200 import api
     if api.device_count() < WORLD:
         pytest.skip("needs %d GPUs" % WORLD)
-    x, l, off = common.dataset(n=20000, f=24, q=200, seed=21)
-    with api.Trainer(x, l, off, algo=algo, **kw) as tr:
+    tkw = {k: v for k, v in kw.items() if k != "_data"}
+    x, l, off = common.dataset(n=20000, f=24, q=200, seed=21, **kw.get("_data", {}))
+    with api.Trainer(x, l, off, algo=algo, **tkw) as tr:
         want = [tr.boost_iteration() for _ in range(T)]
         want_scores = tr.get_scores()
     ctx = mp.get_context("spawn")
