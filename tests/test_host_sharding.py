@@ -63,3 +63,11 @@ def test_quicklearn_on_two_gpus_grows_the_single_gpu_model(tmp_path):
             assert np.array_equal(a[k], b[k]), k
         lv = a["feature"] < 0
         assert np.max(np.abs(a["value"][lv] - b["value"][lv])) <= 1e-12 * np.max(np.abs(a["value"][lv]))
+
+
+def test_dart_on_several_gpus_is_refused_up_front(tmp_path):
+    """DART's passes over the documents are not sharded in this build: the CLI says so before it forks or
+    touches a device (the reference's error convention: message on stderr, EXIT_FAILURE)."""
+    out = subprocess.run([QL, "--algo", "DART", "--train", str(tmp_path / "missing.txt"), "--gpus", "2"],
+                         capture_output=True, text=True, timeout=60)
+    assert out.returncode != 0 and "DART trains on one GPU" in out.stderr
