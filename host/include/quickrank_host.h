@@ -70,6 +70,9 @@ class Dataset {
   const std::vector<uint64_t> &offsets() const { return offsets_; }
   std::unique_ptr<QueryResults> getQueryResults(size_t i) const;
   void addInstance(QueryID q_id, Label i_label, const std::vector<Feature> &i_features);
+  // bulk counterpart of addInstance for readers that already know the layout (binary cache): labels of all
+  // max_instances rows and the query offsets; the feature matrix is then filled through at()
+  void set_structure(const Label *labels, const std::vector<uint64_t> &offsets);
   size_t num_features() const { return num_features_; }
   size_t num_queries() const { return num_queries_; }
   size_t num_instances() const { return num_instances_; }
@@ -154,7 +157,9 @@ namespace io {
 
 class Svml {
  public:
-  // SVMLight / LETOR text: "<label> qid:<id> <fid>:<val> ... [# comment]" (svml.cc:38-161)
+  // SVMLight / LETOR text: "<label> qid:<id> <fid>:<val> ... [# comment]" (svml.cc:38-161).
+  // QR_SVML_CACHE=1: the parsed dataset is also written next to the text as <filename>.qrb and read back
+  // from there (one sequential read instead of a parse) as long as the text's size and mtime are unchanged.
   std::unique_ptr<data::Dataset> read_horizontal(const std::string &filename);
   void write(std::shared_ptr<data::Dataset> dataset, const std::string &filename);
 };

@@ -16,6 +16,9 @@
 #include <sstream>
 #include <thread>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 namespace quickrank {
 
 // ------------------------------------------------------------------------------------------------
@@ -68,6 +71,17 @@ void Dataset::addInstance(QueryID q_id, Label i_label, const std::vector<Feature
   }
   num_instances_++;
   offsets_.back() = num_instances_;
+}
+
+void Dataset::set_structure(const Label *labels, const std::vector<uint64_t> &offsets) {
+  if (offsets.empty() || offsets.front() != 0 || offsets.back() != max_instances_) {
+    std::cerr << "!!! Impossible to set the dataset structure." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  std::copy(labels, labels + max_instances_, labels_);
+  offsets_ = offsets;
+  num_instances_ = max_instances_;
+  num_queries_ = offsets.size() - 1;
 }
 
 std::unique_ptr<QueryResults> Dataset::getQueryResults(size_t i) const {
@@ -208,7 +222,78 @@ void parse_svml_range(char *p, char *end, SvmlChunk &out) {
 }
 }  // namespace
 
+// Binary cache of a parsed SVMLight file (QR_SVML_CACHE=1): header, labels, query offsets, row-major features.
+namespace {
+struct QrbHeader {
+  char magic[8];            // "QRB1\0\0\0\0"
+  uint64_t src_size;        // size and modification time of the text the cache was made from
+  int64_t src_mtime_s, src_mtime_ns;
+  uint64_t nrows, nfeatures, nqueries;
+};
+
+bool svml_cache_enabled() {
+  const char *e = getenv("QR_SVML_CACHE");
+  return e != nullptr && atoi(e) != 0;
+}
+
+bool stat_source(const std::string &filename, QrbHeader *h) {
+  struct stat st;
+  if (stat(filename.c_str(), &st) != 0) return false;
+  h->src_size = (uint64_t) st.st_size;
+  h->src_mtime_s = (int64_t) st.st_mtim.tv_sec;
+  h->src_mtime_ns = (int64_t) st.st_mtim.tv_nsec;
+  return true;
+}
+
+std::unique_ptr<data::Dataset> load_svml_cache(const std::string &filename) {
+  QrbHeader want, got;
+  std::memset(&want, 0, sizeof(want));
+  if (!stat_source(filename, &want)) return nullptr;
+  FILE *f = fopen((filename + ".qrb").c_str(), "rb");
+  if (!f) return nullptr;
+  std::unique_ptr<data::Dataset> ds;
+  if (fread(&got, sizeof(got), 1, f) == 1 && std::memcmp(got.magic, "QRB1\0\0\0", 8) == 0 &&
+      got.src_size == want.src_size && got.src_mtime_s == want.src_mtime_s && got.src_mtime_ns == want.src_mtime_ns &&
+      got.nqueries <= got.nrows) {
+    std::vector<Label> labels(got.nrows);
+    std::vector<uint64_t> offsets(got.nqueries + 1);
+    ds.reset(new data::Dataset(got.nrows, got.nfeatures));
+    const size_t cells = (size_t) got.nrows * got.nfeatures;
+    const bool ok = fread(labels.data(), sizeof(Label), labels.size(), f) == labels.size() &&
+                    fread(offsets.data(), sizeof(uint64_t), offsets.size(), f) == offsets.size() &&
+                    offsets.front() == 0 && offsets.back() == got.nrows &&
+                    std::is_sorted(offsets.begin(), offsets.end()) &&
+                    (cells == 0 || fread(ds->at(0, 0), sizeof(Feature), cells, f) == cells);
+    if (ok) ds->set_structure(labels.data(), offsets);
+    else ds.reset();
+  }
+  fclose(f);
+  return ds;
+}
+
+void write_svml_cache(const std::string &filename, const data::Dataset &ds) {
+  QrbHeader h;
+  std::memset(&h, 0, sizeof(h));
+  std::memcpy(h.magic, "QRB1", 4);
+  if (!stat_source(filename, &h)) return;
+  h.nrows = ds.num_instances(); h.nfeatures = ds.num_features(); h.nqueries = ds.num_queries();
+  const std::string tmp = filename + ".qrb.tmp" + std::to_string((long) getpid());
+  FILE *f = fopen(tmp.c_str(), "wb");
+  if (!f) return;   // read-only directory: no cache, no error
+  const size_t cells = (size_t) h.nrows * h.nfeatures;
+  const bool ok = fwrite(&h, sizeof(h), 1, f) == 1 &&
+                  fwrite(ds.labels(), sizeof(Label), h.nrows, f) == h.nrows &&
+                  fwrite(ds.offsets().data(), sizeof(uint64_t), ds.offsets().size(), f) == ds.offsets().size() &&
+                  (cells == 0 || fwrite(ds.data(), sizeof(Feature), cells, f) == cells);
+  if (fclose(f) != 0 || !ok || rename(tmp.c_str(), (filename + ".qrb").c_str()) != 0) remove(tmp.c_str());
+}
+}  // namespace
+
 std::unique_ptr<data::Dataset> Svml::read_horizontal(const std::string &filename) {
+  if (svml_cache_enabled()) {
+    std::unique_ptr<data::Dataset> cached = load_svml_cache(filename);
+    if (cached) return cached;
+  }
   FILE *f = fopen(filename.c_str(), "rb");
   if (!f) {
     std::cerr << "!!! Error while opening file " << filename << "." << std::endl;
@@ -273,6 +358,7 @@ std::unique_ptr<data::Dataset> Svml::read_horizontal(const std::string &filename
     fill(0);
     for (auto &th : pool) th.join();
   }
+  if (svml_cache_enabled()) write_svml_cache(filename, *ds);
   return ds;
 }
 

@@ -65,3 +65,34 @@ def test_malformed_lines_exit_like_the_reference(tmp_path, line, code):
     open(path, "w").write("2 qid:1 1:0.1 2:0.2\n" + line)
     out = subprocess.run([CHECK, path], capture_output=True, text=True)
     assert out.returncode == code
+
+
+def test_binary_cache_round_trip_and_invalidation(tmp_path):
+    """QR_SVML_CACHE=1: <file>.qrb is written after the parse and read instead of the text while the text's size and
+    mtime are unchanged; a changed text is parsed again (and the cache rewritten)."""
+    path = str(tmp_path / "data.txt")
+    rows = ["%d qid:%d 1:%.3f 3:%.3f 7:%.3f" % (i % 5, i // 6 + 1, i * 0.001, i * 0.5, 1.0 / (i + 1)) for i in range(500)]
+    open(path, "w").write("\n".join(rows) + "\n")
+    plain = run(path, 3)
+    assert not os.path.exists(path + ".qrb")
+    env = dict(os.environ, QR_SVML_CACHE="1")
+    first = subprocess.run([CHECK, path], capture_output=True, text=True, env=env)
+    assert first.returncode == 0 and first.stdout.split() == plain and os.path.exists(path + ".qrb")
+    # the second run must come from the cache: corrupt the text IN PLACE (same size, same mtime) and see it ignored
+    st = os.stat(path)
+    with open(path, "r+b") as fh:
+        fh.write(b"x" * 64)
+    os.utime(path, ns=(st.st_atime_ns, st.st_mtime_ns))
+    second = subprocess.run([CHECK, path], capture_output=True, text=True, env=env)
+    assert second.returncode == 0 and second.stdout.split() == plain
+    assert subprocess.run([CHECK, path], capture_output=True, text=True).returncode == 2   # without the cache: malformed
+    # a new text (different size) invalidates the cache
+    open(path, "w").write("\n".join(rows[:300]) + "\n")
+    third = subprocess.run([CHECK, path], capture_output=True, text=True, env=env)
+    assert third.returncode == 0 and third.stdout.split()[0] == "300"
+    # a truncated cache is ignored, not trusted
+    blob = open(path + ".qrb", "rb").read()
+    open(path + ".qrb", "wb").write(blob[:len(blob) // 2])
+    os.utime(path + ".qrb")
+    fourth = subprocess.run([CHECK, path], capture_output=True, text=True, env=env)
+    assert fourth.returncode == 0 and fourth.stdout.split() == third.stdout.split()
