@@ -21,21 +21,26 @@
 
 using namespace quickrank;
 
-// Multi-GPU training: `--gpus N` forks N-1 more processes (one per GPU, before any CUDA call); under an
-// external launcher that sets RANK / WORLD_SIZE / LOCAL_RANK (torchrun, mpirun wrappers) the processes are
-// taken as they come.  Rank 0 serves the NCCL communicator id on MASTER_ADDR : QR_COMM_PORT.  Every rank
+// Multi-GPU training: `--gpus N` forks N-1 more processes (one per GPU, before any CUDA call); when an
+// external launcher has set RANK / WORLD_SIZE (= N) / LOCAL_RANK (torchrun, mpirun wrappers) its processes
+// are taken as they come instead.  Rank 0 serves the NCCL communicator id on MASTER_ADDR : QR_COMM_PORT.  Every rank
 // runs the same training loop; only rank 0 prints and writes files.
 static std::vector<pid_t> g_children;
 static int setup_sharding(int gpus) {
   host::Sharding sh;
   const char *er = getenv("RANK"), *ew = getenv("WORLD_SIZE");
+  if (gpus <= 1) return 0;   // sharding is opt-in: an inherited RANK / WORLD_SIZE alone changes nothing
   if (er && ew && atoi(ew) > 1) {
+    if (atoi(ew) != gpus) {
+      std::cerr << "!!! --gpus " << gpus << " but the launcher's WORLD_SIZE is " << atoi(ew) << "." << std::endl;
+      exit(EXIT_FAILURE);
+    }
     sh.rank = atoi(er);
     sh.world = atoi(ew);
     sh.local_rank = getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : sh.rank;
     if (getenv("MASTER_ADDR")) sh.addr = getenv("MASTER_ADDR");
     sh.port = getenv("QR_COMM_PORT") ? atoi(getenv("QR_COMM_PORT")) : (getenv("MASTER_PORT") ? atoi(getenv("MASTER_PORT")) + 17 : 29517);
-  } else if (gpus > 1) {
+  } else {
     sh.world = gpus;
     sh.port = getenv("QR_COMM_PORT") ? atoi(getenv("QR_COMM_PORT")) : 20000 + (int) (getpid() % 20000);
     std::cout.flush();
@@ -46,8 +51,6 @@ static int setup_sharding(int gpus) {
       g_children.push_back(pid);
     }
     sh.local_rank = sh.rank;
-  } else {
-    return 0;
   }
   if (sh.rank < 0 || sh.rank >= sh.world) { std::cerr << "!!! Bad RANK / WORLD_SIZE" << std::endl; exit(EXIT_FAILURE); }
   host::set_sharding(sh);
@@ -73,8 +76,8 @@ static void usage() {
                "  --train-metric NDCG  --train-cutoff K (10)  --test-metric NDCG  --test-cutoff K (10)\n"
                "  --partial N (100)  --scores <file>\n"
                "  --hist-mode <fast|reference> (fast)  --device N\n"
-               "  --gpus N   train on N GPUs (documents sharded by query, one process per GPU; or launch the\n"
-               "             processes yourself with RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR set)\n";
+               "  --gpus N   train on N GPUs (documents sharded by query, one process per GPU: quicklearn forks them,\n"
+               "             or takes the N processes of a launcher that sets RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR)\n";
 }
 
 int main(int argc, char **argv) {
@@ -105,7 +108,7 @@ int main(int argc, char **argv) {
   int rank = 0;
   if (opt.count("train")) {
     const int gpus = (int) geti("gpus", 1);
-    if ((gpus > 1 || (getenv("WORLD_SIZE") && atoi(getenv("WORLD_SIZE")) > 1)) && algo == "DART") {
+    if (gpus > 1 && algo == "DART") {
       std::cerr << "!!! DART trains on one GPU in this build." << std::endl;
       return EXIT_FAILURE;
     }

@@ -1690,6 +1690,7 @@ void GenOblivious::generate_oblivious_code(const std::string model_filename, con
 #include <arpa/inet.h>
 #include <netinet/in.h>
 #include <netinet/tcp.h>
+#include <netdb.h>
 #include <sys/socket.h>
 #include <unistd.h>
 
@@ -1765,9 +1766,17 @@ bool exchange_bytes(unsigned char *id, size_t nbytes, const Sharding &s, int tim
     ::close(ls);
     return ok;
   }
-  if (inet_pton(AF_INET, s.addr.c_str(), &a.sin_addr) != 1) {
-    std::cerr << "!!! bad rendezvous address " << s.addr << " (dotted IPv4 expected)" << std::endl;
-    return false;
+  if (inet_pton(AF_INET, s.addr.c_str(), &a.sin_addr) != 1) {   // not dotted IPv4: a host name
+    addrinfo hints, *res = nullptr;
+    std::memset(&hints, 0, sizeof(hints));
+    hints.ai_family = AF_INET;
+    hints.ai_socktype = SOCK_STREAM;
+    if (getaddrinfo(s.addr.c_str(), nullptr, &hints, &res) != 0 || res == nullptr) {
+      std::cerr << "!!! cannot resolve the rendezvous address " << s.addr << std::endl;
+      return false;
+    }
+    a.sin_addr = ((sockaddr_in *) res->ai_addr)->sin_addr;
+    freeaddrinfo(res);
   }
   const auto t0 = std::chrono::steady_clock::now();
   for (;;) {

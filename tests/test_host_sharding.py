@@ -30,9 +30,10 @@ def test_host_query_shards_equal_the_python_rule(seed):
         assert got == [tuple(s) for s in query_shards(off, world)]
 
 
-def test_communicator_id_rendezvous():
-    port = 21000 + os.getpid() % 20000
-    out = subprocess.run([SC, "rendezvous", "4", str(port)], capture_output=True, text=True, timeout=120)
+@pytest.mark.parametrize("addr", ["127.0.0.1", "localhost"])
+def test_communicator_id_rendezvous(addr):
+    port = 21000 + (os.getpid() + len(addr)) % 20000
+    out = subprocess.run([SC, "rendezvous", "4", str(port), addr], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr + out.stdout
 
 
@@ -71,3 +72,16 @@ def test_dart_on_several_gpus_is_refused_up_front(tmp_path):
     out = subprocess.run([QL, "--algo", "DART", "--train", str(tmp_path / "missing.txt"), "--gpus", "2"],
                          capture_output=True, text=True, timeout=60)
     assert out.returncode != 0 and "DART trains on one GPU" in out.stderr
+
+
+def test_inherited_launcher_variables_alone_do_not_shard(tmp_path):
+    """RANK / WORLD_SIZE in the environment (a process started under some launcher) must not switch sharding on:
+    it is opt-in through --gpus.  Without a GPU the run still ends at the reference-style error, not in a rendezvous."""
+    tr = str(tmp_path / "t.txt")
+    open(tr, "w").write("1 qid:1 1:0.5\n0 qid:1 1:0.25\n")
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT="29999")
+    out = subprocess.run([QL, "--train", tr, "--num-trees", "1"], capture_output=True, text=True, timeout=60, env=env)
+    assert "training on" not in out.stdout and "cannot reach rank 0" not in out.stderr
+    mismatch = subprocess.run([QL, "--train", tr, "--num-trees", "1", "--gpus", "4"], capture_output=True, text=True,
+                              timeout=60, env=env)
+    assert mismatch.returncode != 0 and "WORLD_SIZE is 2" in mismatch.stderr
