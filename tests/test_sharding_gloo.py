@@ -97,3 +97,41 @@ def test_sharded_histograms_allreduce_to_the_global_one():
     port = _free_port()
     tmp.spawn(_rank_main, args=(world, port, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world))
+
+
+class _FakeTrainer:
+    """Stands in for api.Trainer (which needs a GPU): records what sharded_trainer would create."""
+
+    def __init__(self, x, labels, qoff, device=-1, comm=None, **kw):
+        self.x, self.labels, self.qoff, self.device, self.comm, self.kw = x, labels, qoff, device, comm, kw
+
+
+def _sharded_trainer_main(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quickrank_b200.distributed import sharded_trainer
+    x, l, off = common.dataset(n=3000, f=6, q=30, seed=9)
+    tr = sharded_trainer(x, l, off, dist=dist, trainer_cls=_FakeTrainer, algo="LAMBDAMART", nleaves=8)
+    cid, r, w = tr.comm
+    d0, d1 = tr.doc_range
+    ret[rank] = dict(cid=cid, rank=r, world=w, d0=d0, d1=d1, device=tr.device, nq=len(tr.qoff) - 1,
+                     rows_ok=bool(np.array_equal(tr.x, x[d0:d1]) and np.array_equal(tr.labels, l[d0:d1])),
+                     off_ok=bool(tr.qoff[0] == 0 and tr.qoff[-1] == d1 - d0), kw=tr.kw)
+    dist.destroy_process_group()
+
+
+def test_sharded_trainer_helper_hands_every_rank_its_queries_and_the_same_id():
+    """quickrank_b200.distributed.sharded_trainer over gloo (world 2): one communicator id for all ranks
+    (created by rank 0 through the C ABI), disjoint contiguous document ranges that cover the dataset, local
+    query offsets rebased to 0."""
+    world = 2
+    mgr = tmp.Manager()
+    ret = mgr.dict()
+    tmp.spawn(_sharded_trainer_main, args=(world, _free_port(), ret), nprocs=world, join=True)
+    a, b = ret[0], ret[1]
+    assert a["cid"] == b["cid"] and len(a["cid"]) == 128 and any(a["cid"])
+    assert (a["rank"], a["world"], b["rank"], b["world"]) == (0, 2, 1, 2)
+    assert a["d0"] == 0 and a["d1"] == b["d0"] and b["d1"] == 3000
+    assert a["nq"] + b["nq"] == 30 and a["rows_ok"] and b["rows_ok"] and a["off_ok"] and b["off_ok"]
+    assert a["kw"] == dict(algo="LAMBDAMART", nleaves=8)
