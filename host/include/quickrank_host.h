@@ -96,7 +96,9 @@ class VerticalDataset {
   size_t num_instances() const { return src_->num_instances(); }
   size_t offset(size_t i) const { return src_->offset(i); }
   Label getLabel(size_t document_id) const { return src_->getLabel(document_id); }
-  std::unique_ptr<QueryResults> getQueryResults(size_t i) const { return src_->getQueryResults(i); }
+  // vertical_dataset.cc:80-88: the query's labels and a pointer into the COLUMN-major matrix at its first
+  // document (feature f of its document d is features()[f * num_instances() + d])
+  std::unique_ptr<QueryResults> getQueryResults(size_t i);
   Feature *at(size_t document_id, size_t feature_id);   // data_[feature_id * N + document_id]
   std::shared_ptr<Dataset> horizontal() const { return src_; }
 

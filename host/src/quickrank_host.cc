@@ -102,6 +102,11 @@ Feature *VerticalDataset::at(size_t document_id, size_t feature_id) {
   return col_.data() + feature_id * src_->num_instances() + document_id;
 }
 
+std::unique_ptr<QueryResults> VerticalDataset::getQueryResults(size_t i) {
+  const size_t d0 = src_->offset(i), n = src_->offset(i + 1) - d0;
+  return std::unique_ptr<QueryResults>(new QueryResults(n, const_cast<Label *>(src_->labels()) + d0, at(d0, 0)));
+}
+
 }  // namespace data
 
 // ------------------------------------------------------------------------------------------------
