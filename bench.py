@@ -119,6 +119,20 @@ def load_traffic():
     return None, "no ncu capture committed"
 
 
+def shared_atomics_view(hk_docs, root_docs, hk_ms, n_features, ceiling=3.1e12):
+    """The histogram launches against the limit that actually binds them: shared-memory
+    atomic lane-operations per second.  A (document, feature) update costs two limb atomics, plus a count atomic
+    on child launches (the root refresh copies its counts); the ceiling is what scripts/hist_mb2.cu sustains on
+    B200 (16 lanes per clock per SM)."""
+    child_docs = max(hk_docs - root_docs, 0.0)
+    atomics = (root_docs * 2.0 + child_docs * 3.0) * n_features
+    rate = atomics / max(hk_ms * 1e-3, 1e-12)
+    return {"achieved": round(rate / 1e12, 3), "ceiling": round(ceiling / 1e12, 2), "unit": "T lane-atomics/s",
+            "frac": round(rate / ceiling, 3),
+            "ceiling_source": "scripts/hist_mb2.cu microbenchmark on B200 (DESIGN.md section 4); small launches "
+                              "sit below it because of their fixed costs (shared-memory clear, flush)"}
+
+
 def hist_bytes_per_tree(n, f, rho, bin_bytes=1):
     """Algorithmic bytes of the histogram kernels for one tree:
     root: every bin once + lambda once; children: bins + doc id + gathered lambda."""
@@ -273,6 +287,11 @@ def run_ours(args):
                                                    w["leaves"], 0) / (ms_per_step * 1e-3) / 1e9, 1),
                 "note": "bound in practice by the shared-memory atomic issue rate (16 lanes/clk/SM), "
                         "see DESIGN.md section 4"}
+
+    try:   # an explanatory extra, never allowed to cost the line
+        roofline["shared_atomics"] = shared_atomics_view(hk_docs, root_docs, hk_ms, f)
+    except Exception as e:   # noqa: BLE001
+        roofline["shared_atomics"] = {"error": str(e)}
 
     tr.close()
     scoring = run_scoring(args, x, rank, world, local_rank, dist, barrier)
