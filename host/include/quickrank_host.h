@@ -268,6 +268,8 @@ class Ensemble {
   Ensemble() {}
   ~Ensemble();
   Ensemble(const Ensemble &) = delete;
+  // ensemble.cc:53-62: move assignment, used by import_model_state to take over a loaded model's trees
+  Ensemble &operator=(Ensemble &&other);
   void set_capacity(size_t n) { trees_.reserve(n); }
   void push(RTNode *root, double weight, float maxlabel);
   void pop();
@@ -307,6 +309,9 @@ class LTR_Algorithm {
   // <name>.T<iter>.xml for partial saves (ltr_algorithm.cc:54-65)
   virtual void save(std::string model_filename, int suffix = -1) const;
   static std::shared_ptr<LTR_Algorithm> load_model_from_file(std::string model_filename);
+  // --restart-train (ltr_algorithm_factory.cc:249-257): take over the trees of a loaded model when its
+  // parameters are compatible with this object's; false = not compatible
+  virtual bool import_model_state(LTR_Algorithm &other) { (void) other; return false; }
   virtual void write_xml_model(std::ostream &os) const = 0;
   friend std::ostream &operator<<(std::ostream &os, const LTR_Algorithm &a) { return a.put(os); }
 
@@ -336,6 +341,7 @@ class Mart : public LTR_Algorithm {
   void score_dataset(std::shared_ptr<data::Dataset> dataset, Score *scores) const override;
   std::string name() const override { return NAME_; }
   void write_xml_model(std::ostream &os) const override;
+  bool import_model_state(LTR_Algorithm &other) override;   // mart.cc:493-518
   std::vector<double> get_weights() const { return ensemble_model_.get_weights(); }
   const Ensemble &ensemble() const { return ensemble_model_; }
   // histogram accumulation mode of the CUDA library (QR_HIST_FAST / QR_HIST_REFERENCE)
@@ -377,6 +383,7 @@ class Mart : public LTR_Algorithm {
   size_t metric_cutoff_ = 10;
   qr_ctx *ctx_ = nullptr;         // training set on the GPU (Mart::init .. Mart::clear)
   qr_ctx *valid_ctx_ = nullptr;   // validation set binned with the training thresholds
+  size_t shard_d0_ = 0;           // first document of this rank's shard (sharded training), set by init()
 };
 
 class LambdaMart : public Mart {
@@ -396,6 +403,7 @@ class ObliviousMart : public Mart {
       : Mart(ntrees, shrinkage, nthresholds, (size_t) 1 << treedepth, minleafsupport, subsample, max_features, esr,
              collapse_leaves_factor), treedepth_(treedepth) {}
   explicit ObliviousMart(const XmlModel &model);
+  bool import_model_state(LTR_Algorithm &other) override;   // obliviousmart.cc:88-106
   std::string name() const override { return NAME_; }
   static const std::string NAME_;
 
@@ -439,6 +447,7 @@ class Dart : public LambdaMart {
        NormalizationType normalize_type, AdaptiveType adaptive_rate, double rate_drop, double skip_drop, bool keep_drop,
        bool best_on_train, double random_keep, double drop_on_best);
   explicit Dart(const XmlModel &model);
+  bool import_model_state(LTR_Algorithm &other) override;   // dart.cc:604-632
   void learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_ptr<data::Dataset> validation_dataset,
              std::shared_ptr<metric::ir::Metric> training_metric, size_t partial_save,
              const std::string output_basename) override;

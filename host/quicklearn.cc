@@ -11,6 +11,7 @@
 #include <map>
 #include <string>
 
+#include <signal.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -26,6 +27,14 @@ using namespace quickrank;
 // are taken as they come instead.  Rank 0 serves the NCCL communicator id on MASTER_ADDR : QR_COMM_PORT.  Every rank
 // runs the same training loop; only rank 0 prints and writes files.
 static std::vector<pid_t> g_children;
+// rank 0 is going away without having waited for the others (an error path): stop them
+static void reap_children() {
+  for (pid_t k : g_children) {
+    int st = 0;
+    if (waitpid(k, &st, WNOHANG) == 0) { kill(k, SIGTERM); waitpid(k, &st, 0); }
+  }
+  g_children.clear();
+}
 static int setup_sharding(int gpus) {
   host::Sharding sh;
   const char *er = getenv("RANK"), *ew = getenv("WORLD_SIZE");
@@ -50,6 +59,7 @@ static int setup_sharding(int gpus) {
       if (pid == 0) { sh.rank = r; g_children.clear(); break; }
       g_children.push_back(pid);
     }
+    if (sh.rank == 0) atexit(reap_children);   // exit() paths (die(), early returns) must not leave the peers waiting
     sh.local_rank = sh.rank;
   }
   if (sh.rank < 0 || sh.rank >= sh.world) { std::cerr << "!!! Bad RANK / WORLD_SIZE" << std::endl; exit(EXIT_FAILURE); }
@@ -58,11 +68,13 @@ static int setup_sharding(int gpus) {
 }
 // rank 0 of a self-launched run: the exit status covers the other ranks
 static int finish(int rc) {
+  if (rc != EXIT_SUCCESS) { reap_children(); return rc; }
   for (pid_t k : g_children) {
     int st = 0;
     waitpid(k, &st, 0);
     if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) { std::cerr << "!!! A training process failed." << std::endl; rc = EXIT_FAILURE; }
   }
+  g_children.clear();
   return rc;
 }
 
@@ -106,7 +118,7 @@ int main(int argc, char **argv) {
   }
   const std::string algo = get("algo", "LAMBDAMART");
   int rank = 0;
-  if (opt.count("train")) {
+  if (opt.count("train") && (!opt.count("model-in") || opt.count("restart-train"))) {
     const int gpus = (int) geti("gpus", 1);
     if (gpus > 1 && algo == "DART") {
       std::cerr << "!!! DART trains on one GPU in this build." << std::endl;
@@ -125,12 +137,19 @@ int main(int argc, char **argv) {
   const double shrinkage = strtod(get("shrinkage", "0.1").c_str(), nullptr);
   const size_t partial = geti("partial", 100);
 
-  std::shared_ptr<learning::LTR_Algorithm> ranker;
+  // ltr_algorithm_factory.cc:45-259: --model-in alone = the loaded model, no training; with --restart-train the
+  // algorithm is built from the command line and takes over the loaded trees if the two are compatible
+  std::shared_ptr<learning::LTR_Algorithm> ranker, loaded;
   learning::forests::Mart *mart = nullptr;
-  if (opt.count("model-in") && !opt.count("restart-train")) {
+  const bool from_scratch = !opt.count("model-in") || opt.count("restart-train");
+  if (opt.count("model-in")) {
     std::cout << "# Loading model from file " << opt["model-in"] << std::endl;
-    ranker = learning::LTR_Algorithm::load_model_from_file(opt["model-in"]);
-    if (!ranker) { std::cerr << "!!! Model type not supported for loading" << std::endl; return EXIT_FAILURE; }
+    loaded = learning::LTR_Algorithm::load_model_from_file(opt["model-in"]);
+    if (!loaded) std::cerr << " !! Unable to load model from file." << std::endl;
+  }
+  if (!from_scratch) {
+    if (!loaded) return finish(EXIT_FAILURE);
+    ranker = loaded;
   } else if (algo == "MART") {
     ranker.reset(mart = new learning::forests::Mart(ntrees, shrinkage, nthr, nleaves, minls, 1.0f, 1.0f, esr, 0.0f));
   } else if (algo == "LAMBDAMART") {
@@ -151,7 +170,11 @@ int main(int argc, char **argv) {
                                  opt.count("drop-on-best") ? 1.0 : 0.0));
   } else {
     std::cerr << "!!! Algorithm " << algo << " is not accelerated by this build (see DESIGN.md, out of scope)." << std::endl;
-    return EXIT_FAILURE;
+    return finish(EXIT_FAILURE);
+  }
+  if (loaded && from_scratch && !ranker->import_model_state(*loaded)) {
+    std::cerr << " !! Models not compatible for restart!" << std::endl;
+    return finish(EXIT_FAILURE);
   }
   if (!mart) mart = dynamic_cast<learning::forests::Mart *>(ranker.get());
   if (mart) {
@@ -164,7 +187,7 @@ int main(int argc, char **argv) {
 
   if (get("train-metric", "NDCG") != "NDCG" || get("test-metric", "NDCG") != "NDCG") {
     std::cerr << "!!! Only NDCG is supported by the GPU engine." << std::endl;
-    return EXIT_FAILURE;
+    return finish(EXIT_FAILURE);
   }
   auto load = [](const std::string &file) {
     io::Svml reader;
@@ -178,7 +201,7 @@ int main(int argc, char **argv) {
     return ds;
   };
 
-  if (opt.count("train")) {
+  if (opt.count("train") && from_scratch) {   // driver.cc:136-138: a model loaded without --restart-train is not trained
     std::shared_ptr<metric::ir::Metric> train_metric(new metric::ir::Ndcg(geti("train-cutoff", 10)));
     std::cout << "# Reading training dataset: " << opt["train"] << std::endl;
     auto train = load(opt["train"]);

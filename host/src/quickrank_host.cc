@@ -426,6 +426,15 @@ Ensemble::~Ensemble() {
   for (auto &t : trees_) delete t.root;
 }
 
+Ensemble &Ensemble::operator=(Ensemble &&other) {
+  if (this != &other) {
+    for (auto &t : trees_) delete t.root;
+    trees_ = std::move(other.trees_);
+    other.trees_.clear();
+  }
+  return *this;
+}
+
 void Ensemble::push(RTNode *root, double weight, float maxlabel) { trees_.push_back({root, weight, maxlabel}); }
 
 void Ensemble::pop() {
@@ -691,6 +700,7 @@ std::ostream &ObliviousMart::put(std::ostream &os) const {
 // ---- the hooks: every body is a call into the CUDA library ------------------------------------
 
 void Mart::init(std::shared_ptr<data::VerticalDataset> training_dataset) {
+  shard_d0_ = 0;
   qr_params p;
   std::memset(&p, 0, sizeof(p));
   p.algo = algo_id();
@@ -713,6 +723,7 @@ void Mart::init(std::shared_ptr<data::VerticalDataset> training_dataset) {
     const auto shards = host::query_shards(h->offsets().data(), h->num_queries(), sh.world);
     const size_t q0 = shards[sh.rank].first, q1 = shards[sh.rank].second;
     const uint64_t d0 = h->offsets()[q0], d1 = h->offsets()[q1];
+    shard_d0_ = (size_t) d0;
     std::vector<uint64_t> off(q1 - q0 + 1);
     for (size_t q = q0; q <= q1; ++q) off[q - q0] = h->offsets()[q] - d0;
     unsigned char id[QR_COMM_ID_BYTES];
@@ -792,6 +803,22 @@ MetricScore Mart::evaluate_training(metric::ir::Metric *) {
   return m;
 }
 
+bool Mart::import_model_state(LTR_Algorithm &other) {
+  Mart *o = dynamic_cast<Mart *>(&other);
+  if (!o) return false;
+  if (std::abs(shrinkage_ - o->shrinkage_) > 0.000001 || nthresholds_ != o->nthresholds_ || nleaves_ != o->nleaves_ ||
+      minleafsupport_ != o->minleafsupport_ || valid_iterations_ != o->valid_iterations_)
+    return false;
+  ensemble_model_ = std::move(o->ensemble_model_);
+  return true;
+}
+
+bool ObliviousMart::import_model_state(LTR_Algorithm &other) {
+  ObliviousMart *o = dynamic_cast<ObliviousMart *>(&other);
+  if (!o || treedepth_ != o->treedepth_) return false;
+  return Mart::import_model_state(other);
+}
+
 // Mart::learn (mart.cc:208-416): same loop, same stdout table
 void Mart::learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_ptr<data::Dataset> validation_dataset,
                  std::shared_ptr<metric::ir::Metric> scorer, size_t partial_save, const std::string output_basename) {
@@ -824,7 +851,8 @@ void Mart::learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_pt
     best_model_ = ensemble_model_.get_size() - 1;
     std::vector<Score> s(training_dataset->num_instances());
     score_dataset(training_dataset, s.data());
-    if (qr_set_scores(ctx_, s.data()) != QR_OK) die("restart");
+    // (sharded training: the context holds this rank's documents only)
+    if (qr_set_scores(ctx_, s.data() + shard_d0_) != QR_OK) die("restart");
     best_metric_on_training_ = evaluate_training(scorer.get());
     if (validation_dataset) {
       std::vector<Score> v(validation_dataset->num_instances());
@@ -1013,6 +1041,18 @@ Dart::Dart(const XmlModel &model) : LambdaMart(model) {
     random_keep = strtod(info->child_text("random_keep", "0").c_str(), nullptr);
     drop_on_best = info->child_text("drop_on_best", "false") == "true";
   }
+}
+
+bool Dart::import_model_state(LTR_Algorithm &other) {
+  Dart *o = dynamic_cast<Dart *>(&other);
+  if (!o) return false;
+  if (std::abs(shrinkage_ - o->shrinkage_) > 0.000001 || nthresholds_ != o->nthresholds_ || nleaves_ != o->nleaves_ ||
+      minleafsupport_ != o->minleafsupport_ || valid_iterations_ != o->valid_iterations_ ||
+      sample_type != o->sample_type || normalize_type != o->normalize_type || rate_drop != o->rate_drop ||
+      skip_drop != o->skip_drop)
+    return false;
+  ensemble_model_ = std::move(o->ensemble_model_);
+  return true;
 }
 
 void Dart::check_supported() const {

@@ -50,8 +50,9 @@ struct SplitResult {
 };
 
 struct HostNode {
-  uint32_t lo = 0, n = 0;   // segment [lo, lo+n) of the id buffer `buf` (local documents)
-  int buf = 0;              // 0 / 1: id buffer; 2: identity list (root)
+  uint32_t lo = 0, n = 0;   // REFERENCE mode: segment [lo, lo+n) of the id buffer `buf`
+  int buf = 0;              // REFERENCE mode: 0 / 1: id buffer; 2: identity list (root)
+  int parent = -1;          // FAST mode: the node's index is the id its documents carry in node_of_doc
   int hist = -1;            // histogram slot, -1 once released
   int left = -1, right = -1;
   bool expanded = false;    // children (and their split scans) have been computed
@@ -62,11 +63,8 @@ struct HostNode {
 };
 
 struct Comm;      // NCCL plumbing (qr_comm.cu)
-struct LeafSeg;
-struct RoundHdr;
-struct GrowState;
-struct GrowOut;
-struct DevNode;
+struct ChildOut;
+struct DevCand;
 
 }  // namespace qr
 
@@ -100,7 +98,21 @@ struct qr_ctx {
   double *d_lg = nullptr;         // [maxlen] log2((float)i+2)
   double *d_scores = nullptr, *d_lambda = nullptr, *d_weight = nullptr;  // [N]
   long long *d_lamq = nullptr;    // [N] fixed-point pseudo-responses (FAST mode)
-  long long *d_lamq_c = nullptr;  // [N] the same, compacted by the partition next to the built child's id list
+  // FAST mode (qr_fast_kernels.cuh): a node is the set of documents carrying its id
+  uint16_t *d_node = nullptr;     // [N padded to 4] node_of_doc
+  uint32_t *d_cids = nullptr;     // [compact_cap] compact lists of the round's built children: document ids ...
+  long long *d_clamq = nullptr;   // [compact_cap] ... and their fixed-point pseudo-responses
+  size_t compact_cap = 0;
+  uint32_t *d_counts = nullptr;   // [2][max_tasks] entries appended to each task's list (double-buffered by round)
+  uint32_t count_parity = 0;
+  uint32_t max_nodes = 0;         // node ids are 16 bits
+  // one GPU: the split scan hands per-feature candidates to the host, which reduces over features
+  bool fused_scan = false;
+  qr::ChildOut *h_out = nullptr, *d_out_mapped = nullptr;           // [max_tasks][2] mapped pinned: the round's results
+  qr::DevCand *d_cand = nullptr;                                    // [max_tasks][2][F] per-feature winners
+  double2 *d_noderec = nullptr;                                     // [max_tasks][2]
+  ulonglong2 *d_sq_acc = nullptr;                                   // [max_tasks]
+  bool maxabs_valid = false;      // d_maxabs holds max |lambda| of the current pseudo-responses (written by their kernel)
   unsigned long long *d_maxabs = nullptr;  // bits of max |lambda|
   int *d_qexp = nullptr;          // fixed-point exponent chosen for this tree
   uint32_t *d_rankpos = nullptr;  // [N] position (within its query) of the doc at each rank
@@ -108,14 +120,12 @@ struct qr_ctx {
   double *d_metric = nullptr;     // [1]
   uint32_t *d_ids[2] = {nullptr, nullptr};  // [N] node document lists (ping-pong)
   uint32_t *d_leaf_of_doc = nullptr;        // [N]
-  uint32_t *d_blockcnt = nullptr;           // partition scratch
+  uint32_t *d_blockcnt = nullptr;           // partition scratch (REFERENCE mode)
   double *d_partials = nullptr;             // REFERENCE: squares per task [max_tasks]
   ulonglong2 *d_sq128 = nullptr;            // FAST: exact squares per histogram slice [max_slices]
   uint32_t max_slices = 0;
   uint32_t *d_task_done = nullptr;          // [max_tasks] finalize completion counters
-  unsigned long long *d_part_status = nullptr;  // one-pass partition look-back words
-  uint32_t *d_ticket = nullptr;             // one-pass partition block tickets
-  uint32_t ticket_base = 0, part_epoch = 0;
+  double *d_sq_built = nullptr;             // [max_tasks] squares sum of each task's built child (split scan scratch)
   uint32_t *d_root_cnt = nullptr;           // [ncells] per-bin document counts of the whole dataset
   unsigned long long *d_hist_sum = nullptr; // [nslots][ncells] int64 (FAST) or double (REFERENCE)
   uint32_t *d_hist_cnt = nullptr;           // [nslots][ncells]
@@ -124,20 +134,22 @@ struct qr_ctx {
   uint32_t max_tasks = 0;                   // node expansions per round
   qr::NodeTask *d_tasks = nullptr, *h_tasks = nullptr;   // [max_tasks] (host copy pinned)
   qr::TaskPack pack{};                      // task records of a small round, passed as kernel parameters
-  uint32_t *d_lcount = nullptr, *h_lcount = nullptr;     // [max_tasks] local left counts
-  uint32_t *d_lcount_mapped = nullptr;      // device view of h_lcount (sharded training: written by the partition)
-  bool part_3pass = false;                  // sharded training with the count/prefix/scatter partition (QR_COMM_3PASS=1)
-  double *d_fbest_score = nullptr;          // [max_tasks][2][F]
+  uint32_t *d_lcount = nullptr;             // [max_tasks] left counts (REFERENCE mode partition)
+  double *d_fbest_score = nullptr;          // [max_tasks][2][F] per-feature winners of the split scan
   uint32_t *d_fbest_t = nullptr;            // [max_tasks][2][F]
   uint32_t *d_fbest_lc = nullptr;           // [max_tasks][2][F] left count at each feature's best split
   ulonglong2 *d_totals = nullptr;           // [max_tasks][2] (node size, node sum bits)
-  qr::SplitResult *d_res = nullptr;         // [max_tasks][2]
-  qr::SplitResult *h_res = nullptr;         // pinned + mapped: finalize_kernel writes it directly
+  qr::SplitResult *d_res = nullptr;         // [max_tasks][2] (oblivious level arg-max)
+  qr::SplitResult *h_res = nullptr;         // pinned + mapped: scan_kernel writes it directly
   qr::SplitResult *d_res_mapped = nullptr;  // device view of h_res
   uint32_t *h_flags = nullptr, *d_flags_mapped = nullptr;   // [max_tasks] per-task "result published" round ids
   uint32_t round_id = 0;
-  qr::LeafSeg *d_segs = nullptr, *h_segs = nullptr;      // [maxleaves]
-  double2 *d_leaf_partials = nullptr;       // [N / kLeafItems + maxleaves]
+  uint32_t *h_err = nullptr, *d_err_mapped = nullptr;       // [1] set by a kernel whose wait for a peer rank timed out
+  qr::LeafSeg *d_segs = nullptr, *h_segs = nullptr;      // [maxleaves] (REFERENCE mode)
+  double2 *d_leaf_partials = nullptr;       // [blocks][leaves] per-block leaf sums (FAST mode)
+  size_t leaf_part_cap = 0, leaf_smem_set = 0;
+  unsigned char *h_leafmeta = nullptr, *d_leafmeta = nullptr;   // node -> leaf table (u16) | leaf sizes (u64 at leafn_off)
+  size_t leafn_off = 0;
   double2 *d_leafsum = nullptr;             // [maxleaves] (sum lambda, sum weight)
   double *d_leafval = nullptr;              // [maxleaves]
   double *h_leafval = nullptr;              // pinned
@@ -163,19 +175,6 @@ struct qr_ctx {
   uint64_t histk_launches = 0;
   double histk_docs = 0;                          // documents accumulated by those launches
 
-  // device-driven leaf-wise growth (qr_grow.cuh)
-  bool device_growth = false;               // single GPU, leaf-wise, fixed-point mode
-  qr::RoundHdr *d_hdr = nullptr;            // [2] double-buffered round header
-  qr::GrowState *d_grow = nullptr, *h_grow = nullptr;
-  qr::GrowOut *h_grow_out = nullptr, *d_grow_out = nullptr;   // mapped pinned
-  qr::DevNode *d_nodes = nullptr, *h_nodes = nullptr;         // [max_nodes]; host copy pinned
-  uint32_t max_nodes = 0;
-  uint32_t root_dpb = 0;
-  size_t grow_smem = 0;                     // dynamic shared memory of grow_step_kernel
-  void *d_grow_arrays[7] = {nullptr};       // heap/slots/candidate arrays owned by the grow state
-
-  uint32_t *d_part_done = nullptr, *d_panel_done = nullptr;   // counters of the fused round kernel
-  bool fused_rounds = false, fuse_partition = false;
   void *d_apply = nullptr, *h_apply = nullptr;   // staging of qr_apply_trees (device / pinned host)
   size_t apply_cap = 0;
 
@@ -185,7 +184,7 @@ struct qr_ctx {
   // sharded training over peer memory (qr_comm.cu): per-round state of the histogram exchange
   int stage_slot0 = 0;                      // first of the 2 x max_tasks staging slots (after the nslots pool slots)
   uint32_t xround = 0;                      // exchange rounds so far (its parity selects the staging set)
-  bool round_fused = false;                 // this round's all-reduce happens inside finalize_kernel
+  bool round_fused = false;                 // this round's all-reduce happens inside scan_kernel
   uint32_t round_parity = 0, round_sq_off = 0;   // staging set / offset into d_sq128 of this round
   bool peer_fused = true;                   // QR_PEER_FUSED=0: always the stand-alone exchange kernel
   uint32_t oneshot_max = 4;                 // fuse when (world - 1) * tasks <= this (QR_PEER_ONESHOT_MAX)

@@ -520,9 +520,13 @@ __global__ void choose_scale_kernel(const unsigned long long *maxbits, int log2n
   *qexp = (62 - log2n_ceil) - e;    // |lam * 2^qexp| < 2^(62 - log2n)
 }
 
-__global__ void quantize_kernel(const double *lam, size_t N, const int *qexp, long long *lamq) {
+// also puts every document back into the root (node 0) for the tree about to be grown
+__global__ void quantize_kernel(const double *lam, size_t N, const int *qexp, long long *lamq, uint16_t *node) {
   size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) lamq[i] = __double2ll_rn(ldexp(lam[i], *qexp));
+  if (i < N) {
+    lamq[i] = __double2ll_rn(ldexp(lam[i], *qexp));
+    node[i] = 0;
+  }
 }
 
 

@@ -10,13 +10,16 @@ namespace qr {
 // bin(f, doc) <= t, the histogram of one child is built from that child's documents and the
 // sibling's is derived as parent - built (rt.cc:337-347).
 struct NodeTask {
-  uint32_t lo, n;        // the node's segment of the id buffer (local documents)
-  uint32_t src, dst;     // id buffers: 0 / 1, src == 2 means the identity list (root)
+  uint32_t lo, n;        // REFERENCE mode: the node's segment of the id buffer; FAST mode, whole node: n = local documents
+  uint32_t src, dst;     // REFERENCE mode: id buffers 0 / 1, src == 2 means the identity list (root)
   uint32_t f, t;         // split feature and threshold index
   uint32_t build_left;   // 1: the left child's histogram is built from samples, 0: the right one's
   uint32_t whole;        // 1: histogram of the whole node (root refresh, mart.cc:335); no split
   int32_t slotP, slotB, slotD;  // histogram slots: parent, built child, derived child
-  uint32_t part_blk0;    // first flat partition block of this task
+  uint32_t node;         // FAST mode: id of the node being split (value of node_of_doc for its documents)
+  uint32_t child0;       // FAST mode: id of the left child; the right child is child0 + 1
+  uint32_t region0;      // FAST mode: where the built child's compacted (doc id, pseudo-response) list starts
+  uint32_t part_blk0;    // first flat partition block of this task (REFERENCE mode)
   uint32_t hist_blk0;    // first flat histogram slice of this task
   uint32_t hist_dpb;     // documents per histogram slice
   uint32_t hist_nblk;    // histogram slices of this task
@@ -70,8 +73,9 @@ __device__ __forceinline__ void wait_flag(const uint32_t *p, uint32_t epoch) {
 constexpr uint32_t kPackTasks = 12;
 struct TaskPack { uint32_t n; uint32_t pad; NodeTask t[kPackTasks]; };
 
-constexpr uint32_t kPartItems = 2048;   // documents per partition block
-constexpr uint32_t kSqParts = 16;       // squares partials per task (FAST)
+constexpr uint32_t kPartItems = 2048;   // documents per partition block (REFERENCE mode)
+
+struct LeafSeg { uint32_t lo, n; uint32_t buf; uint32_t blk0; };  // REFERENCE mode leaf pass; buf 2 = identity (unsplit root)
 
 // 128-bit unsigned accumulator for the exact sum of squared fixed-point pseudo-responses
 struct U128 { unsigned long long lo, hi; };

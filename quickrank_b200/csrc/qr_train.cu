@@ -18,7 +18,6 @@
 
 #include "qr_comm.cuh"
 #include "qr_tree_kernels.cuh"
-#include "qr_round_kernel.cuh"
 
 namespace qr {
 
@@ -44,6 +43,31 @@ void set_error(const char *fmt, ...) {
                     cudaGetErrorString(_le));                                          \
       return QR_ECUDA;                                                                 \
     }                                                                                  \
+  } while (0)
+
+// launch with programmatic stream serialization: the kernel may become resident before its predecessor in the
+// stream has finished; it must execute griddepcontrol.wait (pdl_wait) before touching the predecessor's output
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+
+#define QR_LAUNCH_PDL(ctx, phase, kernel, grid, block, smem, ...)                              \
+  do {                                                                                         \
+    cudaError_t _le = launch_pdl(kernel, grid, block, smem, (ctx)->stream, __VA_ARGS__);       \
+    (ctx)->launches++;                                                                         \
+    (ctx)->phase_launches[phase]++;                                                            \
+    if (_le != cudaSuccess) {                                                                  \
+      qr::set_error("%s:%d: launch of %s failed: %s", __FILE__, __LINE__, #kernel,             \
+                    cudaGetErrorString(_le));                                                  \
+      return QR_ECUDA;                                                                         \
+    }                                                                                          \
   } while (0)
 
 struct PhaseTimer {
@@ -318,8 +342,8 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   c->lambda = params->algo == QR_ALGO_LAMBDAMART || params->algo == QR_ALGO_OBVLAMBDAMART;
   c->oblivious = params->algo == QR_ALGO_OBVMART || params->algo == QR_ALGO_OBVLAMBDAMART;
   c->exact = params->hist_mode == QR_HIST_REFERENCE;
-  if (c->oblivious && (params->treedepth == 0 || params->treedepth > 16)) {
-    delete c; set_error("treedepth must be in 1..16"); return QR_EINVAL;
+  if (c->oblivious && (params->treedepth == 0 || params->treedepth > 15)) {
+    delete c; set_error("treedepth must be in 1..15"); return QR_EINVAL;
   }
   if (!c->oblivious && params->nleaves < 1) { delete c; set_error("nleaves must be >= 1"); return QR_EINVAL; }
   *out = c;  // destroyed by the caller on failure paths below via qr_ctx_destroy
@@ -424,14 +448,11 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_lambda, N));
   QR_TRY(dev_alloc(&c->d_weight, N));
   QR_TRY(dev_alloc(&c->d_lamq, N));
-  QR_TRY(dev_alloc(&c->d_lamq_c, N));
   QR_TRY(dev_alloc(&c->d_maxabs, 1));
   QR_TRY(dev_alloc(&c->d_qexp, 1));
   QR_TRY(dev_alloc(&c->d_rankpos, N));
   QR_TRY(dev_alloc(&c->d_qndcg, Q));
   QR_TRY(dev_alloc(&c->d_metric, 1));
-  QR_TRY(dev_alloc(&c->d_ids[0], N));
-  QR_TRY(dev_alloc(&c->d_ids[1], N));
   QR_TRY(dev_alloc(&c->d_leaf_of_doc, N));
   QR_CUDA(cudaMemset(c->d_scores, 0, N * sizeof(double)));
   QR_CUDA(cudaMemset(c->d_lambda, 0, N * sizeof(double)));
@@ -449,11 +470,23 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   // every expansion holds two child histograms until the node is popped or the tree is finished;
   // speculative expansions (qr_tree_host.cuh) can double the number of live nodes
   c->nslots = (int) (4 * maxleaves + 8);
+  // node ids (one per expansion child) are 16 bits in node_of_doc
+  const size_t max_nodes = c->oblivious ? ((size_t) 2 << params->treedepth) : 4 * maxleaves + 16;
+  if (!c->exact && max_nodes > 65535) {
+    set_error("trees of more than %s are not supported by the fixed-point growth path (node ids are 16 bits)",
+              c->oblivious ? "depth 14" : "16379 leaves");
+    return QR_ELIMIT;
+  }
+  c->max_nodes = (uint32_t) max_nodes;
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  // sharded training: two sets of staging slots behind the pool (local histograms of a round's built children)
+  // behind the pool: sharded training, two sets of staging slots (local histograms of a round's built
+  // children); one GPU, fixed-point mode: one raw slot per task of a round (kept clear by the fused split scan)
   c->stage_slot0 = c->nslots;
-  const size_t pool_slots = (size_t) c->nslots + (c->comm ? 2 * (maxleaves + 1) : 0);
+  const size_t hist_smem_bytes = (size_t) c->fpp * c->max_thr * 12;
+  (void) hist_smem_bytes;
+  c->fused_scan = !c->exact && !c->comm && F <= 65535;   // one GPU: scan_pub_kernel (its records pack the feature in 16 bits)
+  const size_t pool_slots = (size_t) c->nslots + (c->comm ? 2 * (maxleaves + 1) : (c->fused_scan ? maxleaves + 1 : 0));
   const size_t hist_bytes = pool_slots * c->ncells * 12;
   if (hist_bytes + (64u << 20) > free_b) {
     set_error("histogram pool needs %zu MB (%d nodes x %u cells); not enough device memory — bound the "
@@ -467,28 +500,31 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_hist_cnt, pool_cells));
   for (int i = c->nslots - 1; i >= 0; --i) c->free_slots.push_back(i);
   const size_t mt = c->max_tasks;
-  QR_TRY(dev_alloc(&c->d_blockcnt, (N + kPartItems - 1) / kPartItems + mt + 1));
+  if (c->fused_scan) {
+    QR_CUDA(cudaMemset(c->d_hist_sum + (size_t) c->nslots * c->ncells, 0, mt * c->ncells * sizeof(unsigned long long)));
+    QR_CUDA(cudaMemset(c->d_hist_cnt + (size_t) c->nslots * c->ncells, 0, mt * c->ncells * sizeof(uint32_t)));
+    QR_CUDA(cudaHostAlloc((void **) &c->h_out, mt * 2 * sizeof(ChildOut), cudaHostAllocMapped));
+    QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_out_mapped, c->h_out, 0));
+    memset(c->h_out, 0, mt * 2 * sizeof(ChildOut));   // (tag 0 = not written)
+    QR_TRY(dev_alloc(&c->d_cand, mt * 2 * F));
+    QR_TRY(dev_alloc(&c->d_noderec, mt * 2));
+    QR_TRY(dev_alloc(&c->d_sq_acc, mt));
+    QR_CUDA(cudaMemset(c->d_sq_acc, 0, mt * sizeof(ulonglong2)));
+  }
   QR_TRY(dev_alloc(&c->d_partials, mt));
+  QR_TRY(dev_alloc(&c->d_sq_built, mt));
   c->max_slices = 4096 + (uint32_t) mt;
   QR_TRY(dev_alloc(&c->d_sq128, std::max<size_t>(c->max_slices, c->comm ? ((size_t) 2 << 20) / sizeof(ulonglong2) : 1)));   // (exported over IPC)
   QR_TRY(dev_alloc(&c->d_task_done, mt));
   QR_CUDA(cudaMemset(c->d_task_done, 0, mt * sizeof(uint32_t)));
-  QR_TRY(dev_alloc(&c->d_part_status, (N + kPartItems - 1) / kPartItems + mt + 1));
-  QR_CUDA(cudaMemset(c->d_part_status, 0, ((N + kPartItems - 1) / kPartItems + mt + 1) * sizeof(unsigned long long)));
-  QR_TRY(dev_alloc(&c->d_ticket, 1));
-  QR_CUDA(cudaMemset(c->d_ticket, 0, sizeof(uint32_t)));
-  QR_TRY(dev_alloc(&c->d_tasks, 2 * mt));   // double-buffered by the device-driven growth
+  QR_TRY(dev_alloc(&c->d_tasks, mt));
   QR_CUDA(cudaMallocHost((void **) &c->h_tasks, mt * sizeof(NodeTask)));
   QR_TRY(dev_alloc(&c->d_lcount, mt));
-  QR_CUDA(cudaHostAlloc((void **) &c->h_lcount, mt * sizeof(uint32_t), cudaHostAllocMapped));
-  memset(c->h_lcount, 0, mt * sizeof(uint32_t));
-  if (c->comm) QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_lcount_mapped, c->h_lcount, 0));
-  c->part_3pass = c->comm != nullptr && getenv("QR_COMM_3PASS") != nullptr;
   if (const char *e = getenv("QR_PEER_FUSED")) c->peer_fused = atoi(e) != 0;
   if (const char *e = getenv("QR_PEER_ONESHOT_MAX")) c->oneshot_max = (uint32_t) std::max(0, atoi(e));
-  QR_TRY(dev_alloc(&c->d_fbest_score, mt * 2 * F * kFinParts));
-  QR_TRY(dev_alloc(&c->d_fbest_t, mt * 2 * F * kFinParts));
-  QR_TRY(dev_alloc(&c->d_fbest_lc, mt * 2 * F * kFinParts));
+  QR_TRY(dev_alloc(&c->d_fbest_score, mt * 2 * F));
+  QR_TRY(dev_alloc(&c->d_fbest_t, mt * 2 * F));
+  QR_TRY(dev_alloc(&c->d_fbest_lc, mt * 2 * F));
   QR_TRY(dev_alloc(&c->d_totals, mt * 2));
   QR_TRY(dev_alloc(&c->d_res, mt * 2));
   QR_CUDA(cudaHostAlloc((void **) &c->h_res, mt * 2 * sizeof(SplitResult), cudaHostAllocMapped));
@@ -496,9 +532,9 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_CUDA(cudaHostAlloc((void **) &c->h_flags, mt * sizeof(uint32_t), cudaHostAllocMapped));
   QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_flags_mapped, c->h_flags, 0));
   memset(c->h_flags, 0, mt * sizeof(uint32_t));
-  QR_TRY(dev_alloc(&c->d_segs, maxleaves + 1));
-  QR_CUDA(cudaMallocHost((void **) &c->h_segs, (maxleaves + 1) * sizeof(LeafSeg)));
-  QR_TRY(dev_alloc(&c->d_leaf_partials, (N + kLeafItems - 1) / kLeafItems + maxleaves + 1));
+  QR_CUDA(cudaHostAlloc((void **) &c->h_err, sizeof(uint32_t), cudaHostAllocMapped));
+  QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_err_mapped, c->h_err, 0));
+  *c->h_err = 0u;
   QR_TRY(dev_alloc(&c->d_leafsum, maxleaves + 1));
   QR_TRY(dev_alloc(&c->d_leafval, maxleaves + 1));
   QR_CUDA(cudaMallocHost((void **) &c->h_leafval, (maxleaves + 1) * sizeof(double)));
@@ -506,68 +542,44 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_TRY(dev_alloc(&c->d_obv_slots, mt));
   QR_TRY(dev_alloc(&c->d_obv_lcounts, mt));
   QR_CUDA(cudaMallocHost((void **) &c->h_obv_lcounts, mt * sizeof(uint64_t)));
-
-  // device-side growth controller (qr_grow.cuh)
-  // opt-in (QR_DEVICE_GROWTH=1): measured on B200 at config 2 the device-side replay costs ~20 us per
-  // round (one GPU thread is a slow place for a heap), about what the host round trip costs, and the
-  // upper-bound grids add a little: 2.1 ms/tree against 1.75 ms/tree for the host-driven rounds.
-  c->device_growth = !c->oblivious && !c->exact && c->comm == nullptr && getenv("QR_DEVICE_GROWTH") != nullptr;
-  c->max_nodes = (uint32_t) (2 * c->nslots + 8);
-  c->grow_smem = grow_smem_bytes(c->max_nodes, (uint32_t) c->nslots, c->max_tasks);
-  if (c->grow_smem > 200 * 1024) c->device_growth = false;   // very large trees: host-driven rounds
-  if (c->device_growth) {
-    cudaFuncSetAttribute(grow_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(c->grow_smem, 48 * 1024));
-    GrowState gs{};
-    gs.nleaves = (uint32_t) maxleaves; gs.max_tasks = c->max_tasks; gs.max_nodes = c->max_nodes;
-    gs.nslots = (uint32_t) c->nslots; gs.exact = 0;
-    gs.n_global = (double) c->N_global;
-    QR_TRY(dev_alloc(&c->d_nodes, c->max_nodes));
-    QR_CUDA(cudaMallocHost((void **) &c->h_nodes, c->max_nodes * sizeof(DevNode)));
-    QR_TRY(dev_alloc(&gs.heap_key, c->max_nodes + 1));
-    QR_TRY(dev_alloc(&gs.heap_val, c->max_nodes + 1));
-    QR_TRY(dev_alloc(&gs.free_slots, (size_t) c->nslots));
-    QR_TRY(dev_alloc(&gs.S, mt));
-    QR_TRY(dev_alloc(&gs.cand_key, c->max_nodes));
-    QR_TRY(dev_alloc(&gs.cand_val, c->max_nodes));
-    QR_TRY(dev_alloc(&gs.stack, c->max_nodes));
-    gs.nodes = c->d_nodes;
-    void *arrs[7] = {gs.heap_key, gs.heap_val, gs.free_slots, gs.S, gs.cand_key, gs.cand_val, gs.stack};
-    memcpy(c->d_grow_arrays, arrs, sizeof(arrs));
-    gs.want_slices = std::max<uint32_t>(1, 148u / c->npanels);
-    gs.max_slices = c->max_slices - c->max_tasks;
-    gs.min_dpb = 2u * kHistThreads;
-    c->h_grow = new GrowState(gs);
-    QR_TRY(dev_alloc(&c->d_grow, 1));
-    QR_CUDA(cudaMemcpy(c->d_grow, &gs, sizeof(gs), cudaMemcpyHostToDevice));
-    QR_TRY(dev_alloc(&c->d_hdr, 2));
-    QR_CUDA(cudaMemset(c->d_hdr, 0, 2 * sizeof(RoundHdr)));
-    QR_CUDA(cudaHostAlloc((void **) &c->h_grow_out, sizeof(GrowOut), cudaHostAllocMapped));
-    QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_grow_out, c->h_grow_out, 0));
-    memset((void *) c->h_grow_out, 0, sizeof(GrowOut));
+  if (c->exact) {
+    // REFERENCE mode: sample-id lists cut by a stable partition, leaves summed in list order
+    QR_TRY(dev_alloc(&c->d_ids[0], N));
+    QR_TRY(dev_alloc(&c->d_ids[1], N));
+    QR_TRY(dev_alloc(&c->d_blockcnt, (N + kPartItems - 1) / kPartItems + mt + 1));
+    QR_TRY(dev_alloc(&c->d_segs, maxleaves + 1));
+    QR_CUDA(cudaMallocHost((void **) &c->h_segs, (maxleaves + 1) * sizeof(LeafSeg)));
+  } else {
+    // FAST mode: node_of_doc + the compact lists of a round's built children.  One GPU: the built child is the
+    // smaller one, so a round appends at most N/2 documents.  Several ranks: a task's region must hold whatever
+    // share of the (globally smaller) child is local: min(global size, N) each, N_global/2 + ... in total.
+    QR_TRY(dev_alloc(&c->d_node, N + 8));
+    QR_CUDA(cudaMemset(c->d_node, 0, (N + 8) * sizeof(uint16_t)));
+    c->compact_cap = (c->comm ? c->N_global / 2 : N / 2) + 8;
+    QR_TRY(dev_alloc(&c->d_cids, c->compact_cap));
+    QR_TRY(dev_alloc(&c->d_clamq, c->compact_cap));
+    QR_TRY(dev_alloc(&c->d_counts, 2 * mt));
+    QR_CUDA(cudaMemset(c->d_counts, 0, 2 * mt * sizeof(uint32_t)));
+    c->leafn_off = ((size_t) c->max_nodes * 2 + 15) & ~(size_t) 15;
+    const size_t meta = c->leafn_off + (maxleaves + 1) * sizeof(unsigned long long);
+    QR_CUDA(cudaMallocHost((void **) &c->h_leafmeta, meta));
+    QR_TRY(dev_alloc(&c->d_leafmeta, meta));
+    QR_CUDA(cudaFuncSetAttribute(route_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
+    QR_CUDA(cudaFuncSetAttribute(route_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024));
   }
-
-  // counters of the fused round kernel (qr_round_kernel.cuh)
-  QR_TRY(dev_alloc(&c->d_part_done, mt));
-  QR_TRY(dev_alloc(&c->d_panel_done, mt * c->npanels));
-  QR_CUDA(cudaMemset(c->d_part_done, 0, mt * sizeof(uint32_t)));
-  QR_CUDA(cudaMemset(c->d_panel_done, 0, mt * c->npanels * sizeof(uint32_t)));
-  // opt-in (QR_FUSED_ROUNDS=1): measured on B200 at config 2 the fused launch is SLOWER than the three
-  // kernels (2.66 vs 2.45 ms per steady-state tree): its blocks carry the histogram role's 512 threads,
-  // 48 KB of shared memory and 64-register budget, so the partition role runs at 2 blocks per SM instead
-  // of 6 and the split scan spills; see DESIGN.md section 4.
-  c->fused_rounds = !c->exact && c->comm == nullptr && getenv("QR_FUSED_ROUNDS") != nullptr;
-  c->fuse_partition = getenv("QR_FUSE_PARTITION") != nullptr;
 
   // opt in to large dynamic shared memory where needed
   const size_t hist_smem = (size_t) c->fpp * c->max_thr * 12;
   if (hist_smem <= 200 * 1024) {
     const int bytes = (int) hist_smem;
-    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(round_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    cudaFuncSetAttribute(round_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint8_t, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(hist_limb_kernel<uint16_t, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   }
   QR_CUDA(cudaGetLastError());
   clk.lap("state + pools");
@@ -713,24 +725,21 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_qndcg, c->d_metric, c->d_ids[0], c->d_ids[1], c->d_leaf_of_doc, c->d_blockcnt,
                   c->d_partials, c->d_hist_sum, c->d_hist_cnt, c->d_fbest_score, c->d_fbest_t, c->d_res,
                   c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
-                  c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done, c->d_part_status,
-                  c->d_ticket, c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_hdr, c->d_grow, c->d_nodes,
-                  c->d_part_done, c->d_panel_done, c->d_lamq_c,
-                  c->d_grow_arrays[0], c->d_grow_arrays[1], c->d_grow_arrays[2], c->d_grow_arrays[3],
-                  c->d_grow_arrays[4], c->d_grow_arrays[5], c->d_grow_arrays[6]};
+                  c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done,
+                  c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_node, c->d_cids, c->d_clamq, c->d_counts,
+                  c->d_sq_built, c->d_leafmeta, c->d_sq_acc, c->d_cand, c->d_noderec};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);
   if (c->h_tasks) cudaFreeHost(c->h_tasks);
   if (c->h_flags) cudaFreeHost(c->h_flags);
-  if (c->h_lcount) cudaFreeHost(c->h_lcount);
+  if (c->h_err) cudaFreeHost(c->h_err);
   if (c->h_segs) cudaFreeHost(c->h_segs);
   if (c->h_obv_lcounts) cudaFreeHost(c->h_obv_lcounts);
-  if (c->h_nodes) cudaFreeHost(c->h_nodes);
+  if (c->h_leafmeta) cudaFreeHost(c->h_leafmeta);
+  if (c->h_out) cudaFreeHost(c->h_out);
   if (c->d_apply) cudaFree(c->d_apply);
   if (c->h_apply) cudaFreeHost(c->h_apply);
-  delete c->h_grow;
-  if (c->h_grow_out) cudaFreeHost((void *) c->h_grow_out);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev_t0) cudaEventDestroy(c->ev_t0);
@@ -778,33 +787,14 @@ int qr_update_modelscores(qr_ctx *c, double weight) {
   return update_modelscores(c, weight);
 }
 
+int qr_apply_trees(qr_ctx *c, const qr_flat_tree *trees, const double *weights, size_t ntrees);
+
+// one tree = a set of one (the staging buffers of qr_apply_trees are reused: no allocation and no stream
+// synchronisation per call, the validation set takes one of these per boosting iteration)
 int qr_apply_tree(qr_ctx *c, const qr_flat_tree *t, double weight) {
   QR_CHECK_CTX(c);
   if (!t || t->nnodes == 0) { set_error("qr_apply_tree: empty tree"); return QR_EINVAL; }
-  const uint32_t n = t->nnodes;
-  for (uint32_t i = 0; i < n; ++i)
-    if (t->feature[i] >= 0 && ((size_t) t->feature[i] >= c->F || t->threshold_idx[i] >= c->thr[t->feature[i]].size())) {
-      set_error("qr_apply_tree: node %u does not belong to this context's binning", i);
-      return QR_EINVAL;
-    }
-  int32_t *d_feat, *d_left, *d_right; uint32_t *d_tidx; double *d_val;
-  QR_TRY(dev_alloc(&d_feat, n)); QR_TRY(dev_alloc(&d_left, n)); QR_TRY(dev_alloc(&d_right, n));
-  QR_TRY(dev_alloc(&d_tidx, n)); QR_TRY(dev_alloc(&d_val, n));
-  QR_CUDA(cudaMemcpyAsync(d_feat, t->feature, n * 4, cudaMemcpyHostToDevice, c->stream));
-  QR_CUDA(cudaMemcpyAsync(d_left, t->left, n * 4, cudaMemcpyHostToDevice, c->stream));
-  QR_CUDA(cudaMemcpyAsync(d_right, t->right, n * 4, cudaMemcpyHostToDevice, c->stream));
-  QR_CUDA(cudaMemcpyAsync(d_tidx, t->threshold_idx, n * 4, cudaMemcpyHostToDevice, c->stream));
-  QR_CUDA(cudaMemcpyAsync(d_val, t->value, n * 8, cudaMemcpyHostToDevice, c->stream));
-  DevTree dt{d_feat, d_tidx, d_left, d_right, d_val};
-  int rc = dispatch_bins(c, [&](auto tag) -> int {
-    using B = decltype(tag);
-    QR_LAUNCH(c, PH_LEAF, apply_tree_kernel<B>, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_panels, c->N, dt, weight, c->d_scores);
-    return QR_OK;
-  });
-  cudaStreamSynchronize(c->stream);
-  cudaFree(d_feat); cudaFree(d_left); cudaFree(d_right); cudaFree(d_tidx); cudaFree(d_val);
-  c->ranking_valid = false;
-  return rc;
+  return qr_apply_trees(c, t, &weight, 1);
 }
 
 int qr_apply_trees(qr_ctx *c, const qr_flat_tree *trees, const double *weights, size_t ntrees) {

@@ -35,7 +35,7 @@ static int prepare_fixed_point(qr_ctx *c) {
   if (c->comm) QR_TRY(comm_allreduce_max_u64(c->comm, c->d_maxabs, 1, c->stream));
   QR_LAUNCH(c, PH_HIST, choose_scale_kernel, 1, 1, 0, c->d_maxabs, ceil_log2(c->N_global) + 1, c->d_qexp);
   QR_LAUNCH(c, PH_HIST, quantize_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_lambda, c->N,
-            c->d_qexp, c->d_lamq);
+            c->d_qexp, c->d_lamq, c->d_node);
   return QR_OK;
 }
 
@@ -68,11 +68,9 @@ struct NodeHeap {
   }
 };
 
-// Launches the histogram + finalize kernels for the tasks already uploaded to c->d_tasks.
-// `slots_ready`: the slots were already cleared by the one-pass partition kernel.
 // QR_TRACE=1: GPU timeline of the growth rounds (events between the kernels of a round), printed per tree
 struct RoundTrace {
-  std::vector<cudaEvent_t> ev;   // 4 per round: start, after partition, after histogram, after finalize
+  std::vector<cudaEvent_t> ev;   // 4 per round: start, after route/partition, after histogram, after the split scan
   size_t used = 0;
   cudaEvent_t next() {
     if (used == ev.size()) { cudaEvent_t e; cudaEventCreate(&e); ev.push_back(e); }
@@ -81,10 +79,18 @@ struct RoundTrace {
 };
 static RoundTrace g_trace;
 static const bool g_trace_on = getenv("QR_TRACE") != nullptr;
+static const bool g_pdl_on = getenv("QR_NO_PDL") == nullptr;
+static const int g_ktrace_round = getenv("QR_KTRACE") ? atoi(getenv("QR_KTRACE")) : -1;
+// host-side stamps of the traced round (ns, steady clock): 0 expand start, 1 tasks built, 2 route launched,
+// 3 histogram launched, 4 scan launched, 5 first flag seen, 6 all flags seen, 7 results reduced
+static int64_t g_hstamp[8];
+static inline void hstamp(int i) {
+  if (g_ktrace_round >= 0) g_hstamp[i] = std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 #define QR_TRACE_MARK(c) do { if (g_trace_on) cudaEventRecord(g_trace.next(), (c)->stream); } while (0)
 
 // wait for the k per-task flags of the current round (bounded spin; a launch failure surfaces through
-// cudaStreamQuery)
+// cudaStreamQuery, a peer that never arrived through the error word the split scan writes)
 static int wait_round_flags(qr_ctx *c, uint32_t k) {
   volatile uint32_t *flags = c->h_flags;
   uint64_t spins = 0;
@@ -104,6 +110,10 @@ static int wait_round_flags(qr_ctx *c, uint32_t k) {
     }
   }
   std::atomic_thread_fence(std::memory_order_acquire);
+  if (c->h_err && *(volatile uint32_t *) c->h_err) {
+    set_error("histogram exchange timed out waiting for a peer rank (is every rank still alive?)");
+    return QR_ECOMM;
+  }
   return QR_OK;
 }
 
@@ -122,19 +132,133 @@ static void begin_exchange_round(qr_ctx *c, uint32_t k) {
   c->round_fused = c->peer_fused && (uint32_t) (comm_world(c->comm) - 1) * k <= c->oneshot_max;
 }
 static uint32_t stage_of(const qr_ctx *c, uint32_t j) {
+  if (c->fused_scan) return 1u + (uint32_t) c->stage_slot0 + j;   // one GPU: the raw slot of task j (cleared by its scan)
   return c->round_fused ? 1u + (uint32_t) c->stage_slot0 + c->round_parity * c->max_tasks + j : 0u;
 }
 
-static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, bool slots_ready,
-                                double built_docs) {
+// One GPU: waits for the (task, feature) flags of the round's split scan (scan_pub_kernel), then takes the first
+// maximum over features of every child (rt.cc:297-306: ascending feature index, strict '>') and fills the node
+// statistics of RTNode(sampleids, hist) (rtnode.h:97-107) into h_res, where the growth code reads them.
+static int collect_fused_round(qr_ctx *c, uint32_t k) {
+  const uint32_t tag = c->round_id;
+  uint64_t spins = 0;
+  bool first = true;
+  for (uint32_t j = 0; j < k; ++j) {
+    const NodeTask &t = c->h_tasks[j];
+    const int nchild = t.whole ? 1 : 2;
+    for (int child = 0; child < nchild; ++child) {
+      ChildOut *o = c->h_out + (size_t) j * 2 + child;
+      volatile uint32_t *tags[3] = {&o->split.tag, &o->where.tag, &o->stats.tag};
+      for (int r = 0; r < 3; ++r) {
+        while (*tags[r] != tag) {
+          if ((++spins & 0xfffff) == 0) {   // bounded: a launch failure surfaces through cudaStreamQuery
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) {
+              set_error("growth round failed: %s", cudaGetErrorString(e));
+              return QR_ECUDA;
+            }
+            if (e == cudaSuccess && *tags[r] != tag) {
+              set_error("internal: growth round finished without publishing task %u", j);
+              return QR_ECUDA;
+            }
+          }
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
+      if (first) { hstamp(5); first = false; }
+      const bool built = t.whole || ((child == 0) == (t.build_left != 0u));
+      const double sqB = o->stats.v;
+      SplitResult r;
+      r.n = o->stats.a;
+      r.sum = o->where.v;
+      r.squares = built ? sqB : t.parent_squares - sqB;          // rtnode_histogram.cc:86,207
+      r.deviance = r.squares - r.sum * r.sum / (double) r.n;      // rtnode.h:106
+      r.score = o->split.v;
+      r.valid = r.score != -1.0;
+      r.feature = r.valid ? (o->where.a >> 16) : 0xffffffffu;
+      r.threshold_idx = r.valid ? (o->where.a & 0xffffu) : 0xffffffffu;
+      r.lcount = r.valid ? o->split.a : 0;
+      r.pad = 0;
+      c->h_res[(size_t) j * 2 + child] = r;
+      *tags[0] = 0u; *tags[1] = 0u; *tags[2] = 0u;   // consumed
+    }
+  }
+  hstamp(6);
+  hstamp(7);
+  return QR_OK;
+}
+
+// QR_KTRACE=<round>: device-side timeline (%globaltimer stamps of every block, qr_fast_kernels.cuh) of growth
+// round <round> of every 50th tree, printed on stderr.  Development aid.
+constexpr uint32_t kTraceBlocks = 8192;
+static unsigned long long *g_ktrace_dev = nullptr, *g_ktrace_host = nullptr;
+static uint64_t g_ktrace_tree = 0;
+static bool ktrace_active(const qr_ctx *c) {
+  return g_ktrace_round >= 0 && (int) c->nrounds == g_ktrace_round && g_ktrace_tree % 50 == 49;
+}
+static unsigned long long *ktrace_buffer(const qr_ctx *c, int which) {
+  if (!ktrace_active(c)) return nullptr;
+  if (!g_ktrace_dev) {
+    cudaMalloc((void **) &g_ktrace_dev, 3 * (size_t) kTraceBlocks * kTraceStamps * sizeof(unsigned long long));
+    g_ktrace_host = (unsigned long long *) malloc(3 * (size_t) kTraceBlocks * kTraceStamps * sizeof(unsigned long long));
+    cudaMemset(g_ktrace_dev, 0, 3 * (size_t) kTraceBlocks * kTraceStamps * sizeof(unsigned long long));
+  }
+  return g_ktrace_dev + (size_t) which * kTraceBlocks * kTraceStamps;
+}
+static void ktrace_report(qr_ctx *c, uint32_t route_blocks, uint32_t hist_blocks, uint32_t scan_blocks) {
+  if (!ktrace_active(c) || !g_ktrace_dev) return;
+  cudaStreamSynchronize(c->stream);
+  cudaMemcpy(g_ktrace_host, g_ktrace_dev, 3 * (size_t) kTraceBlocks * kTraceStamps * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  unsigned long long t0 = ~0ull;
+  const uint32_t nb[3] = {std::min(route_blocks, kTraceBlocks), std::min(hist_blocks, kTraceBlocks), std::min(scan_blocks, kTraceBlocks)};
+  for (int w = 0; w < 3; ++w)
+    for (uint32_t b = 0; b < nb[w]; ++b) {
+      const unsigned long long v = g_ktrace_host[((size_t) w * kTraceBlocks + b) * kTraceStamps];
+      if (v && v < t0) t0 = v;
+    }
+  const char *names[3] = {"route", "hist", "scan"};
+  for (int w = 0; w < 3; ++w) {
+    fprintf(stderr, "[ktrace] tree %llu round %u %s (%u blocks): ", (unsigned long long) g_ktrace_tree, c->nrounds, names[w], nb[w]);
+    for (uint32_t i = 0; i < kTraceStamps; ++i) {
+      unsigned long long mn = ~0ull, mx = 0, cnt = 0;
+      for (uint32_t b = 0; b < nb[w]; ++b) {
+        const unsigned long long v = g_ktrace_host[((size_t) w * kTraceBlocks + b) * kTraceStamps + i];
+        if (!v) continue;
+        mn = std::min(mn, v); mx = std::max(mx, v); ++cnt;
+      }
+      if (cnt) fprintf(stderr, " s%u[n=%llu %.1f..%.1f us]", i, cnt, (double) (mn - t0) * 1e-3, (double) (mx - t0) * 1e-3);
+    }
+    fprintf(stderr, "\n");
+  }
+  fprintf(stderr, "[ktrace] host: tasks +%.1f route-launched +%.1f hist-launched +%.1f scan-launched +%.1f first-flag +%.1f all-flags +%.1f reduced +%.1f us\n",
+          (g_hstamp[1] - g_hstamp[0]) * 1e-3, (g_hstamp[2] - g_hstamp[0]) * 1e-3, (g_hstamp[3] - g_hstamp[0]) * 1e-3,
+          (g_hstamp[4] - g_hstamp[0]) * 1e-3, (g_hstamp[5] - g_hstamp[0]) * 1e-3, (g_hstamp[6] - g_hstamp[0]) * 1e-3,
+          (g_hstamp[7] - g_hstamp[0]) * 1e-3);
+  cudaMemset(g_ktrace_dev, 0, 3 * (size_t) kTraceBlocks * kTraceStamps * sizeof(unsigned long long));
+}
+
+// small rounds carry their task records in the kernel parameters; otherwise they are copied to d_tasks
+// (sharded training: only with the peer-memory exchange, whose kernel takes the records the same way)
+static int publish_tasks(qr_ctx *c, uint32_t k) {
+  c->pack.n = 0;
+  if (!c->exact && k <= kPackTasks && (!c->comm || comm_transport(c->comm) == 2)) {
+    c->pack.n = k;
+    memcpy(c->pack.t, c->h_tasks, k * sizeof(NodeTask));
+  } else {
+    QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
+  }
+  return QR_OK;
+}
+
+// Launches the histogram + split-scan kernels of a round whose task records were published.
+static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, double built_docs) {
   const uint32_t F = (uint32_t) c->F;
-  if (root) { QR_TRACE_MARK(c); QR_TRACE_MARK(c); }
   {
     PhaseTimer pt(c, PH_HIST);
     const bool static_counts = root && !c->exact && c->d_root_cnt != nullptr;
-    if (!slots_ready)
+    if ((root || c->exact) && !c->fused_scan)   // (FAST child rounds: route_kernel cleared the slots; fused scan: raw slots stay clear)
       QR_LAUNCH(c, PH_HIST, prep_slots_kernel, dim3(std::max<uint32_t>(1, std::min<uint32_t>(32, (c->ncells + 1023) / 1024)), k),
-                256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells, static_counts ? c->d_root_cnt : nullptr);
+                256, 0, c->d_tasks, c->pack, c->d_hist_sum, c->d_hist_cnt, c->ncells, static_counts ? c->d_root_cnt : nullptr);
     if (c->exact) {
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
@@ -149,20 +273,33 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
       const size_t smem = (size_t) c->fpp * c->max_thr * 12;
       const bool use_smem = smem <= 200 * 1024;
       if (total_slices > (c->comm ? kSqRegion : c->max_slices - c->max_tasks)) { set_error("internal: %u histogram slices > capacity", total_slices); return QR_ECUDA; }
-#define QR_HIST_LAUNCH(SMEMF, COUNTF)                                                                        \
-  QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF>), dim3(total_slices, c->npanels), kHistThreads,   \
-            SMEMF ? smem : 0, c->d_tasks, k, c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1],        \
-            c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128 + c->round_sq_off, c->max_thr, \
-            (const RoundHdr *) nullptr, c->pack, (const long long *) (c->part_3pass ? nullptr : c->d_lamq_c))
+      const uint32_t *counts = c->d_counts + (size_t) c->count_parity * c->max_tasks;
+      unsigned long long *kt = c->fused_scan ? ktrace_buffer(c, 1) : nullptr;
+  // (a child round's histogram kernel follows the route kernel: programmatic dependent launch, unless timed)
+  const bool pdl = !root && !c->profiling && !g_trace_on && g_pdl_on;
+#define QR_HIST_LAUNCH(SMEMF, COUNTF, ACCF)                                                                   \
+  do {                                                                                                        \
+    if (pdl)                                                                                                  \
+      QR_LAUNCH_PDL(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF, ACCF>), dim3(total_slices, c->npanels), dim3(kHistThreads), \
+                    SMEMF ? smem : 0, (const NodeTask *) c->d_tasks, k, c->pack, counts, (const uint4 *) c->d_panels, c->N, \
+                    (const uint32_t *) c->d_cids, (const long long *) c->d_clamq, (const long long *) c->d_lamq, \
+                    (const uint32_t *) c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128 + c->round_sq_off, \
+                    c->max_thr, c->d_sq_acc, kt);                                                             \
+    else                                                                                                      \
+      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF, ACCF>), dim3(total_slices, c->npanels), kHistThreads, \
+                SMEMF ? smem : 0, c->d_tasks, k, c->pack, counts, c->d_panels, c->N, c->d_cids, c->d_clamq,   \
+                c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128 + c->round_sq_off, \
+                c->max_thr, c->d_sq_acc, kt);                                                                 \
+  } while (0)
       if (c->profiling) cudaEventRecord(c->ev_k0, c->stream);
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
         if (use_smem) {
-          if (static_counts) QR_HIST_LAUNCH(true, false);
-          else QR_HIST_LAUNCH(true, true);
+          if (c->fused_scan) { if (static_counts) QR_HIST_LAUNCH(true, false, true); else QR_HIST_LAUNCH(true, true, true); }
+          else { if (static_counts) QR_HIST_LAUNCH(true, false, false); else QR_HIST_LAUNCH(true, true, false); }
         } else {
-          if (static_counts) QR_HIST_LAUNCH(false, false);
-          else QR_HIST_LAUNCH(false, true);
+          if (c->fused_scan) { if (static_counts) QR_HIST_LAUNCH(false, false, true); else QR_HIST_LAUNCH(false, true, true); }
+          else { if (static_counts) QR_HIST_LAUNCH(false, false, false); else QR_HIST_LAUNCH(false, true, false); }
         }
         return QR_OK;
       }));
@@ -180,6 +317,34 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
     if (c->comm && !c->round_fused) QR_TRY(comm_reduce_tasks(c, k, root));
   }
   QR_TRACE_MARK(c);
+  hstamp(3);
+  if (c->fused_scan) {
+    // one GPU: the scan publishes per-feature candidates, the host reduces over features; launched behind the
+    // histogram kernel with programmatic stream serialization (resident and waiting when that kernel ends)
+    PhaseTimer pt(c, PH_SCAN);
+    c->round_id++;
+    ScanOut so{};
+    so.out = c->d_out_mapped; so.cand = c->d_cand; so.node = c->d_noderec; so.sq_built = c->d_sq_built;
+    so.done = c->d_task_done; so.sq_acc = c->d_sq_acc; so.root_cnt = c->d_root_cnt; so.qexp = c->d_qexp;
+    so.round_id = c->round_id; so.minls = c->p.minleafsupport; so.ktrace = ktrace_buffer(c, 2);
+    const bool static_counts = root && c->d_root_cnt != nullptr;
+    const bool pdl = !c->profiling && !g_trace_on && g_pdl_on;
+#define QR_SCANPUB_LAUNCH(COUNTF)                                                                             \
+  do {                                                                                                        \
+    if (pdl)                                                                                                  \
+      QR_LAUNCH_PDL(c, PH_SCAN, scan_pub_kernel<COUNTF>, dim3(F, k), dim3(kPubThreads), 0, (const NodeTask *) c->d_tasks, \
+                    c->pack, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const uint32_t *) c->d_thr_off, F, so);  \
+    else                                                                                                      \
+      QR_LAUNCH(c, PH_SCAN, scan_pub_kernel<COUNTF>, dim3(F, k), kPubThreads, 0, c->d_tasks, c->pack, c->d_hist_sum, \
+                c->d_hist_cnt, c->ncells, c->d_thr_off, F, so);                                               \
+  } while (0)
+    if (static_counts) QR_SCANPUB_LAUNCH(false);
+    else QR_SCANPUB_LAUNCH(true);
+#undef QR_SCANPUB_LAUNCH
+    hstamp(4);
+    QR_TRACE_MARK(c);
+    return collect_fused_round(c, k);
+  }
   {
     PhaseTimer pt(c, PH_SCAN);
     // results are written straight into mapped pinned host memory and announced through per-task
@@ -187,28 +352,16 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
     c->round_id++;
     PeerView pv{};
     if (c->round_fused) comm_peer_view(c, !(root && c->d_root_cnt != nullptr), &pv);
-    if (c->exact)
-      QR_LAUNCH(c, PH_SCAN, finalize_kernel<true>, dim3(fin_blocks(F), k), kFinWarps * 32, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
-                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
-                c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack, pv);
-    else if (c->round_fused)
-      QR_LAUNCH(c, PH_SCAN, (finalize_kernel<false, true>), dim3(fin_blocks(F), k), kFinWarps * 32, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
-                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
-                c->d_fbest_lc, c->d_totals, c->d_sq128 + c->round_sq_off, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack, pv);
-    else
-      QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3(fin_blocks(F), k), kFinWarps * 32, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt,
-                c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t,
-                c->d_fbest_lc, c->d_totals, c->d_sq128 + c->round_sq_off, c->d_partials, c->d_task_done, c->d_res_mapped,
-                c->d_flags_mapped, c->round_id, (const RoundHdr *) nullptr, c->pack, pv);
+#define QR_SCAN_LAUNCH(PEERF, EXACTF)                                                                          \
+  QR_LAUNCH(c, PH_SCAN, (scan_kernel<PEERF, EXACTF>), dim3(F, k), kScanThreads, 0, c->d_tasks, c->pack, c->d_hist_sum,  \
+            c->d_hist_cnt, c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t, \
+            c->d_fbest_lc, c->d_totals, c->d_sq_built, c->d_sq128 + c->round_sq_off, c->d_partials, c->d_task_done,    \
+            c->d_res_mapped, c->d_flags_mapped, c->round_id, c->d_err_mapped, pv)
+    if (c->exact) QR_SCAN_LAUNCH(false, true);
+    else if (c->round_fused) QR_SCAN_LAUNCH(true, false);
+    else QR_SCAN_LAUNCH(false, false);
+#undef QR_SCAN_LAUNCH
     QR_TRACE_MARK(c);
-    if (c->comm && c->part_3pass) {
-      QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-      QR_CUDA(cudaStreamSynchronize(c->stream));
-    }
-    // (sharded, one-pass partition: the local left counts were written to mapped host memory by the
-    // partition kernel, two kernels before the flags below)
     QR_TRY(wait_round_flags(c, k));
   }
   return QR_OK;
@@ -241,8 +394,10 @@ static int build_root(qr_ctx *c) {
   t.hist_blk0 = 0; t.part_blk0 = 0; t.sq0 = 0; t.fused_sq = 0;
   const uint32_t slices = std::max<uint32_t>(1, (layout_n + t.hist_dpb - 1) / t.hist_dpb);
   t.hist_nblk = slices;
-  QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
-  QR_TRY(launch_hist_and_scan(c, 1, slices, true, false, (double) root.n));
+  QR_TRACE_MARK(c); QR_TRACE_MARK(c);
+  QR_TRY(publish_tasks(c, 1));
+  QR_TRY(launch_hist_and_scan(c, 1, slices, true, (double) root.n));
+  c->pack.n = 0;
   root.res = c->h_res[0];
   c->nodes.push_back(root);
   return QR_OK;
@@ -253,17 +408,16 @@ static int build_root(qr_ctx *c) {
 static int init_root_counts(qr_ctx *c) {
   if (c->exact) return QR_OK;
   QR_CUDA(cudaMemsetAsync(c->d_lamq, 0, c->N * sizeof(long long), c->stream));
-  HostNode root;
-  root.n = (uint32_t) c->N;
   const int slot = alloc_slot(c);
   NodeTask &t = c->h_tasks[0];
   memset(&t, 0, sizeof(t));
-  t.n = root.n; t.src = 2; t.whole = 1; t.build_left = 1;
+  t.n = (uint32_t) c->N; t.src = 2; t.whole = 1; t.build_left = 1;
   t.slotP = -1; t.slotB = slot; t.slotD = -1;
-  t.hist_dpb = pick_hist_dpb(c, root.n);
-  t.hist_nblk = std::max<uint32_t>(1, (root.n + t.hist_dpb - 1) / t.hist_dpb);
+  t.hist_dpb = pick_hist_dpb(c, c->N);
+  t.hist_nblk = std::max<uint32_t>(1, (t.n + t.hist_dpb - 1) / t.hist_dpb);
+  c->pack.n = 0;
   QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
-  QR_LAUNCH(c, PH_HIST, prep_slots_kernel, dim3(32, 1), 256, 0, c->d_tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells,
+  QR_LAUNCH(c, PH_HIST, prep_slots_kernel, dim3(32, 1), 256, 0, c->d_tasks, c->pack, c->d_hist_sum, c->d_hist_cnt, c->ncells,
             (const uint32_t *) nullptr);
   const size_t smem = (size_t) c->fpp * c->max_thr * 12;
   const bool use_smem = smem <= 200 * 1024;
@@ -271,13 +425,13 @@ static int init_root_counts(qr_ctx *c) {
   QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
     using B = decltype(tag);
     if (use_smem)
-      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, smem, c->d_tasks, 1u,
-                c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr, c->pack, (const long long *) nullptr);
+      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true, false>), dim3(t.hist_nblk, c->npanels), kHistThreads, smem, c->d_tasks, 1u,
+                c->pack, c->d_counts, c->d_panels, c->N, c->d_cids, c->d_clamq, c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (ulonglong2 *) nullptr, (unsigned long long *) nullptr);
     else
-      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(t.hist_nblk, c->npanels), kHistThreads, 0, c->d_tasks, 1u,
-                c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) nullptr, c->pack, (const long long *) nullptr);
+      QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true, false>), dim3(t.hist_nblk, c->npanels), kHistThreads, 0, c->d_tasks, 1u,
+                c->pack, c->d_counts, c->d_panels, c->N, c->d_cids, c->d_clamq, c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (ulonglong2 *) nullptr, (unsigned long long *) nullptr);
     return QR_OK;
   }));
   QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
@@ -290,156 +444,18 @@ static int init_root_counts(qr_ctx *c) {
   return QR_OK;
 }
 
-// RegressionTree::split (rt.cc:209-362) for every node in `S` (their best splits are known)
-static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_hists) {
-  const uint32_t k = (uint32_t) S.size();
-  if (k == 0) return QR_OK;
-  if (k > c->max_tasks) { set_error("internal: %u tasks > capacity %u", k, c->max_tasks); return QR_ECUDA; }
-  uint64_t built_total = 0;
-  for (uint32_t j = 0; j < k; ++j) {
-    const HostNode &nd = c->nodes[S[j]];
-    const uint64_t lc = nd.res.lcount, rc = nd.res.n - nd.res.lcount;
-    const bool build_left = c->exact ? true : lc <= rc;
-    // local sizes are only known exactly on a single GPU; with several ranks: the expected share
-    built_total += c->comm ? std::min(lc, rc) / (uint64_t) comm_world(c->comm) : (build_left ? lc : rc);
-  }
-  uint32_t dpb = pick_hist_dpb(c, built_total);
-  if (build_child_hists) begin_exchange_round(c, k);
-  if (c->comm) {
-    // The local size of the built child is unknown until the partition has run, and the slicing must be the
-    // same on every rank (the fused exchange reads the peers' per-slice squares partials): it is derived
-    // from replicated quantities only.  bound = min(global size of the built child, largest shard) covers
-    // any rank's share; queries are sharded without regard to their content, so the typical share is the
-    // global size / W: slices are sized for that (plus a margin), their number for the bound (slices past
-    // the real end return at once), capped so that a round never launches waves of empty blocks.
-    const uint64_t W = (uint64_t) comm_world(c->comm);
-    uint64_t est_total = 0, bound_total = 0;
-    for (uint32_t j = 0; j < k; ++j) {
-      const HostNode &nd = c->nodes[S[j]];
-      const uint64_t built = std::min(nd.res.lcount, nd.res.n - nd.res.lcount);
-      const uint64_t bound = std::min<uint64_t>(built, c->N_local_max);
-      est_total += std::min<uint64_t>(bound, built / W + built / (4 * W) + 256u);
-      bound_total += bound;
-    }
-    const uint32_t max_slices = 4u * std::max<uint32_t>(1, 148u / c->npanels) + k;
-    const uint64_t floor_dpb = ((bound_total + max_slices - 1) / max_slices + 255u) & ~(uint64_t) 255u;
-    dpb = (uint32_t) std::min<uint64_t>(std::max<uint64_t>(pick_hist_dpb(c, est_total), floor_dpb), 1u << 20);
-  }
-  uint32_t part_blk = 0, hist_blk = 0;
-  for (uint32_t j = 0; j < k; ++j) {
-    HostNode &nd = c->nodes[S[j]];
-    NodeTask &t = c->h_tasks[j];
-    memset(&t, 0, sizeof(t));
-    const uint64_t lc = nd.res.lcount, rc = nd.res.n - nd.res.lcount;
-    t.lo = nd.lo; t.n = nd.n; t.src = (uint32_t) nd.buf; t.dst = nd.buf == 2 ? 0u : (uint32_t) (1 - nd.buf);
-    t.f = nd.res.feature; t.t = nd.res.threshold_idx;
-    t.build_left = c->exact ? 1u : (lc <= rc ? 1u : 0u);
-    t.whole = 0;
-    t.slotP = nd.hist;
-    t.slotB = t.slotD = -1;
-    if (build_child_hists) {
-      t.slotB = alloc_slot(c);
-      t.slotD = alloc_slot(c);
-      if (t.slotB < 0 || t.slotD < 0) { set_error("internal: histogram pool exhausted"); return QR_ECUDA; }
-    }
-    t.part_blk0 = part_blk;
-    part_blk += std::max<uint32_t>(1, (nd.n + kPartItems - 1) / kPartItems);
-    t.hist_blk0 = hist_blk;
-    t.hist_dpb = dpb;
-    const uint64_t built_n = c->comm ? std::min<uint64_t>(std::min(lc, rc), c->N_local_max) : (t.build_left ? lc : rc);
-    t.hist_nblk = std::max<uint32_t>(1, (uint32_t) ((built_n + dpb - 1) / dpb));
-    t.stage1 = build_child_hists ? stage_of(c, j) : 0u;
-    hist_blk += t.hist_nblk;
-    if (build_child_hists) c->beta += (double) (t.build_left ? lc : rc) / (double) c->N_global;
-    t.lcount = (uint32_t) lc;
-    t.lc_known = c->comm ? 0u : 1u;
-    t.sq0 = j;
-    t.fused_sq = 1;
-    t.parent_squares = nd.res.squares;
-  }
-  QR_TRACE_MARK(c);
-  const bool onepass = !c->part_3pass;
-  c->pack.n = 0;
-  // (sharded training: only with the peer-memory exchange, whose kernel takes the records the same way)
-  if (onepass && !c->exact && (!c->comm || comm_transport(c->comm) == 2) && build_child_hists && k <= kPackTasks) {
-    // small round: the task records travel in the kernel parameters
-    c->pack.n = k;
-    memcpy(c->pack.t, c->h_tasks, k * sizeof(NodeTask));
-  } else {
-    QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
-  }
-  // one launch for the whole round (qr_round_kernel.cuh) when the per-phase breakdown is not asked for
-  const size_t fused_smem = (size_t) c->fpp * c->max_thr * 12;
-  const bool fused = c->fused_rounds && onepass && build_child_hists && !c->profiling && !g_trace_on &&
-                     fused_smem <= 200 * 1024 && hist_blk <= c->max_slices - c->max_tasks;
-  if (fused) {
-    c->part_epoch++;
-    c->round_id++;
-    // QR_FUSE_PARTITION=1 also chains the partition inside the launch; by default it stays a kernel of its
-    // own: its 256-thread blocks without shared memory fit 6 to an SM, the round kernel's blocks only 2
-    const bool fuse_partition = c->fuse_partition;
-    const uint32_t fused_part = fuse_partition ? part_blk : 0u;
-    const uint32_t grid = fused_part + hist_blk * c->npanels;
-    RoundCounters rc{c->d_part_done, c->d_panel_done, c->d_task_done};
-    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
-      using B = decltype(tag);
-      if (!fuse_partition) {
-        QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
-                  c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
-                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack,
-                  (const long long *) c->d_lamq, c->d_lamq_c, c->d_lcount, c->d_lcount_mapped);
-        c->ticket_base += part_blk;
-      }
-      QR_LAUNCH(c, PH_HIST, round_kernel<B>, grid, kRoundThreads, fused_smem, c->d_tasks, k, fused_part, hist_blk, c->d_panels,
-                c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, (uint32_t) c->F, c->npanels, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, c->d_part_status, c->d_ticket, c->ticket_base,
-                c->part_epoch, rc, c->p.minleafsupport, c->d_qexp, c->d_fbest_score, c->d_fbest_t, c->d_fbest_lc,
-                c->d_totals, c->d_res_mapped, c->d_flags_mapped, c->round_id, c->pack);
-      return QR_OK;
-    }));
-    c->ticket_base += grid;
-    QR_TRY(wait_round_flags(c, k));
-  } else {
-  {
-    PhaseTimer pt(c, PH_PARTITION);
-    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
-      using B = decltype(tag);
-      if (onepass) {
-        c->part_epoch++;
-        QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
-                  c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket,
-                  c->ticket_base, c->part_epoch, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) nullptr, c->pack,
-                  (const long long *) c->d_lamq, c->d_lamq_c, c->d_lcount, c->d_lcount_mapped);
-        c->ticket_base += part_blk;
-      } else {
-        QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
-                  c->d_ids[0], c->d_ids[1], c->d_blockcnt);
-        QR_LAUNCH(c, PH_PARTITION, part_prefix_kernel, k, 256, 0, c->d_tasks, c->d_blockcnt, c->d_lcount);
-        QR_LAUNCH(c, PH_PARTITION, part_scatter_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
-                  c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_blockcnt, c->d_lcount);
-      }
-      return QR_OK;
-    }));
-  }
-  QR_TRACE_MARK(c);
-  if (build_child_hists) {
-    QR_TRY(launch_hist_and_scan(c, k, hist_blk, false, onepass, (double) built_total));
-  } else if (c->comm) {
-    // last oblivious level: no split scan follows whose flags could be waited for
-    if (c->part_3pass)
-      QR_CUDA(cudaMemcpyAsync(c->h_lcount, c->d_lcount, k * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    QR_CUDA(cudaStreamSynchronize(c->stream));
-  }
-  }
-  c->pack.n = 0;
-  for (uint32_t j = 0; j < k; ++j) {
+// links the two children of every expanded node (results of the round are in h_res)
+static void link_children(qr_ctx *c, const std::vector<int> &S, bool build_child_hists, const uint32_t *lc_local) {
+  for (uint32_t j = 0; j < (uint32_t) S.size(); ++j) {
     const int i = S[j];
     const NodeTask &t = c->h_tasks[j];
     const HostNode nd = c->nodes[i];
-    const uint32_t lc_local = c->comm ? c->h_lcount[j] : (uint32_t) nd.res.lcount;
     HostNode L, R;
-    L.lo = nd.lo; L.n = lc_local; L.buf = (int) t.dst;
-    R.lo = nd.lo + lc_local; R.n = nd.n - lc_local; R.buf = (int) t.dst;
+    L.parent = R.parent = i;
+    if (lc_local) {   // REFERENCE mode: the children are segments of the id buffer
+      L.lo = nd.lo; L.n = lc_local[j]; L.buf = (int) t.dst;
+      R.lo = nd.lo + lc_local[j]; R.n = nd.n - lc_local[j]; R.buf = (int) t.dst;
+    }
     if (build_child_hists) {
       L.hist = t.build_left ? t.slotB : t.slotD;
       R.hist = t.build_left ? t.slotD : t.slotB;
@@ -458,8 +474,172 @@ static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_h
     c->nodes[i].right = li + 1;
     c->nodes[i].expanded = true;
   }
+}
+
+// RegressionTree::split (rt.cc:209-362) for every node in `S` (their best splits are known), FAST mode:
+// route -> histogram of the smaller child -> split scan of both children (qr_fast_kernels.cuh)
+static int expand_nodes_fast(qr_ctx *c, const std::vector<int> &S, bool build_child_hists) {
+  hstamp(0);
+  const uint32_t k = (uint32_t) S.size();
+  const uint64_t W = c->comm ? (uint64_t) comm_world(c->comm) : 1u;
+  uint64_t built_total = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    const HostNode &nd = c->nodes[S[j]];
+    // local sizes are only known exactly on a single GPU; with several ranks: the expected share
+    built_total += std::min(nd.res.lcount, nd.res.n - nd.res.lcount) / W;
+  }
+  uint32_t dpb = pick_hist_dpb(c, built_total);
+  if (build_child_hists) begin_exchange_round(c, k);
+  if (c->comm) {
+    // The local size of the built child is unknown until the route kernel has run, and the slicing must be
+    // the same on every rank (the fused exchange reads the peers' per-slice squares partials): it is derived
+    // from replicated quantities only.  bound = min(global size of the built child, largest shard) covers
+    // any rank's share; queries are sharded without regard to their content, so the typical share is the
+    // global size / W: slices are sized for that (plus a margin), their number for the bound (slices past
+    // the real end return at once), capped so that a round never launches waves of empty blocks.
+    uint64_t est_total = 0, bound_total = 0;
+    for (uint32_t j = 0; j < k; ++j) {
+      const HostNode &nd = c->nodes[S[j]];
+      const uint64_t built = std::min(nd.res.lcount, nd.res.n - nd.res.lcount);
+      const uint64_t bound = std::min<uint64_t>(built, c->N_local_max);
+      est_total += std::min<uint64_t>(bound, built / W + built / (4 * W) + 256u);
+      bound_total += bound;
+    }
+    const uint32_t max_slices = 4u * std::max<uint32_t>(1, 148u / c->npanels) + k;
+    const uint64_t floor_dpb = ((bound_total + max_slices - 1) / max_slices + 255u) & ~(uint64_t) 255u;
+    dpb = (uint32_t) std::min<uint64_t>(std::max<uint64_t>(pick_hist_dpb(c, est_total), floor_dpb), 1u << 20);
+  }
+  uint32_t hist_blk = 0;
+  uint64_t region = 0;
+  const uint32_t child_base = (uint32_t) c->nodes.size();
+  if ((size_t) child_base + 2 * k > c->max_nodes) { set_error("internal: node table full (%u nodes)", child_base + 2 * k); return QR_ECUDA; }
+  for (uint32_t j = 0; j < k; ++j) {
+    HostNode &nd = c->nodes[S[j]];
+    NodeTask &t = c->h_tasks[j];
+    memset(&t, 0, sizeof(t));
+    const uint64_t lc = nd.res.lcount, rc = nd.res.n - nd.res.lcount;
+    t.f = nd.res.feature; t.t = nd.res.threshold_idx;
+    t.build_left = lc <= rc ? 1u : 0u;      // the smaller child is built, its sibling is parent - built (exact in integers)
+    t.whole = 0;
+    t.slotP = nd.hist;
+    t.slotB = t.slotD = -1;
+    if (build_child_hists) {
+      t.slotB = alloc_slot(c);
+      t.slotD = alloc_slot(c);
+      if (t.slotB < 0 || t.slotD < 0) { set_error("internal: histogram pool exhausted"); return QR_ECUDA; }
+    }
+    t.node = (uint32_t) S[j];
+    t.child0 = child_base + 2 * j;
+    t.region0 = (uint32_t) region;
+    const uint64_t built = std::min(lc, rc);
+    if (build_child_hists) region += std::min<uint64_t>(built, c->N);
+    t.hist_blk0 = hist_blk;
+    t.hist_dpb = dpb;
+    const uint64_t layout_n = c->comm ? std::min<uint64_t>(built, c->N_local_max) : built;
+    t.hist_nblk = std::max<uint32_t>(1, (uint32_t) ((layout_n + dpb - 1) / dpb));
+    t.stage1 = build_child_hists ? stage_of(c, j) : 0u;
+    hist_blk += t.hist_nblk;
+    if (build_child_hists) c->beta += (double) built / (double) c->N_global;
+    t.lcount = (uint32_t) lc;
+    t.parent_squares = nd.res.squares;
+  }
+  if (region > c->compact_cap) { set_error("internal: compact lists need %llu entries > capacity %zu", (unsigned long long) region, c->compact_cap); return QR_ECUDA; }
+  QR_TRACE_MARK(c);
+  QR_TRY(publish_tasks(c, k));
+  hstamp(1);
+  {
+    PhaseTimer pt(c, PH_PARTITION);
+    const uint32_t parity = c->count_parity ^ 1u;   // this round's half of the counters; the other half is cleared
+    c->count_parity = parity;
+    const unsigned grid = (unsigned) ((c->N + kRouteDocs - 1) / kRouteDocs);
+    for (uint32_t j0 = 0; j0 < k; j0 += kRouteTasks) {
+      const uint32_t kc = std::min<uint32_t>(kRouteTasks, k - j0);
+      uint32_t nmin = 0xffffffffu, nmax = 0;
+      for (uint32_t j = j0; j < j0 + kc; ++j) { nmin = std::min(nmin, c->h_tasks[j].node); nmax = std::max(nmax, c->h_tasks[j].node); }
+      const uint32_t range = nmax - nmin + 1;
+      const size_t smem = ((size_t) range * 2 + 15) & ~(size_t) 15;
+      TaskPack pk = c->pack;
+      if (j0 != 0) pk.n = 0;   // (packed rounds have a single chunk)
+      QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+        using B = decltype(tag);
+        QR_LAUNCH(c, PH_PARTITION, route_kernel<B>, grid, kRouteThreads, smem, c->d_tasks + j0, kc, pk, c->d_panels, c->N,
+                  c->d_node, nmin, range, (const long long *) c->d_lamq, c->d_cids, c->d_clamq,
+                  c->d_counts + (size_t) parity * c->max_tasks + j0, c->d_counts + (size_t) (parity ^ 1u) * c->max_tasks,
+                  j0 == 0 ? c->max_tasks : 0u, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->fused_scan ? 0 : 1,
+                  ktrace_buffer(c, 0));
+        return QR_OK;
+      }));
+    }
+  }
+  QR_TRACE_MARK(c);
+  hstamp(2);
+  if (build_child_hists) QR_TRY(launch_hist_and_scan(c, k, hist_blk, false, (double) built_total));
+  c->pack.n = 0;
+  ktrace_report(c, (uint32_t) ((c->N + kRouteDocs - 1) / kRouteDocs), hist_blk * c->npanels, k * (uint32_t) c->F);
+  link_children(c, S, build_child_hists, nullptr);
   c->nrounds++;
   return QR_OK;
+}
+
+// The same in REFERENCE mode: stable partition of the node's sample-id list (count -> prefix -> scatter), the
+// LEFT child's histogram accumulated in the reference's order, right = parent - left (rt.cc:325-347)
+static int expand_nodes_exact(qr_ctx *c, const std::vector<int> &S, bool build_child_hists) {
+  const uint32_t k = (uint32_t) S.size();
+  uint32_t part_blk = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    HostNode &nd = c->nodes[S[j]];
+    NodeTask &t = c->h_tasks[j];
+    memset(&t, 0, sizeof(t));
+    const uint64_t lc = nd.res.lcount;
+    t.lo = nd.lo; t.n = nd.n; t.src = (uint32_t) nd.buf; t.dst = nd.buf == 2 ? 0u : (uint32_t) (1 - nd.buf);
+    t.f = nd.res.feature; t.t = nd.res.threshold_idx;
+    t.build_left = 1u;
+    t.whole = 0;
+    t.slotP = nd.hist;
+    t.slotB = t.slotD = -1;
+    if (build_child_hists) {
+      t.slotB = alloc_slot(c);
+      t.slotD = alloc_slot(c);
+      if (t.slotB < 0 || t.slotD < 0) { set_error("internal: histogram pool exhausted"); return QR_ECUDA; }
+    }
+    t.part_blk0 = part_blk;
+    part_blk += std::max<uint32_t>(1, (nd.n + kPartItems - 1) / kPartItems);
+    if (build_child_hists) c->beta += (double) lc / (double) c->N_global;
+    t.lcount = (uint32_t) lc;
+    t.lc_known = 1u;
+    t.sq0 = j;
+    t.fused_sq = 1;
+    t.parent_squares = nd.res.squares;
+  }
+  QR_TRACE_MARK(c);
+  c->pack.n = 0;
+  QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));
+  {
+    PhaseTimer pt(c, PH_PARTITION);
+    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+      using B = decltype(tag);
+      QR_LAUNCH(c, PH_PARTITION, part_count_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
+                c->d_ids[0], c->d_ids[1], c->d_blockcnt);
+      QR_LAUNCH(c, PH_PARTITION, part_prefix_kernel, k, 256, 0, c->d_tasks, c->d_blockcnt, c->d_lcount);
+      QR_LAUNCH(c, PH_PARTITION, part_scatter_kernel<B>, part_blk, 256, 0, c->d_tasks, k, c->d_panels, c->N,
+                c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_blockcnt, c->d_lcount);
+      return QR_OK;
+    }));
+  }
+  QR_TRACE_MARK(c);
+  if (build_child_hists) QR_TRY(launch_hist_and_scan(c, k, 0, false, 0.0));
+  std::vector<uint32_t> lcs(k);
+  for (uint32_t j = 0; j < k; ++j) lcs[j] = (uint32_t) c->nodes[S[j]].res.lcount;
+  link_children(c, S, build_child_hists, lcs.data());
+  c->nrounds++;
+  return QR_OK;
+}
+
+static int expand_nodes(qr_ctx *c, const std::vector<int> &S, bool build_child_hists) {
+  const uint32_t k = (uint32_t) S.size();
+  if (k == 0) return QR_OK;
+  if (k > c->max_tasks) { set_error("internal: %u tasks > capacity %u", k, c->max_tasks); return QR_ECUDA; }
+  return c->exact ? expand_nodes_exact(c, S, build_child_hists) : expand_nodes_fast(c, S, build_child_hists);
 }
 
 static bool can_split(const qr_ctx *c, int i) {
@@ -603,155 +783,70 @@ static uint32_t count_reachable(const qr_ctx *c, int i) {
   return nd.is_leaf() ? 1u : 1u + count_reachable(c, nd.left) + count_reachable(c, nd.right);
 }
 
-static int fit_leaves(qr_ctx *c) {
+// leaf outputs (rt.cc:165-207), REFERENCE mode: one warp per leaf, sums in list order
+static int fit_leaves_exact(qr_ctx *c) {
   const size_t nl = c->leaves.size();
   PhaseTimer pt(c, PH_LEAF);
-  uint32_t blk = 0;
   for (size_t k = 0; k < nl; ++k) {
     const HostNode &nd = c->nodes[c->leaves[k]];
-    c->h_segs[k] = LeafSeg{nd.lo, nd.n, (uint32_t) nd.buf, blk};
-    blk += (nd.n + kLeafItems - 1) / kLeafItems;
+    c->h_segs[k] = LeafSeg{nd.lo, nd.n, (uint32_t) nd.buf, 0u};
   }
   QR_CUDA(cudaMemcpyAsync(c->d_segs, c->h_segs, nl * sizeof(LeafSeg), cudaMemcpyHostToDevice, c->stream));
   const double *w = c->lambda ? c->d_weight : nullptr;
-  if (c->exact && !c->comm) {
-    QR_LAUNCH(c, PH_LEAF, leaf_exact_kernel, (unsigned) nl, 32, 0, c->d_segs, c->d_ids[0], c->d_ids[1], c->d_lambda,
-              w, c->d_leafval, c->d_leaf_of_doc);
-  } else {
-    if (blk > 0)
-      QR_LAUNCH(c, PH_LEAF, leaf_partial_kernel, blk, 256, 0, c->d_segs, (uint32_t) nl, c->d_ids[0], c->d_ids[1],
-                c->d_lambda, w, c->d_leaf_partials, c->d_leaf_of_doc, (const RoundHdr *) nullptr);
-    QR_LAUNCH(c, PH_LEAF, leaf_final_kernel, (unsigned) ((nl + 63) / 64), 64, 0, c->d_segs, (uint32_t) nl,
-              c->d_leaf_partials, c->lambda, c->d_leafsum, c->d_leafval, (const RoundHdr *) nullptr);
-    if (c->comm) QR_TRY(comm_leaf_values(c, (uint32_t) nl));
-  }
+  QR_LAUNCH(c, PH_LEAF, leaf_exact_kernel, (unsigned) nl, 32, 0, c->d_segs, c->d_ids[0], c->d_ids[1], c->d_lambda,
+            w, c->d_leafval, c->d_leaf_of_doc);
   QR_CUDA(cudaMemcpyAsync(c->h_leafval, c->d_leafval, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   QR_CUDA(cudaStreamSynchronize(c->stream));
   for (size_t k = 0; k < nl; ++k) c->nodes[c->leaves[k]].value = c->h_leafval[k];
   return QR_OK;
 }
 
-
-// ------------------------------------------------------------------------------------------
-// Device-driven leaf-wise growth (qr_grow.cuh): the host only keeps launches queued.
-// ------------------------------------------------------------------------------------------
-static int enqueue_device_round(qr_ctx *c, uint32_t round, bool root) {
-  const uint32_t F = (uint32_t) c->F;
-  const uint32_t mt = c->max_tasks;
-  RoundHdr *hdr = c->d_hdr + (round & 1u), *next_hdr = c->d_hdr + ((round + 1u) & 1u);
-  NodeTask *tasks = c->d_tasks + (size_t) (round & 1u) * mt, *next_tasks = c->d_tasks + (size_t) ((round + 1u) & 1u) * mt;
-  const size_t smem = (size_t) c->fpp * c->max_thr * 12;
-  const bool use_smem = smem <= 200 * 1024;
-  const uint32_t want_slices = c->h_grow->want_slices;
-  if (root) {
-    const uint32_t slices = std::max<uint32_t>(1, ((uint32_t) c->N + c->root_dpb - 1) / c->root_dpb);
-    QR_LAUNCH(c, PH_HIST, prep_slots_kernel, dim3(std::max<uint32_t>(1, std::min<uint32_t>(32, (c->ncells + 1023) / 1024)), 1),
-              256, 0, tasks, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_root_cnt);
-    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
-      using B = decltype(tag);
-      if (use_smem)
-        QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, false>), dim3(slices, c->npanels), kHistThreads, smem, tasks, 1u,
-                  c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq_c);
-      else
-        QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, false>), dim3(slices, c->npanels), kHistThreads, 0, tasks, 1u,
-                  c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq_c);
-      return QR_OK;
-    }));
-  } else {
-    const uint32_t part_grid = (uint32_t) ((c->N + kPartItems - 1) / kPartItems) + mt;
-    const uint32_t hist_grid = want_slices + mt;
-    c->part_epoch++;
-    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
-      using B = decltype(tag);
-      QR_LAUNCH(c, PH_PARTITION, partition_onepass_kernel<B>, part_grid, 256, 0, tasks, 0u, c->d_panels, c->N,
-                c->d_ids[0], c->d_ids[1], c->d_ids[0], c->d_ids[1], c->d_part_status, c->d_ticket, 0u, c->part_epoch,
-                c->d_hist_sum, c->d_hist_cnt, c->ncells, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq, c->d_lamq_c,
-                c->d_lcount, (uint32_t *) nullptr);
-      if (use_smem)
-        QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true>), dim3(hist_grid, c->npanels), kHistThreads, smem, tasks, 0u,
-                  c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq_c);
-      else
-        QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true>), dim3(hist_grid, c->npanels), kHistThreads, 0, tasks, 0u,
-                  c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (const RoundHdr *) hdr, c->pack, (const long long *) c->d_lamq_c);
-      return QR_OK;
-    }));
+// FAST mode: one pass over node_of_doc.  Every node id maps to the leaf it ended up under: a node that was
+// expanded speculatively but never popped by the replay is a leaf whose documents already carry its
+// children's ids.
+static int fit_leaves_fast(qr_ctx *c) {
+  const size_t nl = c->leaves.size(), nn = c->nodes.size();
+  PhaseTimer pt(c, PH_LEAF);
+  uint16_t *lut = reinterpret_cast<uint16_t *>(c->h_leafmeta);
+  unsigned long long *leafn = reinterpret_cast<unsigned long long *>(c->h_leafmeta + c->leafn_off);
+  for (size_t i = 0; i < nn; ++i) lut[i] = 0xffffu;
+  for (size_t k = 0; k < nl; ++k) { lut[c->leaves[k]] = (uint16_t) k; leafn[k] = c->nodes[c->leaves[k]].res.n; }
+  for (size_t i = 1; i < nn; ++i)   // parents precede their children
+    if (lut[i] == 0xffffu && lut[c->nodes[i].parent] != 0xffffu) lut[i] = lut[c->nodes[i].parent];
+  QR_CUDA(cudaMemcpyAsync(c->d_leafmeta, c->h_leafmeta, c->leafn_off + nl * sizeof(unsigned long long),
+                          cudaMemcpyHostToDevice, c->stream));
+  const uint16_t *d_lut = reinterpret_cast<const uint16_t *>(c->d_leafmeta);
+  const unsigned long long *d_leafn = reinterpret_cast<const unsigned long long *>(c->d_leafmeta + c->leafn_off);
+  // warps per block: as many as the per-warp accumulator tables leave room for
+  const size_t lut_bytes = (nn * 2 + 15) & ~(size_t) 15;
+  uint32_t wpb = 8;
+  while (wpb > 1 && (size_t) wpb * (nl + 32) * 16 + lut_bytes > 160 * 1024) wpb >>= 1;
+  const size_t smem = (size_t) wpb * (nl + 32) * 16 + lut_bytes;
+  if (smem > 200 * 1024) { set_error("a tree of %zu leaves exceeds the leaf-fit kernel's shared-memory budget", nl); return QR_ELIMIT; }
+  if (smem > c->leaf_smem_set) {
+    QR_CUDA(cudaFuncSetAttribute(leaf_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024)));
+    c->leaf_smem_set = std::max<size_t>(smem, 48 * 1024);
   }
-  QR_LAUNCH(c, PH_SCAN, finalize_kernel<false>, dim3(fin_blocks(F), root ? 1u : mt), kFinWarps * 32, 0, tasks,
-            c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_thr_off, F, c->p.minleafsupport, c->d_qexp, c->d_fbest_score,
-            c->d_fbest_t, c->d_fbest_lc, c->d_totals, c->d_sq128, c->d_partials, c->d_task_done, c->d_res,
-            (volatile uint32_t *) nullptr, 0u, (const RoundHdr *) hdr, c->pack, PeerView{});
-  QR_LAUNCH(c, PH_SCAN, grow_step_kernel, 1, kGrowThreads, c->grow_smem, c->d_grow, hdr, next_hdr, tasks, next_tasks,
-            c->d_res, c->d_ticket, c->d_segs, c->d_grow_out);
+  const uint32_t blocks = (uint32_t) ((c->N + (size_t) wpb * kLeafWarpDocs - 1) / ((size_t) wpb * kLeafWarpDocs));
+  if ((size_t) blocks * nl > c->leaf_part_cap) {
+    if (c->d_leaf_partials) cudaFree(c->d_leaf_partials);
+    c->d_leaf_partials = nullptr;
+    c->leaf_part_cap = (size_t) blocks * nl * 2;
+    QR_TRY(dev_alloc(&c->d_leaf_partials, c->leaf_part_cap));
+  }
+  const double *w = c->lambda ? c->d_weight : nullptr;
+  QR_LAUNCH(c, PH_LEAF, leaf_node_kernel, blocks, wpb * 32, smem, c->d_node, d_lut, (uint32_t) nn, (uint32_t) nl, c->d_lambda,
+            w, c->N, c->d_leaf_partials, c->d_leaf_of_doc);
+  QR_LAUNCH(c, PH_LEAF, leaf_reduce_kernel, (unsigned) ((nl + 7) / 8), 256, 0, c->d_leaf_partials, blocks, (uint32_t) nl,
+            d_leafn, c->lambda, c->d_leafsum, c->d_leafval);
+  if (c->comm) QR_TRY(comm_leaf_values(c, (uint32_t) nl));
+  QR_CUDA(cudaMemcpyAsync(c->h_leafval, c->d_leafval, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  QR_CUDA(cudaStreamSynchronize(c->stream));
+  for (size_t k = 0; k < nl; ++k) c->nodes[c->leaves[k]].value = c->h_leafval[k];
   return QR_OK;
 }
 
-static int fit_leafwise_device(qr_ctx *c, bool want_nodes) {
-  constexpr uint32_t kAhead = 2;   // rounds kept queued beyond the last completed grow_step
-  GrowOut *go = c->h_grow_out;
-  go->steps = 0; go->done = 0; go->error = 0;
-  std::atomic_thread_fence(std::memory_order_seq_cst);
-  c->root_dpb = pick_hist_dpb(c, c->N);
-  QR_LAUNCH(c, PH_HIST, grow_init_kernel, 1, 1, 0, c->d_grow, c->d_hdr, c->d_tasks, (uint32_t) c->N, c->root_dpb, c->d_ticket);
-  QR_TRY(enqueue_device_round(c, 0, true));
-  uint32_t enq = 0;   // growth rounds enqueued (the round after grow_step number enq + 1)
-  uint64_t spins = 0;
-  for (;;) {
-    while (!go->done && enq >= go->steps + kAhead) {
-      if ((++spins & 0xfffff) == 0) {
-        cudaError_t e = cudaStreamQuery(c->stream);
-        if (e != cudaSuccess && e != cudaErrorNotReady) { set_error("tree growth failed: %s", cudaGetErrorString(e)); return QR_ECUDA; }
-        if (e == cudaSuccess && !go->done && enq >= go->steps + kAhead) {
-          set_error("internal: growth rounds finished without progress (steps %u, enqueued %u)", go->steps, enq);
-          return QR_ECUDA;
-        }
-      }
-    }
-    if (go->done) break;
-    ++enq;
-    QR_TRY(enqueue_device_round(c, enq, false));
-  }
-  std::atomic_thread_fence(std::memory_order_acquire);
-  if (go->error) {
-    set_error(go->error == 1 ? "internal: histogram pool exhausted" : go->error == 2 ? "internal: node table full"
-                                                                                    : "internal: histogram slice table full");
-    return QR_ECUDA;
-  }
-  c->rho = go->rho; c->sigma = go->sigma; c->beta = go->beta; c->nsplits = go->nsplits; c->nrounds = go->nrounds;
-  // leaf outputs (rt.cc:165-207): the segments were written by the last grow_step
-  const RoundHdr *hdr = c->d_hdr + ((go->steps) & 1u);   // header written by the last step
-  {
-    PhaseTimer pt(c, PH_LEAF);
-    const size_t maxleaves = std::max<size_t>(c->p.nleaves, 1);
-    const uint32_t leaf_grid = (uint32_t) ((c->N + kLeafItems - 1) / kLeafItems + maxleaves);
-    const double *w = c->lambda ? c->d_weight : nullptr;
-    QR_LAUNCH(c, PH_LEAF, leaf_partial_kernel, leaf_grid, 256, 0, c->d_segs, 0u, c->d_ids[0], c->d_ids[1], c->d_lambda, w,
-              c->d_leaf_partials, c->d_leaf_of_doc, hdr);
-    QR_LAUNCH(c, PH_LEAF, leaf_final_kernel, (unsigned) ((maxleaves + 63) / 64), 64, 0, c->d_segs, 0u, c->d_leaf_partials,
-              c->lambda, c->d_leafsum, c->d_leafval, hdr);
-  }
-  c->nodes.clear();
-  c->leaves.clear();
-  if (want_nodes) {   // the caller wants the tree on the host
-    const uint32_t nn = go->nnodes, nl = go->nleaves;
-    QR_CUDA(cudaMemcpyAsync(c->h_nodes, c->d_nodes, nn * sizeof(DevNode), cudaMemcpyDeviceToHost, c->stream));
-    QR_CUDA(cudaMemcpyAsync(c->h_leafval, c->d_leafval, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    QR_CUDA(cudaStreamSynchronize(c->stream));
-    c->nodes.resize(nn);
-    for (uint32_t i = 0; i < nn; ++i) {
-      const DevNode &d = c->h_nodes[i];
-      HostNode &h = c->nodes[i];
-      h.lo = d.lo; h.n = d.n; h.buf = d.buf; h.hist = -1; h.left = d.left; h.right = d.right;
-      h.expanded = d.expanded != 0; h.pushed = d.pushed != 0; h.res = d.res;
-    }
-    collect_leaves(c, 0);
-    for (size_t k = 0; k < c->leaves.size(); ++k) c->nodes[c->leaves[k]].value = c->h_leafval[k];
-  }
-  return QR_OK;
-}
+static int fit_leaves(qr_ctx *c) { return c->exact ? fit_leaves_exact(c) : fit_leaves_fast(c); }
 
 static int fit_tree(qr_ctx *c, qr_flat_tree *out) {
   // release histograms still held by the previous tree
@@ -764,24 +859,8 @@ static int fit_tree(qr_ctx *c, qr_flat_tree *out) {
   c->nrounds = 0;
   c->has_tree = false;
 
+  ++g_ktrace_tree;
   QR_TRY(prepare_fixed_point(c));
-  if (c->device_growth && !c->profiling) {
-    QR_TRY(fit_leafwise_device(c, out != nullptr));
-    c->has_tree = true;
-    if (out) {
-      const uint32_t nn = count_reachable(c, 0);
-      if (out->capacity < nn) { set_error("qr_flat_tree capacity %u < %u nodes", out->capacity, nn); return QR_EINVAL; }
-      uint32_t next = 0;
-      flatten(c, 0, out, &next);
-      out->nnodes = nn;
-      out->nleaves = (uint32_t) c->leaves.size();
-    }
-    return QR_OK;
-  }
-  if (c->device_growth) {   // the device-driven path leaves the partition ticket counter at an arbitrary value
-    QR_CUDA(cudaMemsetAsync(c->d_ticket, 0, sizeof(uint32_t), c->stream));
-    c->ticket_base = 0;
-  }
   QR_TRY(build_root(c));
   QR_TRY(c->oblivious ? fit_oblivious(c) : fit_leafwise(c));
 
@@ -806,9 +885,9 @@ static int fit_tree(qr_ctx *c, qr_flat_tree *out) {
       cudaEventElapsedTime(&d, g_trace.ev[4 * r + 2], g_trace.ev[4 * r + 3]);
       if (r + 1 < nr) cudaEventElapsedTime(&g, g_trace.ev[4 * r + 3], g_trace.ev[4 * r + 4]);
       tp += a; th += b; tf += d; tg += g;
-      if (getenv("QR_TRACE_ROUNDS")) fprintf(stderr, "[trace] round %2zu: partition %6.1f hist %6.1f finalize %6.1f gap-to-next %6.1f us\n", r, a * 1e3, b * 1e3, d * 1e3, g * 1e3);
+      if (getenv("QR_TRACE_ROUNDS")) fprintf(stderr, "[trace] round %2zu: route %6.1f hist %6.1f scan %6.1f gap-to-next %6.1f us\n", r, a * 1e3, b * 1e3, d * 1e3, g * 1e3);
     }
-    fprintf(stderr, "[trace] %zu rounds: partition %.0f hist %.0f finalize %.0f gaps %.0f us\n", nr, tp * 1e3, th * 1e3, tf * 1e3, tg * 1e3);
+    fprintf(stderr, "[trace] %zu rounds: route %.0f hist %.0f scan %.0f gaps %.0f us\n", nr, tp * 1e3, th * 1e3, tf * 1e3, tg * 1e3);
     g_trace.used = 0;
   }
 

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/r02_pytest_gpu.log 2>&1
+tail -8 gpurun_out/r02_pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1; tail -3 gpurun_out/r02_smoke.log
+timeout 300 python scripts/longrun.py 400 > gpurun_out/r02_longrun.log 2>&1; tail -8 gpurun_out/r02_longrun.log
+ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 12000 -c 400 --csv --log-file gpurun_out/r02_launches_late.csv python scripts/longrun.py 200 > gpurun_out/r02_ncu_longrun.log 2>&1
+python scripts/summarize_launches.py gpurun_out/r02_launches_late.csv | head -30

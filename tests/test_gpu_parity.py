@@ -353,63 +353,6 @@ def test_errors_are_reported():
         api.Trainer(x, l, off[:-1])
 
 
-@pytest.mark.parametrize("algo,leaves,minls", [("LAMBDAMART", 64, 1), ("MART", 31, 5), ("LAMBDAMART", 2, 1),
-                                                ("LAMBDAMART", 200, 1)])
-def test_device_growth_equals_host_growth(algo, leaves, minls, monkeypatch):
-    """The device-side replay of RegressionTree::fit's heap (qr_grow.cuh) takes the decisions of the
-    host-side replay (qr_tree_host.cuh) statement for statement: identical trees, leaf outputs,
-    doc->leaf maps and scores, bit for bit."""
-    x, l, off = common.dataset(n=30000, f=23, q=300)
-    runs = []
-    for host in (False, True):
-        if host:
-            monkeypatch.delenv("QR_DEVICE_GROWTH", raising=False)
-        else:
-            monkeypatch.setenv("QR_DEVICE_GROWTH", "1")
-        with api.Trainer(x, l, off, algo=algo, nleaves=leaves, minleafsupport=minls, cutoff=10,
-                         hist_mode=api.HIST_FAST) as tr:
-            trees, metrics = [], []
-            for m in range(6):
-                # alternate the two entry styles: with and without the tree copied to the host
-                tree, metric = tr.boost_iteration(want_tree=(m % 2 == 0))
-                trees.append(tree)
-                metrics.append(metric)
-            runs.append((trees, metrics, tr.get_scores(), tr.get_leaf_assignment(), tr.last_tree_stats(),
-                         tr.last_tree_rounds()))
-    (ta, ma, sa, la, sta, ra), (tb, mb, sb, lb, stb, rb) = runs
-    assert ma == mb
-    assert np.array_equal(sa, sb) and np.array_equal(la, lb)
-    assert sta == stb and ra == rb
-    for a, b in zip(ta, tb):
-        assert (a is None) == (b is None)
-        if a is not None:
-            for k in ("feature", "threshold_idx", "left", "right", "value", "count"):
-                assert np.array_equal(a[k], b[k]), k
-
-
-@pytest.mark.parametrize("fuse_partition", [False, True])
-def test_fused_round_kernel_equals_three_kernels(fuse_partition, monkeypatch):
-    """qr_round_kernel.cuh chains histogram -> split scan (and optionally partition) inside one launch per
-    growth round; same arithmetic as the separate kernels, so identical trees and scores."""
-    x, l, off = common.dataset(n=30000, f=23, q=300)
-    runs = []
-    for fused in (False, True):
-        monkeypatch.delenv("QR_FUSED_ROUNDS", raising=False)
-        monkeypatch.delenv("QR_FUSE_PARTITION", raising=False)
-        if fused:
-            monkeypatch.setenv("QR_FUSED_ROUNDS", "1")
-            if fuse_partition:
-                monkeypatch.setenv("QR_FUSE_PARTITION", "1")
-        with api.Trainer(x, l, off, algo="LAMBDAMART", nleaves=64, cutoff=10, hist_mode=api.HIST_FAST) as tr:
-            trees = [tr.boost_iteration()[0] for _ in range(5)]
-            runs.append((trees, tr.get_scores(), tr.get_leaf_assignment()))
-    (ta, sa, la), (tb, sb, lb) = runs
-    assert np.array_equal(sa, sb) and np.array_equal(la, lb)
-    for a, b in zip(ta, tb):
-        for k in ("feature", "threshold_idx", "left", "right", "value", "count"):
-            assert np.array_equal(a[k], b[k]), k
-
-
 def _edge_cases():
     rng = np.random.default_rng(77)
     cases = {}
