@@ -28,6 +28,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+PARITY_TREES = 5   # trees of the job whose digest every bench line carries
 WORKLOAD = dict(n_docs=1_000_000, n_features=136, n_queries=10_000, leaves=64, cutoff=10,
                 shrinkage=0.1, nthresholds=0, minls=1, seed=20260102)
 METRIC = "lambdamart_trees_per_sec"
@@ -94,11 +95,94 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_shard(rank, world, w=WORKLOAD):
+def tree_digest(trees):
+    """SHA-1 over (split feature, threshold index, node size) of the given trees, in pre-order.  Histogram sums are
+    exact integers in the benchmarked mode, so the digest is the same on 1, 2, 4 and 8 GPUs."""
+    import hashlib
+    h = hashlib.sha1()
+    for t in trees:
+        for k in ("feature", "threshold_idx", "count"):
+            h.update(np.ascontiguousarray(t[k]).astype(np.int64).tobytes())
+    return h.hexdigest()
+
+
+def oracle_first_trees(x, labels, qoff, ntrees, w=WORKLOAD):
+    """The first trees of the same job grown by the unmodified reference (oracle/_ref) on the host."""
+    from oracle import pyref
+    if not pyref.available():
+        return None
+    pyref.set_threads(cpu_threads())
+    out = []
+    with pyref.RefSession("LAMBDAMART", x, labels, qoff, ntrees=ntrees + 1, shrinkage=w["shrinkage"],
+                          nthresholds=w["nthresholds"], nleaves=w["leaves"], minleafsupport=w["minls"],
+                          cutoff=w["cutoff"]) as s:
+        s.init()
+        for m in range(ntrees):
+            s.compute_pseudoresponses()
+            s.fit_tree(True)
+            out.append(s.tree(m))
+    return out
+
+
+def _same_tree(a, b):
+    return bool(all(len(a[k]) == len(b[k]) and np.array_equal(np.asarray(a[k]).astype(np.int64), np.asarray(b[k]).astype(np.int64))
+                    for k in ("feature", "threshold_idx", "count")))
+
+
+def stagewise_vs_reference(x, labels, qoff, device, first_trees, ntrees=2, w=WORKLOAD):
+    from oracle import pyref
+    from quickrank_b200 import api
+    if not pyref.available():
+        return {"kind": "oracle/_ref not built", "trees_compared": 0}
+    pyref.set_threads(cpu_threads())
+    out = {"kind": "oracle/_ref (unmodified reference sources)", "trees_compared": ntrees,
+           "how": "every tree fitted from the reference's pseudo-responses at the reference's scores"}
+    kw = dict(algo="LAMBDAMART", nleaves=w["leaves"], minleafsupport=w["minls"], nthresholds=w["nthresholds"],
+              cutoff=w["cutoff"], shrinkage=w["shrinkage"], device=device)
+    with pyref.RefSession("LAMBDAMART", x, labels, qoff, ntrees=ntrees + 1, shrinkage=w["shrinkage"],
+                          nthresholds=w["nthresholds"], nleaves=w["leaves"], minleafsupport=w["minls"],
+                          cutoff=w["cutoff"]) as ref, \
+            api.Trainer(x, labels, qoff, hist_mode=api.HIST_FAST, **kw) as tf, \
+            api.Trainer(x, labels, qoff, hist_mode=api.HIST_REFERENCE, **kw) as te:
+        ref.init()
+        eq_fast, eq_exact, leaf_fast, leaf_exact, lam_err, free = [], [], [], [], [], []
+        for m in range(ntrees):
+            scores = ref.get_scores()
+            ref.compute_pseudoresponses()
+            lam, wt = ref.get_gradients()
+            ref.fit_tree(True)
+            want = ref.tree(m)
+            lv = np.asarray(want["feature"]) < 0
+            free.append(_same_tree(first_trees[m], want))
+            for tr_, eq, le in ((tf, eq_fast, leaf_fast), (te, eq_exact, leaf_exact)):
+                tr_.set_scores(scores)
+                if tr_ is tf:
+                    tr_.compute_pseudoresponses()
+                    gl, _gw = tr_.get_pseudoresponses()
+                    lam_err.append(float(np.max(np.abs(gl - lam)) / np.max(np.abs(lam))))
+                tr_.set_pseudoresponses(lam, wt)
+                got = tr_.fit_regressor_on_gradient()
+                same = _same_tree(got, want)
+                eq.append(same)
+                if same:
+                    d = np.abs(np.asarray(got["value"])[lv] - np.asarray(want["value"])[lv])
+                    le.append(float(np.max(d / np.maximum(np.abs(np.asarray(want["value"])[lv]), 1e-300))))
+                tr_.update_modelscores()
+    out["split_indices_and_counts_equal"] = {"QR_HIST_REFERENCE": eq_exact, "QR_HIST_FAST": eq_fast,
+                                             "QR_HIST_FAST free-running (own pseudo-responses)": free}
+    out["max_rel_leaf_output_error"] = {"QR_HIST_REFERENCE": max(leaf_exact) if leaf_exact else None,
+                                        "QR_HIST_FAST": max(leaf_fast) if leaf_fast else None}
+    out["max_rel_pseudo_response_error"] = max(lam_err) if lam_err else None
+    return out
+
+
+def make_shard(rank, world, w=WORKLOAD, keep_global=False):
     """The rank's contiguous range of queries of the one global dataset, balanced by document count
     (lambdas need whole queries: lambdamart.cc:71-151)."""
     from quickrank_b200 import synth
     x, labels, qoff = synth.make_dataset(w["n_docs"], w["n_features"], w["n_queries"], seed=w["seed"])
+    if keep_global:
+        make_shard.global_data = (x, labels, qoff)
     if world == 1:
         return x, labels, qoff
     from quickrank_b200.sharding import query_shards
@@ -161,7 +245,7 @@ def run_ours(args):
     if api.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback on the hot path)")
     w = WORKLOAD
-    x, labels, qoff = make_shard(rank, world)
+    x, labels, qoff = make_shard(rank, world, keep_global=(rank == 0))
 
     comm = None
     if world > 1:
@@ -189,39 +273,75 @@ def run_ours(args):
             torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") ----
-    # The workload is a 1000-tree run.  During its first ~25 trees nearly every query still has tied
-    # scores (documents that shared every leaf so far) and ranking takes the sequential std::sort
-    # replica; afterwards (97% of the run) ties are gone.  `--settle` untimed trees put the timed
-    # region in that steady state; --settle 0 times the start of the run instead.
-    # clocks are sampled from the settle trees on: the same workload runs before and inside the timed
-    # region, so every sample is a sample under load even when the timed region itself is short
+    # The workload is a 1000-tree run and its trees are not alike: the first ~25 trees rank queries full of tied
+    # scores (sequential sort replica) and need ~11 growth rounds; from tree ~150 on LambdaMART's gradients grow
+    # chain-like trees of ~32 rounds, which is what 85% of the run consists of.  The timed region (exactly
+    # --steps trees after --settle + --warmup untimed ones) therefore sits in that deep regime (--settle 300);
+    # `windows` reports the same measurement early (tree 30) and late (tree 900) in the run, and `e2e` is the
+    # whole job.  Clocks are sampled from the first tree on: the same workload runs before and inside the timed
+    # region, so every sample is a sample under load.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.settle):
+    windows = []
+
+    def timed_window(first_tree, ntrees):
+        barrier()
+        tr.timer_start()
+        rr = rho = sigma = 0.0
+        for _ in range(ntrees):
+            tr.boost_iteration(want_tree=False, want_metric=True)
+            r, s_, _ns = tr.last_tree_stats()
+            rho += r
+            sigma += s_
+            rr += tr.last_tree_rounds()[0]
+        ms_ = tr.timer_stop()
+        barrier()
+        if dist is not None:
+            import torch
+            t_ = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms_ = float(t_.item())
+        windows.append({"first_tree": first_tree, "trees": ntrees, "ms_per_tree": round(ms_ / ntrees, 4),
+                        "trees_per_s": round(1000.0 * ntrees / ms_, 2), "growth_rounds_per_tree": round(rr / ntrees, 1)})
+        return ms_, rho / ntrees, sigma / ntrees
+
+    done = 0
+    # parity: the first trees of the job, digest identical for every N (and equal to the reference's, below)
+    first_trees = []
+    for _ in range(PARITY_TREES):
+        tree, _m = tr.boost_iteration(want_tree=True, want_metric=True)
+        first_trees.append(tree)
+        done += 1
+    early = min(30, args.settle)
+    while done < early:
         tr.boost_iteration(want_tree=False, want_metric=True)
+        done += 1
+    if args.settle >= early + args.steps:
+        timed_window(done, args.steps)
+        done += args.steps
+    while done < args.settle:
+        tr.boost_iteration(want_tree=False, want_metric=True)
+        done += 1
     for _ in range(max(args.warmup, 3)):
         tr.boost_iteration(want_tree=False, want_metric=True)
+        done += 1
     launches0 = tr.launch_count()
-    barrier()
-    tr.timer_start()
-    rho_sum = sigma_sum = 0.0
-    for _ in range(args.steps):
-        tr.boost_iteration(want_tree=False, want_metric=True)
-        r, s, _ns = tr.last_tree_stats()
-        rho_sum += r
-        sigma_sum += s
-    ms = tr.timer_stop()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    first_timed = done
+    ms, rho_mean, sigma_mean = timed_window(done, args.steps)
+    done += args.steps
     launches = tr.launch_count() - launches0
-    if dist is not None:
-        import torch
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    main_window = windows[-1]
+    if args.late_window and done + args.steps <= args.late_window + args.steps:
+        while done < args.late_window:
+            tr.boost_iteration(want_tree=False, want_metric=True)
+            done += 1
+        timed_window(done, args.steps)
+        done += args.steps
+    clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = 1000.0 / ms_per_step  # trees/s of the whole job (all ranks grow the same tree)
+    rho_sum, sigma_sum = rho_mean * args.steps, sigma_mean * args.steps
 
     # ---- end to end: the whole job through the C ABI, starting from HOST buffers ----
     # A new context is created from the host feature matrix (host->device copy of the dataset, threshold
@@ -294,6 +414,34 @@ def run_ours(args):
         roofline["shared_atomics"] = {"error": str(e)}
 
     tr.close()
+
+    # ---- parity block: digest of the job's first trees + the same trees from the unmodified reference ----
+    parity = {"trees": PARITY_TREES, "digest_sha1": tree_digest(first_trees),
+              "digest_of": "(split feature, threshold index, node size) of the first %d trees, pre-order; fixed-point "
+                           "histograms make it identical for every number of GPUs" % PARITY_TREES}
+    reference_mode = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # Against the UNMODIFIED reference (oracle/_ref), stage by stage: each tree is fitted from the reference's own
+        # pseudo-responses at the reference's own scores, so nothing but the tree fit is compared.  REFERENCE mode must
+        # reproduce the reference bit for bit; FAST mode (the benchmarked one) may differ only inside exact-arithmetic
+        # ties, which tests/test_gpu_parity_baseline_shapes.py audits node by node on this very dataset.
+        parity["reference"] = stagewise_vs_reference(x, labels, qoff, local_rank, first_trees)
+    # ---- the bit-exact mode (QR_HIST_REFERENCE: reference accumulation order, single GPU) next to FAST ----
+    if world == 1 and args.reference_mode_trees > 0:
+        tre = api.Trainer(x, labels, qoff, algo="LAMBDAMART", nleaves=w["leaves"], minleafsupport=w["minls"],
+                          nthresholds=w["nthresholds"], cutoff=w["cutoff"], shrinkage=w["shrinkage"],
+                          hist_mode=api.HIST_REFERENCE, device=local_rank)
+        for i in range(2):
+            tre.boost_iteration(want_tree=False, want_metric=True)
+        tre.timer_start()
+        for _ in range(args.reference_mode_trees):
+            tre.boost_iteration(want_tree=False, want_metric=True)
+        ems = tre.timer_stop()
+        tre.close()
+        reference_mode = {"hist_mode": "QR_HIST_REFERENCE (per-bin FP64 sums in the reference's order: bit-exact trees)",
+                          "trees_per_s": round(1000.0 * args.reference_mode_trees / ems, 2),
+                          "ms_per_tree": round(ems / args.reference_mode_trees, 3),
+                          "trees_timed": args.reference_mode_trees, "first_tree_timed": 2}
     scoring = run_scoring(args, x, rank, world, local_rank, dist, barrier)
 
     out = None
@@ -311,7 +459,8 @@ def run_ours(args):
                        "docs_per_gpu": int(len(labels)), "global_docs": w["n_docs"],
                        "hist_mode": "fixed-point int64 (FAST)", "parallelism": "query-sharded dp%d" % world,
                        "histogram_exchange": exchange,
-                       "trees_before_timed_region": args.settle + max(args.warmup, 3),
+                       "trees_before_timed_region": first_timed,
+                       "growth_rounds_per_tree_in_timed_region": main_window["growth_rounds_per_tree"],
                        "l2": "inputs larger than L2 (136 MB bin matrix + 40 MB state per step)"},
             "clocks": clocks,
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT,
@@ -327,6 +476,9 @@ def run_ours(args):
                                "the peers' histogram pools is inside")},
             "init_s": round(init_s, 3), "init_h2d_bytes": int(x.nbytes + labels.nbytes + qoff.nbytes),
             "gpu_launches": int(launches),
+            "windows": windows,
+            "parity": parity,
+            "reference_mode": reference_mode,
             "roofline": roofline,
             "scoring": scoring,
         }
@@ -413,7 +565,9 @@ def reference_scoring(x, sample):
     from oracle import pyref
     from quickrank_b200 import modelxml
     nthreads = cpu_threads()
-    os.environ.setdefault("OMP_NUM_THREADS", str(nthreads))
+    os.environ["OMP_NUM_THREADS"] = str(nthreads)   # (a launcher such as torchrun exports OMP_NUM_THREADS=1)
+    if pyref.available():
+        nthreads = pyref.set_threads(nthreads)
     trees, weights = scoring_ensemble(x.shape[1])
     xs = np.ascontiguousarray(x[:sample])
     if pyref.available():
@@ -438,6 +592,11 @@ def reference_scoring(x, sample):
             "sample": "%d of the %d documents, %d trees (model load excluded)" % (len(xs), x.shape[0], SCORING["trees"])}
 
 
+REF_BUILD = ("oracle/_ref: the unmodified reference sources, g++ -O3 -march=x86-64-v3 -fopenmp (the reference's Release "
+             "flags are -O3 -march=native -fopenmp -D_GLIBCXX_PARALLEL: x86-64-v3 so that the library also runs on "
+             "the GPU box, no libstdc++ parallel mode, which only affects std::sort of >= 1000 elements)")
+
+
 def cpu_threads():
     try:
         return len(os.sched_getaffinity(0))
@@ -450,8 +609,9 @@ def reference_steps(x, labels, qoff, warmup, steps, w=WORKLOAD):
     (oracle/_ref) when it is built, else the C restatement (oracle/qr_oracle.c)."""
     from oracle import pyref
     nthreads = cpu_threads()
-    os.environ.setdefault("OMP_NUM_THREADS", str(nthreads))
+    os.environ["OMP_NUM_THREADS"] = str(nthreads)   # (a launcher such as torchrun exports OMP_NUM_THREADS=1)
     if pyref.available():
+        nthreads = pyref.set_threads(nthreads)       # what the OpenMP runtime will actually use
         s = pyref.RefSession("LAMBDAMART", x, labels, qoff, ntrees=warmup + steps + 1,
                              shrinkage=w["shrinkage"], nthresholds=w["nthresholds"], nleaves=w["leaves"],
                              minleafsupport=w["minls"], cutoff=w["cutoff"])
@@ -494,7 +654,8 @@ def cpu_baseline(args, quick=True):
     n = w["n_docs"]
     x, labels, qoff = synth.make_dataset(n, w["n_features"], w["n_queries"], seed=w["seed"])
     sec_per_tree, init_s, kind, nthreads = reference_steps(x, labels, qoff, 1, 3)
-    return {"value": round(1.0 / sec_per_tree, 4), "unit": UNIT, "cores": nthreads, "kind": kind,
+    return {"value": round(1.0 / sec_per_tree, 4), "unit": UNIT, "cores": nthreads, "omp_max_threads": nthreads,
+            "kind": kind, "build": REF_BUILD if kind == "reference" else "oracle/qr_oracle.c (restatement)",
             "sample": "full config-2 workload (%d docs), 1 warm-up + 3 timed boosting iterations; init "
                       "(transpose, argsort, binning) %.1f s excluded as in the reference's own Training Time"
                       % (n, init_s)}
@@ -519,7 +680,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "LambdaMART 64 leaves, synthetic %d docs x %d feat x %d queries, NDCG@10 "
                                "(BASELINE.json configs[1]) on the host CPU" % (w["n_docs"], w["n_features"], w["n_queries"])},
-        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": nthreads, "kind": kind,
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": nthreads, "omp_max_threads": nthreads,
+                         "kind": kind, "build": REF_BUILD if kind == "reference" else "oracle/qr_oracle.c (restatement)",
                          "sample": "full workload, %d timed iterations (capped at 20), init %.1f s excluded" % (steps, init_s)},
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "scoring": {"metric": "ensemble_docs_per_sec", "value": ref_sc["value"], "unit": "docs/s", "cpu_baseline": ref_sc},
@@ -535,8 +697,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-trees", type=int, default=1000,
                     help="boosting iterations of the end-to-end job (BASELINE.json configs[1]: 1000 trees)")
-    ap.add_argument("--settle", type=int, default=30,
-                    help="untimed boosting iterations before the warm-up (see run_ours)")
+    ap.add_argument("--settle", type=int, default=300,
+                    help="untimed boosting iterations before the warm-up: the timed region sits in the deep-tree "
+                         "regime most of the 1000-tree job consists of (see run_ours)")
+    ap.add_argument("--late-window", type=int, default=900,
+                    help="first tree of the extra timed window late in the run (0: none)")
+    ap.add_argument("--reference-mode-trees", type=int, default=5,
+                    help="trees timed in the bit-exact QR_HIST_REFERENCE mode (0: skip)")
     args = ap.parse_args()
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:

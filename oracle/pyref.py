@@ -87,8 +87,16 @@ def lib():
         L.qref_ndcg_jacobian.argtypes = [fp, dp, u64, u64, dp]
         L.qref_sort_indices.argtypes = [dp, u64, C.POINTER(u64)]
         L.qref_radix_argsort.argtypes = [fp, u64, C.POINTER(u64)]
+        L.qref_set_threads.argtypes = [C.c_int]
+        L.qref_max_threads.restype = C.c_int
         _lib = L
     return _lib
+
+
+def set_threads(n: int) -> int:
+    """Sets the OpenMP team size of the reference's loops; returns what the runtime will use."""
+    lib().qref_set_threads(int(n))
+    return int(lib().qref_max_threads())
 
 
 def _p(a, t):

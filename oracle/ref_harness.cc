@@ -9,6 +9,7 @@
 //
 // Nothing here re-implements reference arithmetic: every number returned is
 // produced by reference code.
+#include <omp.h>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -481,5 +482,10 @@ void qref_radix_argsort(const float *v, uint64_t n, uint64_t *dest) {
   auto r = idx_radixsort(v, n);
   for (uint64_t i = 0; i < n; ++i) dest[i] = r[i];
 }
+
+// OpenMP team size of the reference's loops (a launcher such as torchrun exports OMP_NUM_THREADS=1: the
+// benchmark's reference legs set the team size explicitly and report what the runtime then uses)
+void qref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int qref_max_threads(void) { return omp_get_max_threads(); }
 
 }  // extern "C"

@@ -351,7 +351,7 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
                  const uint32_t *__restrict__ cids, const long long *__restrict__ clamq,
                  const long long *__restrict__ lamq, const uint32_t *__restrict__ thr_off, uint32_t F,
                  unsigned long long *hsum, uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials,
-                 uint32_t stride, ulonglong2 *sq_acc, unsigned long long *ktrace) {
+                 uint32_t stride, ulonglong2 *sq_acc, unsigned long long *ktrace, unsigned long long *kspan) {
   if (pack.n) tasks = pack.t;
   constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
   extern __shared__ __align__(1024) unsigned char hist_smem[];
@@ -360,6 +360,13 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
   __shared__ U128 s_sq[kHistThreads / 32];
   const uint32_t kblock = blockIdx.y * gridDim.x + blockIdx.x;
   kstamp(ktrace, kblock, 0);
+  // profiling (bench.py roofline): first block start .. last block end of this launch on the device's own
+  // clock; CUDA events around a launch on an idle stream also time the launch itself
+  if (kspan != nullptr && threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    atomicMin(kspan, t0);
+  }
   if (threadIdx.x == 0) s_task = find_task_by(tasks, ntasks, blockIdx.x, true);
   __syncthreads();
   const uint32_t task = s_task;
@@ -383,6 +390,11 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
   const bool empty = begin >= seglen;
   if (empty) {
     if (!ACC && p == 0 && threadIdx.x == 0) sq_partials[blockIdx.x] = make_ulonglong2(0ull, 0ull);
+    if (kspan != nullptr && threadIdx.x == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicMax(kspan + 1, t1);
+    }
     return;
   }
   const uint32_t end = min(seglen, begin + dpb);
@@ -514,6 +526,14 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
     }
   }
   kstamp(ktrace, kblock, 3);
+  if (kspan != nullptr) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      atomicMax(kspan + 1, t1);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------

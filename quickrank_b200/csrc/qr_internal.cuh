@@ -171,6 +171,7 @@ struct qr_ctx {
   uint64_t phase_launches[qr::kNumPhases] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;   // around each histogram-kernel launch while profiling
+  unsigned long long *d_kspan = nullptr;          // [2] first block start / last block end of the profiled launch (ns)
   double histk_ms = 0;
   uint64_t histk_launches = 0;
   double histk_docs = 0;                          // documents accumulated by those launches

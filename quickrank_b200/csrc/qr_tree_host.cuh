@@ -284,14 +284,20 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
                     SMEMF ? smem : 0, (const NodeTask *) c->d_tasks, k, c->pack, counts, (const uint4 *) c->d_panels, c->N, \
                     (const uint32_t *) c->d_cids, (const long long *) c->d_clamq, (const long long *) c->d_lamq, \
                     (const uint32_t *) c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128 + c->round_sq_off, \
-                    c->max_thr, c->d_sq_acc, kt);                                                             \
+                    c->max_thr, c->d_sq_acc, kt, kspan);                                                      \
     else                                                                                                      \
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF, ACCF>), dim3(total_slices, c->npanels), kHistThreads, \
                 SMEMF ? smem : 0, c->d_tasks, k, c->pack, counts, c->d_panels, c->N, c->d_cids, c->d_clamq,   \
                 c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128 + c->round_sq_off, \
-                c->max_thr, c->d_sq_acc, kt);                                                                 \
+                c->max_thr, c->d_sq_acc, kt, kspan);                                                          \
   } while (0)
-      if (c->profiling) cudaEventRecord(c->ev_k0, c->stream);
+      unsigned long long *kspan = nullptr;
+      if (c->profiling) {
+        if (!c->d_kspan) QR_TRY(dev_alloc(&c->d_kspan, 2));
+        kspan = c->d_kspan;
+        QR_CUDA(cudaMemsetAsync(kspan, 0xff, sizeof(unsigned long long), c->stream));
+        QR_CUDA(cudaMemsetAsync(kspan + 1, 0, sizeof(unsigned long long), c->stream));
+      }
       QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
         using B = decltype(tag);
         if (use_smem) {
@@ -305,11 +311,10 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
       }));
 #undef QR_HIST_LAUNCH
       if (c->profiling) {
-        cudaEventRecord(c->ev_k1, c->stream);
-        cudaEventSynchronize(c->ev_k1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, c->ev_k0, c->ev_k1);
-        c->histk_ms += ms;
+        unsigned long long span[2] = {0, 0};
+        QR_CUDA(cudaMemcpyAsync(span, kspan, sizeof(span), cudaMemcpyDeviceToHost, c->stream));
+        QR_CUDA(cudaStreamSynchronize(c->stream));
+        if (span[1] > span[0]) c->histk_ms += (double) (span[1] - span[0]) * 1e-6;
         c->histk_launches++;
         c->histk_docs += built_docs;
       }
@@ -427,11 +432,13 @@ static int init_root_counts(qr_ctx *c) {
     if (use_smem)
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true, false>), dim3(t.hist_nblk, c->npanels), kHistThreads, smem, c->d_tasks, 1u,
                 c->pack, c->d_counts, c->d_panels, c->N, c->d_cids, c->d_clamq, c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (ulonglong2 *) nullptr, (unsigned long long *) nullptr);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (ulonglong2 *) nullptr, (unsigned long long *) nullptr,
+                (unsigned long long *) nullptr);
     else
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true, false>), dim3(t.hist_nblk, c->npanels), kHistThreads, 0, c->d_tasks, 1u,
                 c->pack, c->d_counts, c->d_panels, c->N, c->d_cids, c->d_clamq, c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
-                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (ulonglong2 *) nullptr, (unsigned long long *) nullptr);
+                c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (ulonglong2 *) nullptr, (unsigned long long *) nullptr,
+                (unsigned long long *) nullptr);
     return QR_OK;
   }));
   QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
