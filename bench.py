@@ -195,11 +195,13 @@ def make_shard(rank, world, w=WORKLOAD, keep_global=False):
 def load_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
     (profiles/hist_full_summary.json, written by scripts/ncu_summary.py)."""
-    p = os.path.join(ROOT, "profiles", "hist_full_summary.json")
+    p = os.path.join(ROOT, "profiles", "r02_hist_full_summary.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "hist_full_summary.json")
     if os.path.exists(p):
         with open(p) as fh:
             d = json.load(fh)
-        return d.get("dram_bytes_per_launch"), "profiles/hist_full_summary.json (%s)" % d.get("capture", "")
+        return d.get("dram_bytes_per_launch"), "profiles/%s (%s)" % (os.path.basename(p), d.get("capture", ""))
     return None, "no ncu capture committed"
 
 
@@ -552,10 +554,22 @@ def run_scoring(args, x, rank, world, local_rank, dist, barrier):
                 "d2h_bytes_per_step": int(n * 8), "host_equals_device_path": same},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
-                     "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                     "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), **score_traffic(),
                      "note": "the walk is bound by shared-memory wavefronts (one 8-byte node + one code per level at "
-                             "data-dependent addresses), not by HBM; see profiles/ for the ncu capture"},
+                             "data-dependent addresses), not by HBM: l1tex__data_pipe_lsu_wavefronts_mem_shared at 75% of "
+                             "its peak, DRAM at 0.2% (profiles/r02_score_codes_counters.txt)"},
     }
+
+
+def score_traffic():
+    """DRAM bytes of one score_codes_kernel launch from the committed `ncu --set full` capture."""
+    p = os.path.join(ROOT, "profiles", "r02_score_codes_full_summary.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return {"traffic": d.get("dram_bytes_per_launch"),
+                "traffic_source": "profiles/r02_score_codes_full_summary.json (%s)" % d.get("capture", "")}
+    return {"traffic": None, "traffic_source": "no ncu capture committed"}
 
 
 def reference_scoring(x, sample):
@@ -688,6 +702,274 @@ def run_reference(args):
     }
 
 
+# ----------------------------------------------------------------------------------------------------------
+# The other BASELINE.json configurations (`--config 3|4`).  The default line stays configs[1] (config 2).
+# ----------------------------------------------------------------------------------------------------------
+CONFIG4 = dict(n_docs=4_000_000, n_features=220, n_queries=40_000, depth=6, cutoff=10, shrinkage=0.1, nthresholds=0,
+               minls=1, seed=20260104, trees=2000)
+CONFIG3 = dict(n_docs=10_000_000, n_features=700, trees=5000, leaves=64, seed=13, slice_docs=1_000_000)
+
+
+def _dist_setup():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(v):
+        if dist is None:
+            return v
+        import torch
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    return rank, world, local_rank, dist, barrier, maxr
+
+
+def run_config4(args):
+    """BASELINE.json configs[3]: oblivious LambdaMART depth 6 on 4M docs x 220 features x 40k queries, documents
+    sharded by query over the ranks, the per-level histograms of every node all-reduced over NVLink peer memory."""
+    from quickrank_b200 import api, synth
+    rank, world, local_rank, dist, barrier, maxr = _dist_setup()
+    w = dict(CONFIG4)
+    if args.docs:
+        w["n_docs"], w["n_queries"] = args.docs, max(1, args.docs // 100)
+    x, labels, qoff = synth.make_dataset(w["n_docs"], w["n_features"], w["n_queries"], seed=w["seed"])
+    gx = x[:400_000] if rank == 0 else None   # the reference leg's bounded sample (whole queries: see below)
+    if world > 1:
+        from quickrank_b200.sharding import query_shards
+        q0, q1 = query_shards(qoff, world)[rank]
+        d0, d1 = int(qoff[q0]), int(qoff[q1])
+        gq = qoff
+        gl = labels
+        x, labels, qoff = (np.ascontiguousarray(x[d0:d1]), np.ascontiguousarray(labels[d0:d1]),
+                           (qoff[q0:q1 + 1] - qoff[q0]).astype(np.uint64))
+    else:
+        gq, gl = qoff, labels
+    comm = None
+    if world > 1:
+        import torch
+        idt = torch.zeros(api.COMM_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        comm = (bytes(idt.cpu().numpy().tobytes()), rank, world)
+    kw = dict(algo="OBVLAMBDAMART", treedepth=w["depth"], minleafsupport=w["minls"], nthresholds=w["nthresholds"],
+              cutoff=w["cutoff"], shrinkage=w["shrinkage"], hist_mode=api.HIST_FAST, device=local_rank, comm=comm)
+    tr = api.Trainer(x, labels, qoff, **kw)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    first = []
+    for _ in range(3):
+        t_, _m = tr.boost_iteration(want_tree=True, want_metric=True)
+        first.append(t_)
+    for _ in range(max(args.warmup, 3)):
+        tr.boost_iteration(want_tree=False, want_metric=True)
+    l0 = tr.launch_count()
+    barrier()
+    tr.timer_start()
+    for _ in range(args.steps):
+        tr.boost_iteration(want_tree=False, want_metric=True)
+    ms = maxr(tr.timer_stop())
+    barrier()
+    launches = tr.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # roofline of the histogram kernel, timed on the device clock
+    prof = min(args.steps, 5)
+    tr.set_profiling(True)
+    tr.hist_kernel_time(reset=True)
+    for _ in range(prof):
+        tr.boost_iteration(want_tree=False, want_metric=True)
+    hk_ms, hk_launches, hk_docs = tr.hist_kernel_time()
+    tr.set_profiling(False)
+    tr.close()
+    # end to end: context from host buffers + e2e trees, tree and metric back to the host every iteration
+    e2e_trees = min(args.e2e_trees, 100)
+    barrier()
+    t0 = time.perf_counter()
+    tr2 = api.Trainer(x, labels, qoff, **kw)
+    d2h = 0
+    for _ in range(e2e_trees):
+        tr2.compute_pseudoresponses()
+        tree = tr2.fit_regressor_on_gradient(want_tree=True)
+        tr2.update_modelscores()
+        tr2.evaluate_dataset()
+        d2h += sum(tree[k].nbytes for k in tree if hasattr(tree[k], "nbytes")) + 8
+    e2e_s = maxr(time.perf_counter() - t0)
+    tr2.close()
+    peak, peak_src = load_peaks()
+    f = w["n_features"]
+    n_local = len(labels)
+    alg = hk_docs * (f + 8) + max(hk_docs - n_local * prof, 0) * 4
+    ms_per_step = ms / args.steps
+    out = None
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = reference_config4(gx, gl, gq, w)
+        out = {"metric": "obv_lambdamart_trees_per_sec", "value": round(1000.0 / ms_per_step, 3), "unit": UNIT,
+               "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "Oblivious LambdaMART depth %d, synthetic %d docs x %d feat x %d queries, NDCG@10 "
+                                      "(BASELINE.json configs[3])" % (w["depth"], w["n_docs"], f, w["n_queries"]),
+                          "docs_per_gpu": int(n_local), "parallelism": "query-sharded dp%d" % world,
+                          "l2": "inputs larger than L2 (%d MB bin matrix per GPU)" % (n_local * ((f + 15) // 16) * 16 >> 20)},
+               "clocks": clocks,
+               "e2e": {"value": round(e2e_trees / e2e_s, 3), "unit": UNIT, "trees": e2e_trees, "job_s": round(e2e_s, 3),
+                       "h2d_bytes_per_step": int((x.nbytes + labels.nbytes + qoff.nbytes) / e2e_trees),
+                       "d2h_bytes_per_step": int(d2h / e2e_trees)},
+               "gpu_launches": int(launches),
+               "parity": {"trees": 3, "digest_sha1": tree_digest(first)},
+               "roofline": {"bound": "hbm", "kernel": "hist_limb_kernel", "achieved": round(alg / (hk_ms * 1e-3) / 1e9, 1),
+                            "peak": peak, "unit": "GB/s", "frac": round(alg / (hk_ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                            "peak_source": peak_src, "us_per_launch": round(hk_ms * 1e3 / max(hk_launches, 1), 2),
+                            "kernel_ms_per_tree": round(hk_ms / prof, 4),
+                            "kernel_share_of_step": round(hk_ms / prof / ms_per_step, 3),
+                            "note": "bound by the shared-memory atomic rate (16 lanes/clk/SM), DESIGN.md section 4"}}
+        if cpu:
+            out["cpu_baseline"] = cpu
+    if dist is not None:
+        dist.destroy_process_group()
+    return out
+
+
+def reference_config4(x, labels, qoff, w):
+    """The reference's OBVLAMBDAMART on a bounded sample (the first whole queries within 400k documents)."""
+    from oracle import pyref
+    if not pyref.available():
+        return None
+    nthreads = pyref.set_threads(cpu_threads())
+    q = int(np.searchsorted(qoff, len(x), side="right") - 1)
+    n = int(qoff[q])
+    xs, ls, qs = np.ascontiguousarray(x[:n]), np.ascontiguousarray(labels[:n]), np.ascontiguousarray(qoff[:q + 1])
+    with pyref.RefSession("OBVLAMBDAMART", xs, ls, qs, ntrees=4, shrinkage=w["shrinkage"], nthresholds=w["nthresholds"],
+                          treedepth=w["depth"], minleafsupport=w["minls"], cutoff=w["cutoff"]) as s:
+        s.init()
+        s.compute_pseudoresponses(); s.fit_tree(True); s.evaluate()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            s.compute_pseudoresponses(); s.fit_tree(True); s.evaluate()
+        dt = (time.perf_counter() - t0) / 2
+    # the reference's cost per tree is linear in the documents: scaled to the full workload
+    full = dt * w["n_docs"] / n
+    return {"value": round(1.0 / full, 4), "unit": UNIT, "cores": nthreads, "omp_max_threads": nthreads, "kind": "reference",
+            "build": REF_BUILD,
+            "sample": "%d of the %d documents (%d whole queries), 1 warm-up + 2 timed boosting iterations at %.2f s each, "
+                      "scaled linearly to the full workload" % (n, w["n_docs"], q, dt)}
+
+
+def run_config3(args):
+    """BASELINE.json configs[2]: a 5000-tree x 64-leaf ensemble over 10M docs x 700 features, documents sharded over
+    the ranks, no collective.  The documents stream through qr_score_dataset from page-locked host memory in slices
+    (upload of slice k+1 on a copy stream under the encode + walk of slice k); synthetic: each rank streams its share
+    of the 10M documents as repeated passes over one 1M-document buffer."""
+    import torch
+    from quickrank_b200 import api, synth
+    rank, world, local_rank, dist, barrier, maxr = _dist_setup()
+    w = dict(CONFIG3)
+    if args.docs:
+        w["n_docs"] = args.docs
+    f = w["n_features"]
+    trees, weights = synth.random_ensemble(w["trees"], w["leaves"], f, seed=w["seed"])
+    local_docs = w["n_docs"] // world
+    slice_docs = min(local_docs, w["slice_docs"])
+    passes = max(1, local_docs // slice_docs)
+    x, _l, _q = synth.make_dataset(slice_docs, f, max(1, slice_docs // 100), seed=20260103 + rank)
+    sc = api.Scorer(trees, weights, f, device=local_rank)
+    xp = torch.from_numpy(x).pin_memory()
+    outp = torch.empty(slice_docs, dtype=torch.float64).pin_memory()
+    xd = xp.cuda()
+    outd = torch.empty(slice_docs, dtype=torch.float64, device="cuda")
+    for _ in range(max(args.warmup, 3) if slice_docs <= 200_000 else 1):
+        sc.score_dataset_device(xd.data_ptr(), slice_docs, outd.data_ptr())
+    sc.sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = sc.launch_count()
+    barrier()
+    sc.timer_start()
+    for _ in range(passes):
+        sc.score_dataset_device(xd.data_ptr(), slice_docs, outd.data_ptr())
+    ms = maxr(sc.timer_stop())
+    barrier()
+    launches = sc.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    xh, oh = xp.numpy(), outp.numpy()
+    sc.score_dataset(xh[:4096], out=oh[:4096])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(passes):
+        sc.score_dataset(xh, out=oh)
+    e2e_s = maxr(time.perf_counter() - t0)
+    same = bool(np.array_equal(oh, outd.cpu().numpy()))
+    sc.close()
+    docs = passes * slice_docs * world
+    peak, peak_src = load_peaks()
+    alg = passes * slice_docs * (4 * f + 8)
+    out = None
+    if rank == 0:
+        out = {"metric": "ensemble_docs_per_sec", "value": round(docs / (ms * 1e-3), 1), "unit": "docs/s", "n_gpus": world,
+               "steps": passes, "warmup": 3, "ms_per_step": round(ms / passes, 3), "higher_is_better": True,
+               "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+               "config": {"workload": "%d-tree x %d-leaf random ensemble over %d docs x %d feat (BASELINE.json configs[2]), "
+                                      "documents sharded over ranks, no collective; a step = one pass over a %d-document slice"
+                                      % (w["trees"], w["leaves"], docs, f, slice_docs),
+                          "docs_per_gpu": int(passes * slice_docs), "l2": "inputs larger than L2 (%d MB of rows per pass)" % (x.nbytes >> 20)},
+               "doc_trees_per_sec": round(docs * w["trees"] / (ms * 1e-3), 1),
+               "clocks": clocks,
+               "e2e": {"value": round(docs / e2e_s, 1), "unit": "docs/s", "h2d_bytes_per_step": int(x.nbytes),
+                       "d2h_bytes_per_step": int(slice_docs * 8), "host_equals_device_path": same,
+                       "pcie_bound_docs_per_s_at_50GBs": round(50e9 / (4 * f) * world, 1)},
+               "gpu_launches": int(launches),
+               "roofline": {"bound": "hbm", "kernel": "score_codes_kernel", "achieved": round(alg / (ms * 1e-3) / 1e9, 1),
+                            "peak": peak, "unit": "GB/s", "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), **score_traffic(),
+                            "peak_source": peak_src,
+                            "note": "the walk visits one 8-byte node per level and tree in shared memory: bound by "
+                                    "shared-memory wavefronts (75% of their peak in the ncu capture), not HBM"}}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = reference_scoring_ensemble(xh, 20_000, trees, weights, w["trees"])
+    if dist is not None:
+        dist.destroy_process_group()
+    return out
+
+
+def reference_scoring_ensemble(x, sample, trees, weights, ntrees):
+    import tempfile
+    from oracle import pyref
+    from quickrank_b200 import modelxml
+    if not pyref.available():
+        return None
+    nthreads = pyref.set_threads(cpu_threads())
+    xs = np.ascontiguousarray(x[:sample])
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "ensemble.xml")
+        modelxml.write_model(path, trees, weights)
+        t0 = time.perf_counter()
+        pyref.score_with_model(path, xs[:1])
+        load_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        pyref.score_with_model(path, xs)
+        dt = max(time.perf_counter() - t0 - load_s, 1e-9)
+    return {"value": round(len(xs) / dt, 1), "unit": "docs/s", "cores": nthreads, "omp_max_threads": nthreads,
+            "kind": "reference", "build": REF_BUILD,
+            "sample": "%d documents, %d trees (model load excluded)" % (len(xs), ntrees)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -704,8 +986,17 @@ def main():
                     help="first tree of the extra timed window late in the run (0: none)")
     ap.add_argument("--reference-mode-trees", type=int, default=5,
                     help="trees timed in the bit-exact QR_HIST_REFERENCE mode (0: skip)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json configuration: 2 (default, the headline), 3 (ensemble scoring 10M x 700), "
+                         "4 (oblivious LambdaMART 4M x 220)")
+    ap.add_argument("--docs", type=int, default=0, help="override the document count of --config 3|4")
     args = ap.parse_args()
-    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if args.config == 4 and args.impl == "ours":
+        out = run_config4(args)
+    elif args.config == 3 and args.impl == "ours":
+        out = run_config3(args)
+    else:
+        out = run_reference(args) if args.impl == "reference" else run_ours(args)
     if out is not None:
         print(json.dumps(out), flush=True)
 

@@ -550,15 +550,34 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
 // with it, is among them; candidates are compared in ascending threshold order with a strict '>'
 // (rt.cc:272-291), ties across threads go to the smaller threshold.
 // ------------------------------------------------------------------------------------------
+// bounded spin on a peer's flag: a peer that never arrives (crashed process) must not hang the GPU; the
+// timeout is reported through `err` (mapped host memory) and surfaces as QR_ECOMM on the host
+__device__ __forceinline__ void wait_flag_or_report(const uint32_t *p, uint32_t epoch, uint32_t *err) {
+  const long long t0 = clock64();
+  while ((int32_t) (ld_flag(p) - epoch) < 0) {
+    if (clock64() - t0 > 40000000000ll) {   // ~20 s
+      if (err) { *reinterpret_cast<volatile uint32_t *>(err) = 1u; __threadfence_system(); }
+      return;
+    }
+  }
+}
+
 constexpr uint32_t kPubThreads = 128;    // 4 warps; kPubCPT consecutive bins per thread: one pass covers 384 thresholds.
 constexpr uint32_t kPubWarps = kPubThreads / 32;   // Small blocks: 8+ are resident per SM, so a round of up to ~8 node
 constexpr int kPubCPT = 3;                         // expansions (136 features each) is ONE wave of blocks.
 
-template <bool COUNT>
+// PEER (sharded training, small rounds): every rank accumulated the built child's LOCAL histogram in a staging
+// slot; after its own histogram kernel has completed, the first block tells the peers "my staging slots of this
+// round are complete", every block waits for the same word from all peers, and the loads add the W staging slots
+// (NVLink loads from the peers' pools).  Integer sums: every rank obtains the same totals and takes the same
+// decision.  Nothing is written to a peer and the staging slots alternate between two sets by round, so one flag
+// barrier per round is enough.
+template <bool COUNT, bool PEER>
 __global__ void __launch_bounds__(kPubThreads, 6)
 scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ TaskPack pack, unsigned long long *hsum,
                 uint32_t *hcnt, uint32_t ncells, const uint32_t *__restrict__ thr_off, uint32_t F,
-                const __grid_constant__ ScanOut out) {
+                const __grid_constant__ ScanOut out, const ulonglong2 *__restrict__ sq128, uint32_t *host_err,
+                const __grid_constant__ PeerView pv) {
   if (pack.n) tasks = pack.t;
   const uint32_t f = blockIdx.x, task = blockIdx.y;
   const NodeTask &t = tasks[task];
@@ -601,20 +620,61 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
   const double inv = ldexp(1.0, -*out.qexp);
   pdl_wait();
   kstamp(out.ktrace, kb, 1);
-  // the bins were accumulated with atomics by blocks on other SMs: read them from L2
+  const int W = (PEER && pv.world > 1 && t.stage1) ? pv.world : 1;   // PEER = false: compiled out
+  const bool own_raw = out.sq_acc != nullptr;   // one GPU: the raw slot is this kernel's to clear
+  if (W > 1) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid < (uint32_t) W && tid != (uint32_t) pv.rank)
+      st_flag(pv.peer_flags[tid] + pv.rank, pv.epoch);
+    if (tid < (uint32_t) W && tid != (uint32_t) pv.rank) wait_flag_or_report(pv.flags + tid, pv.epoch, host_err);
+    __syncthreads();
+  }
+  // the bins were accumulated with atomics by blocks on other SMs (or GPUs): read them from L2
 #pragma unroll
   for (int i = 0; i < kPubCPT; ++i) {
     const bool in = k0 + i < cells;
     s[i] = in ? __ldcg(Rs + k0 + i) : 0ull;
     c[i] = in ? __ldcg(Cc + k0 + i) : 0u;
   }
-  if (f == 0 && tid == 0) {
-    // exact squares of the built child: every p == 0 histogram slice has added its part
-    unsigned long long *acc = reinterpret_cast<unsigned long long *>(out.sq_acc + task);
-    const unsigned long long lo = __ldcg(acc), hi = __ldcg(acc + 1);
-    acc[0] = 0ull; acc[1] = 0ull;
-    const double inv2 = ldexp(1.0, -2 * *out.qexp);
-    out.sq_built[task] = ((double) hi * 18446744073709551616.0 + (double) lo) * inv2;
+  if (W > 1) {
+    for (int pr = 0; pr < W; ++pr) {
+      if (pr == pv.rank) continue;
+#pragma unroll
+      for (int i = 0; i < kPubCPT; ++i) {
+        if (k0 + i < cells) {
+          s[i] += *reinterpret_cast<const volatile unsigned long long *>(pv.sum[pr] + roff + k0 + i);
+          if (COUNT && pv.with_counts) c[i] += *reinterpret_cast<const volatile uint32_t *>(pv.cnt[pr] + roff + k0 + i);
+        }
+      }
+    }
+  }
+  if (f == 0 && warp == 0) {
+    // exact squares of the built child
+    U128 tot{0ull, 0ull};
+    if (own_raw) {   // one GPU: every p == 0 histogram slice has added its part to the accumulator
+      if (lane == 0) {
+        unsigned long long *acc = reinterpret_cast<unsigned long long *>(out.sq_acc + task);
+        tot.lo = __ldcg(acc); tot.hi = __ldcg(acc + 1);
+        acc[0] = 0ull; acc[1] = 0ull;
+      }
+    } else {         // sharded: the slices' partials of every rank (or the all-reduced total in the first slice)
+      const uint32_t items = (uint32_t) W * t.hist_nblk;
+      for (uint32_t it = lane; it < items; it += 32) {
+        const uint32_t pr = it / t.hist_nblk, i = it - pr * t.hist_nblk;
+        const ulonglong2 *src = (W > 1 ? pv.sq[pr] : sq128) + t.hist_blk0 + i;
+        const volatile unsigned long long *v = reinterpret_cast<const volatile unsigned long long *>(src);
+        const unsigned long long lo = v[0], hi = v[1];
+        u128_add(tot, lo, hi);
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long ol = __shfl_xor_sync(0xffffffffu, tot.lo, o);
+        const unsigned long long oh = __shfl_xor_sync(0xffffffffu, tot.hi, o);
+        u128_add(tot, ol, oh);
+      }
+    }
+    if (lane == 0) {
+      const double inv2 = ldexp(1.0, -2 * *out.qexp);
+      out.sq_built[task] = ((double) tot.hi * 18446744073709551616.0 + (double) tot.lo) * inv2;
+    }
   }
 
   // phase 1: inclusive prefix over the bins of the built child -> slotB; the raw cells are cleared
@@ -628,11 +688,20 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
         const bool in = kk + i < cells;
         s[i] = in ? __ldcg(Rs + kk + i) : 0ull;
         c[i] = in ? __ldcg(Cc + kk + i) : 0u;
+        if (W > 1 && in) {
+          for (int pr = 0; pr < W; ++pr) {
+            if (pr == pv.rank) continue;
+            s[i] += *reinterpret_cast<const volatile unsigned long long *>(pv.sum[pr] + roff + kk + i);
+            if (COUNT && pv.with_counts) c[i] += *reinterpret_cast<const volatile uint32_t *>(pv.cnt[pr] + roff + kk + i);
+          }
+        }
       }
     }
+    if (own_raw) {
 #pragma unroll
-    for (int i = 0; i < kPubCPT; ++i)
-      if (kk + i < cells) { Rs[kk + i] = 0ull; if (COUNT) Rc[kk + i] = 0u; }
+      for (int i = 0; i < kPubCPT; ++i)
+        if (kk + i < cells) { Rs[kk + i] = 0ull; if (COUNT) Rc[kk + i] = 0u; }
+    }
 #pragma unroll
     for (int i = 1; i < kPubCPT; ++i) { s[i] += s[i - 1]; c[i] += c[i - 1]; }
     unsigned long long run_s = s[kPubCPT - 1];
@@ -849,18 +918,6 @@ constexpr uint32_t kScanWarps = kScanThreads / 32;
 // every rank obtains the same totals.  Nothing is written to a peer and the staging slots alternate
 // between two sets by round, so one flag barrier per round is enough.
 // ------------------------------------------------------------------------------------------
-
-// bounded spin on a peer's flag: a peer that never arrives (crashed process) must not hang the GPU; the
-// timeout is reported through `err` (mapped host memory) and surfaces as QR_ECOMM on the host
-__device__ __forceinline__ void wait_flag_or_report(const uint32_t *p, uint32_t epoch, uint32_t *err) {
-  const long long t0 = clock64();
-  while ((int32_t) (ld_flag(p) - epoch) < 0) {
-    if (clock64() - t0 > 40000000000ll) {   // ~20 s
-      if (err) { *reinterpret_cast<volatile uint32_t *>(err) = 1u; __threadfence_system(); }
-      return;
-    }
-  }
-}
 
 template <bool PEER, bool EXACT>
 __global__ void __launch_bounds__(kScanThreads)

@@ -108,6 +108,7 @@ struct qr_ctx {
   uint32_t max_nodes = 0;         // node ids are 16 bits
   // one GPU: the split scan hands per-feature candidates to the host, which reduces over features
   bool fused_scan = false;
+  bool pub_ok = false;              // scan_pub_kernel usable (fixed-point mode, F <= 65535): one GPU, and sharded over peer memory
   qr::ChildOut *h_out = nullptr, *d_out_mapped = nullptr;           // [max_tasks][2] mapped pinned: the round's results
   qr::DevCand *d_cand = nullptr;                                    // [max_tasks][2][F] per-feature winners
   double2 *d_noderec = nullptr;                                     // [max_tasks][2]
@@ -188,5 +189,5 @@ struct qr_ctx {
   bool round_fused = false;                 // this round's all-reduce happens inside scan_kernel
   uint32_t round_parity = 0, round_sq_off = 0;   // staging set / offset into d_sq128 of this round
   bool peer_fused = true;                   // QR_PEER_FUSED=0: always the stand-alone exchange kernel
-  uint32_t oneshot_max = 4;                 // fuse when (world - 1) * tasks <= this (QR_PEER_ONESHOT_MAX)
+  uint32_t oneshot_max = 12;                // fuse while (world - 1) * tasks * histogram bytes <= this many MB (QR_PEER_ONESHOT_MAX)
 };

@@ -503,13 +503,16 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   if (c->fused_scan) {
     QR_CUDA(cudaMemset(c->d_hist_sum + (size_t) c->nslots * c->ncells, 0, mt * c->ncells * sizeof(unsigned long long)));
     QR_CUDA(cudaMemset(c->d_hist_cnt + (size_t) c->nslots * c->ncells, 0, mt * c->ncells * sizeof(uint32_t)));
+    QR_TRY(dev_alloc(&c->d_sq_acc, mt));
+    QR_CUDA(cudaMemset(c->d_sq_acc, 0, mt * sizeof(ulonglong2)));
+  }
+  c->pub_ok = !c->exact && F <= 65535;   // scan_pub_kernel's records pack the feature in 16 bits
+  if (c->pub_ok) {
     QR_CUDA(cudaHostAlloc((void **) &c->h_out, mt * 2 * sizeof(ChildOut), cudaHostAllocMapped));
     QR_CUDA(cudaHostGetDevicePointer((void **) &c->d_out_mapped, c->h_out, 0));
     memset(c->h_out, 0, mt * 2 * sizeof(ChildOut));   // (tag 0 = not written)
     QR_TRY(dev_alloc(&c->d_cand, mt * 2 * F));
     QR_TRY(dev_alloc(&c->d_noderec, mt * 2));
-    QR_TRY(dev_alloc(&c->d_sq_acc, mt));
-    QR_CUDA(cudaMemset(c->d_sq_acc, 0, mt * sizeof(ulonglong2)));
   }
   QR_TRY(dev_alloc(&c->d_partials, mt));
   QR_TRY(dev_alloc(&c->d_sq_built, mt));

@@ -129,7 +129,10 @@ static void begin_exchange_round(qr_ctx *c, uint32_t k) {
   if (!c->comm || comm_transport(c->comm) != 2) return;
   c->round_parity = c->xround++ & 1u;
   c->round_sq_off = c->round_parity * kSqRegion;
-  c->round_fused = c->peer_fused && (uint32_t) (comm_world(c->comm) - 1) * k <= c->oneshot_max;
+  // one-shot (every rank reads the W-1 other copies itself, one flag barrier) while that is at most a few MB per
+  // rank; beyond, the stand-alone reduce-scatter + all-gather moves 2(W-1)/W of the payload instead of W-1 times it
+  const size_t oneshot_bytes = (size_t) (comm_world(c->comm) - 1) * k * c->ncells * 12;
+  c->round_fused = c->peer_fused && oneshot_bytes <= (size_t) c->oneshot_max << 20;
 }
 static uint32_t stage_of(const qr_ctx *c, uint32_t j) {
   if (c->fused_scan) return 1u + (uint32_t) c->stage_slot0 + j;   // one GPU: the raw slot of task j (cleared by its scan)
@@ -185,6 +188,10 @@ static int collect_fused_round(qr_ctx *c, uint32_t k) {
   }
   hstamp(6);
   hstamp(7);
+  if (c->h_err && *(volatile uint32_t *) c->h_err) {
+    set_error("histogram exchange timed out waiting for a peer rank (is every rank still alive?)");
+    return QR_ECOMM;
+  }
   return QR_OK;
 }
 
@@ -323,28 +330,34 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
   }
   QR_TRACE_MARK(c);
   hstamp(3);
-  if (c->fused_scan) {
-    // one GPU: the scan publishes per-feature candidates, the host reduces over features; launched behind the
-    // histogram kernel with programmatic stream serialization (resident and waiting when that kernel ends)
+  // scan_pub_kernel: one GPU, and sharded training over peer memory (the NCCL fallback keeps scan_kernel)
+  const bool pub = c->fused_scan || (c->pub_ok && c->comm && comm_transport(c->comm) == 2);
+  if (pub) {
+    // the scan reduces over features on the device and publishes tagged records the host polls; launched behind
+    // the histogram kernel with programmatic stream serialization (resident and waiting when that kernel ends)
     PhaseTimer pt(c, PH_SCAN);
     c->round_id++;
     ScanOut so{};
     so.out = c->d_out_mapped; so.cand = c->d_cand; so.node = c->d_noderec; so.sq_built = c->d_sq_built;
-    so.done = c->d_task_done; so.sq_acc = c->d_sq_acc; so.root_cnt = c->d_root_cnt; so.qexp = c->d_qexp;
+    so.done = c->d_task_done; so.sq_acc = c->fused_scan ? c->d_sq_acc : nullptr; so.root_cnt = c->d_root_cnt; so.qexp = c->d_qexp;
     so.round_id = c->round_id; so.minls = c->p.minleafsupport; so.ktrace = ktrace_buffer(c, 2);
     const bool static_counts = root && c->d_root_cnt != nullptr;
-    const bool pdl = !c->profiling && !g_trace_on && g_pdl_on;
-#define QR_SCANPUB_LAUNCH(COUNTF)                                                                             \
+    // (PDL only directly behind the histogram kernel: a stand-alone exchange kernel in between is not PDL-aware)
+    const bool pdl = !c->profiling && !g_trace_on && g_pdl_on && (!c->comm || c->round_fused);
+    PeerView pv{};
+    if (c->round_fused) comm_peer_view(c, !static_counts, &pv);
+    const ulonglong2 *sqp = c->d_sq128 + c->round_sq_off;
+#define QR_SCANPUB_LAUNCH(COUNTF, PEERF)                                                                      \
   do {                                                                                                        \
     if (pdl)                                                                                                  \
-      QR_LAUNCH_PDL(c, PH_SCAN, scan_pub_kernel<COUNTF>, dim3(F, k), dim3(kPubThreads), 0, (const NodeTask *) c->d_tasks, \
-                    c->pack, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const uint32_t *) c->d_thr_off, F, so);  \
+      QR_LAUNCH_PDL(c, PH_SCAN, (scan_pub_kernel<COUNTF, PEERF>), dim3(F, k), dim3(kPubThreads), 0, (const NodeTask *) c->d_tasks, \
+                    c->pack, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const uint32_t *) c->d_thr_off, F, so, sqp, c->d_err_mapped, pv); \
     else                                                                                                      \
-      QR_LAUNCH(c, PH_SCAN, scan_pub_kernel<COUNTF>, dim3(F, k), kPubThreads, 0, c->d_tasks, c->pack, c->d_hist_sum, \
-                c->d_hist_cnt, c->ncells, c->d_thr_off, F, so);                                               \
+      QR_LAUNCH(c, PH_SCAN, (scan_pub_kernel<COUNTF, PEERF>), dim3(F, k), kPubThreads, 0, c->d_tasks, c->pack, c->d_hist_sum, \
+                c->d_hist_cnt, c->ncells, c->d_thr_off, F, so, sqp, c->d_err_mapped, pv);                     \
   } while (0)
-    if (static_counts) QR_SCANPUB_LAUNCH(false);
-    else QR_SCANPUB_LAUNCH(true);
+    if (c->round_fused) { if (static_counts) QR_SCANPUB_LAUNCH(false, true); else QR_SCANPUB_LAUNCH(true, true); }
+    else { if (static_counts) QR_SCANPUB_LAUNCH(false, false); else QR_SCANPUB_LAUNCH(true, false); }
 #undef QR_SCANPUB_LAUNCH
     hstamp(4);
     QR_TRACE_MARK(c);

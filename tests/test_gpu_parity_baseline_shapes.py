@@ -5,8 +5,8 @@
 * config 2: 1 000 000 docs x 136 features x 10 000 queries, LAMBDAMART 64 leaves (the benchmarked workload,
   bench.py WORKLOAD, same seed) — the first 3 trees.
 
-Each boosting iteration starts from the reference's own scores: the GPU's pseudo-responses are compared with the
-reference's (<= 1e-13 relative), then the tree is fitted from the REFERENCE's pseudo-responses:
+Each boosting iteration starts from the reference's own scores: the GPU's pseudo-responses must equal the
+reference's bit for bit, then the tree is fitted from the REFERENCE's pseudo-responses:
 QR_HIST_REFERENCE must reproduce the reference's tree bit for bit (split feature / threshold index, counts,
 leaf outputs), QR_HIST_FAST up to audited exact-arithmetic ties (qr_testlib.audit_tree) with leaf outputs within
 1e-5 relative; NDCG@10 within 1e-5 relative.  The restatement (oracle/qr_oracle.c, bit-identical to the reference:
@@ -50,8 +50,9 @@ def _stagewise(x, l, off, leaves, ntrees, mode, max_near):
             glam, gw = tr.get_pseudoresponses()
             assert np.max(np.abs(glam - lam)) <= 1e-13 * np.max(np.abs(lam)), "lambda, tree %d" % m
             assert np.max(np.abs(gw - w)) <= 1e-13 * np.max(np.abs(w)), "weights, tree %d" % m
-            if m == 0:   # all scores 0: exp(0) = 1, nothing left to the math library
-                assert np.array_equal(glam, lam) and np.array_equal(gw, w)
+            # bit for bit at every iteration: the kernel's exp() is glibc's algorithm restated (qr_kernels.cuh, exp_lambda),
+            # everything else on the path is IEEE arithmetic in the reference's order
+            assert np.array_equal(glam, lam) and np.array_equal(gw, w), "pseudo-responses differ in the last bits, tree %d" % m
             tr.set_pseudoresponses(lam, w)
             got = tr.fit_regressor_on_gradient()
             ref.fit_tree(True)
