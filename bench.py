@@ -886,8 +886,8 @@ def run_config3(args):
     f = w["n_features"]
     trees, weights = synth.random_ensemble(w["trees"], w["leaves"], f, seed=w["seed"])
     local_docs = w["n_docs"] // world
-    slice_docs = min(local_docs, w["slice_docs"])
-    passes = max(1, local_docs // slice_docs)
+    passes = max(1, -(-local_docs // w["slice_docs"]))          # slices of at most slice_docs documents ...
+    slice_docs = local_docs // passes                            # ... that add up to the rank's share
     x, _l, _q = synth.make_dataset(slice_docs, f, max(1, slice_docs // 100), seed=20260103 + rank)
     sc = api.Scorer(trees, weights, f, device=local_rank)
     xp = torch.from_numpy(x).pin_memory()

@@ -573,7 +573,7 @@ constexpr int kPubCPT = 3;                         // expansions (136 features e
 // decision.  Nothing is written to a peer and the staging slots alternate between two sets by round, so one flag
 // barrier per round is enough.
 template <bool COUNT, bool PEER>
-__global__ void __launch_bounds__(kPubThreads, 6)
+__global__ void __launch_bounds__(kPubThreads, PEER ? 4 : 6)
 scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ TaskPack pack, unsigned long long *hsum,
                 uint32_t *hcnt, uint32_t ncells, const uint32_t *__restrict__ thr_off, uint32_t F,
                 const __grid_constant__ ScanOut out, const ulonglong2 *__restrict__ sq128, uint32_t *host_err,
@@ -636,15 +636,31 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
     c[i] = in ? __ldcg(Cc + k0 + i) : 0u;
   }
   if (W > 1) {
-    for (int pr = 0; pr < W; ++pr) {
-      if (pr == pv.rank) continue;
+    // every peer's bins in flight together (an NVLink load is ~2 us: seven of them one after the other would be
+    // most of the round), sums first, then counts
+    unsigned long long rs[kMaxPeers][kPubCPT];
 #pragma unroll
-      for (int i = 0; i < kPubCPT; ++i) {
-        if (k0 + i < cells) {
-          s[i] += *reinterpret_cast<const volatile unsigned long long *>(pv.sum[pr] + roff + k0 + i);
-          if (COUNT && pv.with_counts) c[i] += *reinterpret_cast<const volatile uint32_t *>(pv.cnt[pr] + roff + k0 + i);
-        }
-      }
+    for (int pr = 0; pr < kMaxPeers; ++pr)
+#pragma unroll
+      for (int i = 0; i < kPubCPT; ++i)
+        rs[pr][i] = (pr < W && pr != pv.rank && k0 + i < cells)
+                        ? *reinterpret_cast<const volatile unsigned long long *>(pv.sum[pr] + roff + k0 + i) : 0ull;
+#pragma unroll
+    for (int pr = 0; pr < kMaxPeers; ++pr)
+#pragma unroll
+      for (int i = 0; i < kPubCPT; ++i) s[i] += rs[pr][i];
+    if (COUNT && pv.with_counts) {
+      uint32_t rc[kMaxPeers][kPubCPT];
+#pragma unroll
+      for (int pr = 0; pr < kMaxPeers; ++pr)
+#pragma unroll
+        for (int i = 0; i < kPubCPT; ++i)
+          rc[pr][i] = (pr < W && pr != pv.rank && k0 + i < cells)
+                          ? *reinterpret_cast<const volatile uint32_t *>(pv.cnt[pr] + roff + k0 + i) : 0u;
+#pragma unroll
+      for (int pr = 0; pr < kMaxPeers; ++pr)
+#pragma unroll
+        for (int i = 0; i < kPubCPT; ++i) c[i] += rc[pr][i];
     }
   }
   if (f == 0 && warp == 0) {
