@@ -110,6 +110,8 @@ struct Comm {
   PeerSignals *d_sig = nullptr;      // own signal buffer (exported)
   uint32_t *d_done = nullptr;        // block counter of peer_reduce_kernel
   uint32_t epoch = 0;                // two barrier epochs per reduce launch
+  size_t mail_off = 0;               // byte offset of the candidate mailbox inside the signal buffer
+  uint32_t mail_tasks = 0;
   void *opened[4 * kMaxPeers] = {nullptr};
   int nopened = 0;
 };
@@ -367,7 +369,12 @@ int comm_setup_peers(qr_ctx *ctx) {
   const char *env = getenv("QR_PEER_REDUCE");
   int ok = (env == nullptr || atoi(env) != 0) && c->world <= kMaxPeers;
   const char *why = ok ? "" : (c->world > kMaxPeers ? "more than 8 ranks" : "QR_PEER_REDUCE=0");
-  const size_t sig_bytes = std::max<size_t>((size_t) 2 << 20, sizeof(PeerSignals) + (size_t) ctx->max_tasks * sizeof(ulonglong2));
+  // signal buffer: flags | squares of the current round | candidate mailbox of the feature-sliced exchange
+  // ([2 parities][kMaxPeers sources][max_tasks][2 children] records of kMailWords words, zero = never written)
+  c->mail_off = (sizeof(PeerSignals) + (size_t) ctx->max_tasks * sizeof(ulonglong2) + 255) & ~(size_t) 255;
+  c->mail_tasks = ctx->max_tasks;
+  const size_t mail_bytes = (size_t) 2 * kMaxPeers * ctx->max_tasks * 2 * kMailWords * sizeof(unsigned long long);
+  const size_t sig_bytes = std::max<size_t>((size_t) 2 << 20, c->mail_off + mail_bytes);
   QR_CUDA(cudaMalloc((void **) &c->d_sig, sig_bytes));
   QR_CUDA(cudaMalloc((void **) &c->d_done, sizeof(uint32_t)));
   QR_CUDA(cudaMemsetAsync(c->d_sig, 0, sig_bytes, st));
@@ -470,6 +477,14 @@ void comm_peer_view(qr_ctx *ctx, bool with_counts, PeerView *pv) {
   pv->world = c->world;
   pv->epoch = ++c->epoch;
   pv->with_counts = with_counts ? 1 : 0;
+  if (ctx->sliced) {
+    // contiguous feature ranges, ascending with the rank: the first maximum over ranks is the first over features
+    pv->f_lo = (uint32_t) ((size_t) ctx->F * (size_t) c->rank / (size_t) c->world);
+    pv->f_hi = (uint32_t) ((size_t) ctx->F * (size_t) (c->rank + 1) / (size_t) c->world);
+    for (int p = 0; p < c->world; ++p)
+      pv->mail[p] = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(c->peers.sig[p]) + c->mail_off);
+    pv->mail_tasks = c->mail_tasks;
+  }
 }
 
 static int peer_reduce_tasks(qr_ctx *ctx, uint32_t k, bool root) {

@@ -351,7 +351,8 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
                  const uint32_t *__restrict__ cids, const long long *__restrict__ clamq,
                  const long long *__restrict__ lamq, const uint32_t *__restrict__ thr_off, uint32_t F,
                  unsigned long long *hsum, uint32_t *hcnt, uint32_t ncells, ulonglong2 *sq_partials,
-                 uint32_t stride, ulonglong2 *sq_acc, unsigned long long *ktrace, unsigned long long *kspan) {
+                 uint32_t stride, ulonglong2 *sq_acc, unsigned long long *ktrace, unsigned long long *kspan,
+                 const uint4 *__restrict__ rows, uint32_t npanels) {
   if (pack.n) tasks = pack.t;
   constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
   extern __shared__ __align__(1024) unsigned char hist_smem[];
@@ -405,7 +406,10 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
   uint32_t *gc = hcnt + (size_t) build_slot(t) * ncells + cell0;
   const uint32_t *ids = cids + t.region0;
   const long long *lq = identity ? lamq : clamq + t.region0;
-  const uint4 *prow = panels + (size_t) p * N;
+  // a gathered list reads the document-major copy when there is one (document d's row of panel p at d * npanels + p)
+  const bool by_doc = !identity && rows != nullptr;
+  const uint4 *prow = by_doc ? rows + p : panels + (size_t) p * N;
+  const uint32_t rstride = by_doc ? npanels : 1u;
   U128 sq{0ull, 0ull};
   if (SMEM) {
     const uint32_t rot = lane_id() & (FPP - 1);
@@ -416,8 +420,8 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
     uint4 c0 = make_uint4(0u, 0u, 0u, 0u), c1 = c0;
     long long q0 = 0, q1 = 0;
     bool v0 = i < end, v1 = i + kHistThreads < end;
-    if (v0) { c0 = prow[identity ? i : ids[i]]; q0 = lq[i]; }
-    if (v1) { c1 = prow[identity ? i + kHistThreads : ids[i + kHistThreads]]; q1 = lq[i + kHistThreads]; }
+    if (v0) { c0 = prow[(size_t) (identity ? i : ids[i]) * rstride]; q0 = lq[i]; }
+    if (v1) { c1 = prow[(size_t) (identity ? i + kHistThreads : ids[i + kHistThreads]) * rstride]; q1 = lq[i + kHistThreads]; }
     bool w0 = i + 2 * kHistThreads < end, w1 = i + 3 * kHistThreads < end;
     uint32_t nd0 = 0, nd1 = 0;   // documents of the NEXT iteration
     if (w0) nd0 = identity ? i + 2 * kHistThreads : ids[i + 2 * kHistThreads];
@@ -425,8 +429,8 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
     while (v0) {
       uint4 n0 = make_uint4(0u, 0u, 0u, 0u), n1 = n0;
       long long nq0 = 0, nq1 = 0;
-      if (w0) { n0 = prow[nd0]; nq0 = lq[i + 2 * kHistThreads]; }
-      if (w1) { n1 = prow[nd1]; nq1 = lq[i + 3 * kHistThreads]; }
+      if (w0) { n0 = prow[(size_t) nd0 * rstride]; nq0 = lq[i + 2 * kHistThreads]; }
+      if (w1) { n1 = prow[(size_t) nd1 * rstride]; nq1 = lq[i + 3 * kHistThreads]; }
       i += 2 * kHistThreads;
       const bool z0 = i + 2 * kHistThreads < end, z1 = i + 3 * kHistThreads < end;
       if (z0) nd0 = identity ? i + 2 * kHistThreads : ids[i + 2 * kHistThreads];
@@ -447,7 +451,7 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
     const uint32_t rotb = rot * (uint32_t) sizeof(BinT);
     for (uint32_t i = begin + threadIdx.x; i < end; i += kHistThreads) {
       const uint32_t d = identity ? i : ids[i];
-      const uint4 row = rotate_bytes(prow[d], rotb);
+      const uint4 row = rotate_bytes(prow[(size_t) d * rstride], rotb);
       const long long q = lq[i];
       if (p == 0) {
         const unsigned long long a = (unsigned long long) (q < 0 ? -q : q);
@@ -579,7 +583,10 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
                 const __grid_constant__ ScanOut out, const ulonglong2 *__restrict__ sq128, uint32_t *host_err,
                 const __grid_constant__ PeerView pv) {
   if (pack.n) tasks = pack.t;
-  const uint32_t f = blockIdx.x, task = blockIdx.y;
+  // feature-sliced exchange: this rank's blocks cover its own features [f_lo, f_hi) only
+  const bool sliced = PEER && pv.f_hi != 0u;
+  const uint32_t f_first = sliced ? pv.f_lo : 0u, nf_scan = sliced ? pv.f_hi - pv.f_lo : F;
+  const uint32_t f = f_first + blockIdx.x, task = blockIdx.y;
   const NodeTask &t = tasks[task];
   const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
   const uint32_t kb = blockIdx.y * gridDim.x + blockIdx.x;
@@ -627,6 +634,7 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
       st_flag(pv.peer_flags[tid] + pv.rank, pv.epoch);
     if (tid < (uint32_t) W && tid != (uint32_t) pv.rank) wait_flag_or_report(pv.flags + tid, pv.epoch, host_err);
     __syncthreads();
+    kstamp(out.ktrace, kb, 4);
   }
   // the bins were accumulated with atomics by blocks on other SMs (or GPUs): read them from L2
 #pragma unroll
@@ -636,34 +644,36 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
     c[i] = in ? __ldcg(Cc + k0 + i) : 0u;
   }
   if (W > 1) {
-    // every peer's bins in flight together (an NVLink load is ~2 us: seven of them one after the other would be
-    // most of the round), sums first, then counts
+    // Every peer's bins in flight together: an NVLink load takes ~3 us, and left to itself ptxas adds each peer's
+    // values as they arrive to save registers, which serialises the round trips (7 peers x (sums, counts) = 24 us
+    // measured at 8 GPUs).  The empty asm statements take every loaded value as an operand, so all loads are issued
+    // before the first of them is waited for.
     unsigned long long rs[kMaxPeers][kPubCPT];
+    uint32_t rc[kMaxPeers][kPubCPT];
+    const bool wc = COUNT && pv.with_counts;
 #pragma unroll
-    for (int pr = 0; pr < kMaxPeers; ++pr)
+    for (int pr = 0; pr < kMaxPeers; ++pr) {
+      const bool on = pr < W && pr != pv.rank;
 #pragma unroll
-      for (int i = 0; i < kPubCPT; ++i)
-        rs[pr][i] = (pr < W && pr != pv.rank && k0 + i < cells)
-                        ? *reinterpret_cast<const volatile unsigned long long *>(pv.sum[pr] + roff + k0 + i) : 0ull;
-#pragma unroll
-    for (int pr = 0; pr < kMaxPeers; ++pr)
-#pragma unroll
-      for (int i = 0; i < kPubCPT; ++i) s[i] += rs[pr][i];
-    if (COUNT && pv.with_counts) {
-      uint32_t rc[kMaxPeers][kPubCPT];
-#pragma unroll
-      for (int pr = 0; pr < kMaxPeers; ++pr)
-#pragma unroll
-        for (int i = 0; i < kPubCPT; ++i)
-          rc[pr][i] = (pr < W && pr != pv.rank && k0 + i < cells)
-                          ? *reinterpret_cast<const volatile uint32_t *>(pv.cnt[pr] + roff + k0 + i) : 0u;
-#pragma unroll
-      for (int pr = 0; pr < kMaxPeers; ++pr)
-#pragma unroll
-        for (int i = 0; i < kPubCPT; ++i) c[i] += rc[pr][i];
+      for (int i = 0; i < kPubCPT; ++i) {
+        rs[pr][i] = 0ull; rc[pr][i] = 0u;
+        if (on && k0 + i < cells) {
+          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(rs[pr][i]) : "l"(pv.sum[pr] + roff + k0 + i) : "memory");
+          if (wc) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(rc[pr][i]) : "l"(pv.cnt[pr] + roff + k0 + i) : "memory");
+        }
+      }
     }
+    static_assert(kPubCPT == 3, "the operand lists below name three cells per thread");
+#pragma unroll
+    for (int pr = 0; pr < kMaxPeers; ++pr)
+      asm volatile("" : "+l"(rs[pr][0]), "+l"(rs[pr][1]), "+l"(rs[pr][2]), "+r"(rc[pr][0]), "+r"(rc[pr][1]), "+r"(rc[pr][2]));
+#pragma unroll
+    for (int pr = 0; pr < kMaxPeers; ++pr)
+#pragma unroll
+      for (int i = 0; i < kPubCPT; ++i) { s[i] += rs[pr][i]; c[i] += rc[pr][i]; }
+    kstamp(out.ktrace, kb, 5);
   }
-  if (f == 0 && warp == 0) {
+  if (f == f_first && warp == 0) {
     // exact squares of the built child
     U128 tot{0ull, 0ull};
     if (own_raw) {   // one GPU: every p == 0 histogram slice has added its part to the accumulator
@@ -850,14 +860,14 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
       r.score = best1; r.lc = bl1; r.t = bt1;
       out.cand[((size_t) task * 2 + (1 - child0)) * F + f] = r;
     }
-    if (f == 0) {
+    if (f == f_first) {   // (integer sums: every feature's last cumulative bin holds the same node totals)
       out.node[(size_t) task * 2 + child0] = make_double2(ts0, (double) tot_cn0);
       if (two) out.node[(size_t) task * 2 + (1 - child0)] = make_double2(ts1, (double) tot_cn1);
     }
     kstamp(out.ktrace, kb, 2);
     // the last feature of the task to get here takes the first maximum over features (rt.cc:297-306)
     __threadfence();
-    s_bt[0][0] = (atomicAdd(out.done + task, 1u) == F - 1u) ? 1u : 0u;
+    s_bt[0][0] = (atomicAdd(out.done + task, 1u) == nf_scan - 1u) ? 1u : 0u;
   }
   __syncthreads();
   if (s_bt[0][0] == 0u) return;
@@ -866,7 +876,7 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
   const int nchild = two ? 2 : 1;
   double fb[2] = {-1.0, -1.0};
   uint32_t ff[2] = {0xffffffffu, 0xffffffffu}, ft[2] = {0xffffffffu, 0xffffffffu}, fl[2] = {0u, 0u};
-  for (uint32_t g = tid; g < F; g += kPubThreads) {   // ascending g per thread: its first maximum
+  for (uint32_t g = f_first + tid; g < f_first + nf_scan; g += kPubThreads) {   // ascending g per thread: its first maximum
 #pragma unroll
     for (int child = 0; child < 2; ++child) {
       if (child < nchild) {
@@ -893,15 +903,66 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
     s_bs[1][warp] = fb[1]; s_bf[1][warp] = ff[1]; s_bt[1][warp] = ft[1]; s_bl[1][warp] = fl[1];
   }
   __syncthreads();
+  double b = -1.0;
+  uint32_t f1 = 0xffffffffu, t1 = 0xffffffffu, l1 = 0u;
   if ((int) tid < nchild) {   // thread c finishes child c
     const int child = (int) tid;
     const double *sb = child == 0 ? s_bs[0] : s_bs[1];
     const uint32_t *sf = child == 0 ? s_bf[0] : s_bf[1], *st = child == 0 ? s_bt[0] : s_bt[1], *sl = child == 0 ? s_bl[0] : s_bl[1];
-    double b = sb[0];
-    uint32_t f1 = sf[0], t1 = st[0], l1 = sl[0];
+    b = sb[0];
+    f1 = sf[0]; t1 = st[0]; l1 = sl[0];
 #pragma unroll
     for (uint32_t w = 1; w < kPubWarps; ++w)
       if (sb[w] > b || (sb[w] == b && sf[w] < f1)) { b = sb[w]; f1 = sf[w]; t1 = st[w]; l1 = sl[w]; }
+  }
+  if (PEER && sliced) {
+    // The winners over this rank's features go to every rank's mailbox (records of four tagged words, see
+    // qr_task.cuh); the ranks' winners are then compared in rank order = ascending feature order with a strict '>'
+    // (rt.cc:297-306), so every rank publishes the same split.
+    __shared__ double s_xb[2][kMaxPeers];
+    __shared__ uint32_t s_xa[2][kMaxPeers], s_xl[2][kMaxPeers];
+    __syncthreads();
+    if ((int) tid < nchild) { s_xb[tid][pv.rank] = b; s_xa[tid][pv.rank] = (f1 << 16) | (t1 & 0xffffu); s_xl[tid][pv.rank] = l1; }
+    __syncthreads();
+    const uint32_t Wn = (uint32_t) pv.world, ep = pv.epoch;
+    if (tid < (uint32_t) nchild * Wn) {
+      const int child = (int) (tid / Wn), p = (int) (tid % Wn);
+      if (p != pv.rank) {
+        const unsigned long long bits = (unsigned long long) __double_as_longlong(s_xb[child][pv.rank]);
+        volatile unsigned long long *dst = pv.mail[p] + mail_index(ep, pv.rank, pv.mail_tasks, task, child);
+        dst[0] = (bits << 32) | ep;
+        dst[1] = (bits & 0xffffffff00000000ull) | ep;
+        dst[2] = ((unsigned long long) s_xl[child][pv.rank] << 32) | ep;
+        dst[3] = ((unsigned long long) s_xa[child][pv.rank] << 32) | ep;
+        const volatile unsigned long long *src = pv.mail[pv.rank] + mail_index(ep, p, pv.mail_tasks, task, child);
+        unsigned long long w0, w1, w2, w3;
+        const long long t0 = clock64();
+        for (;;) {
+          w0 = src[0]; w1 = src[1]; w2 = src[2]; w3 = src[3];
+          if ((uint32_t) w0 == ep && (uint32_t) w1 == ep && (uint32_t) w2 == ep && (uint32_t) w3 == ep) break;
+          if (clock64() - t0 > 40000000000ll) {   // ~20 s: a peer never arrived
+            if (host_err) { *reinterpret_cast<volatile uint32_t *>(host_err) = 1u; __threadfence_system(); }
+            break;
+          }
+        }
+        s_xb[child][p] = __longlong_as_double((long long) ((w0 >> 32) | (w1 & 0xffffffff00000000ull)));
+        s_xl[child][p] = (uint32_t) (w2 >> 32);
+        s_xa[child][p] = (uint32_t) (w3 >> 32);
+      }
+    }
+    __syncthreads();
+    kstamp(out.ktrace, kb, 6);
+    if ((int) tid < nchild) {
+      b = s_xb[tid][0];
+      uint32_t a = s_xa[tid][0];
+      l1 = s_xl[tid][0];
+      for (uint32_t p = 1; p < Wn; ++p)
+        if (s_xb[tid][p] > b) { b = s_xb[tid][p]; a = s_xa[tid][p]; l1 = s_xl[tid][p]; }
+      f1 = a >> 16; t1 = a & 0xffffu;
+    }
+  }
+  if ((int) tid < nchild) {
+    const int child = (int) tid;
     const double2 nd = __ldcg(out.node + (size_t) task * 2 + child);
     const double sq = __ldcg(out.sq_built + task);
     ChildOut *o = out.out + (size_t) task * 2 + child;

@@ -89,6 +89,7 @@ struct qr_ctx {
 
   // device state
   uint4 *d_panels = nullptr;      // [npanels][N]
+  uint4 *d_rows = nullptr;        // [N][npanels] document-major copy for gathered histogram launches (FAST mode)
   uint32_t *d_thr_off = nullptr;  // [F+1]
   float *d_labels = nullptr;      // [N]
   double *d_gain = nullptr;       // [N] pow(2, label)
@@ -189,5 +190,7 @@ struct qr_ctx {
   bool round_fused = false;                 // this round's all-reduce happens inside scan_kernel
   uint32_t round_parity = 0, round_sq_off = 0;   // staging set / offset into d_sq128 of this round
   bool peer_fused = true;                   // QR_PEER_FUSED=0: always the stand-alone exchange kernel
+  bool sliced = false;                      // leaf-wise growth over peer memory: every rank adds up and scans F / world
+                                            // features, the ranks exchange their winners (QR_PEER_SLICED=0: every rank scans all)
   uint32_t oneshot_max = 12;                // fuse while (world - 1) * tasks * histogram bytes <= this many MB (QR_PEER_ONESHOT_MAX)
 };

@@ -95,7 +95,7 @@ __global__ void transpose_kernel(const float *rowmajor, float *colmajor, size_t 
 // one document's 16-byte panel row.
 template <typename BinT>
 __global__ void binning_kernel(const float *colmajor, size_t N, uint32_t F, const float *thr,
-                               const uint32_t *thr_off, uint4 *panels, uint32_t npanels) {
+                               const uint32_t *thr_off, uint4 *panels, uint32_t npanels, uint4 *rows) {
   constexpr uint32_t FPP = kPanelBytes / sizeof(BinT);
   size_t d = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t p = blockIdx.y;
@@ -117,6 +117,9 @@ __global__ void binning_kernel(const float *colmajor, size_t N, uint32_t F, cons
     }
   }
   panels[(size_t) p * N + d] = row.v;
+  // second copy, document-major: a document's npanels rows are contiguous, so the histogram blocks of the
+  // npanels panels that gather the same (sparse) document list share its DRAM bursts (FAST mode only)
+  if (rows != nullptr) rows[d * npanels + p] = row.v;
 }
 
 // ------------------------------------------------------------------------------------------

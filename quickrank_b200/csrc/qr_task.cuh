@@ -49,7 +49,18 @@ struct PeerView {
   int rank, world;                            // world <= 1: nothing is exchanged inside the kernel
   uint32_t epoch;
   int with_counts;                            // 0: the counts are global already (root refresh)
+  // feature-sliced exchange (leaf-wise growth): this rank adds up and scans only the features [f_lo, f_hi) and the
+  // ranks exchange their per-child winners through the mailboxes (f_hi == 0: every rank scans every feature)
+  uint32_t f_lo, f_hi;
+  unsigned long long *mail[kMaxPeers];        // mailbox of every rank, own at [rank]
+  uint32_t mail_tasks;                        // tasks per (parity, source rank) block of a mailbox
 };
+// A mailbox record is four 8-byte words, each carrying the round's epoch in its low half: a word is written and
+// read whole, so a record whose four tags match is complete — no fence, no separate flag, one NVLink write of latency.
+constexpr uint32_t kMailWords = 4;
+__host__ __device__ __forceinline__ size_t mail_index(uint32_t epoch, int src, uint32_t mail_tasks, uint32_t task, int child) {
+  return ((((size_t) (epoch & 1u) * kMaxPeers + (size_t) src) * mail_tasks + task) * 2 + (size_t) child) * kMailWords;
+}
 
 // flags: release store (everything this thread wrote or observed before it, at system scope) / acquire load
 __device__ __forceinline__ uint32_t ld_flag(const uint32_t *p) {

@@ -286,11 +286,14 @@ static int finish_binning(qr_ctx *c, const float *d_col, uint32_t max_bin) {
   QR_CUDA(cudaMemcpy(d_thr, flat.data(), c->ncells * sizeof(float), cudaMemcpyHostToDevice));
   QR_CUDA(cudaMemcpy(c->d_thr_off, c->thr_off.data(), (F + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
   QR_TRY(dev_alloc(&c->d_panels, (size_t) c->npanels * N));
+  // FAST mode gathers the built child's documents from a document-major copy (QR_ROW_COPY=0: from the panels)
+  if (!c->exact && c->npanels > 1 && (getenv("QR_ROW_COPY") == nullptr || atoi(getenv("QR_ROW_COPY")) != 0))
+    QR_TRY(dev_alloc(&c->d_rows, (size_t) c->npanels * N));
   dim3 grid((unsigned) ((N + 127) / 128), c->npanels);
   if (c->bin_bytes == 1)
-    binning_kernel<uint8_t><<<grid, 128, 0, st>>>(d_col, N, (uint32_t) F, d_thr, c->d_thr_off, c->d_panels, c->npanels);
+    binning_kernel<uint8_t><<<grid, 128, 0, st>>>(d_col, N, (uint32_t) F, d_thr, c->d_thr_off, c->d_panels, c->npanels, c->d_rows);
   else
-    binning_kernel<uint16_t><<<grid, 128, 0, st>>>(d_col, N, (uint32_t) F, d_thr, c->d_thr_off, c->d_panels, c->npanels);
+    binning_kernel<uint16_t><<<grid, 128, 0, st>>>(d_col, N, (uint32_t) F, d_thr, c->d_thr_off, c->d_panels, c->npanels, c->d_rows);
   QR_CUDA(cudaGetLastError());
   QR_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_thr);
@@ -587,6 +590,11 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   QR_CUDA(cudaGetLastError());
   clk.lap("state + pools");
   QR_TRY(comm_setup_peers(c));
+  {
+    const char *e = getenv("QR_PEER_SLICED");
+    c->sliced = c->comm && comm_transport(c->comm) == 2 && c->pub_ok && c->peer_fused && !c->oblivious &&
+                F >= (size_t) comm_world(c->comm) && comm_world(c->comm) > 1 && (e == nullptr || atoi(e) != 0);
+  }
   QR_TRY(init_root_counts(c));
   QR_CUDA(cudaGetLastError());
   clk.lap("root counts");
@@ -730,7 +738,7 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
                   c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done,
                   c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_node, c->d_cids, c->d_clamq, c->d_counts,
-                  c->d_sq_built, c->d_leafmeta, c->d_sq_acc, c->d_cand, c->d_noderec, c->d_kspan};
+                  c->d_sq_built, c->d_leafmeta, c->d_sq_acc, c->d_cand, c->d_noderec, c->d_kspan, c->d_rows};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);

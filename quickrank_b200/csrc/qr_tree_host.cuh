@@ -133,6 +133,9 @@ static void begin_exchange_round(qr_ctx *c, uint32_t k) {
   // rank; beyond, the stand-alone reduce-scatter + all-gather moves 2(W-1)/W of the payload instead of W-1 times it
   const size_t oneshot_bytes = (size_t) (comm_world(c->comm) - 1) * k * c->ncells * 12;
   c->round_fused = c->peer_fused && oneshot_bytes <= (size_t) c->oneshot_max << 20;
+  // feature-sliced exchange: a rank only ever holds the cumulative histograms of its own features, so every round
+  // takes the in-scan path (it reads 1 / world of every peer's bins, what a reduce-scatter would move)
+  if (c->sliced) c->round_fused = true;
 }
 static uint32_t stage_of(const qr_ctx *c, uint32_t j) {
   if (c->fused_scan) return 1u + (uint32_t) c->stage_slot0 + j;   // one GPU: the raw slot of task j (cleared by its scan)
@@ -291,12 +294,12 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
                     SMEMF ? smem : 0, (const NodeTask *) c->d_tasks, k, c->pack, counts, (const uint4 *) c->d_panels, c->N, \
                     (const uint32_t *) c->d_cids, (const long long *) c->d_clamq, (const long long *) c->d_lamq, \
                     (const uint32_t *) c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128 + c->round_sq_off, \
-                    c->max_thr, c->d_sq_acc, kt, kspan);                                                      \
+                    c->max_thr, c->d_sq_acc, kt, kspan, (const uint4 *) c->d_rows, c->npanels);               \
     else                                                                                                      \
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, SMEMF, COUNTF, ACCF>), dim3(total_slices, c->npanels), kHistThreads, \
                 SMEMF ? smem : 0, c->d_tasks, k, c->pack, counts, c->d_panels, c->N, c->d_cids, c->d_clamq,   \
                 c->d_lamq, c->d_thr_off, F, c->d_hist_sum, c->d_hist_cnt, c->ncells, c->d_sq128 + c->round_sq_off, \
-                c->max_thr, c->d_sq_acc, kt, kspan);                                                          \
+                c->max_thr, c->d_sq_acc, kt, kspan, c->d_rows, c->npanels);                                   \
   } while (0)
       unsigned long long *kspan = nullptr;
       if (c->profiling) {
@@ -347,13 +350,14 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
     PeerView pv{};
     if (c->round_fused) comm_peer_view(c, !static_counts, &pv);
     const ulonglong2 *sqp = c->d_sq128 + c->round_sq_off;
+    const uint32_t scan_f = pv.f_hi ? pv.f_hi - pv.f_lo : F;   // feature-sliced exchange: this rank's features only
 #define QR_SCANPUB_LAUNCH(COUNTF, PEERF)                                                                      \
   do {                                                                                                        \
     if (pdl)                                                                                                  \
-      QR_LAUNCH_PDL(c, PH_SCAN, (scan_pub_kernel<COUNTF, PEERF>), dim3(F, k), dim3(kPubThreads), 0, (const NodeTask *) c->d_tasks, \
+      QR_LAUNCH_PDL(c, PH_SCAN, (scan_pub_kernel<COUNTF, PEERF>), dim3(scan_f, k), dim3(kPubThreads), 0, (const NodeTask *) c->d_tasks, \
                     c->pack, c->d_hist_sum, c->d_hist_cnt, c->ncells, (const uint32_t *) c->d_thr_off, F, so, sqp, c->d_err_mapped, pv); \
     else                                                                                                      \
-      QR_LAUNCH(c, PH_SCAN, (scan_pub_kernel<COUNTF, PEERF>), dim3(F, k), kPubThreads, 0, c->d_tasks, c->pack, c->d_hist_sum, \
+      QR_LAUNCH(c, PH_SCAN, (scan_pub_kernel<COUNTF, PEERF>), dim3(scan_f, k), kPubThreads, 0, c->d_tasks, c->pack, c->d_hist_sum, \
                 c->d_hist_cnt, c->ncells, c->d_thr_off, F, so, sqp, c->d_err_mapped, pv);                     \
   } while (0)
     if (c->round_fused) { if (static_counts) QR_SCANPUB_LAUNCH(false, true); else QR_SCANPUB_LAUNCH(true, true); }
@@ -446,12 +450,12 @@ static int init_root_counts(qr_ctx *c) {
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, true, true, false>), dim3(t.hist_nblk, c->npanels), kHistThreads, smem, c->d_tasks, 1u,
                 c->pack, c->d_counts, c->d_panels, c->N, c->d_cids, c->d_clamq, c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
                 c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (ulonglong2 *) nullptr, (unsigned long long *) nullptr,
-                (unsigned long long *) nullptr);
+                (unsigned long long *) nullptr, (const uint4 *) nullptr, c->npanels);
     else
       QR_LAUNCH(c, PH_HIST, (hist_limb_kernel<B, false, true, false>), dim3(t.hist_nblk, c->npanels), kHistThreads, 0, c->d_tasks, 1u,
                 c->pack, c->d_counts, c->d_panels, c->N, c->d_cids, c->d_clamq, c->d_lamq, c->d_thr_off, F, c->d_hist_sum,
                 c->d_hist_cnt, c->ncells, c->d_sq128, c->max_thr, (ulonglong2 *) nullptr, (unsigned long long *) nullptr,
-                (unsigned long long *) nullptr);
+                (unsigned long long *) nullptr, (const uint4 *) nullptr, c->npanels);
     return QR_OK;
   }));
   QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));

@@ -19,8 +19,9 @@ T = 6
 
 MODES = {
     # name: (environment, expected transport)
-    "peer-auto": ({}, "peer"),                                   # fused for small rounds, stand-alone kernel for wide ones
-    "peer-fused": ({"QR_PEER_ONESHOT_MAX": "100000"}, "peer"),   # every round: all-reduce inside the split-scan kernel
+    "peer-auto": ({}, "peer"),                                   # leaf-wise: feature-sliced scan + winner exchange; oblivious: as below
+    "peer-unsliced": ({"QR_PEER_SLICED": "0"}, "peer"),          # every rank scans every feature: fused for small rounds, stand-alone kernel for wide ones
+    "peer-fused": ({"QR_PEER_SLICED": "0", "QR_PEER_ONESHOT_MAX": "100000"}, "peer"),   # every round: all-reduce inside the split-scan kernel
     "peer-twoshot": ({"QR_PEER_FUSED": "0"}, "peer"),            # every round: the in-place reduce-scatter + all-gather kernel
     "nccl": ({"QR_PEER_REDUCE": "0"}, "nccl"),
 }
@@ -28,7 +29,7 @@ WORLD = int(os.environ.get("QR_TEST_WORLD", "2"))
 
 
 def _worker(rank, world, q, out_q, algo, kw, mode):
-    for k in ("QR_PEER_REDUCE", "QR_PEER_FUSED", "QR_PEER_ONESHOT_MAX"):
+    for k in ("QR_PEER_REDUCE", "QR_PEER_FUSED", "QR_PEER_ONESHOT_MAX", "QR_PEER_SLICED"):
         os.environ.pop(k, None)
     os.environ.update(MODES[mode][0])
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
