@@ -120,10 +120,6 @@ int main(int argc, char **argv) {
   int rank = 0;
   if (opt.count("train") && (!opt.count("model-in") || opt.count("restart-train"))) {
     const int gpus = (int) geti("gpus", 1);
-    if (gpus > 1 && algo == "DART") {
-      std::cerr << "!!! DART trains on one GPU in this build." << std::endl;
-      return EXIT_FAILURE;
-    }
     rank = setup_sharding(gpus);
     if (rank != 0) {   // same loop, no report
       // (never destroyed: std::cout is flushed once more when the process exits)

@@ -137,6 +137,11 @@ int qr_apply_tree(qr_ctx *ctx, const qr_flat_tree *tree, double weight);
  * sequence of operations of Dart::update_modelscores' loop over `trees_to_update` (dart.cc:634-650),
  * which visits the documents once per tree instead. */
 int qr_apply_trees(qr_ctx *ctx, const qr_flat_tree *trees, const double *weights, size_t ntrees);
+/* Replaces Dart::update_contribution_scores (src/learning/forests/dart.cc:689-706), for `ntrees` trees in one pass:
+ * contribution[t] = mean over the dataset (all ranks' documents) of |tree_t(doc)|, the unweighted leaf output
+ * (RTNode::score_instance), the quantity DART's CONTR / WCONTR sampling and normalisation read
+ * (dart.cc:774-850, 917-940). */
+int qr_tree_contributions(qr_ctx *ctx, const qr_flat_tree *trees, size_t ntrees, double *contribution);
 
 /* Replaces Metric::evaluate_dataset(VerticalDataset, scores) for Ndcg (metric.h:93-106,
  * ndcg.cc:49-58) on the training scores held by the context. */
@@ -204,6 +209,13 @@ int qr_ctx_comm_transport(const qr_ctx *ctx);
 /* Uploads an ensemble (replaces building Ensemble from XML, ensemble.cc / mart.cc:37-89). */
 int qr_scorer_create(const qr_flat_tree *trees, const double *weights, size_t ntrees, size_t F,
                      int device, qr_scorer **out);
+/* The same with options.  QR_SCORER_CONDOP_WEIGHTS: every tree weight is replaced by the one a `ranker()` emitted by
+ * the reference's conditional-operator generator uses — the weight as a float printed with three decimals and an `f`
+ * suffix (src/io/generate_conditional_operators.cc:95-105) — so that the scores equal that generated code's
+ * (compiled without floating-point contraction) bit for bit. */
+#define QR_SCORER_CONDOP_WEIGHTS 1u
+int qr_scorer_create_ex(const qr_flat_tree *trees, const double *weights, size_t ntrees, size_t F,
+                        int device, unsigned flags, qr_scorer **out);
 int qr_scorer_destroy(qr_scorer *s);
 /* Replaces LTR_Algorithm::score_dataset (ltr_algorithm.cc:44-52): scores[i] = sum_t w_t*leaf_t(doc_i)
  * for row-major documents; host buffers, copies included. */
@@ -211,6 +223,14 @@ int qr_score_dataset(qr_scorer *s, const float *docs_rowmajor, size_t N, size_t 
 /* Same with device-resident documents and scores (no copies). */
 int qr_score_dataset_device(qr_scorer *s, const float *docs_rowmajor_device, size_t N, size_t F,
                             double *scores_device);
+/* The per-tree score matrix partial[doc][tree] = (float) (weight_tree * leaf_tree(doc)) for row-major documents:
+ * Ensemble::partial_scores_instance (src/learning/tree/ensemble.cc:121-131) for every document, cast to Feature as
+ * Driver::extract_partial_scores does (src/driver/driver.cc:411-446) — the input of CLEAVER and of the line search.
+ * ignore_weights = a scorer created with unit weights.  `scores` (may be NULL) also receives the ensemble scores. */
+int qr_score_partial(qr_scorer *s, const float *docs_rowmajor, size_t N, size_t F, float *partial, double *scores);
+/* Same with device-resident documents and outputs (asynchronous; `scores_device` may be NULL). */
+int qr_score_partial_device(qr_scorer *s, const float *docs_rowmajor_device, size_t N, size_t F,
+                            float *partial_device, double *scores_device);
 /* Waits for the scorer's stream (qr_score_dataset_device is asynchronous). */
 int qr_scorer_sync(qr_scorer *s);
 /* kernel launches issued by this scorer so far */

@@ -77,6 +77,7 @@ def lib():
         L.qr_update_modelscores.argtypes = [vp, C.c_double]
         L.qr_apply_tree.argtypes = [vp, C.POINTER(FlatTree), C.c_double]
         L.qr_apply_trees.argtypes = [vp, C.POINTER(FlatTree), dp, C.c_size_t]
+        L.qr_tree_contributions.argtypes = [vp, C.POINTER(FlatTree), C.c_size_t, dp]
         L.qr_evaluate.argtypes = [vp, dp]
         L.qr_boost_iteration.argtypes = [vp, C.POINTER(FlatTree), dp]
         L.qr_get_scores.argtypes = [vp, dp]
@@ -100,7 +101,10 @@ def lib():
                                             C.POINTER(C.c_ubyte), C.c_int, C.c_int, C.POINTER(vp)]
         L.qr_ctx_comm_transport.argtypes = [vp]
         L.qr_scorer_create.argtypes = [C.POINTER(FlatTree), dp, sz, sz, C.c_int, C.POINTER(vp)]
+        L.qr_scorer_create_ex.argtypes = [C.POINTER(FlatTree), dp, sz, sz, C.c_int, C.c_uint, C.POINTER(vp)]
         L.qr_scorer_destroy.argtypes = [vp]
+        L.qr_score_partial.argtypes = [vp, fp, sz, sz, fp, dp]
+        L.qr_score_partial_device.argtypes = [vp, vp, sz, sz, vp, vp]
         L.qr_score_dataset.argtypes = [vp, fp, sz, sz, dp]
         L.qr_score_dataset_device.argtypes = [vp, vp, sz, sz, vp]
         L.qr_scorer_sync.argtypes = [vp]
@@ -251,6 +255,14 @@ class Trainer:
         w = np.ascontiguousarray(weights, np.float64)
         _check(lib().qr_apply_trees(self.h, arr, _p(w, C.c_double), len(bufs)))
 
+    def tree_contributions(self, trees):
+        """mean |tree(doc)| over the dataset for each tree (Dart::update_contribution_scores, dart.cc:689-706)"""
+        bufs = [TreeBuffer.from_dict(t) for t in trees]
+        arr = (FlatTree * len(bufs))(*[b.t for b in bufs])
+        out = np.zeros(len(bufs), np.float64)
+        _check(lib().qr_tree_contributions(self.h, arr, len(bufs), _p(out, C.c_double)))
+        return out
+
     def evaluate_dataset(self):
         m = C.c_double()
         _check(lib().qr_evaluate(self.h, C.byref(m)))
@@ -352,15 +364,18 @@ def comm_unique_id() -> bytes:
 class Scorer:
     """An ensemble resident on one GPU (the quickscore path)."""
 
-    def __init__(self, trees, weights, n_features, device=-1):
+    def __init__(self, trees, weights, n_features, device=-1, condop_weights=False):
+        """condop_weights: use the tree weights of the ranker() the reference's conditional-operator generator
+        emits (floats printed with three decimals, generate_conditional_operators.cc:95-105)."""
         L = lib()
         self.bufs = [TreeBuffer.from_dict(t) for t in trees]
         arr = (FlatTree * len(self.bufs))(*[b.t for b in self.bufs])
         w = np.ascontiguousarray(weights, np.float64)
         self.F = n_features
+        self.ntrees = len(self.bufs)
         self.h = C.c_void_p()
-        _check(L.qr_scorer_create(arr, _p(w, C.c_double), len(self.bufs), n_features, device,
-                                  C.byref(self.h)))
+        _check(L.qr_scorer_create_ex(arr, _p(w, C.c_double), len(self.bufs), n_features, device,
+                                     1 if condop_weights else 0, C.byref(self.h)))
 
     def close(self):
         if self.h:
@@ -383,6 +398,16 @@ class Scorer:
         _check(lib().qr_score_dataset(self.h, _p(x, C.c_float), x.shape[0], x.shape[1],
                                       _p(out, C.c_double)))
         return out
+
+    def partial_scores(self, x, with_scores=False):
+        """Row-major host documents -> the per-tree score matrix [N][ntrees] (float32) of
+        Driver::extract_partial_scores (driver.cc:411-446); with_scores: also the ensemble scores."""
+        x = np.ascontiguousarray(x, np.float32)
+        part = np.empty((x.shape[0], self.ntrees), np.float32)
+        sc = np.empty(x.shape[0], np.float64) if with_scores else None
+        _check(lib().qr_score_partial(self.h, _p(x, C.c_float), x.shape[0], x.shape[1], _p(part, C.c_float),
+                                      _p(sc, C.c_double) if with_scores else None))
+        return (part, sc) if with_scores else part
 
     def score_dataset_device(self, docs_ptr, n, scores_ptr):
         _check(lib().qr_score_dataset_device(self.h, C.c_void_p(docs_ptr), n, self.F,

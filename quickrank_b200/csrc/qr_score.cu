@@ -44,7 +44,8 @@ constexpr uint32_t kMaxChunkNodes = 8191, kMaxChunkLeaves = 32767;
 // product[] holds weight_t * leaf output, rounded once exactly as `leaf * weight` is in
 // ensemble.cc:116 (the reference build does not fuse that multiply into the sum).
 struct ChunkHeader {
-  uint32_t prod_off, pad[3];            // byte offset of product[] inside the blob
+  uint32_t prod_off;                    // byte offset of product[] inside the blob
+  uint32_t t0, nt, pad;                 // first tree of the chunk and how many of the slots hold a tree
   uint16_t root[kChunkTrees];           // child reference of each tree's root
 };
 constexpr uint32_t kNodesOff = sizeof(ChunkHeader);
@@ -164,11 +165,14 @@ template <> __device__ __forceinline__ uint32_t lds_code<uint16_t>(uint32_t row,
 // are staged in shared memory (rows padded to an odd number of 32-bit words so that the lanes of a
 // warp, which read different documents, hit different banks); otherwise the codes are read from
 // global memory.
-template <typename CodeT, int TPD, bool TILE>
+// PARTIAL: also stores every tree's weighted output as a float, partial[doc][tree] — the per-tree score matrix of
+// Ensemble::partial_scores_instance (ensemble.cc:121-131) cast to Feature as Driver::extract_partial_scores does
+// (driver.cc:411-446), the input of CLEAVER and of the line search.
+template <typename CodeT, int TPD, bool TILE, bool PARTIAL>
 __global__ void __launch_bounds__(1024)
 score_codes_kernel(const CodeT *__restrict__ codes, size_t n, uint32_t stride, uint32_t tile_words,
                    const unsigned char *__restrict__ chunks, uint32_t chunk_bytes, uint32_t nchunks,
-                   uint32_t docs_per_block, double *__restrict__ scores) {
+                   uint32_t docs_per_block, double *__restrict__ scores, float *__restrict__ partial, uint32_t ntrees) {
   static_assert(kChunkTrees % TPD == 0, "a chunk is walked in whole groups of TPD trees");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -220,6 +224,8 @@ score_codes_kernel(const CodeT *__restrict__ codes, size_t n, uint32_t stride, u
     const uint32_t nodes = buf + kNodesOff;
     const uint32_t prod = buf + lds_u32(buf);
     const uint32_t roots = buf + (uint32_t) offsetof(ChunkHeader, root) + 2u * sub;
+    const uint32_t ct0 = PARTIAL ? lds_u32(buf + (uint32_t) offsetof(ChunkHeader, t0)) : 0u;
+    const uint32_t cnt = PARTIAL ? lds_u32(buf + (uint32_t) offsetof(ChunkHeader, nt)) : 0u;
 #pragma unroll 1
     for (uint32_t g = 0; g < (uint32_t) kChunkTrees; g += TPD) {
       uint32_t cur = lds_u16(roots + 2u * g);
@@ -230,6 +236,7 @@ score_codes_kernel(const CodeT *__restrict__ codes, size_t n, uint32_t stride, u
         cur = (code << 16) <= nd.x ? (nd.y & 0xFFFFu) : (nd.y >> 16);   // rtnode.h:141-144
       }
       const double val = lds_f64(prod + ((cur & 0xFFFEu) << 2));
+      if (PARTIAL) { if (ldoc < ndocs && g + sub < cnt) partial[d * ntrees + ct0 + g + sub] = (float) val; }
       // ordered accumulation (ensemble.cc:116): the TPD lanes of a document add the group's products in
       // tree order; each lane performs every addition, so all of them hold the same running sum
       if (TPD == 1) {
@@ -242,7 +249,7 @@ score_codes_kernel(const CodeT *__restrict__ codes, size_t n, uint32_t stride, u
     }
     __syncthreads();   // every thread is done with buffer b before it is refilled
   }
-  if (ldoc < ndocs && sub == 0) scores[d] = sum;
+  if (ldoc < ndocs && sub == 0 && (!PARTIAL || scores != nullptr)) scores[d] = sum;
 }
 
 }  // namespace qr
@@ -306,27 +313,64 @@ static ScoreShape score_shape(const qr_scorer *s) {
 }
 
 template <typename CodeT, int TPD, bool TILE>
-static cudaError_t score_launch(qr_scorer *s, size_t n, uint32_t dpb, uint32_t tile_words, size_t smem, double *scores) {
-  cudaFuncSetAttribute(score_codes_kernel<CodeT, TPD, TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+static cudaError_t score_launch(qr_scorer *s, size_t n, uint32_t dpb, uint32_t tile_words, size_t smem, double *scores,
+                                float *partial) {
   const unsigned sg = (unsigned) ((n + dpb - 1) / dpb);
-  score_codes_kernel<CodeT, TPD, TILE><<<sg, dpb * TPD, smem, s->stream>>>(
-      (const CodeT *) s->d_codes, n, s->stride, tile_words, s->d_chunks, s->chunk_bytes, s->nchunks, dpb, scores);
+  if (partial) {
+    cudaFuncSetAttribute(score_codes_kernel<CodeT, TPD, TILE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    score_codes_kernel<CodeT, TPD, TILE, true><<<sg, dpb * TPD, smem, s->stream>>>(
+        (const CodeT *) s->d_codes, n, s->stride, tile_words, s->d_chunks, s->chunk_bytes, s->nchunks, dpb, scores, partial,
+        (uint32_t) s->ntrees);
+  } else {
+    cudaFuncSetAttribute(score_codes_kernel<CodeT, TPD, TILE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+    score_codes_kernel<CodeT, TPD, TILE, false><<<sg, dpb * TPD, smem, s->stream>>>(
+        (const CodeT *) s->d_codes, n, s->stride, tile_words, s->d_chunks, s->chunk_bytes, s->nchunks, dpb, scores, nullptr,
+        (uint32_t) s->ntrees);
+  }
   return cudaGetLastError();
 }
 
 template <typename CodeT>
 static cudaError_t score_dispatch(qr_scorer *s, const ScoreShape &sh, size_t n, uint32_t dpb, uint32_t tile_words, size_t smem,
-                                  double *scores) {
-  if (sh.docs == 0) return score_launch<CodeT, 4, false>(s, n, dpb, tile_words, smem, scores);
-  if (sh.tpd == 1) return score_launch<CodeT, 1, true>(s, n, dpb, tile_words, smem, scores);
-  if (sh.tpd == 2) return score_launch<CodeT, 2, true>(s, n, dpb, tile_words, smem, scores);
-  return score_launch<CodeT, 4, true>(s, n, dpb, tile_words, smem, scores);
+                                  double *scores, float *partial) {
+  if (sh.docs == 0) return score_launch<CodeT, 4, false>(s, n, dpb, tile_words, smem, scores, partial);
+  if (sh.tpd == 1) return score_launch<CodeT, 1, true>(s, n, dpb, tile_words, smem, scores, partial);
+  if (sh.tpd == 2) return score_launch<CodeT, 2, true>(s, n, dpb, tile_words, smem, scores, partial);
+  return score_launch<CodeT, 4, true>(s, n, dpb, tile_words, smem, scores, partial);
 }
 
 extern "C" {
 
+// The weight a ranker() generated by the reference's conditional-operator generator multiplies a tree's leaf with:
+// the XML weight read as a float and printed with three decimals and an `f` suffix
+// (generate_conditional_operators.cc:95-105), i.e. the float nearest to that decimal, promoted to double.
+static double condop_weight(double w) {
+  char buf[64];
+  snprintf(buf, sizeof(buf), "%.3f", (double) (float) w);
+  return (double) strtof(buf, nullptr);
+}
+
+static int scorer_create_impl(const qr_flat_tree *trees, const double *weights, size_t ntrees, size_t F, int device,
+                              qr_scorer **out);
+
 int qr_scorer_create(const qr_flat_tree *trees, const double *weights, size_t ntrees, size_t F, int device,
                      qr_scorer **out) {
+  return scorer_create_impl(trees, weights, ntrees, F, device, out);
+}
+
+int qr_scorer_create_ex(const qr_flat_tree *trees, const double *weights, size_t ntrees, size_t F, int device,
+                        unsigned flags, qr_scorer **out) {
+  if (flags & ~(unsigned) QR_SCORER_CONDOP_WEIGHTS) { set_error("qr_scorer_create_ex: unknown flags 0x%x", flags); return QR_EINVAL; }
+  if (!(flags & QR_SCORER_CONDOP_WEIGHTS) || !weights) return scorer_create_impl(trees, weights, ntrees, F, device, out);
+  std::vector<double> w(ntrees);
+  for (size_t t = 0; t < ntrees; ++t) w[t] = condop_weight(weights[t]);
+  return scorer_create_impl(trees, w.data(), ntrees, F, device, out);
+}
+
+}  // extern "C"
+
+static int scorer_create_impl(const qr_flat_tree *trees, const double *weights, size_t ntrees, size_t F, int device,
+                              qr_scorer **out) {
   if (!out) { set_error("qr_scorer_create: null out"); return QR_EINVAL; }
   *out = nullptr;
   if ((!trees || !weights) && ntrees) { set_error("qr_scorer_create: null argument"); return QR_EINVAL; }
@@ -402,6 +446,8 @@ int qr_scorer_create(const qr_flat_tree *trees, const double *weights, size_t nt
     unsigned char *base = blob.data() + ci * chunk_bytes;
     ChunkHeader *h = reinterpret_cast<ChunkHeader *>(base);
     h->prod_off = (uint32_t) (sizeof(ChunkHeader) + c.inner * 8);
+    h->t0 = (uint32_t) c.t0;
+    h->nt = (uint32_t) (c.t1 - c.t0);
     CodeNode *nodes = reinterpret_cast<CodeNode *>(base + kNodesOff);
     double *product = reinterpret_cast<double *>(base + h->prod_off);
     product[0] = 0.0;
@@ -459,6 +505,8 @@ int qr_scorer_create(const qr_flat_tree *trees, const double *weights, size_t nt
   return QR_OK;
 }
 
+extern "C" {
+
 int qr_scorer_destroy(qr_scorer *s) {
   if (!s) return QR_OK;
   cudaSetDevice(s->device);
@@ -476,8 +524,10 @@ int qr_scorer_destroy(qr_scorer *s) {
   return QR_OK;
 }
 
-int qr_score_dataset_device(qr_scorer *s, const float *docs, size_t N, size_t F, double *scores) {
-  if (!s || !docs || !scores) { set_error("qr_score_dataset_device: null argument"); return QR_EINVAL; }
+// encode + walk of device-resident documents; `partial` (device, [N][ntrees] floats) may be null, and so may
+// `scores` when `partial` is given
+static int score_device_impl(qr_scorer *s, const float *docs, size_t N, size_t F, double *scores, float *partial) {
+  if (!s || !docs || (!scores && !partial)) { set_error("qr_score_dataset_device: null argument"); return QR_EINVAL; }
   if (F != s->F) { set_error("dataset has %zu features, the model was built for %zu", F, s->F); return QR_EINVAL; }
   cudaSetDevice(s->device);
   if (N == 0) return QR_OK;
@@ -513,11 +563,61 @@ int qr_score_dataset_device(qr_scorer *s, const float *docs, size_t N, size_t F,
       }
       s->launches += 1;
     }
-    QR_CUDA(s->code_bytes == 1 ? score_dispatch<uint8_t>(s, sh, n, dpb, tile_words, smem, scores + n0)
-                               : score_dispatch<uint16_t>(s, sh, n, dpb, tile_words, smem, scores + n0));
+    double *sc = scores ? scores + n0 : nullptr;
+    float *pa = partial ? partial + n0 * s->ntrees : nullptr;
+    QR_CUDA(s->code_bytes == 1 ? score_dispatch<uint8_t>(s, sh, n, dpb, tile_words, smem, sc, pa)
+                               : score_dispatch<uint16_t>(s, sh, n, dpb, tile_words, smem, sc, pa));
     s->launches += 1;
   }
   return QR_OK;
+}
+
+int qr_score_dataset_device(qr_scorer *s, const float *docs, size_t N, size_t F, double *scores) {
+  if (!scores) { set_error("qr_score_dataset_device: null argument"); return QR_EINVAL; }
+  return score_device_impl(s, docs, N, F, scores, nullptr);
+}
+
+int qr_score_partial_device(qr_scorer *s, const float *docs, size_t N, size_t F, float *partial, double *scores) {
+  if (!partial) { set_error("qr_score_partial_device: null argument"); return QR_EINVAL; }
+  return score_device_impl(s, docs, N, F, scores, partial);
+}
+
+// Host buffers: the per-tree score matrix [N][ntrees] (floats) of Driver::extract_partial_scores
+// (driver.cc:411-446); `scores` (may be NULL) also receives the ensemble scores.  Slices of at most 256 MB of
+// output pass through the device one after the other.
+int qr_score_partial(qr_scorer *s, const float *docs, size_t N, size_t F, float *partial, double *scores) {
+  if (!s || !docs || !partial) { set_error("qr_score_partial: null argument"); return QR_EINVAL; }
+  if (F != s->F) { set_error("dataset has %zu features, the model was built for %zu", F, s->F); return QR_EINVAL; }
+  cudaSetDevice(s->device);
+  if (N == 0 || s->ntrees == 0) return QR_OK;
+  const size_t row = std::max(F * sizeof(float), s->ntrees * sizeof(float));
+  const size_t slice = std::min(N, std::max<size_t>(1024, ((size_t) 256 << 20) / row));
+  float *d_in = nullptr, *d_part = nullptr;
+  double *d_sc = nullptr;
+  int rc = QR_OK;
+  if (cudaMalloc((void **) &d_in, slice * F * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void **) &d_part, slice * s->ntrees * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void **) &d_sc, slice * sizeof(double)) != cudaSuccess) {
+    set_error("qr_score_partial: out of device memory");
+    rc = QR_ECUDA;
+  }
+  for (size_t n0 = 0; n0 < N && rc == QR_OK; n0 += slice) {
+    const size_t n = std::min(slice, N - n0);
+    cudaError_t e = cudaMemcpyAsync(d_in, docs + n0 * F, n * F * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) {
+      rc = score_device_impl(s, d_in, n, F, d_sc, d_part);
+      if (rc != QR_OK) break;
+      e = cudaMemcpyAsync(partial + n0 * s->ntrees, d_part, n * s->ntrees * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    }
+    if (e == cudaSuccess && scores) e = cudaMemcpyAsync(scores + n0, d_sc, n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    if (e != cudaSuccess) { set_error("qr_score_partial failed: %s", cudaGetErrorString(e)); rc = QR_ECUDA; }
+  }
+  cudaStreamSynchronize(s->stream);
+  if (d_in) cudaFree(d_in);
+  if (d_part) cudaFree(d_part);
+  if (d_sc) cudaFree(d_sc);
+  return rc;
 }
 
 int qr_scorer_sync(qr_scorer *s) {

@@ -254,9 +254,30 @@ static int build_binning(qr_ctx *c, const float *d_col, const qr_ctx *thr_from) 
 }
 
 // phase D: bin width, cell layout, device copies of the thresholds, the panel matrix
+static int binning_layout(qr_ctx *c, uint32_t max_bin, float **d_thr_out);
 static int finish_binning(qr_ctx *c, const float *d_col, uint32_t max_bin) {
   const size_t N = c->N, F = c->F;
   cudaStream_t st = c->stream;
+  float *d_thr = nullptr;
+  QR_TRY(binning_layout(c, max_bin, &d_thr));
+  QR_TRY(dev_alloc(&c->d_panels, (size_t) c->npanels * N));
+  // FAST mode gathers the built child's documents from a document-major copy (QR_ROW_COPY=0: from the panels)
+  if (!c->exact && c->npanels > 1 && (getenv("QR_ROW_COPY") == nullptr || atoi(getenv("QR_ROW_COPY")) != 0))
+    QR_TRY(dev_alloc(&c->d_rows, (size_t) c->npanels * N));
+  dim3 grid((unsigned) ((N + 127) / 128), c->npanels);
+  if (c->bin_bytes == 1)
+    binning_kernel<uint8_t><<<grid, 128, 0, st>>>(d_col, N, (uint32_t) F, d_thr, c->d_thr_off, c->d_panels, c->npanels, c->d_rows);
+  else
+    binning_kernel<uint16_t><<<grid, 128, 0, st>>>(d_col, N, (uint32_t) F, d_thr, c->d_thr_off, c->d_panels, c->npanels, c->d_rows);
+  QR_CUDA(cudaGetLastError());
+  QR_CUDA(cudaStreamSynchronize(st));
+  cudaFree(d_thr);
+  return QR_OK;
+}
+
+// bin width and cell layout from c->thr; uploads the threshold offsets (and, when asked, the thresholds)
+static int binning_layout(qr_ctx *c, uint32_t max_bin, float **d_thr_out) {
+  const size_t F = c->F;
   if (max_bin > 65535u) {
     set_error("a feature has %u occupied bins; this build stores bins in at most 16 bits "
               "(use --num-thresholds)", max_bin + 1);
@@ -280,23 +301,14 @@ static int finish_binning(qr_ctx *c, const float *d_col, uint32_t max_bin) {
   // upload thresholds, build panels
   std::vector<float> flat(c->ncells);
   for (size_t f = 0; f < F; ++f) std::copy(c->thr[f].begin(), c->thr[f].end(), flat.begin() + c->thr_off[f]);
-  float *d_thr = nullptr;
-  QR_TRY(dev_alloc(&d_thr, c->ncells));
   QR_TRY(dev_alloc(&c->d_thr_off, F + 1));
-  QR_CUDA(cudaMemcpy(d_thr, flat.data(), c->ncells * sizeof(float), cudaMemcpyHostToDevice));
   QR_CUDA(cudaMemcpy(c->d_thr_off, c->thr_off.data(), (F + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  QR_TRY(dev_alloc(&c->d_panels, (size_t) c->npanels * N));
-  // FAST mode gathers the built child's documents from a document-major copy (QR_ROW_COPY=0: from the panels)
-  if (!c->exact && c->npanels > 1 && (getenv("QR_ROW_COPY") == nullptr || atoi(getenv("QR_ROW_COPY")) != 0))
-    QR_TRY(dev_alloc(&c->d_rows, (size_t) c->npanels * N));
-  dim3 grid((unsigned) ((N + 127) / 128), c->npanels);
-  if (c->bin_bytes == 1)
-    binning_kernel<uint8_t><<<grid, 128, 0, st>>>(d_col, N, (uint32_t) F, d_thr, c->d_thr_off, c->d_panels, c->npanels, c->d_rows);
-  else
-    binning_kernel<uint16_t><<<grid, 128, 0, st>>>(d_col, N, (uint32_t) F, d_thr, c->d_thr_off, c->d_panels, c->npanels, c->d_rows);
-  QR_CUDA(cudaGetLastError());
-  QR_CUDA(cudaStreamSynchronize(st));
-  cudaFree(d_thr);
+  if (d_thr_out) {
+    float *d_thr = nullptr;
+    QR_TRY(dev_alloc(&d_thr, c->ncells));
+    QR_CUDA(cudaMemcpy(d_thr, flat.data(), c->ncells * sizeof(float), cudaMemcpyHostToDevice));
+    *d_thr_out = d_thr;
+  }
   return QR_OK;
 }
 
@@ -315,6 +327,8 @@ struct InitClock {
     t0 = t1;
   }
 };
+
+static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoffsets, const qr_params *params, InitClock &clk);
 
 static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t F, const float *labels,
                              const uint64_t *qoffsets, size_t Q, const qr_params *params,
@@ -405,7 +419,12 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   cudaFree(d_col);
   if (rc != QR_OK) return rc;
   clk.lap("thresholds + binning");
+  return ctx_create_state(c, labels, qoffsets, params, clk);
+}
 
+// second half of context creation: per-query tables, state arrays, histogram pool, kernel attributes, peers
+static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoffsets, const qr_params *params, InitClock &clk) {
+  const size_t N = c->N, F = c->F, Q = c->Q;
   // labels, gains, query offsets, ideal DCG per query, discount tables (host glibc, once)
   std::vector<uint32_t> qoff(Q + 1);
   uint32_t maxlen = 0;
@@ -415,6 +434,8 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     if (q) maxlen = std::max<uint32_t>(maxlen, qoff[q] - qoff[q - 1]);
   }
   c->maxlen = (maxlen + 3u) & ~3u;
+  c->h_labels.assign(labels, labels + N);   // (document samples are cut from these, qr_set_sample)
+  c->h_qoff = qoff;
   std::vector<double> gain(N), idcg(Q), lg(c->maxlen + 1), invlg(c->maxlen + 1);
   for (size_t i = 0; i < N; ++i) gain[i] = std::pow(2.0, (double) labels[i]);              // dcg.cc:37
   for (uint32_t i = 0; i <= c->maxlen; ++i) {
@@ -618,14 +639,38 @@ static int ensure_ranking(qr_ctx *c) {
     attr_set = true;
   }
   const unsigned grid = (unsigned) ((c->Q + kRankWarps - 1) / kRankWarps);
-  QR_LAUNCH(c, PH_RANK, rank_kernel<kRankWarps>, grid, kRankWarps * 32, smem, c->d_scores, c->d_labels,
+  QR_LAUNCH(c, PH_RANK, rank_kernel<kRankWarps>, grid, kRankWarps * 32, smem, c->d_sortkey ? c->d_sortkey : c->d_scores, c->d_labels,
             c->d_gain, c->d_qoff, c->d_idcg, c->d_lg, (uint32_t) c->Q, c->maxlen, c->cutoff,
             c->d_rankpos, c->d_qndcg);
   c->ranking_valid = true;
   return QR_OK;
 }
 
+static int compute_pseudo(qr_ctx *c);
+// pseudo-responses of a sampled iteration: computed on the sample (absent documents take no part in any query's
+// ranked list, lambdamart.cc:84-103) and written back to the full arrays, which are zero elsewhere (:76-78)
+static int compute_pseudo_sampled(qr_ctx *c) {
+  qr_ctx *s = c->sample;
+  const size_t n = s->N;
+  const unsigned grid = (unsigned) ((n + 255) / 256);
+  sample_scores_kernel<<<grid, 256, 0, c->stream>>>(c->d_scores, c->d_sample_ids, c->d_sample_keysrc, n, s->d_scores, s->d_sortkey_buf);
+  c->launches++;
+  QR_CUDA(cudaGetLastError());
+  QR_CUDA(cudaStreamSynchronize(c->stream));
+  s->ranking_valid = false;
+  QR_TRY(compute_pseudo(s));
+  QR_CUDA(cudaStreamSynchronize(s->stream));
+  QR_CUDA(cudaMemsetAsync(c->d_lambda, 0, c->N * sizeof(double), c->stream));
+  if (c->lambda) QR_CUDA(cudaMemsetAsync(c->d_weight, 0, c->N * sizeof(double), c->stream));
+  sample_scatter_kernel<<<grid, 256, 0, c->stream>>>(s->d_lambda, c->lambda ? s->d_weight : nullptr, c->d_sample_ids, n, c->d_lambda, c->d_weight);
+  c->launches++;
+  QR_CUDA(cudaGetLastError());
+  c->maxabs_valid = false;
+  return QR_OK;
+}
+
 static int compute_pseudo(qr_ctx *c) {
+  if (c->sample) return compute_pseudo_sampled(c);
   if (!c->lambda) {
     PhaseTimer pt(c, PH_PSEUDO);
     QR_LAUNCH(c, PH_PSEUDO, mart_pseudo_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_scores,
@@ -808,22 +853,21 @@ int qr_apply_tree(qr_ctx *c, const qr_flat_tree *t, double weight) {
   return qr_apply_trees(c, t, &weight, 1);
 }
 
-int qr_apply_trees(qr_ctx *c, const qr_flat_tree *trees, const double *weights, size_t ntrees) {
-  QR_CHECK_CTX(c);
-  if (ntrees == 0) return QR_OK;
-  if (!trees || !weights) { set_error("qr_apply_trees: null argument"); return QR_EINVAL; }
+// packs `ntrees` trees (and their weights, when given) into the context's staging buffer and copies it to the device:
+// weights | nodes | roots
+struct StagedTrees { const double *w; const qr::PackedNode *nodes; const uint32_t *roots; size_t total; };
+static int stage_trees(qr_ctx *c, const char *who, const qr_flat_tree *trees, const double *weights, size_t ntrees, StagedTrees *st) {
   size_t total = 0;
   for (size_t t = 0; t < ntrees; ++t) {
     const qr_flat_tree &ft = trees[t];
-    if (ft.nnodes == 0) { set_error("qr_apply_trees: empty tree %zu", t); return QR_EINVAL; }
+    if (ft.nnodes == 0) { set_error("%s: empty tree %zu", who, t); return QR_EINVAL; }
     for (uint32_t i = 0; i < ft.nnodes; ++i)
       if (ft.feature[i] >= 0 && ((size_t) ft.feature[i] >= c->F || ft.threshold_idx[i] >= c->thr[ft.feature[i]].size())) {
-        set_error("qr_apply_trees: node %u of tree %zu does not belong to this context's binning", i, t);
+        set_error("%s: node %u of tree %zu does not belong to this context's binning", who, i, t);
         return QR_EINVAL;
       }
     total += ft.nnodes;
   }
-  // one staging buffer: nodes | roots | weights
   const size_t bytes = total * sizeof(PackedNode) + ntrees * sizeof(uint32_t) + ntrees * sizeof(double) + 16;
   if (bytes > c->apply_cap) {
     if (c->d_apply) cudaFree(c->d_apply);
@@ -842,23 +886,64 @@ int qr_apply_trees(qr_ctx *c, const qr_flat_tree *trees, const double *weights, 
   for (size_t t = 0; t < ntrees; ++t) {
     const qr_flat_tree &ft = trees[t];
     hr[t] = (uint32_t) o;
-    hw[t] = weights[t];
+    hw[t] = weights ? weights[t] : 1.0;
     for (uint32_t i = 0; i < ft.nnodes; ++i)
       hn[o + i] = PackedNode{ft.feature[i], ft.feature[i] >= 0 ? ft.threshold_idx[i] : 0u, ft.left[i], ft.right[i], ft.value[i]};
     o += ft.nnodes;
   }
   QR_CUDA(cudaMemcpyAsync(c->d_apply, c->h_apply, bytes, cudaMemcpyHostToDevice, c->stream));
   unsigned char *d = (unsigned char *) c->d_apply;
-  const double *dw = (const double *) d;
-  const PackedNode *dn = (const PackedNode *) (d + ntrees * sizeof(double));
-  const uint32_t *dr = (const uint32_t *) (dn + total);
+  st->w = (const double *) d;
+  st->nodes = (const PackedNode *) (d + ntrees * sizeof(double));
+  st->roots = (const uint32_t *) (st->nodes + total);
+  st->total = total;
+  return QR_OK;
+}
+
+int qr_apply_trees(qr_ctx *c, const qr_flat_tree *trees, const double *weights, size_t ntrees) {
+  QR_CHECK_CTX(c);
+  if (ntrees == 0) return QR_OK;
+  if (!trees || !weights) { set_error("qr_apply_trees: null argument"); return QR_EINVAL; }
+  StagedTrees st{};
+  QR_TRY(stage_trees(c, "qr_apply_trees", trees, weights, ntrees, &st));
   int rc = dispatch_bins(c, [&](auto tag) -> int {
     using B = decltype(tag);
-    QR_LAUNCH(c, PH_LEAF, apply_trees_kernel<B>, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_panels, c->N, dn, dr, dw,
+    QR_LAUNCH(c, PH_LEAF, apply_trees_kernel<B>, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_panels, c->N, st.nodes, st.roots, st.w,
               (uint32_t) ntrees, c->d_scores);
     return QR_OK;
   });
   c->ranking_valid = false;
+  return rc;
+}
+
+// Dart::update_contribution_scores (dart.cc:689-706) for `ntrees` trees in one pass over the documents:
+// contribution[t] = mean over the (global) dataset of |tree_t(doc)|, the unweighted leaf output.
+int qr_tree_contributions(qr_ctx *c, const qr_flat_tree *trees, size_t ntrees, double *contribution) {
+  QR_CHECK_CTX(c);
+  if (ntrees == 0) return QR_OK;
+  if (!trees || !contribution) { set_error("qr_tree_contributions: null argument"); return QR_EINVAL; }
+  StagedTrees st{};
+  QR_TRY(stage_trees(c, "qr_tree_contributions", trees, nullptr, ntrees, &st));
+  const unsigned nblocks = (unsigned) ((c->N + kContribThreads - 1) / kContribThreads);
+  double *d_part = nullptr, *d_out = nullptr;
+  QR_TRY(dev_alloc(&d_part, (size_t) nblocks * ntrees));
+  if (dev_alloc(&d_out, ntrees) != QR_OK) { cudaFree(d_part); return QR_ECUDA; }
+  int rc = dispatch_bins(c, [&](auto tag) -> int {
+    using B = decltype(tag);
+    QR_LAUNCH(c, PH_LEAF, tree_contrib_kernel<B>, nblocks, kContribThreads, 0, c->d_panels, c->N, st.nodes, st.roots,
+              (uint32_t) ntrees, d_part);
+    QR_LAUNCH(c, PH_LEAF, contrib_reduce_kernel, (unsigned) ntrees, 32, 0, d_part, nblocks, (uint32_t) ntrees, d_out);
+    return QR_OK;
+  });
+  if (rc == QR_OK && c->comm) rc = comm_allreduce_sum_f64(c->comm, d_out, ntrees, c->stream);
+  if (rc == QR_OK) {
+    cudaError_t e = cudaMemcpyAsync(contribution, d_out, ntrees * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { set_error("qr_tree_contributions: %s", cudaGetErrorString(e)); rc = QR_ECUDA; }
+  }
+  cudaFree(d_part);
+  cudaFree(d_out);
+  if (rc == QR_OK) for (size_t t = 0; t < ntrees; ++t) contribution[t] /= (double) c->N_global;
   return rc;
 }
 

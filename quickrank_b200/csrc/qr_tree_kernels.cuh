@@ -281,6 +281,44 @@ __global__ void apply_trees_kernel(const uint4 *__restrict__ panels, size_t N, c
   scores[i] = s;
 }
 
+// Dart::update_contribution_scores (dart.cc:689-706): sum over the documents of |tree_t(doc)| (the unweighted leaf
+// output) for each of `ntrees` trees; block partials in a fixed shape, reduced in block order by
+// contrib_reduce_kernel, so the result does not depend on the launch.
+constexpr uint32_t kContribThreads = 256;
+template <typename BinT>
+__global__ void __launch_bounds__(kContribThreads)
+tree_contrib_kernel(const uint4 *__restrict__ panels, size_t N, const PackedNode *__restrict__ nodes,
+                    const uint32_t *__restrict__ root_of, uint32_t ntrees, double *partials) {
+  __shared__ double s_w[kContribThreads / 32];
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  for (uint32_t t = 0; t < ntrees; ++t) {
+    double v = 0.0;
+    if (i < N) {
+      const PackedNode *tn = nodes + root_of[t];
+      int32_t nd = 0;
+      while (tn[nd].feature >= 0)
+        nd = load_bin<BinT>(panels, N, (uint32_t) tn[nd].feature, (uint32_t) i) <= tn[nd].tidx ? tn[nd].left : tn[nd].right;
+      v = fabs(tn[nd].value);
+    }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31u) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a = 0.0;
+      for (uint32_t w = 0; w < kContribThreads / 32; ++w) a += s_w[w];
+      partials[(size_t) blockIdx.x * ntrees + t] = a;
+    }
+    __syncthreads();
+  }
+}
+__global__ void contrib_reduce_kernel(const double *__restrict__ partials, uint32_t nblocks, uint32_t ntrees, double *out) {
+  const uint32_t t = blockIdx.x, lane = threadIdx.x;   // one warp per tree
+  double a = 0.0;
+  for (uint32_t b = lane; b < nblocks; b += 32) a += partials[(size_t) b * ntrees + t];
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[t] = a;
+}
+
 // ------------------------------------------------------------------------------------------
 // Oblivious trees (ObliviousRT::fit / fill, ot.cc:32-201): per level, sum the split gain of every
 // (f, t) over the level's nodes in node order; a cell is invalid as soon as one node violates the

@@ -2,6 +2,8 @@
 inputs.  Bit-exact for indices (bins, ranks, split feature / threshold index, doc->leaf); floating
 point within the tolerance written at each assert (north_star: 1e-5 relative on leaf outputs and
 NDCG@k; most checks here are far tighter, and exact where the arithmetic order is replicated)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -302,6 +304,20 @@ def test_apply_trees_equals_one_tree_at_a_time():
         assert not np.array_equal(batched, base)
 
 
+def test_tree_contributions_match_oracle():
+    """qr_tree_contributions = Dart::update_contribution_scores (dart.cc:689-706): mean |tree(doc)| per tree (the
+    reference sums in an OpenMP reduction, i.e. in no fixed order: 1e-12 relative)."""
+    x, l, off = common.dataset(n=5000, f=12, q=50, seed=6)
+    with api.Trainer(x, l, off, nleaves=10) as tr:
+        trees = [tr.boost_iteration()[0] for _ in range(4)]
+        got = tr.tree_contributions(trees)
+        again = tr.tree_contributions(trees[::-1])[::-1]
+    assert np.array_equal(got, again)   # fixed reduction shape: independent of how the trees are batched
+    for t, tree in enumerate(trees):
+        want = np.mean(np.abs(po.score_dataset([tree], [1.0], x)))
+        assert abs(got[t] - want) <= 1e-12 * want, (t, got[t], want)
+
+
 def test_scoring_matches_oracle_bit_for_bit():
     x, l, off = common.dataset(n=3000, f=30, q=30)
     trees, weights = synth.random_ensemble(40, 16, 30, seed=3)
@@ -311,6 +327,54 @@ def test_scoring_matches_oracle_bit_for_bit():
         one = sc.score_document(x[17])
     assert np.array_equal(got, want)
     assert one == want[17]
+
+
+def test_partial_scores_match_oracle():
+    """qr_score_partial: the per-tree score matrix of Driver::extract_partial_scores (driver.cc:411-446) =
+    Ensemble::partial_scores_instance (ensemble.cc:121-131) per document, cast to float."""
+    x, l, off = common.dataset(n=2100, f=30, q=21)
+    trees, weights = synth.random_ensemble(37, 16, 30, seed=5)   # three chunks of trees, the last one part-filled
+    weights = np.linspace(0.05, 1.0, len(trees))
+    with api.Scorer(trees, weights, 30) as sc:
+        part, full = sc.partial_scores(x, with_scores=True)
+    assert part.shape == (len(x), len(trees)) and part.dtype == np.float32
+    for t, (tree, w) in enumerate(zip(trees, weights)):
+        want = po.score_dataset([tree], [w], x).astype(np.float32)
+        assert np.array_equal(part[:, t], want), t
+    assert np.array_equal(full, po.score_dataset(trees, weights, x))
+    with api.Scorer(trees, np.ones(len(trees)), 30) as sc:   # ignore_weights = true
+        raw = sc.partial_scores(x)
+    assert np.array_equal(raw[:, 11], po.score_dataset([trees[11]], [1.0], x).astype(np.float32))
+
+
+def test_condop_weight_mode_equals_the_generated_ranker(tmp_path):
+    """QR_SCORER_CONDOP_WEIGHTS: the GPU scores equal, bit for bit, the `double ranker(float *v)` the
+    conditional-operator generator emits (weights as 3-decimal floats, generate_conditional_operators.cc:95-105),
+    compiled without floating-point contraction."""
+    import ctypes as C
+    import subprocess
+    from quickrank_b200 import modelxml
+    ql = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "host", "bin", "quicklearn")
+    if not os.path.exists(ql):
+        pytest.skip("host/bin/quicklearn not built")
+    trees, _ = synth.random_ensemble(20, 9, 17, seed=4)
+    weights = np.array([0.1, 0.25, 0.0625, 0.1, 1.0, 0.333, 0.1, 0.05, 0.1, 0.2] * 2)
+    model, code, so = str(tmp_path / "m.xml"), str(tmp_path / "ranker.c"), str(tmp_path / "ranker.so")
+    modelxml.write_model(model, trees, weights)
+    out = subprocess.run([ql, "--model-file", model, "--code-file", code, "--generator", "condop"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    subprocess.check_call(["gcc", "-O1", "-ffp-contract=off", "-shared", "-fPIC", "-x", "c", code, "-o", so])
+    rk = C.CDLL(so)
+    rk.ranker.restype = C.c_double
+    rk.ranker.argtypes = [C.POINTER(C.c_float)]
+    rng = np.random.default_rng(1)
+    x = (rng.integers(0, 256, size=(500, 17)) / 255.0).astype(np.float32)
+    want = np.array([rk.ranker(x[i].ctypes.data_as(C.POINTER(C.c_float))) for i in range(len(x))])
+    with api.Scorer(trees, weights, 17, condop_weights=True) as sc:
+        got = sc.score_dataset(x)
+    assert np.array_equal(got, want)
+    with api.Scorer(trees, weights, 17) as sc:   # (the plain scorer uses the double weights: 0.0625 and 0.333 differ)
+        assert not np.array_equal(sc.score_dataset(x), want)
 
 
 def test_scoring_a_trained_model():
