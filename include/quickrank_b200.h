@@ -173,6 +173,12 @@ uint64_t qr_launch_count(qr_ctx *ctx);
  * score update, [5] ranking/NDCG; also returns per-phase launch counts (either may be NULL). */
 int qr_phase_times(qr_ctx *ctx, double ms[6], uint64_t launches[6], int reset);
 int qr_set_profiling(qr_ctx *ctx, int enabled);
+/* Self-test of QR_HIST_REFERENCE's squares sum (RTNodeHistogram's squares_sum_, rtnode_histogram.cc:65-69 fused,
+ * :199-203 multiply then add): sum of values[i]^2 in index order, once by the parallel scheme the mode uses for long
+ * lists (quickrank_b200/csrc/qr_exact_kernels.cuh) and once by the plain sequential chain; the two must be
+ * bit-identical.  replayed_chunks (may be NULL): 256-addend chunks the parallel scheme had to replay one by one. */
+int qr_selftest_ordered_squares(const double *values, size_t n, int fused, int device, double *parallel,
+                                double *serial, uint64_t *replayed_chunks);
 /* while profiling is enabled every launch of the histogram kernel (the dominant kernel of the path) is
  * bracketed by its own pair of CUDA events: accumulated device time (ms), number of launches and
  * number of documents whose bin rows those launches accumulated, since the last reset */

@@ -79,6 +79,7 @@ def lib():
         L.qr_apply_trees.argtypes = [vp, C.POINTER(FlatTree), dp, C.c_size_t]
         L.qr_tree_contributions.argtypes = [vp, C.POINTER(FlatTree), C.c_size_t, dp]
         L.qr_evaluate.argtypes = [vp, dp]
+        L.qr_selftest_ordered_squares.argtypes = [dp, sz, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_uint64)]
         L.qr_boost_iteration.argtypes = [vp, C.POINTER(FlatTree), dp]
         L.qr_get_scores.argtypes = [vp, dp]
         L.qr_set_scores.argtypes = [vp, dp]
@@ -353,6 +354,16 @@ class Trainer:
         ln = (C.c_uint64 * 6)()
         _check(lib().qr_phase_times(self.h, ms, ln, int(reset)))
         return dict(zip(PHASES, list(ms))), dict(zip(PHASES, [int(v) for v in ln]))
+
+
+def selftest_ordered_squares(values, fused, device=-1):
+    """(parallel, serial, replayed_chunks): sum of values**2 in index order by REFERENCE mode's parallel scheme and
+    by the plain chain (qr_selftest_ordered_squares)."""
+    v = np.ascontiguousarray(values, np.float64)
+    par, ser, rep = C.c_double(), C.c_double(), C.c_uint64()
+    _check(lib().qr_selftest_ordered_squares(_p(v, C.c_double), len(v), 1 if fused else 0, device, C.byref(par),
+                                             C.byref(ser), C.byref(rep)))
+    return par.value, ser.value, rep.value
 
 
 def comm_unique_id() -> bytes:

@@ -124,6 +124,16 @@ struct qr_ctx {
   uint32_t *d_leaf_of_doc = nullptr;        // [N]
   uint32_t *d_blockcnt = nullptr;           // partition scratch (REFERENCE mode)
   double *d_partials = nullptr;             // REFERENCE: squares per task [max_tasks]
+  // REFERENCE mode, large nodes (qr_exact_kernels.cuh): per feature the documents sorted by (bin, document),
+  // where each histogram cell's documents start, this round's node marks, chunk records of the ordered squares sums
+  uint32_t *d_perm = nullptr;               // [F][N]
+  unsigned long long *d_cell_pos = nullptr; // [ncells + 1]
+  uint32_t *d_mark = nullptr;               // [N]
+  uint8_t *d_fskip = nullptr;               // [F] 1: single-bin feature, not accumulated (nullptr: none)
+  void *d_sq_chunks = nullptr;              // [N / kSqChunk + max_tasks] SqChunk
+  uint32_t walk_min = 0;                    // built children of at least this many documents take the walk
+  uint32_t mark_tag = 0;
+  unsigned long long *d_sq_replayed = nullptr;   // chunks of the ordered squares sums replayed addition by addition
   ulonglong2 *d_sq128 = nullptr;            // FAST: exact squares per histogram slice [max_slices]
   uint32_t max_slices = 0;
   uint32_t *d_task_done = nullptr;          // [max_tasks] finalize completion counters

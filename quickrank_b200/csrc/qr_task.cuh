@@ -27,6 +27,8 @@ struct NodeTask {
   uint32_t fused_sq;     // REFERENCE: 1 = fma chain (child ctor), 0 = mul+add (root update)
   uint32_t lcount;       // local left count when the host knows it (single GPU), see lc_known
   uint32_t lc_known;     // 0: kernels read the count computed by part_prefix_kernel instead
+  uint32_t walk;         // REFERENCE mode: 1 = the built child is large: hist_exact_walk_kernel (qr_exact_kernels.cuh)
+  uint32_t sq_chunk0;    // REFERENCE mode: first chunk record of this task's ordered squares sum
   uint32_t stage1;       // sharded training, fused exchange: 1 + the staging slot the built child's LOCAL histogram
                          // is accumulated in (the split scan adds all ranks' staging slots into slotB); 0: the
                          // histogram is built in place in slotB

@@ -312,6 +312,69 @@ static int binning_layout(qr_ctx *c, uint32_t max_bin, float **d_thr_out) {
   return QR_OK;
 }
 
+// REFERENCE mode, large nodes (qr_exact_kernels.cuh): per feature, the documents in (bin, document) order — a stable
+// sort of the bin column, made once since the bins never change — and the position of every histogram cell in it.
+// QR_EXACT_WALK_MIN: built children of at least this many documents are accumulated by walking those lists (default
+// max(N/8, 65536); never below N/16, which bounds the large nodes of a round by kWalkMax).
+static int build_exact_walk_tables(qr_ctx *c) {
+  const size_t N = c->N, F = c->F;
+  cudaStream_t st = c->stream;
+  QR_TRY(dev_alloc((qr::SqChunk **) &c->d_sq_chunks, N / qr::kSqChunk + c->max_tasks + 2));
+  QR_TRY(dev_alloc(&c->d_sq_replayed, 1));
+  QR_CUDA(cudaMemset(c->d_sq_replayed, 0, sizeof(unsigned long long)));
+  size_t want = std::max<size_t>(N / 8, 65536);
+  if (const char *e = getenv("QR_EXACT_WALK_MIN")) want = (size_t) std::max<long long>(1, atoll(e));
+  want = std::max(want, N / 16 + 1);
+  c->walk_min = (uint32_t) std::min<size_t>(want, 0xffffffffu);
+  if (N > 0xfffffff0u) { set_error("QR_HIST_REFERENCE: more than 2^32 documents"); return QR_ELIMIT; }
+  QR_TRY(dev_alloc(&c->d_perm, F * N));
+  QR_TRY(dev_alloc(&c->d_cell_pos, (size_t) c->ncells + 1));
+  QR_TRY(dev_alloc(&c->d_mark, N));
+  QR_CUDA(cudaMemsetAsync(c->d_mark, 0, N * sizeof(uint32_t), st));
+  uint32_t *d_keys = nullptr, *d_keys_out = nullptr, *d_iota = nullptr;
+  void *d_tmp = nullptr;
+  QR_TRY(dev_alloc(&d_keys, N));
+  QR_TRY(dev_alloc(&d_keys_out, N));
+  QR_TRY(dev_alloc(&d_iota, N));
+  size_t tmp_bytes = 0;
+  const int bits = c->bin_bytes == 1 ? 8 : 16;
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys, d_keys_out, d_iota, c->d_perm, (int) N, 0, bits, st);
+  QR_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(tmp_bytes, 16)));
+  const unsigned blocks = (unsigned) ((N + 255) / 256);
+  int rc = QR_OK;
+  std::vector<uint32_t> ends(2 * F, 0u);   // first and last bin of every feature's sorted column
+  for (size_t f = 0; f < F && rc == QR_OK; ++f) {
+    if (c->bin_bytes == 1) qr::bin_column_kernel<uint8_t><<<blocks, 256, 0, st>>>(c->d_panels, N, (uint32_t) f, d_keys, d_iota);
+    else qr::bin_column_kernel<uint16_t><<<blocks, 256, 0, st>>>(c->d_panels, N, (uint32_t) f, d_keys, d_iota);
+    size_t tb = tmp_bytes;
+    if (cub::DeviceRadixSort::SortPairs(d_tmp, tb, d_keys, d_keys_out, d_iota, c->d_perm + f * N, (int) N, 0, bits, st) != cudaSuccess) {
+      set_error("sorting the bin column of feature %zu failed", f);
+      rc = QR_ECUDA;
+      break;
+    }
+    const uint32_t cells = c->thr_off[f + 1] - c->thr_off[f];
+    qr::cell_pos_kernel<<<(cells + 255) / 256, 256, 0, st>>>(d_keys_out, N, (uint32_t) f, c->thr_off[f], cells, c->d_cell_pos);
+    cudaMemcpyAsync(&ends[2 * f], d_keys_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&ends[2 * f + 1], d_keys_out + (N - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) { set_error("building the sorted document lists failed: %s", cudaGetErrorString(cudaGetLastError())); rc = QR_ECUDA; }
+  }
+  const unsigned long long end = (unsigned long long) F * N;
+  if (rc == QR_OK && cudaMemcpy(c->d_cell_pos + c->ncells, &end, sizeof(end), cudaMemcpyHostToDevice) != cudaSuccess) rc = QR_ECUDA;
+  // single-bin features (every document in one bin) cannot be split on once a leaf needs >= 1 document, and feature 0
+  // apart (node totals, rtnode.h:99-104) nothing reads their sums: they are not accumulated
+  if (rc == QR_OK && c->p.minleafsupport >= 1 && (getenv("QR_EXACT_SKIP") == nullptr || atoi(getenv("QR_EXACT_SKIP")) != 0)) {
+    std::vector<uint8_t> skip(F, 0);
+    bool any = false;
+    for (size_t f = 1; f < F; ++f) if (ends[2 * f] == ends[2 * f + 1]) { skip[f] = 1; any = true; }
+    if (any) {
+      rc = dev_alloc(&c->d_fskip, F);
+      if (rc == QR_OK && cudaMemcpy(c->d_fskip, skip.data(), F, cudaMemcpyHostToDevice) != cudaSuccess) rc = QR_ECUDA;
+    }
+  }
+  cudaFree(d_keys); cudaFree(d_keys_out); cudaFree(d_iota); cudaFree(d_tmp);
+  return rc;
+}
+
 static int init_root_counts(qr_ctx *c);
 
 // QR_INIT_TIMING=1: wall-clock breakdown of qr_ctx_create on stderr (development aid)
@@ -576,6 +639,7 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
     QR_TRY(dev_alloc(&c->d_blockcnt, (N + kPartItems - 1) / kPartItems + mt + 1));
     QR_TRY(dev_alloc(&c->d_segs, maxleaves + 1));
     QR_CUDA(cudaMallocHost((void **) &c->h_segs, (maxleaves + 1) * sizeof(LeafSeg)));
+    QR_TRY(build_exact_walk_tables(c));
   } else {
     // FAST mode: node_of_doc + the compact lists of a round's built children.  One GPU: the built child is the
     // smaller one, so a round appends at most N/2 documents.  Several ranks: a task's region must hold whatever
@@ -783,7 +847,8 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_leafval, c->d_obv_scores, c->d_tasks, c->d_lcount, c->d_segs, c->d_leaf_partials,
                   c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done,
                   c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_node, c->d_cids, c->d_clamq, c->d_counts,
-                  c->d_sq_built, c->d_leafmeta, c->d_sq_acc, c->d_cand, c->d_noderec, c->d_kspan, c->d_rows};
+                  c->d_sq_built, c->d_leafmeta, c->d_sq_acc, c->d_cand, c->d_noderec, c->d_kspan, c->d_rows,
+                  c->d_perm, c->d_cell_pos, c->d_mark, c->d_sq_chunks, c->d_sq_replayed, c->d_fskip};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);
@@ -1063,6 +1128,56 @@ int qr_set_profiling(qr_ctx *c, int enabled) {
   QR_CHECK_CTX(c);
   c->profiling = enabled != 0;
   return QR_OK;
+}
+
+// Self-test of the ordered squares sum (qr_exact_kernels.cuh): the parallel scheme and the plain chain on the same
+// values (as one node whose list is the identity), so that a test can require bit equality on adversarial inputs.
+int qr_selftest_ordered_squares(const double *values, size_t n, int fused, int device, double *parallel, double *serial,
+                                uint64_t *replayed_chunks) {
+  if (!values || n == 0 || n > 0xfffffff0u || !parallel || !serial) { set_error("qr_selftest_ordered_squares: bad arguments"); return QR_EINVAL; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { set_error("no CUDA device"); return QR_ECUDA; }
+  QR_CUDA(cudaSetDevice(device < 0 ? 0 : device));
+  double *d_v = nullptr, *d_out = nullptr;
+  NodeTask *d_t = nullptr;
+  SqChunk *d_ch = nullptr;
+  unsigned long long *d_rep = nullptr;
+  const uint32_t nch = (uint32_t) ((n + kSqChunk - 1) / kSqChunk);
+  QR_TRY(dev_alloc(&d_v, n));
+  QR_TRY(dev_alloc(&d_out, 2));
+  QR_TRY(dev_alloc(&d_t, 2));
+  QR_TRY(dev_alloc(&d_ch, nch + 1));
+  QR_TRY(dev_alloc(&d_rep, 1));
+  NodeTask t[2];
+  memset(t, 0, sizeof(t));
+  for (int i = 0; i < 2; ++i) { t[i].n = (uint32_t) n; t[i].src = 2; t[i].whole = 1; t[i].build_left = 1; t[i].fused_sq = fused ? 1u : 0u; t[i].sq0 = (uint32_t) i; }
+  int rc = QR_OK;
+  auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == QR_OK) { set_error("qr_selftest_ordered_squares: %s", cudaGetErrorString(e)); rc = QR_ECUDA; } };
+  ck(cudaMemcpy(d_v, values, n * sizeof(double), cudaMemcpyHostToDevice));
+  ck(cudaMemcpy(d_t, t, sizeof(t), cudaMemcpyHostToDevice));
+  ck(cudaMemset(d_out, 0, 2 * sizeof(double)));
+  ck(cudaMemset(d_rep, 0, sizeof(unsigned long long)));
+  if (rc == QR_OK) {
+    squares_exact_kernel<<<1, 32>>>(d_t + 1, nullptr, d_v, nullptr, nullptr, d_out, 1);
+    if (n > kSqSerialMax) {
+      ordered_squares_sums_kernel<<<(nch + 3) / 4, 128>>>(d_t, 1, nullptr, d_v, nullptr, nullptr, d_ch, nch);
+      ordered_squares_binade_kernel<<<1, 256>>>(d_t, nullptr, d_ch);
+      ordered_squares_pairs_kernel<<<(nch + 3) / 4, 128>>>(d_t, 1, nullptr, d_v, nullptr, nullptr, d_ch, nch);
+      ordered_squares_resolve_kernel<<<1, 32>>>(d_t, nullptr, d_v, nullptr, nullptr, d_ch, d_out, d_rep);
+    } else {
+      squares_exact_kernel<<<1, 32>>>(d_t, nullptr, d_v, nullptr, nullptr, d_out, 1);
+    }
+    ck(cudaGetLastError());
+    ck(cudaDeviceSynchronize());
+  }
+  double out[2] = {0, 0};
+  unsigned long long rep = 0;
+  ck(cudaMemcpy(out, d_out, sizeof(out), cudaMemcpyDeviceToHost));
+  ck(cudaMemcpy(&rep, d_rep, sizeof(rep), cudaMemcpyDeviceToHost));
+  cudaFree(d_v); cudaFree(d_out); cudaFree(d_t); cudaFree(d_ch); cudaFree(d_rep);
+  *parallel = out[0]; *serial = out[1];
+  if (replayed_chunks) *replayed_chunks = rep;
+  return rc;
 }
 
 }  // extern "C"

@@ -260,6 +260,78 @@ static int publish_tasks(qr_ctx *c, uint32_t k) {
   return QR_OK;
 }
 
+// REFERENCE mode: which accumulation a task's built child takes (sizes are known on the host)
+static uint32_t sq_chunks_host(uint64_t n) { return n > kSqSerialMax ? (uint32_t) ((n + kSqChunk - 1) / kSqChunk) : 0u; }
+static uint32_t built_size_host(const NodeTask &t) { return t.whole ? t.n : (t.build_left ? t.lcount : t.n - t.lcount); }
+static void plan_exact_tasks(qr_ctx *c, uint32_t k) {
+  uint32_t chunk0 = 0;
+  for (uint32_t j = 0; j < k; ++j) {
+    NodeTask &t = c->h_tasks[j];
+    const uint32_t built = built_size_host(t);
+    t.walk = (c->d_perm != nullptr && built >= c->walk_min && t.slotB >= 0) ? 1u : 0u;
+    t.sq_chunk0 = chunk0;
+    chunk0 += sq_chunks_host(built);
+  }
+}
+
+// REFERENCE mode: the built child of every task in the reference's accumulation order (qr_exact_kernels.cuh).  Small
+// children: a warp per (feature, task) over the list; large ones (NodeTask::walk, set by the host, which knows the sizes):
+// a thread per histogram cell over the dataset's sorted lists.  Squares: the chain for short lists, the parallel scheme
+// for long ones (NodeTask::sq_chunk0).
+static int launch_exact_hist(qr_ctx *c, uint32_t k) {
+  const uint32_t F = (uint32_t) c->F;
+  WalkList wl{};
+  uint32_t total_chunks = 0;
+  bool whole = false;
+  for (uint32_t j = 0; j < k; ++j) {
+    const NodeTask &t = c->h_tasks[j];
+    if (t.walk) { if (wl.n == kWalkMax) { set_error("internal: more than %u large nodes in a round", kWalkMax); return QR_ECUDA; } wl.idx[wl.n++] = j; whole = whole || t.whole; }
+    total_chunks = std::max(total_chunks, t.sq_chunk0 + sq_chunks_host(built_size_host(t)));
+  }
+  if (wl.n < k)
+    QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
+      using B = decltype(tag);
+      QR_LAUNCH(c, PH_HIST, hist_exact_list_kernel<B>, dim3((F + kExactWarps - 1) / kExactWarps, k), kExactWarps * 32, 0, c->d_tasks,
+                c->d_lcount, c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lambda, c->d_thr_off, F, c->d_fskip, c->d_hist_sum,
+                c->d_hist_cnt, c->ncells);
+      return QR_OK;
+    }));
+  if (wl.n) {
+    const unsigned cblocks = (c->ncells + kWalkWarps - 1) / kWalkWarps;
+    if (whole) {   // the root: every document belongs to it
+      QR_LAUNCH(c, PH_HIST, hist_exact_walk_kernel<0>, dim3(cblocks, 1), kWalkWarps * 32, 0, c->d_tasks, wl, c->d_perm, c->d_cell_pos,
+                c->d_mark, 0u, c->d_lambda, c->d_thr_off, F, c->d_fskip, c->d_hist_sum, c->d_hist_cnt, c->ncells);
+    } else {
+      c->mark_tag = (c->mark_tag + 1u) & 0x0fffffffu;
+      if (c->mark_tag == 0u) c->mark_tag = 1u;
+      QR_LAUNCH(c, PH_HIST, mark_walk_kernel, dim3(296, wl.n), 256, 0, c->d_tasks, wl, c->d_lcount, c->d_ids[0], c->d_ids[1],
+                c->d_mark, c->mark_tag);
+#define QR_WALK_LAUNCH(KK)                                                                                                  \
+  QR_LAUNCH(c, PH_HIST, hist_exact_walk_kernel<KK>, dim3(cblocks, (wl.n + KK - 1) / KK), kWalkWarps * 32, 0, c->d_tasks, wl,   \
+            c->d_perm, c->d_cell_pos, c->d_mark, c->mark_tag, c->d_lambda, c->d_thr_off, F, c->d_fskip, c->d_hist_sum,      \
+            c->d_hist_cnt, c->ncells)
+      if (wl.n == 1) QR_WALK_LAUNCH(1);
+      else QR_WALK_LAUNCH(2);
+#undef QR_WALK_LAUNCH
+    }
+    QR_LAUNCH(c, PH_HIST, hist_exact_prefix_kernel, dim3((F + 63) / 64, wl.n), 64, 0, c->d_tasks, wl, c->d_thr_off, F,
+              c->d_hist_sum, c->d_hist_cnt, c->ncells);
+  }
+  QR_LAUNCH(c, PH_HIST, squares_exact_kernel, k, 32, 0, c->d_tasks, c->d_lcount, c->d_lambda, c->d_ids[0], c->d_ids[1],
+            c->d_partials, 0);
+  if (total_chunks) {
+    SqChunk *chunks = static_cast<SqChunk *>(c->d_sq_chunks);
+    QR_LAUNCH(c, PH_HIST, ordered_squares_sums_kernel, (total_chunks + 3) / 4, 128, 0, c->d_tasks, k, c->d_lcount, c->d_lambda,
+              c->d_ids[0], c->d_ids[1], chunks, total_chunks);
+    QR_LAUNCH(c, PH_HIST, ordered_squares_binade_kernel, k, 256, 0, c->d_tasks, c->d_lcount, chunks);
+    QR_LAUNCH(c, PH_HIST, ordered_squares_pairs_kernel, (total_chunks + 3) / 4, 128, 0, c->d_tasks, k, c->d_lcount, c->d_lambda,
+              c->d_ids[0], c->d_ids[1], chunks, total_chunks);
+    QR_LAUNCH(c, PH_HIST, ordered_squares_resolve_kernel, k, 32, 0, c->d_tasks, c->d_lcount, c->d_lambda, c->d_ids[0],
+              c->d_ids[1], chunks, c->d_partials, c->d_sq_replayed);
+  }
+  return QR_OK;
+}
+
 // Launches the histogram + split-scan kernels of a round whose task records were published.
 static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bool root, double built_docs) {
   const uint32_t F = (uint32_t) c->F;
@@ -270,15 +342,7 @@ static int launch_hist_and_scan(qr_ctx *c, uint32_t k, uint32_t total_slices, bo
       QR_LAUNCH(c, PH_HIST, prep_slots_kernel, dim3(std::max<uint32_t>(1, std::min<uint32_t>(32, (c->ncells + 1023) / 1024)), k),
                 256, 0, c->d_tasks, c->pack, c->d_hist_sum, c->d_hist_cnt, c->ncells, static_counts ? c->d_root_cnt : nullptr);
     if (c->exact) {
-      QR_TRY(dispatch_bins(c, [&](auto tag) -> int {
-        using B = decltype(tag);
-        QR_LAUNCH(c, PH_HIST, hist_exact_kernel<B>, dim3((F + 3) / 4, k), 128, 0, c->d_tasks, c->d_lcount,
-                  c->d_panels, c->N, c->d_ids[0], c->d_ids[1], c->d_lambda, c->d_thr_off, F, c->d_hist_sum,
-                  c->d_hist_cnt, c->ncells);
-        return QR_OK;
-      }));
-      QR_LAUNCH(c, PH_HIST, squares_exact_kernel, k, 32, 0, c->d_tasks, c->d_lcount, c->d_lambda, c->d_ids[0],
-                c->d_ids[1], c->d_partials);
+      QR_TRY(launch_exact_hist(c, k));
     } else {
       const size_t smem = (size_t) c->fpp * c->max_thr * 12;
       const bool use_smem = smem <= 200 * 1024;
@@ -416,6 +480,7 @@ static int build_root(qr_ctx *c) {
   t.hist_blk0 = 0; t.part_blk0 = 0; t.sq0 = 0; t.fused_sq = 0;
   const uint32_t slices = std::max<uint32_t>(1, (layout_n + t.hist_dpb - 1) / t.hist_dpb);
   t.hist_nblk = slices;
+  if (c->exact) plan_exact_tasks(c, 1);
   QR_TRACE_MARK(c); QR_TRACE_MARK(c);
   QR_TRY(publish_tasks(c, 1));
   QR_TRY(launch_hist_and_scan(c, 1, slices, true, (double) root.n));
@@ -635,6 +700,7 @@ static int expand_nodes_exact(qr_ctx *c, const std::vector<int> &S, bool build_c
     t.fused_sq = 1;
     t.parent_squares = nd.res.squares;
   }
+  plan_exact_tasks(c, k);
   QR_TRACE_MARK(c);
   c->pack.n = 0;
   QR_CUDA(cudaMemcpyAsync(c->d_tasks, c->h_tasks, k * sizeof(NodeTask), cudaMemcpyHostToDevice, c->stream));

@@ -7,20 +7,9 @@
 #include "qr_kernels.cuh"
 #include "qr_task.cuh"
 #include "qr_fast_kernels.cuh"
+#include "qr_exact_kernels.cuh"
 
 namespace qr {
-
-// segment (in buffer `dst`, or identity when whole && src == 2) whose histogram is built
-__device__ __forceinline__ uint32_t task_lcount(const NodeTask &t, const uint32_t *lcount, uint32_t task) {
-  return t.whole ? 0u : (t.lc_known ? t.lcount : lcount[task]);
-}
-
-__device__ __forceinline__ void built_segment(const NodeTask &t, uint32_t lcount, uint32_t &begin,
-                                              uint32_t &len) {
-  if (t.whole) { begin = t.lo; len = t.n; }
-  else if (t.build_left) { begin = t.lo; len = lcount; }
-  else { begin = t.lo + lcount; len = t.n - lcount; }
-}
 
 // Clears the histogram slot each task builds into.  For the root refresh the per-bin counts never
 // change from tree to tree ("count doesn't change, so no need to re-compute",
@@ -140,115 +129,6 @@ part_scatter_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const u
     }
     left_run += total;
     __syncthreads();
-  }
-}
-
-// REFERENCE order: one warp per (feature, task) walks the node's documents in list order;
-// documents of a 32-wide chunk that fall in the same bin are added one after the other in document
-// order (__match_any_sync ranks them), so every per-bin FP64 sum sees its addends in the sequence
-// the reference's loop does (rtnode_histogram.cc:51-58).  Then the sequential inclusive prefix
-// over bins (rtnode_histogram.cc:59-62).  The slot must be zero on entry.
-template <typename BinT>
-__global__ void __launch_bounds__(128)
-hist_exact_kernel(const NodeTask *__restrict__ tasks, const uint32_t *__restrict__ lcount,
-                  const uint4 *__restrict__ panels, size_t N, const uint32_t *__restrict__ ids0,
-                  const uint32_t *__restrict__ ids1, const double *__restrict__ lam,
-                  const uint32_t *__restrict__ thr_off, uint32_t F, unsigned long long *hsum,
-                  uint32_t *hcnt, uint32_t ncells) {
-  const uint32_t f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (f >= F) return;
-  const NodeTask t = tasks[blockIdx.y];
-  uint32_t seg0, n;
-  built_segment(t, task_lcount(t, lcount, blockIdx.y), seg0, n);
-  const bool identity = t.whole && t.src == 2;
-  const uint32_t *ids = (t.whole ? t.src : t.dst) == 1 ? ids1 : ids0;
-  const uint32_t lane = lane_id();
-  double *sum = reinterpret_cast<double *>(hsum + (size_t) t.slotB * ncells) + thr_off[f];
-  uint32_t *cnt = hcnt + (size_t) t.slotB * ncells + thr_off[f];
-  const uint32_t cells = thr_off[f + 1] - thr_off[f];
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t i = base + lane;
-    const bool act = i < n;
-    uint32_t b = 0xffffffffu;   // inactive lanes share a bin no document can have
-    double v = 0.0;
-    if (act) {
-      const uint32_t d = identity ? seg0 + i : ids[seg0 + i];
-      b = load_bin<BinT>(panels, N, f, d);
-      v = lam[d];
-    }
-    const uint32_t peers = __match_any_sync(0xffffffffu, b);
-    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-    uint32_t maxr = act ? __popc(peers) : 0u;
-    for (int o = 16; o > 0; o >>= 1) maxr = max(maxr, __shfl_xor_sync(0xffffffffu, maxr, o));
-    for (uint32_t r = 0; r < maxr; ++r) {
-      if (act && rank == r) { sum[b] += v; cnt[b] += 1u; }
-      __syncwarp();
-    }
-  }
-  __syncwarp();
-  if (lane == 0)
-    for (uint32_t k = 1; k < cells; ++k) { sum[k] += sum[k - 1]; cnt[k] += cnt[k - 1]; }
-}
-
-// squares_sum_ (rtnode_histogram.cc:65-69, 199-203), sequential in list order; one warp per task.
-__global__ void squares_exact_kernel(const NodeTask *__restrict__ tasks, const uint32_t *__restrict__ lcount,
-                                     const double *__restrict__ lam, const uint32_t *__restrict__ ids0,
-                                     const uint32_t *__restrict__ ids1, double *partials) {
-  const NodeTask t = tasks[blockIdx.x];
-  uint32_t seg0, n;
-  built_segment(t, task_lcount(t, lcount, blockIdx.x), seg0, n);
-  const bool identity = t.whole && t.src == 2;
-  const uint32_t *ids = (t.whole ? t.src : t.dst) == 1 ? ids1 : ids0;
-  const uint32_t lane = lane_id();
-  double acc = 0.0;
-  for (uint32_t base = 0; base < n; base += 32) {
-    const uint32_t i = base + lane;
-    double v = 0.0;
-    if (i < n) v = lam[identity ? seg0 + i : ids[seg0 + i]];
-    const uint32_t cntk = min(32u, n - base);
-    if (t.fused_sq) {
-      for (uint32_t k = 0; k < cntk; ++k) { const double vk = __shfl_sync(0xffffffffu, v, k); acc = fma(vk, vk, acc); }
-    } else {
-      for (uint32_t k = 0; k < cntk; ++k) { const double vk = __shfl_sync(0xffffffffu, v, k); acc = __dadd_rn(acc, __dmul_rn(vk, vk)); }
-    }
-  }
-  if (lane == 0) partials[t.sq0] = acc;
-}
-
-// ------------------------------------------------------------------------------------------
-// Leaf outputs (RegressionTree::update_output, rt.cc:165-207) and score update
-// (Mart::update_modelscores, mart.cc:459-468).
-// ------------------------------------------------------------------------------------------
-
-
-// REFERENCE: one warp per leaf, sums in list order.
-__global__ void __launch_bounds__(32)
-leaf_exact_kernel(const LeafSeg *__restrict__ segs, const uint32_t *__restrict__ ids0,
-                  const uint32_t *__restrict__ ids1, const double *__restrict__ lam,
-                  const double *__restrict__ wgt, double *leafval, uint32_t *__restrict__ leaf_of_doc) {
-  const uint32_t leaf = blockIdx.x;
-  const LeafSeg sg = segs[leaf];
-  const uint32_t *ids = sg.buf == 1 ? ids1 : ids0;
-  const uint32_t lane = lane_id();
-  double s1 = 0.0, s2 = 0.0;
-  for (uint32_t base = 0; base < sg.n; base += 32) {
-    const uint32_t i = base + lane;
-    double v = 0.0, w = 0.0;
-    if (i < sg.n) {
-      const uint32_t d = sg.buf == 2 ? sg.lo + i : ids[sg.lo + i];
-      leaf_of_doc[d] = leaf;
-      v = lam[d];
-      if (wgt) w = wgt[d];
-    }
-    const uint32_t cntk = min(32u, sg.n - base);
-    for (uint32_t k = 0; k < cntk; ++k) {
-      s1 += __shfl_sync(0xffffffffu, v, k);
-      s2 += __shfl_sync(0xffffffffu, w, k);
-    }
-  }
-  if (lane == 0) {
-    if (wgt) leafval[leaf] = s2 >= DBL_EPSILON ? s1 / s2 : 0.0;   // rt.cc:200
-    else leafval[leaf] = s1 / (double) sg.n;                      // rt.cc:178
   }
 }
 

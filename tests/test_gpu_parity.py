@@ -132,6 +132,67 @@ def test_fit_tree_reference_mode_is_bit_exact(cfg):
 
 
 @pytest.mark.parametrize("cfg", [
+    dict(n=20000, f=30, q=200, gridded=True, nthr=0, leaves=32, minls=1),     # 8-bit bins
+    dict(n=6000, f=20, q=60, gridded=False, nthr=0, leaves=16, minls=3),      # one bin per distinct value: 16-bit bins
+    dict(n=9000, f=17, q=90, gridded=True, nthr=0, leaves=64, minls=1, algo="MART"),
+])
+def test_reference_mode_large_node_path_is_bit_exact(cfg, monkeypatch):
+    """REFERENCE mode accumulates large nodes by walking per-feature lists of documents sorted by (bin, document)
+    (hist_exact_walk_kernel) and long squares sums by the parallel ordered scheme: with QR_EXACT_WALK_MIN=1 every
+    built child above N/16 documents takes that path; the tree must still be the reference's bit for bit."""
+    monkeypatch.setenv("QR_EXACT_WALK_MIN", "1")
+    x, l, off = common.dataset(n=cfg["n"], f=cfg["f"], q=cfg["q"], gridded=cfg["gridded"])
+    algo = cfg.get("algo", "LAMBDAMART")
+    lam, w = _gradients(x, l, off, 3)
+    if algo == "MART":
+        w = None
+    ob = po.Binning(np.ascontiguousarray(x.T), cfg["nthr"])
+    want = ob.fit_tree(lam, w, nleaves=cfg["leaves"], minls=cfg["minls"])
+    with api.Trainer(x, l, off, algo=algo, nleaves=cfg["leaves"], minleafsupport=cfg["minls"],
+                     nthresholds=cfg["nthr"], hist_mode=api.HIST_REFERENCE) as tr:
+        tr.set_pseudoresponses(lam, w)
+        got = tr.fit_regressor_on_gradient()
+        leaf = tr.get_leaf_assignment()
+    assert common.same_structure(got, want), common.describe_tree_diff(got, want)
+    assert np.array_equal(got["value"], want["value"]), common.describe_tree_diff(got, want)
+    assert np.array_equal(got["count"], want["count"])
+    assert np.array_equal(got["deviance"][got["feature"] >= 0], want["deviance"][want["feature"] >= 0])
+    assert np.array_equal(leaf, want["leaf_of_doc"])
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_ordered_squares_scheme_equals_the_sequential_chain(fused):
+    """squares_sum_ is ONE sequentially rounded chain over a node's documents (rtnode_histogram.cc:65-69, 199-203);
+    REFERENCE mode computes long ones in parallel (per-chunk parity -> increment functions, qr_exact_kernels.cuh).
+    Bit equality with the plain chain on inputs chosen to hurt: wide exponent ranges, zeros, runs of exact ties,
+    magnitudes that shrink or grow along the list, a huge first addend."""
+    rng = np.random.default_rng(3)
+    n = 300_000
+    cases = {
+        "pseudo-responses": rng.normal(0, 1e-3, n),
+        "wide exponents": rng.normal(0, 1, n) * np.exp2(rng.integers(-20, 20, n)),
+        "zeros and eighths": rng.integers(-8, 9, n) / 8.0 * (rng.random(n) > 0.25),
+        "shrinking": rng.random(n) * np.exp2(-(np.arange(n) % 1000)),
+        "growing": rng.random(n) * np.exp2(np.arange(n) / n * 60 - 30),
+        "ties": np.concatenate([[741456.0], rng.integers(1, 16, n - 1) * 2.0 ** -7 * rng.choice([-1, 1], n - 1)]),
+        "tiny": rng.normal(0, 1e-160, n),
+        "short": rng.normal(0, 1, 4097),
+    }
+    for name, v in cases.items():
+        par, ser, replayed = api.selftest_ordered_squares(v, fused)
+        want = 0.0
+        if len(v) <= 5000:   # the chain in Python for the short case (no fused multiply-add in numpy: unfused only)
+            for xv in v:
+                want = want + float(xv) * float(xv)
+            if not fused:
+                assert ser == want, name
+        assert par == ser, (name, par, ser)
+        assert np.isfinite(par) and par > 0
+        if name in ("pseudo-responses", "ties"):
+            assert replayed <= 40, (name, replayed)    # the scheme, not the fallback, did the work
+
+
+@pytest.mark.parametrize("cfg", [
     dict(n=3000, f=20, q=30, gridded=True, nthr=0, leaves=12, minls=1),
     dict(n=3000, f=20, q=30, gridded=False, nthr=0, leaves=8, minls=1),
     dict(n=6000, f=40, q=60, gridded=True, nthr=0, leaves=24, minls=20),
@@ -173,7 +234,7 @@ def test_oblivious_tree(algo, depth, mode):
     ob = po.Binning(np.ascontiguousarray(x.T), 0)
     want = ob.fit_tree(lam, w, nleaves=1 << depth, minls=1, depth=depth)
     with api.Trainer(x, l, off, algo=algo, treedepth=depth, hist_mode=mode) as tr:
-        tr.set_pseudoresponses(lam, w if w is not None else np.zeros_like(lam))
+        tr.set_pseudoresponses(lam, w)
         got = tr.fit_regressor_on_gradient()
         leaf = tr.get_leaf_assignment()
     assert common.same_structure(got, want), common.describe_tree_diff(got, want)
