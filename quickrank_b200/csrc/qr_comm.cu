@@ -531,19 +531,17 @@ int comm_reduce_tasks(qr_ctx *ctx, uint32_t k, bool root) {
   return QR_OK;
 }
 
-__global__ void leaf_values_kernel(const double2 *__restrict__ leafsum, const unsigned long long *__restrict__ leafn,
-                                   uint32_t nleaves, bool newton, double *leafval) {
+__global__ void leaf_values_kernel(const longlong2 *__restrict__ leafsum, const unsigned long long *__restrict__ leafn,
+                                   uint32_t nleaves, bool newton, const int *__restrict__ qexp, double *leafval) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nleaves) return;
-  const double2 s = leafsum[i];
-  if (newton) leafval[i] = s.y >= DBL_EPSILON ? s.x / s.y : 0.0;   // rt.cc:200
-  else leafval[i] = s.x / (double) leafn[i];                       // rt.cc:178
+  leafval[i] = leaf_value_of(leafsum[i], leafn[i], newton, qexp);   // exact integer sums: the same on every rank
 }
 
 int comm_leaf_values(qr_ctx *ctx, uint32_t nleaves) {
   Comm *c = ctx->comm;
   cudaStream_t st = ctx->stream;
-  QR_NCCL(g_nccl.AllReduce(ctx->d_leafsum, ctx->d_leafsum, (size_t) nleaves * 2, ncclFloat64, ncclSum, c->nccl, st));
+  QR_NCCL(g_nccl.AllReduce(ctx->d_leafsum, ctx->d_leafsum, (size_t) nleaves * 2, ncclInt64, ncclSum, c->nccl, st));
   // global leaf sizes for the MART mean
   std::vector<unsigned long long> n(std::max<uint32_t>(nleaves, 1));
   for (uint32_t k = 0; k < nleaves; ++k) n[k] = ctx->nodes[ctx->leaves[k]].res.n;
@@ -553,7 +551,7 @@ int comm_leaf_values(qr_ctx *ctx, uint32_t nleaves) {
     QR_CUDA(cudaMalloc((void **) &c->d_leafn, c->leafn_cap * sizeof(unsigned long long)));
   }
   QR_CUDA(cudaMemcpyAsync(c->d_leafn, n.data(), nleaves * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
-  leaf_values_kernel<<<(nleaves + 63) / 64, 64, 0, st>>>(ctx->d_leafsum, c->d_leafn, nleaves, ctx->lambda, ctx->d_leafval);
+  leaf_values_kernel<<<(nleaves + 63) / 64, 64, 0, st>>>(reinterpret_cast<const longlong2 *>(ctx->d_leafsum), c->d_leafn, nleaves, ctx->lambda, ctx->d_qexp, ctx->d_leafval);
   ctx->launches++;
   QR_CUDA(cudaGetLastError());
   QR_CUDA(cudaStreamSynchronize(st));   // `n` is pageable: the copy above must have left it

@@ -1241,37 +1241,41 @@ scan_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ TaskPack
 
 // ------------------------------------------------------------------------------------------
 // Leaf outputs (RegressionTree::update_output, rt.cc:165-207): per-leaf sums of the pseudo-responses
-// and of the Newton weights in ONE pass over node_of_doc, in FP64 with a fixed reduction shape
-// (a warp takes 32 consecutive documents per step: the documents of each leaf present are summed in document
-// order by the first of them and added to the warp's per-leaf accumulator in shared memory; warps, then
-// blocks are summed in index order): the result does not depend on how the tree was grown.  Also writes the
-// doc -> leaf map used by the score update (mart.cc:459-468).
+// and of the Newton weights in ONE pass over node_of_doc (a warp takes 32 consecutive documents per step: the
+// documents of each leaf present are summed by the first of them and added to the warp's per-leaf accumulator in
+// shared memory; warps, then blocks are summed).  Also writes the doc -> leaf map used by the score update
+// (mart.cc:459-468).
 // ------------------------------------------------------------------------------------------
 constexpr uint32_t kLeafWarpDocs = 256;   // documents per warp
 
+// The sums are exact integers — the fixed-point pseudo-responses the histograms are made of (lamq, scale qexp[0]) and
+// the weights at their own scale (qexp[1]) — so a leaf's output is the same for any slicing of the documents over
+// blocks and over GPUs: sharded runs grow bit-identical models.
 __global__ void leaf_node_kernel(const uint16_t *__restrict__ node, const uint16_t *__restrict__ leaf_lut,
-                                 uint32_t nnodes, uint32_t nl, const double *__restrict__ lam,
-                                 const double *__restrict__ wgt, size_t N, double2 *partials,
-                                 uint32_t *__restrict__ leaf_of_doc) {
+                                 uint32_t nnodes, uint32_t nl, const long long *__restrict__ lamq,
+                                 const double *__restrict__ wgt, const int *__restrict__ qexp, size_t N,
+                                 longlong2 *partials, uint32_t *__restrict__ leaf_of_doc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const uint32_t nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-  double2 *tab = reinterpret_cast<double2 *>(smem_raw);                    // [nwarps][nl] per-warp leaf accumulators
-  double2 *stage = tab + (size_t) nwarps * nl;                              // [nwarps][32] the step's values
+  longlong2 *tab = reinterpret_cast<longlong2 *>(smem_raw);                 // [nwarps][nl] per-warp leaf accumulators
+  longlong2 *stage = tab + (size_t) nwarps * nl;                            // [nwarps][32] the step's values
   uint16_t *lut = reinterpret_cast<uint16_t *>(stage + (size_t) nwarps * 32);   // [nnodes]
-  for (uint32_t i = threadIdx.x; i < nwarps * nl; i += blockDim.x) tab[i] = make_double2(0.0, 0.0);
+  for (uint32_t i = threadIdx.x; i < nwarps * nl; i += blockDim.x) tab[i] = make_longlong2(0ll, 0ll);
   for (uint32_t i = threadIdx.x; i < nnodes; i += blockDim.x) lut[i] = leaf_lut[i];
-  double2 *mine = tab + (size_t) warp * nl;
-  double2 *sv = stage + (size_t) warp * 32;
+  longlong2 *mine = tab + (size_t) warp * nl;
+  longlong2 *sv = stage + (size_t) warp * 32;
   const size_t base = ((size_t) blockIdx.x * nwarps + warp) * kLeafWarpDocs;
   constexpr uint32_t kIt = kLeafWarpDocs / 32;
+  const int wexp = wgt ? qexp[1] : 0;
   // every load of the warp's documents is issued up front (one memory round trip instead of one per step)
   uint32_t nid[kIt];
-  double l1[kIt], l2[kIt];
+  long long l1[kIt];
+  double l2[kIt];
 #pragma unroll
   for (uint32_t it = 0; it < kIt; ++it) {
     const size_t d = base + it * 32 + lane;
     nid[it] = d < N ? node[d] : 0xffffffffu;
-    l1[it] = d < N ? lam[d] : 0.0;
+    l1[it] = d < N ? lamq[d] : 0ll;
     l2[it] = (d < N && wgt) ? wgt[d] : 0.0;
   }
   __syncthreads();   // (the node -> leaf table)
@@ -1283,17 +1287,17 @@ __global__ void leaf_node_kernel(const uint16_t *__restrict__ node, const uint16
       leaf = lut[nid[it]];
       leaf_of_doc[d] = leaf;
     }
-    sv[lane] = make_double2(l1[it], l2[it]);
-    // the documents of each leaf present in this step are summed by the first of them, in document order
+    sv[lane] = make_longlong2(l1[it], __double2ll_rn(ldexp(l2[it], wexp)));
+    // the documents of each leaf present in this step are summed by the first of them
     const uint32_t peers = __match_any_sync(0xffffffffu, leaf);
     __syncwarp();
     if (d < N && (peers & ((1u << lane) - 1u)) == 0u) {
-      double a = 0.0, b = 0.0;
+      long long a = 0, b = 0;
       for (uint32_t m = peers; m; m &= m - 1u) {
-        const double2 x = sv[__ffs(m) - 1];
+        const longlong2 x = sv[__ffs(m) - 1];
         a += x.x; b += x.y;
       }
-      double2 acc = mine[leaf];
+      longlong2 acc = mine[leaf];
       acc.x += a; acc.y += b;
       mine[leaf] = acc;
     }
@@ -1301,28 +1305,27 @@ __global__ void leaf_node_kernel(const uint16_t *__restrict__ node, const uint16
   }
   __syncthreads();
   for (uint32_t l = threadIdx.x; l < nl; l += blockDim.x) {
-    double a = 0.0, b = 0.0;
-    for (uint32_t w = 0; w < nwarps; ++w) { const double2 x = tab[(size_t) w * nl + l]; a += x.x; b += x.y; }
-    partials[(size_t) blockIdx.x * nl + l] = make_double2(a, b);
+    long long a = 0, b = 0;
+    for (uint32_t w = 0; w < nwarps; ++w) { const longlong2 x = tab[(size_t) w * nl + l]; a += x.x; b += x.y; }
+    partials[(size_t) blockIdx.x * nl + l] = make_longlong2(a, b);
   }
 }
 
-// one warp per leaf: block partials in index order (32 interleaved running sums, then a butterfly)
-__global__ void leaf_reduce_kernel(const double2 *__restrict__ partials, uint32_t nblocks, uint32_t nl,
-                                   const unsigned long long *__restrict__ leafn, bool newton, double2 *leafsum,
-                                   double *leafval) {
+// one warp per leaf: block partials summed (integers: any order)
+__global__ void leaf_reduce_kernel(const longlong2 *__restrict__ partials, uint32_t nblocks, uint32_t nl,
+                                   const unsigned long long *__restrict__ leafn, bool newton, const int *__restrict__ qexp,
+                                   longlong2 *leafsum, double *leafval) {
   const uint32_t l = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
   if (l >= nl) return;
-  double a = 0.0, b = 0.0;
-  for (uint32_t k = lane; k < nblocks; k += 32) { const double2 x = partials[(size_t) k * nl + l]; a += x.x; b += x.y; }
+  long long a = 0, b = 0;
+  for (uint32_t k = lane; k < nblocks; k += 32) { const longlong2 x = partials[(size_t) k * nl + l]; a += x.x; b += x.y; }
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(0xffffffffu, a, o);
     b += __shfl_xor_sync(0xffffffffu, b, o);
   }
   if (lane == 0) {
-    leafsum[l] = make_double2(a, b);
-    if (newton) leafval[l] = b >= DBL_EPSILON ? a / b : 0.0;   // rt.cc:200
-    else leafval[l] = a / (double) leafn[l];                   // rt.cc:178
+    leafsum[l] = make_longlong2(a, b);
+    leafval[l] = leaf_value_of(make_longlong2(a, b), leafn[l], newton, qexp);
   }
 }
 

@@ -349,7 +349,7 @@ rank_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
 }
 
 // mean over queries (metric.h:96-105).  REFERENCE: sequential sum in query order.
-__global__ void ndcg_mean_kernel(const double *qndcg, uint32_t Q, uint32_t Qdiv, bool exact, double *out) {
+__global__ void ndcg_mean_kernel(const double *qndcg, uint32_t Q, uint32_t Qdiv, bool exact, int qshift, double *out) {
   __shared__ double part[1024];
   if (exact) {
     // one warp, values fetched 32 at a time, summed in order by every lane
@@ -364,18 +364,19 @@ __global__ void ndcg_mean_kernel(const double *qndcg, uint32_t Q, uint32_t Qdiv,
     if (threadIdx.x == 0) out[0] = Qdiv ? acc / (double) Qdiv : 0.0;
     return;
   }
-  // deterministic: contiguous chunk per thread, then a fixed-shape tree
-  uint32_t per = (Q + blockDim.x - 1) / blockDim.x;
-  uint32_t b = threadIdx.x * per, e = min(Q, b + per);
-  double acc = 0.0;
-  for (uint32_t i = b; i < e; ++i) acc += qndcg[i];
-  part[threadIdx.x] = acc;
+  // FAST: an exact integer sum of the per-query values in fixed point (scale 2^qshift: Q_global values below 2 stay
+  // under 2^63), so the mean is the same for any reduction shape and any sharding of the queries over GPUs
+  long long acc = 0;
+  for (uint32_t i = threadIdx.x; i < Q; i += blockDim.x) acc += __double2ll_rn(ldexp(qndcg[i], qshift));
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  long long *parti = reinterpret_cast<long long *>(part);
+  if (lane_id() == 0) parti[threadIdx.x >> 5] = acc;
   __syncthreads();
-  for (uint32_t st = blockDim.x >> 1; st > 0; st >>= 1) {
-    if (threadIdx.x < st) part[threadIdx.x] += part[threadIdx.x + st];
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    long long tot = 0;
+    for (uint32_t w = 0; w < (blockDim.x >> 5); ++w) tot += parti[w];
+    *reinterpret_cast<long long *>(out) = tot;   // the caller (all-reduces and) scales it
   }
-  if (threadIdx.x == 0) out[0] = Qdiv ? part[0] / (double) Qdiv : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -645,12 +646,13 @@ __global__ void maxabs_kernel(const double *lam, size_t N, unsigned long long *m
   if (lane_id() == 0 && m > 0.0) atomicMax(maxbits, (unsigned long long) __double_as_longlong(m));
 }
 
-// qexp = 2^k scale such that N_total * max|q| < 2^62
+// qexp = 2^k scale such that N_total * max|q| < 2^62; thread 0: pseudo-responses, thread 1: their weights (Newton
+// denominators of the leaf outputs, rt.cc:186-200)
 __global__ void choose_scale_kernel(const unsigned long long *maxbits, int log2n_ceil, int *qexp) {
-  double m = __longlong_as_double((long long) *maxbits);
+  double m = __longlong_as_double((long long) maxbits[threadIdx.x]);
   int e = 0;
   if (m > 0.0) frexp(m, &e);        // m = f * 2^e, f in [0.5, 1)
-  *qexp = (62 - log2n_ceil) - e;    // |lam * 2^qexp| < 2^(62 - log2n)
+  qexp[threadIdx.x] = (62 - log2n_ceil) - e;    // |lam * 2^qexp| < 2^(62 - log2n)
 }
 
 // also puts every document back into the root (node 0) for the tree about to be grown

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <float.h>
 #include <stdint.h>
 
 namespace qr {
@@ -95,6 +96,15 @@ struct U128 { unsigned long long lo, hi; };
 __device__ __forceinline__ void u128_add(U128 &a, unsigned long long lo, unsigned long long hi) {
   a.lo += lo;
   a.hi += hi + (a.lo < lo);
+}
+
+// FAST mode: leaf output from the exact fixed-point sums of the pseudo-responses (scale qexp[0]) and of their weights
+// (scale qexp[1]): rt.cc:178 mean of the pseudo-responses, rt.cc:200 Newton step
+__device__ __forceinline__ double leaf_value_of(longlong2 s, unsigned long long n, bool newton, const int *qexp) {
+  const double a = (double) s.x * ldexp(1.0, -qexp[0]);
+  if (!newton) return a / (double) n;
+  const double b = (double) s.y * ldexp(1.0, -qexp[1]);
+  return b >= DBL_EPSILON ? a / b : 0.0;
 }
 
 }  // namespace qr

@@ -535,8 +535,8 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
   QR_TRY(dev_alloc(&c->d_lambda, N));
   QR_TRY(dev_alloc(&c->d_weight, N));
   QR_TRY(dev_alloc(&c->d_lamq, N));
-  QR_TRY(dev_alloc(&c->d_maxabs, 1));
-  QR_TRY(dev_alloc(&c->d_qexp, 1));
+  QR_TRY(dev_alloc(&c->d_maxabs, 2));
+  QR_TRY(dev_alloc(&c->d_qexp, 2));
   QR_TRY(dev_alloc(&c->d_rankpos, N));
   QR_TRY(dev_alloc(&c->d_qndcg, Q));
   QR_TRY(dev_alloc(&c->d_metric, 1));
@@ -545,7 +545,7 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
   QR_CUDA(cudaMemset(c->d_lambda, 0, N * sizeof(double)));
   QR_CUDA(cudaMemset(c->d_weight, 0, N * sizeof(double)));
   QR_CUDA(cudaMemset(c->d_leaf_of_doc, 0, N * sizeof(uint32_t)));
-  QR_CUDA(cudaMemset(c->d_qexp, 0, sizeof(int)));
+  QR_CUDA(cudaMemset(c->d_qexp, 0, 2 * sizeof(int)));
 
   const size_t maxleaves = c->oblivious ? ((size_t) 1 << params->treedepth) : std::max<size_t>(params->nleaves, 1);
   c->max_tasks = (uint32_t) maxleaves + 1;
@@ -756,22 +756,24 @@ static int compute_pseudo(qr_ctx *c) {
 
 static int evaluate(qr_ctx *c, double *metric) {
   QR_TRY(ensure_ranking(c));
+  // FAST: the per-query values are added as fixed-point integers (exact, so the mean does not depend on how the
+  // queries are spread over blocks or GPUs); REFERENCE: the sequential sum in query order (metric.h:96-105)
+  const int qshift = 62 - (ceil_log2(c->Q_global ? c->Q_global : c->Q) + 1);
   {
     PhaseTimer pt(c, PH_RANK);
-    if (c->comm) {
-      // sum of per-query NDCG over all ranks, divided by the global query count
-      QR_LAUNCH(c, PH_RANK, ndcg_mean_kernel, 1, c->exact ? 32 : 1024, 0, c->d_qndcg, (uint32_t) c->Q, 1u,
-                c->exact, c->d_metric);
-      QR_TRY(comm_allreduce_sum_f64(c->comm, c->d_metric, 1, c->stream));
-    } else {
-      QR_LAUNCH(c, PH_RANK, ndcg_mean_kernel, 1, c->exact ? 32 : 1024, 0, c->d_qndcg, (uint32_t) c->Q,
-                (uint32_t) c->Q, c->exact, c->d_metric);
-    }
+    QR_LAUNCH(c, PH_RANK, ndcg_mean_kernel, 1, c->exact ? 32 : 1024, 0, c->d_qndcg, (uint32_t) c->Q, (uint32_t) c->Q,
+              c->exact, qshift, c->d_metric);
+    if (c->comm) QR_TRY(comm_allreduce_sum_u64(c->comm, reinterpret_cast<unsigned long long *>(c->d_metric), 1, c->stream));
   }
   double m = 0;
   QR_CUDA(cudaMemcpyAsync(&m, c->d_metric, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   QR_CUDA(cudaStreamSynchronize(c->stream));
-  if (c->comm) m /= (double) c->Q_global;
+  if (!c->exact) {
+    long long q;
+    memcpy(&q, &m, sizeof(q));
+    const size_t nq = c->comm ? c->Q_global : c->Q;
+    m = nq ? std::ldexp((double) q, -qshift) / (double) nq : 0.0;
+  }
   if (metric) *metric = m;
   return QR_OK;
 }

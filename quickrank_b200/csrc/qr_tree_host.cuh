@@ -30,10 +30,11 @@ static void release_slot(qr_ctx *c, int &s) {
 static int prepare_fixed_point(qr_ctx *c) {
   if (c->exact) return QR_OK;
   PhaseTimer pt(c, PH_HIST);
-  QR_CUDA(cudaMemsetAsync(c->d_maxabs, 0, sizeof(unsigned long long), c->stream));
+  QR_CUDA(cudaMemsetAsync(c->d_maxabs, 0, 2 * sizeof(unsigned long long), c->stream));
   QR_LAUNCH(c, PH_HIST, maxabs_kernel, 296, 256, 0, c->d_lambda, c->N, c->d_maxabs);
-  if (c->comm) QR_TRY(comm_allreduce_max_u64(c->comm, c->d_maxabs, 1, c->stream));
-  QR_LAUNCH(c, PH_HIST, choose_scale_kernel, 1, 1, 0, c->d_maxabs, ceil_log2(c->N_global) + 1, c->d_qexp);
+  if (c->lambda) QR_LAUNCH(c, PH_HIST, maxabs_kernel, 296, 256, 0, c->d_weight, c->N, c->d_maxabs + 1);   // leaf outputs' denominators
+  if (c->comm) QR_TRY(comm_allreduce_max_u64(c->comm, c->d_maxabs, 2, c->stream));
+  QR_LAUNCH(c, PH_HIST, choose_scale_kernel, 1, 2, 0, c->d_maxabs, ceil_log2(c->N_global) + 1, c->d_qexp);
   QR_LAUNCH(c, PH_HIST, quantize_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_lambda, c->N,
             c->d_qexp, c->d_lamq, c->d_node);
   return QR_OK;
@@ -925,10 +926,10 @@ static int fit_leaves_fast(qr_ctx *c) {
     QR_TRY(dev_alloc(&c->d_leaf_partials, c->leaf_part_cap));
   }
   const double *w = c->lambda ? c->d_weight : nullptr;
-  QR_LAUNCH(c, PH_LEAF, leaf_node_kernel, blocks, wpb * 32, smem, c->d_node, d_lut, (uint32_t) nn, (uint32_t) nl, c->d_lambda,
-            w, c->N, c->d_leaf_partials, c->d_leaf_of_doc);
-  QR_LAUNCH(c, PH_LEAF, leaf_reduce_kernel, (unsigned) ((nl + 7) / 8), 256, 0, c->d_leaf_partials, blocks, (uint32_t) nl,
-            d_leafn, c->lambda, c->d_leafsum, c->d_leafval);
+  QR_LAUNCH(c, PH_LEAF, leaf_node_kernel, blocks, wpb * 32, smem, c->d_node, d_lut, (uint32_t) nn, (uint32_t) nl, c->d_lamq,
+            w, c->d_qexp, c->N, reinterpret_cast<longlong2 *>(c->d_leaf_partials), c->d_leaf_of_doc);
+  QR_LAUNCH(c, PH_LEAF, leaf_reduce_kernel, (unsigned) ((nl + 7) / 8), 256, 0, reinterpret_cast<const longlong2 *>(c->d_leaf_partials),
+            blocks, (uint32_t) nl, d_leafn, c->lambda, c->d_qexp, reinterpret_cast<longlong2 *>(c->d_leafsum), c->d_leafval);
   if (c->comm) QR_TRY(comm_leaf_values(c, (uint32_t) nl));
   QR_CUDA(cudaMemcpyAsync(c->h_leafval, c->d_leafval, nl * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   QR_CUDA(cudaStreamSynchronize(c->stream));
