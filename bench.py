@@ -96,13 +96,16 @@ class ClockSampler:
 
 
 def tree_digest(trees):
-    """SHA-1 over (split feature, threshold index, node size) of the given trees, in pre-order.  Histogram sums are
-    exact integers in the benchmarked mode, so the digest is the same on 1, 2, 4 and 8 GPUs."""
+    """SHA-1 over (split feature, threshold index, node size, leaf output bits) of the given trees, in pre-order.
+    Histogram sums, leaf sums and the NDCG mean are exact integers in the benchmarked mode, so the digest — the whole
+    model, leaf outputs included — is the same on 1, 2, 4 and 8 GPUs."""
     import hashlib
     h = hashlib.sha1()
     for t in trees:
         for k in ("feature", "threshold_idx", "count"):
             h.update(np.ascontiguousarray(t[k]).astype(np.int64).tobytes())
+        leaves = np.asarray(t["feature"]) < 0
+        h.update(np.ascontiguousarray(np.asarray(t["value"], np.float64)[leaves]).tobytes())
     return h.hexdigest()
 
 
@@ -419,8 +422,9 @@ def run_ours(args):
 
     # ---- parity block: digest of the job's first trees + the same trees from the unmodified reference ----
     parity = {"trees": PARITY_TREES, "digest_sha1": tree_digest(first_trees),
-              "digest_of": "(split feature, threshold index, node size) of the first %d trees, pre-order; fixed-point "
-                           "histograms make it identical for every number of GPUs" % PARITY_TREES}
+              "digest_of": "(split feature, threshold index, node size, leaf output bits) of the first %d trees, pre-order; "
+                           "fixed-point histograms, leaf sums and NDCG mean make the model bit-identical for every "
+                           "number of GPUs" % PARITY_TREES}
     reference_mode = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # Against the UNMODIFIED reference (oracle/_ref), stage by stage: each tree is fitted from the reference's own

@@ -191,25 +191,6 @@ struct qr_ctx {
   void *d_apply = nullptr, *h_apply = nullptr;   // staging of qr_apply_trees (device / pinned host)
   size_t apply_cap = 0;
 
-  // document sample (LambdaMartSelective, lambdamartselective.cc:188-215; qr_set_sample): the sampled documents are a
-  // dataset of their own — a sub-context cut from this one's bins — on which the pseudo-responses are computed and
-  // the tree is fitted; the tree is then applied to all documents of this context
-  std::vector<float> h_labels;              // host copies the samples are cut from
-  std::vector<uint32_t> h_qoff;
-  qr_ctx *sample = nullptr;
-  uint32_t *d_sample_ids = nullptr;         // [sample->N] document of this context behind each sampled document (ascending)
-  uint32_t *d_sample_keysrc = nullptr;      // [sample->N] document whose score the reference ranks the sampled document by
-  const double *d_sortkey = nullptr;        // (in the sub-context) scores the ranking is made from; null: d_scores
-  double *d_sortkey_buf = nullptr;
-  struct SampleTree {                       // the tree fitted on the sample, kept for update_modelscores
-    std::vector<int32_t> feature, left, right;
-    std::vector<uint32_t> tidx;
-    std::vector<float> thr;
-    std::vector<double> value;
-    qr_flat_tree flat{};
-    bool valid = false;
-  } sample_tree;
-
   qr::Comm *comm = nullptr;
   size_t N_global = 0, Q_global = 0;
   size_t N_local_max = 0;                   // largest shard (documents) over the ranks

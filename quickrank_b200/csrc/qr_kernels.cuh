@@ -123,37 +123,6 @@ __global__ void binning_kernel(const float *colmajor, size_t N, uint32_t F, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// Document samples (LambdaMartSelective): the sampled documents' rows of the bin matrix, their scores,
-// and the way back for the pseudo-responses.
-// ------------------------------------------------------------------------------------------
-__global__ void gather_panels_kernel(const uint4 *__restrict__ par, size_t Npar, const uint32_t *__restrict__ ids, size_t n,
-                                     uint32_t npanels, uint4 *panels, uint4 *rows) {
-  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t p = blockIdx.y;
-  if (i >= n) return;
-  const uint4 v = par[(size_t) p * Npar + ids[i]];
-  panels[(size_t) p * n + i] = v;
-  if (rows != nullptr) rows[i * npanels + p] = v;
-}
-// scores[i] = the sampled document's own score (used in rho, lambdamart.cc:132-134); sortkey[i] = the score the
-// reference ranks it by: scores_on_training_[d] with d the document's index WITHIN its query (lambdamart.cc:94 reads
-// the array without the query offset), reproduced as is
-__global__ void sample_scores_kernel(const double *__restrict__ par_scores, const uint32_t *__restrict__ ids,
-                                     const uint32_t *__restrict__ keysrc, size_t n, double *scores, double *sortkey) {
-  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  scores[i] = par_scores[ids[i]];
-  sortkey[i] = par_scores[keysrc[i]];
-}
-__global__ void sample_scatter_kernel(const double *__restrict__ lam, const double *__restrict__ w,
-                                      const uint32_t *__restrict__ ids, size_t n, double *plam, double *pw) {
-  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  plam[ids[i]] = lam[i];
-  if (w != nullptr) pw[ids[i]] = w[i];
-}
-
-// ------------------------------------------------------------------------------------------
 // Per-query ranking: std::sort(idx, comp = score[i] > score[j]) with libstdc++'s introsort,
 // reproduced move for move so that tied scores land where the reference puts them
 // (QueryResults::indexing_of_sorted_labels, queryresults.cc:37-53; SURVEY.md section 7.1 "Sort").

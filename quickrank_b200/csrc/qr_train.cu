@@ -497,8 +497,6 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
     if (q) maxlen = std::max<uint32_t>(maxlen, qoff[q] - qoff[q - 1]);
   }
   c->maxlen = (maxlen + 3u) & ~3u;
-  c->h_labels.assign(labels, labels + N);   // (document samples are cut from these, qr_set_sample)
-  c->h_qoff = qoff;
   std::vector<double> gain(N), idcg(Q), lg(c->maxlen + 1), invlg(c->maxlen + 1);
   for (size_t i = 0; i < N; ++i) gain[i] = std::pow(2.0, (double) labels[i]);              // dcg.cc:37
   for (uint32_t i = 0; i <= c->maxlen; ++i) {
@@ -703,38 +701,14 @@ static int ensure_ranking(qr_ctx *c) {
     attr_set = true;
   }
   const unsigned grid = (unsigned) ((c->Q + kRankWarps - 1) / kRankWarps);
-  QR_LAUNCH(c, PH_RANK, rank_kernel<kRankWarps>, grid, kRankWarps * 32, smem, c->d_sortkey ? c->d_sortkey : c->d_scores, c->d_labels,
+  QR_LAUNCH(c, PH_RANK, rank_kernel<kRankWarps>, grid, kRankWarps * 32, smem, c->d_scores, c->d_labels,
             c->d_gain, c->d_qoff, c->d_idcg, c->d_lg, (uint32_t) c->Q, c->maxlen, c->cutoff,
             c->d_rankpos, c->d_qndcg);
   c->ranking_valid = true;
   return QR_OK;
 }
 
-static int compute_pseudo(qr_ctx *c);
-// pseudo-responses of a sampled iteration: computed on the sample (absent documents take no part in any query's
-// ranked list, lambdamart.cc:84-103) and written back to the full arrays, which are zero elsewhere (:76-78)
-static int compute_pseudo_sampled(qr_ctx *c) {
-  qr_ctx *s = c->sample;
-  const size_t n = s->N;
-  const unsigned grid = (unsigned) ((n + 255) / 256);
-  sample_scores_kernel<<<grid, 256, 0, c->stream>>>(c->d_scores, c->d_sample_ids, c->d_sample_keysrc, n, s->d_scores, s->d_sortkey_buf);
-  c->launches++;
-  QR_CUDA(cudaGetLastError());
-  QR_CUDA(cudaStreamSynchronize(c->stream));
-  s->ranking_valid = false;
-  QR_TRY(compute_pseudo(s));
-  QR_CUDA(cudaStreamSynchronize(s->stream));
-  QR_CUDA(cudaMemsetAsync(c->d_lambda, 0, c->N * sizeof(double), c->stream));
-  if (c->lambda) QR_CUDA(cudaMemsetAsync(c->d_weight, 0, c->N * sizeof(double), c->stream));
-  sample_scatter_kernel<<<grid, 256, 0, c->stream>>>(s->d_lambda, c->lambda ? s->d_weight : nullptr, c->d_sample_ids, n, c->d_lambda, c->d_weight);
-  c->launches++;
-  QR_CUDA(cudaGetLastError());
-  c->maxabs_valid = false;
-  return QR_OK;
-}
-
 static int compute_pseudo(qr_ctx *c) {
-  if (c->sample) return compute_pseudo_sampled(c);
   if (!c->lambda) {
     PhaseTimer pt(c, PH_PSEUDO);
     QR_LAUNCH(c, PH_PSEUDO, mart_pseudo_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, c->d_scores,
