@@ -1,4 +1,13 @@
 // quickrank_b200 host layer — implementation.  See host/include/quickrank_host.h.
+//
+// Provenance: this file is the reference-facing HOST layer (north_star keeps QuickRank's CLI, Dataset API, XML model
+// format and training-loop control flow; the GPU engine sits below it behind include/quickrank_b200.h).  Its control
+// flow — Mart::learn / Dart::learn, DART's tree selection and weight normalisation, the XML and stdout formats, the
+// code generators — is a condensed restatement of hpclab/quickrank's src/learning/forests/{mart,dart}.cc,
+// src/io/generate_*.cc and src/data/*.cc (Reciprocal Public License 1.5), kept statement-compatible on purpose: the
+// std::rand() stream, the printed table and the saved model must equal the reference's for the parity tests to mean
+// anything.  It is derived work of that code and is to be read under the same licence; no arithmetic on the hot path
+// lives here (every pass over documents is a call into the C ABI), and it is not meant to grow.
 #include "quickrank_host.h"
 
 #include <algorithm>
