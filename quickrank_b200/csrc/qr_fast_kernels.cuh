@@ -637,29 +637,38 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
     kstamp(out.ktrace, kb, 4);
   }
   // the bins were accumulated with atomics by blocks on other SMs (or GPUs): read them from L2
-#pragma unroll
-  for (int i = 0; i < kPubCPT; ++i) {
-    const bool in = k0 + i < cells;
-    s[i] = in ? __ldcg(Rs + k0 + i) : 0ull;
-    c[i] = in ? __ldcg(Cc + k0 + i) : 0u;
-  }
   if (W > 1) {
-    // Every peer's bins in flight together: an NVLink load takes ~3 us, and left to itself ptxas adds each peer's
-    // values as they arrive to save registers, which serialises the round trips (7 peers x (sums, counts) = 24 us
-    // measured at 8 GPUs).  The empty asm statements take every loaded value as an operand, so all loads are issued
-    // before the first of them is waited for.
+    // The W copies of the chunk are read COALESCED — lane l of load i takes cell i * kPubThreads + tid, so a warp's
+    // load is 256 contiguous bytes of a peer's pool: an NVLink read moves whole 32-byte sectors and system-scope
+    // loads are not cached, so the scan's own layout (three consecutive cells per thread: a stride of 24 bytes
+    // between lanes) asked every sector three times over and was bound by the number of remote requests in flight
+    // per SM (24-28 us at 8 GPUs) — added up in that layout and handed to the scan's layout through shared memory.
+    // Every peer's loads are in flight together: left to itself ptxas adds each peer's values as they arrive to
+    // save registers, which serialises the NVLink round trips; the empty asm statements take every loaded value as
+    // an operand, so all loads are issued before the first of them is waited for.
+    __shared__ unsigned long long x_s[kPubThreads * kPubCPT];
+    __shared__ uint32_t x_c[kPubThreads * kPubCPT];
+    unsigned long long ts[kPubCPT];
+    uint32_t tc[kPubCPT];
     unsigned long long rs[kMaxPeers][kPubCPT];
     uint32_t rc[kMaxPeers][kPubCPT];
     const bool wc = COUNT && pv.with_counts;
+#pragma unroll
+    for (int i = 0; i < kPubCPT; ++i) {
+      const uint32_t j = (uint32_t) i * kPubThreads + tid;
+      ts[i] = j < cells ? __ldcg(Rs + j) : 0ull;
+      tc[i] = j < cells ? __ldcg(Cc + j) : 0u;
+    }
 #pragma unroll
     for (int pr = 0; pr < kMaxPeers; ++pr) {
       const bool on = pr < W && pr != pv.rank;
 #pragma unroll
       for (int i = 0; i < kPubCPT; ++i) {
+        const uint32_t j = (uint32_t) i * kPubThreads + tid;
         rs[pr][i] = 0ull; rc[pr][i] = 0u;
-        if (on && k0 + i < cells) {
-          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(rs[pr][i]) : "l"(pv.sum[pr] + roff + k0 + i) : "memory");
-          if (wc) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(rc[pr][i]) : "l"(pv.cnt[pr] + roff + k0 + i) : "memory");
+        if (on && j < cells) {
+          asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(rs[pr][i]) : "l"(pv.sum[pr] + roff + j) : "memory");
+          if (wc) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(rc[pr][i]) : "l"(pv.cnt[pr] + roff + j) : "memory");
         }
       }
     }
@@ -670,8 +679,23 @@ scan_pub_kernel(const NodeTask *__restrict__ tasks, const __grid_constant__ Task
 #pragma unroll
     for (int pr = 0; pr < kMaxPeers; ++pr)
 #pragma unroll
-      for (int i = 0; i < kPubCPT; ++i) { s[i] += rs[pr][i]; c[i] += rc[pr][i]; }
+      for (int i = 0; i < kPubCPT; ++i) { ts[i] += rs[pr][i]; tc[i] += rc[pr][i]; }
+#pragma unroll
+    for (int i = 0; i < kPubCPT; ++i) {
+      const uint32_t j = (uint32_t) i * kPubThreads + tid;
+      x_s[j] = ts[i]; x_c[j] = tc[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kPubCPT; ++i) { s[i] = x_s[k0 + i]; c[i] = x_c[k0 + i]; }   // (cells beyond the feature's are 0)
     kstamp(out.ktrace, kb, 5);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kPubCPT; ++i) {
+      const bool in = k0 + i < cells;
+      s[i] = in ? __ldcg(Rs + k0 + i) : 0ull;
+      c[i] = in ? __ldcg(Cc + k0 + i) : 0u;
+    }
   }
   if (f == f_first && warp == 0) {
     // exact squares of the built child
