@@ -268,7 +268,7 @@ constexpr uint32_t kPeerThreads = 256;
 __global__ void __launch_bounds__(kPeerThreads)
 peer_reduce_kernel(const PeerTable pt, int rank, int world, const NodeTask *__restrict__ tasks, uint32_t k,
                    uint32_t ncells, uint32_t epoch_a, int with_counts, ulonglong2 *sq128, uint32_t *done,
-                   const __grid_constant__ TaskPack pack) {
+                   uint32_t *host_err, const __grid_constant__ TaskPack pack) {
   if (pack.n) tasks = pack.t;
   __shared__ uint32_t s_last;
   PeerSignals *mine = pt.sig[rank];
@@ -294,7 +294,7 @@ peer_reduce_kernel(const PeerTable pt, int rank, int world, const NodeTask *__re
     if (tid < (uint32_t) world && tid != (uint32_t) rank) st_flag(&pt.sig[tid]->flags[rank], epoch_a);
   }
   // barrier A
-  if (tid < (uint32_t) world && tid != (uint32_t) rank) wait_flag(&mine->flags[tid], epoch_a);
+  if (tid < (uint32_t) world && tid != (uint32_t) rank) wait_flag_or_report(&mine->flags[tid], epoch_a, host_err);
   __syncthreads();
 
   const uint32_t c0 = (uint32_t) ((unsigned long long) ncells * (uint32_t) rank / (uint32_t) world);
@@ -304,15 +304,25 @@ peer_reduce_kernel(const PeerTable pt, int rank, int world, const NodeTask *__re
   for (uint32_t idx = blockIdx.x * kPeerThreads + tid; idx < total; idx += gridDim.x * kPeerThreads) {
     const uint32_t j = idx / span, i = c0 + (idx - j * span);
     const size_t off = (size_t) build_slot(tasks[j]) * ncells + i;
+    // every pool's copy in flight together (as in scan_pub_kernel: left to itself ptxas adds each value as it arrives,
+    // which serialises the NVLink round trips)
+    unsigned long long v[kMaxPeers];
+    uint32_t m[kMaxPeers];
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      v[p] = 0ull; m[p] = 0u;
+      if (p < world) {
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v[p]) : "l"(pt.sum[p] + off) : "memory");
+        if (with_counts) asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(m[p]) : "l"(pt.cnt[p] + off) : "memory");
+      }
+    }
+    static_assert(kMaxPeers == 8, "the operand list below names eight pools");
+    asm volatile("" : "+l"(v[0]), "+l"(v[1]), "+l"(v[2]), "+l"(v[3]), "+l"(v[4]), "+l"(v[5]), "+l"(v[6]), "+l"(v[7]),
+                      "+r"(m[0]), "+r"(m[1]), "+r"(m[2]), "+r"(m[3]), "+r"(m[4]), "+r"(m[5]), "+r"(m[6]), "+r"(m[7]));
     unsigned long long s = 0ull;
     uint32_t n = 0u;
 #pragma unroll
-    for (int p = 0; p < kMaxPeers; ++p) {
-      if (p < world) {
-        s += *reinterpret_cast<const volatile unsigned long long *>(pt.sum[p] + off);
-        if (with_counts) n += *reinterpret_cast<const volatile uint32_t *>(pt.cnt[p] + off);
-      }
-    }
+    for (int p = 0; p < kMaxPeers; ++p) { s += v[p]; n += m[p]; }
 #pragma unroll
     for (int p = 0; p < kMaxPeers; ++p) {
       if (p < world) {
@@ -350,7 +360,7 @@ peer_reduce_kernel(const PeerTable pt, int rank, int world, const NodeTask *__re
   if (tid == 0) *done = 0u;   // for the next launch (stream-ordered after this one)
   if (tid < (uint32_t) world && tid != (uint32_t) rank) {
     st_flag(&pt.sig[tid]->flags[rank], epoch_a + 1u);
-    wait_flag(&mine->flags[tid], epoch_a + 1u);
+    wait_flag_or_report(&mine->flags[tid], epoch_a + 1u, host_err);
   }
 }
 
@@ -496,7 +506,7 @@ static int peer_reduce_tasks(qr_ctx *ctx, uint32_t k, bool root) {
   c->epoch += 2u;
   peer_reduce_kernel<<<grid, kPeerThreads, 0, ctx->stream>>>(c->peers, c->rank, c->world, ctx->d_tasks, k, ctx->ncells,
                                                              epoch_a, with_counts, ctx->d_sq128 + ctx->round_sq_off, c->d_done,
-                                                             ctx->pack);
+                                                             ctx->d_err_mapped, ctx->pack);
   ctx->launches++;
   QR_CUDA(cudaGetLastError());
   return QR_OK;

@@ -554,18 +554,6 @@ hist_limb_kernel(const NodeTask *__restrict__ tasks, uint32_t ntasks, const __gr
 // with it, is among them; candidates are compared in ascending threshold order with a strict '>'
 // (rt.cc:272-291), ties across threads go to the smaller threshold.
 // ------------------------------------------------------------------------------------------
-// bounded spin on a peer's flag: a peer that never arrives (crashed process) must not hang the GPU; the
-// timeout is reported through `err` (mapped host memory) and surfaces as QR_ECOMM on the host
-__device__ __forceinline__ void wait_flag_or_report(const uint32_t *p, uint32_t epoch, uint32_t *err) {
-  const long long t0 = clock64();
-  while ((int32_t) (ld_flag(p) - epoch) < 0) {
-    if (clock64() - t0 > 40000000000ll) {   // ~20 s
-      if (err) { *reinterpret_cast<volatile uint32_t *>(err) = 1u; __threadfence_system(); }
-      return;
-    }
-  }
-}
-
 constexpr uint32_t kPubThreads = 128;    // 4 warps; kPubCPT consecutive bins per thread: one pass covers 384 thresholds.
 constexpr uint32_t kPubWarps = kPubThreads / 32;   // Small blocks: 8+ are resident per SM, so a round of up to ~8 node
 constexpr int kPubCPT = 3;                         // expansions (136 features each) is ONE wave of blocks.

@@ -74,11 +74,15 @@ __device__ __forceinline__ uint32_t ld_flag(const uint32_t *p) {
 __device__ __forceinline__ void st_flag(uint32_t *p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
-// bounded spin: a peer that never arrives (crashed process) must not hang the GPU
-__device__ __forceinline__ void wait_flag(const uint32_t *p, uint32_t epoch) {
+// bounded spin on a peer's flag: a peer that never arrives (crashed process) must neither hang the GPU nor kill every
+// rank's context with a trap; the timeout is reported through `err` (mapped host memory) and surfaces as QR_ECOMM
+__device__ __forceinline__ void wait_flag_or_report(const uint32_t *p, uint32_t epoch, uint32_t *err) {
   const long long t0 = clock64();
   while ((int32_t) (ld_flag(p) - epoch) < 0) {
-    if (clock64() - t0 > 120000000000ll) __trap();   // ~60 s
+    if (clock64() - t0 > 40000000000ll) {   // ~20 s
+      if (err) { *reinterpret_cast<volatile uint32_t *>(err) = 1u; __threadfence_system(); }
+      return;
+    }
   }
 }
 
