@@ -237,6 +237,25 @@ int qr_score_partial(qr_scorer *s, const float *docs_rowmajor, size_t N, size_t 
 /* Same with device-resident documents and outputs (asynchronous; `scores_device` may be NULL). */
 int qr_score_partial_device(qr_scorer *s, const float *docs_rowmajor_device, size_t N, size_t F,
                             float *partial_device, double *scores_device);
+/* ---- Line search over a score matrix (src/learning/linear/line_search.cc, the optimiser behind CLEAVER,
+ * src/optimization/post_learning/cleaver/cleaver.cc:166-330) ----
+ * The matrix is row-major [N][T]: one column per tree (qr_score_partial) or per feature.  The device does the passes
+ * over documents — LineSearch::score / preCompute (line_search.cc:447-482), the candidate score vectors of step 1
+ * (:252-272) and step 2 (:303-316) in the reference's own arithmetic, and Metric::evaluate_dataset (NDCG@cutoff,
+ * metric.h:77-92) of each; the search itself stays on the host (quickrank_b200/linesearch.py). */
+typedef struct qr_linesearch qr_linesearch;
+int qr_ls_create(const float *x_rowmajor, size_t N, size_t T, const float *labels, const uint64_t *qoffsets, size_t Q,
+                 uint32_t ndcg_cutoff, int device, qr_linesearch **out);
+int qr_ls_destroy(qr_linesearch *ls);
+/* metric of the ranking by sum_f weights[f] * x[.][f] (line_search.cc:215-219) */
+int qr_ls_evaluate(qr_linesearch *ls, const double *weights, double *metric);
+/* step 1 for column f: metrics[p] = metric with weights[f] replaced by points[p] (line_search.cc:252-281) */
+int qr_ls_feature_points(qr_linesearch *ls, const double *weights, uint32_t f, const double *points, uint32_t npoints,
+                         double *metrics);
+/* step 2: metrics[p] = metric of weights + p * step, p = 0 .. npoints-1 (line_search.cc:303-325) */
+int qr_ls_line_points(qr_linesearch *ls, const double *weights, const double *step, uint32_t npoints, double *metrics);
+uint64_t qr_ls_launch_count(qr_linesearch *ls);
+
 /* Waits for the scorer's stream (qr_score_dataset_device is asynchronous). */
 int qr_scorer_sync(qr_scorer *s);
 /* kernel launches issued by this scorer so far */

@@ -87,6 +87,8 @@ def lib():
         L.qref_ndcg_jacobian.argtypes = [fp, dp, u64, u64, dp]
         L.qref_sort_indices.argtypes = [dp, u64, C.POINTER(u64)]
         L.qref_radix_argsort.argtypes = [fp, u64, C.POINTER(u64)]
+        L.qref_linesearch.argtypes = [fp, u64, u64, fp, C.POINTER(u64), u64, u64, C.c_uint32, C.c_double, C.c_double,
+                                      C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, dp, dp]
         L.qref_set_threads.argtypes = [C.c_int]
         L.qref_max_threads.restype = C.c_int
         _lib = L
@@ -284,4 +286,24 @@ def radix_argsort(v):
     v = np.ascontiguousarray(v, np.float32)
     out = np.empty(len(v), np.uint64)
     lib().qref_radix_argsort(_p(v, C.c_float), len(v), _p(out, C.c_uint64))
+    return out
+
+
+def linesearch(x, labels, qoff, cutoff=10, num_points=20, window_size=1.0, reduction_factor=0.95, max_iterations=5,
+               max_failed_vali=20, adaptive=False, last_only=0, init_weights=None):
+    """The reference's LineSearch::learn (line_search.cc:153-416) on a row-major matrix, NDCG@cutoff, no validation
+    set; returns the learned weights."""
+    x = np.ascontiguousarray(x, np.float32)
+    labels = np.ascontiguousarray(labels, np.float32)
+    qoff = np.ascontiguousarray(qoff, np.uint64)
+    out = np.zeros(x.shape[1], np.float64)
+    iw = None
+    if init_weights is not None:
+        init_weights = np.ascontiguousarray(init_weights, np.float64)
+        iw = _p(init_weights, C.c_double)
+    rc = lib().qref_linesearch(_p(x, C.c_float), x.shape[0], x.shape[1], _p(labels, C.c_float), _p(qoff, C.c_uint64),
+                               len(qoff) - 1, cutoff, num_points, window_size, reduction_factor, max_iterations,
+                               max_failed_vali, int(adaptive), last_only, iw, _p(out, C.c_double))
+    if rc:
+        raise RuntimeError("reference line search failed")
     return out

@@ -24,6 +24,7 @@
 #include "metric/ir/dcg.h"
 #include "learning/ltr_algorithm.h"
 #include "learning/forests/mart.h"
+#include "learning/linear/line_search.h"
 #include "learning/forests/lambdamart.h"
 #include "learning/forests/obliviousmart.h"
 #include "learning/forests/obliviouslambdamart.h"
@@ -487,5 +488,36 @@ void qref_radix_argsort(const float *v, uint64_t n, uint64_t *dest) {
 // benchmark's reference legs set the team size explicitly and report what the runtime then uses)
 void qref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 int qref_max_threads(void) { return omp_get_max_threads(); }
+
+// LineSearch::learn (src/learning/linear/line_search.cc:153-416) on a row-major matrix — the per-tree partial scores
+// CLEAVER works on (driver.cc:411-446), or any feature matrix — with NDCG@cutoff as the metric and no validation
+// set; returns the learned weights.  The reference's progress table goes to a discarded stream.
+int qref_linesearch(const float *x, uint64_t N, uint64_t T, const float *labels, const uint64_t *qoff, uint64_t Q,
+                    uint64_t cutoff, uint32_t num_points, double window_size, double reduction_factor,
+                    uint32_t max_iterations, uint32_t max_failed_vali, int adaptive, uint32_t last_only,
+                    const double *init_weights, double *out_weights) {
+  auto ds = std::make_shared<data::Dataset>(N, T);
+  std::vector<Feature> row(T);
+  for (uint64_t q = 0; q < Q; ++q)
+    for (uint64_t i = qoff[q]; i < qoff[q + 1]; ++i) {
+      row.assign(x + i * T, x + (i + 1) * T);
+      ds->addInstance((QueryID) (q + 1), labels[i], row);
+    }
+  auto metric = std::make_shared<metric::ir::Ndcg>(cutoff);
+  learning::linear::LineSearch ls(num_points, window_size, reduction_factor, max_iterations, max_failed_vali,
+                                  adaptive != 0, last_only);
+  if (init_weights) {
+    std::vector<double> w(init_weights, init_weights + T);
+    ls.update_weights(w);
+  }
+  std::ostringstream sink;
+  std::streambuf *old = std::cout.rdbuf(sink.rdbuf());
+  ls.learn(ds, nullptr, metric, 0, std::string());
+  std::cout.rdbuf(old);
+  const std::vector<double> w = ls.get_weights();
+  if (w.size() != T) return 1;
+  for (uint64_t f = 0; f < T; ++f) out_weights[f] = w[f];
+  return 0;
+}
 
 }  // extern "C"

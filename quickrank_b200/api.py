@@ -79,6 +79,13 @@ def lib():
         L.qr_apply_trees.argtypes = [vp, C.POINTER(FlatTree), dp, C.c_size_t]
         L.qr_tree_contributions.argtypes = [vp, C.POINTER(FlatTree), C.c_size_t, dp]
         L.qr_evaluate.argtypes = [vp, dp]
+        L.qr_ls_create.argtypes = [fp, sz, sz, fp, u64p, sz, C.c_uint32, C.c_int, C.POINTER(vp)]
+        L.qr_ls_destroy.argtypes = [vp]
+        L.qr_ls_evaluate.argtypes = [vp, dp, dp]
+        L.qr_ls_feature_points.argtypes = [vp, dp, C.c_uint32, dp, C.c_uint32, dp]
+        L.qr_ls_line_points.argtypes = [vp, dp, dp, C.c_uint32, dp]
+        L.qr_ls_launch_count.argtypes = [vp]
+        L.qr_ls_launch_count.restype = C.c_uint64
         L.qr_selftest_ordered_squares.argtypes = [dp, sz, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_uint64)]
         L.qr_boost_iteration.argtypes = [vp, C.POINTER(FlatTree), dp]
         L.qr_get_scores.argtypes = [vp, dp]
@@ -354,6 +361,54 @@ class Trainer:
         ln = (C.c_uint64 * 6)()
         _check(lib().qr_phase_times(self.h, ms, ln, int(reset)))
         return dict(zip(PHASES, list(ms))), dict(zip(PHASES, [int(v) for v in ln]))
+
+
+class LineSearchDevice:
+    """The device side of a line search over a row-major score matrix [N][T] (qr_ls_*): weighted sums per document
+    and NDCG@cutoff of the rankings they induce, in the reference's arithmetic (line_search.cc)."""
+
+    def __init__(self, x, labels, qoffsets, cutoff=10, device=-1):
+        x = np.ascontiguousarray(x, np.float32)
+        labels = np.ascontiguousarray(labels, np.float32)
+        qoffsets = np.ascontiguousarray(qoffsets, np.uint64)
+        self.N, self.T = x.shape
+        self.h = C.c_void_p()
+        _check(lib().qr_ls_create(_p(x, C.c_float), self.N, self.T, _p(labels, C.c_float), _p(qoffsets, C.c_uint64),
+                                  len(qoffsets) - 1, cutoff, device, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().qr_ls_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def evaluate(self, weights):
+        w = np.ascontiguousarray(weights, np.float64)
+        m = C.c_double()
+        _check(lib().qr_ls_evaluate(self.h, _p(w, C.c_double), C.byref(m)))
+        return m.value
+
+    def feature_points(self, weights, f, points):
+        w = np.ascontiguousarray(weights, np.float64)
+        pts = np.ascontiguousarray(points, np.float64)
+        out = np.zeros(len(pts), np.float64)
+        _check(lib().qr_ls_feature_points(self.h, _p(w, C.c_double), int(f), _p(pts, C.c_double), len(pts), _p(out, C.c_double)))
+        return out
+
+    def line_points(self, weights, step, npoints):
+        w = np.ascontiguousarray(weights, np.float64)
+        st = np.ascontiguousarray(step, np.float64)
+        out = np.zeros(npoints, np.float64)
+        _check(lib().qr_ls_line_points(self.h, _p(w, C.c_double), _p(st, C.c_double), npoints, _p(out, C.c_double)))
+        return out
+
+    def launch_count(self):
+        return int(lib().qr_ls_launch_count(self.h))
 
 
 def selftest_ordered_squares(values, fused, device=-1):

@@ -1,0 +1,115 @@
+"""Line search / CLEAVER on the GPU against the UNMODIFIED reference (oracle/_ref,
+LineSearch::learn, src/learning/linear/line_search.cc:153-416) and against the oracle's NDCG.
+
+The learned weights must equal the reference's bit for bit: every candidate's score vector is formed in the
+reference's arithmetic (separate multiply/add where its Release build has them, fused where it fuses), rankings use the
+libstdc++ introsort replica, the metric is the sequential mean of per-query NDCG@k, and acceptance takes the first
+maximum — so every comparison `metric > best` sees the same two doubles."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from oracle import pyref
+from quickrank_b200 import api, synth
+from quickrank_b200.linesearch import Cleaver, LineSearch
+import qr_testlib as common
+
+pytestmark = pytest.mark.gpu
+
+
+def _features(n=3000, f=8, q=30, seed=3):
+    return synth.make_dataset(n, f, q, seed=seed)
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref is not built")
+@pytest.mark.parametrize("cfg", [
+    dict(num_points=8, max_iterations=3),
+    dict(num_points=21, max_iterations=4, window_size=2.0, reduction_factor=0.8),
+    dict(num_points=10, max_iterations=6, adaptive=True),
+    dict(num_points=12, max_iterations=3, last_only=3),
+])
+def test_line_search_learns_the_reference_weights(cfg):
+    x, l, off = _features()
+    want = pyref.linesearch(x, l, off, cutoff=10, **cfg)
+    ls = LineSearch(**cfg)
+    with api.LineSearchDevice(x, l, off, cutoff=10) as dev:
+        got = ls.learn(dev)
+        assert dev.launch_count() > 0
+    assert np.array_equal(got, want), (got, want)
+    # the learned weights are worth what the oracle says they are
+    scores = (x.astype(np.float64) * got).sum(axis=1)
+    assert abs(ls.metric_on_training - po.ndcg_dataset(l, scores, off, 10)) <= 1e-9
+
+
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref is not built")
+def test_line_search_on_the_partial_scores_of_an_ensemble():
+    """The CLEAVER input: one column per tree (Driver::extract_partial_scores with unit weights, driver.cc:411-446),
+    starting from the ensemble's own weights."""
+    x, l, off = common.dataset(n=4000, f=12, q=40, seed=9)
+    with api.Trainer(x, l, off, nleaves=8, shrinkage=0.1) as tr:
+        trees = [tr.boost_iteration()[0] for _ in range(10)]
+    with api.Scorer(trees, np.ones(len(trees)), x.shape[1]) as sc:
+        part = sc.partial_scores(x)
+    w0 = np.full(len(trees), 0.1)
+    want = pyref.linesearch(part, l, off, cutoff=10, num_points=10, max_iterations=3, window_size=1.0, init_weights=w0)
+    ls = LineSearch(num_points=10, max_iterations=3, window_size=1.0)
+    ls.weights = w0.copy()
+    with api.LineSearchDevice(part, l, off, cutoff=10) as dev:
+        before = dev.evaluate(w0)
+        got = ls.learn(dev)
+    assert np.array_equal(got, want)
+    assert ls.metric_on_training >= before
+
+
+def test_device_metrics_match_the_oracle():
+    """qr_ls_evaluate / feature_points / line_points: NDCG@10 of the candidate weight vectors (oracle: numpy scores in
+    float64 + the restated NDCG; the sums differ from the device's in rounding only: 1e-12)."""
+    x, l, off = _features(n=2500, f=6, q=25, seed=5)
+    rng = np.random.default_rng(1)
+    w = rng.random(6)
+    xd = x.astype(np.float64)
+    with api.LineSearchDevice(x, l, off, cutoff=10) as dev:
+        assert abs(dev.evaluate(w) - po.ndcg_dataset(l, xd @ w, off, 10)) <= 1e-12
+        pts = np.array([0.0, 0.3, 1.7])
+        got = dev.feature_points(w, 2, pts)
+        for p, g in zip(pts, got):
+            w2 = w.copy(); w2[2] = p
+            assert abs(g - po.ndcg_dataset(l, xd @ w2, off, 10)) <= 1e-12
+        step = rng.normal(0, 0.05, 6)
+        got = dev.line_points(w, step, 5)
+        for p, g in enumerate(got):
+            assert abs(g - po.ndcg_dataset(l, xd @ (w + step * p), off, 10)) <= 1e-12
+
+
+@pytest.mark.parametrize("method", ["LAST", "SKIP", "LOW_WEIGHTS", "QUALITY_LOSS"])
+def test_cleaver_prunes_and_reweights(method):
+    x, l, off = common.dataset(n=4000, f=12, q=40, seed=11)
+    with api.Trainer(x, l, off, nleaves=8, shrinkage=0.1) as tr:
+        trees = [tr.boost_iteration()[0] for _ in range(12)]
+    with api.Scorer(trees, np.ones(len(trees)), x.shape[1]) as sc:
+        part = sc.partial_scores(x)
+    w0 = np.full(len(trees), 0.1)
+    cl = Cleaver(0.25, method, LineSearch(num_points=8, max_iterations=2))
+    w, pruned = cl.optimize(part, l, off, w0, cutoff=10)
+    assert len(pruned) == 3 and all(w[f] == 0 for f in pruned) and np.all(w >= 0)
+    if method == "LAST":
+        assert pruned == {9, 10, 11}
+    if method == "SKIP":    # skip_pruning.cc:44-56: the kept trees are ceil(12/9 * i), i = 0..8
+        assert pruned == set(range(12)) - {int(np.ceil(12 / 9 * i)) for i in range(9)}
+    if method == "QUALITY_LOSS":
+        # quality_loss_pruning.cc:55-82 restated: NDCG without each tree (under the pre-pruning line search's weights
+        # the strategy sees), the three trees whose removal leaves the best metric are pruned
+        ls = LineSearch(num_points=8, max_iterations=2)
+        ls.weights = w0.copy()
+        with api.LineSearchDevice(part, l, off, cutoff=10) as dev:
+            wls = ls.learn(dev).copy()
+        pd = part.astype(np.float64)
+        full = pd @ wls
+        loss = [po.ndcg_dataset(l, full - wls[f] * pd[:, f], off, 10) for f in range(12)]
+        order = sorted(range(12), key=lambda a: -loss[a])
+        top = sorted(loss, reverse=True)
+        if top[2] - top[3] > 1e-9:   # (an exact tie at the cut would be decided by rounding)
+            assert pruned == set(order[:3])
+    # the optimised ensemble scores what the oracle says
+    assert abs(cl.metric_after - po.ndcg_dataset(l, part.astype(np.float64) @ w, off, 10)) <= 1e-9
+    assert cl.metric_after >= cl.metric_before - 0.05
