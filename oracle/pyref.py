@@ -89,6 +89,8 @@ def lib():
         L.qref_radix_argsort.argtypes = [fp, u64, C.POINTER(u64)]
         L.qref_linesearch.argtypes = [fp, u64, u64, fp, C.POINTER(u64), u64, u64, C.c_uint32, C.c_double, C.c_double,
                                       C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, dp, dp]
+        L.qref_cleaver.argtypes = [C.c_int, fp, u64, u64, fp, C.POINTER(u64), u64, u64, C.c_double, dp, C.c_uint32,
+                                   C.c_double, C.c_double, C.c_uint32, dp]
         L.qref_set_threads.argtypes = [C.c_int]
         L.qref_max_threads.restype = C.c_int
         _lib = L
@@ -306,4 +308,24 @@ def linesearch(x, labels, qoff, cutoff=10, num_points=20, window_size=1.0, reduc
                                max_failed_vali, int(adaptive), last_only, iw, _p(out, C.c_double))
     if rc:
         raise RuntimeError("reference line search failed")
+    return out
+
+
+CLEAVER_METHODS = {"LAST": 0, "SKIP": 1, "LOW_WEIGHTS": 2, "QUALITY_LOSS": 3}
+
+
+def cleaver(method, x, labels, qoff, weights, pruning_rate, cutoff=10, num_points=0, window_size=1.0,
+            reduction_factor=0.95, max_iterations=5):
+    """The reference's Cleaver::optimize (cleaver.cc:166-412) on a partial-score matrix; returns the new weights
+    (0 for pruned trees).  num_points == 0: no line search."""
+    x = np.ascontiguousarray(x, np.float32)
+    labels = np.ascontiguousarray(labels, np.float32)
+    qoff = np.ascontiguousarray(qoff, np.uint64)
+    w = np.ascontiguousarray(weights, np.float64)
+    out = np.zeros(x.shape[1], np.float64)
+    rc = lib().qref_cleaver(CLEAVER_METHODS[method], _p(x, C.c_float), x.shape[0], x.shape[1], _p(labels, C.c_float),
+                            _p(qoff, C.c_uint64), len(qoff) - 1, cutoff, pruning_rate, _p(w, C.c_double), num_points,
+                            window_size, reduction_factor, max_iterations, _p(out, C.c_double))
+    if rc:
+        raise RuntimeError("reference cleaver failed (%d)" % rc)
     return out

@@ -25,6 +25,11 @@
 #include "learning/ltr_algorithm.h"
 #include "learning/forests/mart.h"
 #include "learning/linear/line_search.h"
+#include "optimization/post_learning/cleaver/cleaver.h"
+#include "optimization/post_learning/cleaver/last_pruning.h"
+#include "optimization/post_learning/cleaver/skip_pruning.h"
+#include "optimization/post_learning/cleaver/low_weights_pruning.h"
+#include "optimization/post_learning/cleaver/quality_loss_pruning.h"
 #include "learning/forests/lambdamart.h"
 #include "learning/forests/obliviousmart.h"
 #include "learning/forests/obliviouslambdamart.h"
@@ -517,6 +522,46 @@ int qref_linesearch(const float *x, uint64_t N, uint64_t T, const float *labels,
   const std::vector<double> w = ls.get_weights();
   if (w.size() != T) return 1;
   for (uint64_t f = 0; f < T; ++f) out_weights[f] = w[f];
+  return 0;
+}
+
+// Cleaver::optimize (src/optimization/post_learning/cleaver/cleaver.cc:166-412) with one of the deterministic pruning
+// strategies on a partial-score matrix, starting from `weights`; line search before / after pruning as the strategy
+// asks (num_points == 0: no line search).  method: 0 LAST, 1 SKIP, 2 LOW_WEIGHTS, 3 QUALITY_LOSS.
+int qref_cleaver(int method, const float *x, uint64_t N, uint64_t T, const float *labels, const uint64_t *qoff,
+                 uint64_t Q, uint64_t cutoff, double pruning_rate, const double *weights, uint32_t num_points,
+                 double window_size, double reduction_factor, uint32_t max_iterations, double *out_weights) {
+  namespace pr = optimization::post_learning::pruning;
+  auto ds = std::make_shared<data::Dataset>(N, T);
+  std::vector<Feature> row(T);
+  for (uint64_t q = 0; q < Q; ++q)
+    for (uint64_t i = qoff[q]; i < qoff[q + 1]; ++i) {
+      row.assign(x + i * T, x + (i + 1) * T);
+      ds->addInstance((QueryID) (q + 1), labels[i], row);
+    }
+  std::shared_ptr<metric::ir::Metric> metric = std::make_shared<metric::ir::Ndcg>(cutoff);
+  std::shared_ptr<learning::linear::LineSearch> ls;
+  if (num_points)
+    ls = std::make_shared<learning::linear::LineSearch>(num_points, window_size, reduction_factor, max_iterations, 20u,
+                                                        false, 0u);
+  std::shared_ptr<pr::Cleaver> cl;
+  switch (method) {
+    case 0: cl = std::make_shared<pr::LastPruning>(pruning_rate, ls); break;
+    case 1: cl = std::make_shared<pr::SkipPruning>(pruning_rate, ls); break;
+    case 2: cl = std::make_shared<pr::LowWeightsPruning>(pruning_rate, ls); break;
+    case 3: cl = std::make_shared<pr::QualityLossPruning>(pruning_rate, ls); break;
+    default: return 2;
+  }
+  std::vector<double> w(weights, weights + T);
+  cl->update_weights(w);
+  cl->set_update_model(false);
+  std::ostringstream sink;
+  std::streambuf *old = std::cout.rdbuf(sink.rdbuf());
+  cl->optimize(nullptr, ds, nullptr, metric, 0, std::string());
+  std::cout.rdbuf(old);
+  const std::vector<double> r = cl->get_weigths();
+  if (r.size() != T) return 1;
+  for (uint64_t f = 0; f < T; ++f) out_weights[f] = r[f];
   return 0;
 }
 

@@ -121,6 +121,117 @@ def _mean_seq(w):
     return acc / len(w)
 
 
+def std_sort(a, less):
+    """libstdc++'s std::sort (introsort: median-of-3 quicksort to depth 2*floor(log2 n), heapsort below it, one final
+    insertion sort; bits/stl_algo.h) on a Python list, in place: the order of elements that compare equal is the one
+    the reference's `std::sort(idx...)` calls produce (low_weights_pruning.cc:47-51, quality_loss_pruning.cc:79-84)."""
+    n = len(a)
+    if n < 2:
+        return a
+
+    def swap(i, j):
+        a[i], a[j] = a[j], a[i]
+
+    def unguarded_linear_insert(last):
+        val = a[last]
+        nxt = last - 1
+        while less(val, a[nxt]):
+            a[last] = a[nxt]
+            last = nxt
+            nxt -= 1
+        a[last] = val
+
+    def insertion_sort(first, last):
+        for i in range(first + 1, last):
+            if less(a[i], a[first]):
+                val = a[i]
+                a[first + 1:i + 1] = a[first:i]
+                a[first] = val
+            else:
+                unguarded_linear_insert(i)
+
+    def adjust_heap(first, hole, length, value):
+        top = hole
+        child = hole
+        while child < (length - 1) // 2:
+            child = 2 * (child + 1)
+            if less(a[first + child], a[first + child - 1]):
+                child -= 1
+            a[first + hole] = a[first + child]
+            hole = child
+        if (length & 1) == 0 and child == (length - 2) // 2:
+            child = 2 * (child + 1)
+            a[first + hole] = a[first + child - 1]
+            hole = child - 1
+        parent = (hole - 1) // 2                       # __push_heap
+        while hole > top and less(a[first + parent], value):
+            a[first + hole] = a[first + parent]
+            hole = parent
+            parent = (hole - 1) // 2
+        a[first + hole] = value
+
+    def heapsort(first, last):                         # std::__partial_sort(first, last, last)
+        length = last - first
+        if length >= 2:                                # __make_heap
+            parent = (length - 2) // 2
+            while True:
+                adjust_heap(first, parent, length, a[first + parent])
+                if parent == 0:
+                    break
+                parent -= 1
+        while last - first > 1:                        # __sort_heap
+            last -= 1
+            value = a[last]
+            a[last] = a[first]
+            adjust_heap(first, 0, last - first, value)
+
+    def move_median_to_first(result, x, y, z):
+        if less(a[x], a[y]):
+            if less(a[y], a[z]):
+                swap(result, y)
+            elif less(a[x], a[z]):
+                swap(result, z)
+            else:
+                swap(result, x)
+        elif less(a[x], a[z]):
+            swap(result, x)
+        elif less(a[y], a[z]):
+            swap(result, z)
+        else:
+            swap(result, y)
+
+    def introsort_loop(first, last, depth):
+        while last - first > 16:
+            if depth == 0:
+                heapsort(first, last)
+                return
+            depth -= 1
+            mid = first + (last - first) // 2
+            move_median_to_first(first, first + 1, mid, last - 1)
+            lo, hi, pivot = first + 1, last, first     # __unguarded_partition
+            while True:
+                while less(a[lo], a[pivot]):
+                    lo += 1
+                hi -= 1
+                while less(a[pivot], a[hi]):
+                    hi -= 1
+                if not lo < hi:
+                    break
+                swap(lo, hi)
+                lo += 1
+            introsort_loop(lo, last, depth)
+            last = lo
+
+    introsort_loop(0, n, 2 * (n.bit_length() - 1))
+    if n > 16:
+        insertion_sort(0, 16)
+        for i in range(16, n):
+            unguarded_linear_insert(i)
+    else:
+        insertion_sort(0, n)
+    return a
+
+
 PRUNING_METHODS = ("LAST", "SKIP", "LOW_WEIGHTS", "QUALITY_LOSS")
 _PRE_PRUNING_LS = {"LAST": False, "SKIP": False, "LOW_WEIGHTS": True, "QUALITY_LOSS": True}
 
@@ -149,11 +260,11 @@ class Cleaver:
             selected = {int(math.ceil(step * i + start_last)) for i in range(to_select)}
             return {f for f in range(start_last, T) if f not in selected}
         if self.method == "LOW_WEIGHTS":
-            idx = sorted(range(start_last, T), key=lambda a: weights[a])      # (std::sort on distinct keys)
+            idx = std_sort(list(range(start_last, T)), lambda a, b: weights[a] < weights[b])
             return set(idx[:to_prune])
         # QUALITY_LOSS: the metric of the ensemble without tree f, for every f; the trees whose removal hurts least go
         metrics = [dev.feature_points(weights, f, [0.0])[0] for f in range(start_last, T)]
-        idx = sorted(range(start_last, T), key=lambda a: -metrics[a - start_last])
+        idx = std_sort(list(range(start_last, T)), lambda a, b: metrics[a - start_last] > metrics[b - start_last])
         return set(idx[:to_prune])
 
     def optimize(self, x, labels, qoffsets, weights, cutoff=10, device=-1):
