@@ -120,6 +120,8 @@ struct qr_ctx {
   uint32_t *d_rankpos = nullptr;  // [N] position (within its query) of the doc at each rank
   double *d_qndcg = nullptr;      // [Q]
   double *d_metric = nullptr;     // [1]
+  double *d_vec_qndcg = nullptr, *d_vec_metric = nullptr;   // evaluate_vectors: [vec_cap][Q] per-query values, [vec_cap] means
+  uint32_t vec_cap = 0;
   uint32_t *d_ids[2] = {nullptr, nullptr};  // [N] node document lists (ping-pong)
   uint32_t *d_leaf_of_doc = nullptr;        // [N]
   uint32_t *d_blockcnt = nullptr;           // partition scratch (REFERENCE mode)
@@ -204,3 +206,8 @@ struct qr_ctx {
                                             // features, the ranks exchange their winners (QR_PEER_SLICED=0: every rank scans all)
   uint32_t oneshot_max = 12;                // fuse while (world - 1) * tasks * histogram bytes <= this many MB (QR_PEER_ONESHOT_MAX)
 };
+
+namespace qr {
+// NDCG@k of several score vectors over a REFERENCE-mode context's documents in one ranking launch (qr_train.cu)
+int evaluate_vectors(qr_ctx *c, const double *scores_dev, uint32_t nvec, double *metrics_host);
+}  // namespace qr

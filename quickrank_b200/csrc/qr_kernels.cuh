@@ -269,6 +269,12 @@ rank_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
   const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t q = blockIdx.x * WARPS + warp;
   if (q >= Q) return;
+  // blockIdx.y: one of several score vectors over the same documents (the line search's candidates, qr_linesearch.cu):
+  // vector y starts at scores + y * qoff[Q], its per-query values at qndcg + y * Q; rankpos is then not written
+  if (gridDim.y > 1) {
+    scores += (size_t) blockIdx.y * qoff[Q];
+    qndcg += (size_t) blockIdx.y * Q;
+  }
   SortElem *el = reinterpret_cast<SortElem *>(smem_raw) + (size_t) warp * maxlen;
   uint32_t *idx = reinterpret_cast<uint32_t *>(reinterpret_cast<SortElem *>(smem_raw) + (size_t) WARPS * maxlen) +
                   (size_t) warp * maxlen;
@@ -300,7 +306,8 @@ rank_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
     for (uint32_t i = lane; i < n; i += 32) idx[i] = el[i].id;
   }
   __syncwarp();
-  for (uint32_t i = lane; i < n; i += 32) rankpos[off + i] = idx[i];
+  if (gridDim.y == 1)
+    for (uint32_t i = lane; i < n; i += 32) rankpos[off + i] = idx[i];
   if (lane == 0) {
     double r = 0.0;
     if (n > 0) {
@@ -321,7 +328,9 @@ rank_kernel(const double *__restrict__ scores, const float *__restrict__ labels,
 __global__ void ndcg_mean_kernel(const double *qndcg, uint32_t Q, uint32_t Qdiv, bool exact, int qshift, double *out) {
   __shared__ double part[1024];
   if (exact) {
-    // one warp, values fetched 32 at a time, summed in order by every lane
+    // one warp, values fetched 32 at a time, summed in order by every lane; block b: the b-th vector of Q values
+    qndcg += (size_t) blockIdx.x * Q;
+    out += blockIdx.x;
     if (threadIdx.x >= 32) return;
     double acc = 0.0;
     for (uint32_t base = 0; base < Q; base += 32) {

@@ -112,15 +112,7 @@ struct qr_linesearch {
 };
 
 static int ls_metric_of(qr_linesearch *ls, double *scores_dev, double *metric) {
-  // the context ranks and evaluates whatever its score array holds
-  qr_ctx *c = ls->ctx;
-  double *keep = c->d_scores;
-  c->d_scores = scores_dev;
-  c->ranking_valid = false;
-  const int rc = qr_evaluate(c, metric);
-  c->d_scores = keep;
-  c->ranking_valid = false;
-  return rc;
+  return evaluate_vectors(ls->ctx, scores_dev, 1, metric);
 }
 
 static int ls_upload(qr_linesearch *ls, double *dst, const double *src, size_t n) {
@@ -205,7 +197,7 @@ int qr_ls_feature_points(qr_linesearch *ls, const double *weights, uint32_t f, c
         ls->d_x, ls->N, (uint32_t) ls->T, f, weights[f], ls->d_total, ls->d_points, np, ls->d_scores);
     QR_CUDA(cudaGetLastError());
     ls->ctx->launches++;
-    for (uint32_t p = 0; p < np; ++p) QR_TRY(ls_metric_of(ls, ls->d_scores + (size_t) p * ls->N, metrics + p0 + p));
+    QR_TRY(evaluate_vectors(ls->ctx, ls->d_scores, np, metrics + p0));
   }
   return QR_OK;
 }
@@ -222,7 +214,7 @@ int qr_ls_line_points(qr_linesearch *ls, const double *weights, const double *st
                                                                       p0, np, ls->d_scores);
     QR_CUDA(cudaGetLastError());
     ls->ctx->launches++;
-    for (uint32_t p = 0; p < np; ++p) QR_TRY(ls_metric_of(ls, ls->d_scores + (size_t) p * ls->N, metrics + p0 + p));
+    QR_TRY(evaluate_vectors(ls->ctx, ls->d_scores, np, metrics + p0));
   }
   return QR_OK;
 }

@@ -708,6 +708,32 @@ static int ensure_ranking(qr_ctx *c) {
   return QR_OK;
 }
 
+// NDCG@k of `nvec` score vectors over this context's documents (scores_dev[v * N + doc]) in one ranking launch and
+// one launch of sequential means: the line search's candidates (qr_linesearch.cu).  REFERENCE-mode contexts only.
+int evaluate_vectors(qr_ctx *c, const double *scores_dev, uint32_t nvec, double *metrics_host) {
+  if (!c->exact || nvec == 0) { set_error("internal: evaluate_vectors needs a REFERENCE-mode context"); return QR_EINVAL; }
+  const size_t smem = (size_t) kRankWarps * rank_smem_per_warp(c->maxlen);
+  if (smem > 200 * 1024) { set_error("longest query (%u documents) exceeds the ranking kernel's shared-memory budget", c->maxlen); return QR_ELIMIT; }
+  cudaFuncSetAttribute(rank_kernel<kRankWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(smem, 48 * 1024));
+  if (c->vec_cap < nvec) {
+    if (c->d_vec_qndcg) cudaFree(c->d_vec_qndcg);
+    if (c->d_vec_metric) cudaFree(c->d_vec_metric);
+    c->d_vec_qndcg = nullptr; c->d_vec_metric = nullptr;
+    c->vec_cap = std::max<uint32_t>(nvec, 32);
+    QR_TRY(dev_alloc(&c->d_vec_qndcg, (size_t) c->vec_cap * c->Q));
+    QR_TRY(dev_alloc(&c->d_vec_metric, c->vec_cap));
+  }
+  const dim3 grid((unsigned) ((c->Q + kRankWarps - 1) / kRankWarps), nvec);
+  // (a one-vector grid takes the kernel's single-vector path, which also writes rankpos: the cached ranking is dropped)
+  QR_LAUNCH(c, PH_RANK, rank_kernel<kRankWarps>, grid, kRankWarps * 32, smem, scores_dev, c->d_labels, c->d_gain, c->d_qoff,
+            c->d_idcg, c->d_lg, (uint32_t) c->Q, c->maxlen, c->cutoff, c->d_rankpos, c->d_vec_qndcg);
+  c->ranking_valid = false;
+  QR_LAUNCH(c, PH_RANK, ndcg_mean_kernel, nvec, 32, 0, c->d_vec_qndcg, (uint32_t) c->Q, (uint32_t) c->Q, true, 0, c->d_vec_metric);
+  QR_CUDA(cudaMemcpyAsync(metrics_host, c->d_vec_metric, nvec * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  QR_CUDA(cudaStreamSynchronize(c->stream));
+  return QR_OK;
+}
+
 static int compute_pseudo(qr_ctx *c) {
   if (!c->lambda) {
     PhaseTimer pt(c, PH_PSEUDO);
@@ -824,7 +850,8 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_leafsum, c->d_obv_slots, c->d_obv_lcounts, c->d_sq128, c->d_task_done,
                   c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_node, c->d_cids, c->d_clamq, c->d_counts,
                   c->d_sq_built, c->d_leafmeta, c->d_sq_acc, c->d_cand, c->d_noderec, c->d_kspan, c->d_rows,
-                  c->d_perm, c->d_cell_pos, c->d_mark, c->d_sq_chunks, c->d_sq_replayed, c->d_fskip};
+                  c->d_perm, c->d_cell_pos, c->d_mark, c->d_sq_chunks, c->d_sq_replayed, c->d_fskip,
+                  c->d_vec_qndcg, c->d_vec_metric};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);
