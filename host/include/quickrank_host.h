@@ -360,6 +360,9 @@ class Mart : public LTR_Algorithm {
   virtual void update_modelscores(std::shared_ptr<data::Dataset> dataset, Score *scores, RegressionTree *tree);
   virtual void update_modelscores(std::shared_ptr<data::VerticalDataset> dataset, Score *scores, RegressionTree *tree);
   virtual MetricScore evaluate_training(metric::ir::Metric *metric);
+  // the two device calls behind the hooks above, on a context of the caller's choice (validation set, document sample)
+  std::unique_ptr<RegressionTree> fit_tree_on(qr_ctx *ctx);
+  void apply_tree_on(qr_ctx *target, RegressionTree *tree);
   virtual uint32_t algo_id() const { return QR_ALGO_MART; }
   virtual size_t tree_depth() const { return 0; }
   virtual void write_xml_info(std::ostream &os) const;
@@ -423,6 +426,100 @@ class ObliviousLambdaMart : public ObliviousMart {
 
  protected:
   uint32_t algo_id() const override { return QR_ALGO_OBVLAMBDAMART; }
+};
+
+// LambdaMART on a per-query document sample that is redrawn as training goes on: the common loop of
+// LambdaMartSelective::learn (lambdamartselective.cc:46-313) and StochasticNegative::learn
+// (stochasticnegative.cc:46-283).  What touches documents runs on the GPU: the sample is a training context of
+// its own (qr_ctx_create_sample) in which pseudo-responses, root histogram, tree fit and leaf outputs see the
+// sampled documents only; the new tree is then applied to, and NDCG evaluated on, ALL documents in the full
+// context.  Choosing the sample (sorts, quotas, shuffles) is host logic, in host/src/sampled_trainers.cc.
+class SampledLambdaMart : public LambdaMart {
+ public:
+  using LambdaMart::LambdaMart;
+  ~SampledLambdaMart() override;
+  void learn(std::shared_ptr<data::Dataset> training_dataset, std::shared_ptr<data::Dataset> validation_dataset,
+             std::shared_ptr<metric::ir::Metric> training_metric, size_t partial_save,
+             const std::string output_basename) override;
+
+ protected:
+  // does this configuration sample at all (if not, the loop is plain LambdaMART on the full context)
+  virtual bool sampling_enabled() const = 0;
+  virtual void check_supported() const = 0;
+  // is a new sample drawn before iteration m
+  virtual bool resample_due(size_t m) const = 0;
+  // draws a sample: `ids` arrives as 0..N-1 and leaves permuted with the sample in front; returns its size.
+  // `scores` = the current model's scores of all training documents.
+  virtual size_t draw_sample(const data::Dataset &dataset, const std::vector<Score> &scores,
+                             const std::vector<size_t> &npositives, std::vector<size_t> &ids) = 0;
+  virtual void before_training() {}
+  virtual void after_iteration(size_t m, bool is_best) { (void) m; (void) is_best; }
+  void clear(size_t num_features) override;
+
+ private:
+  void build_sample_context(const data::Dataset &dataset, const std::vector<size_t> &ids, size_t n);
+  qr_ctx *sample_ctx_ = nullptr;
+};
+
+// lambdamartselective.h:34-107
+class LambdaMartSelective : public SampledLambdaMart {
+ public:
+  LambdaMartSelective(size_t ntrees, double shrinkage, size_t nthresholds, size_t ntreeleaves, size_t minleafsupport,
+                      float subsample, float max_features, size_t esr, float collapse_leaves_factor,
+                      int sampling_iterations, float max_sampling_factor, float random_sampling_factor,
+                      float normalization_factor, std::string adaptive_strategy, std::string negative_strategy)
+      : SampledLambdaMart(ntrees, shrinkage, nthresholds, ntreeleaves, minleafsupport, subsample, max_features, esr,
+                          collapse_leaves_factor),
+        sampling_iterations(sampling_iterations), rank_sampling_factor(max_sampling_factor),
+        random_sampling_factor(random_sampling_factor), normalization_factor(normalization_factor),
+        adaptive_strategy(std::move(adaptive_strategy)), negative_strategy(std::move(negative_strategy)) {}
+  explicit LambdaMartSelective(const XmlModel &model) : SampledLambdaMart(model) {}
+  std::string name() const override { return NAME_; }
+  static const std::string NAME_;
+  // LambdaMartSelective::sampling_query_level (lambdamartselective.cc:326-493), public for host/selective_check.cc
+  size_t sampling_query_level(const data::Dataset &dataset, const std::vector<Score> &scores,
+                              const std::vector<size_t> &npositives, std::vector<size_t> &ids, float adapt_factor);
+
+ protected:
+  bool sampling_enabled() const override { return rank_sampling_factor > 0 || random_sampling_factor > 0; }
+  void check_supported() const override;
+  bool resample_due(size_t m) const override { return m > 0 && m % (size_t) sampling_iterations == 0; }
+  size_t draw_sample(const data::Dataset &dataset, const std::vector<Score> &scores,
+                     const std::vector<size_t> &npositives, std::vector<size_t> &ids) override {
+    return sampling_query_level(dataset, scores, npositives, ids, adapt_factor_);
+  }
+  void before_training() override;
+  void after_iteration(size_t m, bool is_best) override;
+  std::ostream &put(std::ostream &os) const override;
+
+ private:
+  int sampling_iterations = 0;
+  float rank_sampling_factor = 1.0f, random_sampling_factor = 0.0f, normalization_factor = 100.0f;
+  std::string adaptive_strategy = "NO", negative_strategy = "RATIO";
+  std::vector<bool> improvements_;
+  float adapt_factor_ = 1.0f;
+};
+
+// stochasticnegative.h: every positive document and, per query, a random share `subsample` of the negatives,
+// redrawn at every iteration.  The reference seeds the shuffle from the wall clock (stochasticnegative.cc:315-316),
+// so two of its own runs differ; here the stream is std::default_random_engine seeded by --seed (default 0) + the
+// number of draws so far, which keeps a run reproducible.
+class StochasticNegative : public SampledLambdaMart {
+ public:
+  using SampledLambdaMart::SampledLambdaMart;
+  std::string name() const override { return NAME_; }
+  static const std::string NAME_;
+  void set_seed(unsigned long long s) { seed_ = s; }
+
+ protected:
+  bool sampling_enabled() const override { return subsample_ != 1.0f; }
+  void check_supported() const override;
+  bool resample_due(size_t m) const override { return m > 0; }
+  size_t draw_sample(const data::Dataset &dataset, const std::vector<Score> &scores,
+                     const std::vector<size_t> &npositives, std::vector<size_t> &ids) override;
+
+ private:
+  unsigned long long seed_ = 0, draws_ = 0;
 };
 
 // DART on top of LambdaMART (dart.h:34-199, dart.cc).  The dropout selection, the weight

@@ -80,13 +80,16 @@ static int finish(int rc) {
 
 static void usage() {
   std::cout << "quicklearn (quickrank_b200): LambdaMART / MART / oblivious variants on NVIDIA B200\n"
-               "  --algo <MART|LAMBDAMART|OBVMART|OBVLAMBDAMART>   (default LAMBDAMART)\n"
+               "  --algo <MART|LAMBDAMART|OBVMART|OBVLAMBDAMART|DART|LAMBDAMART-SELECTIVE|STOCHASTIC-NEGATIVE>   (default LAMBDAMART)\n"
                "  --train <svml file> [--valid <svml file>] [--test <svml file>]\n"
                "  --model-out <xml> | --model-in <xml>  [--restart-train]\n"
                "  --num-trees N (1000)  --shrinkage X (0.1)  --num-thresholds N (0 = unlimited)\n"
                "  --min-leaf-support N (1)  --end-after-rounds N (100)  --num-leaves N (10)  --tree-depth N (3)\n"
                "  --train-metric NDCG  --train-cutoff K (10)  --test-metric NDCG  --test-cutoff K (10)\n"
                "  --partial N (100)  --scores <file>\n"
+               "  LAMBDAMART-SELECTIVE: --sampling-iterations N  --rank-sampling-factor X (1.0)  --random-sampling-factor X (0)\n"
+               "                        --normalization-factor X (100)  --adaptive-strategy <NO|FIXED|RATIO|MIX>  --negative-strategy <RATIO|MUL|POS>\n"
+               "  STOCHASTIC-NEGATIVE:  --subsample X (share, or count if > 1, of each query's negatives)  --seed N (0)\n"
                "  --hist-mode <fast|reference> (fast)  --device N\n"
                "  --gpus N   train on N GPUs (documents sharded by query, one process per GPU: quicklearn forks them,\n"
                "             or takes the N processes of a launcher that sets RANK / WORLD_SIZE / LOCAL_RANK / MASTER_ADDR)\n";
@@ -150,6 +153,18 @@ int main(int argc, char **argv) {
     ranker.reset(mart = new learning::forests::Mart(ntrees, shrinkage, nthr, nleaves, minls, 1.0f, 1.0f, esr, 0.0f));
   } else if (algo == "LAMBDAMART") {
     ranker.reset(mart = new learning::forests::LambdaMart(ntrees, shrinkage, nthr, nleaves, minls, 1.0f, 1.0f, esr, 0.0f));
+  } else if (algo == "LAMBDAMART-SELECTIVE") {   // ltr_algorithm_factory.cc:80-98, defaults of quicklearn.cc:114-119
+    ranker.reset(mart = new learning::forests::LambdaMartSelective(
+                     ntrees, shrinkage, nthr, nleaves, minls, 1.0f, 1.0f, esr, 0.0f, atoi(get("sampling-iterations", "0").c_str()),
+                     strtof(get("rank-sampling-factor", "1.0").c_str(), nullptr),
+                     strtof(get("random-sampling-factor", "0.0").c_str(), nullptr),
+                     strtof(get("normalization-factor", "100").c_str(), nullptr), get("adaptive-strategy", "NO"),
+                     get("negative-strategy", "RATIO")));
+  } else if (algo == "STOCHASTIC-NEGATIVE") {    // ltr_algorithm_factory.cc:99-111
+    auto *sn = new learning::forests::StochasticNegative(ntrees, shrinkage, nthr, nleaves, minls,
+                                                         strtof(get("subsample", "1.0").c_str(), nullptr), 1.0f, esr, 0.0f);
+    sn->set_seed(strtoull(get("seed", "0").c_str(), nullptr, 10));
+    ranker.reset(mart = sn);
   } else if (algo == "OBVMART") {
     ranker.reset(mart = new learning::forests::ObliviousMart(ntrees, shrinkage, nthr, depth, minls, 1.0f, 1.0f, esr, 0.0f));
   } else if (algo == "OBVLAMBDAMART") {

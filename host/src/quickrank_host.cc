@@ -764,7 +764,7 @@ void Mart::compute_pseudoresponses(std::shared_ptr<data::VerticalDataset>, metri
   if (qr_compute_pseudoresponses(ctx_) != QR_OK) die("compute_pseudoresponses");
 }
 
-std::unique_ptr<RegressionTree> Mart::fit_regressor_on_gradient(std::shared_ptr<data::VerticalDataset>, size_t *) {
+std::unique_ptr<RegressionTree> Mart::fit_tree_on(qr_ctx *ctx) {
   const uint32_t cap = 2 * (uint32_t) std::max<size_t>(nleaves_, 1) + 1;
   std::vector<int32_t> feature(cap), left(cap), right(cap);
   std::vector<uint32_t> tidx(cap);
@@ -775,8 +775,12 @@ std::unique_ptr<RegressionTree> Mart::fit_regressor_on_gradient(std::shared_ptr<
   t.capacity = cap; t.nnodes = t.nleaves = 0;
   t.feature = feature.data(); t.threshold_idx = tidx.data(); t.threshold = thr.data();
   t.left = left.data(); t.right = right.data(); t.value = value.data(); t.deviance = dev.data(); t.count = count.data();
-  if (qr_fit_tree(ctx_, &t) != QR_OK) die("fit_regressor_on_gradient");
+  if (qr_fit_tree(ctx, &t) != QR_OK) die("fit_regressor_on_gradient");
   return std::unique_ptr<RegressionTree>(new RegressionTree(RegressionTree::from_flat(t)));
+}
+
+std::unique_ptr<RegressionTree> Mart::fit_regressor_on_gradient(std::shared_ptr<data::VerticalDataset>, size_t *) {
+  return fit_tree_on(ctx_);
 }
 
 void Mart::update_modelscores(std::shared_ptr<data::VerticalDataset>, Score *, RegressionTree *) {
@@ -785,6 +789,10 @@ void Mart::update_modelscores(std::shared_ptr<data::VerticalDataset>, Score *, R
 
 // validation set: the new tree is applied on the device to the validation context
 void Mart::update_modelscores(std::shared_ptr<data::Dataset>, Score *, RegressionTree *tree) {
+  apply_tree_on(valid_ctx_, tree);
+}
+
+void Mart::apply_tree_on(qr_ctx *target, RegressionTree *tree) {
   std::vector<int32_t> feature, left, right;
   std::vector<float> thr;
   std::vector<double> value;
@@ -803,7 +811,7 @@ void Mart::update_modelscores(std::shared_ptr<data::Dataset>, Score *, Regressio
   t.nleaves = 0;
   t.feature = feature.data(); t.threshold_idx = tidx.data(); t.threshold = thr.data();
   t.left = left.data(); t.right = right.data(); t.value = value.data(); t.deviance = nullptr; t.count = nullptr;
-  if (qr_apply_tree(valid_ctx_, &t, shrinkage_) != QR_OK) die("update_modelscores (validation)");
+  if (qr_apply_tree(target, &t, shrinkage_) != QR_OK) die("update_modelscores (tree applied to a dataset)");
 }
 
 MetricScore Mart::evaluate_training(metric::ir::Metric *) {
@@ -1484,6 +1492,8 @@ std::shared_ptr<LTR_Algorithm> LTR_Algorithm::load_model_from_file(std::string m
   const std::string type = info ? info->child_text("type") : "";
   if (type == forests::Mart::NAME_) return std::shared_ptr<LTR_Algorithm>(new forests::Mart(model));
   if (type == forests::LambdaMart::NAME_) return std::shared_ptr<LTR_Algorithm>(new forests::LambdaMart(model));
+  if (type == forests::LambdaMartSelective::NAME_)   // ltr_algorithm.cc:100-102
+    return std::shared_ptr<LTR_Algorithm>(new forests::LambdaMartSelective(model));
   if (type == forests::ObliviousMart::NAME_) return std::shared_ptr<LTR_Algorithm>(new forests::ObliviousMart(model));
   if (type == forests::ObliviousLambdaMart::NAME_)
     return std::shared_ptr<LTR_Algorithm>(new forests::ObliviousLambdaMart(model));

@@ -110,6 +110,25 @@ int qr_ctx_create_rowmajor(const float *feat_rowmajor, size_t N, size_t F, const
  * qr_evaluate, qr_get_scores / qr_set_scores on it.  Row-major features. */
 int qr_ctx_create_eval(qr_ctx *train, const float *feat_rowmajor, size_t N, size_t F, const float *labels,
                        const uint64_t *qoffsets, size_t Q, qr_ctx **out);
+/* A document SAMPLE of `full` as a training context of its own: what LambdaMartSelective::learn
+ * (lambdamartselective.cc:185-206) and StochasticNegative::learn (stochasticnegative.cc:188-206) do
+ * with `sampleids` / `sample_presence` — pseudo-responses over the sampled documents of each query
+ * (LambdaMart::compute_pseudoresponses with sample_presence, lambdamart.cc:84-105), root histogram over
+ * the sample (RTNodeHistogram::update(labels, nsampleids, sampleids), rtnode_histogram.cc:172-204), tree
+ * fit and leaf outputs on it.  The rows are the sampled documents in ascending order within each query
+ * (the "cleaned" order of lambdamart.cc:90-98; queries left empty are dropped), binned with the
+ * thresholds of `full`; sums are fixed-point (QR_HIST_FAST) whatever the mode of `full`.
+ * src_doc[i] = the document of `full` row i is; key_doc[i] = the document of `full` whose score row i is
+ * RANKED by (lambdamart.cc:94 reads scores_on_training_[d] with d relative to the query, so
+ * key_doc[i] = src_doc[i] - offset(query of i); NULL: rank by the document's own score).
+ * Per iteration: qr_sample_pull_scores, qr_compute_pseudoresponses and qr_fit_tree on the sample, then
+ * qr_apply_tree(full, tree, shrinkage) and qr_evaluate(full) (update_modelscores and the metric run
+ * over ALL documents, lambdamartselective.cc:211-215). */
+int qr_ctx_create_sample(qr_ctx *full, const float *feat_rowmajor, size_t N, size_t F, const float *labels,
+                         const uint64_t *qoffsets, size_t Q, const uint32_t *src_doc, const uint32_t *key_doc,
+                         qr_ctx **out);
+/* Copies the current scores of `full` into the sample (own scores and ranking keys). */
+int qr_sample_pull_scores(qr_ctx *sample, qr_ctx *full);
 /* Replaces Mart::clear (mart.cc:178-206). */
 int qr_ctx_destroy(qr_ctx *ctx);
 

@@ -11,7 +11,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "libqr_ref.so")
 
-ALGOS = {"MART": 0, "LAMBDAMART": 1, "OBVMART": 2, "OBVLAMBDAMART": 3, "DART": 4}
+ALGOS = {"MART": 0, "LAMBDAMART": 1, "OBVMART": 2, "OBVLAMBDAMART": 3, "DART": 4, "LAMBDAMART-SELECTIVE": 5}
+SEL_ADAPTIVE = ["NO", "FIXED", "RATIO", "MIX"]
+SEL_NEGATIVE = ["RATIO", "MUL", "POS"]
 
 
 class Params(C.Structure):
@@ -33,6 +35,13 @@ class Params(C.Structure):
         ("dart_best_on_train", C.c_int32),
         ("dart_random_keep", C.c_double),
         ("dart_drop_on_best", C.c_double),
+        ("sel_sampling_iterations", C.c_int32),
+        ("sel_adaptive", C.c_int32),
+        ("sel_negative", C.c_int32),
+        ("sel_pad", C.c_int32),
+        ("sel_rank_factor", C.c_double),
+        ("sel_random_factor", C.c_double),
+        ("sel_normalization_factor", C.c_double),
     ]
 
 
@@ -56,6 +65,7 @@ def lib():
         L.qref_set_scores.argtypes = [vp, dp]
         L.qref_get_scores.argtypes = [vp, dp]
         L.qref_compute_pseudoresponses.argtypes = [vp]
+        L.qref_compute_pseudoresponses_masked.argtypes = [vp, C.POINTER(C.c_uint8)]
         L.qref_get_gradients.argtypes = [vp, dp, dp]
         L.qref_set_gradients.argtypes = [vp, dp, dp]
         L.qref_fit_tree.argtypes = [vp, C.c_int]
@@ -91,6 +101,11 @@ def lib():
                                       C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, dp, dp]
         L.qref_cleaver.argtypes = [C.c_int, fp, u64, u64, fp, C.POINTER(u64), u64, u64, C.c_double, dp, C.c_uint32,
                                    C.c_double, C.c_double, C.c_uint32, dp]
+        L.qref_log.restype = u64
+        L.qref_log.argtypes = [vp, C.c_char_p, u64]
+        L.qref_selective_sample.restype = u64
+        L.qref_selective_sample.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, fp, dp, C.POINTER(u64),
+                                            u64, u64, C.POINTER(u64)]
         L.qref_set_threads.argtypes = [C.c_int]
         L.qref_max_threads.restype = C.c_int
         _lib = L
@@ -111,7 +126,7 @@ class RefSession:
     """One reference algorithm object bound to one dataset."""
 
     def __init__(self, algo, x, labels, qoff, ntrees=10, shrinkage=0.1, nthresholds=0, nleaves=10,
-                 treedepth=3, minleafsupport=1, cutoff=10, dart=None):
+                 treedepth=3, minleafsupport=1, cutoff=10, dart=None, selective=None):
         L = lib()
         self.x = np.ascontiguousarray(x, dtype=np.float32)
         self.labels = np.ascontiguousarray(labels, dtype=np.float32)
@@ -130,6 +145,13 @@ class RefSession:
         p.dart_rate_drop, p.dart_skip_drop = d["rate_drop"], d["skip_drop"]
         p.dart_keep_drop, p.dart_best_on_train = d["keep_drop"], d["best_on_train"]
         p.dart_random_keep, p.dart_drop_on_best = d["random_keep"], d["drop_on_best"]
+        sel = dict(sampling_iterations=0, rank_factor=1.0, random_factor=0.0, normalization_factor=100.0,
+                   adaptive="NO", negative="RATIO")
+        sel.update(selective or {})
+        p.sel_sampling_iterations = sel["sampling_iterations"]
+        p.sel_adaptive, p.sel_negative = SEL_ADAPTIVE.index(sel["adaptive"]), SEL_NEGATIVE.index(sel["negative"])
+        p.sel_rank_factor, p.sel_random_factor = sel["rank_factor"], sel["random_factor"]
+        p.sel_normalization_factor = sel["normalization_factor"]
         self.h = L.qref_open(C.byref(p), _p(self.x, C.c_float), _p(self.labels, C.c_float),
                              _p(self.qoff, C.c_uint64), self.N, self.F, self.Q)
         if not self.h:
@@ -151,6 +173,13 @@ class RefSession:
         lib().qref_learn(self.h, int(keep_gradients), int(quiet))
 
     # step-wise protocol
+    def log(self):
+        """stdout of the last quiet learn()"""
+        n = int(lib().qref_log(self.h, None, 0))
+        buf = C.create_string_buffer(n + 1)
+        lib().qref_log(self.h, buf, n + 1)
+        return buf.value.decode()
+
     def init(self):
         lib().qref_init(self.h)
 
@@ -165,6 +194,12 @@ class RefSession:
 
     def compute_pseudoresponses(self):
         lib().qref_compute_pseudoresponses(self.h)
+
+    def compute_pseudoresponses_masked(self, presence):
+        """LambdaMart::compute_pseudoresponses with sample_presence (lambdamart.cc:84-105)"""
+        m = np.ascontiguousarray(presence, dtype=np.uint8)
+        assert len(m) == self.N
+        lib().qref_compute_pseudoresponses_masked(self.h, _p(m, C.c_uint8))
 
     def get_gradients(self):
         lam = np.zeros(self.N, dtype=np.float64)
@@ -329,3 +364,16 @@ def cleaver(method, x, labels, qoff, weights, pruning_rate, cutoff=10, num_point
     if rc:
         raise RuntimeError("reference cleaver failed (%d)" % rc)
     return out
+
+
+def selective_sample(labels, scores, qoff, rank_factor, random_factor, adaptive="NO", negative="RATIO", adapt_factor=1.0):
+    """One draw of the reference's LambdaMartSelective::sampling_query_level after srand(0): (sample size, id list)."""
+    labels = np.ascontiguousarray(labels, dtype=np.float32)
+    scores = np.ascontiguousarray(scores, dtype=np.float64)
+    qoff = np.ascontiguousarray(qoff, dtype=np.uint64)
+    ids = np.zeros(len(labels), dtype=np.uint64)
+    n = lib().qref_selective_sample(float(rank_factor), float(random_factor), SEL_ADAPTIVE.index(adaptive),
+                                    SEL_NEGATIVE.index(negative), float(adapt_factor), _p(labels, C.c_float),
+                                    _p(scores, C.c_double), _p(qoff, C.c_uint64), len(labels), len(qoff) - 1,
+                                    _p(ids, C.c_uint64))
+    return int(n), ids

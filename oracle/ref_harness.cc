@@ -37,6 +37,7 @@
 #include "io/generate_oblivious.h"
 #include "io/generate_vpred.h"
 #include "learning/forests/dart.h"
+#include "learning/forests/lambdamartselective.h"
 #include "utils/radix.h"
 #include "driver/driver.h"
 
@@ -56,6 +57,7 @@ using quickrank::learning::forests::LambdaMart;
 using quickrank::learning::forests::ObliviousMart;
 using quickrank::learning::forests::ObliviousLambdaMart;
 using quickrank::learning::forests::Dart;
+using quickrank::learning::forests::LambdaMartSelective;
 
 namespace {
 
@@ -168,6 +170,10 @@ class Trace : public Base {
   void x_pseudo(std::shared_ptr<data::VerticalDataset> d, metric::ir::Metric *m) {
     this->compute_pseudoresponses(d, m, NULL);
   }
+  // the document-sampling trainers' call (lambdamartselective.cc:194): sample_presence[doc]
+  void x_pseudo_masked(std::shared_ptr<data::VerticalDataset> d, metric::ir::Metric *m, bool *presence) {
+    this->compute_pseudoresponses(d, m, presence);
+  }
   // mart.cc:335-345 of the reference, in that order
   void x_fit_and_update(std::shared_ptr<data::VerticalDataset> d, bool update) {
     this->hist_->update(this->pseudoresponses_, n_, ids_.data());
@@ -204,7 +210,7 @@ class TraceNdcg : public metric::ir::Ndcg {
   }
 };
 
-enum Algo { A_MART = 0, A_LAMBDAMART = 1, A_OBVMART = 2, A_OBVLAMBDAMART = 3, A_DART = 4 };
+enum Algo { A_MART = 0, A_LAMBDAMART = 1, A_OBVMART = 2, A_OBVLAMBDAMART = 3, A_DART = 4, A_SELECTIVE = 5 };
 
 struct Session {
   int algo;
@@ -216,6 +222,8 @@ struct Session {
   std::unique_ptr<Trace<ObliviousMart>> omart;
   std::unique_ptr<Trace<ObliviousLambdaMart>> olmart;
   std::unique_ptr<Trace<Dart>> dart;
+  std::unique_ptr<Trace<LambdaMartSelective>> sel;
+  std::string log;   // what the last quiet learn() printed
   bool inited = false;
   Recorder *rec() {
     switch (algo) {
@@ -223,6 +231,7 @@ struct Session {
       case A_LAMBDAMART: return &lmart->rec;
       case A_OBVMART: return &omart->rec;
       case A_OBVLAMBDAMART: return &olmart->rec;
+      case A_SELECTIVE: return &sel->rec;
       default: return &dart->rec;
     }
   }
@@ -232,6 +241,7 @@ struct Session {
       case A_LAMBDAMART: return lmart.get();
       case A_OBVMART: return omart.get();
       case A_OBVLAMBDAMART: return olmart.get();
+      case A_SELECTIVE: return sel.get();
       default: return dart.get();
     }
   }
@@ -243,6 +253,7 @@ struct Session {
     case A_LAMBDAMART: { auto &a = *(s)->lmart; expr; } break;   \
     case A_OBVMART: { auto &a = *(s)->omart; expr; } break;      \
     case A_OBVLAMBDAMART: { auto &a = *(s)->olmart; expr; } break; \
+    case A_SELECTIVE: { auto &a = *(s)->sel; expr; } break;      \
     default: { auto &a = *(s)->dart; expr; } break;              \
   }
 
@@ -272,7 +283,13 @@ struct qref_params {
   double dart_rate_drop, dart_skip_drop;
   int32_t dart_keep_drop, dart_best_on_train;
   double dart_random_keep, dart_drop_on_best;
+  // LAMBDAMART-SELECTIVE only (lambdamartselective.h:47-61); strategies by index: NO FIXED RATIO MIX / RATIO MUL POS
+  int32_t sel_sampling_iterations, sel_adaptive, sel_negative, sel_pad;
+  double sel_rank_factor, sel_random_factor, sel_normalization_factor;
 };
+
+static const char *kSelAdaptive[] = {"NO", "FIXED", "RATIO", "MIX"};
+static const char *kSelNegative[] = {"RATIO", "MUL", "POS"};
 
 void *qref_open(const qref_params *p, const float *rowmajor, const float *labels,
                 const uint64_t *qoffsets, uint64_t N, uint64_t F, uint64_t Q) {
@@ -312,6 +329,12 @@ void *qref_open(const qref_params *p, const float *rowmajor, const float *labels
           p->dart_keep_drop != 0, p->dart_best_on_train != 0, p->dart_random_keep,
           p->dart_drop_on_best));
       break;
+    case A_SELECTIVE:
+      s->sel.reset(new Trace<LambdaMartSelective>(
+          p->ntrees, p->shrinkage, p->nthresholds, p->nleaves, p->minleafsupport, 1.0f, 1.0f, 0, 0.0f,
+          p->sel_sampling_iterations, (float) p->sel_rank_factor, (float) p->sel_random_factor,
+          (float) p->sel_normalization_factor, kSelAdaptive[p->sel_adaptive & 3], kSelNegative[p->sel_negative % 3]));
+      break;
     default:
       delete s;
       return nullptr;
@@ -331,10 +354,24 @@ int qref_learn(void *h, int keep_gradients, int quiet) {
   auto *s = (Session *) h;
   s->rec()->keep_gradients = keep_gradients != 0;
   s->metric->sink = &s->rec()->metric_train;
-  Silence sil(quiet != 0);
-  s->ltr()->learn(s->ds, nullptr, s->metric, 0, "");
+  {
+    Silence sil(quiet != 0);
+    s->ltr()->learn(s->ds, nullptr, s->metric, 0, "");
+    if (quiet) s->log = sil.sink.str();
+  }
   s->metric->sink = nullptr;
   return 0;
+}
+
+// what that learn() wrote to stdout (quiet runs); returns the length
+uint64_t qref_log(void *h, char *buf, uint64_t cap) {
+  auto *s = (Session *) h;
+  if (buf && cap) {
+    const uint64_t n = std::min<uint64_t>(cap - 1, s->log.size());
+    memcpy(buf, s->log.data(), n);
+    buf[n] = 0;
+  }
+  return s->log.size();
 }
 
 // ---- step-wise protocol (same call order as mart.cc:307-347) ----
@@ -356,6 +393,14 @@ void qref_get_scores(void *h, double *v) {
 void qref_compute_pseudoresponses(void *h) {
   auto *s = (Session *) h;
   DISPATCH(s, a.x_pseudo(s->vds, s->metric.get()));
+}
+void qref_compute_pseudoresponses_masked(void *h, const uint8_t *presence) {
+  auto *s = (Session *) h;
+  DISPATCH(s, {
+    std::unique_ptr<bool[]> sp(new bool[a.n()]);
+    for (size_t i = 0; i < a.n(); ++i) sp[i] = presence[i] != 0;
+    a.x_pseudo_masked(s->vds, s->metric.get(), sp.get());
+  });
 }
 void qref_get_gradients(void *h, double *lambdas, double *weights) {
   auto *s = (Session *) h;
@@ -491,6 +536,41 @@ void qref_radix_argsort(const float *v, uint64_t n, uint64_t *dest) {
 
 // OpenMP team size of the reference's loops (a launcher such as torchrun exports OMP_NUM_THREADS=1: the
 // benchmark's reference legs set the team size explicitly and report what the runtime then uses)
+// One draw of the reference's LambdaMartSelective::sampling_query_level (lambdamartselective.cc:326-493) on given
+// labels / scores, after srand(0): ids_out = the permuted sample-id list, returns the sample size.
+namespace {
+class SelectiveProbe : public LambdaMartSelective {
+ public:
+  using LambdaMartSelective::LambdaMartSelective;
+  size_t draw(std::shared_ptr<data::Dataset> ds, double *scores, size_t *ids, size_t *npos, float adapt) {
+    this->scores_on_training_ = scores;
+    size_t n = this->sampling_query_level(ds, ids, npos, adapt);
+    this->scores_on_training_ = NULL;
+    return n;
+  }
+};
+}  // namespace
+
+uint64_t qref_selective_sample(double rank_factor, double random_factor, int adaptive, int negative, double adapt_factor,
+                               const float *labels, const double *scores, const uint64_t *qoff, uint64_t N, uint64_t Q,
+                               uint64_t *ids_out) {
+  auto ds = std::make_shared<data::Dataset>(N, 1);
+  for (uint64_t q = 0; q < Q; ++q)
+    for (uint64_t i = qoff[q]; i < qoff[q + 1]; ++i) ds->addInstance((QueryID) (q + 1), labels[i], std::vector<Feature>(1, 0.0f));
+  SelectiveProbe probe(1, 0.1, 0, 4, 1, 1.0f, 1.0f, 0, 0.0f, 1, (float) rank_factor, (float) random_factor, 100.0f,
+                       kSelAdaptive[adaptive & 3], kSelNegative[negative % 3]);
+  std::vector<size_t> ids(N), npos(Q, 0);
+  for (uint64_t i = 0; i < N; ++i) ids[i] = i;
+  for (uint64_t q = 0; q < Q; ++q)
+    for (uint64_t i = qoff[q]; i < qoff[q + 1]; ++i) npos[q] += labels[i] > 0;
+  std::vector<double> sc(scores, scores + N);
+  Silence sil(true);
+  srand(0);
+  const size_t n = probe.draw(ds, sc.data(), ids.data(), npos.data(), (float) adapt_factor);
+  for (uint64_t i = 0; i < N; ++i) ids_out[i] = ids[i];
+  return n;
+}
+
 void qref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 int qref_max_threads(void) { return omp_get_max_threads(); }
 

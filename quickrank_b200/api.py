@@ -70,6 +70,9 @@ def lib():
         for name in ("qr_ctx_create", "qr_ctx_create_rowmajor"):
             getattr(L, name).argtypes = [fp, sz, sz, fp, u64p, sz, C.POINTER(Params), C.POINTER(vp)]
         L.qr_ctx_create_eval.argtypes = [vp, fp, sz, sz, fp, u64p, sz, C.POINTER(vp)]
+        L.qr_ctx_create_sample.argtypes = [vp, fp, sz, sz, fp, u64p, sz, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                           C.POINTER(vp)]
+        L.qr_sample_pull_scores.argtypes = [vp, vp]
         L.qr_ctx_destroy.argtypes = [vp]
         L.qr_get_thresholds.argtypes = [vp, sz, C.POINTER(fp), C.POINTER(sz)]
         L.qr_compute_pseudoresponses.argtypes = [vp]
@@ -216,6 +219,33 @@ class Trainer:
         _check(lib().qr_ctx_create_eval(self.h, _p(x, C.c_float), ev.N, ev.F, _p(ev.labels, C.c_float),
                                         _p(ev.qoff, C.c_uint64), ev.Q, C.byref(ev.h)))
         return ev
+
+    def sample_context(self, x, doc_ids, rank_by_position=True):
+        """The documents `doc_ids` (ascending; whole set `x` row-major) as a training context of their own, binned with
+        this trainer's thresholds (qr_ctx_create_sample): what LambdaMartSelective / StochasticNegative fit a tree on.
+        rank_by_position: the reference's ranking key (lambdamart.cc:94: the score of the document whose index is this
+        one's position inside its query); False: the document's own score."""
+        doc_ids = np.ascontiguousarray(doc_ids, np.uint32)
+        assert np.all(np.diff(doc_ids.astype(np.int64)) > 0), "sampled documents must be ascending"
+        q_of = np.searchsorted(self.qoff, doc_ids, side="right") - 1
+        counts = np.bincount(q_of, minlength=self.Q)
+        sm = Trainer.__new__(Trainer)
+        sm.labels = np.ascontiguousarray(self.labels[doc_ids], np.float32)
+        sm.qoff = np.concatenate([[0], np.cumsum(counts[counts > 0])]).astype(np.uint64)
+        rows = np.ascontiguousarray(np.asarray(x, np.float32)[doc_ids])
+        sm.N, sm.F = rows.shape
+        sm.Q = len(sm.qoff) - 1
+        sm.params, sm.shrinkage, sm.max_nodes = self.params, self.shrinkage, self.max_nodes
+        key = np.ascontiguousarray(doc_ids - self.qoff[q_of].astype(np.uint32), np.uint32) if rank_by_position else None
+        sm.h = C.c_void_p()
+        _check(lib().qr_ctx_create_sample(self.h, _p(rows, C.c_float), sm.N, sm.F, _p(sm.labels, C.c_float),
+                                          _p(sm.qoff, C.c_uint64), sm.Q, _p(doc_ids, C.c_uint32),
+                                          _p(key, C.c_uint32) if key is not None else None, C.byref(sm.h)))
+        return sm
+
+    def pull_scores(self, full):
+        """(sample context) copies the current scores of `full` (qr_sample_pull_scores)"""
+        _check(lib().qr_sample_pull_scores(self.h, full.h))
 
     def close(self):
         if self.h:

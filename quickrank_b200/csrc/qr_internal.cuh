@@ -118,6 +118,11 @@ struct qr_ctx {
   unsigned long long *d_maxabs = nullptr;  // bits of max |lambda|
   int *d_qexp = nullptr;          // fixed-point exponent chosen for this tree
   uint32_t *d_rankpos = nullptr;  // [N] position (within its query) of the doc at each rank
+  // document sample of another context (qr_ctx_create_sample): where each document's score and its ranking key
+  // live in the sampled context's score array, and the gathered ranking keys (nullptr: rank by d_scores)
+  uint32_t *d_src_doc = nullptr, *d_key_doc = nullptr;   // [N]
+  double *d_rankkey = nullptr;                           // [N]
+  size_t sample_of_N = 0;                                // documents of the sampled context (0: not a sample)
   double *d_qndcg = nullptr;      // [Q]
   double *d_metric = nullptr;     // [1]
   double *d_vec_qndcg = nullptr, *d_vec_metric = nullptr;   // evaluate_vectors: [vec_cap][Q] per-query values, [vec_cap] means

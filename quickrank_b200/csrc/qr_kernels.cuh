@@ -615,6 +615,17 @@ __global__ void mart_pseudo_kernel(const double *scores, const float *labels, si
   if (i < N) lam[i] = (double) labels[i] - scores[i];
 }
 
+// A document sample's view of the sampled context's scores (qr_sample_pull_scores): each document's own score, and
+// the score it is RANKED by — lambdamart.cc:94 copies scores_on_training_[d], d the document's position within its
+// query, not offset + d, so a sampled query is sorted by the scores of the first documents of the dataset.
+__global__ void sample_gather_kernel(const double *__restrict__ full_scores, const uint32_t *__restrict__ src,
+                                     const uint32_t *__restrict__ key, size_t N, double *scores, double *rankkey) {
+  size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  scores[i] = full_scores[src[i]];
+  if (key) rankkey[i] = full_scores[key[i]];
+}
+
 // ---- fixed-point view of the pseudo-responses (FAST histogram mode) -----------------------
 __global__ void maxabs_kernel(const double *lam, size_t N, unsigned long long *maxbits) {
   double m = 0.0;

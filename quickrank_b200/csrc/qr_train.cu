@@ -396,7 +396,7 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
 static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t F, const float *labels,
                              const uint64_t *qoffsets, size_t Q, const qr_params *params,
                              const unsigned char *comm_id, int rank, int world, const qr_ctx *thr_from,
-                             qr_ctx **out) {
+                             qr_ctx **out, bool sample = false) {
   if (!feat || !labels || !qoffsets || !params || !out || N == 0 || F == 0 || Q == 0) {
     set_error("qr_ctx_create: null or empty argument");
     return QR_EINVAL;
@@ -476,7 +476,7 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   } else {
     QR_CUDA(cudaMemcpyAsync(d_col, feat, N * F * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   }
-  c->eval_only = thr_from != nullptr;
+  c->eval_only = thr_from != nullptr && !sample;   // (a document sample is binned with the thresholds of the whole set and trained on)
   clk.lap("feature upload (+transpose)");
   int rc = build_binning(c, d_col, thr_from);
   cudaFree(d_col);
@@ -701,7 +701,9 @@ static int ensure_ranking(qr_ctx *c) {
     attr_set = true;
   }
   const unsigned grid = (unsigned) ((c->Q + kRankWarps - 1) / kRankWarps);
-  QR_LAUNCH(c, PH_RANK, rank_kernel<kRankWarps>, grid, kRankWarps * 32, smem, c->d_scores, c->d_labels,
+  // (a document sample ranks by its gathered keys: lambdamart.cc:94, see qr_ctx_create_sample)
+  QR_LAUNCH(c, PH_RANK, rank_kernel<kRankWarps>, grid, kRankWarps * 32, smem,
+            (const double *) (c->d_rankkey ? c->d_rankkey : c->d_scores), c->d_labels,
             c->d_gain, c->d_qoff, c->d_idcg, c->d_lg, (uint32_t) c->Q, c->maxlen, c->cutoff,
             c->d_rankpos, c->d_qndcg);
   c->ranking_valid = true;
@@ -837,6 +839,52 @@ int qr_ctx_create_eval(qr_ctx *train, const float *feat_rowmajor, size_t N, size
   return rc;
 }
 
+// A document sample of `full` as a training context of its own (LambdaMartSelective::learn,
+// lambdamartselective.cc:185-206: pseudo-responses, root histogram and tree fit run over `sampleids` only).
+int qr_ctx_create_sample(qr_ctx *full, const float *feat_rowmajor, size_t N, size_t F, const float *labels,
+                         const uint64_t *qoff, size_t Q, const uint32_t *src_doc, const uint32_t *key_doc, qr_ctx **out) {
+  if (out) *out = nullptr;
+  if (!full || !src_doc) { set_error("qr_ctx_create_sample: null argument"); return QR_EINVAL; }
+  if (full->eval_only || full->comm) { set_error("qr_ctx_create_sample: the sampled context must be a single-GPU training context"); return QR_EINVAL; }
+  if (F != full->F) { set_error("the sample has %zu features, the training set has %zu", F, full->F); return QR_EINVAL; }
+  for (size_t i = 0; i < N; ++i)
+    if (src_doc[i] >= full->N || (key_doc && key_doc[i] >= full->N)) {
+      set_error("qr_ctx_create_sample: document index out of range at %zu", i);
+      return QR_EINVAL;
+    }
+  qr_params p = full->p;
+  p.device = full->device;
+  p.hist_mode = QR_HIST_FAST;   // (sums over a sample have no reference order to follow: fixed point)
+  int rc = ctx_create_common(feat_rowmajor, true, N, F, labels, qoff, Q, &p, nullptr, 0, 1, full, out, true);
+  if (rc == QR_OK) {
+    qr_ctx *c = *out;
+    c->sample_of_N = full->N;
+    rc = dev_alloc(&c->d_src_doc, N);
+    if (rc == QR_OK && cudaMemcpy(c->d_src_doc, src_doc, N * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = QR_ECUDA;
+    if (rc == QR_OK && key_doc) {
+      rc = dev_alloc(&c->d_key_doc, N);
+      if (rc == QR_OK) rc = dev_alloc(&c->d_rankkey, N);
+      if (rc == QR_OK && cudaMemcpy(c->d_key_doc, key_doc, N * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = QR_ECUDA;
+    }
+    if (rc == QR_ECUDA) set_error("qr_ctx_create_sample: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
+  return rc;
+}
+
+int qr_sample_pull_scores(qr_ctx *c, qr_ctx *full) {
+  if (!c || !full || !c->d_src_doc || c->sample_of_N != full->N || c->device != full->device) {
+    set_error("qr_sample_pull_scores: not a sample of this context");
+    return QR_EINVAL;
+  }
+  cudaSetDevice(c->device);
+  QR_CUDA(cudaStreamSynchronize(full->stream));   // (the two contexts run on streams of their own)
+  QR_LAUNCH(c, PH_RANK, sample_gather_kernel, (unsigned) ((c->N + 255) / 256), 256, 0, (const double *) full->d_scores,
+            (const uint32_t *) c->d_src_doc, (const uint32_t *) c->d_key_doc, c->N, c->d_scores, c->d_rankkey);
+  c->ranking_valid = false;
+  return QR_OK;
+}
+
 int qr_ctx_destroy(qr_ctx *c) {
   if (!c) return QR_OK;
   cudaSetDevice(c->device);
@@ -851,7 +899,7 @@ int qr_ctx_destroy(qr_ctx *c) {
                   c->d_root_cnt, c->d_fbest_lc, c->d_totals, c->d_node, c->d_cids, c->d_clamq, c->d_counts,
                   c->d_sq_built, c->d_leafmeta, c->d_sq_acc, c->d_cand, c->d_noderec, c->d_kspan, c->d_rows,
                   c->d_perm, c->d_cell_pos, c->d_mark, c->d_sq_chunks, c->d_sq_replayed, c->d_fskip,
-                  c->d_vec_qndcg, c->d_vec_metric};
+                  c->d_vec_qndcg, c->d_vec_metric, c->d_src_doc, c->d_key_doc, c->d_rankkey};
   for (void *p : ptrs) if (p) cudaFree(p);
   if (c->h_res) cudaFreeHost(c->h_res);
   if (c->h_leafval) cudaFreeHost(c->h_leafval);

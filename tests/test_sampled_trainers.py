@@ -1,0 +1,233 @@
+"""LambdaMART on a per-query document sample: LAMBDAMART-SELECTIVE and STOCHASTIC-NEGATIVE.
+
+CPU: the host's sample selection (host/src/sampled_trainers.cc) against the unmodified reference's
+LambdaMartSelective::sampling_query_level on the same labels / scores, every strategy.
+GPU: the sample as a training context of its own (qr_ctx_create_sample) — pseudo-responses of a masked dataset
+bit-equal to the reference's LambdaMart::compute_pseudoresponses(sample_presence), the identity sample growing the
+trees of the full context, and whole `quicklearn --algo LAMBDAMART-SELECTIVE` runs against the reference's learn()."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import qr_testlib as common
+from oracle import pyref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+QL = os.path.join(ROOT, "host", "bin", "quicklearn")
+CHECK = os.path.join(ROOT, "host", "bin", "selective_check")
+
+needs_ref = pytest.mark.skipif(not pyref.available(), reason="oracle/_ref/libqr_ref.so not built")
+
+
+def _sampling_case(seed, ties, q=40):
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(1, 60, size=q)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    n = int(off[-1])
+    labels = rng.choice([0, 0, 0, 1, 2, 3], size=n).astype(np.float32)
+    scores = rng.normal(size=n)
+    if ties:
+        scores = np.round(scores, 1)
+    return labels, scores, off
+
+
+@needs_ref
+@pytest.mark.parametrize("negative", ["RATIO", "MUL", "POS"])
+@pytest.mark.parametrize("adaptive", ["NO", "FIXED", "RATIO", "MIX"])
+def test_sample_selection_matches_the_reference(negative, adaptive):
+    """sampling_query_level (lambdamartselective.cc:326-493): same sample size and the same permuted id list —
+    std::sort under the reference's comparators, float quotas, random_shuffle's rand() stream after srand(0)."""
+    assert os.path.exists(CHECK), "build host/ first"
+    checked = 0
+    for rank, rnd in [(0.3, 0.2), (0.1, 0.0), (0.0, 0.37), (0.55, 0.45), (0.7, 0.6), (0.013, 0.9)]:
+        for adapt in (1.0, 0.37, 0.0):
+            for ties in (False, True):
+                if negative == "RATIO" and adaptive == "RATIO" and rank + rnd > 1:
+                    continue   # rank factor = sum of the two > 1: the reference's unsigned arithmetic underflows
+                labels, scores, off = _sampling_case(int(rank * 1000 + rnd * 10), ties)
+                inp = "%d %d\n%s\n%s\n" % (len(off) - 1, len(labels), " ".join(str(int(o)) for o in off),
+                                           "\n".join("%d %.17g" % (l, s) for l, s in zip(labels, scores)))
+                out = subprocess.run([CHECK, repr(rank), repr(rnd), adaptive, negative, repr(adapt)], input=inp,
+                                     capture_output=True, text=True)
+                assert out.returncode == 0, out.stderr
+                vals = np.array(out.stdout.split(), dtype=np.uint64)
+                want_n, want_ids = pyref.selective_sample(labels, scores, off, rank, rnd, adaptive, negative, adapt)
+                assert int(vals[0]) == want_n, (rank, rnd, adapt, ties)
+                assert np.array_equal(vals[1:], want_ids), (rank, rnd, adapt, ties)
+                checked += 1
+    assert checked >= 30
+
+
+def test_selective_rejects_what_the_reference_dies_on(tmp_path):
+    """--sampling-iterations 0 with a sampling factor set is a division by zero in the reference
+    (lambdamartselective.cc:170-171); here it is an error message — checked before any device work."""
+    from quickrank_b200 import api
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is present (the check below relies on failing before the device is touched)")
+    tr = str(tmp_path / "t.txt")
+    open(tr, "w").write("1 qid:1 1:0.5\n0 qid:1 1:0.1\n")
+    out = subprocess.run([QL, "--algo", "LAMBDAMART-SELECTIVE", "--train", tr, "--num-trees", "2"], capture_output=True, text=True)
+    assert out.returncode != 0
+    assert "sampling-iterations" in out.stderr or "CUDA" in out.stderr or "GPU" in out.stderr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU
+# ---------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("share", [1.0, 0.6, 0.15])
+def test_masked_pseudoresponses_match_the_reference(share):
+    """compute_pseudoresponses with sample_presence (lambdamart.cc:84-105): queries compacted to their sampled
+    documents and ranked by scores_on_training_[position in query] (the offset is dropped, :94), rho from the
+    documents' own scores.  Bit-equal lambdas and weights on the sampled documents, tie-heavy scores included."""
+    from quickrank_b200 import api
+    x, l, off = common.dataset(n=6000, f=10, q=60, seed=21)
+    rng = np.random.default_rng(5)
+    for scores in (rng.normal(size=len(l)), common.tie_heavy_scores(len(l), rng)):
+        mask = rng.random(len(l)) < share if share < 1 else np.ones(len(l), bool)
+        with pyref.RefSession("LAMBDAMART", x, l, off, ntrees=1, nleaves=4) as s:
+            s.init()
+            s.set_scores(scores)
+            s.compute_pseudoresponses_masked(mask)
+            want_lam, want_w = s.get_gradients()
+        ids = np.nonzero(mask)[0]
+        with api.Trainer(x, l, off, nleaves=4) as full:
+            full.set_scores(scores)
+            with full.sample_context(x, ids) as sm:
+                sm.pull_scores(full)
+                assert np.array_equal(sm.get_scores(), scores[ids])
+                sm.compute_pseudoresponses()
+                lam, w = sm.get_pseudoresponses()
+        assert np.array_equal(lam, want_lam[ids])
+        assert np.array_equal(w, want_w[ids])
+        assert not want_lam[~mask].any()
+
+
+@pytest.mark.gpu
+def test_identity_sample_grows_the_trees_of_the_full_context():
+    """A sample holding every document, ranked by its own scores, is the training set: the same trees, bit for bit,
+    as the full context in fixed-point mode, over several iterations of pull -> lambdas -> fit -> apply."""
+    from quickrank_b200 import api
+    x, l, off = common.dataset(n=8000, f=16, q=80, seed=4)
+    with api.Trainer(x, l, off, nleaves=12, minleafsupport=20) as plain, \
+            api.Trainer(x, l, off, nleaves=12, minleafsupport=20) as full:
+        with full.sample_context(x, np.arange(len(l)), rank_by_position=False) as sm:
+            for _ in range(4):
+                want, want_metric = plain.boost_iteration()
+                sm.pull_scores(full)
+                sm.compute_pseudoresponses()
+                got = sm.fit_regressor_on_gradient()
+                full.apply_tree(got, full.shrinkage)
+                for k in ("feature", "threshold_idx", "left", "right", "value", "count"):
+                    assert np.array_equal(got[k], want[k]), k
+                assert np.array_equal(full.get_scores(), plain.get_scores())
+                assert full.evaluate_dataset() == want_metric
+
+
+def _write_svml(path, x, l, off):
+    with open(path, "w") as f:
+        for q in range(len(off) - 1):
+            for i in range(int(off[q]), int(off[q + 1])):
+                f.write("%d qid:%d %s\n" % (int(l[i]), q + 1, " ".join("%d:%.9g" % (j + 1, x[i, j]) for j in range(x.shape[1]))))
+
+
+def _leaf_of(t, data):
+    node = np.zeros(len(data), np.int64)
+    while True:
+        f = t["feature"][node]
+        act = np.nonzero(f >= 0)[0]
+        if len(act) == 0:
+            return node
+        left = data[act, f[act]] <= t["threshold"][node[act]]
+        node[act] = np.where(left, t["left"][node[act]], t["right"][node[act]])
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("sel,cli", [
+    (dict(sampling_iterations=3, rank_factor=0.3, random_factor=0.2),
+     ["--sampling-iterations", "3", "--rank-sampling-factor", "0.3", "--random-sampling-factor", "0.2"]),
+    (dict(sampling_iterations=2, rank_factor=0.5, random_factor=0.0, negative="POS"),
+     ["--sampling-iterations", "2", "--rank-sampling-factor", "0.5", "--random-sampling-factor", "0.0", "--negative-strategy", "POS"]),
+    (dict(sampling_iterations=2, rank_factor=1.5, random_factor=0.5, negative="MUL", adaptive="MIX", normalization_factor=4.0),
+     ["--sampling-iterations", "2", "--rank-sampling-factor", "1.5", "--random-sampling-factor", "0.5", "--negative-strategy", "MUL",
+      "--adaptive-strategy", "MIX", "--normalization-factor", "4"]),
+])
+def test_selective_matches_the_reference_learn_loop(tmp_path, sel, cli):
+    """LambdaMartSelective::learn (lambdamartselective.cc:46-313) end to end: the sizes of every sample ("Reducing
+    training size from N to M"), the sampling factors it prints, the NDCG trajectory (4 decimals printed) and the
+    trees — split features and structure equal, thresholds equal or cutting the training documents into the same
+    sets, leaf outputs within 1e-9 relative (fixed-point sums on the sample against the reference's FP64 order)."""
+    from quickrank_b200 import modelxml
+    x, l, off = common.dataset(n=4000, f=12, q=40, seed=8)
+    ntrees = 9
+    with pyref.RefSession("LAMBDAMART-SELECTIVE", x, l, off, ntrees=ntrees, nleaves=8, minleafsupport=10, selective=sel) as s:
+        s.learn()
+        want_metric = s.metric_history()
+        want_log = s.log()
+        want_trees = [s.tree(t) for t in range(s.num_trees())]
+    tr, model = str(tmp_path / "train.txt"), str(tmp_path / "sel.xml")
+    _write_svml(tr, x, l, off)
+    cmd = [QL, "--algo", "LAMBDAMART-SELECTIVE", "--train", tr, "--num-trees", str(ntrees), "--num-leaves", "8",
+           "--min-leaf-support", "10", "--model-out", model, "--end-after-rounds", "0", "--partial", "0"] + cli
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    pick = lambda text, pat: re.findall(pat, text, flags=re.M)
+    for pat in (r"^Reducing training size from \d+ to \d+", r"^Rank Factor: .*", r"^N\. Positives: .*"):
+        assert pick(out.stdout, pat) == pick(want_log, pat), (pat, out.stdout, want_log)
+    assert len(pick(want_log, r"^Reducing")) >= 3
+    rows = re.findall(r"^\s+(\d+)\s+([0-9.]+)", out.stdout, flags=re.M)
+    assert len(rows) == ntrees == len(want_metric), out.stdout
+    got_metric = np.array([float(r[1]) for r in rows])
+    assert np.max(np.abs(got_metric - want_metric)) <= 6e-5, (got_metric, want_metric)
+    _info, got_trees, _weights = modelxml.read_model(model)
+    assert len(got_trees) == ntrees and "<type>LAMBDAMART-SELECTIVE</type>" in open(model).read()
+    for a, b in zip(got_trees, want_trees):
+        assert np.array_equal(a["feature"], b["feature"])
+        assert np.array_equal(a["left"], b["left"]) and np.array_equal(a["right"], b["right"])
+        if not np.array_equal(a["threshold"], b["threshold"]):
+            assert np.array_equal(_leaf_of(a, x), _leaf_of(b, x))
+        lv = a["feature"] < 0
+        assert np.allclose(a["value"][lv], b["value"][lv], rtol=1e-9, atol=1e-14)
+    # the saved model loads in stock QuickRank (type dispatch, ltr_algorithm.cc:100-102)
+    assert np.all(np.isfinite(pyref.score_with_model(model, x)))
+
+
+@pytest.mark.gpu
+def test_stochastic_negative_keeps_positives_and_a_share_of_negatives(tmp_path):
+    """StochasticNegative::learn (stochasticnegative.cc:46-283): every iteration after the first trains on all positives
+    plus floor(subsample x negatives) documents per query.  The reference seeds its shuffle from the wall clock, so the
+    checks are structural: the sample size it reports, reproducibility under --seed, a different draw under another
+    seed, and a model that improves on the training set."""
+    x, l, off = common.dataset(n=4000, f=12, q=40, seed=8)
+    tr = str(tmp_path / "train.txt")
+    _write_svml(tr, x, l, off)
+    want = 0
+    for q in range(len(off) - 1):
+        lab = l[int(off[q]):int(off[q + 1])]
+        npos = int((lab > 0).sum())
+        want += npos + int(np.floor(np.float32(0.4) * np.float32(len(lab) - npos)))
+
+    def run(seed):
+        model = str(tmp_path / ("sn%d.xml" % seed))
+        cmd = [QL, "--algo", "STOCHASTIC-NEGATIVE", "--train", tr, "--num-trees", "6", "--num-leaves", "8", "--subsample", "0.4",
+               "--min-leaf-support", "10", "--model-out", model, "--end-after-rounds", "0", "--partial", "0", "--seed", str(seed)]
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr + out.stdout
+        sizes = [int(v) for v in re.findall(r"^Reducing training size from 4000 to (\d+)", out.stdout, flags=re.M)]
+        assert sizes == [want] * 5, (sizes, want)
+        rows = re.findall(r"^\s+(\d+)\s+([0-9.]+)", out.stdout, flags=re.M)
+        assert len(rows) == 6
+        metric = [float(r[1]) for r in rows]
+        assert metric[-1] > metric[0]
+        return open(model).read()
+
+    a, b, c = run(1), run(1), run(2)
+    assert a == b
+    assert a != c
+    assert "<type>STOCHASTIC-NEGATIVE</type>" in a
