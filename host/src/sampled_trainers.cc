@@ -54,8 +54,6 @@ void SampledLambdaMart::build_sample_context(const data::Dataset &dataset, const
   const size_t N = dataset.num_instances(), F = dataset.num_features();
   std::vector<char> present(N, 0);
   for (size_t i = 0; i < n; ++i) present[ids[i]] = 1;
-  std::vector<float> rows;
-  rows.reserve(n * F);
   std::vector<float> labels;
   labels.reserve(n);
   std::vector<uint32_t> src, key;
@@ -66,7 +64,6 @@ void SampledLambdaMart::build_sample_context(const data::Dataset &dataset, const
     const size_t begin = dataset.offset(q), end = dataset.offset(q + 1);
     for (size_t d = begin; d < end; ++d) {
       if (!present[d]) continue;
-      rows.insert(rows.end(), dataset.data() + d * F, dataset.data() + (d + 1) * F);
       labels.push_back(dataset.getLabel(d));
       src.push_back((uint32_t) d);
       key.push_back((uint32_t) (d - begin));   // lambdamart.cc:94
@@ -79,7 +76,8 @@ void SampledLambdaMart::build_sample_context(const data::Dataset &dataset, const
     std::cerr << "!!! The document sample is empty." << std::endl;
     exit(EXIT_FAILURE);
   }
-  if (qr_ctx_create_sample(ctx_, rows.data(), src.size(), F, labels.data(), qoff.data(), qoff.size() - 1, src.data(),
+  // (no feature rows: the sample's bins are gathered on the device from the full context's)
+  if (qr_ctx_create_sample(ctx_, nullptr, src.size(), F, labels.data(), qoff.data(), qoff.size() - 1, src.data(),
                            key.data(), &sample_ctx_) != QR_OK)
     die("Impossible to initialise the GPU context of the document sample");
 }

@@ -118,6 +118,8 @@ int qr_ctx_create_eval(qr_ctx *train, const float *feat_rowmajor, size_t N, size
  * fit and leaf outputs on it.  The rows are the sampled documents in ascending order within each query
  * (the "cleaned" order of lambdamart.cc:90-98; queries left empty are dropped), binned with the
  * thresholds of `full`; sums are fixed-point (QR_HIST_FAST) whatever the mode of `full`.
+ * feat_rowmajor = the sampled rows [N][F], or NULL: the bins are then gathered on the device from those `full`
+ * already holds (no feature values are uploaded and nothing is binned again) — what the host trainers do.
  * src_doc[i] = the document of `full` row i is; key_doc[i] = the document of `full` whose score row i is
  * RANKED by (lambdamart.cc:94 reads scores_on_training_[d] with d relative to the query, so
  * key_doc[i] = src_doc[i] - offset(query of i); NULL: rank by the document's own score).

@@ -626,6 +626,18 @@ __global__ void sample_gather_kernel(const double *__restrict__ full_scores, con
   if (key) rankkey[i] = full_scores[key[i]];
 }
 
+// The bin matrix of a document sample, gathered from the sampled context's panels (same thresholds, same layout):
+// panels[p][i] = from[p][src[i]], plus the document-major copy when the sample keeps one.
+__global__ void sample_gather_panels_kernel(const uint4 *__restrict__ from, size_t from_N, const uint32_t *__restrict__ src,
+                                            size_t N, uint32_t npanels, uint4 *panels, uint4 *rows) {
+  const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = blockIdx.y;
+  if (i >= N) return;
+  const uint4 v = from[(size_t) p * from_N + src[i]];
+  panels[(size_t) p * N + i] = v;
+  if (rows != nullptr) rows[i * npanels + p] = v;
+}
+
 // ---- fixed-point view of the pseudo-responses (FAST histogram mode) -----------------------
 __global__ void maxabs_kernel(const double *lam, size_t N, unsigned long long *maxbits) {
   double m = 0.0;

@@ -123,6 +123,8 @@ static int build_binning(qr_ctx *c, const float *d_col, const qr_ctx *thr_from) 
     cudaFree(d_bad);
     cudaFree(d_scratch);
     if (bad) { set_error("feature matrix contains NaN or infinite values"); return QR_EINVAL; }
+    // a document sample holds training documents only: no bin beyond those the sampled context occupies, same bin width
+    if (!c->eval_only && thr_from->bin_bytes == 1) max_bin = std::min<uint32_t>(max_bin, 255u);
     return finish_binning(c, d_col, max_bin);
   }
   uint32_t *d_keys = nullptr, *d_keys_out = nullptr;
@@ -393,11 +395,37 @@ struct InitClock {
 
 static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoffsets, const qr_params *params, InitClock &clk);
 
+// The bins of a document sample taken from the sampled context on the device: same thresholds, same bin width and
+// panel layout, rows src[0..N) of its panels — no feature values cross the bus and nothing is binned again.
+static int gather_binning(qr_ctx *c, const qr_ctx *from, const uint32_t *src_host) {
+  const size_t N = c->N, F = c->F;
+  c->thr = from->thr;
+  uint32_t max_bin = 0;
+  for (size_t f = 0; f < F; ++f) max_bin = std::max<uint32_t>(max_bin, (uint32_t) c->thr[f].size() - 1);
+  if (from->bin_bytes == 1) max_bin = std::min<uint32_t>(max_bin, 255u);
+  QR_TRY(binning_layout(c, max_bin, nullptr));
+  if (c->bin_bytes != from->bin_bytes || c->npanels != from->npanels || c->ncells != from->ncells) {
+    set_error("internal: the sample's bin layout differs from the sampled context's");
+    return QR_ECUDA;
+  }
+  QR_TRY(dev_alloc(&c->d_src_doc, N));
+  QR_CUDA(cudaMemcpyAsync(c->d_src_doc, src_host, N * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  QR_TRY(dev_alloc(&c->d_panels, (size_t) c->npanels * N));
+  if (!c->exact && c->npanels > 1 && (getenv("QR_ROW_COPY") == nullptr || atoi(getenv("QR_ROW_COPY")) != 0))
+    QR_TRY(dev_alloc(&c->d_rows, (size_t) c->npanels * N));
+  QR_CUDA(cudaStreamSynchronize(from->stream));
+  sample_gather_panels_kernel<<<dim3((unsigned) ((N + 255) / 256), c->npanels), 256, 0, c->stream>>>(
+      from->d_panels, from->N, c->d_src_doc, N, c->npanels, c->d_panels, c->d_rows);
+  QR_CUDA(cudaGetLastError());
+  QR_CUDA(cudaStreamSynchronize(c->stream));
+  return QR_OK;
+}
+
 static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t F, const float *labels,
                              const uint64_t *qoffsets, size_t Q, const qr_params *params,
                              const unsigned char *comm_id, int rank, int world, const qr_ctx *thr_from,
-                             qr_ctx **out, bool sample = false) {
-  if (!feat || !labels || !qoffsets || !params || !out || N == 0 || F == 0 || Q == 0) {
+                             qr_ctx **out, bool sample = false, const uint32_t *gather_src = nullptr) {
+  if ((!feat && !gather_src) || !labels || !qoffsets || !params || !out || N == 0 || F == 0 || Q == 0) {
     set_error("qr_ctx_create: null or empty argument");
     return QR_EINVAL;
   }
@@ -461,6 +489,12 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     c->N_local_max = (size_t) nmax;
   }
 
+  if (gather_src) {   // a document sample cut from the bins of `thr_from`
+    c->eval_only = false;
+    QR_TRY(gather_binning(c, thr_from, gather_src));
+    clk.lap("bins gathered from the sampled context");
+    return ctx_create_state(c, labels, qoffsets, params, clk);
+  }
   // features -> device column-major (VerticalDataset layout), then bins; floats are released
   float *d_col = nullptr;
   QR_TRY(dev_alloc(&d_col, N * F));
@@ -855,12 +889,16 @@ int qr_ctx_create_sample(qr_ctx *full, const float *feat_rowmajor, size_t N, siz
   qr_params p = full->p;
   p.device = full->device;
   p.hist_mode = QR_HIST_FAST;   // (sums over a sample have no reference order to follow: fixed point)
-  int rc = ctx_create_common(feat_rowmajor, true, N, F, labels, qoff, Q, &p, nullptr, 0, 1, full, out, true);
+  // feat_rowmajor == NULL: the sample's bins are gathered on the device from the panels of `full`
+  int rc = ctx_create_common(feat_rowmajor, true, N, F, labels, qoff, Q, &p, nullptr, 0, 1, full, out, true,
+                             feat_rowmajor ? nullptr : src_doc);
   if (rc == QR_OK) {
     qr_ctx *c = *out;
     c->sample_of_N = full->N;
-    rc = dev_alloc(&c->d_src_doc, N);
-    if (rc == QR_OK && cudaMemcpy(c->d_src_doc, src_doc, N * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = QR_ECUDA;
+    if (!c->d_src_doc) {
+      rc = dev_alloc(&c->d_src_doc, N);
+      if (rc == QR_OK && cudaMemcpy(c->d_src_doc, src_doc, N * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = QR_ECUDA;
+    }
     if (rc == QR_OK && key_doc) {
       rc = dev_alloc(&c->d_key_doc, N);
       if (rc == QR_OK) rc = dev_alloc(&c->d_rankkey, N);

@@ -98,7 +98,7 @@ def test_masked_pseudoresponses_match_the_reference(share):
         ids = np.nonzero(mask)[0]
         with api.Trainer(x, l, off, nleaves=4) as full:
             full.set_scores(scores)
-            with full.sample_context(x, ids) as sm:
+            with full.sample_context(x, ids, gather=bool(share < 0.5)) as sm:
                 sm.pull_scores(full)
                 assert np.array_equal(sm.get_scores(), scores[ids])
                 sm.compute_pseudoresponses()
@@ -109,14 +109,15 @@ def test_masked_pseudoresponses_match_the_reference(share):
 
 
 @pytest.mark.gpu
-def test_identity_sample_grows_the_trees_of_the_full_context():
+@pytest.mark.parametrize("gather", [True, False])
+def test_identity_sample_grows_the_trees_of_the_full_context(gather):
     """A sample holding every document, ranked by its own scores, is the training set: the same trees, bit for bit,
     as the full context in fixed-point mode, over several iterations of pull -> lambdas -> fit -> apply."""
     from quickrank_b200 import api
     x, l, off = common.dataset(n=8000, f=16, q=80, seed=4)
     with api.Trainer(x, l, off, nleaves=12, minleafsupport=20) as plain, \
             api.Trainer(x, l, off, nleaves=12, minleafsupport=20) as full:
-        with full.sample_context(x, np.arange(len(l)), rank_by_position=False) as sm:
+        with full.sample_context(x, np.arange(len(l)), rank_by_position=False, gather=gather) as sm:
             for _ in range(4):
                 want, want_metric = plain.boost_iteration()
                 sm.pull_scores(full)
@@ -180,7 +181,7 @@ def test_selective_matches_the_reference_learn_loop(tmp_path, sel, cli):
     pick = lambda text, pat: re.findall(pat, text, flags=re.M)
     for pat in (r"^Reducing training size from \d+ to \d+", r"^Rank Factor: .*", r"^N\. Positives: .*"):
         assert pick(out.stdout, pat) == pick(want_log, pat), (pat, out.stdout, want_log)
-    assert len(pick(want_log, r"^Reducing")) >= 3
+    assert len(pick(want_log, r"^Reducing")) >= 2
     rows = re.findall(r"^\s+(\d+)\s+([0-9.]+)", out.stdout, flags=re.M)
     assert len(rows) == ntrees == len(want_metric), out.stdout
     got_metric = np.array([float(r[1]) for r in rows])
