@@ -275,6 +275,16 @@ int qr_ls_feature_points(qr_linesearch *ls, const double *weights, uint32_t f, c
                          double *metrics);
 /* step 2: metrics[p] = metric of weights + p * step, p = 0 .. npoints-1 (line_search.cc:303-325) */
 int qr_ls_line_points(qr_linesearch *ls, const double *weights, const double *step, uint32_t npoints, double *metrics);
+/* CLEAVER's quality-loss passes (quality_loss_pruning.cc:59-70, quality_loss_adv_pruning.cc:60-81): metrics[c] = metric
+ * of the ensemble without column cols[c], i.e. of sum_f weights[f] * x[.][f] - weights[col] * x[.][col] */
+int qr_ls_drop_points(qr_linesearch *ls, const double *weights, const uint32_t *cols, uint32_t ncols, double *metrics);
+/* QUALITY_LOSS_ADV's running scores (quality_loss_adv_pruning.cc:88-92): the cached weighted sums of `weights` lose
+ * column f in place (sum -= weights[f] * x[.][f]) and from now on stand for `weights` with weights[f] = 0 — the
+ * sequentially updated vector the reference carries from one greedy step to the next, not a fresh sum */
+int qr_ls_drop_column(qr_linesearch *ls, const double *weights, uint32_t f);
+/* ScoreLossPruning (score_loss_pruning.cc:58-63): loss[f] = sum over documents, in document order, of
+ * weights[f] * x[s][f] / (sum_g weights[g] * x[s][g]); loss has T entries */
+int qr_ls_score_loss(qr_linesearch *ls, const double *weights, double *loss);
 uint64_t qr_ls_launch_count(qr_linesearch *ls);
 
 /* Waits for the scorer's stream (qr_score_dataset_device is asynchronous). */

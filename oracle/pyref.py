@@ -346,7 +346,7 @@ def linesearch(x, labels, qoff, cutoff=10, num_points=20, window_size=1.0, reduc
     return out
 
 
-CLEAVER_METHODS = {"LAST": 0, "SKIP": 1, "LOW_WEIGHTS": 2, "QUALITY_LOSS": 3}
+CLEAVER_METHODS = {"LAST": 0, "SKIP": 1, "LOW_WEIGHTS": 2, "QUALITY_LOSS": 3, "QUALITY_LOSS_ADV": 4, "SCORE_LOSS": 5}
 
 
 def cleaver(method, x, labels, qoff, weights, pruning_rate, cutoff=10, num_points=0, window_size=1.0,

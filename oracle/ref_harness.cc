@@ -30,6 +30,8 @@
 #include "optimization/post_learning/cleaver/skip_pruning.h"
 #include "optimization/post_learning/cleaver/low_weights_pruning.h"
 #include "optimization/post_learning/cleaver/quality_loss_pruning.h"
+#include "optimization/post_learning/cleaver/quality_loss_adv_pruning.h"
+#include "optimization/post_learning/cleaver/score_loss_pruning.h"
 #include "learning/forests/lambdamart.h"
 #include "learning/forests/obliviousmart.h"
 #include "learning/forests/obliviouslambdamart.h"
@@ -607,7 +609,8 @@ int qref_linesearch(const float *x, uint64_t N, uint64_t T, const float *labels,
 
 // Cleaver::optimize (src/optimization/post_learning/cleaver/cleaver.cc:166-412) with one of the deterministic pruning
 // strategies on a partial-score matrix, starting from `weights`; line search before / after pruning as the strategy
-// asks (num_points == 0: no line search).  method: 0 LAST, 1 SKIP, 2 LOW_WEIGHTS, 3 QUALITY_LOSS.
+// asks (num_points == 0: no line search).  method: 0 LAST, 1 SKIP, 2 LOW_WEIGHTS, 3 QUALITY_LOSS, 4 QUALITY_LOSS_ADV,
+// 5 SCORE_LOSS.
 int qref_cleaver(int method, const float *x, uint64_t N, uint64_t T, const float *labels, const uint64_t *qoff,
                  uint64_t Q, uint64_t cutoff, double pruning_rate, const double *weights, uint32_t num_points,
                  double window_size, double reduction_factor, uint32_t max_iterations, double *out_weights) {
@@ -630,6 +633,8 @@ int qref_cleaver(int method, const float *x, uint64_t N, uint64_t T, const float
     case 1: cl = std::make_shared<pr::SkipPruning>(pruning_rate, ls); break;
     case 2: cl = std::make_shared<pr::LowWeightsPruning>(pruning_rate, ls); break;
     case 3: cl = std::make_shared<pr::QualityLossPruning>(pruning_rate, ls); break;
+    case 4: cl = std::make_shared<pr::QualityLossAdvPruning>(pruning_rate, ls); break;
+    case 5: cl = std::make_shared<pr::ScoreLossPruning>(pruning_rate, ls); break;
     default: return 2;
   }
   std::vector<double> w(weights, weights + T);

@@ -87,6 +87,9 @@ def lib():
         L.qr_ls_evaluate.argtypes = [vp, dp, dp]
         L.qr_ls_feature_points.argtypes = [vp, dp, C.c_uint32, dp, C.c_uint32, dp]
         L.qr_ls_line_points.argtypes = [vp, dp, dp, C.c_uint32, dp]
+        L.qr_ls_drop_points.argtypes = [vp, dp, C.POINTER(C.c_uint32), C.c_uint32, dp]
+        L.qr_ls_drop_column.argtypes = [vp, dp, C.c_uint32]
+        L.qr_ls_score_loss.argtypes = [vp, dp, dp]
         L.qr_ls_launch_count.argtypes = [vp]
         L.qr_ls_launch_count.restype = C.c_uint64
         L.qr_selftest_ordered_squares.argtypes = [dp, sz, C.c_int, C.c_int, dp, dp, C.POINTER(C.c_uint64)]
@@ -436,6 +439,26 @@ class LineSearchDevice:
         st = np.ascontiguousarray(step, np.float64)
         out = np.zeros(npoints, np.float64)
         _check(lib().qr_ls_line_points(self.h, _p(w, C.c_double), _p(st, C.c_double), npoints, _p(out, C.c_double)))
+        return out
+
+    def drop_points(self, weights, cols):
+        """metric of the ensemble without column c, for every c in cols (qr_ls_drop_points)"""
+        w = np.ascontiguousarray(weights, np.float64)
+        cols = np.ascontiguousarray(cols, np.uint32)
+        out = np.zeros(len(cols), np.float64)
+        _check(lib().qr_ls_drop_points(self.h, _p(w, C.c_double), _p(cols, C.c_uint32), len(cols), _p(out, C.c_double)))
+        return out
+
+    def drop_column(self, weights, f):
+        """the device's running sums lose column f in place (qr_ls_drop_column); continue with weights[f] = 0"""
+        w = np.ascontiguousarray(weights, np.float64)
+        _check(lib().qr_ls_drop_column(self.h, _p(w, C.c_double), int(f)))
+
+    def score_loss(self, weights):
+        """per column: sum over documents of the column's share of the score (qr_ls_score_loss)"""
+        w = np.ascontiguousarray(weights, np.float64)
+        out = np.zeros(self.T, np.float64)
+        _check(lib().qr_ls_score_loss(self.h, _p(w, C.c_double), _p(out, C.c_double)))
         return out
 
     def launch_count(self):

@@ -96,6 +96,50 @@ ls_line_points_kernel(const float *__restrict__ x, size_t N, uint32_t T, const d
   }
 }
 
+// CLEAVER's quality-loss passes (quality_loss_pruning.cc:59-70, quality_loss_adv_pruning.cc:60-81): candidate c is
+// the ensemble without column cols[c]: scores[c][s] = total[s] - w[col] * x[s][col] (multiply, then subtract)
+__global__ void ls_drop_points_kernel(const float *__restrict__ x, size_t N, uint32_t T, const uint32_t *__restrict__ cols,
+                                      const double *__restrict__ w, const double *__restrict__ total, uint32_t nc,
+                                      double *scores) {
+  const size_t s = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N) return;
+  const double tot = total[s];
+  const float *row = x + s * T;
+  for (uint32_t c = 0; c < nc; ++c) {
+    const uint32_t f = cols[c];
+    scores[(size_t) c * N + s] = __dsub_rn(tot, __dmul_rn(w[f], (double) row[f]));
+  }
+}
+
+// the reference's running scores after a column is pruned (quality_loss_adv_pruning.cc:88-92): total -= w_f * x[.][f]
+__global__ void ls_drop_column_kernel(const float *__restrict__ x, size_t N, uint32_t T, uint32_t f, double w_f, double *total) {
+  const size_t s = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < N) total[s] = __dsub_rn(total[s], __dmul_rn(w_f, (double) x[s * T + f]));
+}
+
+// ScoreLossPruning (score_loss_pruning.cc:58-63): out[f] = sum over documents, in document order, of
+// w[f] * x[s][f] / total[s] — one sequentially rounded FP64 chain per column.  Thread f owns column f (a warp reads 32
+// consecutive columns of a row: coalesced); the quotients of a batch of documents are computed ahead of the chain of
+// additions, which is the only dependent part.
+constexpr uint32_t kSlBatch = 16;
+__global__ void ls_score_loss_kernel(const float *__restrict__ x, size_t N, uint32_t T, const double *__restrict__ w,
+                                     const double *__restrict__ total, double *out) {
+  const uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= T) return;
+  const double wf = w[f];
+  double acc = 0.0;
+  size_t s = 0;
+  for (; s + kSlBatch <= N; s += kSlBatch) {
+    double q[kSlBatch];
+#pragma unroll
+    for (uint32_t j = 0; j < kSlBatch; ++j) q[j] = __ddiv_rn(__dmul_rn(wf, (double) x[(s + j) * T + f]), total[s + j]);
+#pragma unroll
+    for (uint32_t j = 0; j < kSlBatch; ++j) acc = __dadd_rn(acc, q[j]);
+  }
+  for (; s < N; ++s) acc = __dadd_rn(acc, __ddiv_rn(__dmul_rn(wf, (double) x[s * T + f]), total[s]));
+  out[f] = acc;
+}
+
 }  // namespace qr
 
 using namespace qr;
@@ -216,6 +260,54 @@ int qr_ls_line_points(qr_linesearch *ls, const double *weights, const double *st
     ls->ctx->launches++;
     QR_TRY(evaluate_vectors(ls->ctx, ls->d_scores, np, metrics + p0));
   }
+  return QR_OK;
+}
+
+int qr_ls_drop_points(qr_linesearch *ls, const double *weights, const uint32_t *cols, uint32_t ncols, double *metrics) {
+  if (!ls || !weights || !cols || !metrics) { set_error("qr_ls_drop_points: bad arguments"); return QR_EINVAL; }
+  for (uint32_t c = 0; c < ncols; ++c)
+    if (cols[c] >= ls->T) { set_error("qr_ls_drop_points: column %u out of range", cols[c]); return QR_EINVAL; }
+  QR_CUDA(cudaSetDevice(ls->device));
+  QR_TRY(ls_total(ls, weights));
+  // (after qr_ls_drop_column the cached sums belong to weights the device copy does not hold any more)
+  QR_TRY(ls_upload(ls, ls->d_w, weights, ls->T));
+  uint32_t *d_cols = reinterpret_cast<uint32_t *>(ls->d_points);   // kLsMaxPoints doubles hold kLsMaxPoints indices
+  for (uint32_t c0 = 0; c0 < ncols; c0 += kLsMaxPoints) {
+    const uint32_t nc = std::min(kLsMaxPoints, ncols - c0);
+    QR_CUDA(cudaMemcpyAsync(d_cols, cols + c0, nc * sizeof(uint32_t), cudaMemcpyHostToDevice, ls->ctx->stream));
+    QR_CUDA(cudaStreamSynchronize(ls->ctx->stream));
+    ls_drop_points_kernel<<<(unsigned) ((ls->N + 255) / 256), 256, 0, ls->ctx->stream>>>(
+        ls->d_x, ls->N, (uint32_t) ls->T, d_cols, ls->d_w, ls->d_total, nc, ls->d_scores);
+    QR_CUDA(cudaGetLastError());
+    ls->ctx->launches++;
+    QR_TRY(evaluate_vectors(ls->ctx, ls->d_scores, nc, metrics + c0));
+  }
+  return QR_OK;
+}
+
+int qr_ls_drop_column(qr_linesearch *ls, const double *weights, uint32_t f) {
+  if (!ls || !weights || f >= ls->T) { set_error("qr_ls_drop_column: bad arguments"); return QR_EINVAL; }
+  QR_CUDA(cudaSetDevice(ls->device));
+  QR_TRY(ls_total(ls, weights));
+  ls_drop_column_kernel<<<(unsigned) ((ls->N + 255) / 256), 256, 0, ls->ctx->stream>>>(ls->d_x, ls->N, (uint32_t) ls->T, f,
+                                                                                     weights[f], ls->d_total);
+  QR_CUDA(cudaGetLastError());
+  ls->ctx->launches++;
+  ls->total_w[f] = 0.0;   // the sums now stand for these weights: the next call with them keeps the running sums
+  return QR_OK;
+}
+
+int qr_ls_score_loss(qr_linesearch *ls, const double *weights, double *loss) {
+  if (!ls || !weights || !loss) { set_error("qr_ls_score_loss: bad arguments"); return QR_EINVAL; }
+  QR_CUDA(cudaSetDevice(ls->device));
+  QR_TRY(ls_total(ls, weights));
+  QR_TRY(ls_upload(ls, ls->d_w, weights, ls->T));
+  ls_score_loss_kernel<<<(unsigned) ((ls->T + 127) / 128), 128, 0, ls->ctx->stream>>>(ls->d_x, ls->N, (uint32_t) ls->T, ls->d_w,
+                                                                                    ls->d_total, ls->d_step);
+  QR_CUDA(cudaGetLastError());
+  ls->ctx->launches++;
+  QR_CUDA(cudaMemcpyAsync(loss, ls->d_step, ls->T * sizeof(double), cudaMemcpyDeviceToHost, ls->ctx->stream));
+  QR_CUDA(cudaStreamSynchronize(ls->ctx->stream));
   return QR_OK;
 }
 

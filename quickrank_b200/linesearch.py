@@ -6,10 +6,15 @@ every pass over the documents (weighted sums, rankings, NDCG@k of each candidate
 ``api.LineSearchDevice`` (quickrank_b200/csrc/qr_linesearch.cu), in the reference's own arithmetic: given the same
 matrix the learned weights equal the reference's bit for bit (tests/test_linesearch.py, against oracle/_ref).
 
-``Cleaver.optimize`` is ``Cleaver::optimize`` (src/optimization/post_learning/cleaver/cleaver.cc:166-412) for the
-pruning strategies that need no random numbers: LAST, SKIP, LOW_WEIGHTS (last_pruning.cc, skip_pruning.cc,
-low_weights_pruning.cc) and QUALITY_LOSS (quality_loss_pruning.cc: NDCG of the ensemble without each tree, one GPU
-evaluation per tree).  The matrix is what ``api.Scorer.partial_scores`` returns for an ensemble (driver.cc:411-446).
+``Cleaver.optimize`` is ``Cleaver::optimize`` (src/optimization/post_learning/cleaver/cleaver.cc:166-412) with the
+pruning strategies LAST, SKIP, LOW_WEIGHTS (last_pruning.cc, skip_pruning.cc, low_weights_pruning.cc), QUALITY_LOSS
+(quality_loss_pruning.cc: NDCG of the ensemble without each tree, 32 trees per ranking launch), QUALITY_LOSS_ADV
+(quality_loss_adv_pruning.cc: the same greedily, one tree at a time, on the reference's running score vector),
+SCORE_LOSS (score_loss_pruning.cc: each tree's summed share of the document scores, one ordered FP64 chain per tree on
+the device) — all pinned bit for bit against the unmodified reference — and RANDOM (random_pruning.cc; the reference
+seeds rand() from the wall clock, here from ``seed``).  RANDOM_ADV is not provided (its OpenMP loop shares one rand()
+stream and one never-reset candidate set between threads: the result is not a function of its inputs).
+The matrix is what ``api.Scorer.partial_scores`` returns for an ensemble (driver.cc:411-446).
 """
 from __future__ import annotations
 
@@ -41,6 +46,7 @@ class LineSearch:
         self.max_failed_vali = int(max_failed_vali)
         self.adaptive = bool(adaptive)
         self.last_only = int(last_only)
+        self.seed = int(seed)
         self.weights = None          # best_weights_
         self.history = []            # (iteration, training metric, validation metric or None, gain, window)
 
@@ -232,20 +238,22 @@ def std_sort(a, less):
     return a
 
 
-PRUNING_METHODS = ("LAST", "SKIP", "LOW_WEIGHTS", "QUALITY_LOSS")
-_PRE_PRUNING_LS = {"LAST": False, "SKIP": False, "LOW_WEIGHTS": True, "QUALITY_LOSS": True}
+PRUNING_METHODS = ("LAST", "SKIP", "LOW_WEIGHTS", "QUALITY_LOSS", "QUALITY_LOSS_ADV", "SCORE_LOSS", "RANDOM")
+_PRE_PRUNING_LS = {"LAST": False, "SKIP": False, "LOW_WEIGHTS": True, "QUALITY_LOSS": True, "QUALITY_LOSS_ADV": True,
+                   "SCORE_LOSS": True, "RANDOM": False}
 
 
 class Cleaver:
     """Ensemble pruning + re-weighting (cleaver.cc).  pruning_rate < 1: a fraction of the trees, else a count."""
 
-    def __init__(self, pruning_rate, method="QUALITY_LOSS", line_search: LineSearch | None = None, last_only=0):
+    def __init__(self, pruning_rate, method="QUALITY_LOSS", line_search: LineSearch | None = None, last_only=0, seed=0):
         if method not in PRUNING_METHODS:
             raise ValueError("pruning method %s is not supported (supported: %s)" % (method, ", ".join(PRUNING_METHODS)))
         self.pruning_rate = float(pruning_rate)
         self.method = method
         self.line_search = line_search
         self.last_only = int(last_only)
+        self.seed = int(seed)
         self.weights = None
         self.pruned = set()
 
@@ -262,8 +270,31 @@ class Cleaver:
         if self.method == "LOW_WEIGHTS":
             idx = std_sort(list(range(start_last, T)), lambda a, b: weights[a] < weights[b])
             return set(idx[:to_prune])
+        if self.method == "RANDOM":   # random_pruning.cc:47-55 (srand(time(NULL)) there)
+            libc = C.CDLL("libc.so.6")
+            libc.srand(C.c_uint(self.seed & 0xffffffff))
+            pruned = set()
+            while len(pruned) < to_prune:
+                pruned.add(libc.rand() % last + start_last)
+            return pruned
+        if self.method == "SCORE_LOSS":   # score_loss_pruning.cc:58-77: the trees with the smallest summed share go
+            loss = dev.score_loss(weights)
+            idx = std_sort(list(range(start_last, T)), lambda a, b: loss[a] < loss[b])
+            return set(idx[:to_prune])
+        if self.method == "QUALITY_LOSS_ADV":
+            # quality_loss_adv_pruning.cc:58-93: one tree per step — the one whose removal leaves the best metric
+            # (std::max_element: the first maximum) — on running scores that lose the pruned column in place
+            w, pruned = np.array(weights, np.float64), set()
+            for _ in range(to_prune):
+                cand = [f for f in range(start_last, T) if f not in pruned]
+                metrics = dev.drop_points(w, cand)
+                f_prune = cand[int(np.argmax(metrics))]   # (np.argmax: first maximum; pruned trees hold `lowest` there)
+                pruned.add(f_prune)
+                dev.drop_column(w, f_prune)
+                w[f_prune] = 0.0
+            return pruned
         # QUALITY_LOSS: the metric of the ensemble without tree f, for every f; the trees whose removal hurts least go
-        metrics = [dev.feature_points(weights, f, [0.0])[0] for f in range(start_last, T)]
+        metrics = dev.drop_points(weights, list(range(start_last, T)))
         idx = std_sort(list(range(start_last, T)), lambda a, b: metrics[a - start_last] > metrics[b - start_last])
         return set(idx[:to_prune])
 

@@ -83,7 +83,7 @@ def test_device_metrics_match_the_oracle():
 
 @pytest.mark.skipif(not pyref.available(), reason="oracle/_ref is not built")
 @pytest.mark.parametrize("with_ls", [True, False])
-@pytest.mark.parametrize("method", ["LAST", "SKIP", "LOW_WEIGHTS", "QUALITY_LOSS"])
+@pytest.mark.parametrize("method", ["LAST", "SKIP", "LOW_WEIGHTS", "QUALITY_LOSS", "QUALITY_LOSS_ADV", "SCORE_LOSS"])
 def test_cleaver_equals_the_reference(method, with_ls):
     """Cleaver::optimize (cleaver.cc:166-412) on the partial scores of a trained ensemble: the pruned set and the
     re-learned weights equal the unmodified reference's bit for bit, with and without the line search."""
@@ -103,3 +103,22 @@ def test_cleaver_equals_the_reference(method, with_ls):
         assert pruned == set(range(14, 20))
     # the optimised ensemble scores what the oracle says
     assert abs(cl.metric_after - po.ndcg_dataset(l, part.astype(np.float64) @ w, off, 10)) <= 1e-9
+
+
+@pytest.mark.gpu
+def test_cleaver_random_pruning_is_seeded():
+    """RandomPruning (random_pruning.cc:47-55) draws trees with rand() % last + start until enough distinct ones are
+    hit; the reference seeds from the wall clock, here `seed` makes the draw reproducible."""
+    x, l, off = common.dataset(n=2000, f=8, q=20, seed=3)
+    rng = np.random.default_rng(1)
+    part = rng.normal(size=(len(l), 15)).astype(np.float32)
+    w0 = np.full(15, 0.1)
+    a = Cleaver(5, "RANDOM", None, seed=7).optimize(part, l, off, w0)
+    b = Cleaver(5, "RANDOM", None, seed=7).optimize(part, l, off, w0)
+    c = Cleaver(5, "RANDOM", None, seed=8).optimize(part, l, off, w0)
+    assert len(a[1]) == 5 and a[1] == b[1] and np.array_equal(a[0], b[0])
+    assert all(a[0][f] == 0 for f in a[1]) and np.count_nonzero(a[0]) == 10
+    assert a[1] != c[1]
+    # last_only: only the last trees are candidates
+    d = Cleaver(3, "RANDOM", None, last_only=6, seed=1).optimize(part, l, off, w0)
+    assert len(d[1]) == 3 and min(d[1]) >= 9
