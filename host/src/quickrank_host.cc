@@ -1801,6 +1801,11 @@ static bool recv_all(int fd, unsigned char *p, size_t n) {
   return true;
 }
 
+namespace {
+const char kRendezvousMagic[9] = "QRB2RDV1";
+struct RendezvousHello { char magic[8]; int32_t rank, world; };
+}  // namespace
+
 bool exchange_bytes(unsigned char *id, size_t nbytes, const Sharding &s, int timeout_s) {
   if (s.world <= 1) return true;
   sockaddr_in a;
@@ -1812,19 +1817,46 @@ bool exchange_bytes(unsigned char *id, size_t nbytes, const Sharding &s, int tim
     if (ls < 0) { perror("socket"); return false; }
     int one = 1;
     setsockopt(ls, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
-    a.sin_addr.s_addr = htonl(INADDR_ANY);
-    if (::bind(ls, (sockaddr *) &a, sizeof(a)) != 0 || ::listen(ls, s.world) != 0) {
+    // listen on the rendezvous address itself (127.0.0.1 when quicklearn forked the ranks), not on every interface
+    if (inet_pton(AF_INET, s.addr.c_str(), &a.sin_addr) != 1) a.sin_addr.s_addr = htonl(INADDR_ANY);
+    if (::bind(ls, (sockaddr *) &a, sizeof(a)) != 0) {
+      a.sin_addr.s_addr = htonl(INADDR_ANY);   // (an address of another interface of this host: fall back)
+      if (::bind(ls, (sockaddr *) &a, sizeof(a)) != 0) {
+        std::cerr << "!!! rank 0 cannot bind port " << s.port << ": " << strerror(errno) << std::endl;
+        ::close(ls);
+        return false;
+      }
+    }
+    if (::listen(ls, s.world + 8) != 0) {
       std::cerr << "!!! rank 0 cannot listen on port " << s.port << ": " << strerror(errno) << std::endl;
       ::close(ls);
       return false;
     }
-    timeval tv{timeout_s, 0};
+    timeval tv{1, 0};
     setsockopt(ls, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
+    // a peer introduces itself (magic, rank, world); anything else that connects — a port scanner, another job that
+    // guessed the same port — is dropped without using up one of the world-1 hand-offs
+    std::vector<char> served((size_t) s.world, 0);
+    int remaining = s.world - 1;
+    const auto t0 = std::chrono::steady_clock::now();
     bool ok = true;
-    for (int k = 1; k < s.world && ok; ++k) {
+    while (remaining > 0) {
+      if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s) {
+        std::cerr << "!!! rank 0: " << remaining << " peer(s) did not connect within " << timeout_s << " s" << std::endl;
+        ok = false;
+        break;
+      }
       const int fd = ::accept(ls, nullptr, nullptr);
-      if (fd < 0) { std::cerr << "!!! rank 0: a peer did not connect within " << timeout_s << " s" << std::endl; ok = false; break; }
-      ok = send_all(fd, id, nbytes);
+      if (fd < 0) continue;   // (accept timed out after 1 s: look at the clock again)
+      timeval ptv{5, 0};
+      setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &ptv, sizeof(ptv));
+      RendezvousHello h{};
+      const bool hello = recv_all(fd, (unsigned char *) &h, sizeof(h)) && std::memcmp(h.magic, kRendezvousMagic, 8) == 0 &&
+                         h.world == s.world && h.rank >= 1 && h.rank < s.world && !served[(size_t) h.rank];
+      if (hello && send_all(fd, id, nbytes)) {
+        served[(size_t) h.rank] = 1;
+        --remaining;
+      }
       ::close(fd);
     }
     ::close(ls);
@@ -1849,7 +1881,11 @@ bool exchange_bytes(unsigned char *id, size_t nbytes, const Sharding &s, int tim
     if (::connect(fd, (sockaddr *) &a, sizeof(a)) == 0) {
       timeval tv{timeout_s, 0};
       setsockopt(fd, SOL_SOCKET, SO_RCVTIMEO, &tv, sizeof(tv));
-      const bool ok = recv_all(fd, id, nbytes);
+      RendezvousHello h{};
+      std::memcpy(h.magic, kRendezvousMagic, 8);
+      h.rank = s.rank;
+      h.world = s.world;
+      const bool ok = send_all(fd, (const unsigned char *) &h, sizeof(h)) && recv_all(fd, id, nbytes);
       ::close(fd);
       if (!ok) std::cerr << "!!! rank " << s.rank << ": the communicator id did not arrive" << std::endl;
       return ok;

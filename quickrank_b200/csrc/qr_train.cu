@@ -532,7 +532,19 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
   }
   c->maxlen = (maxlen + 3u) & ~3u;
   std::vector<double> gain(N), idcg(Q), lg(c->maxlen + 1), invlg(c->maxlen + 1);
-  for (size_t i = 0; i < N; ++i) gain[i] = std::pow(2.0, (double) labels[i]);              // dcg.cc:37
+  // pow(2, label) (dcg.cc:37) through a memo of the few distinct label values: the same glibc results without a
+  // pow() call per document
+  float memo_label[8];
+  double memo_gain[8];
+  int memo_n = 0;
+  auto gain_of = [&](float label) {
+    for (int k = 0; k < memo_n; ++k)
+      if (memo_label[k] == label) return memo_gain[k];
+    const double g = std::pow(2.0, (double) label);
+    if (memo_n < 8) { memo_label[memo_n] = label; memo_gain[memo_n] = g; ++memo_n; }
+    return g;
+  };
+  for (size_t i = 0; i < N; ++i) gain[i] = gain_of(labels[i]);
   for (uint32_t i = 0; i <= c->maxlen; ++i) {
     lg[i] = std::log2((double) ((float) i + 2.0f));                                          // dcg.cc:37
     invlg[i] = 1.0 / std::log2((double) (i + 2));                                            // ndcg.cc:79
@@ -544,7 +556,7 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
       std::sort(tmp.begin(), tmp.end(), std::greater<int>());
       const size_t size = std::min(c->cutoff, tmp.size());
       double dcg = 0.0;
-      for (size_t i = 0; i < size; ++i) dcg += (std::pow(2.0, (double) tmp[i]) - 1.0) / lg[i];
+      for (size_t i = 0; i < size; ++i) dcg += (gain_of(tmp[i]) - 1.0) / lg[i];
       idcg[q] = dcg;
     }
   }

@@ -46,7 +46,6 @@ class LineSearch:
         self.max_failed_vali = int(max_failed_vali)
         self.adaptive = bool(adaptive)
         self.last_only = int(last_only)
-        self.seed = int(seed)
         self.weights = None          # best_weights_
         self.history = []            # (iteration, training metric, validation metric or None, gain, window)
 

@@ -37,6 +37,40 @@ def test_communicator_id_rendezvous(addr):
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr + out.stdout
 
 
+def test_rendezvous_ignores_strangers():
+    """Connections that do not introduce themselves (a port scanner, another job on the same port) do not use up one
+    of the world-1 hand-offs and do not receive the communicator id."""
+    import socket
+    import threading
+    import time
+    port = 23000 + os.getpid() % 20000
+    got = []
+
+    def stranger():
+        deadline = time.time() + 10
+        while time.time() < deadline:
+            try:
+                with socket.create_connection(("127.0.0.1", port), timeout=1) as c:
+                    c.sendall(b"GET / HTTP/1.0\r\n\r\n")
+                    c.settimeout(2)
+                    try:
+                        got.append(c.recv(256))
+                    except OSError:
+                        got.append(b"")
+                return
+            except OSError:
+                time.sleep(0.01)
+
+    threads = [threading.Thread(target=stranger) for _ in range(3)]
+    for t in threads:
+        t.start()
+    out = subprocess.run([SC, "rendezvous", "3", str(port), "127.0.0.1"], capture_output=True, text=True, timeout=120)
+    for t in threads:
+        t.join()
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr + out.stdout
+    assert all(len(g) == 0 for g in got), got
+
+
 @pytest.mark.gpu
 def test_quicklearn_on_two_gpus_grows_the_single_gpu_model(tmp_path):
     from quickrank_b200 import api, modelxml
