@@ -3,6 +3,7 @@
 // input (text): Q N, then Q+1 query offsets, then N lines "label score".  srand(0) before the draw.
 // output: the size of the sample, then the N ids of the permuted list.  tests/test_sampled_trainers.py compares it
 // with the unmodified reference's function on the same input.
+#include <chrono>
 #include <cstdlib>
 #include <iostream>
 #include <sstream>
@@ -33,8 +34,11 @@ int main(int argc, char **argv) {
   std::ostringstream log;
   std::streambuf *keep = std::cout.rdbuf(log.rdbuf());
   srand(0);
+  const auto t0 = std::chrono::steady_clock::now();
   const size_t n = algo.sampling_query_level(ds, scores, npos, ids, strtof(argv[5], nullptr));
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   std::cout.rdbuf(keep);
+  std::cerr << "draw over " << N << " documents: " << ms << " ms" << std::endl;
   std::cout << n << "\n";
   for (size_t i = 0; i < N; ++i) std::cout << ids[i] << "\n";
   std::cerr << log.str();

@@ -29,7 +29,9 @@
 #include <iostream>
 #include <limits>
 #include <numeric>
+#include <atomic>
 #include <random>
+#include <thread>
 
 namespace quickrank {
 namespace learning {
@@ -70,16 +72,20 @@ void SampledLambdaMart::build_sample_context(const data::Dataset &dataset, const
     }
     if (src.size() > qoff.back()) qoff.push_back(src.size());
   }
-  if (sample_ctx_) qr_ctx_destroy(sample_ctx_);
-  sample_ctx_ = nullptr;
   if (src.empty()) {
     std::cerr << "!!! The document sample is empty." << std::endl;
     exit(EXIT_FAILURE);
   }
-  // (no feature rows: the sample's bins are gathered on the device from the full context's)
-  if (qr_ctx_create_sample(ctx_, nullptr, src.size(), F, labels.data(), qoff.data(), qoff.size() - 1, src.data(),
-                           key.data(), &sample_ctx_) != QR_OK)
-    die("Impossible to initialise the GPU context of the document sample");
+  // no feature rows: the sample's bins are gathered on the device from the full context's; the first call creates a
+  // context sized for the whole training set, later draws refill it in place
+  if (sample_ctx_ == nullptr) {
+    if (qr_ctx_create_sample(ctx_, nullptr, src.size(), F, labels.data(), qoff.data(), qoff.size() - 1, src.data(),
+                             key.data(), &sample_ctx_) != QR_OK)
+      die("Impossible to initialise the GPU context of the document sample");
+  } else if (qr_sample_redraw(sample_ctx_, ctx_, src.size(), labels.data(), qoff.data(), qoff.size() - 1, src.data(),
+                              key.data()) != QR_OK) {
+    die("Impossible to load the new document sample");
+  }
 }
 
 void SampledLambdaMart::learn(std::shared_ptr<data::Dataset> training_dataset,
@@ -315,47 +321,72 @@ size_t LambdaMartSelective::sampling_query_level(const data::Dataset &dataset, c
             << " - Adapt Factor: " << adapt_factor << std::setprecision(4) << std::endl;
 
   const bool by_ratio = negative_strategy == "RATIO", by_mul = negative_strategy == "MUL";
+  const size_t Q = dataset.num_queries();
+  // Phase 1, queries in parallel: each query's quotas and its final order.  A query's sorts read and write its own
+  // segment of `ids` only, and phase 2 of an earlier query never writes behind that query's end, so doing all the
+  // sorts first leaves every segment exactly as the reference's interleaved loop finds it.
+  struct Quota { size_t n_top, n_random; };
+  std::vector<Quota> quotas(Q);
+  std::atomic<size_t> bad_query(Q);
+  auto order_queries = [&](size_t q0, size_t q1) {
+    for (size_t q = q0; q < q1; ++q) {
+      const size_t begin = dataset.offset(q), end = dataset.offset(q + 1), len = end - begin;
+      const size_t npos = npositives[q], nneg = len - npos;
+      size_t n_top = 0, n_random = 0;
+      if (by_ratio) {
+        n_top = quota(rank_factor, nneg);
+        n_random = quota(random_factor, nneg);
+      } else if (by_mul) {
+        n_top = std::min(quota(rank_factor, npos), nneg);
+        n_random = std::min(quota(random_factor, npos), nneg);
+      } else if (npos > 0) {   // POS: quotas relative to the negatives ranked above the last positive
+        std::sort(ids.begin() + begin, ids.begin() + end, [score](size_t a, size_t b) { return score[a] > score[b]; });
+        size_t last_positive = 0;
+        for (size_t i = 0; i < len; ++i)
+          if (dataset.getLabel(ids[begin + i]) > 0) last_positive = i;
+        const size_t above = last_positive - npos + 1;
+        n_top = std::min(quota(rank_factor, above), nneg);
+        n_random = std::min(quota(random_factor, above), nneg - n_top);
+      }
+      if (n_top > nneg) {   // (the reference's unsigned `n_neg_query - n_top_neg` wraps around here and it dies in a vector constructor)
+        size_t seen = bad_query.load();
+        while (q < seen && !bad_query.compare_exchange_weak(seen, q)) {}
+        n_top = nneg;
+      }
+      if (n_top + n_random > nneg) n_random = nneg - n_top;
+      quotas[q] = Quota{n_top, n_random};
+      // positives first, then negatives, each group by decreasing score (the reference's comparator, verbatim in
+      // meaning: a positive precedes a zero label or a lower score; a non-positive precedes only a zero label of
+      // lower score)
+      std::sort(ids.begin() + begin, ids.begin() + end, [score, &dataset](size_t a, size_t b) {
+        const bool higher = score[a] > score[b];
+        const bool b_zero = dataset.getLabel(b) == 0;
+        return dataset.getLabel(a) > 0 ? (b_zero || higher) : (b_zero && higher);
+      });
+    }
+  };
+  const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t) std::thread::hardware_concurrency(), (size_t) 32,
+                                                               dataset.num_instances() / 20000 + 1}));
+  if (nthreads == 1) {
+    order_queries(0, Q);
+  } else {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nthreads; ++t) pool.emplace_back(order_queries, Q * t / nthreads, Q * (t + 1) / nthreads);
+    for (auto &t : pool) t.join();
+  }
+  if (bad_query.load() < Q) {
+    std::cerr << "!!! " << name() << ": the rank sampling factor selects more negatives than query " << bad_query.load()
+              << " has." << std::endl;
+    exit(EXIT_FAILURE);
+  }
+  // Phase 2, in query order: the selected documents move to the front, the random negatives follow rand()'s stream
   size_t front = 0, picked_top = 0, picked_random = 0, positives = 0;
-  for (size_t q = 0; q < dataset.num_queries(); ++q) {
-    const size_t begin = dataset.offset(q), end = dataset.offset(q + 1), len = end - begin;
-    const size_t npos = npositives[q], nneg = len - npos;
-    size_t n_top = 0, n_random = 0;
-    if (by_ratio) {
-      n_top = quota(rank_factor, nneg);
-      n_random = quota(random_factor, nneg);
-    } else if (by_mul) {
-      n_top = std::min(quota(rank_factor, npos), nneg);
-      n_random = std::min(quota(random_factor, npos), nneg);
-    } else if (npos > 0) {   // POS: quotas relative to the negatives ranked above the last positive
-      std::sort(ids.begin() + begin, ids.begin() + end, [score](size_t a, size_t b) { return score[a] > score[b]; });
-      size_t last_positive = 0;
-      for (size_t i = 0; i < len; ++i)
-        if (dataset.getLabel(ids[begin + i]) > 0) last_positive = i;
-      const size_t above = last_positive - npos + 1;
-      n_top = std::min(quota(rank_factor, above), nneg);
-      n_random = std::min(quota(random_factor, above), nneg - n_top);
-    }
-    if (n_top > nneg) {   // (the reference's unsigned `n_neg_query - n_top_neg` wraps around here and it dies in a vector constructor)
-      std::cerr << "!!! " << name() << ": the rank sampling factor selects more negatives than query " << q << " has." << std::endl;
-      exit(EXIT_FAILURE);
-    }
-    size_t n_neg = n_top + n_random;
-    if (n_neg > nneg) {
-      n_neg = nneg;
-      n_random = nneg - n_top;
-    }
+  for (size_t q = 0; q < Q; ++q) {
+    const size_t begin = dataset.offset(q), len = dataset.offset(q + 1) - begin;
+    const size_t npos = npositives[q], n_top = quotas[q].n_top, n_random = quotas[q].n_random;
     picked_top += n_top;
     picked_random += n_random;
     positives += npos;
-
-    // positives first, then negatives, each group by decreasing score (the reference's comparator, verbatim in
-    // meaning: a positive precedes a zero label or a lower score; a non-positive precedes only a zero label of
-    // lower score)
-    std::sort(ids.begin() + begin, ids.begin() + end, [score, &dataset](size_t a, size_t b) {
-      const bool higher = score[a] > score[b];
-      const bool b_zero = dataset.getLabel(b) == 0;
-      return dataset.getLabel(a) > 0 ? (b_zero || higher) : (b_zero && higher);
-    });
     const size_t head = npos + n_top;
     if (front > 0)
       for (size_t j = 0; j < head; ++j) std::swap(ids[front + j], ids[begin + j]);
@@ -365,7 +396,7 @@ size_t LambdaMartSelective::sampling_query_level(const data::Dataset &dataset, c
       rand_shuffle(rest);
       for (size_t j = 0; j < n_random; ++j) std::swap(ids[front + head + j], ids[begin + rest[j]]);
     }
-    front += npos + n_neg;
+    front += head + n_random;
   }
   std::cout << std::setprecision(0) << "N. Positives: " << positives << " - Neg sel rank: " << picked_top
             << " - Neg sel random: " << picked_random << std::setprecision(4) << std::endl;

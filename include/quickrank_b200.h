@@ -129,6 +129,12 @@ int qr_ctx_create_eval(qr_ctx *train, const float *feat_rowmajor, size_t N, size
 int qr_ctx_create_sample(qr_ctx *full, const float *feat_rowmajor, size_t N, size_t F, const float *labels,
                          const uint64_t *qoffsets, size_t Q, const uint32_t *src_doc, const uint32_t *key_doc,
                          qr_ctx **out);
+/* A new draw into an existing sample context (created with feat_rowmajor == NULL: it is sized for every document of
+ * `full`): same arguments as above, nothing is allocated or freed — the bins of the new documents are gathered, the
+ * per-query tables and per-bin counts rebuilt, the state of the previous sample (scores, last tree) dropped.  What
+ * LambdaMartSelective::learn does every `sampling_iterations` trees (lambdamartselective.cc:170-192). */
+int qr_sample_redraw(qr_ctx *sample, qr_ctx *full, size_t N, const float *labels, const uint64_t *qoffsets, size_t Q,
+                     const uint32_t *src_doc, const uint32_t *key_doc);
 /* Copies the current scores of `full` into the sample (own scores and ranking keys). */
 int qr_sample_pull_scores(qr_ctx *sample, qr_ctx *full);
 /* Replaces Mart::clear (mart.cc:178-206). */

@@ -72,6 +72,7 @@ def lib():
         L.qr_ctx_create_eval.argtypes = [vp, fp, sz, sz, fp, u64p, sz, C.POINTER(vp)]
         L.qr_ctx_create_sample.argtypes = [vp, fp, sz, sz, fp, u64p, sz, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                            C.POINTER(vp)]
+        L.qr_sample_redraw.argtypes = [vp, vp, sz, fp, u64p, sz, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.qr_sample_pull_scores.argtypes = [vp, vp]
         L.qr_ctx_destroy.argtypes = [vp]
         L.qr_get_thresholds.argtypes = [vp, sz, C.POINTER(fp), C.POINTER(sz)]
@@ -223,29 +224,41 @@ class Trainer:
                                         _p(ev.qoff, C.c_uint64), ev.Q, C.byref(ev.h)))
         return ev
 
+    def _sample_layout(self, doc_ids, rank_by_position):
+        doc_ids = np.ascontiguousarray(doc_ids, np.uint32)
+        assert np.all(np.diff(doc_ids.astype(np.int64)) > 0), "sampled documents must be ascending"
+        q_of = np.searchsorted(self.qoff, doc_ids, side="right") - 1
+        counts = np.bincount(q_of, minlength=self.Q)
+        labels = np.ascontiguousarray(self.labels[doc_ids], np.float32)
+        qoff = np.concatenate([[0], np.cumsum(counts[counts > 0])]).astype(np.uint64)
+        key = np.ascontiguousarray(doc_ids - self.qoff[q_of].astype(np.uint32), np.uint32) if rank_by_position else None
+        return doc_ids, labels, qoff, key
+
     def sample_context(self, x, doc_ids, rank_by_position=True, gather=True):
         """The documents `doc_ids` (ascending; whole set `x` row-major) as a training context of their own, binned with
         this trainer's thresholds (qr_ctx_create_sample): what LambdaMartSelective / StochasticNegative fit a tree on.
         rank_by_position: the reference's ranking key (lambdamart.cc:94: the score of the document whose index is this
         one's position inside its query); False: the document's own score.  gather: take the bins from this context on
         the device (x is not read) instead of uploading and binning the sampled rows."""
-        doc_ids = np.ascontiguousarray(doc_ids, np.uint32)
-        assert np.all(np.diff(doc_ids.astype(np.int64)) > 0), "sampled documents must be ascending"
-        q_of = np.searchsorted(self.qoff, doc_ids, side="right") - 1
-        counts = np.bincount(q_of, minlength=self.Q)
+        doc_ids, labels, qoff, key = self._sample_layout(doc_ids, rank_by_position)
         sm = Trainer.__new__(Trainer)
-        sm.labels = np.ascontiguousarray(self.labels[doc_ids], np.float32)
-        sm.qoff = np.concatenate([[0], np.cumsum(counts[counts > 0])]).astype(np.uint64)
+        sm.labels, sm.qoff = labels, qoff
         rows = None if gather else np.ascontiguousarray(np.asarray(x, np.float32)[doc_ids])
         sm.N, sm.F = len(doc_ids), self.F
         sm.Q = len(sm.qoff) - 1
         sm.params, sm.shrinkage, sm.max_nodes = self.params, self.shrinkage, self.max_nodes
-        key = np.ascontiguousarray(doc_ids - self.qoff[q_of].astype(np.uint32), np.uint32) if rank_by_position else None
         sm.h = C.c_void_p()
-        _check(lib().qr_ctx_create_sample(self.h, _p(rows, C.c_float) if rows is not None else None, sm.N, sm.F, _p(sm.labels, C.c_float),
-                                          _p(sm.qoff, C.c_uint64), sm.Q, _p(doc_ids, C.c_uint32),
+        _check(lib().qr_ctx_create_sample(self.h, _p(rows, C.c_float) if rows is not None else None, sm.N, sm.F,
+                                          _p(sm.labels, C.c_float), _p(sm.qoff, C.c_uint64), sm.Q, _p(doc_ids, C.c_uint32),
                                           _p(key, C.c_uint32) if key is not None else None, C.byref(sm.h)))
         return sm
+
+    def redraw(self, full, doc_ids, rank_by_position=True):
+        """(sample context created with gather=True) a new draw in place: qr_sample_redraw"""
+        doc_ids, labels, qoff, key = full._sample_layout(doc_ids, rank_by_position)
+        _check(lib().qr_sample_redraw(self.h, full.h, len(doc_ids), _p(labels, C.c_float), _p(qoff, C.c_uint64), len(qoff) - 1,
+                                      _p(doc_ids, C.c_uint32), _p(key, C.c_uint32) if key is not None else None))
+        self.labels, self.qoff, self.N, self.Q = labels, qoff, len(doc_ids), len(qoff) - 1
 
     def pull_scores(self, full):
         """(sample context) copies the current scores of `full` (qr_sample_pull_scores)"""

@@ -123,6 +123,10 @@ struct qr_ctx {
   uint32_t *d_src_doc = nullptr, *d_key_doc = nullptr;   // [N]
   double *d_rankkey = nullptr;                           // [N]
   size_t sample_of_N = 0;                                // documents of the sampled context (0: not a sample)
+  // buffers that scale with the documents / queries / longest query are allocated for these counts (>= N, Q, maxlen):
+  // a sample context is sized for the whole sampled set, so that qr_sample_redraw can refill it in place
+  size_t cap_N = 0, cap_Q = 0;
+  uint32_t cap_maxlen = 0;
   double *d_qndcg = nullptr;      // [Q]
   double *d_metric = nullptr;     // [1]
   double *d_vec_qndcg = nullptr, *d_vec_metric = nullptr;   // evaluate_vectors: [vec_cap][Q] per-query values, [vec_cap] means

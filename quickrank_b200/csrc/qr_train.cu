@@ -397,6 +397,17 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
 
 // The bins of a document sample taken from the sampled context on the device: same thresholds, same bin width and
 // panel layout, rows src[0..N) of its panels — no feature values cross the bus and nothing is binned again.
+static int gather_sample_bins(qr_ctx *c, const qr_ctx *from, const uint32_t *src_host) {
+  const size_t N = c->N;
+  QR_CUDA(cudaMemcpyAsync(c->d_src_doc, src_host, N * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  QR_CUDA(cudaStreamSynchronize(from->stream));
+  sample_gather_panels_kernel<<<dim3((unsigned) ((N + 255) / 256), c->npanels), 256, 0, c->stream>>>(
+      from->d_panels, from->N, c->d_src_doc, N, c->npanels, c->d_panels, c->d_rows);
+  QR_CUDA(cudaGetLastError());
+  QR_CUDA(cudaStreamSynchronize(c->stream));   // (src_host is pageable memory of the caller)
+  return QR_OK;
+}
+
 static int gather_binning(qr_ctx *c, const qr_ctx *from, const uint32_t *src_host) {
   const size_t N = c->N, F = c->F;
   c->thr = from->thr;
@@ -408,17 +419,12 @@ static int gather_binning(qr_ctx *c, const qr_ctx *from, const uint32_t *src_hos
     set_error("internal: the sample's bin layout differs from the sampled context's");
     return QR_ECUDA;
   }
-  QR_TRY(dev_alloc(&c->d_src_doc, N));
-  QR_CUDA(cudaMemcpyAsync(c->d_src_doc, src_host, N * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-  QR_TRY(dev_alloc(&c->d_panels, (size_t) c->npanels * N));
+  const size_t cap = std::max(c->cap_N, N);
+  QR_TRY(dev_alloc(&c->d_src_doc, cap));
+  QR_TRY(dev_alloc(&c->d_panels, (size_t) c->npanels * cap));
   if (!c->exact && c->npanels > 1 && (getenv("QR_ROW_COPY") == nullptr || atoi(getenv("QR_ROW_COPY")) != 0))
-    QR_TRY(dev_alloc(&c->d_rows, (size_t) c->npanels * N));
-  QR_CUDA(cudaStreamSynchronize(from->stream));
-  sample_gather_panels_kernel<<<dim3((unsigned) ((N + 255) / 256), c->npanels), 256, 0, c->stream>>>(
-      from->d_panels, from->N, c->d_src_doc, N, c->npanels, c->d_panels, c->d_rows);
-  QR_CUDA(cudaGetLastError());
-  QR_CUDA(cudaStreamSynchronize(c->stream));
-  return QR_OK;
+    QR_TRY(dev_alloc(&c->d_rows, (size_t) c->npanels * cap));
+  return gather_sample_bins(c, from, src_host);
 }
 
 static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t F, const float *labels,
@@ -489,8 +495,9 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
     c->N_local_max = (size_t) nmax;
   }
 
-  if (gather_src) {   // a document sample cut from the bins of `thr_from`
+  if (gather_src) {   // a document sample cut from the bins of `thr_from`, sized for all of its documents
     c->eval_only = false;
+    c->cap_N = thr_from->N; c->cap_Q = thr_from->Q; c->cap_maxlen = thr_from->maxlen;
     QR_TRY(gather_binning(c, thr_from, gather_src));
     clk.lap("bins gathered from the sampled context");
     return ctx_create_state(c, labels, qoffsets, params, clk);
@@ -519,19 +526,12 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
   return ctx_create_state(c, labels, qoffsets, params, clk);
 }
 
-// second half of context creation: per-query tables, state arrays, histogram pool, kernel attributes, peers
-static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoffsets, const qr_params *params, InitClock &clk) {
-  const size_t N = c->N, F = c->F, Q = c->Q;
-  // labels, gains, query offsets, ideal DCG per query, discount tables (host glibc, once)
-  std::vector<uint32_t> qoff(Q + 1);
-  uint32_t maxlen = 0;
-  for (size_t q = 0; q <= Q; ++q) {
-    if (q && qoffsets[q] < qoffsets[q - 1]) { set_error("query offsets must be non-decreasing"); return QR_EINVAL; }
-    qoff[q] = (uint32_t) qoffsets[q];
-    if (q) maxlen = std::max<uint32_t>(maxlen, qoff[q] - qoff[q - 1]);
-  }
-  c->maxlen = (maxlen + 3u) & ~3u;
-  std::vector<double> gain(N), idcg(Q), lg(c->maxlen + 1), invlg(c->maxlen + 1);
+// Contents of the per-document / per-query tables for the context's current N and Q: labels, gains, query offsets,
+// ideal DCG per query (host glibc), zeroed state arrays (mart.cc:121-122, lambdamart.cc:38).  The buffers exist and hold
+// at least cap_N / cap_Q entries.  Used by context creation and by qr_sample_redraw.
+static int fill_query_tables(qr_ctx *c, const float *labels, const std::vector<uint32_t> &qoff, const std::vector<double> &lg) {
+  const size_t N = c->N, Q = c->Q;
+  std::vector<double> gain(N), idcg(Q);
   // pow(2, label) (dcg.cc:37) through a memo of the few distinct label values: the same glibc results without a
   // pow() call per document
   float memo_label[8];
@@ -545,10 +545,6 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
     return g;
   };
   for (size_t i = 0; i < N; ++i) gain[i] = gain_of(labels[i]);
-  for (uint32_t i = 0; i <= c->maxlen; ++i) {
-    lg[i] = std::log2((double) ((float) i + 2.0f));                                          // dcg.cc:37
-    invlg[i] = 1.0 / std::log2((double) (i + 2));                                            // ndcg.cc:79
-  }
   {
     std::vector<float> tmp;
     for (size_t q = 0; q < Q; ++q) {                                                         // ndcg.cc:35-47
@@ -560,21 +556,63 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
       idcg[q] = dcg;
     }
   }
-  clk.lap("host gain/idcg tables");
-  QR_TRY(dev_alloc(&c->d_labels, N));
-  QR_TRY(dev_alloc(&c->d_gain, N));
-  QR_TRY(dev_alloc(&c->d_qoff, Q + 1));
-  QR_TRY(dev_alloc(&c->d_idcg, Q));
-  QR_TRY(dev_alloc(&c->d_lg, c->maxlen + 1));
-  QR_TRY(dev_alloc(&c->d_invlg, c->maxlen + 1));
   QR_CUDA(cudaMemcpy(c->d_labels, labels, N * sizeof(float), cudaMemcpyHostToDevice));
   QR_CUDA(cudaMemcpy(c->d_gain, gain.data(), N * sizeof(double), cudaMemcpyHostToDevice));
   QR_CUDA(cudaMemcpy(c->d_qoff, qoff.data(), (Q + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice));
   QR_CUDA(cudaMemcpy(c->d_idcg, idcg.data(), Q * sizeof(double), cudaMemcpyHostToDevice));
-  QR_CUDA(cudaMemcpy(c->d_lg, lg.data(), (c->maxlen + 1) * sizeof(double), cudaMemcpyHostToDevice));
-  QR_CUDA(cudaMemcpy(c->d_invlg, invlg.data(), (c->maxlen + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  QR_CUDA(cudaMemset(c->d_scores, 0, N * sizeof(double)));
+  QR_CUDA(cudaMemset(c->d_lambda, 0, N * sizeof(double)));
+  QR_CUDA(cudaMemset(c->d_weight, 0, N * sizeof(double)));
+  QR_CUDA(cudaMemset(c->d_leaf_of_doc, 0, N * sizeof(uint32_t)));
+  QR_CUDA(cudaMemset(c->d_qexp, 0, 2 * sizeof(int)));
+  return QR_OK;
+}
 
-  // state arrays (mart.cc:121-122, lambdamart.cc:38: zero-initialised)
+// query offsets as 32-bit device offsets, and the longest query
+static int check_query_offsets(const uint64_t *qoffsets, size_t Q, std::vector<uint32_t> &qoff, uint32_t *maxlen_out) {
+  qoff.resize(Q + 1);
+  uint32_t maxlen = 0;
+  for (size_t q = 0; q <= Q; ++q) {
+    if (q && qoffsets[q] < qoffsets[q - 1]) { set_error("query offsets must be non-decreasing"); return QR_EINVAL; }
+    qoff[q] = (uint32_t) qoffsets[q];
+    if (q) maxlen = std::max<uint32_t>(maxlen, qoff[q] - qoff[q - 1]);
+  }
+  *maxlen_out = maxlen;
+  return QR_OK;
+}
+
+// discount tables (host glibc): lg[i] = log2((float) i + 2) (dcg.cc:37), invlg[i] = 1 / log2(i + 2) (ndcg.cc:79)
+static void discount_tables(uint32_t n, std::vector<double> &lg, std::vector<double> &invlg) {
+  lg.resize(n + 1);
+  invlg.resize(n + 1);
+  for (uint32_t i = 0; i <= n; ++i) {
+    lg[i] = std::log2((double) ((float) i + 2.0f));
+    invlg[i] = 1.0 / std::log2((double) (i + 2));
+  }
+}
+
+// second half of context creation: per-query tables, state arrays, histogram pool, kernel attributes, peers
+static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoffsets, const qr_params *params, InitClock &clk) {
+  const size_t F = c->F;
+  std::vector<uint32_t> qoff;
+  uint32_t maxlen = 0;
+  QR_TRY(check_query_offsets(qoffsets, c->Q, qoff, &maxlen));
+  c->maxlen = (maxlen + 3u) & ~3u;
+  // everything below that scales with the documents / queries / longest query is sized by these (see qr_internal.cuh)
+  c->cap_N = std::max(c->cap_N, c->N);
+  c->cap_Q = std::max(c->cap_Q, c->Q);
+  c->cap_maxlen = std::max(c->cap_maxlen, c->maxlen);
+  const size_t N = c->cap_N, Q = c->cap_Q;
+  std::vector<double> lg, invlg;
+  discount_tables(c->cap_maxlen, lg, invlg);
+  QR_TRY(dev_alloc(&c->d_labels, N));
+  QR_TRY(dev_alloc(&c->d_gain, N));
+  QR_TRY(dev_alloc(&c->d_qoff, Q + 1));
+  QR_TRY(dev_alloc(&c->d_idcg, Q));
+  QR_TRY(dev_alloc(&c->d_lg, c->cap_maxlen + 1));
+  QR_TRY(dev_alloc(&c->d_invlg, c->cap_maxlen + 1));
+  QR_CUDA(cudaMemcpy(c->d_lg, lg.data(), (c->cap_maxlen + 1) * sizeof(double), cudaMemcpyHostToDevice));
+  QR_CUDA(cudaMemcpy(c->d_invlg, invlg.data(), (c->cap_maxlen + 1) * sizeof(double), cudaMemcpyHostToDevice));
   QR_TRY(dev_alloc(&c->d_scores, N));
   QR_TRY(dev_alloc(&c->d_lambda, N));
   QR_TRY(dev_alloc(&c->d_weight, N));
@@ -585,11 +623,8 @@ static int ctx_create_state(qr_ctx *c, const float *labels, const uint64_t *qoff
   QR_TRY(dev_alloc(&c->d_qndcg, Q));
   QR_TRY(dev_alloc(&c->d_metric, 1));
   QR_TRY(dev_alloc(&c->d_leaf_of_doc, N));
-  QR_CUDA(cudaMemset(c->d_scores, 0, N * sizeof(double)));
-  QR_CUDA(cudaMemset(c->d_lambda, 0, N * sizeof(double)));
-  QR_CUDA(cudaMemset(c->d_weight, 0, N * sizeof(double)));
-  QR_CUDA(cudaMemset(c->d_leaf_of_doc, 0, N * sizeof(uint32_t)));
-  QR_CUDA(cudaMemset(c->d_qexp, 0, 2 * sizeof(int)));
+  QR_TRY(fill_query_tables(c, labels, qoff, lg));
+  clk.lap("per-query tables + state arrays");
 
   const size_t maxleaves = c->oblivious ? ((size_t) 1 << params->treedepth) : std::max<size_t>(params->nleaves, 1);
   c->max_tasks = (uint32_t) maxleaves + 1;
@@ -912,14 +947,54 @@ int qr_ctx_create_sample(qr_ctx *full, const float *feat_rowmajor, size_t N, siz
       if (rc == QR_OK && cudaMemcpy(c->d_src_doc, src_doc, N * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = QR_ECUDA;
     }
     if (rc == QR_OK && key_doc) {
-      rc = dev_alloc(&c->d_key_doc, N);
-      if (rc == QR_OK) rc = dev_alloc(&c->d_rankkey, N);
+      rc = dev_alloc(&c->d_key_doc, std::max(c->cap_N, N));
+      if (rc == QR_OK) rc = dev_alloc(&c->d_rankkey, std::max(c->cap_N, N));
       if (rc == QR_OK && cudaMemcpy(c->d_key_doc, key_doc, N * sizeof(uint32_t), cudaMemcpyHostToDevice) != cudaSuccess) rc = QR_ECUDA;
     }
     if (rc == QR_ECUDA) set_error("qr_ctx_create_sample: %s", cudaGetErrorString(cudaGetLastError()));
   }
   if (rc != QR_OK && out && *out) { std::string keep = g_last_error; qr_ctx_destroy(*out); *out = nullptr; g_last_error = keep; }
   return rc;
+}
+
+int qr_sample_redraw(qr_ctx *c, qr_ctx *full, size_t N, const float *labels, const uint64_t *qoffsets, size_t Q,
+                     const uint32_t *src_doc, const uint32_t *key_doc) {
+  if (!c || !full || !labels || !qoffsets || !src_doc || N == 0 || Q == 0) { set_error("qr_sample_redraw: null or empty argument"); return QR_EINVAL; }
+  if (!c->d_src_doc || c->sample_of_N != full->N || c->device != full->device || c->F != full->F) {
+    set_error("qr_sample_redraw: not a sample of this context");
+    return QR_EINVAL;
+  }
+  if ((key_doc != nullptr) != (c->d_key_doc != nullptr)) { set_error("qr_sample_redraw: the sample was created %s ranking keys", c->d_key_doc ? "with" : "without"); return QR_EINVAL; }
+  if (N > c->cap_N || Q > c->cap_Q || qoffsets[0] != 0 || qoffsets[Q] != N) {
+    set_error("qr_sample_redraw: %zu documents / %zu queries do not fit a sample context created for %zu / %zu "
+              "(create it with feat_rowmajor == NULL), or bad query offsets", N, Q, c->cap_N, c->cap_Q);
+    return QR_EINVAL;
+  }
+  for (size_t i = 0; i < N; ++i)
+    if (src_doc[i] >= full->N || (key_doc && key_doc[i] >= full->N)) { set_error("qr_sample_redraw: document index out of range at %zu", i); return QR_EINVAL; }
+  std::vector<uint32_t> qoff;
+  uint32_t maxlen = 0;
+  QR_TRY(check_query_offsets(qoffsets, Q, qoff, &maxlen));
+  if (((maxlen + 3u) & ~3u) > c->cap_maxlen) { set_error("qr_sample_redraw: a query of %u documents exceeds the longest query of the sampled context", maxlen); return QR_EINVAL; }
+  cudaSetDevice(c->device);
+  QR_CUDA(cudaStreamSynchronize(c->stream));
+  // the last tree of the previous sample goes: its nodes' histogram slots, its document -> node map
+  for (auto &nd : c->nodes) release_slot(c, nd.hist);
+  c->nodes.clear();
+  c->leaves.clear();
+  c->has_tree = false;
+  c->ranking_valid = false;
+  c->N = c->N_global = N;
+  c->Q = c->Q_global = Q;
+  c->maxlen = (maxlen + 3u) & ~3u;
+  QR_TRY(gather_sample_bins(c, full, src_doc));
+  if (key_doc) QR_CUDA(cudaMemcpy(c->d_key_doc, key_doc, N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  std::vector<double> lg, invlg;
+  discount_tables(c->maxlen, lg, invlg);
+  QR_TRY(fill_query_tables(c, labels, qoff, lg));
+  QR_CUDA(cudaMemset(c->d_node, 0, (c->cap_N + 8) * sizeof(uint16_t)));
+  QR_TRY(init_root_counts(c));
+  return QR_OK;
 }
 
 int qr_sample_pull_scores(qr_ctx *c, qr_ctx *full) {

@@ -524,7 +524,7 @@ static int init_root_counts(qr_ctx *c) {
                 (unsigned long long *) nullptr, (const uint4 *) nullptr, c->npanels);
     return QR_OK;
   }));
-  QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));
+  if (!c->d_root_cnt) QR_TRY(dev_alloc(&c->d_root_cnt, c->ncells));   // (qr_sample_redraw counts again into the same array)
   QR_CUDA(cudaMemcpyAsync(c->d_root_cnt, c->d_hist_cnt + (size_t) slot * c->ncells, c->ncells * sizeof(uint32_t),
                           cudaMemcpyDeviceToDevice, c->stream));
   if (c->comm) QR_TRY(comm_allreduce_sum_u32(c->comm, c->d_root_cnt, c->ncells, c->stream));

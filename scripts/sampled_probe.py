@@ -59,8 +59,7 @@ with api.Trainer(x, l, off, nleaves=LEAVES, minleafsupport=1) as full:
             a = time.time()
             ids = draw(full.get_scores())
             b = time.time()
-            sm.close()
-            sm = full.sample_context(x, ids)
+            sm.redraw(full, ids)
             c = time.time()
             t_draw += b - a
             t_ctx += c - b
@@ -75,7 +74,7 @@ with api.Trainer(x, l, off, nleaves=LEAVES, minleafsupport=1) as full:
 gpu_s = t_loop - t_draw
 out["gpu"] = dict(trees_per_s=trees / gpu_s, loop_s=gpu_s, of_which_sample_contexts_s=t_ctx, numpy_draw_s=t_draw,
                   ctx_create_s=t_create, sample_sizes=sizes, ndcg=metric)
-print("GPU: %.1f trees/s (%d trees in %.3f s, %.3f s of it re-creating %d sample contexts; numpy draw %.2f s not counted), "
+print("GPU: %.1f trees/s (%d trees in %.3f s, %.3f s of it loading %d new samples into the sample context; numpy draw %.2f s not counted), "
       "samples %s, NDCG@10 %.4f" % (trees / gpu_s, trees, gpu_s, t_ctx, len(sizes), t_draw, sizes, metric), flush=True)
 if pyref.available():
     threads = pyref.set_threads(os.cpu_count())

@@ -61,6 +61,22 @@ def test_sample_selection_matches_the_reference(negative, adaptive):
     assert checked >= 30
 
 
+@needs_ref
+@pytest.mark.parametrize("negative", ["RATIO", "POS"])
+def test_sample_selection_on_many_queries(negative):
+    """Same as above at a size where the host sorts the queries on several threads (the rand() stream and the moves
+    to the front stay in query order)."""
+    labels, scores, off = _sampling_case(77, True, q=4000)
+    assert len(labels) > 100000
+    inp = "%d %d\n%s\n%s\n" % (len(off) - 1, len(labels), " ".join(str(int(o)) for o in off),
+                               "\n".join("%d %.17g" % (l, s) for l, s in zip(labels, scores)))
+    out = subprocess.run([CHECK, "0.3", "0.25", "NO", negative, "1.0"], input=inp, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    vals = np.array(out.stdout.split(), dtype=np.uint64)
+    want_n, want_ids = pyref.selective_sample(labels, scores, off, 0.3, 0.25, "NO", negative, 1.0)
+    assert int(vals[0]) == want_n and np.array_equal(vals[1:], want_ids)
+
+
 def test_selective_rejects_what_the_reference_dies_on(tmp_path):
     """--sampling-iterations 0 with a sampling factor set is a division by zero in the reference
     (lambdamartselective.cc:170-171); here it is an error message — checked before any device work."""
@@ -128,6 +144,47 @@ def test_identity_sample_grows_the_trees_of_the_full_context(gather):
                     assert np.array_equal(got[k], want[k]), k
                 assert np.array_equal(full.get_scores(), plain.get_scores())
                 assert full.evaluate_dataset() == want_metric
+
+
+@pytest.mark.gpu
+def test_redraw_equals_a_fresh_sample_context():
+    """qr_sample_redraw refills a sample context in place: after a draw that is smaller, one that is larger and one that
+    drops whole queries, pseudo-responses and the fitted tree equal those of a context created afresh for the same draw."""
+    from quickrank_b200 import api
+    x, l, off = common.dataset(n=8000, f=16, q=80, seed=4)
+    rng = np.random.default_rng(9)
+    with api.Trainer(x, l, off, nleaves=10, minleafsupport=5) as full:
+        for _ in range(3):
+            full.boost_iteration()
+        with full.sample_context(x, np.arange(len(l))) as sm:
+            sm.pull_scores(full)
+            sm.compute_pseudoresponses()
+            sm.fit_regressor_on_gradient()     # (leaves a tree and its histogram slots behind, as in training)
+            q_of = np.searchsorted(off, np.arange(len(l)), side="right") - 1
+            for share, drop_queries in ((0.3, False), (0.8, False), (0.5, True)):
+                mask = rng.random(len(l)) < share
+                if drop_queries:
+                    mask &= (q_of % 3) != 0
+                ids = np.nonzero(mask)[0]
+                sm.redraw(full, ids)
+                assert sm.N == len(ids)
+                with full.sample_context(x, ids) as fresh:
+                    out = []
+                    for ctx in (sm, fresh):
+                        ctx.pull_scores(full)
+                        ctx.compute_pseudoresponses()
+                        lam, w = ctx.get_pseudoresponses()
+                        tree = ctx.fit_regressor_on_gradient()
+                        out.append((lam, w, tree, ctx.get_leaf_assignment()))
+                (lam_a, w_a, tree_a, leaf_a), (lam_b, w_b, tree_b, leaf_b) = out
+                assert np.array_equal(lam_a, lam_b) and np.array_equal(w_a, w_b)
+                for k in ("feature", "threshold_idx", "left", "right", "value", "count", "deviance"):
+                    assert np.array_equal(tree_a[k], tree_b[k]), (share, k)
+                assert np.array_equal(leaf_a, leaf_b)
+            # a sample that does not fit is refused
+            with full.sample_context(x, np.arange(100), gather=False) as small:
+                with pytest.raises(api.QrError):
+                    small.redraw(full, np.arange(200))
 
 
 def _write_svml(path, x, l, off):
