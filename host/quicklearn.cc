@@ -121,8 +121,29 @@ int main(int argc, char **argv) {
   }
   const std::string algo = get("algo", "LAMBDAMART");
   int rank = 0;
+  auto load = [](const std::string &file, std::ostream &log) {
+    io::Svml reader;
+    auto t0 = std::chrono::high_resolution_clock::now();
+    std::shared_ptr<data::Dataset> ds = reader.read_horizontal(file);
+    double s = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    log << "#\t Reading time: " << std::setprecision(2) << s << " s." << std::endl
+        << "#\t Dataset size: " << ds->num_instances() << " x " << ds->num_features()
+        << " (instances x features)" << std::endl
+        << "#\t Num queries: " << ds->num_queries() << std::endl;
+    return ds;
+  };
+  // `--gpus N` without an external launcher forks the ranks: the datasets are parsed ONCE, here, before the fork (no
+  // CUDA call has been made yet), and the ranks share the parsed pages copy-on-write instead of each parsing the text
+  // with every core and holding a private copy.  What the reader reports is printed where the reference prints it.
+  std::shared_ptr<data::Dataset> preloaded_train, preloaded_valid;
+  std::ostringstream preload_train_log, preload_valid_log;
   if (opt.count("train") && (!opt.count("model-in") || opt.count("restart-train"))) {
     const int gpus = (int) geti("gpus", 1);
+    const bool launcher = getenv("RANK") && getenv("WORLD_SIZE") && atoi(getenv("WORLD_SIZE")) > 1;
+    if (gpus > 1 && !launcher) {
+      preloaded_train = load(opt["train"], preload_train_log);
+      if (opt.count("valid")) preloaded_valid = load(opt["valid"], preload_valid_log);
+    }
     rank = setup_sharding(gpus);
     if (rank != 0) {   // same loop, no report
       // (never destroyed: std::cout is flushed once more when the process exits)
@@ -200,26 +221,18 @@ int main(int argc, char **argv) {
     std::cerr << "!!! Only NDCG is supported by the GPU engine." << std::endl;
     return finish(EXIT_FAILURE);
   }
-  auto load = [](const std::string &file) {
-    io::Svml reader;
-    auto t0 = std::chrono::high_resolution_clock::now();
-    std::shared_ptr<data::Dataset> ds = reader.read_horizontal(file);
-    double s = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
-    std::cout << "#\t Reading time: " << std::setprecision(2) << s << " s." << std::endl
-              << "#\t Dataset size: " << ds->num_instances() << " x " << ds->num_features()
-              << " (instances x features)" << std::endl
-              << "#\t Num queries: " << ds->num_queries() << std::endl;
-    return ds;
-  };
-
   if (opt.count("train") && from_scratch) {   // driver.cc:136-138: a model loaded without --restart-train is not trained
     std::shared_ptr<metric::ir::Metric> train_metric(new metric::ir::Ndcg(geti("train-cutoff", 10)));
     std::cout << "# Reading training dataset: " << opt["train"] << std::endl;
-    auto train = load(opt["train"]);
+    std::shared_ptr<data::Dataset> train = preloaded_train;
+    if (train) std::cout << preload_train_log.str();
+    else train = load(opt["train"], std::cout);
     std::shared_ptr<data::Dataset> valid;
     if (opt.count("valid")) {
       std::cout << "# Reading validation dataset: " << opt["valid"] << std::endl;
-      valid = load(opt["valid"]);
+      valid = preloaded_valid;
+      if (valid) std::cout << preload_valid_log.str();
+      else valid = load(opt["valid"], std::cout);
     }
     std::cout << "#" << std::endl << "# training scorer: " << *train_metric << std::endl;
     ranker->learn(train, valid, train_metric, rank == 0 ? partial : 0, get("model-out", ""));
@@ -231,7 +244,7 @@ int main(int argc, char **argv) {
   if (opt.count("test") && rank == 0) {   // (the other ranks of a multi-GPU run have nothing to report)
     std::shared_ptr<metric::ir::Metric> test_metric(new metric::ir::Ndcg(geti("test-cutoff", 10)));
     std::cout << "# Reading test dataset: " << opt["test"] << std::endl;
-    auto test = load(opt["test"]);
+    auto test = load(opt["test"], std::cout);
     std::vector<Score> scores(test->num_instances());
     ranker->score_dataset(test, scores.data());
     const MetricScore m = test_metric->evaluate_dataset(test, scores.data());

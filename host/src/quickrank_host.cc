@@ -325,6 +325,9 @@ std::unique_ptr<data::Dataset> Svml::read_horizontal(const std::string &filename
   buf[(size_t) std::max<long>(fsize, 0)] = '\0';
   char *base = buf.data(), *end = base + std::max<long>(fsize, 0);
   unsigned nthreads = std::thread::hardware_concurrency();
+  // the ranks of an external launcher each parse their copy on the same host: share the cores between them
+  // (quicklearn's own `--gpus N` parses once, before it forks the ranks)
+  if (const char *lw = getenv("LOCAL_WORLD_SIZE")) nthreads = std::max(1u, nthreads / (unsigned) std::max(1, atoi(lw)));
   if (const char *env = getenv("QR_SVML_THREADS")) nthreads = (unsigned) atoi(env);
   nthreads = std::max(1u, std::min(nthreads, (unsigned) (fsize / (1 << 20)) + 1u));   // >= 1 MB per thread
   // chunk boundaries on line starts
