@@ -106,6 +106,7 @@ def lib():
         L.qref_selective_sample.restype = u64
         L.qref_selective_sample.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int, C.c_double, fp, dp, C.POINTER(u64),
                                             u64, u64, C.POINTER(u64)]
+        L.qref_read_svml.argtypes = [C.c_char_p, C.POINTER(u64), C.POINTER(u64), dp]
         L.qref_set_threads.argtypes = [C.c_int]
         L.qref_max_threads.restype = C.c_int
         _lib = L
@@ -377,3 +378,14 @@ def selective_sample(labels, scores, qoff, rank_factor, random_factor, adaptive=
                                     _p(scores, C.c_double), _p(qoff, C.c_uint64), len(labels), len(qoff) - 1,
                                     _p(ids, C.c_uint64))
     return int(n), ids
+
+
+def read_svml(path):
+    """The reference's io::Svml::read_horizontal on a file: ((N, F, Q), (fnv labels, fnv offsets, fnv matrix), seconds)."""
+    shape = (C.c_uint64 * 3)()
+    sums = (C.c_uint64 * 3)()
+    sec = C.c_double()
+    rc = lib().qref_read_svml(path.encode(), shape, sums, C.byref(sec))
+    if rc:
+        raise RuntimeError("reference SVMLight reader failed")
+    return tuple(int(v) for v in shape), tuple(int(v) for v in sums), sec.value

@@ -38,6 +38,7 @@
 #include "io/generate_conditional_operators.h"
 #include "io/generate_oblivious.h"
 #include "io/generate_vpred.h"
+#include "io/svml.h"
 #include "learning/forests/dart.h"
 #include "learning/forests/lambdamartselective.h"
 #include "utils/radix.h"
@@ -571,6 +572,37 @@ uint64_t qref_selective_sample(double rank_factor, double random_factor, int ada
   const size_t n = probe.draw(ds, sc.data(), ids.data(), npos.data(), (float) adapt_factor);
   for (uint64_t i = 0; i < N; ++i) ids_out[i] = ids[i];
   return n;
+}
+
+// The reference's own SVMLight reader (io::Svml::read_horizontal, src/io/svml.cc:38-161) on a file: shape, FNV-1a
+// checksums of labels / query offsets / the row-major feature matrix (the quantities host/bin/svml_check prints for the
+// host reader) and the wall time of the call.
+static uint64_t fnv1a(const void *p, size_t n) {
+  uint64_t h = 1469598103934665603ull;
+  const unsigned char *b = (const unsigned char *) p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
+}
+int qref_read_svml(const char *path, uint64_t shape[3], uint64_t sums[3], double *seconds) {
+  io::Svml reader;
+  const double t0 = omp_get_wtime();
+  std::unique_ptr<data::Dataset> ds;
+  {
+    Silence sil(true);
+    ds = reader.read_horizontal(path);
+  }
+  *seconds = omp_get_wtime() - t0;
+  if (!ds) return 1;
+  const size_t n = ds->num_instances(), f = ds->num_features(), q = ds->num_queries();
+  shape[0] = n; shape[1] = f; shape[2] = q;
+  std::vector<float> labels(n);
+  std::vector<uint64_t> off(q + 1);
+  for (size_t i = 0; i < n; ++i) labels[i] = ds->getLabel(i);
+  for (size_t i = 0; i <= q; ++i) off[i] = ds->offset(i);
+  sums[0] = fnv1a(labels.data(), n * sizeof(float));
+  sums[1] = fnv1a(off.data(), off.size() * sizeof(uint64_t));
+  sums[2] = fnv1a(ds->at(0, 0), n * f * sizeof(float));
+  return 0;
 }
 
 void qref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -96,3 +96,29 @@ def test_binary_cache_round_trip_and_invalidation(tmp_path):
     os.utime(path + ".qrb")
     fourth = subprocess.run([CHECK, path], capture_output=True, text=True, env=env)
     assert fourth.returncode == 0 and fourth.stdout.split() == third.stdout.split()
+
+
+def test_host_reader_equals_the_reference_reader(tmp_path):
+    """The same file through the unmodified reference's io::Svml::read_horizontal (svml.cc:38-161, compiled into
+    oracle/_ref): shape, labels, query boundaries and every feature value equal (checksums of the raw arrays)."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref/libqr_ref.so not built")
+    rng = np.random.default_rng(4)
+    n, f = 8000, 31
+    x = rng.normal(size=(n, f)).astype(np.float32)
+    x[rng.random((n, f)) < 0.4] = 0.0
+    labels = rng.integers(0, 5, size=n)
+    qlen = rng.integers(1, 90, size=400)
+    off = np.concatenate([[0], np.cumsum(qlen)])
+    off = off[off < n].tolist() + [n]
+    path = str(tmp_path / "data.txt")
+    with open(path, "w") as fh:
+        for q in range(len(off) - 1):
+            for i in range(off[q], off[q + 1]):
+                feats = " ".join("%d:%.9g" % (j + 1, x[i, j]) for j in range(f) if x[i, j] != 0 or j == f - 1)
+                fh.write("%d qid:%d %s%s\n" % (labels[i], q + 7, feats, " # d%d" % i if i % 11 == 0 else ""))
+    shape, sums, _sec = pyref.read_svml(path)
+    got = run(path, 5)
+    assert [int(v) for v in got[:3]] == list(shape)
+    assert tuple(int(v, 16) for v in got[3:6]) == sums
