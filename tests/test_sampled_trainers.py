@@ -217,22 +217,37 @@ def _leaf_of(t, data):
       "--adaptive-strategy", "MIX", "--normalization-factor", "4"]),
 ])
 def test_selective_matches_the_reference_learn_loop(tmp_path, sel, cli):
+    """Whole `quicklearn --algo LAMBDAMART-SELECTIVE` runs against the unmodified LambdaMartSelective::learn: RATIO with
+    random negatives, POS, MUL with the MIX adaptive strategy (see _selective_against_reference)."""
+    _selective_against_reference(tmp_path, sel, cli, n=4000, f=12, ntrees=9, leaves=8, minls=10)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_selective_matches_the_reference_on_a_larger_set(tmp_path):
+    """The same comparison on 30 000 documents x 20 continuous features, 16 leaves (several threads sort the queries
+    in the host's draw; the sample context holds ~20 000 documents)."""
+    _selective_against_reference(tmp_path, dict(sampling_iterations=2, rank_factor=0.4, random_factor=0.2),
+                                 ["--sampling-iterations", "2", "--rank-sampling-factor", "0.4", "--random-sampling-factor", "0.2"],
+                                 n=30000, f=20, ntrees=7, leaves=16, minls=20, gridded=False)
+
+
+def _selective_against_reference(tmp_path, sel, cli, n, f, ntrees, leaves, minls, gridded=True):
     """LambdaMartSelective::learn (lambdamartselective.cc:46-313) end to end: the sizes of every sample ("Reducing
     training size from N to M"), the sampling factors it prints, the NDCG trajectory (4 decimals printed) and the
     trees — split features and structure equal, thresholds equal or cutting the training documents into the same
     sets, leaf outputs within 1e-9 relative (fixed-point sums on the sample against the reference's FP64 order)."""
     from quickrank_b200 import modelxml
-    x, l, off = common.dataset(n=4000, f=12, q=40, seed=8)
-    ntrees = 9
-    with pyref.RefSession("LAMBDAMART-SELECTIVE", x, l, off, ntrees=ntrees, nleaves=8, minleafsupport=10, selective=sel) as s:
+    x, l, off = common.dataset(n=n, f=f, q=n // 100, seed=8, gridded=gridded)
+    with pyref.RefSession("LAMBDAMART-SELECTIVE", x, l, off, ntrees=ntrees, nleaves=leaves, minleafsupport=minls, selective=sel) as s:
         s.learn()
         want_metric = s.metric_history()
         want_log = s.log()
         want_trees = [s.tree(t) for t in range(s.num_trees())]
     tr, model = str(tmp_path / "train.txt"), str(tmp_path / "sel.xml")
     _write_svml(tr, x, l, off)
-    cmd = [QL, "--algo", "LAMBDAMART-SELECTIVE", "--train", tr, "--num-trees", str(ntrees), "--num-leaves", "8",
-           "--min-leaf-support", "10", "--model-out", model, "--end-after-rounds", "0", "--partial", "0"] + cli
+    cmd = [QL, "--algo", "LAMBDAMART-SELECTIVE", "--train", tr, "--num-trees", str(ntrees), "--num-leaves", str(leaves),
+           "--min-leaf-support", str(minls), "--model-out", model, "--end-after-rounds", "0", "--partial", "0"] + cli
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr + out.stdout
     pick = lambda text, pat: re.findall(pat, text, flags=re.M)
