@@ -215,6 +215,9 @@ def _leaf_of(t, data):
     (dict(sampling_iterations=2, rank_factor=1.5, random_factor=0.5, negative="MUL", adaptive="MIX", normalization_factor=4.0),
      ["--sampling-iterations", "2", "--rank-sampling-factor", "1.5", "--random-sampling-factor", "0.5", "--negative-strategy", "MUL",
       "--adaptive-strategy", "MIX", "--normalization-factor", "4"]),
+    # the full context in reference-order mode (scores, NDCG mean in the reference's order); the sample stays fixed-point
+    (dict(sampling_iterations=4, rank_factor=0.25, random_factor=0.25),
+     ["--sampling-iterations", "4", "--rank-sampling-factor", "0.25", "--random-sampling-factor", "0.25", "--hist-mode", "reference"]),
 ])
 def test_selective_matches_the_reference_learn_loop(tmp_path, sel, cli):
     """Whole `quicklearn --algo LAMBDAMART-SELECTIVE` runs against the unmodified LambdaMartSelective::learn: RATIO with
@@ -304,3 +307,29 @@ def test_stochastic_negative_keeps_positives_and_a_share_of_negatives(tmp_path):
     assert a == b
     assert a != c
     assert "<type>STOCHASTIC-NEGATIVE</type>" in a
+
+
+@pytest.mark.gpu
+def test_selective_with_a_validation_set_rolls_back_to_the_best_model(tmp_path):
+    """The validation branch of the sampled loop (lambdamartselective.cc:217-241, 281-287): validation scores follow
+    every tree, the starred rows are the new bests, early stop after --end-after-rounds rows without one, and the saved
+    ensemble ends at the best row."""
+    x, l, off = common.dataset(n=3000, f=12, q=30, seed=8)
+    xv, lv, offv = common.dataset(n=1500, f=12, q=15, seed=9)
+    tr, va, model = str(tmp_path / "train.txt"), str(tmp_path / "valid.txt"), str(tmp_path / "m.xml")
+    _write_svml(tr, x, l, off)
+    _write_svml(va, xv, lv, offv)
+    cmd = [QL, "--algo", "LAMBDAMART-SELECTIVE", "--train", tr, "--valid", va, "--num-trees", "30", "--num-leaves", "8",
+           "--min-leaf-support", "10", "--model-out", model, "--end-after-rounds", "4", "--partial", "0",
+           "--sampling-iterations", "3", "--rank-sampling-factor", "0.3", "--random-sampling-factor", "0.3"]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    rows = re.findall(r"^\s+(\d+)\s+([0-9.]+)\s+([0-9.]+)( \*)?$", out.stdout, flags=re.M)
+    assert rows, out.stdout
+    best = max(int(r[0]) for r in rows if r[3])
+    valid = [float(r[2]) for r in rows]
+    assert valid[best - 1] == max(valid)
+    assert len(rows) == min(30, best + 4)   # mart.cc:309-311: stop when m > best_model_ + esr (both 0-based)
+    assert len(re.findall(r"<tree id=", open(model).read())) == best
+    m = re.search(r"NDCG@10 on validation data = ([0-9.]+)", out.stdout)
+    assert m and abs(float(m.group(1)) - valid[best - 1]) <= 5e-5
