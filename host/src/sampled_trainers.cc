@@ -19,6 +19,12 @@
 //    random negatives from std::random_shuffle's rand() stream after srand(0): this file calls the same
 //    std::sort with equivalent comparators and restates random_shuffle's loop;
 //  * the quotas are computed in float, as the reference's `float * size_t` products are.
+//
+// Provenance: like host/src/quickrank_host.cc this is reference-facing HOST code — the training loop, its stdout table
+// and the sampling rules restate hpclab/quickrank's src/learning/forests/{lambdamartselective,stochasticnegative}.cc
+// (Reciprocal Public License 1.5) closely enough for the printed lines, the rand() stream and the drawn samples to be
+// identical, and it is to be read under the same licence.  The structure (one shared loop with hooks, a parallel
+// ordering phase and a sequential selection phase in the draw) and everything below the C ABI are this repository's.
 #include "quickrank_host.h"
 
 #include <algorithm>
