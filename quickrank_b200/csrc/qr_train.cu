@@ -13,6 +13,7 @@
 #include <cstring>
 #include <functional>
 #include <limits>
+#include <thread>
 
 #include <cub/cub.cuh>
 
@@ -532,29 +533,39 @@ static int ctx_create_common(const float *feat, bool rowmajor, size_t N, size_t 
 static int fill_query_tables(qr_ctx *c, const float *labels, const std::vector<uint32_t> &qoff, const std::vector<double> &lg) {
   const size_t N = c->N, Q = c->Q;
   std::vector<double> gain(N), idcg(Q);
-  // pow(2, label) (dcg.cc:37) through a memo of the few distinct label values: the same glibc results without a
-  // pow() call per document
-  float memo_label[8];
-  double memo_gain[8];
-  int memo_n = 0;
-  auto gain_of = [&](float label) {
-    for (int k = 0; k < memo_n; ++k)
-      if (memo_label[k] == label) return memo_gain[k];
-    const double g = std::pow(2.0, (double) label);
-    if (memo_n < 8) { memo_label[memo_n] = label; memo_gain[memo_n] = g; ++memo_n; }
-    return g;
-  };
-  for (size_t i = 0; i < N; ++i) gain[i] = gain_of(labels[i]);
-  {
+  // Queries are independent: a few host threads each take a range of them (and of their documents).  pow(2, label)
+  // (dcg.cc:37) goes through a per-thread memo of the few distinct label values: the same glibc results without a
+  // pow() call per document.
+  const size_t cutoff = c->cutoff;
+  auto fill = [&](size_t q0, size_t q1) {
+    float memo_label[8];
+    double memo_gain[8];
+    int memo_n = 0;
+    auto gain_of = [&](float label) {
+      for (int k = 0; k < memo_n; ++k)
+        if (memo_label[k] == label) return memo_gain[k];
+      const double g = std::pow(2.0, (double) label);
+      if (memo_n < 8) { memo_label[memo_n] = label; memo_gain[memo_n] = g; ++memo_n; }
+      return g;
+    };
+    for (size_t i = qoff[q0]; i < qoff[q1]; ++i) gain[i] = gain_of(labels[i]);
     std::vector<float> tmp;
-    for (size_t q = 0; q < Q; ++q) {                                                         // ndcg.cc:35-47
+    for (size_t q = q0; q < q1; ++q) {                                                       // ndcg.cc:35-47
       tmp.assign(labels + qoff[q], labels + qoff[q + 1]);
       std::sort(tmp.begin(), tmp.end(), std::greater<int>());
-      const size_t size = std::min(c->cutoff, tmp.size());
+      const size_t size = std::min(cutoff, tmp.size());
       double dcg = 0.0;
       for (size_t i = 0; i < size; ++i) dcg += (gain_of(tmp[i]) - 1.0) / lg[i];
       idcg[q] = dcg;
     }
+  };
+  const size_t nthreads = std::max<size_t>(1, std::min<size_t>({(size_t) std::thread::hardware_concurrency(), (size_t) 16, N / 50000 + 1, Q}));
+  if (nthreads <= 1) {
+    fill(0, Q);
+  } else {
+    std::vector<std::thread> pool;
+    for (size_t t = 0; t < nthreads; ++t) pool.emplace_back(fill, Q * t / nthreads, Q * (t + 1) / nthreads);
+    for (auto &t : pool) t.join();
   }
   QR_CUDA(cudaMemcpy(c->d_labels, labels, N * sizeof(float), cudaMemcpyHostToDevice));
   QR_CUDA(cudaMemcpy(c->d_gain, gain.data(), N * sizeof(double), cudaMemcpyHostToDevice));
