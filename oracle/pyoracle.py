@@ -58,6 +58,7 @@ def lib():
         L.qro_delta_ndcg.restype = C.c_double
         L.qro_delta_ndcg.argtypes = [fp, sz, sz, C.c_double, sz, sz]
         L.qro_lambdas.argtypes = [dp, fp, u64p, sz, sz, dp, dp]
+        L.qro_lambdas_masked.argtypes = [dp, fp, u64p, sz, sz, C.POINTER(C.c_uint8), dp, dp]
         L.qro_mart_pseudo.argtypes = [dp, fp, sz, dp]
         L.qro_radix_argsort.argtypes = [fp, sz, u64p]
         L.qro_binning.restype = C.POINTER(Bins)
@@ -155,6 +156,19 @@ def lambdas(scores, labels, qoff, cutoff):
     w = np.zeros(len(labels), np.float64)
     lib().qro_lambdas(_p(scores, C.c_double), _p(labels, C.c_float), _p(qoff, C.c_uint64),
                       len(qoff) - 1, cutoff, _p(lam, C.c_double), _p(w, C.c_double))
+    return lam, w
+
+
+def lambdas_masked(scores, labels, qoff, cutoff, presence):
+    """compute_pseudoresponses with sample_presence (lambdamart.cc:84-105): the document-sampling trainers' call"""
+    labels = np.ascontiguousarray(labels, np.float32)
+    scores = np.ascontiguousarray(scores, np.float64)
+    qoff = np.ascontiguousarray(qoff, np.uint64)
+    presence = np.ascontiguousarray(presence, np.uint8)
+    lam = np.zeros(len(labels), np.float64)
+    w = np.zeros(len(labels), np.float64)
+    lib().qro_lambdas_masked(_p(scores, C.c_double), _p(labels, C.c_float), _p(qoff, C.c_uint64), len(qoff) - 1, cutoff,
+                             _p(presence, C.c_uint8), _p(lam, C.c_double), _p(w, C.c_double))
     return lam, w
 
 

@@ -283,6 +283,53 @@ void qro_lambdas(const double *scores, const float *labels, const uint64_t *qoff
   }
 }
 
+/* lambdamart.cc:62-152, sample_presence != NULL branch (the document-sampling trainers: lambdamartselective.cc:194,
+ * stochasticnegative.cc:197).  A query is compacted to its present documents (:84-98); the compacted list is RANKED by
+ * scores_on_training_[d] with d the document's position inside its query — the query offset is not added at :94 —
+ * while rho (:132-134) uses the documents' own scores.  Absent documents keep zero lambdas and weights. */
+void qro_lambdas_masked(const double *scores, const float *labels, const uint64_t *qoff, size_t Q, size_t cutoff,
+                        const uint8_t *presence, double *lambdas, double *weights) {
+  cutoff = norm_cutoff(cutoff);
+#pragma omp parallel for schedule(dynamic, 16)
+  for (size_t q = 0; q < Q; ++q) {
+    const size_t off = qoff[q], n = qoff[q + 1] - qoff[q];
+    for (size_t j = off; j < off + n; ++j) lambdas[j] = weights[j] = 0.0; /* :77-78 */
+    if (n == 0) continue;
+    size_t *map = (size_t *) malloc(n * sizeof(size_t));       /* map_from_cleaned */
+    double *keys = (double *) malloc(n * sizeof(double));      /* training_scores_cleaned */
+    float *lab = (float *) malloc(n * sizeof(float));          /* labels_cleaned */
+    size_t m = 0;
+    for (size_t d = 0; d < n; ++d)
+      if (presence[off + d]) { map[m] = d; lab[m] = labels[off + d]; keys[m] = scores[d]; ++m; }   /* :91-96 */
+    uint32_t *unmap = (uint32_t *) malloc((m ? m : 1) * sizeof(uint32_t));
+    float *sl = (float *) malloc((m ? m : 1) * sizeof(float));
+    qro_sort_desc(keys, m, unmap);
+    for (size_t i = 0; i < m; ++i) sl[i] = lab[unmap[i]];
+    const double idcg = qro_idcg(sl, m, cutoff);
+    for (size_t j = 0; j < m; ++j) {
+      const float jl = sl[j];
+      const size_t ja = off + map[unmap[j]];                   /* :117 */
+      for (size_t k = 0; k < m; ++k) {
+        if (k == j) continue;
+        if (j >= cutoff && k >= cutoff) break;
+        const float kl = sl[k];
+        if (jl > kl) {
+          const size_t ka = off + map[unmap[k]];               /* :121 */
+          const double d = fabs(j < k ? qro_delta_ndcg(sl, m, cutoff, idcg, j, k)
+                                      : qro_delta_ndcg(sl, m, cutoff, idcg, k, j));
+          const double rho = 1.0 / (1.0 + exp(scores[ja] - scores[ka]));
+          const double t = (1.0 - rho) * rho;
+          lambdas[ja] = fma(rho, d, lambdas[ja]);
+          lambdas[ka] = fma(-rho, d, lambdas[ka]);
+          weights[ja] = fma(t, d, weights[ja]);
+          weights[ka] = fma(t, d, weights[ka]);
+        }
+      }
+    }
+    free(map); free(keys); free(lab); free(unmap); free(sl);
+  }
+}
+
 /* mart.cc:418-431: float label minus double score */
 void qro_mart_pseudo(const double *scores, const float *labels, size_t N, double *pseudo) {
   for (size_t i = 0; i < N; ++i) pseudo[i] = (double) labels[i] - scores[i];

@@ -61,7 +61,10 @@ double qro_delta_ndcg(const float *sorted_labels, size_t n, size_t cutoff, doubl
 
 /* --- pseudo-responses */
 void qro_lambdas(const double *scores, const float *labels, const uint64_t *qoff, size_t Q,
-                 size_t cutoff, double *lambdas, double *weights); /* lambdamart.cc:62-152 */
+                 size_t cutoff, double *lambdas, double *weights);
+/* the same with sample_presence (LambdaMartSelective / StochasticNegative): presence[doc] != 0 = sampled */
+void qro_lambdas_masked(const double *scores, const float *labels, const uint64_t *qoff, size_t Q,
+                        size_t cutoff, const uint8_t *presence, double *lambdas, double *weights); /* lambdamart.cc:62-152 */
 void qro_mart_pseudo(const double *scores, const float *labels, size_t N,
                      double *pseudo); /* mart.cc:418-431 */
 

@@ -73,5 +73,50 @@ def main():
     print("wrote pure_functions")
 
 
+def main_sampled():
+    """sampled.npz: the document-sampling trainers (LambdaMartSelective) — masked pseudo-responses, draws of
+    sampling_query_level, one whole learn() run.  Inputs that are not a pure function of a seed are stored too."""
+    vec = {}
+    x, l, off = synth.make_dataset(1500, 6, 18, seed=111)
+    rng = np.random.default_rng(12)
+    scores = rng.integers(0, 9, size=len(l)).astype(np.float64) * 0.25 + np.where(rng.random(len(l)) < 0.5, rng.normal(size=len(l)), 0.0)
+    mask = (rng.random(len(l)) < 0.55).astype(np.uint8)
+    with pyref.RefSession("LAMBDAMART", x, l, off, ntrees=1, nleaves=4, cutoff=10) as s:
+        s.init()
+        s.set_scores(scores)
+        s.compute_pseudoresponses_masked(mask)
+        lam, w = s.get_gradients()
+    vec["masked_scores"], vec["masked_presence"], vec["masked_lambda"], vec["masked_weight"] = scores, mask, lam, w
+    lens = rng.integers(1, 50, size=60)
+    doff = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    dl = rng.choice([0, 0, 0, 1, 2, 3], size=int(doff[-1])).astype(np.float32)
+    ds = np.round(rng.normal(size=int(doff[-1])), 1)
+    vec["draw_labels"], vec["draw_scores"], vec["draw_offsets"] = dl, ds, doff
+    for i, (rank, rnd, adaptive, negative, adapt) in enumerate([(0.3, 0.2, "NO", "RATIO", 1.0), (0.5, 0.25, "MIX", "POS", 0.37),
+                                                               (1.5, 0.5, "FIXED", "MUL", 0.6), (0.2, 0.6, "RATIO", "RATIO", 0.8)]):
+        nsel, ids = pyref.selective_sample(dl, ds, doff, rank, rnd, adaptive, negative, adapt)
+        vec["draw%d_params" % i] = np.array(repr((rank, rnd, adaptive, negative, adapt)))
+        vec["draw%d_n" % i], vec["draw%d_ids" % i] = np.array(nsel), ids
+    c = dict(n=2500, f=10, q=25, seed=112, trees=8, leaves=8, minls=5, cutoff=10,
+             selective=dict(sampling_iterations=3, rank_factor=0.3, random_factor=0.2))
+    x, l, off = synth.make_dataset(c["n"], c["f"], c["q"], seed=c["seed"])
+    vec["learn_case"] = np.array(repr(c))
+    with pyref.RefSession("LAMBDAMART-SELECTIVE", x, l, off, ntrees=c["trees"], nleaves=c["leaves"], minleafsupport=c["minls"],
+                          cutoff=c["cutoff"], selective=c["selective"]) as s:
+        s.learn()
+        vec["learn_metric"] = s.metric_history()
+        vec["learn_log"] = np.array(s.log())
+        for t in range(c["trees"]):
+            tr = s.tree(t)
+            for k in ("feature", "threshold_idx", "threshold", "left", "right", "value", "count"):
+                vec["learn_tree%d_%s" % (t, k)] = tr[k]
+    np.savez_compressed(os.path.join(HERE, "sampled.npz"), **vec)
+    print("wrote sampled")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "sampled":
+        main_sampled()
+    else:
+        main()
+        main_sampled()

@@ -333,3 +333,101 @@ def test_selective_with_a_validation_set_rolls_back_to_the_best_model(tmp_path):
     assert len(re.findall(r"<tree id=", open(model).read())) == best
     m = re.search(r"NDCG@10 on validation data = ([0-9.]+)", out.stdout)
     assert m and abs(float(m.group(1)) - valid[best - 1]) <= 5e-5
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# committed golden vectors (tests/golden/sampled.npz, made from the unmodified reference by tests/golden/make_golden.py):
+# the same checks where oracle/_ref is not available
+# ---------------------------------------------------------------------------------------------------------------
+GOLDEN = os.path.join(ROOT, "tests", "golden", "sampled.npz")
+
+
+def _golden_masked_case():
+    from quickrank_b200 import synth
+    g = np.load(GOLDEN)
+    x, l, off = synth.make_dataset(1500, 6, 18, seed=111)
+    return g, x, l, off
+
+
+def test_oracle_masked_pseudoresponses_against_the_golden_vectors():
+    """oracle/qr_oracle.c qro_lambdas_masked (the sample_presence branch of lambdamart.cc:62-152) reproduces the
+    reference's lambdas and weights bit for bit."""
+    from oracle import pyoracle as po
+    g, _x, l, off = _golden_masked_case()
+    lam, w = po.lambdas_masked(g["masked_scores"], l, off, 10, g["masked_presence"])
+    assert np.array_equal(lam, g["masked_lambda"]) and np.array_equal(w, g["masked_weight"])
+    assert not lam[g["masked_presence"] == 0].any()
+
+
+@needs_ref
+def test_oracle_masked_pseudoresponses_against_the_reference():
+    from oracle import pyoracle as po
+    x, l, off = common.dataset(n=5000, f=6, q=50, seed=23)
+    rng = np.random.default_rng(6)
+    for scores in (rng.normal(size=len(l)), common.tie_heavy_scores(len(l), rng)):
+        for share in (1.0, 0.5, 0.08):
+            mask = (rng.random(len(l)) < share).astype(np.uint8)
+            with pyref.RefSession("LAMBDAMART", x, l, off, ntrees=1, nleaves=4) as s:
+                s.init()
+                s.set_scores(scores)
+                s.compute_pseudoresponses_masked(mask)
+                want_lam, want_w = s.get_gradients()
+            lam, w = po.lambdas_masked(scores, l, off, 10, mask)
+            assert np.array_equal(lam, want_lam) and np.array_equal(w, want_w)
+
+
+def test_host_draw_against_the_golden_vectors():
+    g = np.load(GOLDEN)
+    labels, scores, off = g["draw_labels"], g["draw_scores"], g["draw_offsets"]
+    inp = "%d %d\n%s\n%s\n" % (len(off) - 1, len(labels), " ".join(str(int(o)) for o in off),
+                               "\n".join("%d %.17g" % (a, b) for a, b in zip(labels, scores)))
+    for i in range(4):
+        rank, rnd, adaptive, negative, adapt = eval(str(g["draw%d_params" % i]))
+        out = subprocess.run([CHECK, repr(rank), repr(rnd), adaptive, negative, repr(adapt)], input=inp, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        vals = np.array(out.stdout.split(), dtype=np.uint64)
+        assert int(vals[0]) == int(g["draw%d_n" % i]) and np.array_equal(vals[1:], g["draw%d_ids" % i]), i
+
+
+@pytest.mark.gpu
+def test_sample_context_against_the_golden_vectors(tmp_path):
+    """The GPU path against the committed reference outputs: masked pseudo-responses bit-equal; a whole
+    LAMBDAMART-SELECTIVE run with the reference's sample sizes, NDCG trajectory and trees."""
+    from quickrank_b200 import api, modelxml, synth
+    g, x, l, off = _golden_masked_case()
+    ids = np.nonzero(g["masked_presence"])[0]
+    with api.Trainer(x, l, off, nleaves=4) as full:
+        full.set_scores(g["masked_scores"])
+        with full.sample_context(x, ids) as sm:
+            sm.pull_scores(full)
+            sm.compute_pseudoresponses()
+            lam, w = sm.get_pseudoresponses()
+    assert np.array_equal(lam, g["masked_lambda"][ids]) and np.array_equal(w, g["masked_weight"][ids])
+    c = eval(str(g["learn_case"]))
+    x, l, off = synth.make_dataset(c["n"], c["f"], c["q"], seed=c["seed"])
+    tr, model = str(tmp_path / "train.txt"), str(tmp_path / "sel.xml")
+    _write_svml(tr, x, l, off)
+    sel = c["selective"]
+    cmd = [QL, "--algo", "LAMBDAMART-SELECTIVE", "--train", tr, "--num-trees", str(c["trees"]), "--num-leaves", str(c["leaves"]),
+           "--min-leaf-support", str(c["minls"]), "--model-out", model, "--end-after-rounds", "0", "--partial", "0",
+           "--sampling-iterations", str(sel["sampling_iterations"]), "--rank-sampling-factor", str(sel["rank_factor"]),
+           "--random-sampling-factor", str(sel["random_factor"])]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    want_log = str(g["learn_log"])
+    pick = lambda text, pat: re.findall(pat, text, flags=re.M)
+    for pat in (r"^Reducing training size from \d+ to \d+", r"^N\. Positives: .*"):
+        assert pick(out.stdout, pat) == pick(want_log, pat) and pick(want_log, pat)
+    rows = re.findall(r"^\s+(\d+)\s+([0-9.]+)", out.stdout, flags=re.M)
+    assert np.max(np.abs(np.array([float(r[1]) for r in rows]) - g["learn_metric"])) <= 6e-5
+    _info, trees, _w = modelxml.read_model(model)
+    assert len(trees) == c["trees"]
+    for t, a in enumerate(trees):
+        assert np.array_equal(a["feature"], g["learn_tree%d_feature" % t])
+        assert np.array_equal(a["left"], g["learn_tree%d_left" % t]) and np.array_equal(a["right"], g["learn_tree%d_right" % t])
+        b = dict(feature=g["learn_tree%d_feature" % t], threshold=g["learn_tree%d_threshold" % t],
+                 left=g["learn_tree%d_left" % t], right=g["learn_tree%d_right" % t])
+        if not np.array_equal(a["threshold"], b["threshold"]):
+            assert np.array_equal(_leaf_of(a, x), _leaf_of(b, x))
+        lv = a["feature"] < 0
+        assert np.allclose(a["value"][lv], g["learn_tree%d_value" % t][lv], rtol=1e-9, atol=1e-14)
