@@ -99,6 +99,9 @@ def lib():
         L.qref_radix_argsort.argtypes = [fp, u64, C.POINTER(u64)]
         L.qref_linesearch.argtypes = [fp, u64, u64, fp, C.POINTER(u64), u64, u64, C.c_uint32, C.c_double, C.c_double,
                                       C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, dp, dp]
+        L.qref_linesearch_valid.argtypes = [fp, u64, u64, fp, C.POINTER(u64), u64, fp, u64, fp, C.POINTER(u64), u64, u64,
+                                            C.c_uint32, C.c_double, C.c_double, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32,
+                                            dp, dp]
         L.qref_cleaver.argtypes = [C.c_int, fp, u64, u64, fp, C.POINTER(u64), u64, u64, C.c_double, dp, C.c_uint32,
                                    C.c_double, C.c_double, C.c_uint32, dp]
         L.qref_log.restype = u64
@@ -328,9 +331,9 @@ def radix_argsort(v):
 
 
 def linesearch(x, labels, qoff, cutoff=10, num_points=20, window_size=1.0, reduction_factor=0.95, max_iterations=5,
-               max_failed_vali=20, adaptive=False, last_only=0, init_weights=None):
-    """The reference's LineSearch::learn (line_search.cc:153-416) on a row-major matrix, NDCG@cutoff, no validation
-    set; returns the learned weights."""
+               max_failed_vali=20, adaptive=False, last_only=0, init_weights=None, valid=None):
+    """The reference's LineSearch::learn (line_search.cc:153-416) on a row-major matrix, NDCG@cutoff; valid = (x, labels,
+    query offsets) of a validation set (not larger than the training set) or None; returns the learned weights."""
     x = np.ascontiguousarray(x, np.float32)
     labels = np.ascontiguousarray(labels, np.float32)
     qoff = np.ascontiguousarray(qoff, np.uint64)
@@ -339,6 +342,17 @@ def linesearch(x, labels, qoff, cutoff=10, num_points=20, window_size=1.0, reduc
     if init_weights is not None:
         init_weights = np.ascontiguousarray(init_weights, np.float64)
         iw = _p(init_weights, C.c_double)
+    if valid is not None:
+        xv = np.ascontiguousarray(valid[0], np.float32)
+        lv = np.ascontiguousarray(valid[1], np.float32)
+        ov = np.ascontiguousarray(valid[2], np.uint64)
+        rc = lib().qref_linesearch_valid(_p(x, C.c_float), x.shape[0], x.shape[1], _p(labels, C.c_float), _p(qoff, C.c_uint64),
+                                         len(qoff) - 1, _p(xv, C.c_float), xv.shape[0], _p(lv, C.c_float), _p(ov, C.c_uint64),
+                                         len(ov) - 1, cutoff, num_points, window_size, reduction_factor, max_iterations,
+                                         max_failed_vali, int(adaptive), last_only, iw, _p(out, C.c_double))
+        if rc:
+            raise RuntimeError("reference line search (with validation) failed: %d" % rc)
+        return out
     rc = lib().qref_linesearch(_p(x, C.c_float), x.shape[0], x.shape[1], _p(labels, C.c_float), _p(qoff, C.c_uint64),
                                len(qoff) - 1, cutoff, num_points, window_size, reduction_factor, max_iterations,
                                max_failed_vali, int(adaptive), last_only, iw, _p(out, C.c_double))

@@ -639,6 +639,43 @@ int qref_linesearch(const float *x, uint64_t N, uint64_t T, const float *labels,
   return 0;
 }
 
+// The same with a validation set (line_search.cc:360-383: the weights kept are those of the best validation
+// iteration, `max_failed_vali` iterations without a new best stop the search).  The validation set must not hold more
+// documents than the training set: the reference sizes its validation score buffer by the TRAINING set (:209-210).
+int qref_linesearch_valid(const float *x, uint64_t N, uint64_t T, const float *labels, const uint64_t *qoff, uint64_t Q,
+                          const float *xv, uint64_t Nv, const float *labelsv, const uint64_t *qoffv, uint64_t Qv,
+                          uint64_t cutoff, uint32_t num_points, double window_size, double reduction_factor,
+                          uint32_t max_iterations, uint32_t max_failed_vali, int adaptive, uint32_t last_only,
+                          const double *init_weights, double *out_weights) {
+  if (Nv > N) return 3;
+  auto fill = [&](const float *m, uint64_t n, const float *lab, const uint64_t *off, uint64_t q) {
+    auto ds = std::make_shared<data::Dataset>(n, T);
+    std::vector<Feature> row(T);
+    for (uint64_t k = 0; k < q; ++k)
+      for (uint64_t i = off[k]; i < off[k + 1]; ++i) {
+        row.assign(m + i * T, m + (i + 1) * T);
+        ds->addInstance((QueryID) (k + 1), lab[i], row);
+      }
+    return ds;
+  };
+  auto ds = fill(x, N, labels, qoff, Q), dv = fill(xv, Nv, labelsv, qoffv, Qv);
+  auto metric = std::make_shared<metric::ir::Ndcg>(cutoff);
+  learning::linear::LineSearch ls(num_points, window_size, reduction_factor, max_iterations, max_failed_vali,
+                                  adaptive != 0, last_only);
+  if (init_weights) {
+    std::vector<double> w(init_weights, init_weights + T);
+    ls.update_weights(w);
+  }
+  {
+    Silence sil(true);
+    ls.learn(ds, dv, metric, 0, std::string());
+  }
+  const std::vector<double> w = ls.get_weights();
+  if (w.size() != T) return 1;
+  for (uint64_t f = 0; f < T; ++f) out_weights[f] = w[f];
+  return 0;
+}
+
 // Cleaver::optimize (src/optimization/post_learning/cleaver/cleaver.cc:166-412) with one of the deterministic pruning
 // strategies on a partial-score matrix, starting from `weights`; line search before / after pruning as the strategy
 // asks (num_points == 0: no line search).  method: 0 LAST, 1 SKIP, 2 LOW_WEIGHTS, 3 QUALITY_LOSS, 4 QUALITY_LOSS_ADV,

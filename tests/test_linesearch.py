@@ -122,3 +122,24 @@ def test_cleaver_random_pruning_is_seeded():
     # last_only: only the last trees are candidates
     d = Cleaver(3, "RANDOM", None, last_only=6, seed=1).optimize(part, l, off, w0)
     assert len(d[1]) == 3 and min(d[1]) >= 9
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyref.available(), reason="oracle/_ref is not built")
+@pytest.mark.parametrize("cfg", [
+    dict(num_points=8, max_iterations=6),
+    dict(num_points=10, max_iterations=8, max_failed_vali=2, window_size=2.0),
+    dict(num_points=12, max_iterations=5, adaptive=True, max_failed_vali=3),
+])
+def test_line_search_with_a_validation_set(cfg):
+    """line_search.cc:360-383: the weights returned are those of the best iteration ON THE VALIDATION SET, and
+    `max_failed_vali` iterations in a row without a new validation best end the search — same weights as the
+    unmodified reference, bit for bit."""
+    x, l, off = _features(n=3000, f=8, q=30, seed=3)
+    xv, lv, offv = _features(n=2000, f=8, q=20, seed=4)
+    want = pyref.linesearch(x, l, off, cutoff=10, valid=(xv, lv, offv), **cfg)
+    ls = LineSearch(**cfg)
+    with api.LineSearchDevice(x, l, off, cutoff=10) as dev, api.LineSearchDevice(xv, lv, offv, cutoff=10) as vdev:
+        got = ls.learn(dev, vdev)
+    assert np.array_equal(got, want), (got, want)
+    assert all(h[2] is not None for h in ls.history)
