@@ -77,6 +77,35 @@ def test_sample_selection_on_many_queries(negative):
     assert int(vals[0]) == want_n and np.array_equal(vals[1:], want_ids)
 
 
+@needs_ref
+@pytest.mark.parametrize("negative", ["RATIO", "MUL", "POS"])
+def test_sample_selection_edge_cases(negative):
+    """Queries of one document, without positives, without negatives, with tied scores throughout, and a dataset of a
+    single query: the same draw as the reference's."""
+    cases = []
+    rng = np.random.default_rng(31)
+    lens = np.array([1, 1, 2, 7, 30, 1, 12, 3])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    labels = np.zeros(int(off[-1]), np.float32)
+    labels[0] = 2                       # a one-document query holding a positive
+    labels[int(off[3]):int(off[4])] = 1  # a query of positives only
+    labels[int(off[4]) + 3] = 3          # one positive among 30
+    labels[int(off[6]):int(off[6]) + 6] = rng.integers(1, 4, size=6)
+    cases.append((labels, np.zeros(len(labels)), off))                        # every score tied
+    cases.append((labels, np.round(rng.normal(size=len(labels)), 1), off))
+    one = rng.choice([0, 0, 1, 2], size=40).astype(np.float32)
+    cases.append((one, rng.normal(size=40), np.array([0, 40], np.uint64)))     # a single query
+    for labels, scores, off in cases:
+        inp = "%d %d\n%s\n%s\n" % (len(off) - 1, len(labels), " ".join(str(int(o)) for o in off),
+                                   "\n".join("%d %.17g" % (a, b) for a, b in zip(labels, scores)))
+        for rank, rnd in ((0.5, 0.5), (0.2, 0.0), (0.0, 0.4)):
+            out = subprocess.run([CHECK, repr(rank), repr(rnd), "NO", negative, "1.0"], input=inp, capture_output=True, text=True)
+            assert out.returncode == 0, out.stderr
+            vals = np.array(out.stdout.split(), dtype=np.uint64)
+            want_n, want_ids = pyref.selective_sample(labels, scores, off, rank, rnd, "NO", negative, 1.0)
+            assert int(vals[0]) == want_n and np.array_equal(vals[1:], want_ids), (rank, rnd)
+
+
 def test_selective_rejects_what_the_reference_dies_on(tmp_path):
     """--sampling-iterations 0 with a sampling factor set is a division by zero in the reference
     (lambdamartselective.cc:170-171); here it is an error message — checked before any device work."""
