@@ -460,3 +460,38 @@ def test_sample_context_against_the_golden_vectors(tmp_path):
             assert np.array_equal(_leaf_of(a, x), _leaf_of(b, x))
         lv = a["feature"] < 0
         assert np.allclose(a["value"][lv], g["learn_tree%d_value" % t][lv], rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.gpu
+def test_sample_context_edge_cases_against_the_oracle():
+    """Samples that leave one document per query, keep a single query, or consist of one-document queries: pseudo-
+    responses equal the oracle's masked restatement (itself bit-identical to the reference), and a tree can be fitted."""
+    from oracle import pyoracle as po
+    from quickrank_b200 import api
+    x, l, off = common.dataset(n=2400, f=8, q=24, seed=14, qlen=(1, 200))
+    rng = np.random.default_rng(2)
+    scores = common.tie_heavy_scores(len(l), rng) + np.where(rng.random(len(l)) < 0.3, rng.normal(size=len(l)), 0.0)
+    q_of = np.searchsorted(off, np.arange(len(l)), side="right") - 1
+    masks = {
+        "one document per query": np.isin(np.arange(len(l)), off[:-1].astype(np.int64) + (np.diff(off).astype(np.int64) // 2)),
+        "a single query": q_of == 5,
+        "two documents of every third query": (q_of % 3 == 0) & (np.arange(len(l)) - off[q_of].astype(np.int64) < 2),
+        "everything but the first document of each query": ~np.isin(np.arange(len(l)), off[:-1].astype(np.int64)),
+    }
+    with api.Trainer(x, l, off, nleaves=4, minleafsupport=1) as full:
+        full.set_scores(scores)
+        sm = None
+        for name, mask in masks.items():
+            ids = np.nonzero(mask)[0]
+            want_lam, want_w = po.lambdas_masked(scores, l, off, 10, mask.astype(np.uint8))
+            if sm is None:
+                sm = full.sample_context(x, ids)
+            else:
+                sm.redraw(full, ids)
+            sm.pull_scores(full)
+            sm.compute_pseudoresponses()
+            lam, w = sm.get_pseudoresponses()
+            assert np.array_equal(lam, want_lam[ids]) and np.array_equal(w, want_w[ids]), name
+            tree = sm.fit_regressor_on_gradient()
+            assert int(tree["count"][0]) == len(ids), name
+        sm.close()
