@@ -35,6 +35,12 @@ METRIC = "lambdamart_trees_per_sec"
 UNIT = "trees/s"
 
 
+def workload_string(w):
+    """config.workload, the same string in both arms (ours and --impl reference)"""
+    return ("LambdaMART 64 leaves, synthetic %d docs x %d feat x %d queries, NDCG@10, 256-level features (u8 bins), "
+            "shrinkage 0.1 (BASELINE.json configs[1])" % (w["n_docs"], w["n_features"], w["n_queries"]))
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -459,9 +465,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "LambdaMART 64 leaves, synthetic %d docs x %d feat x %d queries, "
-                                   "NDCG@10, 256-level features (u8 bins), shrinkage 0.1 (BASELINE.json configs[1])"
-                                   % (w["n_docs"], w["n_features"], w["n_queries"]),
+            "config": {"workload": workload_string(w),
                        "docs_per_gpu": int(len(labels)), "global_docs": w["n_docs"],
                        "hist_mode": "fixed-point int64 (FAST)", "parallelism": "query-sharded dp%d" % world,
                        "histogram_exchange": exchange,
@@ -686,7 +690,7 @@ def run_reference(args):
     w = WORKLOAD
     from quickrank_b200 import synth
     x, labels, qoff = synth.make_dataset(w["n_docs"], w["n_features"], w["n_queries"], seed=w["seed"])
-    warm = min(max(args.warmup, 1), 3)
+    warm = min(max(args.warmup, 1), 10)   # (a reference iteration costs ~0.3 s on 16 cores)
     steps = min(args.steps, 20)
     sec_per_tree, init_s, kind, nthreads = reference_steps(x, labels, qoff, warm, steps)
     value = 1.0 / sec_per_tree
@@ -696,8 +700,7 @@ def run_reference(args):
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": steps, "warmup": warm,
         "ms_per_step": round(sec_per_tree * 1e3, 3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "LambdaMART 64 leaves, synthetic %d docs x %d feat x %d queries, NDCG@10 "
-                               "(BASELINE.json configs[1]) on the host CPU" % (w["n_docs"], w["n_features"], w["n_queries"])},
+        "config": {"workload": workload_string(w), "where": "host CPU (the reference's OpenMP path), full workload"},
         "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": nthreads, "omp_max_threads": nthreads,
                          "kind": kind, "build": REF_BUILD if kind == "reference" else "oracle/qr_oracle.c (restatement)",
                          "sample": "full workload, %d timed iterations (capped at 20), init %.1f s excluded" % (steps, init_s)},
