@@ -479,6 +479,8 @@ class LambdaMartSelective : public SampledLambdaMart {
   // LambdaMartSelective::sampling_query_level (lambdamartselective.cc:326-493), public for host/selective_check.cc
   size_t sampling_query_level(const data::Dataset &dataset, const std::vector<Score> &scores,
                               const std::vector<size_t> &npositives, std::vector<size_t> &ids, float adapt_factor);
+  // rand() calls the draws of this process have made so far (a later draw continues the same stream)
+  static size_t rand_calls();
 
  protected:
   bool sampling_enabled() const override { return rank_sampling_factor > 0 || random_sampling_factor > 0; }

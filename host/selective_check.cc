@@ -1,7 +1,9 @@
 // Development / test tool: one draw of LambdaMartSelective::sampling_query_level on the host, no GPU involved.
-//   selective_check <rank_factor> <random_factor> <adaptive> <negative> <adapt_factor> < input
+//   selective_check <rank_factor> <random_factor> <adaptive> <negative> <adapt_factor> [rand_calls_to_skip] < input
 // input (text): Q N, then Q+1 query offsets, then N lines "label score".  srand(0) before the draw.
-// output: the size of the sample, then the N ids of the permuted list.  tests/test_sampled_trainers.py compares it
+// rand_calls_to_skip: rand() calls earlier draws of the same training run have consumed since srand(0).
+// output: the size of the sample, then the N ids of the permuted list; stderr: the draw's log, its duration and the
+// number of rand() calls it made.  tests/test_sampled_trainers.py compares it
 // with the unmodified reference's function on the same input.
 #include <chrono>
 #include <cstdlib>
@@ -34,11 +36,13 @@ int main(int argc, char **argv) {
   std::ostringstream log;
   std::streambuf *keep = std::cout.rdbuf(log.rdbuf());
   srand(0);
+  for (long k = argc > 6 ? atol(argv[6]) : 0; k > 0; --k) (void) rand();
   const auto t0 = std::chrono::steady_clock::now();
   const size_t n = algo.sampling_query_level(ds, scores, npos, ids, strtof(argv[5], nullptr));
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   std::cout.rdbuf(keep);
   std::cerr << "draw over " << N << " documents: " << ms << " ms" << std::endl;
+  std::cerr << "rand calls: " << learning::forests::LambdaMartSelective::rand_calls() << std::endl;
   std::cout << n << "\n";
   for (size_t i = 0; i < N; ++i) std::cout << ids[i] << "\n";
   std::cerr << log.str();

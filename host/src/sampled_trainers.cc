@@ -286,8 +286,10 @@ namespace {
 
 // std::random_shuffle(first, last) of libstdc++ (bits/stl_algo.h): element i trades places with one of
 // 0..i drawn with rand() % (i + 1)
+size_t g_rand_calls = 0;   // rand() calls made by the draws of this process (host/selective_check.cc reports it)
 template <typename T>
 void rand_shuffle(std::vector<T> &v) {
+  g_rand_calls += v.size() > 1 ? v.size() - 1 : 0;
   for (size_t i = 1; i < v.size(); ++i) {
     const size_t j = (size_t) (std::rand() % (long) (i + 1));
     if (i != j) std::swap(v[i], v[j]);
@@ -298,6 +300,8 @@ void rand_shuffle(std::vector<T> &v) {
 inline size_t quota(float factor, size_t count) { return (size_t) std::round(factor * count); }
 
 }  // namespace
+
+size_t LambdaMartSelective::rand_calls() { return g_rand_calls; }
 
 // One draw (lambdamartselective.cc:326-493).  Per query: the positives, the `n_top` negatives the model scores
 // highest and `n_random` of the remaining ones; the selected ids of all queries end up contiguous at the front of

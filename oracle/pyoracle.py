@@ -66,6 +66,8 @@ def lib():
         L.qro_bins_free.argtypes = [C.POINTER(Bins)]
         L.qro_fit_tree.restype = C.POINTER(Tree)
         L.qro_fit_tree.argtypes = [C.POINTER(Bins), dp, dp, sz, sz, sz, u32p]
+        L.qro_fit_tree_sampled.restype = C.POINTER(Tree)
+        L.qro_fit_tree_sampled.argtypes = [C.POINTER(Bins), dp, dp, u64p, sz, sz, sz, sz, u32p]
         L.qro_tree_free.argtypes = [C.POINTER(Tree)]
         L.qro_split_scores.argtypes = [C.POINTER(Bins), dp, u64p, sz, sz, u32p, u32p, sz, dp]
         L.qro_update_scores.argtypes = [C.POINTER(Tree), fp, sz, C.c_double, dp]
@@ -196,15 +198,21 @@ class Binning:
         b = self.h.contents
         return np.ctypeslib.as_array(b.bins, shape=(self.F, self.N)).copy()
 
-    def fit_tree(self, lam, w=None, nleaves=10, minls=1, depth=0):
+    def fit_tree(self, lam, w=None, nleaves=10, minls=1, depth=0, sampleids=None):
+        """sampleids: fit on these documents only, in this order (the document-sampling trainers)"""
         lam = np.ascontiguousarray(lam, np.float64)
         wp = None
         if w is not None:
             w = np.ascontiguousarray(w, np.float64)
             wp = _p(w, C.c_double)
         leaf = np.zeros(self.N, np.uint32)
-        tp = lib().qro_fit_tree(self.h, _p(lam, C.c_double), wp, nleaves, minls, depth,
-                                _p(leaf, C.c_uint32))
+        if sampleids is not None:
+            ids = np.ascontiguousarray(sampleids, np.uint64)
+            tp = lib().qro_fit_tree_sampled(self.h, _p(lam, C.c_double), wp, _p(ids, C.c_uint64), len(ids), nleaves, minls,
+                                            depth, _p(leaf, C.c_uint32))
+        else:
+            tp = lib().qro_fit_tree(self.h, _p(lam, C.c_double), wp, nleaves, minls, depth,
+                                    _p(leaf, C.c_uint32))
         d = tree_to_dict(tp)
         lib().qro_tree_free(tp)
         d["leaf_of_doc"] = leaf
@@ -248,6 +256,39 @@ def score_dataset(trees, weights, rowmajor):
     lib().qro_score_dataset(arr, _p(w, C.c_double), len(cts), _p(x, C.c_float), x.shape[0],
                             x.shape[1], _p(out, C.c_double))
     return out
+
+
+def train_sampled(rowmajor, labels, qoff, ntrees, draw, resample_due, shrinkage=0.1, nthresholds=0, nleaves=10, minls=1,
+                  cutoff=10):
+    """LambdaMART on a redrawn document sample — the loop of LambdaMartSelective::learn / StochasticNegative::learn
+    (lambdamartselective.cc:163-215) restated over the oracle's pieces, in the reference's arithmetic and ORDER (root
+    histogram and leaf sums run over `sampleids` as drawn).  draw(scores) -> (n, ids): a permutation of the documents
+    with the sample in front (the reference's sampling_query_level; the tests pass the host's draw); resample_due(m):
+    is a new sample drawn before iteration m.  Returns (trees, metric per iteration, scores, sample sizes)."""
+    x = np.ascontiguousarray(rowmajor, np.float32)
+    col = np.ascontiguousarray(x.T)
+    labels = np.ascontiguousarray(labels, np.float32)
+    qoff = np.ascontiguousarray(qoff, np.uint64)
+    N = x.shape[0]
+    bins = Binning(col, nthresholds)
+    scores = np.zeros(N, np.float64)
+    ids, n = np.arange(N, dtype=np.uint64), N
+    presence = np.ones(N, np.uint8)
+    trees, metric, sizes = [], [], []
+    for m in range(ntrees):
+        if m > 0 and resample_due(m):
+            n, ids = draw(scores)
+            sizes.append(n)
+            if n < N:                                   # lambdamartselective.cc:188-192
+                presence[:] = 0
+                presence[ids[:n]] = 1
+        lam, w = lambdas_masked(scores, labels, qoff, cutoff, presence)
+        tree = bins.fit_tree(lam, w, nleaves=nleaves, minls=minls, sampleids=ids[:n])
+        scores = update_scores(tree, col, shrinkage, scores)
+        trees.append(tree)
+        metric.append(ndcg_dataset(labels, scores, qoff, cutoff))
+    bins.close()
+    return trees, np.array(metric), scores, sizes
 
 
 def train(algo, rowmajor, labels, qoff, ntrees, shrinkage=0.1, nthresholds=0, nleaves=10, depth=0,

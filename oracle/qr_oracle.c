@@ -680,11 +680,30 @@ static void fit_leaves(node_t *nd, const double *lab, const double *w, uint32_t 
     for (size_t j = 0; j < nd->n; ++j) leaf_of_doc[nd->ids[j]] = li;
 }
 
+static qro_tree *fit_tree_on(const qro_bins *b, const double *lab, const double *w, size_t *ids, size_t N,
+                             size_t nleaves, size_t minls, size_t depth, uint32_t *leaf_of_doc);
+
 qro_tree *qro_fit_tree(const qro_bins *b, const double *lab, const double *w, size_t nleaves,
                        size_t minls, size_t depth, uint32_t *leaf_of_doc) {
   const size_t N = b->N;
   size_t *ids = (size_t *) malloc((N ? N : 1) * sizeof(size_t));
   for (size_t i = 0; i < N; ++i) ids[i] = i;
+  return fit_tree_on(b, lab, w, ids, N, nleaves, minls, depth, leaf_of_doc);
+}
+
+/* The document-sampling trainers (lambdamartselective.cc:199-206, stochasticnegative.cc:201-205): the root histogram
+ * is refreshed over sampleids[0 .. nsampleids) in that order (RTNodeHistogram::update(labels, nsampleids, sampleids),
+ * rtnode_histogram.cc:172-204) and the tree is grown and its leaf outputs fitted on those documents only.
+ * leaf_of_doc is written for the sampled documents. */
+qro_tree *qro_fit_tree_sampled(const qro_bins *b, const double *lab, const double *w, const uint64_t *sampleids,
+                               size_t nsampleids, size_t nleaves, size_t minls, size_t depth, uint32_t *leaf_of_doc) {
+  size_t *ids = (size_t *) malloc((nsampleids ? nsampleids : 1) * sizeof(size_t));
+  for (size_t i = 0; i < nsampleids; ++i) ids[i] = (size_t) sampleids[i];
+  return fit_tree_on(b, lab, w, ids, nsampleids, nleaves, minls, depth, leaf_of_doc);
+}
+
+static qro_tree *fit_tree_on(const qro_bins *b, const double *lab, const double *w, size_t *ids, size_t N,
+                             size_t nleaves, size_t minls, size_t depth, uint32_t *leaf_of_doc) {
   hist_t *root_hist = hist_from_samples(b, ids, N, lab, 1); /* mart.cc:335 */
   node_t *root = node_new(b, ids, root_hist);
 

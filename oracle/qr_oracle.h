@@ -80,6 +80,9 @@ void qro_bins_free(qro_bins *b);
  *     leaf_of_doc (optional, [N]) receives the DFS leaf index of every document. */
 qro_tree *qro_fit_tree(const qro_bins *b, const double *lambdas, const double *weights,
                        size_t nleaves, size_t minls, size_t depth, uint32_t *leaf_of_doc);
+/* the same on sampleids[0 .. nsampleids) only, in that order (the document-sampling trainers) */
+qro_tree *qro_fit_tree_sampled(const qro_bins *b, const double *lambdas, const double *weights, const uint64_t *sampleids,
+                               size_t nsampleids, size_t nleaves, size_t minls, size_t depth, uint32_t *leaf_of_doc);
 void qro_tree_free(qro_tree *t);
 
 /* Tie audit: the reference's split score lsum^2/lcnt + rsum^2/rcnt (rt.cc:272-283) of `ncand`

@@ -495,3 +495,68 @@ def test_sample_context_edge_cases_against_the_oracle():
             tree = sm.fit_regressor_on_gradient()
             assert int(tree["count"][0]) == len(ids), name
         sm.close()
+
+
+def test_cpu_replay_of_a_selective_run_is_bit_identical_to_the_reference():
+    """CPU only: the oracle's pieces (masked pseudo-responses, tree fit over `sampleids` in the reference's order, score
+    update, NDCG) driven by the HOST's draw (host/bin/selective_check, the product's sampling code, continuing one
+    rand() stream across draws) replay the golden LambdaMartSelective::learn run of tests/golden/sampled.npz bit for
+    bit: every tree (structure, thresholds, leaf outputs), every iteration's NDCG, every sample size."""
+    from oracle import pyoracle as po
+    from quickrank_b200 import synth
+    g = np.load(GOLDEN)
+    c = eval(str(g["learn_case"]))
+    sel = c["selective"]
+    x, l, off = synth.make_dataset(c["n"], c["f"], c["q"], seed=c["seed"])
+    state = {"rand_calls": 0}
+
+    def draw(scores):
+        inp = "%d %d\n%s\n%s\n" % (len(off) - 1, len(l), " ".join(str(int(o)) for o in off),
+                                   "\n".join("%d %.17g" % (a, b) for a, b in zip(l, scores)))
+        out = subprocess.run([CHECK, repr(sel["rank_factor"]), repr(sel["random_factor"]), "NO", "RATIO", "1.0",
+                              str(state["rand_calls"])], input=inp, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        state["rand_calls"] += int(re.search(r"rand calls: (\d+)", out.stderr).group(1))
+        vals = np.array(out.stdout.split(), dtype=np.uint64)
+        return int(vals[0]), vals[1:]
+
+    trees, metric, _scores, sizes = po.train_sampled(x, l, off, c["trees"], draw, lambda m: m % sel["sampling_iterations"] == 0,
+                                                     nleaves=c["leaves"], minls=c["minls"], cutoff=c["cutoff"])
+    want_sizes = [int(v) for v in re.findall(r"^Reducing training size from \d+ to (\d+)", str(g["learn_log"]), flags=re.M)]
+    assert sizes == want_sizes and len(sizes) >= 2 and state["rand_calls"] > 0
+    assert np.array_equal(metric, g["learn_metric"])
+    for t, tree in enumerate(trees):
+        for k in ("feature", "threshold_idx", "threshold", "left", "right", "value", "count"):
+            assert np.array_equal(tree[k], g["learn_tree%d_%s" % (t, k)]), (t, k)
+
+
+@needs_ref
+@pytest.mark.parametrize("negative,rank,rnd,every", [("POS", 0.5, 0.3, 2), ("MUL", 1.5, 0.5, 2), ("RATIO", 0.2, 0.0, 3)])
+def test_cpu_replay_against_the_live_reference(negative, rank, rnd, every):
+    """The same CPU replay (oracle pieces + the host's draw) against LambdaMartSelective::learn run here, for the other
+    negative strategies: trees and NDCG trajectory bit for bit."""
+    from oracle import pyoracle as po
+    x, l, off = common.dataset(n=2000, f=8, q=20, seed=17)
+    ntrees = 7
+    sel = dict(sampling_iterations=every, rank_factor=rank, random_factor=rnd, negative=negative)
+    with pyref.RefSession("LAMBDAMART-SELECTIVE", x, l, off, ntrees=ntrees, nleaves=6, minleafsupport=3, selective=sel) as s:
+        s.learn()
+        want_metric = s.metric_history()
+        want_trees = [s.tree(t) for t in range(s.num_trees())]
+    state = {"rand_calls": 0}
+
+    def draw(scores):
+        inp = "%d %d\n%s\n%s\n" % (len(off) - 1, len(l), " ".join(str(int(o)) for o in off),
+                                   "\n".join("%d %.17g" % (a, b) for a, b in zip(l, scores)))
+        out = subprocess.run([CHECK, repr(rank), repr(rnd), "NO", negative, "1.0", str(state["rand_calls"])], input=inp,
+                             capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        state["rand_calls"] += int(re.search(r"rand calls: (\d+)", out.stderr).group(1))
+        vals = np.array(out.stdout.split(), dtype=np.uint64)
+        return int(vals[0]), vals[1:]
+
+    trees, metric, _scores, _sizes = po.train_sampled(x, l, off, ntrees, draw, lambda m: m % every == 0, nleaves=6, minls=3)
+    assert np.array_equal(metric, want_metric)
+    for t, tree in enumerate(trees):
+        for k in ("feature", "threshold_idx", "threshold", "left", "right", "value", "count"):
+            assert np.array_equal(tree[k], want_trees[t][k]), (t, k)
