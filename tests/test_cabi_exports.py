@@ -30,7 +30,9 @@ def test_every_declared_symbol_is_exported():
 def test_header_cites_the_reference_interfaces():
     src = open(HEADER).read()
     for cite in ("mart.cc:117-176", "lambdamart.cc:62-152", "mart.cc:459-468", "ltr_algorithm.cc:44-52",
-                 "rtnode_histogram.cc", "metric.h:93-106", "ranker.cc:23-25", "dart.cc:634-687"):
+                 "rtnode_histogram.cc", "metric.h:93-106", "ranker.cc:23-25", "dart.cc:634-687",
+                 "lambdamartselective.cc:185-206", "lambdamart.cc:84-105", "line_search.cc:252-281",
+                 "quality_loss_adv_pruning.cc:88-92", "score_loss_pruning.cc:58-63"):
         assert cite in src, cite
 
 
