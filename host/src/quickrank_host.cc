@@ -9,6 +9,7 @@
 // anything.  It is derived work of that code and is to be read under the same licence; no arithmetic on the hot path
 // lives here (every pass over documents is a call into the C ABI), and it is not meant to grow.
 #include "quickrank_host.h"
+#include "qr_fast_float.h"
 
 #include <algorithm>
 #include <chrono>
@@ -219,10 +220,11 @@ void parse_svml_range(char *p, char *end, SvmlChunk &out) {
     for (;;) {
       while (*q == ' ' || *q == '\t' || *q == '\r') ++q;
       if (*q == '\0') break;
-      const size_t fid = (size_t) strtoull(q, &e, 10);
+      size_t fid = 0;
+      for (e = q; *e >= '0' && *e <= '9' && e - q < 18; ++e) fid = fid * 10 + (size_t) (*e - '0');
       if (e == q || *e != ':') { out.error = 4; return; }
       q = e + 1;
-      const Feature v = strtof(q, &e);
+      const Feature v = host::parse_float(q, &e);   // = strtof(q, &e), bit for bit (host/include/qr_fast_float.h)
       if (e == q || fid == 0) { out.error = 4; return; }
       q = e;
       out.fids.push_back((uint32_t) fid);

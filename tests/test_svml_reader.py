@@ -122,3 +122,13 @@ def test_host_reader_equals_the_reference_reader(tmp_path):
     got = run(path, 5)
     assert [int(v) for v in got[:3]] == list(shape)
     assert tuple(int(v, 16) for v in got[3:6]) == sums
+
+
+def test_fast_float_parse_equals_strtof():
+    """host/include/qr_fast_float.h (the reader's decimal -> float fast path) against strtof on 2 million random and
+    adversarial strings — exact float rounding boundaries and their neighbours, long digit strings, exponents,
+    range limits, specials: same bits, same end pointer."""
+    tool = os.path.join(ROOT, "host", "bin", "float_check")
+    assert os.path.exists(tool), "build host/ first"
+    out = subprocess.run([tool, "2", "7"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith(" 0 mismatches"), out.stdout + out.stderr
